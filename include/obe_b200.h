@@ -1,0 +1,179 @@
+/* obe_b200.h -- C ABI of libobe_b200.so: the B200 (sm_100a) particle-filter inference and
+ * setting-selection path of usnistgov/optbayesexpt v1.2.0.
+ *
+ * The reference is pure Python/numpy and has NO FFI of its own: its boundary is the method
+ * surface of ParticlePDF / OptBayesExpt / OptBayesExptNoiseParameter.  Each entry point below
+ * names the reference method (file:line under /root/reference/optbayesexpt) whose arithmetic
+ * it replaces; optbayesexpt_b200/*.py re-creates those classes on top of this ABI via ctypes
+ * (INTEGRATION.md shows the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only.  Pointers named *_dev are DEVICE pointers owned by the
+ *     caller (e.g. torch tensors' data_ptr()); everything else is host memory.
+ *   - all floating point is IEEE fp64, all indices int64; particles are SoA (d, ld).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) unless noted;
+ *     the library never allocates device memory behind the caller: scratch comes from the
+ *     obe_cloud_t arrays, sized with the obe_*_len() queries.
+ *   - return 0 on success, <0 on error; obe_last_error() gives the thread-local message.
+ *   - there is no CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef OBE_B200_H
+#define OBE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OBE_ABI_VERSION 1
+#define OBE_TILE_SIZE 2048      /* canonical tile: CDF association, tile_sums granularity   */
+#define OBE_STATS_DOUBLES 64    /* length of the device stats block                         */
+#define OBE_MAX_PARAMS 8
+#define OBE_MAX_CHANNELS 4
+#define OBE_MAX_SETTINGS 4
+#define OBE_MAX_CONSTANTS 8
+
+/* stats block layout (doubles), written by obe_update / obe_refresh / obe_tile_scan */
+enum {
+    OBE_STAT_TOTAL = 0,   /* canonical sum of the un-normalised weights (CDF total)          */
+    OBE_STAT_INVS = 1,    /* weights_normalised = weights * stats[INVS]                      */
+    OBE_STAT_SUMSQ = 2,   /* sum t^2                                                         */
+    OBE_STAT_NEFF = 3,    /* 1/sum(w^2) of particlepdf.py:243-244                            */
+    OBE_STAT_M1 = 4,      /* [8]  sum t (x_j - pivot_j)                                      */
+    OBE_STAT_M2 = 12,     /* [d(d+1)/2] sum t (x_j-p_j)(x_k-p_k), j<=k packed row-major      */
+    OBE_STAT_PIVOT = 48,  /* [8]                                                             */
+    OBE_STAT_NOISE = 56,  /* [4]  sum t sigma_c^2                                            */
+    OBE_STAT_SUMT = 60,   /* sum t from the same pass as the moments                         */
+    OBE_STAT_NZERO = 61   /* particles newly zeroed by the constraint mask                   */
+};
+
+/* The particle cloud resident in HBM (ParticlePDF state, particlepdf.py:96-126). */
+typedef struct obe_cloud {
+    double* particles_dev;    /* (d, ld) row-major: one contiguous row per parameter        */
+    double* weights_dev;      /* (n) UN-normalised weights t; normalised = t * stats[INVS]  */
+    double* tile_sums_dev;    /* (obe_num_tiles(n))                                         */
+    double* tile_prefix_dev;  /* (obe_num_tiles(n) + 1) exclusive prefix; last = CDF total  */
+    double* stats_dev;        /* (OBE_STATS_DOUBLES)                                        */
+    void* scratch_dev;        /* obe_scratch_bytes(n) bytes, zero-initialised by the caller */
+    int64_t n;                /* particles                                                   */
+    int64_t ld;               /* row stride in doubles, even (16-byte aligned rows)          */
+    int32_t d;                /* parameters per particle (1..OBE_MAX_PARAMS)                 */
+    int32_t reserved;
+} obe_cloud_t;
+
+typedef struct obe_model* obe_model_t; /* opaque device functor for model_function */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int obe_abi_version(void);
+const char* obe_last_error(void);
+int obe_device_count(void);                 /* 0 without a usable CUDA device                */
+int64_t obe_num_tiles(int64_t n);
+size_t obe_scratch_bytes(int64_t n);        /* per-cloud scratch (partials, plans, counters) */
+size_t obe_select_scratch_bytes(int64_t n_settings);
+
+/* ---- model_function as a device functor (obe_base.py:50-66, 165, 215-222) ---------------- */
+/* names: lorentzian_hwhm, lorentzian_fwhm, lorentzian_4p, lorentzian_dip, line, rabi,
+ * lockin_coil.  n_params = d of the cloud (>= the model's own parameter count). */
+int obe_model_builtin(const char* name, int n_params, obe_model_t* out);
+/* User CUDA source compiled by NVRTC for sm_100a.  The source must define
+ *   __device__ void <entry>(const double* s, const double* p, const double* c, double* y)
+ * `log`/`log_len` receive the compiler log. */
+int obe_model_compile(const char* cuda_source, const char* entry, int n_settings, int n_params,
+                      int n_model_params, int n_constants, int n_channels, obe_model_t* out,
+                      char* log, size_t log_len);
+int obe_model_info(obe_model_t m, int* n_settings, int* n_model_params, int* n_constants,
+                   int* n_channels, int* n_params);
+void obe_model_free(obe_model_t m);
+
+/* ---- inference half --------------------------------------------------------------------- */
+/* ParticlePDF.__init__/set_pdf (particlepdf.py:121,163-171): weights <- 1/n, stats reset. */
+int obe_set_uniform(const obe_cloud_t* c, void* stream);
+
+/* OptBayesExpt.pdf_update without the resample (obe_base.py:381-394):
+ *   eval_over_all_parameters (obe_base.py:320) -> likelihood (obe_base.py:451-461 |
+ *   obe_noiseparam.py:110-120) -> _normalized_product (particlepdf.py:136-139), plus N_eff
+ *   (particlepdf.py:243-244) and the moments of mean/covariance/std (particlepdf.py:173-214),
+ *   all in one pass over the cloud.  sigma==NULL with noise_index!=NULL selects the
+ *   noise-parameter likelihood.  n_lik_channels = channels that enter the product (zip
+ *   truncation).  choke: pass use_choke=0 for choke=None.  pivot[d]: shift for the moment
+ *   accumulators (any point near the mean; the previous mean). */
+int obe_update(obe_model_t m, const obe_cloud_t* c, const double* setting, const double* constants,
+               const double* y_meas, const double* sigma, const int32_t* noise_index,
+               int n_lik_channels, int use_choke, double choke, const double* pivot, void* stream);
+/* pdf_update(record, y_model_data) (obe_base.py:374-385): model output supplied, (C, ld_y). */
+int obe_update_from_y(const obe_cloud_t* c, const double* y_model_dev, int64_t ld_y, int n_channels,
+                      const double* y_meas, const double* sigma, const int32_t* noise_index,
+                      int n_lik_channels, int use_choke, double choke, const double* pivot,
+                      void* stream);
+/* ParticlePDF.bayesian_update(likelihood) (particlepdf.py:216-231): likelihood supplied, (n). */
+int obe_update_from_likelihood(const obe_cloud_t* c, const double* likelihood_dev,
+                               const double* pivot, void* stream);
+/* Recompute tile sums, CDF prefix and moments from the current weights (after the caller wrote
+ * weights_dev directly: set_pdf(weights=...), `pdf.particle_weights = ...`), optionally
+ * applying enforce_parameter_constraints as data: bit j of mask_le zeroes weights where
+ * x_j <= 0 (obe_noiseparam.py:67-71), of mask_lt where x_j < 0 (lockin_of_coil.py:120-128).
+ * noise_index (may be NULL) selects the rows whose weighted mean square is accumulated
+ * (yvar_noise_model, obe_noiseparam.py:132-136). */
+int obe_refresh(const obe_cloud_t* c, uint32_t mask_le, uint32_t mask_lt, const int32_t* noise_index,
+                int n_noise, const double* pivot, int renormalise, void* stream);
+/* Copy the stats block to host memory (synchronises the stream). */
+int obe_fetch_stats(const obe_cloud_t* c, double* stats_host, void* stream);
+/* Normalised weights (t * INVS, nan_to_num) into out_dev (n). particle_weights getter. */
+int obe_normalized_weights(const obe_cloud_t* c, double* out_dev, void* stream);
+
+/* ---- weighted draws: Generator.choice(p=w) (particlepdf.py:330-331) ---------------------- */
+/* Canonical normalised CDF of the weights into cdf_dev (n). */
+int obe_cdf(const obe_cloud_t* c, double* cdf_dev, void* stream);
+/* idx[i] = #{k : cdf[k] <= u[i]} clamped to n-1  (searchsorted(cdf, u, 'right')). */
+int obe_search(const obe_cloud_t* c, const double* cdf_dev, const double* u_dev, int64_t m,
+               int64_t* idx_dev, void* stream);
+/* randdraw(K) (particlepdf.py:312-345) without materialising the CDF: K uniforms (host),
+ * draws_dev (d, K) row-major, idx_dev (K) optional. */
+int obe_draw(const obe_cloud_t* c, const double* u_host, int k, double* draws_dev, int64_t* idx_dev,
+             void* stream);
+
+/* ---- resample (particlepdf.py:260-310) --------------------------------------------------- */
+/* Gather + Liu-West jitter for given ancestors (reference-parity, multinomial mode):
+ *   out[:, i] = in[:, idx[i]] + z[i, :] @ factor ; optional a*out + (1-a)*mean ; w_out = 1/n.
+ * factor (d*d row-major) and mean (d) on the host; z_dev (n, d) particle-major standard
+ * normals, or NULL to generate them on device (Philox4x32-10, seed, epoch). */
+int obe_gather_jitter(const obe_cloud_t* in, const obe_cloud_t* out, const int64_t* idx_dev,
+                      const double* factor, const double* mean, const double* z_dev, uint64_t seed,
+                      uint32_t epoch, double a_param, int scale, void* stream);
+/* Fused systematic resample (fast path): comb u_i = (i + u0)/n searched in the canonical CDF,
+ * gather, jitter, weight reset, in one pass and with coalesced writes.  factor/mean NULL =>
+ * Cholesky factor of (1-a^2)*cov and the mean are taken from in->stats_dev on the device.
+ * idx_out_dev / z_out_dev (optional) receive the ancestors and the normals used. */
+int obe_resample_systematic(const obe_cloud_t* in, const obe_cloud_t* out, double u0,
+                            const double* factor, const double* mean, uint64_t seed, uint32_t epoch,
+                            double a_param, int scale, int64_t* idx_out_dev, double* z_out_dev,
+                            void* stream);
+
+/* ---- design half ------------------------------------------------------------------------ */
+/* utility_variance (obe_base.py:628-655) over the whole grid + argmax of opt_setting
+ * (obe_base.py:748).  draws_dev (d, K); settings_dev (s, lds); var_noise[C] host or NULL to use
+ * the noise-parameter accumulators of c_stats_dev (obe_noiseparam.py:132-136); cost_dev (S) or
+ * NULL (cost_estimate, obe_base.py:566-577); method 0 = variance, 1 = max-min
+ * (obe_base.py:602-626); log_form=1 gives log(1 + var/sigma^2).  utility_dev (S) out;
+ * best_dev: int64 index then double value (16 bytes). */
+int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* settings_dev,
+                int64_t lds, int64_t n_settings, const double* constants, const double* var_noise,
+                const double* stats_dev, const double* cost_dev, int method, int log_form,
+                double* utility_dev, void* best_dev, void* select_scratch_dev, void* stream);
+/* good_setting (obe_base.py:778-789): index drawn with p ~ nan_to_num(U**pickiness), given its
+ * uniform.  idx_dev: int64. */
+int obe_pick(const double* utility_dev, int64_t n_settings, double pickiness, double u,
+             int64_t* idx_dev, void* select_scratch_dev, void* stream);
+/* eval_over_all_parameters (obe_base.py:298-320) -> y_dev (C, ldy) */
+int obe_eval_parameters(obe_model_t m, const obe_cloud_t* c, const double* setting,
+                        const double* constants, double* y_dev, int64_t ldy, void* stream);
+/* eval_over_all_settings (obe_base.py:322-338) -> y_dev (C, ldy) */
+int obe_eval_settings(obe_model_t m, const double* settings_dev, int64_t lds, int64_t n_settings,
+                      const double* params, const double* constants, double* y_dev, int64_t ldy,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBE_B200_H */

@@ -1,0 +1,123 @@
+"""ctypes binding of libobe_b200.so (include/obe_b200.h).
+
+The shared library is built in-tree by ``optbayesexpt_b200.build`` (nvcc, sm_100a).  There is no
+CPU implementation behind these symbols: a missing library or a machine without a CUDA device
+raises, it never falls back.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libobe_b200.so')
+
+TILE = 2048
+STATS_LEN = 64
+MAX_PARAMS = 8
+MAX_CHANNELS = 4
+MAX_SETTINGS = 4
+MAX_CONSTANTS = 8
+
+ST_TOTAL, ST_INVS, ST_SUMSQ, ST_NEFF = 0, 1, 2, 3
+ST_M1, ST_M2, ST_PIVOT, ST_NOISE, ST_SUMT, ST_NZERO = 4, 12, 48, 56, 60, 61
+
+
+class ObeError(RuntimeError):
+    pass
+
+
+class Cloud(C.Structure):
+    _fields_ = [('particles_dev', C.c_void_p), ('weights_dev', C.c_void_p),
+                ('tile_sums_dev', C.c_void_p), ('tile_prefix_dev', C.c_void_p),
+                ('stats_dev', C.c_void_p), ('scratch_dev', C.c_void_p),
+                ('n', C.c_int64), ('ld', C.c_int64), ('d', C.c_int32), ('reserved', C.c_int32)]
+
+
+_PD = C.POINTER(C.c_double)
+_PI32 = C.POINTER(C.c_int32)
+_PCLOUD = C.POINTER(Cloud)
+_VP = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/obe_b200.h declares
+SIGNATURES = {
+    'obe_abi_version': (C.c_int, []),
+    'obe_last_error': (C.c_char_p, []),
+    'obe_device_count': (C.c_int, []),
+    'obe_num_tiles': (C.c_int64, [C.c_int64]),
+    'obe_scratch_bytes': (C.c_size_t, [C.c_int64]),
+    'obe_select_scratch_bytes': (C.c_size_t, [C.c_int64]),
+    'obe_model_builtin': (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_VP)]),
+    'obe_model_compile': (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(_VP), C.c_char_p, C.c_size_t]),
+    'obe_model_info': (C.c_int, [_VP] + [C.POINTER(C.c_int)] * 5),
+    'obe_model_free': (None, [_VP]),
+    'obe_set_uniform': (C.c_int, [_PCLOUD, _VP]),
+    'obe_update': (C.c_int, [_VP, _PCLOUD, _PD, _PD, _PD, _PD, _PI32, C.c_int, C.c_int, C.c_double, _PD, _VP]),
+    'obe_update_from_y': (C.c_int, [_PCLOUD, _VP, C.c_int64, C.c_int, _PD, _PD, _PI32, C.c_int, C.c_int,
+                                    C.c_double, _PD, _VP]),
+    'obe_update_from_likelihood': (C.c_int, [_PCLOUD, _VP, _PD, _VP]),
+    'obe_refresh': (C.c_int, [_PCLOUD, C.c_uint32, C.c_uint32, _PI32, C.c_int, _PD, C.c_int, _VP]),
+    'obe_fetch_stats': (C.c_int, [_PCLOUD, _PD, _VP]),
+    'obe_normalized_weights': (C.c_int, [_PCLOUD, _VP, _VP]),
+    'obe_cdf': (C.c_int, [_PCLOUD, _VP, _VP]),
+    'obe_search': (C.c_int, [_PCLOUD, _VP, _VP, C.c_int64, _VP, _VP]),
+    'obe_draw': (C.c_int, [_PCLOUD, _PD, C.c_int, _VP, _VP, _VP]),
+    'obe_gather_jitter': (C.c_int, [_PCLOUD, _PCLOUD, _VP, _PD, _PD, _VP, C.c_uint64, C.c_uint32,
+                                    C.c_double, C.c_int, _VP]),
+    'obe_resample_systematic': (C.c_int, [_PCLOUD, _PCLOUD, C.c_double, _PD, _PD, C.c_uint64, C.c_uint32,
+                                          C.c_double, C.c_int, _VP, _VP, _VP]),
+    'obe_utility': (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int64, C.c_int64, _PD, _PD, _VP, _VP, C.c_int,
+                              C.c_int, _VP, _VP, _VP, _VP]),
+    'obe_pick': (C.c_int, [_VP, C.c_int64, C.c_double, C.c_double, _VP, _VP, _VP]),
+    'obe_eval_parameters': (C.c_int, [_VP, _PCLOUD, _PD, _PD, _VP, C.c_int64, _VP]),
+    'obe_eval_settings': (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _PD, _PD, _VP, C.c_int64, _VP]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libobe_b200.so (building it is the caller's job: ``python -m optbayesexpt_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ObeError(f'{LIB_PATH} is missing: run `python -m optbayesexpt_b200.build` '
+                       '(there is no CPU fallback)')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.obe_abi_version() != 1:
+        raise ObeError('libobe_b200.so ABI version mismatch: rebuild')
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise ObeError(load().obe_last_error().decode(errors='replace'))
+
+
+def darr(values, n=None):
+    """Host double array for a by-value kernel argument (or None)."""
+    if values is None:
+        return None
+    vals = [float(v) for v in values]
+    if n is not None and len(vals) < n:
+        vals = vals + [0.0] * (n - len(vals))
+    return (C.c_double * max(len(vals), 1))(*vals) if vals else (C.c_double * 1)(0.0)
+
+
+def iarr(values):
+    if values is None:
+        return None
+    vals = [int(v) for v in values]
+    return (C.c_int32 * max(len(vals), 1))(*vals)
+
+
+def require_device():
+    lib = load()
+    if lib.obe_device_count() <= 0:
+        raise ObeError('no CUDA device visible: optbayesexpt_b200 has no CPU fallback')
+    return lib

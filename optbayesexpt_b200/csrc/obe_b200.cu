@@ -1,0 +1,1283 @@
+// obe_b200.cu -- libobe_b200.so: model-independent kernels, the C ABI (include/obe_b200.h),
+// built-in model instantiations and the NVRTC path for user model source.  sm_100a only.
+//
+// Kernel inventory (reference call site -> kernel), all fp64 / HBM-streaming:
+//   obe_base.py:381-394 + particlepdf.py:136-139,243-244,173-214  -> obe_update_body (obe_device.cuh)
+//   particlepdf.py:330 cumsum (tile level)                        -> k_tile_scan
+//   particlepdf.py:330-331 choice(p=w), K draws                   -> k_draw
+//   particlepdf.py:330-331 choice(p=w), N draws (parity mode)     -> k_cdf + k_search + k_gather_jitter
+//   particlepdf.py:286-310 resample, systematic comb (fast path)  -> k_sys_plan + k_sys_resample
+//   obe_base.py:463-489,628-655,748                               -> obe_utility_body (obe_device.cuh)
+//   obe_base.py:778-789 good_setting                              -> k_pick_weights + k_tile_scan + k_draw
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/obe_b200.h"
+#include "obe_device.cuh"
+#include "obe_models.cuh"
+
+static_assert(OBE_TILE == OBE_TILE_SIZE, "tile size mismatch");
+static_assert(OBE_STATS_LEN == OBE_STATS_DOUBLES, "stats length mismatch");
+static_assert(OBE_TILE == OBE_THREADS * OBE_EPT, "tile geometry");
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int obe_fail(const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return -1;
+}
+#define OBE_CUDA(x)                                                                  \
+    do {                                                                             \
+        cudaError_t e_ = (x);                                                        \
+        if (e_ != cudaSuccess) return obe_fail("%s: %s", #x, cudaGetErrorString(e_)); \
+    } while (0)
+#define OBE_LAUNCH_CHECK(what)                                                        \
+    do {                                                                              \
+        cudaError_t e_ = cudaGetLastError();                                          \
+        if (e_ != cudaSuccess) return obe_fail("launch %s: %s", what, cudaGetErrorString(e_)); \
+    } while (0)
+
+static int g_sms = 0;
+static int obe_sms() {
+    if (g_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_sms = 0;
+    }
+    return g_sms;
+}
+#define OBE_BLOCKS_PER_SM 4
+#define OBE_MAX_GRID 4096
+
+// ---------------------------------------------------------------------------------------------
+// scratch layout of a cloud
+// ---------------------------------------------------------------------------------------------
+struct Scratch {
+    unsigned int* counter;   // 64 words
+    double* partials;        // OBE_MAX_GRID * OBE_NACC_MAX
+    long long* plan_h;       // n_tiles + 1
+    int* unit_start;         // n_tiles + 2
+};
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static size_t scratch_bytes(int64_t n) {
+    const int64_t nt = (n + OBE_TILE - 1) / OBE_TILE;
+    size_t b = 256;
+    b += align_up((size_t)OBE_MAX_GRID * OBE_NACC_MAX * sizeof(double), 256);
+    b += align_up((size_t)(nt + 1) * sizeof(long long), 256);
+    b += align_up((size_t)(nt + 2) * sizeof(int), 256);
+    return b;
+}
+static Scratch scratch_of(const obe_cloud_t* c) {
+    const int64_t nt = (c->n + OBE_TILE - 1) / OBE_TILE;
+    char* p = (char*)c->scratch_dev;
+    Scratch s;
+    s.counter = (unsigned int*)p; p += 256;
+    s.partials = (double*)p; p += align_up((size_t)OBE_MAX_GRID * OBE_NACC_MAX * sizeof(double), 256);
+    s.plan_h = (long long*)p; p += align_up((size_t)(nt + 1) * sizeof(long long), 256);
+    s.unit_start = (int*)p;
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic (model-free) update kernels: y supplied / likelihood supplied / refresh
+// ---------------------------------------------------------------------------------------------
+template <int D, int SRC>
+__global__ void __launch_bounds__(OBE_THREADS) k_update_generic(const ObeUpdateArgs a) {
+    obe_update_body<ObeNoModel, D, SRC>(a);
+}
+template <int SRC>
+static int launch_generic(int d, const ObeUpdateArgs& a, int grid, cudaStream_t st) {
+    switch (d) {
+        case 1: k_update_generic<1, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
+        case 2: k_update_generic<2, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
+        case 3: k_update_generic<3, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
+        case 4: k_update_generic<4, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
+        case 5: k_update_generic<5, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
+        case 6: k_update_generic<6, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
+        case 7: k_update_generic<7, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
+        case 8: k_update_generic<8, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
+        default: return obe_fail("n_params must be 1..8%s%s");
+    }
+    OBE_LAUNCH_CHECK("k_update_generic");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-block scans over per-tile arrays
+// ---------------------------------------------------------------------------------------------
+#define OBE_SCAN_THREADS 1024
+
+// exclusive block scan of one double per thread (sum); returns exclusive prefix, total in *tot
+__device__ __forceinline__ double block_excl_sum_1024(double v, double* sm /*34*/, double* tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();
+    if (lane == 31) sm[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        double xs = sm[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, xs, o);
+            if (lane >= o) xs += y;
+        }
+        double ex = __shfl_up_sync(0xffffffffu, xs, 1);  // exclusive base of each warp
+        if (lane == 0) ex = 0.0;
+        sm[lane] = ex;
+        if (lane == 31) sm[32] = xs;
+    }
+    __syncthreads();
+    const double base = sm[warp];
+    double ex = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) ex = 0.0;
+    *tot = sm[32];
+    return base + ex;
+}
+
+__device__ __forceinline__ long long block_excl_max_1024(long long v, long long* sm /*33*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x = max(x, y);
+    }
+    __syncthreads();
+    if (lane == 31) sm[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        long long xs = sm[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(0xffffffffu, xs, o);
+            if (lane >= o) xs = max(xs, y);
+        }
+        long long ex = __shfl_up_sync(0xffffffffu, xs, 1);
+        if (lane == 0) ex = -1;
+        sm[lane] = ex;
+    }
+    __syncthreads();
+    const long long base = sm[warp];
+    long long ex = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) ex = -1;
+    return max(base, ex);
+}
+
+__device__ __forceinline__ int block_excl_isum_1024(int v, int* sm /*33*/, int* tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();
+    if (lane == 31) sm[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = sm[lane];
+        int xs = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, xs, o);
+            if (lane >= o) xs += y;
+        }
+        sm[lane] = xs - w;
+        if (lane == 31) sm[32] = xs;
+    }
+    __syncthreads();
+    *tot = sm[32];
+    return sm[warp] + (x - v);
+}
+
+// tile_prefix[k] = sum of tile_sums[0..k) in a fixed association (blocked per thread, then a
+// block scan); tile_prefix[n_tiles] is THE total every CDF consumer divides by.
+__global__ void __launch_bounds__(OBE_SCAN_THREADS) k_tile_scan(const double* __restrict__ tile_sums,
+                                                                long long n_tiles, double* __restrict__ prefix,
+                                                                double* __restrict__ stats, int renormalise,
+                                                                int uniform, long long n) {
+    __shared__ double sm[34];
+    const int t = threadIdx.x;
+    const long long per = (n_tiles + OBE_SCAN_THREADS - 1) / OBE_SCAN_THREADS;
+    const long long lo = min((long long)t * per, n_tiles), hi = min(lo + per, n_tiles);
+    double s = 0.0;
+    for (long long k = lo; k < hi; ++k) s += tile_sums[k];
+    double total;
+    double run = block_excl_sum_1024(s, sm, &total);
+    for (long long k = lo; k < hi; ++k) {
+        prefix[k] = run;
+        run += tile_sums[k];
+    }
+    if (t == 0) {
+        prefix[n_tiles] = total;
+        if (stats) {
+            stats[OBE_ST_TOTAL] = total;
+            if (uniform) {
+                // weights are exactly 1/n: normaliser is exactly 1 (particlepdf.py:309-310)
+                stats[OBE_ST_INVS] = 1.0;
+                stats[OBE_ST_SUMSQ] = 1.0 / (double)n;
+                stats[OBE_ST_SUMT] = 1.0;
+                stats[OBE_ST_NEFF] = (double)n;
+            } else {
+                stats[OBE_ST_INVS] = renormalise ? 1.0 / total : 1.0;
+                const double ssq = stats[OBE_ST_SUMSQ];
+                stats[OBE_ST_NEFF] = (total * total) / ssq;
+            }
+        }
+    }
+}
+
+__global__ void k_fill_uniform(double* __restrict__ w, double* __restrict__ tile_sums, long long n,
+                               long long n_tiles, int write_weights) {
+    const double v = 1.0 / (double)n;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (write_weights)
+        for (long long i = i0; i < n; i += stride) w[i] = v;
+    for (long long k = i0; k < n_tiles; k += stride) {
+        const long long cnt = min((long long)OBE_TILE, n - k * OBE_TILE);
+        tile_sums[k] = (double)cnt * v;
+    }
+}
+
+__global__ void k_normalized_weights(const double* __restrict__ w, const double* __restrict__ stats,
+                                     double* __restrict__ out, long long n) {
+    const double inv = stats[OBE_ST_INVS];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = obe_nan_to_num(w[i] * inv);
+}
+
+// ---------------------------------------------------------------------------------------------
+// canonical in-tile scan: thread t owns elements [8t, 8t+8) of the tile.
+//   incl[e] = (sum of earlier warps' totals, sequential) + (exclusive KS scan over lanes) + running
+// The canonical CDF is cdf[j] = (tile_prefix[k] + incl_j) / total, EXCEPT the last valid element
+// of each tile, which is tile_prefix[k+1] / total by definition (so cdf[n-1] == 1 exactly and
+// tile_sums may be reduced in any order).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_load_blocked(const double* __restrict__ w, long long base, long long n,
+                                                  double (&v)[OBE_EPT]) {
+    const long long i0 = base + (long long)threadIdx.x * OBE_EPT;
+    if (i0 + OBE_EPT <= n) {
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; e += 2) {
+            const double2 x = *reinterpret_cast<const double2*>(w + i0 + e);
+            v[e] = x.x; v[e + 1] = x.y;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; ++e) v[e] = (i0 + e < n) ? w[i0 + e] : 0.0;
+    }
+}
+
+__device__ __forceinline__ void tile_scan_blocked(const double (&v)[OBE_EPT], double (&incl)[OBE_EPT],
+                                                  double* sm /*8*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double run = 0.0;
+#pragma unroll
+    for (int e = 0; e < OBE_EPT; ++e) { run += v[e]; incl[e] = run; }
+    double x = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    double ex = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) ex = 0.0;
+    __syncthreads();
+    if (lane == 31) sm[warp] = x;
+    __syncthreads();
+    double wb = 0.0;
+    for (int w2 = 0; w2 < warp; ++w2) wb += sm[w2];
+    const double base = wb + ex;
+#pragma unroll
+    for (int e = 0; e < OBE_EPT; ++e) incl[e] = base + incl[e];
+}
+
+// normalised canonical CDF values of this thread's 8 elements of tile k
+__device__ __forceinline__ void tile_cdf_blocked(const double* __restrict__ w, const double* __restrict__ prefix,
+                                                 long long k, long long n, double total,
+                                                 double (&cn)[OBE_EPT], double* sm) {
+    double v[OBE_EPT], incl[OBE_EPT];
+    const long long base = k * OBE_TILE;
+    tile_load_blocked(w, base, n, v);
+    tile_scan_blocked(v, incl, sm);
+    const double p0 = prefix[k], p1 = prefix[k + 1];
+    const long long last = min(n, base + OBE_TILE) - 1;
+#pragma unroll
+    for (int e = 0; e < OBE_EPT; ++e) {
+        const long long i = base + (long long)threadIdx.x * OBE_EPT + e;
+        double c = obe_div(obe_add(p0, incl[e]), total);
+        if (i >= last) c = obe_div(p1, total);
+        cn[e] = c;
+    }
+}
+
+__global__ void __launch_bounds__(OBE_THREADS) k_cdf(const double* __restrict__ w, const double* __restrict__ prefix,
+                                                     long long n, long long n_tiles, double* __restrict__ cdf) {
+    __shared__ double sm[8];
+    const double total = prefix[n_tiles];
+    for (long long k = blockIdx.x; k < n_tiles; k += gridDim.x) {
+        double cn[OBE_EPT];
+        tile_cdf_blocked(w, prefix, k, n, total, cn, sm);
+        const long long i0 = k * OBE_TILE + (long long)threadIdx.x * OBE_EPT;
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; ++e)
+            if (i0 + e < n) cdf[i0 + e] = cn[e];
+        __syncthreads();
+    }
+}
+
+// tile containing u: #{k in [0, n_tiles) : prefix[k+1]/total <= u}, clamped
+__device__ __forceinline__ long long find_tile(const double* __restrict__ prefix, long long n_tiles, double total,
+                                               double u) {
+    long long lo = 0, hi = n_tiles;  // first k with prefix[k+1]/total > u
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (obe_div(prefix[mid + 1], total) <= u) lo = mid + 1; else hi = mid;
+    }
+    return min(lo, n_tiles - 1);
+}
+
+__global__ void k_search(const double* __restrict__ cdf, const double* __restrict__ prefix, long long n,
+                         long long n_tiles, const double* __restrict__ u, long long m,
+                         long long* __restrict__ idx) {
+    const double total = prefix[n_tiles];
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < m;
+         q += (long long)gridDim.x * blockDim.x) {
+        const double uq = u[q];
+        const long long k = find_tile(prefix, n_tiles, total, uq);
+        long long lo = k * OBE_TILE, hi = min(n, lo + OBE_TILE);
+        const long long last = hi - 1;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (cdf[mid] <= uq) lo = mid + 1; else hi = mid;
+        }
+        idx[q] = min(lo, last);
+    }
+}
+
+struct ObeDrawArgs {
+    const double* w; const double* prefix; long long n; long long n_tiles;
+    const double* particles; long long ld; int d;
+    double* draws; long long* idx; int k;
+    double u[OBE_MAX_DRAWS];
+};
+// one block per draw: tile by binary search on the prefix, element by a canonical scan + count
+__global__ void __launch_bounds__(OBE_THREADS) k_draw(const ObeDrawArgs a) {
+    __shared__ double sm[8];
+    __shared__ int cnt[OBE_THREADS / 32];
+    const int q = blockIdx.x;
+    const double uq = a.u[q];
+    const double total = a.prefix[a.n_tiles];
+    const long long k = find_tile(a.prefix, a.n_tiles, total, uq);
+    double cn[OBE_EPT];
+    tile_cdf_blocked(a.w, a.prefix, k, a.n, total, cn, sm);
+    const long long base = k * OBE_TILE;
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < OBE_EPT; ++e) {
+        const long long i = base + (long long)threadIdx.x * OBE_EPT + e;
+        if (i < a.n && cn[e] <= uq) ++c;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+    if ((threadIdx.x & 31) == 0) cnt[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w2 = 0; w2 < OBE_THREADS / 32; ++w2) tot += cnt[w2];
+        const long long last = min(a.n, base + OBE_TILE) - 1;
+        const long long i = min(base + tot, last);
+        if (a.idx) a.idx[q] = i;
+        for (int j = 0; j < a.d; ++j) a.draws[(long long)j * a.k + q] = a.particles[j * a.ld + i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller (restated in oracle/obe_oracle.py:device_normals)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3,
+                                              unsigned int k0, unsigned int k1, unsigned int (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double u53(unsigned int lo, unsigned int hi) {
+    const unsigned long long x = ((unsigned long long)hi << 32) | lo;
+    return ((double)(x >> 11) + 0.5) * 1.1102230246251565e-16;  // 2^-53
+}
+template <int D>
+__device__ __forceinline__ void device_normals(long long slot, unsigned long long seed, unsigned int epoch,
+                                               double (&z)[D]) {
+#pragma unroll
+    for (int c = 0; c < (D + 1) / 2; ++c) {
+        unsigned int r[4];
+        philox4x32_10((unsigned int)(slot & 0xffffffffll), (unsigned int)((unsigned long long)slot >> 32),
+                      (unsigned int)c, epoch, (unsigned int)(seed & 0xffffffffull), (unsigned int)(seed >> 32), r);
+        const double u1 = u53(r[0], r[1]), u2 = u53(r[2], r[3]);
+        const double rad = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        z[2 * c] = rad * cs;
+        if (2 * c + 1 < D) z[2 * c + 1] = rad * sn;
+    }
+}
+
+// Liu-West move of one particle (particlepdf.py:296-307): x + z @ F, optional contraction
+template <int D>
+__device__ __forceinline__ void liu_west(double (&x)[D], const double (&z)[D], const double* __restrict__ F,
+                                         const double* __restrict__ mean, double a_param, int scale) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        double nud = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) nud += z[k] * F[k * D + j];
+        double v = x[j] + nud;
+        if (scale) v = obe_add(obe_mul(v, a_param), obe_mul(mean[j], obe_sub(1.0, a_param)));
+        x[j] = v;
+    }
+}
+
+struct ObeResampleArgs {
+    const double* pin; long long ld_in; const double* w_in; const double* prefix;
+    long long n; long long n_tiles;
+    double* pout; long long ld_out; double* w_out;
+    const long long* idx_in;       // gather mode
+    const double* z_in;            // gather mode, optional (n, d)
+    const long long* plan_h; const int* unit_start;  // systematic mode
+    const double* stats;
+    long long* idx_out; double* z_out;
+    double u0, a_param;
+    int scale, factor_from_stats, jitter;
+    unsigned int epoch;
+    unsigned long long seed;
+    double factor[OBE_MAX_DIMS * OBE_MAX_DIMS];
+    double mean[OBE_MAX_DIMS];
+};
+
+// F (z @ F convention) and mean into shared memory; from the host, or Cholesky of
+// (1-a^2) * cov(stats) on the device: the "covariance computed in the same pass" path.
+template <int D>
+__device__ __forceinline__ void setup_factor(const ObeResampleArgs& a, double* sF, double* sMean) {
+    if (threadIdx.x == 0) {
+        if (!a.factor_from_stats) {
+            for (int q = 0; q < D * D; ++q) sF[q] = a.factor[q];
+            for (int j = 0; j < D; ++j) sMean[j] = a.mean[j];
+        } else {
+            const double st = a.stats[OBE_ST_SUMT], ssq = a.stats[OBE_ST_SUMSQ];
+            const double fact = st - ssq / st;
+            const double shrink = 1.0 - a.a_param * a.a_param;
+            double cov[D][D], L[D][D];
+            int q = 0;
+            for (int j = 0; j < D; ++j) {
+                sMean[j] = a.stats[OBE_ST_PIVOT + j] + a.stats[OBE_ST_M1 + j] / st;
+                for (int k = j; k < D; ++k) {
+                    const double c = (a.stats[OBE_ST_M2 + q] - a.stats[OBE_ST_M1 + j] * a.stats[OBE_ST_M1 + k] / st) / fact;
+                    cov[j][k] = cov[k][j] = shrink * c;
+                    ++q;
+                }
+            }
+            for (int j = 0; j < D; ++j)
+                for (int k = 0; k < D; ++k) L[j][k] = 0.0;
+            for (int j = 0; j < D; ++j) {
+                double s = cov[j][j];
+                for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+                const double dj = s > 0.0 ? sqrt(s) : 0.0;
+                L[j][j] = dj;
+                for (int i = j + 1; i < D; ++i) {
+                    double t = cov[i][j];
+                    for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+                    L[i][j] = dj > 0.0 ? t / dj : 0.0;
+                }
+            }
+            // x = z @ L^T  ->  F[k][j] = L[j][k]
+            for (int k = 0; k < D; ++k)
+                for (int j = 0; j < D; ++j) sF[k * D + j] = L[j][k];
+        }
+    }
+    __syncthreads();
+}
+
+template <int D>
+__global__ void __launch_bounds__(OBE_THREADS) k_gather_jitter(const ObeResampleArgs a) {
+    __shared__ double sF[D * D];
+    __shared__ double sMean[D];
+    setup_factor<D>(a, sF, sMean);
+    const double wv = 1.0 / (double)a.n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long anc = a.idx_in[i];
+        double x[D], z[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) x[j] = a.pin[j * a.ld_in + anc];
+        if (a.jitter) {
+            if (a.z_in) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) z[j] = a.z_in[i * D + j];
+            } else {
+                device_normals<D>(i, a.seed, a.epoch, z);
+            }
+            if (a.z_out) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) a.z_out[i * D + j] = z[j];
+            }
+            liu_west<D>(x, z, sF, sMean, a.a_param, a.scale);
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) a.pout[j * a.ld_out + i] = x[j];
+        a.w_out[i] = wv;
+    }
+}
+
+// ---- systematic comb --------------------------------------------------------------------------
+// #{i in [0,n) : (i + u0) * inv_n < c}; the comb value is two IEEE ops (add, mul), monotone in i
+__device__ __forceinline__ long long comb_count(double c, double u0, double inv_n, long long n, double nd) {
+    const double est = ceil(c * nd - u0);
+    long long i = est <= 0.0 ? 0 : (est >= nd ? n : (long long)est);
+    while (i > 0 && obe_mul(obe_add((double)(i - 1), u0), inv_n) >= c) --i;
+    while (i < n && obe_mul(obe_add((double)i, u0), inv_n) < c) ++i;
+    return i;
+}
+
+#define OBE_OUT_CHUNK 2048
+// plan: H[k] = first output slot owned by tile k (monotone), unit_start[k] = first work unit
+__global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __restrict__ prefix, long long n_tiles,
+                                                               long long n, double u0, long long* __restrict__ H,
+                                                               int* __restrict__ unit_start) {
+    __shared__ long long sml[34];
+    __shared__ int smi[34];
+    const int t = threadIdx.x;
+    const double total = prefix[n_tiles];
+    const double nd = (double)n, inv_n = 1.0 / nd;
+    const long long cnt = n_tiles + 1;
+    const long long per = (cnt + OBE_SCAN_THREADS - 1) / OBE_SCAN_THREADS;
+    const long long lo = min((long long)t * per, cnt), hi = min(lo + per, cnt);
+    long long mx = -1;
+    for (long long k = lo; k < hi; ++k) {
+        long long h = (k == 0) ? 0 : (k == n_tiles ? n : comb_count(obe_div(prefix[k], total), u0, inv_n, n, nd));
+        mx = max(mx, h);
+        H[k] = mx;  // running max inside the thread's range
+    }
+    const long long before = block_excl_max_1024(mx, sml);
+    for (long long k = lo; k < hi; ++k) H[k] = min(max(H[k], before), n);
+    __syncthreads();
+    __threadfence_block();
+    // units per tile
+    const long long per2 = (n_tiles + OBE_SCAN_THREADS - 1) / OBE_SCAN_THREADS;
+    const long long lo2 = min((long long)t * per2, n_tiles), hi2 = min(lo2 + per2, n_tiles);
+    int s = 0;
+    for (long long k = lo2; k < hi2; ++k) s += (int)((H[k + 1] - H[k] + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK);
+    int tot;
+    int run = block_excl_isum_1024(s, smi, &tot);
+    for (long long k = lo2; k < hi2; ++k) {
+        unit_start[k] = run;
+        run += (int)((H[k + 1] - H[k] + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK);
+    }
+    if (t == 0) unit_start[n_tiles] = tot;
+}
+
+template <int D>
+__global__ void __launch_bounds__(OBE_THREADS) k_sys_resample(const ObeResampleArgs a) {
+    __shared__ double sF[D * D];
+    __shared__ double sMean[D];
+    __shared__ double sm[8];
+    __shared__ int smx[OBE_THREADS / 32];
+    __shared__ int rel_hi[OBE_TILE];
+    setup_factor<D>(a, sF, sMean);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double total = a.prefix[a.n_tiles];
+    const double nd = (double)a.n, inv_n = 1.0 / nd, wv = 1.0 / nd;
+    const int n_units = a.unit_start[a.n_tiles];
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        // tile owning this unit: largest k with unit_start[k] <= unit
+        long long lo = 0, hi = a.n_tiles;  // first k with unit_start[k] > unit
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (a.unit_start[mid] <= unit) lo = mid + 1; else hi = mid;
+        }
+        const long long k = lo - 1;
+        const long long Hk = a.plan_h[k], Hk1 = a.plan_h[k + 1];
+        const long long o_begin = Hk + (long long)(unit - a.unit_start[k]) * OBE_OUT_CHUNK;
+        const long long o_end = min(o_begin + OBE_OUT_CHUNK, Hk1);
+        // canonical CDF of the tile -> first output slot past each element
+        double cn[OBE_EPT];
+        tile_cdf_blocked(a.w_in, a.prefix, k, a.n, total, cn, sm);
+        const long long base = k * OBE_TILE;
+        const long long last = min(a.n, base + OBE_TILE) - 1;
+        int r[OBE_EPT];
+        int run = 0;
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; ++e) {
+            const long long i = base + (long long)tid * OBE_EPT + e;
+            long long h;
+            if (i >= last) h = Hk1;
+            else h = min(max(comb_count(cn[e], a.u0, inv_n, a.n, nd), Hk), Hk1);
+            run = max(run, (int)(h - Hk));
+            r[e] = run;
+        }
+        int x = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x = max(x, y);
+        }
+        int ex = __shfl_up_sync(0xffffffffu, x, 1);
+        if (lane == 0) ex = 0;
+        if (lane == 31) smx[warp] = x;
+        __syncthreads();
+        for (int w2 = 0; w2 < warp; ++w2) ex = max(ex, smx[w2]);
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; ++e) rel_hi[tid * OBE_EPT + e] = max(r[e], ex);
+        __syncthreads();
+        for (long long o = o_begin + tid; o < o_end; o += OBE_THREADS) {
+            const int rel = (int)(o - Hk);
+            int l2 = 0, h2 = OBE_TILE;  // first j with rel_hi[j] > rel
+            while (l2 < h2) {
+                const int mid = (l2 + h2) >> 1;
+                if (rel_hi[mid] <= rel) l2 = mid + 1; else h2 = mid;
+            }
+            const long long anc = min(base + l2, last);
+            double xv[D], z[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) xv[j] = __ldg(a.pin + j * a.ld_in + anc);
+            if (a.jitter) {
+                device_normals<D>(o, a.seed, a.epoch, z);
+                if (a.z_out) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) a.z_out[o * D + j] = z[j];
+                }
+                liu_west<D>(xv, z, sF, sMean, a.a_param, a.scale);
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) a.pout[j * a.ld_out + o] = xv[j];
+            a.w_out[o] = wv;
+            if (a.idx_out) a.idx_out[o] = anc;
+        }
+        __syncthreads();
+    }
+}
+
+#define OBE_DIM_SWITCH(d, KERNEL, grid, st, args)                                     \
+    switch (d) {                                                                      \
+        case 1: KERNEL<1><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
+        case 2: KERNEL<2><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
+        case 3: KERNEL<3><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
+        case 4: KERNEL<4><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
+        case 5: KERNEL<5><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
+        case 6: KERNEL<6><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
+        case 7: KERNEL<7><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
+        case 8: KERNEL<8><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
+        default: return obe_fail("n_params must be 1..8%s%s");                        \
+    }
+
+// ---------------------------------------------------------------------------------------------
+// good_setting: p_j = nan_to_num(U_j ** pickiness) as a weight vector with tile sums
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OBE_THREADS) k_pick_weights(const double* __restrict__ util, long long n,
+                                                              double pickiness, double* __restrict__ p,
+                                                              double* __restrict__ tile_sums) {
+    __shared__ double red[OBE_THREADS / 32];
+    const long long n_tiles = (n + OBE_TILE - 1) / OBE_TILE;
+    for (long long k = blockIdx.x; k < n_tiles; k += gridDim.x) {
+        double s = 0.0;
+        for (int e = 0; e < OBE_EPT; ++e) {
+            const long long i = k * OBE_TILE + e * OBE_THREADS + threadIdx.x;
+            if (i < n) {
+                const double v = obe_nan_to_num(pow(util[i], pickiness));
+                p[i] = v;
+                s += v;
+            }
+        }
+        const double tot = obe_block_sum(s, red);
+        if (threadIdx.x == 0) tile_sums[k] = tot;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// models: built-in instantiations + NVRTC-compiled user functors
+// ---------------------------------------------------------------------------------------------
+template <class M, int D>
+__global__ void __launch_bounds__(OBE_THREADS) k_update_model(const ObeUpdateArgs a) {
+    obe_update_body<M, D, OBE_SRC_MODEL>(a);
+}
+template <class M, int D>
+__global__ void __launch_bounds__(OBE_THREADS) k_evalp_model(const ObeEvalArgs a) {
+    obe_eval_params_body<M, D>(a);
+}
+template <class M>
+__global__ void __launch_bounds__(OBE_THREADS) k_utility_model(const ObeUtilityArgs a) {
+    obe_utility_body<M>(a);
+}
+template <class M>
+__global__ void __launch_bounds__(OBE_THREADS) k_evals_model(const ObeEvalArgs a) {
+    obe_eval_settings_body<M>(a);
+}
+
+struct obe_model {
+    int ns, np_model, ncons, nch, d;
+    bool user;
+    const void* f_update;   // kernel entry (host stub address, or cudaKernel_t for user models)
+    const void* f_evalp;
+    const void* f_utility;
+    const void* f_evals;
+    cudaLibrary_t lib;
+};
+
+template <class M, int D>
+static void fill_model(obe_model* m) {
+    m->ns = M::NS; m->np_model = M::NP; m->ncons = M::NCONS; m->nch = M::NCH; m->d = D;
+    m->user = false; m->lib = nullptr;
+    m->f_update = (const void*)k_update_model<M, D>;
+    m->f_evalp = (const void*)k_evalp_model<M, D>;
+    m->f_utility = (const void*)k_utility_model<M>;
+    m->f_evals = (const void*)k_evals_model<M>;
+}
+template <class M>
+static int make_builtin(int d, obe_model* m) {
+    // pre-instantiated: the model's own parameter count plus up to 2 extra rows (noise parameters)
+    if (d == M::NP) { fill_model<M, M::NP>(m); return 0; }
+    if (d == M::NP + 1) { fill_model<M, M::NP + 1>(m); return 0; }
+    if (d == M::NP + 2) { fill_model<M, (M::NP + 2 <= OBE_MAX_DIMS ? M::NP + 2 : OBE_MAX_DIMS)>(m); return 0; }
+    return obe_fail("built-in model supports n_params in [NP, NP+2]; compile it from source for other sizes%s%s");
+}
+
+static int launch_kernel(const void* f, int grid, size_t smem, cudaStream_t st, const void* args_struct) {
+    void* params[1] = {const_cast<void*>(args_struct)};
+    cudaError_t e = cudaLaunchKernel(f, dim3(grid), dim3(OBE_THREADS), params, smem, st);
+    if (e != cudaSuccess) return obe_fail("cudaLaunchKernel: %s%s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---- NVRTC (loaded lazily so the library loads on machines without it) ----------------------
+struct NvrtcApi {
+    void* h;
+    decltype(&nvrtcCreateProgram) create;
+    decltype(&nvrtcCompileProgram) compile;
+    decltype(&nvrtcGetCUBINSize) cubin_size;
+    decltype(&nvrtcGetCUBIN) cubin;
+    decltype(&nvrtcGetProgramLogSize) log_size;
+    decltype(&nvrtcGetProgramLog) log;
+    decltype(&nvrtcDestroyProgram) destroy;
+    decltype(&nvrtcGetErrorString) errstr;
+};
+static NvrtcApi g_nvrtc = {};
+static int load_nvrtc() {
+    if (g_nvrtc.h) return 0;
+    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                           "/usr/local/cuda/lib64/libnvrtc.so"};
+    void* h = nullptr;
+    for (const char* nm : names) {
+        h = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+        if (h) break;
+    }
+    if (!h) return obe_fail("cannot load libnvrtc: %s%s", dlerror());
+#define OBE_SYM(field, name)                                                   \
+    g_nvrtc.field = (decltype(g_nvrtc.field))dlsym(h, name);                   \
+    if (!g_nvrtc.field) return obe_fail("libnvrtc lacks %s%s", name);
+    OBE_SYM(create, "nvrtcCreateProgram")
+    OBE_SYM(compile, "nvrtcCompileProgram")
+    OBE_SYM(cubin_size, "nvrtcGetCUBINSize")
+    OBE_SYM(cubin, "nvrtcGetCUBIN")
+    OBE_SYM(log_size, "nvrtcGetProgramLogSize")
+    OBE_SYM(log, "nvrtcGetProgramLog")
+    OBE_SYM(destroy, "nvrtcDestroyProgram")
+    OBE_SYM(errstr, "nvrtcGetErrorString")
+#undef OBE_SYM
+    g_nvrtc.h = h;
+    return 0;
+}
+
+static const char* k_src_device =
+#include "obe_device_src.inc"
+    ;
+static const char* k_src_models =
+#include "obe_models_src.inc"
+    ;
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int obe_abi_version(void) { return OBE_ABI_VERSION; }
+const char* obe_last_error(void) { return g_err; }
+int obe_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int64_t obe_num_tiles(int64_t n) { return (n + OBE_TILE - 1) / OBE_TILE; }
+size_t obe_scratch_bytes(int64_t n) { return scratch_bytes(n); }
+size_t obe_select_scratch_bytes(int64_t n_settings) {
+    const int64_t nt = (n_settings + OBE_TILE - 1) / OBE_TILE;
+    size_t b = 256;                                            // counter
+    b += align_up((size_t)OBE_MAX_GRID * sizeof(double), 256);    // part_val
+    b += align_up((size_t)OBE_MAX_GRID * sizeof(long long), 256); // part_idx
+    b += align_up((size_t)n_settings * sizeof(double), 256);      // p
+    b += align_up((size_t)nt * sizeof(double), 256);              // tile sums
+    b += align_up((size_t)(nt + 1) * sizeof(double), 256);        // prefix
+    return b;
+}
+
+int obe_model_builtin(const char* name, int n_params, obe_model_t* out) {
+    if (!name || !out) return obe_fail("null argument%s%s");
+    obe_model* m = new obe_model();
+    int rc;
+    const std::string s(name);
+    if (s == "lorentzian_hwhm") rc = make_builtin<ObeLorentzianHWHM>(n_params, m);
+    else if (s == "lorentzian_fwhm") rc = make_builtin<ObeLorentzianFWHM>(n_params, m);
+    else if (s == "lorentzian_4p") rc = make_builtin<ObeLorentzian4P>(n_params, m);
+    else if (s == "lorentzian_dip") rc = make_builtin<ObeLorentzianDip>(n_params, m);
+    else if (s == "line") rc = make_builtin<ObeLine>(n_params, m);
+    else if (s == "rabi") rc = make_builtin<ObeRabi>(n_params, m);
+    else if (s == "lockin_coil") rc = make_builtin<ObeLockinCoil>(n_params, m);
+    else rc = obe_fail("unknown built-in model '%s'%s", name);
+    if (rc) { delete m; return rc; }
+    *out = m;
+    return 0;
+}
+
+int obe_model_compile(const char* cuda_source, const char* entry, int n_settings, int n_params,
+                      int n_model_params, int n_constants, int n_channels, obe_model_t* out, char* log,
+                      size_t log_len) {
+    if (log && log_len) log[0] = 0;
+    if (!cuda_source || !entry || !out) return obe_fail("null argument%s%s");
+    if (n_params < 1 || n_params > OBE_MAX_DIMS || n_model_params < 0 || n_model_params > n_params ||
+        n_channels < 1 || n_channels > OBE_MAX_CH || n_settings < 0 || n_settings > OBE_MAX_SET ||
+        n_constants < 0 || n_constants > OBE_MAX_CONS)
+        return obe_fail("model dimensions out of range%s%s");
+    if (load_nvrtc()) return -1;
+    char tail[2048];
+    snprintf(tail, sizeof(tail),
+             "\nstruct ObeUserModel {\n"
+             "    enum { NS = %d, NP = %d, NCONS = %d, NCH = %d };\n"
+             "    __device__ static __forceinline__ void eval(const double* s, const double* p, const double* c, double* y) {\n"
+             "        %s(s, p, c, y);\n    }\n};\n"
+             "OBE_DEFINE_MODEL_KERNELS(ObeUserModel, %d, user)\n"
+             "OBE_DEFINE_GRID_KERNELS(ObeUserModel, user)\n",
+             n_settings, n_model_params, n_constants, n_channels, entry, n_params);
+    std::string src = "#include \"obe_device.cuh\"\n#include \"obe_models.cuh\"\n";
+    src += cuda_source;
+    src += tail;
+    nvrtcProgram prog;
+    const char* headers[2] = {k_src_device, k_src_models};
+    const char* names[2] = {"obe_device.cuh", "obe_models.cuh"};
+    nvrtcResult r = g_nvrtc.create(&prog, src.c_str(), "obe_user_model.cu", 2, headers, names);
+    if (r != NVRTC_SUCCESS) return obe_fail("nvrtcCreateProgram: %s%s", g_nvrtc.errstr(r));
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+    r = g_nvrtc.compile(prog, 3, opts);
+    size_t lsz = 0;
+    g_nvrtc.log_size(prog, &lsz);
+    std::vector<char> lbuf(lsz + 1, 0);
+    if (lsz > 1) g_nvrtc.log(prog, lbuf.data());
+    if (log && log_len) {
+        strncpy(log, lbuf.data(), log_len - 1);
+        log[log_len - 1] = 0;
+    }
+    if (r != NVRTC_SUCCESS) {
+        g_nvrtc.destroy(&prog);
+        return obe_fail("NVRTC compile failed: %s\n%s", g_nvrtc.errstr(r), lbuf.data());
+    }
+    size_t csz = 0;
+    g_nvrtc.cubin_size(prog, &csz);
+    std::vector<char> cubin(csz);
+    g_nvrtc.cubin(prog, cubin.data());
+    g_nvrtc.destroy(&prog);
+    obe_model* m = new obe_model();
+    m->ns = n_settings; m->np_model = n_model_params; m->ncons = n_constants; m->nch = n_channels;
+    m->d = n_params; m->user = true;
+    cudaError_t e = cudaLibraryLoadData(&m->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) { delete m; return obe_fail("cudaLibraryLoadData: %s%s", cudaGetErrorString(e)); }
+    cudaKernel_t k[4];
+    const char* kn[4] = {"obe_k_update_user", "obe_k_evalp_user", "obe_k_utility_user", "obe_k_evals_user"};
+    for (int i = 0; i < 4; ++i) {
+        e = cudaLibraryGetKernel(&k[i], m->lib, kn[i]);
+        if (e != cudaSuccess) {
+            cudaLibraryUnload(m->lib);
+            delete m;
+            return obe_fail("cudaLibraryGetKernel(%s): %s", kn[i], cudaGetErrorString(e));
+        }
+    }
+    m->f_update = (const void*)k[0]; m->f_evalp = (const void*)k[1];
+    m->f_utility = (const void*)k[2]; m->f_evals = (const void*)k[3];
+    *out = m;
+    return 0;
+}
+
+int obe_model_info(obe_model_t m, int* ns, int* npm, int* nc, int* nch, int* np) {
+    if (!m) return obe_fail("null model%s%s");
+    if (ns) *ns = m->ns;
+    if (npm) *npm = m->np_model;
+    if (nc) *nc = m->ncons;
+    if (nch) *nch = m->nch;
+    if (np) *np = m->d;
+    return 0;
+}
+void obe_model_free(obe_model_t m) {
+    if (!m) return;
+    if (m->user && m->lib) cudaLibraryUnload(m->lib);
+    delete m;
+}
+
+static int check_cloud(const obe_cloud_t* c) {
+    if (!c || !c->particles_dev || !c->weights_dev || !c->tile_sums_dev || !c->tile_prefix_dev ||
+        !c->stats_dev || !c->scratch_dev)
+        return obe_fail("cloud has null device pointers%s%s");
+    if (c->n < 1 || c->d < 1 || c->d > OBE_MAX_DIMS || c->ld < c->n || (c->ld & 1))
+        return obe_fail("cloud geometry invalid (need 1<=d<=8, ld>=n, ld even)%s%s");
+    if (((uintptr_t)c->particles_dev | (uintptr_t)c->weights_dev) & 15)
+        return obe_fail("particles/weights must be 16-byte aligned%s%s");
+    if (obe_sms() <= 0) return obe_fail("no CUDA device: this library has no CPU fallback%s%s");
+    return 0;
+}
+static int update_grid(const obe_cloud_t* c) {
+    const int64_t nt = obe_num_tiles(c->n);
+    int64_t g = (int64_t)obe_sms() * OBE_BLOCKS_PER_SM;
+    if (g > nt) g = nt;
+    if (g > OBE_MAX_GRID) g = OBE_MAX_GRID;
+    return (int)g;
+}
+static void base_update_args(const obe_cloud_t* c, ObeUpdateArgs& a, const double* pivot) {
+    memset(&a, 0, sizeof(a));
+    const Scratch s = scratch_of(c);
+    a.particles = c->particles_dev; a.ld = c->ld; a.n = c->n;
+    a.weights = c->weights_dev; a.tile_sums = c->tile_sums_dev;
+    a.partials = s.partials; a.counter = s.counter; a.stats = c->stats_dev;
+    for (int j = 0; j < OBE_MAX_CH; ++j) a.noise_idx[j] = -1;
+    if (pivot) for (int j = 0; j < c->d; ++j) a.pivot[j] = pivot[j];
+}
+static int finish_update(const obe_cloud_t* c, int renorm, cudaStream_t st) {
+    k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(c->tile_sums_dev, obe_num_tiles(c->n), c->tile_prefix_dev,
+                                               c->stats_dev, renorm, 0, c->n);
+    OBE_LAUNCH_CHECK("k_tile_scan");
+    return 0;
+}
+static int fill_likelihood_args(ObeUpdateArgs& a, int d, int nch_avail, const double* y_meas, const double* sigma,
+                                const int32_t* noise_index, int n_lik, int use_choke, double choke) {
+    if (n_lik < 0 || n_lik > nch_avail || n_lik > OBE_MAX_CH) return obe_fail("n_lik_channels out of range%s%s");
+    if (!y_meas) return obe_fail("y_meas is null%s%s");
+    if (!sigma && !noise_index) return obe_fail("need sigma or noise_index%s%s");
+    a.n_lik_channels = n_lik;
+    for (int cidx = 0; cidx < n_lik; ++cidx) {
+        a.y_meas[cidx] = y_meas[cidx];
+        a.sigma[cidx] = sigma ? sigma[cidx] : 1.0;
+        if (noise_index) {
+            if (noise_index[cidx] < 0 || noise_index[cidx] >= d) return obe_fail("noise_index out of range%s%s");
+            a.noise_idx[cidx] = noise_index[cidx];
+        }
+    }
+    a.use_choke = use_choke; a.choke = choke;
+    return 0;
+}
+
+int obe_set_uniform(const obe_cloud_t* c, void* stream) {
+    if (check_cloud(c)) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = obe_sms() * 8;
+    k_fill_uniform<<<grid, 256, 0, st>>>(c->weights_dev, c->tile_sums_dev, c->n, obe_num_tiles(c->n), 1);
+    OBE_LAUNCH_CHECK("k_fill_uniform");
+    OBE_CUDA(cudaMemsetAsync(c->stats_dev, 0, OBE_STATS_LEN * sizeof(double), st));
+    k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(c->tile_sums_dev, obe_num_tiles(c->n), c->tile_prefix_dev,
+                                               c->stats_dev, 0, 1, c->n);
+    OBE_LAUNCH_CHECK("k_tile_scan");
+    return 0;
+}
+
+int obe_update(obe_model_t m, const obe_cloud_t* c, const double* setting, const double* constants,
+               const double* y_meas, const double* sigma, const int32_t* noise_index, int n_lik_channels,
+               int use_choke, double choke, const double* pivot, void* stream) {
+    if (!m) return obe_fail("null model%s%s");
+    if (check_cloud(c)) return -1;
+    if (m->d != c->d) return obe_fail("model was built for a different n_params%s%s");
+    ObeUpdateArgs a;
+    base_update_args(c, a, pivot);
+    a.scale_in = 1; a.write_weights = 1;
+    for (int j = 0; j < m->ns; ++j) a.setting[j] = setting[j];
+    for (int j = 0; j < m->ncons; ++j) a.cons[j] = constants[j];
+    if (fill_likelihood_args(a, c->d, m->nch, y_meas, sigma, noise_index, n_lik_channels, use_choke, choke)) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (launch_kernel(m->f_update, update_grid(c), 0, st, &a)) return -1;
+    return finish_update(c, 1, st);
+}
+
+int obe_update_from_y(const obe_cloud_t* c, const double* y_model_dev, int64_t ld_y, int n_channels,
+                      const double* y_meas, const double* sigma, const int32_t* noise_index, int n_lik_channels,
+                      int use_choke, double choke, const double* pivot, void* stream) {
+    if (check_cloud(c)) return -1;
+    if (!y_model_dev || (ld_y & 1) || ((uintptr_t)y_model_dev & 15)) return obe_fail("y_model must be 16-byte aligned with even ld%s%s");
+    ObeUpdateArgs a;
+    base_update_args(c, a, pivot);
+    a.scale_in = 1; a.write_weights = 1;
+    a.y_model = y_model_dev; a.ld_y = ld_y;
+    if (fill_likelihood_args(a, c->d, n_channels, y_meas, sigma, noise_index, n_lik_channels, use_choke, choke)) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (launch_generic<OBE_SRC_Y>(c->d, a, update_grid(c), st)) return -1;
+    return finish_update(c, 1, st);
+}
+
+int obe_update_from_likelihood(const obe_cloud_t* c, const double* likelihood_dev, const double* pivot, void* stream) {
+    if (check_cloud(c)) return -1;
+    if (!likelihood_dev || ((uintptr_t)likelihood_dev & 15)) return obe_fail("likelihood must be 16-byte aligned%s%s");
+    ObeUpdateArgs a;
+    base_update_args(c, a, pivot);
+    a.scale_in = 1; a.write_weights = 1;
+    a.lik = likelihood_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (launch_generic<OBE_SRC_LIK>(c->d, a, update_grid(c), st)) return -1;
+    return finish_update(c, 1, st);
+}
+
+int obe_refresh(const obe_cloud_t* c, uint32_t mask_le, uint32_t mask_lt, const int32_t* noise_index, int n_noise,
+                const double* pivot, int renormalise, void* stream) {
+    if (check_cloud(c)) return -1;
+    ObeUpdateArgs a;
+    base_update_args(c, a, pivot);
+    a.scale_in = 0;
+    a.write_weights = (mask_le | mask_lt) ? 1 : 0;
+    a.mask_le = mask_le; a.mask_lt = mask_lt;
+    if (noise_index)
+        for (int j = 0; j < n_noise && j < OBE_MAX_CH; ++j) a.noise_idx[j] = noise_index[j];
+    cudaStream_t st = (cudaStream_t)stream;
+    if (launch_generic<OBE_SRC_NONE>(c->d, a, update_grid(c), st)) return -1;
+    return finish_update(c, renormalise, st);
+}
+
+int obe_fetch_stats(const obe_cloud_t* c, double* stats_host, void* stream) {
+    if (!c || !stats_host) return obe_fail("null argument%s%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    OBE_CUDA(cudaMemcpyAsync(stats_host, c->stats_dev, OBE_STATS_LEN * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OBE_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int obe_normalized_weights(const obe_cloud_t* c, double* out_dev, void* stream) {
+    if (check_cloud(c)) return -1;
+    k_normalized_weights<<<obe_sms() * 8, 256, 0, (cudaStream_t)stream>>>(c->weights_dev, c->stats_dev, out_dev, c->n);
+    OBE_LAUNCH_CHECK("k_normalized_weights");
+    return 0;
+}
+
+int obe_cdf(const obe_cloud_t* c, double* cdf_dev, void* stream) {
+    if (check_cloud(c)) return -1;
+    const int64_t nt = obe_num_tiles(c->n);
+    int grid = (int)(nt < (int64_t)obe_sms() * 8 ? nt : (int64_t)obe_sms() * 8);
+    k_cdf<<<grid, OBE_THREADS, 0, (cudaStream_t)stream>>>(c->weights_dev, c->tile_prefix_dev, c->n, nt, cdf_dev);
+    OBE_LAUNCH_CHECK("k_cdf");
+    return 0;
+}
+
+int obe_search(const obe_cloud_t* c, const double* cdf_dev, const double* u_dev, int64_t m, int64_t* idx_dev,
+               void* stream) {
+    if (check_cloud(c)) return -1;
+    if (m <= 0) return 0;
+    int64_t blocks = (m + 255) / 256;
+    if (blocks > (int64_t)obe_sms() * 16) blocks = (int64_t)obe_sms() * 16;
+    k_search<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(cdf_dev, c->tile_prefix_dev, c->n, obe_num_tiles(c->n),
+                                                           u_dev, m, (long long*)idx_dev);
+    OBE_LAUNCH_CHECK("k_search");
+    return 0;
+}
+
+static int draw_impl(const double* w, const double* prefix, int64_t n, const double* particles, int64_t ld, int d,
+                     const double* u_host, int k, double* draws_dev, int64_t* idx_dev, cudaStream_t st) {
+    if (k <= 0) return 0;
+    for (int off = 0; off < k; off += OBE_MAX_DRAWS) {
+        const int kk = (k - off) < OBE_MAX_DRAWS ? (k - off) : OBE_MAX_DRAWS;
+        ObeDrawArgs a;
+        a.w = w; a.prefix = prefix; a.n = n; a.n_tiles = obe_num_tiles(n);
+        a.particles = particles; a.ld = ld; a.d = d;
+        a.draws = draws_dev ? draws_dev + off : nullptr;
+        a.idx = idx_dev ? (long long*)idx_dev + off : nullptr;
+        a.k = k;
+        for (int i = 0; i < kk; ++i) a.u[i] = u_host[off + i];
+        k_draw<<<kk, OBE_THREADS, 0, st>>>(a);
+        OBE_LAUNCH_CHECK("k_draw");
+    }
+    return 0;
+}
+
+int obe_draw(const obe_cloud_t* c, const double* u_host, int k, double* draws_dev, int64_t* idx_dev, void* stream) {
+    if (check_cloud(c)) return -1;
+    if (!u_host || !draws_dev) return obe_fail("null argument%s%s");
+    return draw_impl(c->weights_dev, c->tile_prefix_dev, c->n, c->particles_dev, c->ld, c->d, u_host, k, draws_dev,
+                     idx_dev, (cudaStream_t)stream);
+}
+
+static int finish_resample(const obe_cloud_t* out, cudaStream_t st) {
+    k_fill_uniform<<<obe_sms() * 2, 256, 0, st>>>(out->weights_dev, out->tile_sums_dev, out->n, obe_num_tiles(out->n), 0);
+    OBE_LAUNCH_CHECK("k_fill_uniform");
+    k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(out->tile_sums_dev, obe_num_tiles(out->n), out->tile_prefix_dev,
+                                               out->stats_dev, 0, 1, out->n);
+    OBE_LAUNCH_CHECK("k_tile_scan");
+    return 0;
+}
+
+static int fill_resample_args(const obe_cloud_t* in, const obe_cloud_t* out, const double* factor, const double* mean,
+                              double a_param, int scale, uint64_t seed, uint32_t epoch, ObeResampleArgs& a) {
+    if (check_cloud(in) || check_cloud(out)) return -1;
+    if (in->n != out->n || in->d != out->d) return obe_fail("resample: in/out geometry differs%s%s");
+    if (in->particles_dev == out->particles_dev || in->weights_dev == out->weights_dev)
+        return obe_fail("resample is out-of-place: pass a second cloud%s%s");
+    memset(&a, 0, sizeof(a));
+    a.pin = in->particles_dev; a.ld_in = in->ld; a.w_in = in->weights_dev; a.prefix = in->tile_prefix_dev;
+    a.n = in->n; a.n_tiles = obe_num_tiles(in->n);
+    a.pout = out->particles_dev; a.ld_out = out->ld; a.w_out = out->weights_dev;
+    a.stats = in->stats_dev;
+    a.a_param = a_param; a.scale = scale; a.seed = seed; a.epoch = epoch; a.jitter = 1;
+    if (factor) {
+        if (scale && !mean) return obe_fail("resample: mean required with a host factor when scale is on%s%s");
+        for (int q = 0; q < in->d * in->d; ++q) a.factor[q] = factor[q];
+        if (mean) for (int j = 0; j < in->d; ++j) a.mean[j] = mean[j];
+        a.factor_from_stats = 0;
+    } else {
+        a.factor_from_stats = 1;
+    }
+    return 0;
+}
+
+int obe_gather_jitter(const obe_cloud_t* in, const obe_cloud_t* out, const int64_t* idx_dev, const double* factor,
+                      const double* mean, const double* z_dev, uint64_t seed, uint32_t epoch, double a_param, int scale,
+                      void* stream) {
+    ObeResampleArgs a;
+    if (fill_resample_args(in, out, factor, mean, a_param, scale, seed, epoch, a)) return -1;
+    if (!idx_dev) return obe_fail("null ancestors%s%s");
+    a.idx_in = (const long long*)idx_dev; a.z_in = z_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t blocks = (in->n + OBE_THREADS - 1) / OBE_THREADS;
+    if (blocks > (int64_t)obe_sms() * 8) blocks = (int64_t)obe_sms() * 8;
+    const int grid = (int)blocks;
+    OBE_DIM_SWITCH(in->d, k_gather_jitter, grid, st, a)
+    OBE_LAUNCH_CHECK("k_gather_jitter");
+    return finish_resample(out, st);
+}
+
+int obe_resample_systematic(const obe_cloud_t* in, const obe_cloud_t* out, double u0, const double* factor,
+                            const double* mean, uint64_t seed, uint32_t epoch, double a_param, int scale,
+                            int64_t* idx_out_dev, double* z_out_dev, void* stream) {
+    ObeResampleArgs a;
+    if (fill_resample_args(in, out, factor, mean, a_param, scale, seed, epoch, a)) return -1;
+    if (!(u0 >= 0.0 && u0 < 1.0)) return obe_fail("u0 must be in [0,1)%s%s");
+    if (in->n >= (1ll << 31)) return obe_fail("systematic resample supports n < 2^31%s%s");
+    const Scratch s = scratch_of(in);
+    a.plan_h = s.plan_h; a.unit_start = s.unit_start; a.u0 = u0;
+    a.idx_out = (long long*)idx_out_dev; a.z_out = z_out_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, in->n, u0, s.plan_h, s.unit_start);
+    OBE_LAUNCH_CHECK("k_sys_plan");
+    int64_t max_units = a.n_tiles + (in->n + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK;
+    int64_t g = (int64_t)obe_sms() * OBE_BLOCKS_PER_SM;
+    if (g > max_units) g = max_units;
+    const int grid = (int)g;
+    OBE_DIM_SWITCH(in->d, k_sys_resample, grid, st, a)
+    OBE_LAUNCH_CHECK("k_sys_resample");
+    return finish_resample(out, st);
+}
+
+struct SelectScratch {
+    unsigned int* counter; double* part_val; long long* part_idx; double* p; double* tile_sums; double* prefix;
+};
+static SelectScratch select_scratch_of(void* base, int64_t n_settings) {
+    const int64_t nt = (n_settings + OBE_TILE - 1) / OBE_TILE;
+    char* p = (char*)base;
+    SelectScratch s;
+    s.counter = (unsigned int*)p; p += 256;
+    s.part_val = (double*)p; p += align_up((size_t)OBE_MAX_GRID * sizeof(double), 256);
+    s.part_idx = (long long*)p; p += align_up((size_t)OBE_MAX_GRID * sizeof(long long), 256);
+    s.p = (double*)p; p += align_up((size_t)n_settings * sizeof(double), 256);
+    s.tile_sums = (double*)p; p += align_up((size_t)nt * sizeof(double), 256);
+    s.prefix = (double*)p;
+    return s;
+}
+
+int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* settings_dev, int64_t lds,
+                int64_t n_settings, const double* constants, const double* var_noise, const double* stats_dev,
+                const double* cost_dev, int method, int log_form, double* utility_dev, void* best_dev,
+                void* select_scratch_dev, void* stream) {
+    if (!m || !draws_dev || !settings_dev || !utility_dev || !best_dev || !select_scratch_dev)
+        return obe_fail("null argument%s%s");
+    if (!var_noise && !stats_dev) return obe_fail("need var_noise or stats%s%s");
+    if (k < 1) return obe_fail("n_draws must be >= 1%s%s");
+    if (obe_sms() <= 0) return obe_fail("no CUDA device: this library has no CPU fallback%s%s");
+    const SelectScratch s = select_scratch_of(select_scratch_dev, n_settings);
+    ObeUtilityArgs a;
+    memset(&a, 0, sizeof(a));
+    a.draws = draws_dev; a.k = k; a.settings = settings_dev; a.lds = lds; a.n_settings = n_settings;
+    a.cost = cost_dev; a.stats = stats_dev; a.utility = utility_dev;
+    a.part_val = s.part_val; a.part_idx = s.part_idx; a.counter = s.counter;
+    a.best_idx = (long long*)best_dev; a.best_val = (double*)((char*)best_dev + 8);
+    a.noise_from_stats = var_noise ? 0 : 1;
+    a.log_form = log_form; a.method = method;
+    if (var_noise) for (int c = 0; c < m->nch; ++c) a.var_noise[c] = var_noise[c];
+    for (int j = 0; j < m->ncons; ++j) a.cons[j] = constants[j];
+    int64_t blocks = (n_settings + OBE_THREADS - 1) / OBE_THREADS;
+    if (blocks > (int64_t)obe_sms() * 8) blocks = (int64_t)obe_sms() * 8;
+    const size_t smem = (size_t)k * (m->np_model > 0 ? m->np_model : 1) * sizeof(double);
+    if (smem > 48 * 1024) return obe_fail("n_draws too large for shared memory%s%s");
+    return launch_kernel(m->f_utility, (int)blocks, smem, (cudaStream_t)stream, &a);
+}
+
+int obe_pick(const double* utility_dev, int64_t n_settings, double pickiness, double u, int64_t* idx_dev,
+             void* select_scratch_dev, void* stream) {
+    if (!utility_dev || !idx_dev || !select_scratch_dev) return obe_fail("null argument%s%s");
+    if (obe_sms() <= 0) return obe_fail("no CUDA device: this library has no CPU fallback%s%s");
+    const SelectScratch s = select_scratch_of(select_scratch_dev, n_settings);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nt = obe_num_tiles(n_settings);
+    int grid = (int)(nt < (int64_t)obe_sms() * 4 ? nt : (int64_t)obe_sms() * 4);
+    k_pick_weights<<<grid, OBE_THREADS, 0, st>>>(utility_dev, n_settings, pickiness, s.p, s.tile_sums);
+    OBE_LAUNCH_CHECK("k_pick_weights");
+    k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(s.tile_sums, nt, s.prefix, nullptr, 0, 0, n_settings);
+    OBE_LAUNCH_CHECK("k_tile_scan");
+    return draw_impl(s.p, s.prefix, n_settings, nullptr, 0, 0, &u, 1, nullptr, idx_dev, st);
+}
+
+int obe_eval_parameters(obe_model_t m, const obe_cloud_t* c, const double* setting, const double* constants,
+                        double* y_dev, int64_t ldy, void* stream) {
+    if (!m || !y_dev) return obe_fail("null argument%s%s");
+    if (check_cloud(c)) return -1;
+    if (m->d != c->d) return obe_fail("model was built for a different n_params%s%s");
+    ObeEvalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.a = c->particles_dev; a.ld = c->ld; a.n = c->n; a.y = y_dev; a.ldy = ldy;
+    for (int j = 0; j < m->ns; ++j) a.fixed[j] = setting[j];
+    for (int j = 0; j < m->ncons; ++j) a.cons[j] = constants[j];
+    int64_t blocks = (c->n + OBE_THREADS - 1) / OBE_THREADS;
+    if (blocks > (int64_t)obe_sms() * 8) blocks = (int64_t)obe_sms() * 8;
+    return launch_kernel(m->f_evalp, (int)blocks, 0, (cudaStream_t)stream, &a);
+}
+
+int obe_eval_settings(obe_model_t m, const double* settings_dev, int64_t lds, int64_t n_settings, const double* params,
+                      const double* constants, double* y_dev, int64_t ldy, void* stream) {
+    if (!m || !y_dev || !settings_dev) return obe_fail("null argument%s%s");
+    if (obe_sms() <= 0) return obe_fail("no CUDA device: this library has no CPU fallback%s%s");
+    ObeEvalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.a = settings_dev; a.ld = lds; a.n = n_settings; a.y = y_dev; a.ldy = ldy;
+    for (int j = 0; j < m->np_model; ++j) a.fixed[j] = params[j];
+    for (int j = 0; j < m->ncons; ++j) a.cons[j] = constants[j];
+    int64_t blocks = (n_settings + OBE_THREADS - 1) / OBE_THREADS;
+    if (blocks > (int64_t)obe_sms() * 8) blocks = (int64_t)obe_sms() * 8;
+    return launch_kernel(m->f_evals, (int)blocks, 0, (cudaStream_t)stream, &a);
+}
+
+}  // extern "C"

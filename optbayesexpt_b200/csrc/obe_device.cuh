@@ -1,0 +1,599 @@
+// obe_device.cuh -- device-side core of the B200 particle-filter path.
+//
+// Freestanding on purpose (no #include): this file is compiled twice -- by nvcc into
+// libobe_b200.so for the built-in model functors, and by NVRTC at run time (sm_100a cubin)
+// when a user supplies CUDA source for model_function.  Everything that depends on the
+// model functor lives here as a template body; the model-independent kernels live in
+// obe_b200.cu.
+//
+// Data layout in HBM (all fp64, SoA):
+//   particles   (d, ld)   one contiguous row per parameter, ld >= n, rows 16 B aligned
+//   weights     (n)       UN-normalised weights t_i; the normaliser lives in stats[]
+//   tile_sums   (n_tiles) sum of t over each canonical tile of OBE_TILE particles
+//   tile_prefix (n_tiles+1) exclusive prefix of tile_sums; [n_tiles] is the CDF total
+//   stats       (OBE_STATS_LEN) device-resident scalars, see OBE_ST_* below
+//
+// Reference semantics implemented by obe_update_body (optbayesexpt v1.2.0):
+//   obe_base.py:320      y = model(one_setting, particles, cons)
+//   obe_base.py:263-271  L = exp(-((y - y_meas)/sigma)**2 / 2) / sigma      (per channel)
+//   obe_base.py:451-461  product over channels (zip truncation), optional L**choke
+//   obe_noiseparam.py:110-120  sigma_c = particles[noise_index[c]]
+//   particlepdf.py:136-139     w <- nan_to_num(nan_to_num(w*L) / sum)
+//   particlepdf.py:243-244     N_eff = 1/sum(w^2)
+//   particlepdf.py:173-214     mean / covariance / std   (pivot-shifted moments, same pass)
+#ifndef OBE_DEVICE_CUH
+#define OBE_DEVICE_CUH
+
+#define OBE_TILE 2048
+#define OBE_THREADS 256
+#define OBE_EPT 8 /* elements per thread per tile */
+#define OBE_MAX_DIMS 8
+#define OBE_MAX_CH 4
+#define OBE_MAX_SET 4
+#define OBE_MAX_CONS 8
+#define OBE_MAX_DRAWS 128
+
+// stats block (doubles)
+#define OBE_ST_TOTAL 0   /* canonical sum of t = tile_prefix[n_tiles] */
+#define OBE_ST_INVS 1    /* multiplier that normalises t (1/total, or exactly 1 after a resample) */
+#define OBE_ST_SUMSQ 2   /* sum t^2 */
+#define OBE_ST_NEFF 3    /* total^2 / sumsq */
+#define OBE_ST_M1 4      /* [8]  sum t (x_j - pivot_j) */
+#define OBE_ST_M2 12     /* [36] sum t (x_j - p_j)(x_k - p_k), packed j<=k row-major */
+#define OBE_ST_PIVOT 48  /* [8]  pivot used */
+#define OBE_ST_NOISE 56  /* [4]  sum t sigma_c^2 (noise-parameter channels) */
+#define OBE_ST_SUMT 60   /* plain (non-canonical) sum of t from the same pass */
+#define OBE_ST_NZERO 61  /* number of particles zeroed by the constraint mask */
+#define OBE_STATS_LEN 64
+#define OBE_NACC_MAX (2 + OBE_MAX_DIMS + 36 + OBE_MAX_CH + 1)
+
+// likelihood source for obe_update_body
+#define OBE_SRC_MODEL 0  /* evaluate the model functor */
+#define OBE_SRC_Y 1      /* y_model supplied (pdf_update(..., y_model_data)) */
+#define OBE_SRC_LIK 2    /* likelihood supplied (ParticlePDF.bayesian_update) */
+#define OBE_SRC_NONE 3   /* no likelihood: moments / tile sums / constraint mask only */
+
+struct ObeUpdateArgs {
+    const double* particles;
+    long long ld;
+    long long n;
+    double* weights;
+    double* tile_sums;
+    double* partials;        // [gridDim.x][OBE_NACC_MAX]
+    unsigned int* counter;   // zero on entry, zero again on exit
+    double* stats;
+    const double* y_model;   // OBE_SRC_Y: (n_channels, ld_y)
+    long long ld_y;
+    const double* lik;       // OBE_SRC_LIK: (n)
+    int scale_in;            // 1: w_in = nan_to_num(t * stats[INVS]); 0: raw t
+    int write_weights;
+    int n_lik_channels;      // min(C, len(y_meas), len(sigma))  -- zip truncation
+    int use_choke;
+    unsigned int mask_le;    // bit j: weight <- 0 where x_j <= 0   (obe_noiseparam.py:67-71)
+    unsigned int mask_lt;    // bit j: weight <- 0 where x_j <  0   (lockin_of_coil.py:120-128)
+    double choke;
+    double setting[OBE_MAX_SET];
+    double cons[OBE_MAX_CONS];
+    double y_meas[OBE_MAX_CH];
+    double sigma[OBE_MAX_CH];
+    int noise_idx[OBE_MAX_CH]; // >=0: sigma_c is that particle row
+    double pivot[OBE_MAX_DIMS];
+};
+
+struct ObeUtilityArgs {
+    const double* draws;     // (d_model, K) row-major
+    int k;
+    const double* settings;  // (s, lds)
+    long long lds;
+    long long n_settings;
+    const double* cost;      // (S) or null
+    const double* stats;     // noise-parameter mode: var_n[c] = stats[NOISE+c]/stats[SUMT]
+    double* utility;         // (S) out
+    double* part_val;        // [gridDim.x]
+    long long* part_idx;     // [gridDim.x]
+    unsigned int* counter;
+    long long* best_idx;     // out
+    double* best_val;        // out
+    int noise_from_stats;
+    int log_form;
+    int method;              // 0 variance, 1 max-min
+    double var_noise[OBE_MAX_CH];
+    double cons[OBE_MAX_CONS];
+};
+
+struct ObeEvalArgs {
+    const double* a;         // particles (d, ld)  | settings (s, lds)
+    long long ld;
+    long long n;
+    double* y;               // (C, ldy)
+    long long ldy;
+    double fixed[OBE_MAX_DIMS]; // the one setting | the one parameter set
+    double cons[OBE_MAX_CONS];
+};
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+#define OBE_DBL_MAX 1.7976931348623157e308
+
+// numpy.nan_to_num defaults: nan -> 0, +inf -> DBL_MAX, -inf -> -DBL_MAX
+__device__ __forceinline__ double obe_nan_to_num(double x) {
+    if (x != x) return 0.0;
+    if (x > OBE_DBL_MAX) return OBE_DBL_MAX;
+    if (x < -OBE_DBL_MAX) return -OBE_DBL_MAX;
+    return x;
+}
+
+// IEEE ops that the compiler may not contract into FMAs: the built-in rational models use
+// these so their values are bit-identical to numpy's (which never fuses).
+__device__ __forceinline__ double obe_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double obe_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double obe_sub(double a, double b) { return __dadd_rn(a, -b); }
+__device__ __forceinline__ double obe_div(double a, double b) { return __ddiv_rn(a, b); }
+
+__device__ __forceinline__ double obe_shfl_xor(double v, int m) {
+    return __shfl_xor_sync(0xffffffffu, v, m);
+}
+__device__ __forceinline__ double obe_warp_sum(double v) {
+    v += obe_shfl_xor(v, 16);
+    v += obe_shfl_xor(v, 8);
+    v += obe_shfl_xor(v, 4);
+    v += obe_shfl_xor(v, 2);
+    v += obe_shfl_xor(v, 1);
+    return v;
+}
+
+// streaming 16-byte accesses: every particle byte is touched once per pass
+__device__ __forceinline__ double2 obe_ld2(const double* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double2 obe_ld2_rw(const double* p) {
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void obe_st2(double* p, double2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// Sum of one double over the block; result valid in every thread. `red` holds >= 8 doubles.
+__device__ __forceinline__ double obe_block_sum(double v, double* red) {
+    v = obe_warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double s = red[0];
+#pragma unroll
+    for (int w = 1; w < OBE_THREADS / 32; ++w) s += red[w];
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The fused Bayesian update.  One block walks tiles of OBE_TILE particles (grid-stride over
+// tiles), each thread owning 4 double2 columns per row so every global access is a fully
+// coalesced 16-byte vector.  Per tile it writes the new weights and the tile's weight sum;
+// across tiles it keeps sum t^2, the pivot-shifted first and second moments and the noise
+// accumulators in registers, reduced once per block at the end and combined by the last
+// block to finish (fixed order => run-to-run deterministic).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct ObeAcc {
+    double sumsq, sumt, nzero;
+    double m1[D];
+    double m2[D * (D + 1) / 2];
+    double noise[OBE_MAX_CH];
+};
+
+template <class Model, int D, int SRC>
+__device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const double (&p)[D], double w_in,
+                                                 const double (&yg)[OBE_MAX_CH], double lik_given,
+                                                 double invS, ObeAcc<D>& acc) {
+    double t;
+    if (SRC == OBE_SRC_NONE) {
+        t = w_in;
+    } else {
+        const double w = a.scale_in ? obe_nan_to_num(w_in * invS) : w_in;
+        double lik = 1.0;
+        if (SRC == OBE_SRC_LIK) {
+            lik = lik_given;
+        } else {
+            constexpr int NY = (SRC == OBE_SRC_MODEL) ? (Model::NCH > 0 ? Model::NCH : 1) : OBE_MAX_CH;
+            double y[NY];
+            if (SRC == OBE_SRC_MODEL) {
+                Model::eval(a.setting, p, a.cons, y);
+            } else {
+#pragma unroll
+                for (int c = 0; c < NY; ++c) y[c] = yg[c];
+            }
+#pragma unroll
+            for (int c = 0; c < NY; ++c) {
+                if (c < a.n_lik_channels) {
+                    double sig = a.sigma[c];
+                    const int ni = a.noise_idx[c];
+                    if (ni >= 0) {
+#pragma unroll
+                        for (int j = 0; j < D; ++j)
+                            if (j == ni) sig = p[j];
+                    }
+                    // exp(-((y - y_meas)/sigma)**2 / 2) / sigma, the reference's operation order
+                    const double q = obe_div(obe_sub(y[c], a.y_meas[c]), sig);
+                    const double g = obe_div(exp(-obe_mul(q, q) * 0.5), sig);
+                    lik = obe_mul(lik, g);
+                }
+            }
+            if (a.use_choke) lik = pow(lik, a.choke);
+        }
+        t = obe_nan_to_num(obe_mul(w, lik));
+    }
+    if (a.mask_le | a.mask_lt) {
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            if (((a.mask_le >> j) & 1u) && p[j] <= 0.0) bad = true;
+            if (((a.mask_lt >> j) & 1u) && p[j] < 0.0) bad = true;
+        }
+        if (bad) {
+            if (t != 0.0) acc.nzero += 1.0;
+            t = 0.0;
+        }
+    }
+    acc.sumsq += t * t;
+    acc.sumt += t;
+    double dx[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) dx[j] = p[j] - a.pivot[j];
+    int q = 0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const double tj = t * dx[j];
+        acc.m1[j] += tj;
+#pragma unroll
+        for (int k = j; k < D; ++k) acc.m2[q++] += tj * dx[k];
+    }
+#pragma unroll
+    for (int c = 0; c < OBE_MAX_CH; ++c) {
+        const int ni = a.noise_idx[c];
+        if (ni >= 0) {
+            double sig = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                if (j == ni) sig = p[j];
+            acc.noise[c] += t * (sig * sig);
+        }
+    }
+    return t;
+}
+
+template <class Model, int D, int SRC>
+__device__ void obe_update_body(const ObeUpdateArgs& a) {
+    __shared__ double red[OBE_THREADS / 32];
+    __shared__ double fin[OBE_NACC_MAX];
+    __shared__ unsigned int is_last;
+    constexpr int NM2 = D * (D + 1) / 2;
+    constexpr int NACC = 3 + D + NM2 + OBE_MAX_CH;
+    const int tid = threadIdx.x;
+    const long long n = a.n;
+    const long long n_tiles = (n + OBE_TILE - 1) / OBE_TILE;
+    const double invS = a.scale_in ? a.stats[OBE_ST_INVS] : 1.0;
+
+    ObeAcc<D> acc;
+    acc.sumsq = 0.0; acc.sumt = 0.0; acc.nzero = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) acc.m1[j] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NM2; ++j) acc.m2[j] = 0.0;
+#pragma unroll
+    for (int c = 0; c < OBE_MAX_CH; ++c) acc.noise[c] = 0.0;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long base = tile * OBE_TILE;
+        double tsum = 0.0;
+        if (base + OBE_TILE <= n) {
+            // ---- full tile: vector path.  4 column pairs per thread, all loads issued first.
+            double2 w2[4];
+            double2 p2[D][4];
+            double2 yv[SRC == OBE_SRC_Y ? OBE_MAX_CH : 1][4];
+            double2 lk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long i = base + k * (2 * OBE_THREADS) + 2 * tid;
+                w2[k] = obe_ld2_rw(a.weights + i);
+#pragma unroll
+                for (int j = 0; j < D; ++j) p2[j][k] = obe_ld2(a.particles + j * a.ld + i);
+                if (SRC == OBE_SRC_Y) {
+#pragma unroll
+                    for (int c = 0; c < OBE_MAX_CH; ++c) {
+                        yv[SRC == OBE_SRC_Y ? c : 0][k] = make_double2(0.0, 0.0);
+                        if (c < a.n_lik_channels) yv[SRC == OBE_SRC_Y ? c : 0][k] = obe_ld2(a.y_model + c * a.ld_y + i);
+                    }
+                }
+                if (SRC == OBE_SRC_LIK) lk[k] = obe_ld2(a.lik + i);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                double px[D], py[D], ygx[OBE_MAX_CH], ygy[OBE_MAX_CH];
+#pragma unroll
+                for (int j = 0; j < D; ++j) { px[j] = p2[j][k].x; py[j] = p2[j][k].y; }
+#pragma unroll
+                for (int c = 0; c < OBE_MAX_CH; ++c) {
+                    ygx[c] = (SRC == OBE_SRC_Y) ? yv[SRC == OBE_SRC_Y ? c : 0][k].x : 0.0;
+                    ygy[c] = (SRC == OBE_SRC_Y) ? yv[SRC == OBE_SRC_Y ? c : 0][k].y : 0.0;
+                }
+                double2 t2;
+                t2.x = obe_update_one<Model, D, SRC>(a, px, w2[k].x, ygx, (SRC == OBE_SRC_LIK) ? lk[k].x : 1.0, invS, acc);
+                t2.y = obe_update_one<Model, D, SRC>(a, py, w2[k].y, ygy, (SRC == OBE_SRC_LIK) ? lk[k].y : 1.0, invS, acc);
+                tsum += t2.x + t2.y;
+                if (a.write_weights) obe_st2(a.weights + base + k * (2 * OBE_THREADS) + 2 * tid, t2);
+            }
+        } else {
+            // ---- ragged last tile: scalar path
+            for (int k = 0; k < OBE_EPT; ++k) {
+                const long long i = base + k * OBE_THREADS + tid;
+                if (i < n) {
+                    double px[D], yg[OBE_MAX_CH];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) px[j] = a.particles[j * a.ld + i];
+                    double l0 = 1.0;
+#pragma unroll
+                    for (int c = 0; c < OBE_MAX_CH; ++c) {
+                        yg[c] = 0.0;
+                        if (SRC == OBE_SRC_Y && c < a.n_lik_channels) yg[c] = a.y_model[c * a.ld_y + i];
+                    }
+                    if (SRC == OBE_SRC_LIK) l0 = a.lik[i];
+                    const double t = obe_update_one<Model, D, SRC>(a, px, a.weights[i], yg, l0, invS, acc);
+                    tsum += t;
+                    if (a.write_weights) a.weights[i] = t;
+                }
+            }
+        }
+        const double tile_total = obe_block_sum(tsum, red);
+        if (tid == 0) a.tile_sums[tile] = tile_total;
+    }
+
+    // ---- per-block partials, then the last block to arrive combines them in block order
+    double vals[NACC];
+    vals[0] = acc.sumsq; vals[1] = acc.sumt; vals[2] = acc.nzero;
+#pragma unroll
+    for (int j = 0; j < D; ++j) vals[3 + j] = acc.m1[j];
+#pragma unroll
+    for (int j = 0; j < NM2; ++j) vals[3 + D + j] = acc.m2[j];
+#pragma unroll
+    for (int c = 0; c < OBE_MAX_CH; ++c) vals[3 + D + NM2 + c] = acc.noise[c];
+#pragma unroll
+    for (int v = 0; v < NACC; ++v) {
+        const double s = obe_block_sum(vals[v], red);
+        if (tid == 0) a.partials[(long long)blockIdx.x * OBE_NACC_MAX + v] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int v = warp; v < NACC; v += OBE_THREADS / 32) {
+        double s = 0.0;
+        for (unsigned int b = lane; b < gridDim.x; b += 32)
+            s += __ldcg(a.partials + (long long)b * OBE_NACC_MAX + v);
+        s = obe_warp_sum(s);
+        if (lane == 0) fin[v] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        a.stats[OBE_ST_SUMSQ] = fin[0];
+        a.stats[OBE_ST_SUMT] = fin[1];
+        a.stats[OBE_ST_NZERO] = fin[2];
+        for (int j = 0; j < D; ++j) { a.stats[OBE_ST_M1 + j] = fin[3 + j]; a.stats[OBE_ST_PIVOT + j] = a.pivot[j]; }
+        // packed (j<=k) for D dims -> packed layout for OBE_MAX_DIMS is NOT used: stats M2 is D-packed
+        for (int j = 0; j < NM2; ++j) a.stats[OBE_ST_M2 + j] = fin[3 + D + j];
+        for (int c = 0; c < OBE_MAX_CH; ++c) a.stats[OBE_ST_NOISE + c] = fin[3 + D + NM2 + c];
+        *a.counter = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Utility over the setting grid (obe_base.py:463-489, 628-655) fused with the argmax of
+// opt_setting (obe_base.py:748).  One thread per setting; the K drawn parameter sets sit in
+// shared memory and are re-used by every thread.  The (K,C,S) array of the reference
+// (utility_y_space) is never materialised: numpy's two-pass population variance
+// (mean = sum/K sequentially over k, var = sum((y-mean)^2)/K) is reproduced by evaluating
+// the model twice, with non-contracted IEEE ops so rational models give numpy's bits.
+// ---------------------------------------------------------------------------------------------
+template <class Model>
+__device__ void obe_utility_body(const ObeUtilityArgs& a) {
+    extern __shared__ double obe_smem[];
+    double* sdraw = obe_smem;  // [K][NP]
+    __shared__ double bval[OBE_THREADS / 32];
+    __shared__ long long bidx[OBE_THREADS / 32];
+    __shared__ unsigned int is_last;
+    const int tid = threadIdx.x;
+    const int K = a.k;
+    for (int q = tid; q < K * Model::NP; q += blockDim.x) {
+        const int k = q / Model::NP, j = q % Model::NP;
+        sdraw[q] = a.draws[(long long)j * K + k];
+    }
+    __syncthreads();
+    double var_n[Model::NCH];
+#pragma unroll
+    for (int c = 0; c < Model::NCH; ++c) {
+        var_n[c] = a.noise_from_stats ? obe_div(a.stats[OBE_ST_NOISE + c], a.stats[OBE_ST_SUMT]) : a.var_noise[c];
+    }
+    const double kd = (double)K;
+    double best = -1.0;
+    long long besti = -1;
+    bool have = false;
+    for (long long s = (long long)blockIdx.x * blockDim.x + tid; s < a.n_settings;
+         s += (long long)gridDim.x * blockDim.x) {
+        double st[Model::NS > 0 ? Model::NS : 1];
+#pragma unroll
+        for (int j = 0; j < Model::NS; ++j) st[j] = a.settings[j * a.lds + s];
+        double y[Model::NCH];
+        double u = 0.0;
+        if (a.method == 0) {
+            double mean[Model::NCH], ss[Model::NCH];
+#pragma unroll
+            for (int c = 0; c < Model::NCH; ++c) { mean[c] = 0.0; ss[c] = 0.0; }
+            for (int k = 0; k < K; ++k) {
+                Model::eval(st, sdraw + k * Model::NP, a.cons, y);
+#pragma unroll
+                for (int c = 0; c < Model::NCH; ++c) mean[c] = obe_add(mean[c], y[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < Model::NCH; ++c) mean[c] = obe_div(mean[c], kd);
+            for (int k = 0; k < K; ++k) {
+                Model::eval(st, sdraw + k * Model::NP, a.cons, y);
+#pragma unroll
+                for (int c = 0; c < Model::NCH; ++c) {
+                    const double dlt = obe_sub(y[c], mean[c]);
+                    ss[c] = obe_add(ss[c], obe_mul(dlt, dlt));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < Model::NCH; ++c) {
+                const double var_p = obe_div(ss[c], kd);
+                const double r = obe_div(var_p, var_n[c]);
+                u = obe_add(u, a.log_form ? log(obe_add(1.0, r)) : r);
+            }
+        } else {
+            // max-min (obe_base.py:520-535, 602-626): span^2 / var_n
+            double mx[Model::NCH], mn[Model::NCH];
+            for (int k = 0; k < K; ++k) {
+                Model::eval(st, sdraw + k * Model::NP, a.cons, y);
+#pragma unroll
+                for (int c = 0; c < Model::NCH; ++c) {
+                    mx[c] = (k == 0 || y[c] > mx[c]) ? y[c] : mx[c];
+                    mn[c] = (k == 0 || y[c] < mn[c]) ? y[c] : mn[c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < Model::NCH; ++c) {
+                const double span = obe_sub(mx[c], mn[c]);
+                const double r = obe_div(obe_mul(span, span), var_n[c]);
+                u = obe_add(u, a.log_form ? log(obe_add(1.0, r)) : r);
+            }
+        }
+        if (a.cost) u = obe_div(u, a.cost[s]);
+        a.utility[s] = u;
+        // np.argmax: first maximum, NaN counts as the maximum
+        const bool unan = (u != u), bnan = (best != best);
+        if (!have || (!bnan && (unan || u > best))) { best = u; besti = s; have = true; }
+    }
+    // ---- block argmax (lowest index among equals), then last-block combine
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, m);
+        const long long oi = __shfl_xor_sync(0xffffffffu, besti, m);
+        const bool onan = (ov != ov), bnan = (best != best);
+        bool take = false;
+        if (oi >= 0) {
+            if (besti < 0) take = true;
+            else if (onan && bnan) take = oi < besti;
+            else if (onan) take = true;
+            else if (bnan) take = false;
+            else take = (ov > best) || (ov == best && oi < besti);
+        }
+        if (take) { best = ov; besti = oi; }
+    }
+    if (lane == 0) { bval[warp] = best; bidx[warp] = besti; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            const double ov = bval[w];
+            const long long oi = bidx[w];
+            const bool onan = (ov != ov), bnan = (best != best);
+            bool take = false;
+            if (oi >= 0) {
+                if (besti < 0) take = true;
+                else if (onan && bnan) take = oi < besti;
+                else if (onan) take = true;
+                else if (bnan) take = false;
+                else take = (ov > best) || (ov == best && oi < besti);
+            }
+            if (take) { best = ov; besti = oi; }
+        }
+        a.part_val[blockIdx.x] = best;
+        a.part_idx[blockIdx.x] = besti;
+        __threadfence();
+        is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!is_last || tid != 0) return;
+    __threadfence();
+    best = 0.0; besti = -1;
+    for (unsigned int b = 0; b < gridDim.x; ++b) {
+        const double ov = __ldcg(a.part_val + b);
+        const long long oi = __ldcg(a.part_idx + b);
+        const bool onan = (ov != ov), bnan = (best != best);
+        bool take = false;
+        if (oi >= 0) {
+            if (besti < 0) take = true;
+            else if (onan && bnan) take = oi < besti;
+            else if (onan) take = true;
+            else if (bnan) take = false;
+            else take = (ov > best) || (ov == best && oi < besti);
+        }
+        if (take) { best = ov; besti = oi; }
+    }
+    *a.best_idx = besti;
+    *a.best_val = best;
+    *a.counter = 0u;
+}
+
+// eval_over_all_parameters (obe_base.py:298-320): y[c, i] = model(one_setting, particle_i)
+template <class Model, int D>
+__device__ void obe_eval_params_body(const ObeEvalArgs& a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double p[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) p[j] = a.a[j * a.ld + i];
+        double y[Model::NCH];
+        Model::eval(a.fixed, p, a.cons, y);
+#pragma unroll
+        for (int c = 0; c < Model::NCH; ++c) a.y[c * a.ldy + i] = y[c];
+    }
+}
+
+// eval_over_all_settings (obe_base.py:322-338): y[c, s] = model(setting_s, one_parameter_set)
+template <class Model>
+__device__ void obe_eval_settings_body(const ObeEvalArgs& a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double st[Model::NS > 0 ? Model::NS : 1];
+#pragma unroll
+        for (int j = 0; j < Model::NS; ++j) st[j] = a.a[j * a.ld + i];
+        double y[Model::NCH];
+        Model::eval(st, a.fixed, a.cons, y);
+#pragma unroll
+        for (int c = 0; c < Model::NCH; ++c) a.y[c * a.ldy + i] = y[c];
+    }
+}
+
+// A model that is never evaluated: instantiates the update body for the OBE_SRC_Y /
+// OBE_SRC_LIK / OBE_SRC_NONE sources (moments, tile sums, constraint mask).
+struct ObeNoModel {
+    enum { NS = 0, NP = 0, NCONS = 0, NCH = 0 };
+    __device__ static __forceinline__ void eval(const double*, const double*, const double*, double*) {}
+};
+
+#define OBE_DEFINE_MODEL_KERNELS(MODEL, D, SUFFIX)                                                        \
+    extern "C" __global__ void __launch_bounds__(OBE_THREADS) obe_k_update_##SUFFIX(const ObeUpdateArgs a) { \
+        obe_update_body<MODEL, D, OBE_SRC_MODEL>(a);                                                                   \
+    }                                                                                                     \
+    extern "C" __global__ void __launch_bounds__(OBE_THREADS) obe_k_evalp_##SUFFIX(const ObeEvalArgs a) {  \
+        obe_eval_params_body<MODEL, D>(a);                                                                \
+    }
+
+#define OBE_DEFINE_GRID_KERNELS(MODEL, SUFFIX)                                                             \
+    extern "C" __global__ void __launch_bounds__(OBE_THREADS) obe_k_utility_##SUFFIX(const ObeUtilityArgs a) { \
+        obe_utility_body<MODEL>(a);                                                                       \
+    }                                                                                                     \
+    extern "C" __global__ void __launch_bounds__(OBE_THREADS) obe_k_evals_##SUFFIX(const ObeEvalArgs a) {  \
+        obe_eval_settings_body<MODEL>(a);                                                                 \
+    }
+
+#endif  // OBE_DEVICE_CUH

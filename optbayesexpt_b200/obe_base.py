@@ -1,0 +1,358 @@
+"""OptBayesExpt on the GPU: the experiment-design engine of the reference's
+``optbayesexpt/obe_base.py`` (v1.2.0) with the same constructor, methods and attributes.
+
+``pdf_update`` is one fused kernel pass over the resident cloud (model -> Gaussian likelihood
+-> weight product -> tile sums, N_eff and moments) plus a tiny prefix kernel; ``opt_setting`` /
+``good_setting`` draw ``N_DRAWS`` particles through the tile-level CDF, evaluate them over the
+whole setting grid and pick the argmax (or a pickiness-weighted draw) on the device.  Only the
+measurement record goes to the GPU each cycle, and only the stats block (64 doubles) and the
+chosen index come back.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .models import DeviceModel, builtin
+from .particlepdf import ParticlePDF
+
+DEFAULT_N_DRAWS = 30
+rng = np.random.default_rng()
+
+
+class LazyDeviceArray:
+    """numpy-convertible handle returned by pdf_update: materialises (D2H) only when looked at."""
+
+    def __init__(self, getter):
+        self._getter = getter
+
+    def __array__(self, dtype=None, copy=None):
+        arr = self._getter()
+        return arr if dtype is None else arr.astype(dtype)
+
+    def __getitem__(self, item):
+        return self._getter()[item]
+
+    def __len__(self):
+        return len(self._getter())
+
+    @property
+    def shape(self):
+        return self._getter().shape
+
+    def tolist(self):
+        return self._getter().tolist()
+
+    def __repr__(self):
+        return f'LazyDeviceArray({self._getter()!r})'
+
+
+class OptBayesExpt(ParticlePDF):
+    """Sequential Bayesian experiment design (obe_base.py:21-272).
+
+    ``measurement_model`` must be a :class:`~optbayesexpt_b200.models.DeviceModel` (or the name
+    of a built-in): a Python callable cannot run inside a kernel and there is no CPU path.
+    """
+
+    def __init__(self, measurement_model, setting_values, parameter_samples, constants,
+                 n_draws=DEFAULT_N_DRAWS, choke=None, use_jit=True, utility_method='variance_approx',
+                 selection_method='optimal', pickiness=15, default_noise_std=1.0, **kwargs):
+        if isinstance(measurement_model, str):
+            measurement_model = builtin(measurement_model)
+        if not isinstance(measurement_model, DeviceModel):
+            raise TypeError('measurement_model must be a DeviceModel (optbayesexpt_b200.models.builtin(...) or '
+                            'cuda_source(...)): a Python callable cannot run on the GPU and there is no CPU fallback')
+        ParticlePDF.__init__(self, parameter_samples, use_jit=use_jit, **kwargs)
+        torch = self._torch
+        self.model_function = measurement_model
+        self._model_function = measurement_model
+        self._model = measurement_model.handle(self.n_dims)
+        self.setting_values = setting_values
+        # obe_base.py:174-180: all setting combinations, first knob slowest
+        self.allsettings = np.array([s.flatten() for s in
+                                     np.meshgrid(*[np.asarray(v, dtype=np.float64) for v in setting_values],
+                                                 indexing='ij')])
+        if self.allsettings.shape[0] != measurement_model.n_settings:
+            raise ValueError(f'model takes {measurement_model.n_settings} settings, got {self.allsettings.shape[0]}')
+        self.setting_indices = np.arange(len(self.allsettings[0]), dtype=int)
+        n_set = len(self.setting_indices)
+        self._lds = n_set + (n_set & 1)
+        self._settings_dev = torch.zeros((self.allsettings.shape[0], self._lds), dtype=torch.float64,
+                                         device=self._buf.device)
+        self._settings_dev[:, :n_set].copy_(torch.from_numpy(np.ascontiguousarray(self.allsettings)))
+        self.cons = constants
+        if len(tuple(constants)) < measurement_model.n_constants:
+            raise ValueError(f'model takes {measurement_model.n_constants} constants')
+        self._cons_arr = _lib.darr(list(constants)[:_lib.MAX_CONSTANTS], _lib.MAX_CONSTANTS)
+        self.choke = choke
+        self.N_DRAWS = n_draws
+        self.pickiness = pickiness
+        self.measurement_results = []
+        self.last_setting_index = 0
+        self.n_channels = measurement_model.n_channels
+        self.utility_y_space = np.array([])   # never materialised on the device path
+        self.default_noise_std = np.ones((self.n_channels, 1)) * default_noise_std
+
+        utilitymethods = ['variance_approx', 'pseudo_utility', 'full_kld_utility', 'max_min']
+        if utility_method == 'variance_approx':
+            self._utility_code = 0
+        elif utility_method == 'max_min':
+            self._utility_code = 1
+        elif utility_method in ('pseudo_utility', 'full_kld_utility'):
+            raise NotImplementedError(f'utility method {utility_method} has no device kernel yet '
+                                      '(no CPU fallback is provided)')
+        else:
+            raise SyntaxError(f'Unknown utility method, {utility_method}. '
+                              f'Valid utility methods are: {utilitymethods}')
+        self.utility_method = utility_method
+        #: use log(1 + var/sigma^2) instead of the linear form of obe_base.py:654
+        self.utility_log_form = False
+
+        selection_methods = ['optimal', 'good', 'random']
+        if selection_method == 'optimal':
+            self.get_setting = self.opt_setting
+        elif selection_method == 'good':
+            self.get_setting = self.good_setting
+        elif selection_method == 'random':
+            self.get_setting = self.random_setting
+        else:
+            raise SyntaxError(f'Unknown selection_method, {selection_method}. '
+                              f'Valid selection methods are: {selection_methods}')
+
+        self._utility_dev = torch.zeros(n_set, dtype=torch.float64, device=self._buf.device)
+        self._best_dev = torch.zeros(2, dtype=torch.int64, device=self._buf.device)
+        self._pick_dev = torch.zeros(1, dtype=torch.int64, device=self._buf.device)
+        self._select_scratch = torch.zeros(int(self._lib.obe_select_scratch_bytes(n_set)), dtype=torch.uint8,
+                                           device=self._buf.device)
+        self._cost_dev = None
+        self._best_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+
+    # -- the reference rebinds `parameters` to `particles` in pdf_update (obe_base.py:185,395);
+    #    here it is a live alias, which removes the stale-alias quirk after resample()/set_pdf()
+    @property
+    def parameters(self):
+        return self.particles
+
+    def set_n_draws(self, n_draws=None):
+        """obe_base.py:274-296."""
+        if n_draws == 'default':
+            self.N_DRAWS = DEFAULT_N_DRAWS
+        elif n_draws:
+            self.N_DRAWS = n_draws
+        return self.N_DRAWS
+
+    def set_pdf(self, samples, weights=None):
+        noise_index = self._noise_index
+        ParticlePDF.set_pdf(self, samples, weights)
+        self._noise_index = noise_index
+        self._model = self.model_function.handle(self.n_dims)
+
+    # ------------------------------------------------------------------------------------------
+    # model evaluation in both orientations (obe_base.py:298-338)
+    # ------------------------------------------------------------------------------------------
+    def eval_over_all_parameters(self, onesettingset):
+        y = self._eval_parameters_dev(onesettingset)
+        return y[:, :self.n_particles].cpu().numpy()
+
+    def _eval_parameters_dev(self, onesettingset):
+        y = self._torch.empty((self.n_channels, self._buf.ld), dtype=self._torch.float64, device=self._buf.device)
+        self._check(self._lib.obe_eval_parameters(self._model, self._cs(),
+                                                  _lib.darr(np.atleast_1d(onesettingset), _lib.MAX_SETTINGS),
+                                                  self._cons_arr, C.c_void_p(y.data_ptr()), self._buf.ld,
+                                                  self._stream()))
+        return y
+
+    def eval_over_all_settings(self, oneparamset):
+        n_set = len(self.setting_indices)
+        y = self._torch.empty((self.n_channels, self._lds), dtype=self._torch.float64, device=self._buf.device)
+        self._check(self._lib.obe_eval_settings(self._model, C.c_void_p(self._settings_dev.data_ptr()), self._lds,
+                                                n_set, _lib.darr(np.atleast_1d(oneparamset), _lib.MAX_PARAMS),
+                                                self._cons_arr, C.c_void_p(y.data_ptr()), self._lds, self._stream()))
+        return y[:, :n_set].cpu().numpy()
+
+    # ------------------------------------------------------------------------------------------
+    # inference half (obe_base.py:340-461)
+    # ------------------------------------------------------------------------------------------
+    def _likelihood_spec(self, measurement_record):
+        """(y_meas[C], sigma[C] | None, noise_index | None, n_lik) -- the zip() of
+        obe_base.py:453-455 truncates to the shortest of (channels, y_meas, sigma)."""
+        onesetting, y_meas, sigma = measurement_record[0], measurement_record[1], measurement_record[2]
+        y_meas = np.atleast_1d(np.asarray(y_meas, dtype=np.float64))
+        sigma = np.atleast_1d(np.asarray(sigma, dtype=np.float64))
+        n_lik = min(self.n_channels, len(y_meas), len(sigma))
+        return y_meas[:n_lik], sigma[:n_lik], None, n_lik
+
+    def pdf_update(self, measurement_record, y_model_data=None):
+        """Bayesian update of the cloud from one measurement (obe_base.py:340-399).
+
+        Returns ``(particles, particle_weights)`` as lazy, numpy-convertible handles: nothing is
+        copied off the GPU unless the caller looks at them.
+        """
+        onesetting = measurement_record[0]
+        y_meas, sigma, noise_index, n_lik = self._likelihood_spec(measurement_record)
+        use_choke = 0 if self.choke is None else 1
+        choke = 0.0 if self.choke is None else float(self.choke)
+        pivot = _lib.darr(self._pivot, _lib.MAX_PARAMS)
+        if y_model_data is None:
+            self._check(self._lib.obe_update(self._model, self._cs(),
+                                             _lib.darr(np.atleast_1d(onesetting), _lib.MAX_SETTINGS), self._cons_arr,
+                                             _lib.darr(y_meas, _lib.MAX_CHANNELS),
+                                             None if sigma is None else _lib.darr(sigma, _lib.MAX_CHANNELS),
+                                             _lib.iarr(noise_index), n_lik, use_choke, choke, pivot, self._stream()))
+        else:
+            y = self._torch.zeros((self.n_channels, self._buf.ld), dtype=self._torch.float64,
+                                  device=self._buf.device)
+            y[:, :self.n_particles].copy_(self._torch.as_tensor(
+                np.ascontiguousarray(np.asarray(y_model_data, dtype=np.float64).reshape(self.n_channels, -1))))
+            self._check(self._lib.obe_update_from_y(self._cs(), C.c_void_p(y.data_ptr()), self._buf.ld,
+                                                    self.n_channels, _lib.darr(y_meas, _lib.MAX_CHANNELS),
+                                                    None if sigma is None else _lib.darr(sigma, _lib.MAX_CHANNELS),
+                                                    _lib.iarr(noise_index), n_lik, use_choke, choke, pivot,
+                                                    self._stream()))
+        self._after_update()
+        if self.just_resampled:
+            self.enforce_parameter_constraints()
+        return (LazyDeviceArray(lambda: self.particles), LazyDeviceArray(lambda: self.particle_weights))
+
+    def run_cycle_async(self, measurement_record, resample=True, select=True):
+        """One full cycle -- pdf_update, (forced) systematic resample, utility + argmax -- enqueued
+        on the current stream with NO host synchronisation: the resample decision is the
+        caller's, the chosen index stays in ``best_index_dev``.  For pipelined / benchmark use;
+        ``pdf_update`` + ``opt_setting`` is the synchronous, reference-shaped API."""
+        onesetting = measurement_record[0]
+        y_meas, sigma, noise_index, n_lik = self._likelihood_spec(measurement_record)
+        self._check(self._lib.obe_update(self._model, self._cs(),
+                                         _lib.darr(np.atleast_1d(onesetting), _lib.MAX_SETTINGS), self._cons_arr,
+                                         _lib.darr(y_meas, _lib.MAX_CHANNELS),
+                                         None if sigma is None else _lib.darr(sigma, _lib.MAX_CHANNELS),
+                                         _lib.iarr(noise_index), n_lik, 0 if self.choke is None else 1,
+                                         0.0 if self.choke is None else float(self.choke),
+                                         _lib.darr(self._pivot, _lib.MAX_PARAMS), self._stream()))
+        self._invalidate()
+        self._stats = None
+        self._moments_valid = True      # on the device: the resample kernel reads them there
+        self._weights_lazy = True
+        if resample:
+            if self.resampling != 'systematic':
+                raise ValueError('run_cycle_async needs resampling="systematic"')
+            self.resample()
+            self.just_resampled = True
+        if select:
+            self._utility_dev_run()
+
+    @property
+    def best_index_dev(self):
+        """Device tensor: [argmax index, bit pattern of its utility] of the last utility pass."""
+        return self._best_dev
+
+    def enforce_parameter_constraints(self):
+        """Stub, as in the reference (obe_base.py:401-416).  Device-side constraints are data:
+        see ``_apply_constraint_masks``."""
+        pass
+
+    def _apply_constraint_masks(self, mask_le=0, mask_lt=0):
+        """weight <- 0 where x_j <= 0 (mask_le bit j) or x_j < 0 (mask_lt bit j), renormalise."""
+        self._refresh(mask_le=mask_le, mask_lt=mask_lt, renormalise=1)
+        self._weights_lazy = True
+        self._invalidate()
+
+    def likelihood(self, y_model, measurement_record):
+        """Likelihood of the record for every particle (obe_base.py:418-461), on the device."""
+        torch = self._torch
+        y_meas, sigma, noise_index, n_lik = self._likelihood_spec(measurement_record)
+        tmp = self._buf.empty_like(share_particles=True)
+        tmp.weights.fill_(1.0)
+        tmp.stats[_lib.ST_INVS] = 1.0
+        y = torch.zeros((self.n_channels, self._buf.ld), dtype=torch.float64, device=self._buf.device)
+        y[:, :self.n_particles].copy_(torch.as_tensor(
+            np.ascontiguousarray(np.asarray(y_model, dtype=np.float64).reshape(self.n_channels, -1))))
+        use_choke = 0 if self.choke is None else 1
+        self._check(self._lib.obe_update_from_y(C.byref(tmp.struct()), C.c_void_p(y.data_ptr()), self._buf.ld,
+                                                self.n_channels, _lib.darr(y_meas, _lib.MAX_CHANNELS),
+                                                None if sigma is None else _lib.darr(sigma, _lib.MAX_CHANNELS),
+                                                _lib.iarr(noise_index), n_lik, use_choke,
+                                                0.0 if self.choke is None else float(self.choke),
+                                                _lib.darr(self._pivot, _lib.MAX_PARAMS), self._stream()))
+        return tmp.weights[:self.n_particles].cpu().numpy()
+
+    # ------------------------------------------------------------------------------------------
+    # design half (obe_base.py:463-805)
+    # ------------------------------------------------------------------------------------------
+    def y_var_noise_model(self):
+        return self.yvar_noise_model()
+
+    def yvar_noise_model(self):
+        """Constant noise variance per channel, (C,1) (obe_base.py:542-564)."""
+        return self.default_noise_std ** 2
+
+    def cost_estimate(self):
+        """1.0, or an array over settings in subclasses (obe_base.py:566-577)."""
+        return 1.0
+
+    def _noise_from_stats(self):
+        return False
+
+    def _utility_dev_run(self):
+        """draws -> utility over the grid -> argmax, all on the device; returns nothing."""
+        torch = self._torch
+        draws = self._randdraw_dev(self.N_DRAWS)
+        n_set = len(self.setting_indices)
+        if self._noise_from_stats():
+            self._ensure_moments()
+            var_noise = None
+            stats_ptr = C.c_void_p(self._buf.stats.data_ptr())
+        else:
+            var_noise = _lib.darr(np.asarray(self.yvar_noise_model(), dtype=np.float64).reshape(-1),
+                                  _lib.MAX_CHANNELS)
+            stats_ptr = None
+        cost = self.cost_estimate()
+        cost_ptr = None
+        if not (np.isscalar(cost) and float(cost) == 1.0):
+            cost_arr = np.broadcast_to(np.asarray(cost, dtype=np.float64), (n_set,))
+            if self._cost_dev is None:
+                self._cost_dev = torch.empty(n_set, dtype=torch.float64, device=self._buf.device)
+            self._cost_dev.copy_(torch.from_numpy(np.ascontiguousarray(cost_arr)))
+            cost_ptr = C.c_void_p(self._cost_dev.data_ptr())
+        self._check(self._lib.obe_utility(self._model, C.c_void_p(draws.data_ptr()), int(self.N_DRAWS),
+                                          C.c_void_p(self._settings_dev.data_ptr()), self._lds, n_set, self._cons_arr,
+                                          var_noise, stats_ptr, cost_ptr, self._utility_code,
+                                          1 if self.utility_log_form else 0,
+                                          C.c_void_p(self._utility_dev.data_ptr()),
+                                          C.c_void_p(self._best_dev.data_ptr()),
+                                          C.c_void_p(self._select_scratch.data_ptr()), self._stream()))
+
+    def utility(self):
+        """Utility over all settings as a numpy array (obe_base.py:579-655)."""
+        self._utility_dev_run()
+        return self._utility_dev.cpu().numpy()
+
+    utility_variance = utility
+    utility_max_min = utility
+
+    def opt_setting(self):
+        """Setting with the maximum utility (obe_base.py:733-756)."""
+        self._utility_dev_run()
+        self._best_host.copy_(self._best_dev, non_blocking=True)
+        self._torch.cuda.current_stream().synchronize()
+        bestindex = int(self._best_host[0])
+        self.last_setting_index = bestindex
+        return tuple(self.allsettings[:, bestindex])
+
+    def good_setting(self, pickiness=None):
+        """Setting drawn with probability ~ utility**pickiness (obe_base.py:758-789)."""
+        if pickiness is None:
+            pickiness = self.pickiness
+        self._utility_dev_run()
+        u = float(self.rng.random())
+        self._check(self._lib.obe_pick(C.c_void_p(self._utility_dev.data_ptr()), len(self.setting_indices),
+                                       float(pickiness), u, C.c_void_p(self._pick_dev.data_ptr()),
+                                       C.c_void_p(self._select_scratch.data_ptr()), self._stream()))
+        goodindex = int(self._pick_dev.item())
+        self.last_setting_index = goodindex
+        return tuple(self.allsettings[:, goodindex])
+
+    def random_setting(self):
+        """Uniformly random setting (obe_base.py:791-805)."""
+        settingindex = rng.choice(self.setting_indices)
+        self.last_setting_index = settingindex
+        return self.allsettings[:, settingindex]
