@@ -308,7 +308,7 @@ class OptBayesExpt(ParticlePDF):
         cost = self.cost_estimate()
         cost_ptr = None
         if not (np.isscalar(cost) and float(cost) == 1.0):
-            cost_arr = np.broadcast_to(np.asarray(cost, dtype=np.float64), (n_set,))
+            cost_arr = np.array(np.broadcast_to(np.asarray(cost, dtype=np.float64), (n_set,)))
             if self._cost_dev is None:
                 self._cost_dev = torch.empty(n_set, dtype=torch.float64, device=self._buf.device)
             self._cost_dev.copy_(torch.from_numpy(np.ascontiguousarray(cost_arr)))

@@ -136,11 +136,11 @@ def test_ref_optbayesexpt_likelihood_and_update(obe):           # tests/test_opt
 
 
 def test_ref_zinference_infer(obe):                             # tests/test_zinference.py:89-108
-    n, true_mean, true_sigma = 5000, 2.0, 1.5
+    n, true_mean, true_sigma = 5000, 1.0, 1.0
     src = '__device__ void ident(const double* s, const double* p, const double* c, double* y) { y[0] = p[0]; }'
-    model = obe.cuda_source(src, 'ident', n_settings=0, n_params=1)
+    model = obe.cuda_source(src, 'ident', n_settings=1, n_params=1, n_constants=1)
     x = np.linspace(-5, 5, n)
-    eng = obe.OptBayesExpt(model, (), (x, np.ones(n) * true_sigma), ())
+    eng = obe.OptBayesExpt(model, (0,), (x, np.ones(n) * true_sigma), (0,))
     eng.tuning_parameters['resample_threshold'] = 0
     eng.pdf_update(((), true_mean, true_sigma))
     post = np.exp(-(true_mean - x) ** 2 / (2 * true_sigma ** 2)) / (np.sqrt(2 * np.pi) * true_sigma)
@@ -234,7 +234,8 @@ def test_update_matches_oracle(obe, name, n):
     w2, _ = _oracle_update(sc, inp, inp['prior'], w1, rec2)
     eng.pdf_update(rec2)
     wclose(eng.particle_weights, w2, 1e-12, 'second update')
-    assert_allclose(eng.n_eff(), orc.n_effective(w2), rtol=1e-12)
+    if np.sum(w2) > 0:                                           # a lone particle can underflow to 0/0
+        assert_allclose(eng.n_eff(), orc.n_effective(w2), rtol=1e-12)
     if n > 1:
         assert_allclose(eng.mean(), orc.weighted_mean(inp['prior'], w2), rtol=1e-12)
         cov_close(eng.covariance(), orc.weighted_covariance_longdouble(inp['prior'], w2), 1e-12)
