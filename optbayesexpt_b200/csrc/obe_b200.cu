@@ -90,24 +90,42 @@ static Scratch scratch_of(const obe_cloud_t* c) {
 // generic (model-free) update kernels: y supplied / likelihood supplied / refresh
 // ---------------------------------------------------------------------------------------------
 template <int D, int SRC>
-__global__ void __launch_bounds__(OBE_THREADS) k_update_generic(const ObeUpdateArgs a) {
+__global__ void __launch_bounds__(OBE_UPDATE_THREADS, 1) k_update_generic(const ObeUpdateArgs a) {
     obe_update_body<ObeNoModel, D, SRC>(a);
+}
+// dynamic shared memory of the update kernel for (d, source): mirrors ObeStage<NROWS>
+static size_t update_smem_bytes(int d, int src) {
+    const int nrows = 1 + d + (src == OBE_SRC_Y ? OBE_MAX_CH : 0) + (src == OBE_SRC_LIK ? 1 : 0);
+    const int elems = nrows <= 4 ? 2048 : (nrows <= 8 ? 1024 : 512);
+    const int bytes = nrows * elems * 8;
+    int nst = OBE_SMEM_BUDGET / bytes;
+    if (nst > 4) nst = 4;
+    return (size_t)nst * bytes + 1024;
+}
+static int launch_update_kernel(const void* f, int d, int src, const ObeUpdateArgs& a, int grid, cudaStream_t st) {
+    const size_t smem = update_smem_bytes(d, src);
+    cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return obe_fail("cudaFuncSetAttribute(max dynamic smem): %s%s", cudaGetErrorString(e));
+    void* params[1] = {const_cast<ObeUpdateArgs*>(&a)};
+    e = cudaLaunchKernel(f, dim3(grid), dim3(OBE_UPDATE_THREADS), params, smem, st);
+    if (e != cudaSuccess) return obe_fail("launch update kernel: %s%s", cudaGetErrorString(e));
+    return 0;
 }
 template <int SRC>
 static int launch_generic(int d, const ObeUpdateArgs& a, int grid, cudaStream_t st) {
+    const void* f = nullptr;
     switch (d) {
-        case 1: k_update_generic<1, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
-        case 2: k_update_generic<2, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
-        case 3: k_update_generic<3, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
-        case 4: k_update_generic<4, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
-        case 5: k_update_generic<5, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
-        case 6: k_update_generic<6, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
-        case 7: k_update_generic<7, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
-        case 8: k_update_generic<8, SRC><<<grid, OBE_THREADS, 0, st>>>(a); break;
+        case 1: f = (const void*)k_update_generic<1, SRC>; break;
+        case 2: f = (const void*)k_update_generic<2, SRC>; break;
+        case 3: f = (const void*)k_update_generic<3, SRC>; break;
+        case 4: f = (const void*)k_update_generic<4, SRC>; break;
+        case 5: f = (const void*)k_update_generic<5, SRC>; break;
+        case 6: f = (const void*)k_update_generic<6, SRC>; break;
+        case 7: f = (const void*)k_update_generic<7, SRC>; break;
+        case 8: f = (const void*)k_update_generic<8, SRC>; break;
         default: return obe_fail("n_params must be 1..8%s%s");
     }
-    OBE_LAUNCH_CHECK("k_update_generic");
-    return 0;
+    return launch_update_kernel(f, d, SRC, a, grid, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -115,7 +133,9 @@ static int launch_generic(int d, const ObeUpdateArgs& a, int grid, cudaStream_t 
 // ---------------------------------------------------------------------------------------------
 #define OBE_SCAN_THREADS 1024
 
-// exclusive block scan of one double per thread (sum); returns exclusive prefix, total in *tot
+// Block-wide exclusive scans (1024 threads) of one value per thread; the per-array kernels below
+// walk their array in coalesced chunks of 1024 with a running carry, so the association order
+// (carry + (warp base + lane prefix)) depends only on the element index.
 __device__ __forceinline__ double block_excl_sum_1024(double v, double* sm /*34*/, double* tot) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double x = v;
@@ -147,7 +167,8 @@ __device__ __forceinline__ double block_excl_sum_1024(double v, double* sm /*34*
     return base + ex;
 }
 
-__device__ __forceinline__ long long block_excl_max_1024(long long v, long long* sm /*33*/) {
+// inclusive running max; *tot = max over the block
+__device__ __forceinline__ long long block_incl_max_1024(long long v, long long* sm /*34*/, long long* tot) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long x = v;
 #pragma unroll
@@ -168,15 +189,14 @@ __device__ __forceinline__ long long block_excl_max_1024(long long v, long long*
         long long ex = __shfl_up_sync(0xffffffffu, xs, 1);
         if (lane == 0) ex = -1;
         sm[lane] = ex;
+        if (lane == 31) sm[32] = xs;
     }
     __syncthreads();
-    const long long base = sm[warp];
-    long long ex = __shfl_up_sync(0xffffffffu, x, 1);
-    if (lane == 0) ex = -1;
-    return max(base, ex);
+    *tot = sm[32];
+    return max(sm[warp], x);
 }
 
-__device__ __forceinline__ int block_excl_isum_1024(int v, int* sm /*33*/, int* tot) {
+__device__ __forceinline__ int block_excl_isum_1024(int v, int* sm /*34*/, int* tot) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int x = v;
 #pragma unroll
@@ -203,24 +223,25 @@ __device__ __forceinline__ int block_excl_isum_1024(int v, int* sm /*33*/, int* 
     return sm[warp] + (x - v);
 }
 
-// tile_prefix[k] = sum of tile_sums[0..k) in a fixed association (blocked per thread, then a
-// block scan); tile_prefix[n_tiles] is THE total every CDF consumer divides by.
+// tile_prefix[k] = sum of tile_sums[0..k) in a fixed association; tile_prefix[n_tiles] is THE
+// total every CDF consumer divides by.
 __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_tile_scan(const double* __restrict__ tile_sums,
                                                                 long long n_tiles, double* __restrict__ prefix,
                                                                 double* __restrict__ stats, int renormalise,
                                                                 int uniform, long long n) {
     __shared__ double sm[34];
     const int t = threadIdx.x;
-    const long long per = (n_tiles + OBE_SCAN_THREADS - 1) / OBE_SCAN_THREADS;
-    const long long lo = min((long long)t * per, n_tiles), hi = min(lo + per, n_tiles);
-    double s = 0.0;
-    for (long long k = lo; k < hi; ++k) s += tile_sums[k];
-    double total;
-    double run = block_excl_sum_1024(s, sm, &total);
-    for (long long k = lo; k < hi; ++k) {
-        prefix[k] = run;
-        run += tile_sums[k];
+    double carry = 0.0;
+    for (long long base = 0; base < n_tiles; base += OBE_SCAN_THREADS) {
+        const long long k = base + t;
+        const double v = (k < n_tiles) ? tile_sums[k] : 0.0;
+        double tot;
+        const double ex = block_excl_sum_1024(v, sm, &tot);
+        if (k < n_tiles) prefix[k] = carry + ex;
+        carry += tot;
+        __syncthreads();
     }
+    const double total = carry;
     if (t == 0) {
         prefix[n_tiles] = total;
         if (stats) {
@@ -315,14 +336,16 @@ __device__ __forceinline__ void tile_cdf_blocked(const double* __restrict__ w, c
     const long long base = k * OBE_TILE;
     tile_load_blocked(w, base, n, v);
     tile_scan_blocked(v, incl, sm);
-    const double p0 = prefix[k], p1 = prefix[k + 1];
+    const double p0 = prefix[k];
     const long long last = min(n, base + OBE_TILE) - 1;
+    const long long i0 = base + (long long)threadIdx.x * OBE_EPT;
 #pragma unroll
-    for (int e = 0; e < OBE_EPT; ++e) {
-        const long long i = base + (long long)threadIdx.x * OBE_EPT + e;
-        double c = obe_div(obe_add(p0, incl[e]), total);
-        if (i >= last) c = obe_div(p1, total);
-        cn[e] = c;
+    for (int e = 0; e < OBE_EPT; ++e) cn[e] = obe_div(obe_add(p0, incl[e]), total);
+    if (i0 + OBE_EPT > last) {                 // only the thread(s) at the end of the tile
+        const double c1 = obe_div(prefix[k + 1], total);
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; ++e)
+            if (i0 + e >= last) cn[e] = c1;
     }
 }
 
@@ -422,24 +445,38 @@ __device__ __forceinline__ void philox4x32_10(unsigned int c0, unsigned int c1, 
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-__device__ __forceinline__ double u53(unsigned int lo, unsigned int hi) {
-    const unsigned long long x = ((unsigned long long)hi << 32) | lo;
-    return ((double)(x >> 11) + 0.5) * 1.1102230246251565e-16;  // 2^-53
+__device__ __forceinline__ float obe_sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
+// 24-bit uniform in (0,1): ((x >> 8) + 0.5) * 2^-24, exact in fp32
+__device__ __forceinline__ float u24(unsigned int x) {
+    return ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-8f;
+}
+// Standard normals for the Liu-West jitter of output slot `slot`: one Philox4x32-10 call yields
+// four 24-bit uniforms -> two Box-Muller pairs evaluated in fp32 (the jitter is a random nudge of
+// scale sqrt(1-a^2)*sigma; its *value* needs no fp64 accuracy, its arithmetic after this point is
+// fp64).  ctr = (slot_lo, slot_hi, call, epoch), key = seed.
 template <int D>
 __device__ __forceinline__ void device_normals(long long slot, unsigned long long seed, unsigned int epoch,
                                                double (&z)[D]) {
 #pragma unroll
-    for (int c = 0; c < (D + 1) / 2; ++c) {
+    for (int c = 0; c < (D + 3) / 4; ++c) {
         unsigned int r[4];
         philox4x32_10((unsigned int)(slot & 0xffffffffll), (unsigned int)((unsigned long long)slot >> 32),
                       (unsigned int)c, epoch, (unsigned int)(seed & 0xffffffffull), (unsigned int)(seed >> 32), r);
-        const double u1 = u53(r[0], r[1]), u2 = u53(r[2], r[3]);
-        const double rad = sqrt(-2.0 * log(u1));
-        double sn, cs;
-        sincospi(2.0 * u2, &sn, &cs);
-        z[2 * c] = rad * cs;
-        if (2 * c + 1 < D) z[2 * c + 1] = rad * sn;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (4 * c + 2 * h < D) {
+                // MUFU.LG2 / MUFU.RSQ-class approximations: ~1e-6 absolute, ample for a random nudge
+                const float rad = obe_sqrt_approx(-2.0f * __logf(u24(r[2 * h])));
+                float sn, cs;
+                __sincosf(6.2831853071795865f * u24(r[2 * h + 1]), &sn, &cs);
+                z[4 * c + 2 * h] = (double)(rad * cs);
+                if (4 * c + 2 * h + 1 < D) z[4 * c + 2 * h + 1] = (double)(rad * sn);
+            }
+        }
     }
 }
 
@@ -550,17 +587,20 @@ __global__ void __launch_bounds__(OBE_THREADS) k_gather_jitter(const ObeResample
 }
 
 // ---- systematic comb --------------------------------------------------------------------------
-// #{i in [0,n) : (i + u0) * inv_n < c}; the comb value is two IEEE ops (add, mul), monotone in i
-__device__ __forceinline__ long long comb_count(double c, double u0, double inv_n, long long n, double nd) {
-    const double est = ceil(c * nd - u0);
-    long long i = est <= 0.0 ? 0 : (est >= nd ? n : (long long)est);
-    while (i > 0 && obe_mul(obe_add((double)(i - 1), u0), inv_n) >= c) --i;
-    while (i < n && obe_mul(obe_add((double)i, u0), inv_n) < c) ++i;
+// #{i in [0,n) : (i + u0) * inv_n < c}; the comb value is two IEEE ops (add, mul), monotone in i.
+// Works on integer-valued doubles (exact below 2^53) to stay off the int<->fp conversion path.
+__device__ __forceinline__ double comb_count_d(double c, double u0, double inv_n, double nd) {
+    double i = ceil(c * nd - u0);
+    i = (i < 0.0) ? 0.0 : i;
+    i = (i > nd) ? nd : i;
+    while (i > 0.0 && obe_mul(obe_add(i - 1.0, u0), inv_n) >= c) i -= 1.0;
+    while (i < nd && obe_mul(obe_add(i, u0), inv_n) < c) i += 1.0;
     return i;
 }
 
 #define OBE_OUT_CHUNK 2048
-// plan: H[k] = first output slot owned by tile k (monotone), unit_start[k] = first work unit
+// plan: H[k] = first output slot owned by tile k (monotone), unit_start[k] = first work unit of
+// tile k, one unit = up to OBE_OUT_CHUNK output slots of one input tile.
 __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __restrict__ prefix, long long n_tiles,
                                                                long long n, double u0, long long* __restrict__ H,
                                                                int* __restrict__ unit_start) {
@@ -569,57 +609,73 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
     const int t = threadIdx.x;
     const double total = prefix[n_tiles];
     const double nd = (double)n, inv_n = 1.0 / nd;
-    const long long cnt = n_tiles + 1;
-    const long long per = (cnt + OBE_SCAN_THREADS - 1) / OBE_SCAN_THREADS;
-    const long long lo = min((long long)t * per, cnt), hi = min(lo + per, cnt);
-    long long mx = -1;
-    for (long long k = lo; k < hi; ++k) {
-        long long h = (k == 0) ? 0 : (k == n_tiles ? n : comb_count(obe_div(prefix[k], total), u0, inv_n, n, nd));
-        mx = max(mx, h);
-        H[k] = mx;  // running max inside the thread's range
+    long long carry = -1;
+    for (long long base = 0; base <= n_tiles; base += OBE_SCAN_THREADS) {
+        const long long k = base + t;
+        long long h = -1;
+        if (k <= n_tiles)
+            h = (k == 0) ? 0 : (k == n_tiles ? n : (long long)comb_count_d(obe_div(prefix[k], total), u0, inv_n, nd));
+        long long tot;
+        const long long inc = block_incl_max_1024(h, sml, &tot);
+        if (k <= n_tiles) H[k] = min(max(inc, carry), n);
+        carry = max(carry, tot);
+        __syncthreads();
     }
-    const long long before = block_excl_max_1024(mx, sml);
-    for (long long k = lo; k < hi; ++k) H[k] = min(max(H[k], before), n);
-    __syncthreads();
-    __threadfence_block();
-    // units per tile
-    const long long per2 = (n_tiles + OBE_SCAN_THREADS - 1) / OBE_SCAN_THREADS;
-    const long long lo2 = min((long long)t * per2, n_tiles), hi2 = min(lo2 + per2, n_tiles);
-    int s = 0;
-    for (long long k = lo2; k < hi2; ++k) s += (int)((H[k + 1] - H[k] + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK);
-    int tot;
-    int run = block_excl_isum_1024(s, smi, &tot);
-    for (long long k = lo2; k < hi2; ++k) {
-        unit_start[k] = run;
-        run += (int)((H[k + 1] - H[k] + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK);
+    int icarry = 0;
+    for (long long base = 0; base < n_tiles; base += OBE_SCAN_THREADS) {
+        const long long k = base + t;
+        int units = 0;
+        if (k < n_tiles) units = (int)((H[k + 1] - H[k] + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK);
+        int tot;
+        const int ex = block_excl_isum_1024(units, smi, &tot);
+        if (k < n_tiles) unit_start[k] = icarry + ex;
+        icarry += tot;
+        __syncthreads();
     }
-    if (t == 0) unit_start[n_tiles] = tot;
+    if (t == 0) unit_start[n_tiles] = icarry;
 }
 
+// One work unit = (input tile k, chunk of <= 2048 consecutive output slots owned by that tile).
+//  1. canonical CDF of the tile (blocked scan) -> end slot hi_j of every particle (comb count),
+//     made monotone by a running max and clamped to the tile's slot range [H_k, H_k+1)
+//  2. every particle that owns at least one slot of the chunk marks the first of them with its
+//     index; a max-scan over the chunk's slots turns the marks into the ancestor of every slot
+//  3. slots are walked in coalesced order: gather the ancestor (L1-resident tile), jitter, store
 template <int D>
 __global__ void __launch_bounds__(OBE_THREADS) k_sys_resample(const ObeResampleArgs a) {
     __shared__ double sF[D * D];
     __shared__ double sMean[D];
     __shared__ double sm[8];
     __shared__ int smx[OBE_THREADS / 32];
-    __shared__ int rel_hi[OBE_TILE];
+    __shared__ __align__(16) unsigned short anc_s[OBE_OUT_CHUNK];
     setup_factor<D>(a, sF, sMean);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double total = a.prefix[a.n_tiles];
     const double nd = (double)a.n, inv_n = 1.0 / nd, wv = 1.0 / nd;
     const int n_units = a.unit_start[a.n_tiles];
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        // tile owning this unit: largest k with unit_start[k] <= unit
-        long long lo = 0, hi = a.n_tiles;  // first k with unit_start[k] > unit
+    // contiguous range of units per block: one binary search, then a forward walk over the tiles
+    const int per_block = (n_units + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int unit_lo = min((int)blockIdx.x * per_block, n_units);
+    const int unit_hi = min(unit_lo + per_block, n_units);
+    int k32 = 0;
+    if (unit_lo < unit_hi) {
+        int lo = 0, hi = (int)a.n_tiles;       // first k with unit_start[k] > unit_lo
         while (lo < hi) {
-            const long long mid = (lo + hi) >> 1;
-            if (a.unit_start[mid] <= unit) lo = mid + 1; else hi = mid;
+            const int mid = (lo + hi) >> 1;
+            if (a.unit_start[mid] <= unit_lo) lo = mid + 1; else hi = mid;
         }
-        const long long k = lo - 1;
+        k32 = lo - 1;
+    }
+    for (int unit = unit_lo; unit < unit_hi; ++unit) {
+        while (a.unit_start[k32 + 1] <= unit) ++k32;      // largest k with unit_start[k] <= unit
+        const long long k = k32;
         const long long Hk = a.plan_h[k], Hk1 = a.plan_h[k + 1];
-        const long long o_begin = Hk + (long long)(unit - a.unit_start[k]) * OBE_OUT_CHUNK;
-        const long long o_end = min(o_begin + OBE_OUT_CHUNK, Hk1);
-        // canonical CDF of the tile -> first output slot past each element
+        const int span = (int)(Hk1 - Hk);
+        const int rel_begin = (unit - a.unit_start[k]) * OBE_OUT_CHUNK;
+        const int rel_end = min(rel_begin + OBE_OUT_CHUNK, span);
+        // clear the marks (8 per thread, 16-byte store)
+        *reinterpret_cast<uint4*>(&anc_s[tid * OBE_EPT]) = make_uint4(0u, 0u, 0u, 0u);
+        // ---- 1. end slot of every particle of the tile
         double cn[OBE_EPT];
         tile_cdf_blocked(a.w_in, a.prefix, k, a.n, total, cn, sm);
         const long long base = k * OBE_TILE;
@@ -629,10 +685,13 @@ __global__ void __launch_bounds__(OBE_THREADS) k_sys_resample(const ObeResampleA
 #pragma unroll
         for (int e = 0; e < OBE_EPT; ++e) {
             const long long i = base + (long long)tid * OBE_EPT + e;
-            long long h;
-            if (i >= last) h = Hk1;
-            else h = min(max(comb_count(cn[e], a.u0, inv_n, a.n, nd), Hk), Hk1);
-            run = max(run, (int)(h - Hk));
+            int h;
+            if (i >= last) h = span;
+            else {
+                const long long hl = (long long)comb_count_d(cn[e], a.u0, inv_n, nd) - Hk;
+                h = (int)min(max(hl, 0ll), (long long)span);
+            }
+            run = max(run, h);
             r[e] = run;
         }
         int x = run;
@@ -644,19 +703,58 @@ __global__ void __launch_bounds__(OBE_THREADS) k_sys_resample(const ObeResampleA
         int ex = __shfl_up_sync(0xffffffffu, x, 1);
         if (lane == 0) ex = 0;
         if (lane == 31) smx[warp] = x;
-        __syncthreads();
+        __syncthreads();                       // also orders the clearing of anc_s before the marks
         for (int w2 = 0; w2 < warp; ++w2) ex = max(ex, smx[w2]);
+        // ---- 2. mark the first owned slot inside the chunk
+        int prev = ex;                         // end slot of the previous particle
 #pragma unroll
-        for (int e = 0; e < OBE_EPT; ++e) rel_hi[tid * OBE_EPT + e] = max(r[e], ex);
-        __syncthreads();
-        for (long long o = o_begin + tid; o < o_end; o += OBE_THREADS) {
-            const int rel = (int)(o - Hk);
-            int l2 = 0, h2 = OBE_TILE;  // first j with rel_hi[j] > rel
-            while (l2 < h2) {
-                const int mid = (l2 + h2) >> 1;
-                if (rel_hi[mid] <= rel) l2 = mid + 1; else h2 = mid;
+        for (int e = 0; e < OBE_EPT; ++e) {
+            const int end = max(r[e], ex);
+            if (end > prev) {
+                const int head = max(prev, rel_begin);
+                if (head < rel_end && end > rel_begin) anc_s[head - rel_begin] = (unsigned short)(tid * OBE_EPT + e);
             }
-            const long long anc = min(base + l2, last);
+            prev = end;
+        }
+        __syncthreads();
+        // max-scan of the marks over the chunk's slots (blocked: 8 consecutive slots per thread)
+        int m[OBE_EPT];
+        {
+            const uint4 raw = *reinterpret_cast<const uint4*>(&anc_s[tid * OBE_EPT]);
+            const unsigned int wds[4] = {raw.x, raw.y, raw.z, raw.w};
+            int runm = 0;
+#pragma unroll
+            for (int e = 0; e < OBE_EPT; ++e) {
+                const int v = (int)((wds[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
+                runm = max(runm, v);
+                m[e] = runm;
+            }
+            int xm = runm;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, xm, o);
+                if (lane >= o) xm = max(xm, y);
+            }
+            int exm = __shfl_up_sync(0xffffffffu, xm, 1);
+            if (lane == 0) exm = 0;
+            __syncthreads();                   // smx is reused
+            if (lane == 31) smx[warp] = xm;
+            __syncthreads();
+            for (int w2 = 0; w2 < warp; ++w2) exm = max(exm, smx[w2]);
+            unsigned int packed[4];
+#pragma unroll
+            for (int e = 0; e < OBE_EPT; e += 2) {
+                const unsigned int a0 = (unsigned int)max(m[e], exm), a1v = (unsigned int)max(m[e + 1], exm);
+                packed[e >> 1] = a0 | (a1v << 16);
+            }
+            *reinterpret_cast<uint4*>(&anc_s[tid * OBE_EPT]) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        __syncthreads();
+        // ---- 3. outputs in coalesced order
+        const int n_out = rel_end - rel_begin;
+        for (int q = tid; q < n_out; q += OBE_THREADS) {
+            const long long o = Hk + rel_begin + q;
+            const long long anc = min(base + (long long)anc_s[q], last);
             double xv[D], z[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) xv[j] = __ldg(a.pin + j * a.ld_in + anc);
@@ -717,7 +815,7 @@ __global__ void __launch_bounds__(OBE_THREADS) k_pick_weights(const double* __re
 // models: built-in instantiations + NVRTC-compiled user functors
 // ---------------------------------------------------------------------------------------------
 template <class M, int D>
-__global__ void __launch_bounds__(OBE_THREADS) k_update_model(const ObeUpdateArgs a) {
+__global__ void __launch_bounds__(OBE_UPDATE_THREADS, 1) k_update_model(const ObeUpdateArgs a) {
     obe_update_body<M, D, OBE_SRC_MODEL>(a);
 }
 template <class M, int D>
@@ -951,8 +1049,9 @@ static int check_cloud(const obe_cloud_t* c) {
     return 0;
 }
 static int update_grid(const obe_cloud_t* c) {
+    // persistent: one warp-specialised CTA per SM (its stage ring takes most of the shared memory)
     const int64_t nt = obe_num_tiles(c->n);
-    int64_t g = (int64_t)obe_sms() * OBE_BLOCKS_PER_SM;
+    int64_t g = (int64_t)obe_sms();
     if (g > nt) g = nt;
     if (g > OBE_MAX_GRID) g = OBE_MAX_GRID;
     return (int)g;
@@ -980,10 +1079,11 @@ static int fill_likelihood_args(ObeUpdateArgs& a, int d, int nch_avail, const do
     a.n_lik_channels = n_lik;
     for (int cidx = 0; cidx < n_lik; ++cidx) {
         a.y_meas[cidx] = y_meas[cidx];
-        a.sigma[cidx] = sigma ? sigma[cidx] : 1.0;
+        a.inv_sigma[cidx] = sigma ? 1.0 / sigma[cidx] : 1.0;
         if (noise_index) {
             if (noise_index[cidx] < 0 || noise_index[cidx] >= d) return obe_fail("noise_index out of range%s%s");
             a.noise_idx[cidx] = noise_index[cidx];
+            a.n_noise = cidx + 1;
         }
     }
     a.use_choke = use_choke; a.choke = choke;
@@ -1016,7 +1116,7 @@ int obe_update(obe_model_t m, const obe_cloud_t* c, const double* setting, const
     for (int j = 0; j < m->ncons; ++j) a.cons[j] = constants[j];
     if (fill_likelihood_args(a, c->d, m->nch, y_meas, sigma, noise_index, n_lik_channels, use_choke, choke)) return -1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (launch_kernel(m->f_update, update_grid(c), 0, st, &a)) return -1;
+    if (launch_update_kernel(m->f_update, c->d, OBE_SRC_MODEL, a, update_grid(c), st)) return -1;
     return finish_update(c, 1, st);
 }
 
@@ -1056,7 +1156,7 @@ int obe_refresh(const obe_cloud_t* c, uint32_t mask_le, uint32_t mask_lt, const 
     a.write_weights = (mask_le | mask_lt) ? 1 : 0;
     a.mask_le = mask_le; a.mask_lt = mask_lt;
     if (noise_index)
-        for (int j = 0; j < n_noise && j < OBE_MAX_CH; ++j) a.noise_idx[j] = noise_index[j];
+        for (int j = 0; j < n_noise && j < OBE_MAX_CH; ++j) { a.noise_idx[j] = noise_index[j]; a.n_noise = j + 1; }
     cudaStream_t st = (cudaStream_t)stream;
     if (launch_generic<OBE_SRC_NONE>(c->d, a, update_grid(c), st)) return -1;
     return finish_update(c, renormalise, st);

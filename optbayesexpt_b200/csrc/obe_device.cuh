@@ -75,8 +75,9 @@ struct ObeUpdateArgs {
     double setting[OBE_MAX_SET];
     double cons[OBE_MAX_CONS];
     double y_meas[OBE_MAX_CH];
-    double sigma[OBE_MAX_CH];
-    int noise_idx[OBE_MAX_CH]; // >=0: sigma_c is that particle row
+    double inv_sigma[OBE_MAX_CH]; // 1/sigma_c for a known sigma
+    int noise_idx[OBE_MAX_CH];    // >=0: sigma_c is that particle row
+    int n_noise;                  // number of noise-parameter channels (0: known sigma)
     double pivot[OBE_MAX_DIMS];
 };
 
@@ -172,19 +173,120 @@ __device__ __forceinline__ double obe_block_sum(double v, double* red) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// The fused Bayesian update.  One block walks tiles of OBE_TILE particles (grid-stride over
-// tiles), each thread owning 4 double2 columns per row so every global access is a fully
-// coalesced 16-byte vector.  Per tile it writes the new weights and the tile's weight sum;
-// across tiles it keeps sum t^2, the pivot-shifted first and second moments and the noise
-// accumulators in registers, reduced once per block at the end and combined by the last
-// block to finish (fixed order => run-to-run deterministic).
+// mbarrier / bulk-copy (TMA engine, 1-D) primitives
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned obe_smem_addr(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void obe_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(obe_smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void obe_mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void obe_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(obe_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void obe_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(obe_smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void obe_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "OBE_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra OBE_DONE_%=;\n\t"
+        "bra OBE_WAIT_%=;\n\t"
+        "OBE_DONE_%=:\n\t"
+        "}" ::"r"(obe_smem_addr(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy through the TMA engine; completion is signalled on `bar`
+__device__ __forceinline__ void obe_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                             unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            obe_smem_addr(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(obe_smem_addr(bar))
+        : "memory");
+}
+__device__ __forceinline__ void obe_named_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// The fused Bayesian update: a persistent, warp-specialised kernel, one CTA per SM.
+//   producer role (thread 0)   for every stage, 1-D bulk copies (TMA engine, cp.async.bulk +
+//                              mbarrier complete_tx) of the weight row and the D particle rows of
+//                              the next stage of particles into a ring of shared-memory stages,
+//                              NST-1 stages ahead -- HBM stays busy while the FP64 pipe works
+//   consumers (all 16 warps)   16-byte conflict-free LDS of their columns, release the stage,
+//                              model -> likelihood -> weight product -> moments in registers,
+//                              coalesced 16-byte stores of the new weights, tile sums through a
+//                              barrier.  (A dedicated 17th producer warp would cap the kernel at
+//                              96 registers/thread -- 5 warps on one SM sub-partition -- and spill.)
+// Across tiles each consumer keeps sum t^2, the pivot-shifted first/second moments and the noise
+// accumulators in registers; they are reduced once per block and combined by the last block to
+// finish in a fixed order (run-to-run deterministic).
+// ---------------------------------------------------------------------------------------------
+#define OBE_CONSUMER_WARPS 16
+#define OBE_CONSUMER_THREADS (OBE_CONSUMER_WARPS * 32)
+#define OBE_UPDATE_THREADS OBE_CONSUMER_THREADS
+#define OBE_SMEM_BUDGET (200 * 1024)
+
 template <int D>
 struct ObeAcc {
     double sumsq, sumt, nzero;
     double m1[D];
     double m2[D * (D + 1) / 2];
     double noise[OBE_MAX_CH];
+};
+
+// cheap numpy.nan_to_num: nan -> 0, +-inf -> +-DBL_MAX
+__device__ __forceinline__ double obe_nan_to_num_fast(double x) {
+    // inf or nan <=> exponent field all ones: one integer test on the fast path
+    if ((((unsigned)__double2hiint(x)) & 0x7fffffffu) >= 0x7ff00000u)
+        x = (x != x) ? 0.0 : (x > 0.0 ? OBE_DBL_MAX : -OBE_DBL_MAX);
+    return x;
+}
+
+// exp(x) for x <= 0 (the Gaussian log-likelihood): k = rint(x/ln2), r = x - k ln2 in two FMAs,
+// degree-13 Taylor polynomial on |r| <= ln2/2 (truncation 4e-18), scaling by 2^k through the
+// exponent field.  ~2 ulp; results below 2^-1022 flush to 0 (exact would be a denormal weight).
+__device__ __forceinline__ double obe_exp_nonpos(double x) {
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);   // 1.5 * 2^52: round to int
+    int k = __double2loint(t);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;                                   // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 1.984126984126984e-04);
+    p = fma(p, r, 1.3888888888888889e-03);
+    p = fma(p, r, 8.333333333333333e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    k = max(k, -1022);
+    const double scale = __hiloint2double((k + 1023) << 20, 0);
+    return (x < -708.0) ? 0.0 : p * scale;      // also catches -inf; NaN propagates through p
+}
+
+// Models may provide a cheaper evaluation for the update pass (reciprocal of a constant hoisted
+// out of the particle loop).  Default: the exact functor.
+template <class Model>
+struct ObeUpdateEval {
+    __device__ static __forceinline__ void eval(const double* s, const double* p, const double* c, double* y) {
+        Model::eval(s, p, c, y);
+    }
 };
 
 template <class Model, int D, int SRC>
@@ -195,7 +297,7 @@ __device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const d
     if (SRC == OBE_SRC_NONE) {
         t = w_in;
     } else {
-        const double w = a.scale_in ? obe_nan_to_num(w_in * invS) : w_in;
+        const double w = a.scale_in ? obe_nan_to_num_fast(w_in * invS) : w_in;
         double lik = 1.0;
         if (SRC == OBE_SRC_LIK) {
             lik = lik_given;
@@ -203,7 +305,7 @@ __device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const d
             constexpr int NY = (SRC == OBE_SRC_MODEL) ? (Model::NCH > 0 ? Model::NCH : 1) : OBE_MAX_CH;
             double y[NY];
             if (SRC == OBE_SRC_MODEL) {
-                Model::eval(a.setting, p, a.cons, y);
+                ObeUpdateEval<Model>::eval(a.setting, p, a.cons, y);
             } else {
 #pragma unroll
                 for (int c = 0; c < NY; ++c) y[c] = yg[c];
@@ -211,24 +313,27 @@ __device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const d
 #pragma unroll
             for (int c = 0; c < NY; ++c) {
                 if (c < a.n_lik_channels) {
-                    double sig = a.sigma[c];
-                    const int ni = a.noise_idx[c];
-                    if (ni >= 0) {
+                    // exp(-((y - y_meas)/sigma)**2 / 2) / sigma  (obe_base.py:264-271) with the
+                    // division by sigma done as a multiplication by its reciprocal: the host's
+                    // 1/sigma for a known sigma, one in-kernel reciprocal for a noise parameter
+                    double inv_sig = a.inv_sigma[c];
+                    if (a.n_noise > 0) {
+                        const int ni = a.noise_idx[c];
+                        double sig = 1.0;
 #pragma unroll
                         for (int j = 0; j < D; ++j)
                             if (j == ni) sig = p[j];
+                        inv_sig = 1.0 / sig;
                     }
-                    // exp(-((y - y_meas)/sigma)**2 / 2) / sigma, the reference's operation order
-                    const double q = obe_div(obe_sub(y[c], a.y_meas[c]), sig);
-                    const double g = obe_div(exp(-obe_mul(q, q) * 0.5), sig);
-                    lik = obe_mul(lik, g);
+                    const double q = (y[c] - a.y_meas[c]) * inv_sig;
+                    lik *= obe_exp_nonpos(-0.5 * (q * q)) * inv_sig;
                 }
             }
             if (a.use_choke) lik = pow(lik, a.choke);
         }
-        t = obe_nan_to_num(obe_mul(w, lik));
+        t = obe_nan_to_num_fast(w * lik);
     }
-    if (a.mask_le | a.mask_lt) {
+    if (SRC == OBE_SRC_NONE && (a.mask_le | a.mask_lt)) {      // constraint masks ride on the refresh pass only
         bool bad = false;
 #pragma unroll
         for (int j = 0; j < D; ++j) {
@@ -253,32 +358,111 @@ __device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const d
 #pragma unroll
         for (int k = j; k < D; ++k) acc.m2[q++] += tj * dx[k];
     }
+    if (a.n_noise > 0) {
 #pragma unroll
-    for (int c = 0; c < OBE_MAX_CH; ++c) {
-        const int ni = a.noise_idx[c];
-        if (ni >= 0) {
-            double sig = 0.0;
+        for (int c = 0; c < OBE_MAX_CH; ++c) {
+            const int ni = a.noise_idx[c];
+            if (ni >= 0) {
+                double sig = 0.0;
 #pragma unroll
-            for (int j = 0; j < D; ++j)
-                if (j == ni) sig = p[j];
-            acc.noise[c] += t * (sig * sig);
+                for (int j = 0; j < D; ++j)
+                    if (j == ni) sig = p[j];
+                acc.noise[c] += t * (sig * sig);
+            }
         }
     }
     return t;
 }
 
+// stage geometry as a function of the number of rows staged per particle
+template <int NROWS>
+struct ObeStage {
+    static constexpr int ELEMS = NROWS <= 4 ? 2048 : (NROWS <= 8 ? 1024 : 512);
+    static constexpr int BYTES = NROWS * ELEMS * 8;
+    static constexpr int NSTAGES_RAW = OBE_SMEM_BUDGET / BYTES;
+    static constexpr int NSTAGES = NSTAGES_RAW > 4 ? 4 : NSTAGES_RAW;
+    static constexpr int SUB = OBE_TILE / ELEMS;                 // stages per canonical tile
+    static constexpr int EPT = ELEMS / OBE_CONSUMER_THREADS;     // elements per consumer thread per stage
+    static constexpr int SMEM = NSTAGES * BYTES + 1024;
+};
+
+template <int D, int SRC>
+struct ObeUpdateRows {
+    static constexpr int NROWS = 1 + D + (SRC == OBE_SRC_Y ? OBE_MAX_CH : 0) + (SRC == OBE_SRC_LIK ? 1 : 0);
+};
+
 template <class Model, int D, int SRC>
 __device__ void obe_update_body(const ObeUpdateArgs& a) {
-    __shared__ double red[OBE_THREADS / 32];
-    __shared__ double fin[OBE_NACC_MAX];
-    __shared__ unsigned int is_last;
+    constexpr int NROWS = ObeUpdateRows<D, SRC>::NROWS;
+    using ST = ObeStage<NROWS>;
+    constexpr int SE = ST::ELEMS, NST = ST::NSTAGES, SUB = ST::SUB, EPT = ST::EPT;
     constexpr int NM2 = D * (D + 1) / 2;
     constexpr int NACC = 3 + D + NM2 + OBE_MAX_CH;
+    extern __shared__ __align__(128) unsigned char obe_dyn_smem[];
+    double* stage_base = reinterpret_cast<double*>(obe_dyn_smem);
+    unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(obe_dyn_smem + NST * ST::BYTES);
+    unsigned long long* empty_bar = full_bar + NST;
+    __shared__ double red[2][OBE_CONSUMER_WARPS];
+    __shared__ double accsm[OBE_CONSUMER_WARPS][OBE_NACC_MAX];
+    __shared__ double fin[OBE_NACC_MAX];
+    __shared__ unsigned int is_last;
+
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const long long n = a.n;
     const long long n_tiles = (n + OBE_TILE - 1) / OBE_TILE;
-    const double invS = a.scale_in ? a.stats[OBE_ST_INVS] : 1.0;
+    // rows actually staged: weights, D particle rows, then the optional extras
+    const int n_rows_live = 1 + D + (SRC == OBE_SRC_Y ? a.n_lik_channels : 0) + (SRC == OBE_SRC_LIK ? 1 : 0);
 
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            obe_mbar_init(full_bar + s, 1);
+            obe_mbar_init(empty_bar + s, OBE_CONSUMER_WARPS);
+        }
+        obe_mbar_fence_init();
+    }
+    __syncthreads();
+
+    // ---- producer role: thread 0 issues the bulk copies of iteration p (tile, sub-stage) into
+    //      ring slot p % NST, NST-1 iterations ahead of the consumers
+    const long long my_tiles = (n_tiles > (long long)blockIdx.x)
+                                   ? (n_tiles - 1 - (long long)blockIdx.x) / (long long)gridDim.x + 1 : 0;
+    const unsigned total_iters = (unsigned)(my_tiles * SUB);
+    auto produce = [&](unsigned p) {
+        if (p >= total_iters) return;
+        const int s = p % NST;
+        const unsigned k = p / NST;
+        const long long tile = (long long)blockIdx.x + (long long)(p / SUB) * (long long)gridDim.x;
+        const long long base = tile * OBE_TILE + (long long)(p % SUB) * SE;
+        long long cnt = a.ld - base;
+        if (cnt > SE) cnt = SE;
+        obe_mbar_wait(empty_bar + s, (k & 1u) ^ 1u);
+        if (cnt <= 0) {                               // sub-stage past the end of a ragged tile
+            obe_mbar_arrive(full_bar + s);
+            return;
+        }
+        const unsigned row_bytes = (unsigned)cnt * 8u;
+        obe_mbar_expect_tx(full_bar + s, row_bytes * (unsigned)n_rows_live);
+        double* dst = stage_base + (size_t)s * (NROWS * SE);
+        obe_bulk_g2s(dst, a.weights + base, row_bytes, full_bar + s);
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            obe_bulk_g2s(dst + (1 + j) * SE, a.particles + j * a.ld + base, row_bytes, full_bar + s);
+        if (SRC == OBE_SRC_Y) {
+            for (int c = 0; c < a.n_lik_channels; ++c)
+                obe_bulk_g2s(dst + (1 + D + c) * SE, a.y_model + c * a.ld_y + base, row_bytes, full_bar + s);
+        }
+        if (SRC == OBE_SRC_LIK) obe_bulk_g2s(dst + (1 + D) * SE, a.lik + base, row_bytes, full_bar + s);
+    };
+    if (tid == 0) {
+        for (unsigned p = 0; p + 1 < (unsigned)NST; ++p) produce(p);
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const int ct = tid;                   // every thread is a consumer
+    const int cwarp = warp;
+    const double invS = a.scale_in ? a.stats[OBE_ST_INVS] : 1.0;
+    const bool write_weights = a.write_weights != 0;
     ObeAcc<D> acc;
     acc.sumsq = 0.0; acc.sumt = 0.0; acc.nzero = 0.0;
 #pragma unroll
@@ -288,69 +472,94 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
 #pragma unroll
     for (int c = 0; c < OBE_MAX_CH; ++c) acc.noise[c] = 0.0;
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long base = tile * OBE_TILE;
+    unsigned it = 0;
+    unsigned tile_par = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tile_par ^= 1u) {
         double tsum = 0.0;
-        if (base + OBE_TILE <= n) {
-            // ---- full tile: vector path.  4 column pairs per thread, all loads issued first.
-            double2 w2[4];
-            double2 p2[D][4];
-            double2 yv[SRC == OBE_SRC_Y ? OBE_MAX_CH : 1][4];
-            double2 lk[4];
+#pragma unroll 1
+        for (int sub = 0; sub < SUB; ++sub, ++it) {
+            const int s = it % NST;
+            const unsigned k = it / NST;
+            const long long base = tile * OBE_TILE + (long long)sub * SE;
+            const bool stage_full = (base + SE <= n);
+            if (tid == 0) produce(it + NST - 1);
+            obe_mbar_wait(full_bar + s, k & 1u);
+            const double* src = stage_base + (size_t)s * (NROWS * SE);
+            // this thread's columns -> registers
+            double wv[EPT], pv[D][EPT], yv[SRC == OBE_SRC_Y ? OBE_MAX_CH : 1][EPT], lv[EPT];
+            if (EPT >= 2) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const long long i = base + k * (2 * OBE_THREADS) + 2 * tid;
-                w2[k] = obe_ld2_rw(a.weights + i);
+                for (int q = 0; q < EPT / 2; ++q) {
+                    const int e = 2 * (ct + q * OBE_CONSUMER_THREADS);
+                    const double2 w2 = *reinterpret_cast<const double2*>(src + e);
+                    wv[2 * q] = w2.x; wv[2 * q + 1] = w2.y;
 #pragma unroll
-                for (int j = 0; j < D; ++j) p2[j][k] = obe_ld2(a.particles + j * a.ld + i);
+                    for (int j = 0; j < D; ++j) {
+                        const double2 p2 = *reinterpret_cast<const double2*>(src + (1 + j) * SE + e);
+                        pv[j][2 * q] = p2.x; pv[j][2 * q + 1] = p2.y;
+                    }
+                    if (SRC == OBE_SRC_Y) {
+#pragma unroll
+                        for (int c = 0; c < OBE_MAX_CH; ++c) {
+                            double2 y2 = make_double2(0.0, 0.0);
+                            if (c < a.n_lik_channels) y2 = *reinterpret_cast<const double2*>(src + (1 + D + c) * SE + e);
+                            yv[SRC == OBE_SRC_Y ? c : 0][2 * q] = y2.x; yv[SRC == OBE_SRC_Y ? c : 0][2 * q + 1] = y2.y;
+                        }
+                    }
+                    if (SRC == OBE_SRC_LIK) {
+                        const double2 l2 = *reinterpret_cast<const double2*>(src + (1 + D) * SE + e);
+                        lv[2 * q] = l2.x; lv[2 * q + 1] = l2.y;
+                    }
+                }
+            } else {
+                wv[0] = src[ct];
+#pragma unroll
+                for (int j = 0; j < D; ++j) pv[j][0] = src[(1 + j) * SE + ct];
                 if (SRC == OBE_SRC_Y) {
 #pragma unroll
-                    for (int c = 0; c < OBE_MAX_CH; ++c) {
-                        yv[SRC == OBE_SRC_Y ? c : 0][k] = make_double2(0.0, 0.0);
-                        if (c < a.n_lik_channels) yv[SRC == OBE_SRC_Y ? c : 0][k] = obe_ld2(a.y_model + c * a.ld_y + i);
+                    for (int c = 0; c < OBE_MAX_CH; ++c)
+                        yv[SRC == OBE_SRC_Y ? c : 0][0] = (c < a.n_lik_channels) ? src[(1 + D + c) * SE + ct] : 0.0;
+                }
+                if (SRC == OBE_SRC_LIK) lv[0] = src[(1 + D) * SE + ct];
+            }
+            __syncwarp();
+            if (lane == 0) obe_mbar_arrive(empty_bar + s);   // stage can be refilled
+            // compute + store
+#pragma unroll
+            for (int q = 0; q < (EPT >= 2 ? EPT / 2 : 1); ++q) {
+                const long long i0 = base + (EPT >= 2 ? 2 * (ct + q * OBE_CONSUMER_THREADS) : ct);
+                double tv[2] = {0.0, 0.0};
+#pragma unroll
+                for (int h = 0; h < (EPT >= 2 ? 2 : 1); ++h) {
+                    if (stage_full || i0 + h < n) {
+                        double px[D], yg[OBE_MAX_CH];
+#pragma unroll
+                        for (int j = 0; j < D; ++j) px[j] = pv[j][(EPT >= 2 ? 2 * q : 0) + h];
+#pragma unroll
+                        for (int c = 0; c < OBE_MAX_CH; ++c)
+                            yg[c] = (SRC == OBE_SRC_Y) ? yv[SRC == OBE_SRC_Y ? c : 0][(EPT >= 2 ? 2 * q : 0) + h] : 0.0;
+                        tv[h] = obe_update_one<Model, D, SRC>(a, px, wv[(EPT >= 2 ? 2 * q : 0) + h], yg,
+                                                              (SRC == OBE_SRC_LIK) ? lv[(EPT >= 2 ? 2 * q : 0) + h] : 1.0,
+                                                              invS, acc);
                     }
                 }
-                if (SRC == OBE_SRC_LIK) lk[k] = obe_ld2(a.lik + i);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                double px[D], py[D], ygx[OBE_MAX_CH], ygy[OBE_MAX_CH];
-#pragma unroll
-                for (int j = 0; j < D; ++j) { px[j] = p2[j][k].x; py[j] = p2[j][k].y; }
-#pragma unroll
-                for (int c = 0; c < OBE_MAX_CH; ++c) {
-                    ygx[c] = (SRC == OBE_SRC_Y) ? yv[SRC == OBE_SRC_Y ? c : 0][k].x : 0.0;
-                    ygy[c] = (SRC == OBE_SRC_Y) ? yv[SRC == OBE_SRC_Y ? c : 0][k].y : 0.0;
-                }
-                double2 t2;
-                t2.x = obe_update_one<Model, D, SRC>(a, px, w2[k].x, ygx, (SRC == OBE_SRC_LIK) ? lk[k].x : 1.0, invS, acc);
-                t2.y = obe_update_one<Model, D, SRC>(a, py, w2[k].y, ygy, (SRC == OBE_SRC_LIK) ? lk[k].y : 1.0, invS, acc);
-                tsum += t2.x + t2.y;
-                if (a.write_weights) obe_st2(a.weights + base + k * (2 * OBE_THREADS) + 2 * tid, t2);
-            }
-        } else {
-            // ---- ragged last tile: scalar path
-            for (int k = 0; k < OBE_EPT; ++k) {
-                const long long i = base + k * OBE_THREADS + tid;
-                if (i < n) {
-                    double px[D], yg[OBE_MAX_CH];
-#pragma unroll
-                    for (int j = 0; j < D; ++j) px[j] = a.particles[j * a.ld + i];
-                    double l0 = 1.0;
-#pragma unroll
-                    for (int c = 0; c < OBE_MAX_CH; ++c) {
-                        yg[c] = 0.0;
-                        if (SRC == OBE_SRC_Y && c < a.n_lik_channels) yg[c] = a.y_model[c * a.ld_y + i];
-                    }
-                    if (SRC == OBE_SRC_LIK) l0 = a.lik[i];
-                    const double t = obe_update_one<Model, D, SRC>(a, px, a.weights[i], yg, l0, invS, acc);
-                    tsum += t;
-                    if (a.write_weights) a.weights[i] = t;
+                tsum += tv[0] + tv[1];
+                if (write_weights) {
+                    if (EPT >= 2 && (stage_full || i0 + 1 < n)) obe_st2(a.weights + i0, make_double2(tv[0], tv[1]));
+                    else if (i0 < n) a.weights[i0] = tv[0];
                 }
             }
         }
-        const double tile_total = obe_block_sum(tsum, red);
-        if (tid == 0) a.tile_sums[tile] = tile_total;
+        // tile sum: warp partials -> one named barrier among the consumers -> fixed-order sum
+        tsum = obe_warp_sum(tsum);
+        if (lane == 0) red[tile_par][cwarp] = tsum;
+        obe_named_bar(1, OBE_CONSUMER_THREADS);
+        if (ct == 0) {
+            double s = red[tile_par][0];
+#pragma unroll
+            for (int w = 1; w < OBE_CONSUMER_WARPS; ++w) s += red[tile_par][w];
+            a.tile_sums[tile] = s;
+        }
     }
 
     // ---- per-block partials, then the last block to arrive combines them in block order
@@ -364,31 +573,36 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
     for (int c = 0; c < OBE_MAX_CH; ++c) vals[3 + D + NM2 + c] = acc.noise[c];
 #pragma unroll
     for (int v = 0; v < NACC; ++v) {
-        const double s = obe_block_sum(vals[v], red);
-        if (tid == 0) a.partials[(long long)blockIdx.x * OBE_NACC_MAX + v] = s;
+        const double sv = obe_warp_sum(vals[v]);
+        if (lane == 0) accsm[cwarp][v] = sv;
+    }
+    obe_named_bar(1, OBE_CONSUMER_THREADS);
+    if (ct < NACC) {
+        double sv = accsm[0][ct];
+#pragma unroll
+        for (int w = 1; w < OBE_CONSUMER_WARPS; ++w) sv += accsm[w][ct];
+        a.partials[(long long)blockIdx.x * OBE_NACC_MAX + ct] = sv;
     }
     __threadfence();
-    __syncthreads();
-    if (tid == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
+    obe_named_bar(1, OBE_CONSUMER_THREADS);
+    if (ct == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    obe_named_bar(1, OBE_CONSUMER_THREADS);
     if (!is_last) return;
     __threadfence();
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int v = warp; v < NACC; v += OBE_THREADS / 32) {
-        double s = 0.0;
+    for (int v = cwarp; v < NACC; v += OBE_CONSUMER_WARPS) {
+        double sv = 0.0;
         for (unsigned int b = lane; b < gridDim.x; b += 32)
-            s += __ldcg(a.partials + (long long)b * OBE_NACC_MAX + v);
-        s = obe_warp_sum(s);
-        if (lane == 0) fin[v] = s;
+            sv += __ldcg(a.partials + (long long)b * OBE_NACC_MAX + v);
+        sv = obe_warp_sum(sv);
+        if (lane == 0) fin[v] = sv;
     }
-    __syncthreads();
-    if (tid == 0) {
+    obe_named_bar(1, OBE_CONSUMER_THREADS);
+    if (ct == 0) {
         a.stats[OBE_ST_SUMSQ] = fin[0];
         a.stats[OBE_ST_SUMT] = fin[1];
         a.stats[OBE_ST_NZERO] = fin[2];
         for (int j = 0; j < D; ++j) { a.stats[OBE_ST_M1 + j] = fin[3 + j]; a.stats[OBE_ST_PIVOT + j] = a.pivot[j]; }
-        // packed (j<=k) for D dims -> packed layout for OBE_MAX_DIMS is NOT used: stats M2 is D-packed
-        for (int j = 0; j < NM2; ++j) a.stats[OBE_ST_M2 + j] = fin[3 + D + j];
+        for (int j = 0; j < NM2; ++j) a.stats[OBE_ST_M2 + j] = fin[3 + D + j];   // packed j<=k over D dims
         for (int c = 0; c < OBE_MAX_CH; ++c) a.stats[OBE_ST_NOISE + c] = fin[3 + D + NM2 + c];
         *a.counter = 0u;
     }
@@ -581,7 +795,7 @@ struct ObeNoModel {
 };
 
 #define OBE_DEFINE_MODEL_KERNELS(MODEL, D, SUFFIX)                                                        \
-    extern "C" __global__ void __launch_bounds__(OBE_THREADS) obe_k_update_##SUFFIX(const ObeUpdateArgs a) { \
+    extern "C" __global__ void __launch_bounds__(OBE_UPDATE_THREADS, 1) obe_k_update_##SUFFIX(const ObeUpdateArgs a) { \
         obe_update_body<MODEL, D, OBE_SRC_MODEL>(a);                                                                   \
     }                                                                                                     \
     extern "C" __global__ void __launch_bounds__(OBE_THREADS) obe_k_evalp_##SUFFIX(const ObeEvalArgs a) {  \

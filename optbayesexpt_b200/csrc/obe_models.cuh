@@ -19,12 +19,30 @@ struct ObeLorentzianHWHM {
     }
 };
 
+// update-pass variant: the reciprocal of the constant linewidth is loop-invariant, so the
+// particle loop keeps a single division (the utility pass keeps the exact functor above).
+template <>
+struct ObeUpdateEval<ObeLorentzianHWHM> {
+    __device__ static __forceinline__ void eval(const double* s, const double* p, const double* c, double* y) {
+        const double q = (s[0] - p[0]) * (1.0 / c[0]);
+        y[0] = p[2] + p[1] / (q * q + 1.0);
+    }
+};
+
 // a / ((2 * (x - x0) / d)**2 + 1) + b   demos/numba/numbaLorentzian.py:104
 struct ObeLorentzianFWHM {
     enum { NS = 1, NP = 3, NCONS = 1, NCH = 1 };
     __device__ static __forceinline__ void eval(const double* s, const double* p, const double* c, double* y) {
         const double q = obe_div(obe_mul(2.0, obe_sub(s[0], p[0])), c[0]);
         y[0] = obe_add(obe_div(p[1], obe_add(obe_mul(q, q), 1.0)), p[2]);
+    }
+};
+
+template <>
+struct ObeUpdateEval<ObeLorentzianFWHM> {
+    __device__ static __forceinline__ void eval(const double* s, const double* p, const double* c, double* y) {
+        const double q = (2.0 * (s[0] - p[0])) * (1.0 / c[0]);
+        y[0] = p[1] / (q * q + 1.0) + p[2];
     }
 };
 

@@ -422,30 +422,31 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def _u53(lo, hi):
-    """(0,1) double from two uint32: ((hi:lo) >> 11 + 0.5) * 2^-53."""
-    x = (hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)
-    return ((x >> np.uint64(11)).astype(np.float64) + 0.5) * (2.0 ** -53)
+def _u24(x):
+    """24-bit uniform in (0,1), exact in float32: ((x >> 8) + 0.5) * 2^-24."""
+    return ((x >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24)
 
 
 def device_normals(n, d, seed, epoch):
-    """(n, d) standard normals exactly as the device jitter kernel draws them:
-    for slot i, call c: ctr=(i_lo, i_hi, c, epoch), key=(seed_lo, seed_hi);
-    u1,u2 from the 4 words; Box-Muller pair -> dims 2c, 2c+1."""
+    """(n, d) standard normals as the device jitter kernels draw them (csrc/obe_b200.cu
+    device_normals): for output slot i and call c (4 dims per call) ctr=(i_lo, i_hi, c, epoch),
+    key=(seed_lo, seed_hi); the four Philox words give two Box-Muller pairs evaluated in
+    float32.  The device uses CUDA's logf/sqrtf/sincospif, so values agree to float32 rounding
+    (~1e-6), not bit for bit: parity tests feed the kernel's own normals (z_out) to liu_west and
+    check this restatement only to that accuracy."""
     i = np.arange(n, dtype=np.uint64)
     ilo = (i & np.uint64(0xFFFFFFFF)).astype(np.uint32)
     ihi = (i >> np.uint64(32)).astype(np.uint32)
     z = np.empty((n, d))
-    for c in range((d + 1) // 2):
-        x0, x1, x2, x3 = philox4x32_10(ilo, ihi, np.uint32(c), np.uint32(epoch),
-                                       seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-        u1 = _u53(x0, x1)
-        u2 = _u53(x2, x3)
-        r = np.sqrt(-2.0 * np.log(u1))
-        ang = 2.0 * np.pi * u2
-        z[:, 2 * c] = r * np.cos(ang)
-        if 2 * c + 1 < d:
-            z[:, 2 * c + 1] = r * np.sin(ang)
+    for c in range((d + 3) // 4):
+        x = philox4x32_10(ilo, ihi, np.uint32(c), np.uint32(epoch), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        for h in range(2):
+            if 4 * c + 2 * h < d:
+                rad = np.sqrt(np.float32(-2.0) * np.log(_u24(x[2 * h])))
+                ang = np.float32(2.0) * _u24(x[2 * h + 1]).astype(np.float64) * np.pi
+                z[:, 4 * c + 2 * h] = (rad * np.cos(ang).astype(np.float32)).astype(np.float64)
+                if 4 * c + 2 * h + 1 < d:
+                    z[:, 4 * c + 2 * h + 1] = (rad * np.sin(ang).astype(np.float32)).astype(np.float64)
     return z
 
 
