@@ -285,9 +285,11 @@ __global__ void k_normalized_weights(const double* __restrict__ w, const double*
 // ---------------------------------------------------------------------------------------------
 // canonical in-tile scan: thread t owns elements [8t, 8t+8) of the tile.
 //   incl[e] = (sum of earlier warps' totals, sequential) + (exclusive KS scan over lanes) + running
-// The canonical CDF is cdf[j] = (tile_prefix[k] + incl_j) / total, EXCEPT the last valid element
-// of each tile, which is tile_prefix[k+1] / total by definition (so cdf[n-1] == 1 exactly and
-// tile_sums may be reduced in any order).
+// The canonical CDF is cdf[j] = (tile_prefix[k] + incl_j) * (1/total), EXCEPT the last valid element
+// of each tile, which is tile_prefix[k+1] * (1/total) by definition (so tile_sums may be reduced in
+// any order), and the very last particle, which is exactly 1.  (One IEEE multiply by the rounded
+// reciprocal instead of a divide per particle: still a fixed, monotone function of the weights that
+// numpy reproduces bit for bit as cdf_unnormalised * (1.0 / total).)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tile_load_blocked(const double* __restrict__ w, long long base, long long n,
                                                   double (&v)[OBE_EPT]) {
@@ -330,7 +332,7 @@ __device__ __forceinline__ void tile_scan_blocked(const double (&v)[OBE_EPT], do
 
 // normalised canonical CDF values of this thread's 8 elements of tile k
 __device__ __forceinline__ void tile_cdf_blocked(const double* __restrict__ w, const double* __restrict__ prefix,
-                                                 long long k, long long n, double total,
+                                                 long long k, long long n, double inv_total,
                                                  double (&cn)[OBE_EPT], double* sm) {
     double v[OBE_EPT], incl[OBE_EPT];
     const long long base = k * OBE_TILE;
@@ -340,9 +342,9 @@ __device__ __forceinline__ void tile_cdf_blocked(const double* __restrict__ w, c
     const long long last = min(n, base + OBE_TILE) - 1;
     const long long i0 = base + (long long)threadIdx.x * OBE_EPT;
 #pragma unroll
-    for (int e = 0; e < OBE_EPT; ++e) cn[e] = obe_div(obe_add(p0, incl[e]), total);
+    for (int e = 0; e < OBE_EPT; ++e) cn[e] = obe_mul(obe_add(p0, incl[e]), inv_total);
     if (i0 + OBE_EPT > last) {                 // only the thread(s) at the end of the tile
-        const double c1 = obe_div(prefix[k + 1], total);
+        const double c1 = (last == n - 1) ? 1.0 : obe_mul(prefix[k + 1], inv_total);
 #pragma unroll
         for (int e = 0; e < OBE_EPT; ++e)
             if (i0 + e >= last) cn[e] = c1;
@@ -352,10 +354,10 @@ __device__ __forceinline__ void tile_cdf_blocked(const double* __restrict__ w, c
 __global__ void __launch_bounds__(OBE_THREADS) k_cdf(const double* __restrict__ w, const double* __restrict__ prefix,
                                                      long long n, long long n_tiles, double* __restrict__ cdf) {
     __shared__ double sm[8];
-    const double total = prefix[n_tiles];
+    const double inv_total = 1.0 / prefix[n_tiles];
     for (long long k = blockIdx.x; k < n_tiles; k += gridDim.x) {
         double cn[OBE_EPT];
-        tile_cdf_blocked(w, prefix, k, n, total, cn, sm);
+        tile_cdf_blocked(w, prefix, k, n, inv_total, cn, sm);
         const long long i0 = k * OBE_TILE + (long long)threadIdx.x * OBE_EPT;
 #pragma unroll
         for (int e = 0; e < OBE_EPT; ++e)
@@ -364,13 +366,14 @@ __global__ void __launch_bounds__(OBE_THREADS) k_cdf(const double* __restrict__ 
     }
 }
 
-// tile containing u: #{k in [0, n_tiles) : prefix[k+1]/total <= u}, clamped
-__device__ __forceinline__ long long find_tile(const double* __restrict__ prefix, long long n_tiles, double total,
-                                               double u) {
-    long long lo = 0, hi = n_tiles;  // first k with prefix[k+1]/total > u
+// tile containing u: #{k in [0, n_tiles) : cdf(end of tile k) <= u}, clamped
+__device__ __forceinline__ long long find_tile(const double* __restrict__ prefix, long long n_tiles,
+                                               double inv_total, double u) {
+    long long lo = 0, hi = n_tiles;  // first k whose end-of-tile CDF value is > u
     while (lo < hi) {
         const long long mid = (lo + hi) >> 1;
-        if (obe_div(prefix[mid + 1], total) <= u) lo = mid + 1; else hi = mid;
+        const double c = (mid == n_tiles - 1) ? 1.0 : obe_mul(prefix[mid + 1], inv_total);
+        if (c <= u) lo = mid + 1; else hi = mid;
     }
     return min(lo, n_tiles - 1);
 }
@@ -378,11 +381,11 @@ __device__ __forceinline__ long long find_tile(const double* __restrict__ prefix
 __global__ void k_search(const double* __restrict__ cdf, const double* __restrict__ prefix, long long n,
                          long long n_tiles, const double* __restrict__ u, long long m,
                          long long* __restrict__ idx) {
-    const double total = prefix[n_tiles];
+    const double inv_total = 1.0 / prefix[n_tiles];
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < m;
          q += (long long)gridDim.x * blockDim.x) {
         const double uq = u[q];
-        const long long k = find_tile(prefix, n_tiles, total, uq);
+        const long long k = find_tile(prefix, n_tiles, inv_total, uq);
         long long lo = k * OBE_TILE, hi = min(n, lo + OBE_TILE);
         const long long last = hi - 1;
         while (lo < hi) {
@@ -405,10 +408,10 @@ __global__ void __launch_bounds__(OBE_THREADS) k_draw(const ObeDrawArgs a) {
     __shared__ int cnt[OBE_THREADS / 32];
     const int q = blockIdx.x;
     const double uq = a.u[q];
-    const double total = a.prefix[a.n_tiles];
-    const long long k = find_tile(a.prefix, a.n_tiles, total, uq);
+    const double inv_total = 1.0 / a.prefix[a.n_tiles];
+    const long long k = find_tile(a.prefix, a.n_tiles, inv_total, uq);
     double cn[OBE_EPT];
-    tile_cdf_blocked(a.w, a.prefix, k, a.n, total, cn, sm);
+    tile_cdf_blocked(a.w, a.prefix, k, a.n, inv_total, cn, sm);
     const long long base = k * OBE_TILE;
     int c = 0;
 #pragma unroll
@@ -450,9 +453,10 @@ __device__ __forceinline__ float obe_sqrt_approx(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-// 24-bit uniform in (0,1): ((x >> 8) + 0.5) * 2^-24, exact in fp32
+// uniform in (0,1): ((x >> 9) + 0.5) * 2^-23, exact in fp32
 __device__ __forceinline__ float u24(unsigned int x) {
-    return ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-8f;
+    // [1,2) from the top 23 bits, minus (1 - 2^-24): 23-bit uniform on the half-integers of 2^-23
+    return __uint_as_float(0x3f800000u | (x >> 9)) - 0.99999994039535522461f;
 }
 // Standard normals for the Liu-West jitter of output slot `slot`: one Philox4x32-10 call yields
 // four 24-bit uniforms -> two Box-Muller pairs evaluated in fp32 (the jitter is a random nudge of
@@ -589,12 +593,18 @@ __global__ void __launch_bounds__(OBE_THREADS) k_gather_jitter(const ObeResample
 // ---- systematic comb --------------------------------------------------------------------------
 // #{i in [0,n) : (i + u0) * inv_n < c}; the comb value is two IEEE ops (add, mul), monotone in i.
 // Works on integer-valued doubles (exact below 2^53) to stay off the int<->fp conversion path.
-__device__ __forceinline__ double comb_count_d(double c, double u0, double inv_n, double nd) {
-    double i = ceil(c * nd - u0);
-    i = (i < 0.0) ? 0.0 : i;
-    i = (i > nd) ? nd : i;
-    while (i > 0.0 && obe_mul(obe_add(i - 1.0, u0), inv_n) >= c) i -= 1.0;
-    while (i < nd && obe_mul(obe_add(i, u0), inv_n) < c) i += 1.0;
+// The real-valued answer is ceil(c*n - u0).  The comb's three roundings move a tooth by at most
+// ~4.4e-16*n slots, so when c*n - u0 is farther than `tol` = 2e-15*n from an integer the estimate is
+// already exact; only the (probability ~4e-15*n) near-boundary cases run the exact comparison loop.
+__device__ __forceinline__ double comb_count_d(double c, double u0, double inv_n, double nd, double tol) {
+    const double x = fma(c, nd, -u0);
+    double i = ceil(x);
+    if (i - x < tol || i - x > 1.0 - tol || !(i > 0.0) || !(i < nd)) {
+        i = (i < 0.0) ? 0.0 : i;
+        i = (i > nd) ? nd : i;
+        while (i > 0.0 && obe_mul(obe_add(i - 1.0, u0), inv_n) >= c) i -= 1.0;
+        while (i < nd && obe_mul(obe_add(i, u0), inv_n) < c) i += 1.0;
+    }
     return i;
 }
 
@@ -607,14 +617,14 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
     __shared__ long long sml[34];
     __shared__ int smi[34];
     const int t = threadIdx.x;
-    const double total = prefix[n_tiles];
-    const double nd = (double)n, inv_n = 1.0 / nd;
+    const double inv_total = 1.0 / prefix[n_tiles];
+    const double nd = (double)n, inv_n = 1.0 / nd, tol = 2e-15 * nd;
     long long carry = -1;
     for (long long base = 0; base <= n_tiles; base += OBE_SCAN_THREADS) {
         const long long k = base + t;
         long long h = -1;
         if (k <= n_tiles)
-            h = (k == 0) ? 0 : (k == n_tiles ? n : (long long)comb_count_d(obe_div(prefix[k], total), u0, inv_n, nd));
+            h = (k == 0) ? 0 : (k == n_tiles ? n : (long long)comb_count_d(obe_mul(prefix[k], inv_total), u0, inv_n, nd, tol));
         long long tot;
         const long long inc = block_incl_max_1024(h, sml, &tot);
         if (k <= n_tiles) H[k] = min(max(inc, carry), n);
@@ -642,7 +652,7 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
 //     index; a max-scan over the chunk's slots turns the marks into the ancestor of every slot
 //  3. slots are walked in coalesced order: gather the ancestor (L1-resident tile), jitter, store
 template <int D>
-__global__ void __launch_bounds__(OBE_THREADS) k_sys_resample(const ObeResampleArgs a) {
+__global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(const ObeResampleArgs a) {
     __shared__ double sF[D * D];
     __shared__ double sMean[D];
     __shared__ double sm[8];
@@ -650,8 +660,14 @@ __global__ void __launch_bounds__(OBE_THREADS) k_sys_resample(const ObeResampleA
     __shared__ __align__(16) unsigned short anc_s[OBE_OUT_CHUNK];
     setup_factor<D>(a, sF, sMean);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double total = a.prefix[a.n_tiles];
-    const double nd = (double)a.n, inv_n = 1.0 / nd, wv = 1.0 / nd;
+    const double inv_total = 1.0 / a.prefix[a.n_tiles];
+    const double nd = (double)a.n, inv_n = 1.0 / nd, wv = 1.0 / nd, tol = 2e-15 * nd;
+    // the Liu-West factor in registers when it is small enough
+    double Fr[D <= 4 ? D * D : 1];
+    if (D <= 4) {
+#pragma unroll
+        for (int q = 0; q < D * D; ++q) Fr[D <= 4 ? q : 0] = sF[q];
+    }
     const int n_units = a.unit_start[a.n_tiles];
     // contiguous range of units per block: one binary search, then a forward walk over the tiles
     const int per_block = (n_units + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -677,7 +693,7 @@ __global__ void __launch_bounds__(OBE_THREADS) k_sys_resample(const ObeResampleA
         *reinterpret_cast<uint4*>(&anc_s[tid * OBE_EPT]) = make_uint4(0u, 0u, 0u, 0u);
         // ---- 1. end slot of every particle of the tile
         double cn[OBE_EPT];
-        tile_cdf_blocked(a.w_in, a.prefix, k, a.n, total, cn, sm);
+        tile_cdf_blocked(a.w_in, a.prefix, k, a.n, inv_total, cn, sm);
         const long long base = k * OBE_TILE;
         const long long last = min(a.n, base + OBE_TILE) - 1;
         int r[OBE_EPT];
@@ -688,8 +704,8 @@ __global__ void __launch_bounds__(OBE_THREADS) k_sys_resample(const ObeResampleA
             int h;
             if (i >= last) h = span;
             else {
-                const long long hl = (long long)comb_count_d(cn[e], a.u0, inv_n, nd) - Hk;
-                h = (int)min(max(hl, 0ll), (long long)span);
+                const double hd = comb_count_d(cn[e], a.u0, inv_n, nd, tol) - (double)Hk;   // exact: < 2^53
+                h = (hd < 0.0) ? 0 : (hd > (double)span ? span : (int)hd);
             }
             run = max(run, h);
             r[e] = run;
@@ -754,7 +770,7 @@ __global__ void __launch_bounds__(OBE_THREADS) k_sys_resample(const ObeResampleA
         const int n_out = rel_end - rel_begin;
         for (int q = tid; q < n_out; q += OBE_THREADS) {
             const long long o = Hk + rel_begin + q;
-            const long long anc = min(base + (long long)anc_s[q], last);
+            const long long anc = base + min((int)anc_s[q], (int)(last - base));
             double xv[D], z[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) xv[j] = __ldg(a.pin + j * a.ld_in + anc);
@@ -764,7 +780,7 @@ __global__ void __launch_bounds__(OBE_THREADS) k_sys_resample(const ObeResampleA
 #pragma unroll
                     for (int j = 0; j < D; ++j) a.z_out[o * D + j] = z[j];
                 }
-                liu_west<D>(xv, z, sF, sMean, a.a_param, a.scale);
+                liu_west<D>(xv, z, (D <= 4) ? Fr : sF, sMean, a.a_param, a.scale);
             }
 #pragma unroll
             for (int j = 0; j < D; ++j) a.pout[j * a.ld_out + o] = xv[j];

@@ -244,13 +244,33 @@ struct ObeAcc {
     double noise[OBE_MAX_CH];
 };
 
-// cheap numpy.nan_to_num: nan -> 0, +-inf -> +-DBL_MAX
+// numpy.nan_to_num (nan -> 0, +-inf -> +-DBL_MAX): one integer test on the fast path, the rare
+// path out of line so that it is a real branch and not ten predicated instructions per particle.
+__device__ __noinline__ double obe_nan_to_num_rare(double x) {
+    return (x != x) ? 0.0 : (x > 0.0 ? OBE_DBL_MAX : -OBE_DBL_MAX);
+}
 __device__ __forceinline__ double obe_nan_to_num_fast(double x) {
-    // inf or nan <=> exponent field all ones: one integer test on the fast path
-    if ((((unsigned)__double2hiint(x)) & 0x7fffffffu) >= 0x7ff00000u)
-        x = (x != x) ? 0.0 : (x > 0.0 ? OBE_DBL_MAX : -OBE_DBL_MAX);
+    if ((((unsigned)__double2hiint(x)) & 0x7fffffffu) >= 0x7ff00000u) x = obe_nan_to_num_rare(x);
     return x;
 }
+
+// 1/x to ~1 ulp for finite, normal, non-zero x: hardware seed + two Newton steps, no slow path.
+__device__ __forceinline__ double obe_rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// Taylor coefficients 1/13! .. 1/2! of exp, in constant memory so each DFMA takes its
+// coefficient as a constant-bank operand (immediates cost two extra moves per FMA).
+__constant__ double obe_exp_c[12] = {
+    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
+    2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.3888888888888889e-03,
+    8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};
 
 // exp(x) for x <= 0 (the Gaussian log-likelihood): k = rint(x/ln2), r = x - k ln2 in two FMAs,
 // degree-13 Taylor polynomial on |r| <= ln2/2 (truncation 4e-18), scaling by 2^k through the
@@ -261,18 +281,9 @@ __device__ __forceinline__ double obe_exp_nonpos(double x) {
     const double kf = t - 6755399441055744.0;
     double r = fma(kf, -6.93147180369123816490e-01, x);
     r = fma(kf, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;                                   // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);
-    p = fma(p, r, 2.505210838544172e-08);
-    p = fma(p, r, 2.755731922398589e-07);
-    p = fma(p, r, 2.7557319223985893e-06);
-    p = fma(p, r, 2.48015873015873e-05);
-    p = fma(p, r, 1.984126984126984e-04);
-    p = fma(p, r, 1.3888888888888889e-03);
-    p = fma(p, r, 8.333333333333333e-03);
-    p = fma(p, r, 4.1666666666666664e-02);
-    p = fma(p, r, 1.6666666666666666e-01);
-    p = fma(p, r, 0.5);
+    double p = obe_exp_c[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) p = fma(p, r, obe_exp_c[i]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     k = max(k, -1022);
@@ -297,7 +308,9 @@ __device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const d
     if (SRC == OBE_SRC_NONE) {
         t = w_in;
     } else {
-        const double w = a.scale_in ? obe_nan_to_num_fast(w_in * invS) : w_in;
+        // stored weights are finite and <= total, so w_in * invS needs no second nan_to_num: a NaN
+        // (0 * inf when every weight is zero) propagates into t and is zeroed there like numpy does
+        const double w = w_in * invS;
         double lik = 1.0;
         if (SRC == OBE_SRC_LIK) {
             lik = lik_given;
@@ -323,7 +336,7 @@ __device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const d
 #pragma unroll
                         for (int j = 0; j < D; ++j)
                             if (j == ni) sig = p[j];
-                        inv_sig = 1.0 / sig;
+                        inv_sig = obe_rcp_fast(sig);
                     }
                     const double q = (y[c] - a.y_meas[c]) * inv_sig;
                     lik *= obe_exp_nonpos(-0.5 * (q * q)) * inv_sig;
@@ -461,7 +474,7 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
     // ---------------------------------------------------------------------- consumers
     const int ct = tid;                   // every thread is a consumer
     const int cwarp = warp;
-    const double invS = a.scale_in ? a.stats[OBE_ST_INVS] : 1.0;
+    const double invS = a.scale_in ? a.stats[OBE_ST_INVS] : 1.0;   // scale_in == 0: raw weights
     const bool write_weights = a.write_weights != 0;
     ObeAcc<D> acc;
     acc.sumsq = 0.0; acc.sumt = 0.0; acc.nzero = 0.0;
@@ -481,7 +494,7 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
             const int s = it % NST;
             const unsigned k = it / NST;
             const long long base = tile * OBE_TILE + (long long)sub * SE;
-            const bool stage_full = (base + SE <= n);
+            const int n_valid = (base + SE <= n) ? SE : (int)(n - base);   // particles of this stage
             if (tid == 0) produce(it + NST - 1);
             obe_mbar_wait(full_bar + s, k & 1u);
             const double* src = stage_base + (size_t)s * (NROWS * SE);
@@ -527,11 +540,11 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
             // compute + store
 #pragma unroll
             for (int q = 0; q < (EPT >= 2 ? EPT / 2 : 1); ++q) {
-                const long long i0 = base + (EPT >= 2 ? 2 * (ct + q * OBE_CONSUMER_THREADS) : ct);
+                const int e0 = (EPT >= 2 ? 2 * (ct + q * OBE_CONSUMER_THREADS) : ct);   // index in the stage
                 double tv[2] = {0.0, 0.0};
 #pragma unroll
                 for (int h = 0; h < (EPT >= 2 ? 2 : 1); ++h) {
-                    if (stage_full || i0 + h < n) {
+                    if (e0 + h < n_valid) {
                         double px[D], yg[OBE_MAX_CH];
 #pragma unroll
                         for (int j = 0; j < D; ++j) px[j] = pv[j][(EPT >= 2 ? 2 * q : 0) + h];
@@ -545,8 +558,8 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
                 }
                 tsum += tv[0] + tv[1];
                 if (write_weights) {
-                    if (EPT >= 2 && (stage_full || i0 + 1 < n)) obe_st2(a.weights + i0, make_double2(tv[0], tv[1]));
-                    else if (i0 < n) a.weights[i0] = tv[0];
+                    if (EPT >= 2 && e0 + 1 < n_valid) obe_st2(a.weights + base + e0, make_double2(tv[0], tv[1]));
+                    else if (e0 < n_valid) a.weights[base + e0] = tv[0];
                 }
             }
         }

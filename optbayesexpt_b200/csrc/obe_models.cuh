@@ -25,7 +25,7 @@ template <>
 struct ObeUpdateEval<ObeLorentzianHWHM> {
     __device__ static __forceinline__ void eval(const double* s, const double* p, const double* c, double* y) {
         const double q = (s[0] - p[0]) * (1.0 / c[0]);
-        y[0] = p[2] + p[1] / (q * q + 1.0);
+        y[0] = fma(p[1], obe_rcp_fast(fma(q, q, 1.0)), p[2]);      // denominator >= 1: no special cases
     }
 };
 
@@ -42,7 +42,7 @@ template <>
 struct ObeUpdateEval<ObeLorentzianFWHM> {
     __device__ static __forceinline__ void eval(const double* s, const double* p, const double* c, double* y) {
         const double q = (2.0 * (s[0] - p[0])) * (1.0 / c[0]);
-        y[0] = p[1] / (q * q + 1.0) + p[2];
+        y[0] = fma(p[1], obe_rcp_fast(fma(q, q, 1.0)), p[2]);
     }
 };
 

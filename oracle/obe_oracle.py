@@ -423,8 +423,8 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def _u24(x):
-    """24-bit uniform in (0,1), exact in float32: ((x >> 8) + 0.5) * 2^-24."""
-    return ((x >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24)
+    """uniform in (0,1) from the top 23 bits, exact in float32: ((x >> 9) + 0.5) * 2^-23."""
+    return ((x >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -23)
 
 
 def device_normals(n, d, seed, epoch):
