@@ -150,6 +150,28 @@ int obe_resample_systematic(const obe_cloud_t* in, const obe_cloud_t* out, doubl
                             double a_param, int scale, int64_t* idx_out_dev, double* z_out_dev,
                             void* stream);
 
+/* ---- sharded clouds (one process per GPU; particles split into contiguous shards) ---------- */
+/* The same fused kernel for one shard of a cloud of n_total particles: this shard's particles own
+ * the global comb slots [slot_begin, slot_end) (= out->n of them, which may differ from in->n: shard
+ * lengths float, no particle ever crosses NVLink); cdf_offset = summed weight of the lower-ranked
+ * shards, cdf_total = global weight; factor/mean are the GLOBAL Liu-West factor and mean (host).
+ * RNG counters are global slot numbers, so the jitter does not depend on the number of shards. */
+int obe_resample_systematic_sharded(const obe_cloud_t* in, const obe_cloud_t* out, double u0,
+                                    int64_t n_total, int64_t slot_begin, int64_t slot_end,
+                                    double cdf_offset, double cdf_total, int last_shard,
+                                    const double* factor, const double* mean, uint64_t seed,
+                                    uint32_t epoch, double a_param, int scale, int64_t* idx_out_dev,
+                                    double* z_out_dev, void* stream);
+/* weights <- 1/n_total for one shard of a cloud of n_total particles. */
+int obe_set_uniform_total(const obe_cloud_t* c, int64_t n_total, void* stream);
+/* Host twin of the device comb count #{i in [0,n_total) : (i + u0) * (1/n_total) < c}: shard
+ * boundaries slot_begin/slot_end are obe_comb_count(cdf_offset / cdf_total ...) evaluated identically
+ * on every rank. */
+int64_t obe_comb_count(double c, double u0, int64_t n_total);
+/* obe_draw writing its m draws into columns of a wider (d, ld_draws) matrix. */
+int obe_draw_strided(const obe_cloud_t* c, const double* u_host, int m, double* draws_dev, int ld_draws,
+                     int64_t* idx_dev, void* stream);
+
 /* ---- design half ------------------------------------------------------------------------ */
 /* utility_variance (obe_base.py:628-655) over the whole grid + argmax of opt_setting
  * (obe_base.py:748).  draws_dev (d, K); settings_dev (s, lds); var_noise[C] host or NULL to use

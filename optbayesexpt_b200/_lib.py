@@ -65,6 +65,12 @@ SIGNATURES = {
                                     C.c_double, C.c_int, _VP]),
     'obe_resample_systematic': (C.c_int, [_PCLOUD, _PCLOUD, C.c_double, _PD, _PD, C.c_uint64, C.c_uint32,
                                           C.c_double, C.c_int, _VP, _VP, _VP]),
+    'obe_resample_systematic_sharded': (C.c_int, [_PCLOUD, _PCLOUD, C.c_double, C.c_int64, C.c_int64, C.c_int64,
+                                                  C.c_double, C.c_double, C.c_int, _PD, _PD, C.c_uint64, C.c_uint32,
+                                                  C.c_double, C.c_int, _VP, _VP, _VP]),
+    'obe_set_uniform_total': (C.c_int, [_PCLOUD, C.c_int64, _VP]),
+    'obe_comb_count': (C.c_int64, [C.c_double, C.c_double, C.c_int64]),
+    'obe_draw_strided': (C.c_int, [_PCLOUD, _PD, C.c_int, _VP, C.c_int, _VP, _VP]),
     'obe_utility': (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int64, C.c_int64, _PD, _PD, _VP, _VP, C.c_int,
                               C.c_int, _VP, _VP, _VP, _VP]),
     'obe_pick': (C.c_int, [_VP, C.c_int64, C.c_double, C.c_double, _VP, _VP, _VP]),

@@ -228,7 +228,7 @@ __device__ __forceinline__ int block_excl_isum_1024(int v, int* sm /*34*/, int* 
 __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_tile_scan(const double* __restrict__ tile_sums,
                                                                 long long n_tiles, double* __restrict__ prefix,
                                                                 double* __restrict__ stats, int renormalise,
-                                                                int uniform, long long n) {
+                                                                long long uniform, long long n) {
     __shared__ double sm[34];
     const int t = threadIdx.x;
     double carry = 0.0;
@@ -247,11 +247,13 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_tile_scan(const double* __
         if (stats) {
             stats[OBE_ST_TOTAL] = total;
             if (uniform) {
-                // weights are exactly 1/n: normaliser is exactly 1 (particlepdf.py:309-310)
+                // weights are exactly 1/n_total: normaliser is exactly 1 (particlepdf.py:309-310);
+                // `uniform` carries n_total (== n for a whole cloud)
+                const double wv = 1.0 / (double)uniform;
                 stats[OBE_ST_INVS] = 1.0;
-                stats[OBE_ST_SUMSQ] = 1.0 / (double)n;
-                stats[OBE_ST_SUMT] = 1.0;
-                stats[OBE_ST_NEFF] = (double)n;
+                stats[OBE_ST_SUMSQ] = (double)n * wv * wv;
+                stats[OBE_ST_SUMT] = (double)n * wv;
+                stats[OBE_ST_NEFF] = (double)uniform;
             } else {
                 stats[OBE_ST_INVS] = renormalise ? 1.0 / total : 1.0;
                 const double ssq = stats[OBE_ST_SUMSQ];
@@ -262,8 +264,8 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_tile_scan(const double* __
 }
 
 __global__ void k_fill_uniform(double* __restrict__ w, double* __restrict__ tile_sums, long long n,
-                               long long n_tiles, int write_weights) {
-    const double v = 1.0 / (double)n;
+                               long long n_tiles, int write_weights, long long n_total) {
+    const double v = 1.0 / (double)n_total;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (write_weights)
@@ -331,20 +333,23 @@ __device__ __forceinline__ void tile_scan_blocked(const double (&v)[OBE_EPT], do
 }
 
 // normalised canonical CDF values of this thread's 8 elements of tile k
+// Sharded clouds: `offset` is the summed weight of all lower-ranked shards and inv_total the
+// reciprocal of the GLOBAL total; last_shard marks the shard that holds the global last particle.
 __device__ __forceinline__ void tile_cdf_blocked(const double* __restrict__ w, const double* __restrict__ prefix,
                                                  long long k, long long n, double inv_total,
-                                                 double (&cn)[OBE_EPT], double* sm) {
+                                                 double (&cn)[OBE_EPT], double* sm, double offset = 0.0,
+                                                 bool last_shard = true) {
     double v[OBE_EPT], incl[OBE_EPT];
     const long long base = k * OBE_TILE;
     tile_load_blocked(w, base, n, v);
     tile_scan_blocked(v, incl, sm);
-    const double p0 = prefix[k];
+    const double p0 = obe_add(offset, prefix[k]);
     const long long last = min(n, base + OBE_TILE) - 1;
     const long long i0 = base + (long long)threadIdx.x * OBE_EPT;
 #pragma unroll
     for (int e = 0; e < OBE_EPT; ++e) cn[e] = obe_mul(obe_add(p0, incl[e]), inv_total);
     if (i0 + OBE_EPT > last) {                 // only the thread(s) at the end of the tile
-        const double c1 = (last == n - 1) ? 1.0 : obe_mul(prefix[k + 1], inv_total);
+        const double c1 = (last_shard && last == n - 1) ? 1.0 : obe_mul(obe_add(offset, prefix[k + 1]), inv_total);
 #pragma unroll
         for (int e = 0; e < OBE_EPT; ++e)
             if (i0 + e >= last) cn[e] = c1;
@@ -512,6 +517,12 @@ struct ObeResampleArgs {
     int scale, factor_from_stats, jitter;
     unsigned int epoch;
     unsigned long long seed;
+    // shard of a multi-GPU cloud (sharded == 0: the cloud is whole and these are derived on device)
+    int sharded, last_shard;
+    long long n_total;             // particles over all shards = teeth of the comb
+    long long slot_begin, slot_end; // global output slots owned by this shard's particles
+    double cdf_offset;             // summed weight of the lower-ranked shards
+    double cdf_total;              // global total weight
     double factor[OBE_MAX_DIMS * OBE_MAX_DIMS];
     double mean[OBE_MAX_DIMS];
 };
@@ -612,22 +623,27 @@ __device__ __forceinline__ double comb_count_d(double c, double u0, double inv_n
 // plan: H[k] = first output slot owned by tile k (monotone), unit_start[k] = first work unit of
 // tile k, one unit = up to OBE_OUT_CHUNK output slots of one input tile.
 __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __restrict__ prefix, long long n_tiles,
-                                                               long long n, double u0, long long* __restrict__ H,
+                                                               long long n_total, double u0, double cdf_offset,
+                                                               double cdf_total, long long slot_begin,
+                                                               long long slot_end, long long* __restrict__ H,
                                                                int* __restrict__ unit_start) {
     __shared__ long long sml[34];
     __shared__ int smi[34];
     const int t = threadIdx.x;
-    const double inv_total = 1.0 / prefix[n_tiles];
-    const double nd = (double)n, inv_n = 1.0 / nd, tol = 2e-15 * nd;
+    const double inv_total = 1.0 / (cdf_total > 0.0 ? cdf_total : prefix[n_tiles]);
+    const double nd = (double)n_total, inv_n = 1.0 / nd, tol = 2e-15 * nd;
     long long carry = -1;
     for (long long base = 0; base <= n_tiles; base += OBE_SCAN_THREADS) {
         const long long k = base + t;
         long long h = -1;
         if (k <= n_tiles)
-            h = (k == 0) ? 0 : (k == n_tiles ? n : (long long)comb_count_d(obe_mul(prefix[k], inv_total), u0, inv_n, nd, tol));
+            h = (k == 0) ? slot_begin
+                         : (k == n_tiles ? slot_end
+                                         : (long long)comb_count_d(obe_mul(obe_add(cdf_offset, prefix[k]), inv_total),
+                                                                   u0, inv_n, nd, tol));
         long long tot;
         const long long inc = block_incl_max_1024(h, sml, &tot);
-        if (k <= n_tiles) H[k] = min(max(inc, carry), n);
+        if (k <= n_tiles) H[k] = min(max(max(inc, carry), slot_begin), slot_end);
         carry = max(carry, tot);
         __syncthreads();
     }
@@ -660,8 +676,10 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(
     __shared__ __align__(16) unsigned short anc_s[OBE_OUT_CHUNK];
     setup_factor<D>(a, sF, sMean);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double inv_total = 1.0 / a.prefix[a.n_tiles];
-    const double nd = (double)a.n, inv_n = 1.0 / nd, wv = 1.0 / nd, tol = 2e-15 * nd;
+    const double inv_total = 1.0 / (a.sharded ? a.cdf_total : a.prefix[a.n_tiles]);
+    const double nd = (double)a.n_total, inv_n = 1.0 / nd, wv = 1.0 / nd, tol = 2e-15 * nd;
+    const double cdf_offset = a.sharded ? a.cdf_offset : 0.0;
+    const bool last_shard = a.sharded ? (a.last_shard != 0) : true;
     // the Liu-West factor in registers when it is small enough
     double Fr[D <= 4 ? D * D : 1];
     if (D <= 4) {
@@ -693,7 +711,7 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(
         *reinterpret_cast<uint4*>(&anc_s[tid * OBE_EPT]) = make_uint4(0u, 0u, 0u, 0u);
         // ---- 1. end slot of every particle of the tile
         double cn[OBE_EPT];
-        tile_cdf_blocked(a.w_in, a.prefix, k, a.n, inv_total, cn, sm);
+        tile_cdf_blocked(a.w_in, a.prefix, k, a.n, inv_total, cn, sm, cdf_offset, last_shard);
         const long long base = k * OBE_TILE;
         const long long last = min(a.n, base + OBE_TILE) - 1;
         int r[OBE_EPT];
@@ -769,13 +787,14 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(
         // ---- 3. outputs in coalesced order
         const int n_out = rel_end - rel_begin;
         for (int q = tid; q < n_out; q += OBE_THREADS) {
-            const long long o = Hk + rel_begin + q;
+            const long long og = Hk + rel_begin + q;              // global slot: comb tooth, RNG counter
+            const long long o = og - a.slot_begin;                  // position in this shard's output
             const long long anc = base + min((int)anc_s[q], (int)(last - base));
             double xv[D], z[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) xv[j] = __ldg(a.pin + j * a.ld_in + anc);
             if (a.jitter) {
-                device_normals<D>(o, a.seed, a.epoch, z);
+                device_normals<D>(og, a.seed, a.epoch, z);
                 if (a.z_out) {
 #pragma unroll
                     for (int j = 0; j < D; ++j) a.z_out[o * D + j] = z[j];
@@ -1110,11 +1129,24 @@ int obe_set_uniform(const obe_cloud_t* c, void* stream) {
     if (check_cloud(c)) return -1;
     cudaStream_t st = (cudaStream_t)stream;
     int grid = obe_sms() * 8;
-    k_fill_uniform<<<grid, 256, 0, st>>>(c->weights_dev, c->tile_sums_dev, c->n, obe_num_tiles(c->n), 1);
+    k_fill_uniform<<<grid, 256, 0, st>>>(c->weights_dev, c->tile_sums_dev, c->n, obe_num_tiles(c->n), 1, c->n);
     OBE_LAUNCH_CHECK("k_fill_uniform");
     OBE_CUDA(cudaMemsetAsync(c->stats_dev, 0, OBE_STATS_LEN * sizeof(double), st));
     k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(c->tile_sums_dev, obe_num_tiles(c->n), c->tile_prefix_dev,
-                                               c->stats_dev, 0, 1, c->n);
+                                               c->stats_dev, 0, c->n, c->n);
+    OBE_LAUNCH_CHECK("k_tile_scan");
+    return 0;
+}
+
+int obe_set_uniform_total(const obe_cloud_t* c, int64_t n_total, void* stream) {
+    if (check_cloud(c)) return -1;
+    if (n_total < c->n) return obe_fail("n_total < n%s%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_fill_uniform<<<obe_sms() * 8, 256, 0, st>>>(c->weights_dev, c->tile_sums_dev, c->n, obe_num_tiles(c->n), 1, n_total);
+    OBE_LAUNCH_CHECK("k_fill_uniform");
+    OBE_CUDA(cudaMemsetAsync(c->stats_dev, 0, OBE_STATS_LEN * sizeof(double), st));
+    k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(c->tile_sums_dev, obe_num_tiles(c->n), c->tile_prefix_dev,
+                                               c->stats_dev, 0, n_total, c->n);
     OBE_LAUNCH_CHECK("k_tile_scan");
     return 0;
 }
@@ -1215,7 +1247,8 @@ int obe_search(const obe_cloud_t* c, const double* cdf_dev, const double* u_dev,
 }
 
 static int draw_impl(const double* w, const double* prefix, int64_t n, const double* particles, int64_t ld, int d,
-                     const double* u_host, int k, double* draws_dev, int64_t* idx_dev, cudaStream_t st) {
+                     const double* u_host, int k, double* draws_dev, int64_t* idx_dev, cudaStream_t st,
+                     int ld_draws = 0) {
     if (k <= 0) return 0;
     for (int off = 0; off < k; off += OBE_MAX_DRAWS) {
         const int kk = (k - off) < OBE_MAX_DRAWS ? (k - off) : OBE_MAX_DRAWS;
@@ -1224,7 +1257,7 @@ static int draw_impl(const double* w, const double* prefix, int64_t n, const dou
         a.particles = particles; a.ld = ld; a.d = d;
         a.draws = draws_dev ? draws_dev + off : nullptr;
         a.idx = idx_dev ? (long long*)idx_dev + off : nullptr;
-        a.k = k;
+        a.k = ld_draws > 0 ? ld_draws : k;
         for (int i = 0; i < kk; ++i) a.u[i] = u_host[off + i];
         k_draw<<<kk, OBE_THREADS, 0, st>>>(a);
         OBE_LAUNCH_CHECK("k_draw");
@@ -1239,11 +1272,12 @@ int obe_draw(const obe_cloud_t* c, const double* u_host, int k, double* draws_de
                      idx_dev, (cudaStream_t)stream);
 }
 
-static int finish_resample(const obe_cloud_t* out, cudaStream_t st) {
-    k_fill_uniform<<<obe_sms() * 2, 256, 0, st>>>(out->weights_dev, out->tile_sums_dev, out->n, obe_num_tiles(out->n), 0);
+static int finish_resample(const obe_cloud_t* out, int64_t n_total, cudaStream_t st) {
+    k_fill_uniform<<<obe_sms() * 2, 256, 0, st>>>(out->weights_dev, out->tile_sums_dev, out->n, obe_num_tiles(out->n), 0,
+                                                 n_total);
     OBE_LAUNCH_CHECK("k_fill_uniform");
     k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(out->tile_sums_dev, obe_num_tiles(out->n), out->tile_prefix_dev,
-                                               out->stats_dev, 0, 1, out->n);
+                                               out->stats_dev, 0, n_total, out->n);
     OBE_LAUNCH_CHECK("k_tile_scan");
     return 0;
 }
@@ -1251,7 +1285,7 @@ static int finish_resample(const obe_cloud_t* out, cudaStream_t st) {
 static int fill_resample_args(const obe_cloud_t* in, const obe_cloud_t* out, const double* factor, const double* mean,
                               double a_param, int scale, uint64_t seed, uint32_t epoch, ObeResampleArgs& a) {
     if (check_cloud(in) || check_cloud(out)) return -1;
-    if (in->n != out->n || in->d != out->d) return obe_fail("resample: in/out geometry differs%s%s");
+    if (in->d != out->d) return obe_fail("resample: in/out geometry differs%s%s");
     if (in->particles_dev == out->particles_dev || in->weights_dev == out->weights_dev)
         return obe_fail("resample is out-of-place: pass a second cloud%s%s");
     memset(&a, 0, sizeof(a));
@@ -1271,11 +1305,21 @@ static int fill_resample_args(const obe_cloud_t* in, const obe_cloud_t* out, con
     return 0;
 }
 
+int obe_draw_strided(const obe_cloud_t* c, const double* u_host, int m, double* draws_dev, int ld_draws,
+                     int64_t* idx_dev, void* stream) {
+    if (check_cloud(c)) return -1;
+    if (m == 0) return 0;
+    if (!u_host || !draws_dev || ld_draws < m) return obe_fail("bad argument%s%s");
+    return draw_impl(c->weights_dev, c->tile_prefix_dev, c->n, c->particles_dev, c->ld, c->d, u_host, m, draws_dev,
+                     idx_dev, (cudaStream_t)stream, ld_draws);
+}
+
 int obe_gather_jitter(const obe_cloud_t* in, const obe_cloud_t* out, const int64_t* idx_dev, const double* factor,
                       const double* mean, const double* z_dev, uint64_t seed, uint32_t epoch, double a_param, int scale,
                       void* stream) {
     ObeResampleArgs a;
     if (fill_resample_args(in, out, factor, mean, a_param, scale, seed, epoch, a)) return -1;
+    if (in->n != out->n) return obe_fail("gather_jitter: in/out sizes differ%s%s");
     if (!idx_dev) return obe_fail("null ancestors%s%s");
     a.idx_in = (const long long*)idx_dev; a.z_in = z_dev;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1284,29 +1328,67 @@ int obe_gather_jitter(const obe_cloud_t* in, const obe_cloud_t* out, const int64
     const int grid = (int)blocks;
     OBE_DIM_SWITCH(in->d, k_gather_jitter, grid, st, a)
     OBE_LAUNCH_CHECK("k_gather_jitter");
-    return finish_resample(out, st);
+    return finish_resample(out, out->n, st);
 }
 
-int obe_resample_systematic(const obe_cloud_t* in, const obe_cloud_t* out, double u0, const double* factor,
-                            const double* mean, uint64_t seed, uint32_t epoch, double a_param, int scale,
-                            int64_t* idx_out_dev, double* z_out_dev, void* stream) {
+static int resample_systematic_impl(const obe_cloud_t* in, const obe_cloud_t* out, double u0, const double* factor,
+                                    const double* mean, uint64_t seed, uint32_t epoch, double a_param, int scale,
+                                    int64_t* idx_out_dev, double* z_out_dev, int sharded, int64_t n_total,
+                                    int64_t slot_begin, int64_t slot_end, double cdf_offset, double cdf_total,
+                                    int last_shard, void* stream) {
     ObeResampleArgs a;
     if (fill_resample_args(in, out, factor, mean, a_param, scale, seed, epoch, a)) return -1;
     if (!(u0 >= 0.0 && u0 < 1.0)) return obe_fail("u0 must be in [0,1)%s%s");
-    if (in->n >= (1ll << 31)) return obe_fail("systematic resample supports n < 2^31%s%s");
+    if (n_total >= (1ll << 31)) return obe_fail("systematic resample supports n < 2^31%s%s");
+    if (out->n != slot_end - slot_begin) return obe_fail("resample: out->n must equal the number of output slots%s%s");
+    if (sharded && !factor) return obe_fail("sharded resample needs the (global) factor from the host%s%s");
     const Scratch s = scratch_of(in);
     a.plan_h = s.plan_h; a.unit_start = s.unit_start; a.u0 = u0;
     a.idx_out = (long long*)idx_out_dev; a.z_out = z_out_dev;
+    a.sharded = sharded; a.last_shard = last_shard; a.n_total = n_total;
+    a.slot_begin = slot_begin; a.slot_end = slot_end; a.cdf_offset = cdf_offset; a.cdf_total = cdf_total;
     cudaStream_t st = (cudaStream_t)stream;
-    k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, in->n, u0, s.plan_h, s.unit_start);
+    k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, u0, sharded ? cdf_offset : 0.0,
+                                              sharded ? cdf_total : 0.0, slot_begin, slot_end, s.plan_h, s.unit_start);
     OBE_LAUNCH_CHECK("k_sys_plan");
-    int64_t max_units = a.n_tiles + (in->n + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK;
+    int64_t max_units = a.n_tiles + (out->n + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK;
     int64_t g = (int64_t)obe_sms() * OBE_BLOCKS_PER_SM;
     if (g > max_units) g = max_units;
     const int grid = (int)g;
     OBE_DIM_SWITCH(in->d, k_sys_resample, grid, st, a)
     OBE_LAUNCH_CHECK("k_sys_resample");
-    return finish_resample(out, st);
+    return finish_resample(out, n_total, st);
+}
+
+int obe_resample_systematic(const obe_cloud_t* in, const obe_cloud_t* out, double u0, const double* factor,
+                            const double* mean, uint64_t seed, uint32_t epoch, double a_param, int scale,
+                            int64_t* idx_out_dev, double* z_out_dev, void* stream) {
+    if (!in) return obe_fail("null cloud%s%s");
+    return resample_systematic_impl(in, out, u0, factor, mean, seed, epoch, a_param, scale, idx_out_dev, z_out_dev, 0,
+                                    in->n, 0, in->n, 0.0, 0.0, 1, stream);
+}
+
+int obe_resample_systematic_sharded(const obe_cloud_t* in, const obe_cloud_t* out, double u0, int64_t n_total,
+                                    int64_t slot_begin, int64_t slot_end, double cdf_offset, double cdf_total,
+                                    int last_shard, const double* factor, const double* mean, uint64_t seed,
+                                    uint32_t epoch, double a_param, int scale, int64_t* idx_out_dev, double* z_out_dev,
+                                    void* stream) {
+    if (!in) return obe_fail("null cloud%s%s");
+    if (slot_begin < 0 || slot_end <= slot_begin || slot_end > n_total) return obe_fail("bad slot range%s%s");
+    return resample_systematic_impl(in, out, u0, factor, mean, seed, epoch, a_param, scale, idx_out_dev, z_out_dev, 1,
+                                    n_total, slot_begin, slot_end, cdf_offset, cdf_total, last_shard, stream);
+}
+
+int64_t obe_comb_count(double c, double u0, int64_t n_total) {
+    // host twin of the device comb count: #{i in [0,n) : (i + u0) * (1/n) < c}, same IEEE operations
+    const double nd = (double)n_total, inv_n = 1.0 / nd;
+    double i = ceil(c * nd - u0);
+    i = (i < 0.0) ? 0.0 : i;
+    i = (i > nd) ? nd : i;
+    volatile double t;
+    while (i > 0.0) { t = (i - 1.0) + u0; t = t * inv_n; if (t >= c) i -= 1.0; else break; }
+    while (i < nd) { t = i + u0; t = t * inv_n; if (t < c) i += 1.0; else break; }
+    return (int64_t)i;
 }
 
 struct SelectScratch {

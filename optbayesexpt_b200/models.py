@@ -139,7 +139,7 @@ def cuda_source(source, entry, n_settings, n_params, n_constants=0, n_channels=1
 class ParticleBuffers:
     """Device buffers of one particle cloud + the obe_cloud_t that describes them."""
 
-    def __init__(self, particles, device=None):
+    def __init__(self, particles, device=None, capacity=None):
         import torch
         lib = _lib.require_device()
         if isinstance(particles, torch.Tensor):
@@ -154,8 +154,9 @@ class ParticleBuffers:
             raise ValueError('empty particle cloud')
         self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
         self.n, self.d = int(n), int(d)
-        self.ld = self.n + (self.n & 1)
-        nt = int(lib.obe_num_tiles(self.n))
+        cap = max(int(capacity or 0), self.n)      # shards of a multi-GPU cloud change length
+        self.ld = cap + (cap & 1)
+        nt = int(lib.obe_num_tiles(self.ld))
         self.n_tiles = nt
         f64 = dict(dtype=torch.float64, device=self.device)
         self.particles = torch.zeros((self.d, self.ld), **f64)
@@ -167,7 +168,7 @@ class ParticleBuffers:
         self.tile_sums = torch.zeros(nt, **f64)
         self.tile_prefix = torch.zeros(nt + 1, **f64)
         self.stats = torch.zeros(_lib.STATS_LEN, **f64)
-        self.scratch = torch.zeros(int(lib.obe_scratch_bytes(self.n)), dtype=torch.uint8, device=self.device)
+        self.scratch = torch.zeros(int(lib.obe_scratch_bytes(self.ld)), dtype=torch.uint8, device=self.device)
         self._struct = None
 
     def empty_like(self, share_particles=False):
@@ -183,6 +184,13 @@ class ParticleBuffers:
         other.scratch = torch.zeros_like(self.scratch)
         other._struct = None
         return other
+
+    def resize(self, n):
+        """Change the live length (<= capacity); buffers are untouched."""
+        if n > self.ld:
+            raise ValueError(f'shard of {n} particles exceeds the buffer capacity {self.ld}')
+        self.n = int(n)
+        self._struct = None
 
     def struct(self):
         if self._struct is None:

@@ -53,7 +53,7 @@ class ParticlePDF:
     # plumbing
     # ------------------------------------------------------------------------------------------
     def _install(self, samples):
-        self._buf = ParticleBuffers(samples, self._device)
+        self._buf = ParticleBuffers(samples, self._device, capacity=getattr(self, '_capacity', None))
         self._alt = None
         self.n_particles = self._buf.n
         self.n_dims = self._buf.d

@@ -154,6 +154,17 @@ def std_biased_longdouble(particles, weights):
     return np.asarray(np.sqrt(msq - mean * mean), dtype=np.float64)
 
 
+def std_centered(particles, weights):
+    """sqrt(sum w (x - mean)^2) for normalised weights: algebraically the estimator of
+    particlepdf.py:209-214, without its cancellation (what the CUDA path's pivot-shifted
+    accumulators compute).  Use as the truth when E[x^2]/var is huge."""
+    p = np.asarray(particles, dtype=np.longdouble)
+    w = np.asarray(weights, dtype=np.longdouble)
+    w = w / w.sum()
+    mean = (p * w).sum(axis=1)
+    return np.asarray(np.sqrt((w * (p - mean[:, None]) ** 2).sum(axis=1)), dtype=np.float64)
+
+
 # ----------------------------------------------------------------------------
 # weighted draws  (particlepdf.py:312-345  ==  Generator.choice(p=w))
 # ----------------------------------------------------------------------------
