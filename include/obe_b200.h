@@ -60,6 +60,9 @@ typedef struct obe_cloud {
     int64_t ld;               /* row stride in doubles, even (16-byte aligned rows)          */
     int32_t d;                /* parameters per particle (1..OBE_MAX_PARAMS)                 */
     int32_t reserved;
+    int64_t* n_dev;           /* NULL, or a device int64 holding the LIVE particle count; `n` is
+                                 then only an upper bound (shards of a multi-GPU cloud change
+                                 length in a resample without the host being told)            */
 } obe_cloud_t;
 
 typedef struct obe_model* obe_model_t; /* opaque device functor for model_function */
@@ -162,6 +165,26 @@ int obe_resample_systematic_sharded(const obe_cloud_t* in, const obe_cloud_t* ou
                                     const double* factor, const double* mean, uint64_t seed,
                                     uint32_t epoch, double a_param, int scale, int64_t* idx_out_dev,
                                     double* z_out_dev, void* stream);
+/* Device-resident shard plan (no host round-trip between update, collective and resample):
+ * gathered_stats_dev = the all-gathered (world, OBE_STATS_DOUBLES) stats blocks.  Writes plan_dev
+ * (OBE_PLAN_DOUBLES doubles: CDF offset/total, slot bounds of every shard, global moments, Cholesky
+ * Liu-West factor, pre/post-resample shard totals), the global normaliser into local->stats_dev and
+ * the post-resample length of this shard into out->n_dev.  lazy=1: weights are un-normalised. */
+#define OBE_PLAN_DOUBLES 512
+#define OBE_PLAN_GSTATS 352     /* offset of the combined (global) stats block inside the plan  */
+#define OBE_PLAN_COUNTS 416     /* offset of the post-resample shard lengths                    */
+#define OBE_PLAN_OVERFLOW 9     /* 1.0 if this shard outgrew its buffer capacity                */
+int obe_shard_plan(const double* gathered_stats_dev, int rank, int world, int d, double u0,
+                   int64_t n_total, double a_param, int lazy, const obe_cloud_t* local,
+                   const obe_cloud_t* out, double* plan_dev, void* stream);
+/* obe_resample_systematic_sharded with every shard parameter read from plan_dev on the device. */
+int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* out, const double* plan_dev,
+                                    int64_t n_total, uint64_t seed, uint32_t epoch, double a_param,
+                                    int scale, void* stream);
+/* randdraw(K) over a sharded cloud: this rank writes the draws it owns (per plan_dev; post=1 uses the
+ * post-resample shard totals) and zeros elsewhere; an all-reduce(sum) of draws_dev completes it. */
+int obe_draw_planned(const obe_cloud_t* c, const double* u_host, int k, double* draws_dev,
+                     const double* plan_dev, int post, void* stream);
 /* weights <- 1/n_total for one shard of a cloud of n_total particles. */
 int obe_set_uniform_total(const obe_cloud_t* c, int64_t n_total, void* stream);
 /* Host twin of the device comb count #{i in [0,n_total) : (i + u0) * (1/n_total) < c}: shard

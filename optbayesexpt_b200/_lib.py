@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(HERE, 'libobe_b200.so')
 
 TILE = 2048
 STATS_LEN = 64
+PLAN_LEN = 512
+PLAN_GSTATS, PLAN_COUNTS, PLAN_OVERFLOW = 352, 416, 9
 MAX_PARAMS = 8
 MAX_CHANNELS = 4
 MAX_SETTINGS = 4
@@ -29,7 +31,8 @@ class Cloud(C.Structure):
     _fields_ = [('particles_dev', C.c_void_p), ('weights_dev', C.c_void_p),
                 ('tile_sums_dev', C.c_void_p), ('tile_prefix_dev', C.c_void_p),
                 ('stats_dev', C.c_void_p), ('scratch_dev', C.c_void_p),
-                ('n', C.c_int64), ('ld', C.c_int64), ('d', C.c_int32), ('reserved', C.c_int32)]
+                ('n', C.c_int64), ('ld', C.c_int64), ('d', C.c_int32), ('reserved', C.c_int32),
+                ('n_dev', C.c_void_p)]
 
 
 _PD = C.POINTER(C.c_double)
@@ -68,6 +71,11 @@ SIGNATURES = {
     'obe_resample_systematic_sharded': (C.c_int, [_PCLOUD, _PCLOUD, C.c_double, C.c_int64, C.c_int64, C.c_int64,
                                                   C.c_double, C.c_double, C.c_int, _PD, _PD, C.c_uint64, C.c_uint32,
                                                   C.c_double, C.c_int, _VP, _VP, _VP]),
+    'obe_shard_plan': (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64, C.c_double, C.c_int,
+                                 _PCLOUD, _PCLOUD, _VP, _VP]),
+    'obe_resample_systematic_planned': (C.c_int, [_PCLOUD, _PCLOUD, _VP, C.c_int64, C.c_uint64, C.c_uint32,
+                                                  C.c_double, C.c_int, _VP]),
+    'obe_draw_planned': (C.c_int, [_PCLOUD, _PD, C.c_int, _VP, _VP, C.c_int, _VP]),
     'obe_set_uniform_total': (C.c_int, [_PCLOUD, C.c_int64, _VP]),
     'obe_comb_count': (C.c_int64, [C.c_double, C.c_double, C.c_int64]),
     'obe_draw_strided': (C.c_int, [_PCLOUD, _PD, C.c_int, _VP, C.c_int, _VP, _VP]),

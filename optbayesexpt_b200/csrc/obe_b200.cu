@@ -228,9 +228,11 @@ __device__ __forceinline__ int block_excl_isum_1024(int v, int* sm /*34*/, int* 
 __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_tile_scan(const double* __restrict__ tile_sums,
                                                                 long long n_tiles, double* __restrict__ prefix,
                                                                 double* __restrict__ stats, int renormalise,
-                                                                long long uniform, long long n) {
+                                                                long long uniform, long long n,
+                                                                const long long* __restrict__ n_dev = nullptr) {
     __shared__ double sm[34];
     const int t = threadIdx.x;
+    if (n_dev) { n = *n_dev; n_tiles = (n + OBE_TILE - 1) / OBE_TILE; }
     double carry = 0.0;
     for (long long base = 0; base < n_tiles; base += OBE_SCAN_THREADS) {
         const long long k = base + t;
@@ -264,7 +266,9 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_tile_scan(const double* __
 }
 
 __global__ void k_fill_uniform(double* __restrict__ w, double* __restrict__ tile_sums, long long n,
-                               long long n_tiles, int write_weights, long long n_total) {
+                               long long n_tiles, int write_weights, long long n_total,
+                               const long long* __restrict__ n_dev = nullptr) {
+    if (n_dev) { n = *n_dev; n_tiles = (n + OBE_TILE - 1) / OBE_TILE; }
     const double v = 1.0 / (double)n_total;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -277,7 +281,8 @@ __global__ void k_fill_uniform(double* __restrict__ w, double* __restrict__ tile
 }
 
 __global__ void k_normalized_weights(const double* __restrict__ w, const double* __restrict__ stats,
-                                     double* __restrict__ out, long long n) {
+                                     double* __restrict__ out, long long n, const long long* __restrict__ n_dev) {
+    if (n_dev) n = *n_dev;
     const double inv = stats[OBE_ST_INVS];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x)
@@ -405,6 +410,9 @@ struct ObeDrawArgs {
     const double* w; const double* prefix; long long n; long long n_tiles;
     const double* particles; long long ld; int d;
     double* draws; long long* idx; int k;
+    const long long* n_dev;     // optional live count
+    const double* plan;         // optional shard plan: this rank draws only the uniforms it owns
+    int post;                   // use the post-resample shard totals of the plan
     double u[OBE_MAX_DRAWS];
 };
 // one block per draw: tile by binary search on the prefix, element by a canonical scan + count
@@ -412,17 +420,41 @@ __global__ void __launch_bounds__(OBE_THREADS) k_draw(const ObeDrawArgs a) {
     __shared__ double sm[8];
     __shared__ int cnt[OBE_THREADS / 32];
     const int q = blockIdx.x;
-    const double uq = a.u[q];
-    const double inv_total = 1.0 / a.prefix[a.n_tiles];
-    const long long k = find_tile(a.prefix, a.n_tiles, inv_total, uq);
+    double uq = a.u[q];
+    const long long n = a.n_dev ? *a.n_dev : a.n;
+    const long long n_tiles = a.n_dev ? (n + OBE_TILE - 1) / OBE_TILE : a.n_tiles;
+    if (a.plan) {
+        // sharded cloud: owner of u is the shard whose [offset, offset+total) holds u*T; the others
+        // contribute zeros to the all-reduce that follows
+        const int world = (int)a.plan[OBE_PL_WORLD], rank = (int)a.plan[OBE_PL_RANK];
+        const double* off = a.plan + (a.post ? OBE_PL_POST_OFF : OBE_PL_PRE_OFF);
+        const double* tot = a.plan + (a.post ? OBE_PL_POST_TOT : OBE_PL_PRE_TOT);
+        const double target = uq * (a.post ? a.plan[OBE_PL_POST_TOTAL] : a.plan[OBE_PL_TOTAL]);
+        int owner = 0;
+        for (int g = 0; g < world; ++g)
+            if (off[g] + tot[g] <= target) owner = g + 1;
+        owner = min(owner, world - 1);
+        while (owner > 0 && !(tot[owner] > 0.0)) --owner;
+        if (owner != rank) {
+            if (threadIdx.x == 0) {
+                if (a.idx) a.idx[q] = -1;
+                for (int j = 0; j < a.d; ++j) a.draws[(long long)j * a.k + q] = 0.0;
+            }
+            return;
+        }
+        uq = (target - off[rank]) / tot[rank];
+        uq = uq < 0.0 ? 0.0 : (uq > 0.99999999999999989 ? 0.99999999999999989 : uq);
+    }
+    const double inv_total = 1.0 / a.prefix[n_tiles];
+    const long long k = find_tile(a.prefix, n_tiles, inv_total, uq);
     double cn[OBE_EPT];
-    tile_cdf_blocked(a.w, a.prefix, k, a.n, inv_total, cn, sm);
+    tile_cdf_blocked(a.w, a.prefix, k, n, inv_total, cn, sm);
     const long long base = k * OBE_TILE;
     int c = 0;
 #pragma unroll
     for (int e = 0; e < OBE_EPT; ++e) {
         const long long i = base + (long long)threadIdx.x * OBE_EPT + e;
-        if (i < a.n && cn[e] <= uq) ++c;
+        if (i < n && cn[e] <= uq) ++c;
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
@@ -431,7 +463,7 @@ __global__ void __launch_bounds__(OBE_THREADS) k_draw(const ObeDrawArgs a) {
     if (threadIdx.x == 0) {
         int tot = 0;
         for (int w2 = 0; w2 < OBE_THREADS / 32; ++w2) tot += cnt[w2];
-        const long long last = min(a.n, base + OBE_TILE) - 1;
+        const long long last = min(n, base + OBE_TILE) - 1;
         const long long i = min(base + tot, last);
         if (a.idx) a.idx[q] = i;
         for (int j = 0; j < a.d; ++j) a.draws[(long long)j * a.k + q] = a.particles[j * a.ld + i];
@@ -523,6 +555,9 @@ struct ObeResampleArgs {
     long long slot_begin, slot_end; // global output slots owned by this shard's particles
     double cdf_offset;             // summed weight of the lower-ranked shards
     double cdf_total;              // global total weight
+    const long long* n_dev_in;     // optional live count of the input shard
+    const double* plan;            // optional device-resident shard plan (overrides the by-value shard fields)
+    long long cap_out;             // capacity of the output buffers (planned mode)
     double factor[OBE_MAX_DIMS * OBE_MAX_DIMS];
     double mean[OBE_MAX_DIMS];
 };
@@ -532,7 +567,10 @@ struct ObeResampleArgs {
 template <int D>
 __device__ __forceinline__ void setup_factor(const ObeResampleArgs& a, double* sF, double* sMean) {
     if (threadIdx.x == 0) {
-        if (!a.factor_from_stats) {
+        if (a.plan) {
+            for (int q = 0; q < D * D; ++q) sF[q] = a.plan[OBE_PL_FACTOR + q];
+            for (int j = 0; j < D; ++j) sMean[j] = a.plan[OBE_PL_MEAN + j];
+        } else if (!a.factor_from_stats) {
             for (int q = 0; q < D * D; ++q) sF[q] = a.factor[q];
             for (int j = 0; j < D; ++j) sMean[j] = a.mean[j];
         } else {
@@ -626,10 +664,18 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
                                                                long long n_total, double u0, double cdf_offset,
                                                                double cdf_total, long long slot_begin,
                                                                long long slot_end, long long* __restrict__ H,
-                                                               int* __restrict__ unit_start) {
+                                                               int* __restrict__ unit_start,
+                                                               const long long* __restrict__ n_dev = nullptr,
+                                                               const double* __restrict__ plan = nullptr) {
     __shared__ long long sml[34];
     __shared__ int smi[34];
     const int t = threadIdx.x;
+    if (n_dev) n_tiles = (*n_dev + OBE_TILE - 1) / OBE_TILE;
+    if (plan) {
+        n_total = (long long)plan[OBE_PL_NTOTAL]; u0 = plan[OBE_PL_U0];
+        cdf_offset = plan[OBE_PL_OFFSET]; cdf_total = plan[OBE_PL_TOTAL];
+        slot_begin = (long long)plan[OBE_PL_SLOT0]; slot_end = (long long)plan[OBE_PL_SLOT1];
+    }
     const double inv_total = 1.0 / (cdf_total > 0.0 ? cdf_total : prefix[n_tiles]);
     const double nd = (double)n_total, inv_n = 1.0 / nd, tol = 2e-15 * nd;
     long long carry = -1;
@@ -676,24 +722,32 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(
     __shared__ __align__(16) unsigned short anc_s[OBE_OUT_CHUNK];
     setup_factor<D>(a, sF, sMean);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double inv_total = 1.0 / (a.sharded ? a.cdf_total : a.prefix[a.n_tiles]);
-    const double nd = (double)a.n_total, inv_n = 1.0 / nd, wv = 1.0 / nd, tol = 2e-15 * nd;
-    const double cdf_offset = a.sharded ? a.cdf_offset : 0.0;
-    const bool last_shard = a.sharded ? (a.last_shard != 0) : true;
+    const long long n_in = a.n_dev_in ? *a.n_dev_in : a.n;
+    const long long n_tiles_in = a.n_dev_in ? (n_in + OBE_TILE - 1) / OBE_TILE : a.n_tiles;
+    const bool sharded = a.plan ? true : (a.sharded != 0);
+    const double cdf_total = a.plan ? a.plan[OBE_PL_TOTAL] : a.cdf_total;
+    const double u0 = a.plan ? a.plan[OBE_PL_U0] : a.u0;
+    const long long n_total = a.plan ? (long long)a.plan[OBE_PL_NTOTAL] : a.n_total;
+    const long long slot_begin = a.plan ? (long long)a.plan[OBE_PL_SLOT0] : a.slot_begin;
+    const double inv_total = 1.0 / (sharded ? cdf_total : a.prefix[n_tiles_in]);
+    const double nd = (double)n_total, inv_n = 1.0 / nd, wv = 1.0 / nd, tol = 2e-15 * nd;
+    const double cdf_offset = a.plan ? a.plan[OBE_PL_OFFSET] : (sharded ? a.cdf_offset : 0.0);
+    const bool last_shard = a.plan ? (a.plan[OBE_PL_LAST] != 0.0) : (sharded ? (a.last_shard != 0) : true);
+    const long long cap_out = a.plan ? a.cap_out : (1ll << 62);
     // the Liu-West factor in registers when it is small enough
     double Fr[D <= 4 ? D * D : 1];
     if (D <= 4) {
 #pragma unroll
         for (int q = 0; q < D * D; ++q) Fr[D <= 4 ? q : 0] = sF[q];
     }
-    const int n_units = a.unit_start[a.n_tiles];
+    const int n_units = a.unit_start[n_tiles_in];
     // contiguous range of units per block: one binary search, then a forward walk over the tiles
     const int per_block = (n_units + (int)gridDim.x - 1) / (int)gridDim.x;
     const int unit_lo = min((int)blockIdx.x * per_block, n_units);
     const int unit_hi = min(unit_lo + per_block, n_units);
     int k32 = 0;
     if (unit_lo < unit_hi) {
-        int lo = 0, hi = (int)a.n_tiles;       // first k with unit_start[k] > unit_lo
+        int lo = 0, hi = (int)n_tiles_in;      // first k with unit_start[k] > unit_lo
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (a.unit_start[mid] <= unit_lo) lo = mid + 1; else hi = mid;
@@ -711,9 +765,9 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(
         *reinterpret_cast<uint4*>(&anc_s[tid * OBE_EPT]) = make_uint4(0u, 0u, 0u, 0u);
         // ---- 1. end slot of every particle of the tile
         double cn[OBE_EPT];
-        tile_cdf_blocked(a.w_in, a.prefix, k, a.n, inv_total, cn, sm, cdf_offset, last_shard);
+        tile_cdf_blocked(a.w_in, a.prefix, k, n_in, inv_total, cn, sm, cdf_offset, last_shard);
         const long long base = k * OBE_TILE;
-        const long long last = min(a.n, base + OBE_TILE) - 1;
+        const long long last = min(n_in, base + OBE_TILE) - 1;
         int r[OBE_EPT];
         int run = 0;
 #pragma unroll
@@ -722,7 +776,7 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(
             int h;
             if (i >= last) h = span;
             else {
-                const double hd = comb_count_d(cn[e], a.u0, inv_n, nd, tol) - (double)Hk;   // exact: < 2^53
+                const double hd = comb_count_d(cn[e], u0, inv_n, nd, tol) - (double)Hk;     // exact: < 2^53
                 h = (hd < 0.0) ? 0 : (hd > (double)span ? span : (int)hd);
             }
             run = max(run, h);
@@ -788,7 +842,8 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(
         const int n_out = rel_end - rel_begin;
         for (int q = tid; q < n_out; q += OBE_THREADS) {
             const long long og = Hk + rel_begin + q;              // global slot: comb tooth, RNG counter
-            const long long o = og - a.slot_begin;                  // position in this shard's output
+            const long long o = og - slot_begin;                    // position in this shard's output
+            if (o >= cap_out) continue;                             // capacity overflow is flagged in the plan
             const long long anc = base + min((int)anc_s[q], (int)(last - base));
             double xv[D], z[D];
 #pragma unroll
@@ -808,6 +863,101 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(
         }
         __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shard plan: everything a rank must know about the other shards, computed ON THE DEVICE from the
+// all-gathered stats blocks so that update -> collective -> resample -> draws needs no host
+// round-trip.  One thread: G <= 64 shards, d <= 8 (a few hundred flops).  Restated on the host by
+// optbayesexpt_b200/sharded.py (combine_stats, moments_from, shard_slot_bounds), which the tests
+// compare it with.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_shard_plan(const double* __restrict__ gathered, int rank, int world, int d, double u0,
+                             long long n_total, double a_param, int lazy, long long cap_out,
+                             double* __restrict__ plan, double* __restrict__ stats_local,
+                             long long* __restrict__ n_out_dev) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nm2 = d * (d + 1) / 2;
+    double* gs = plan + OBE_PL_GSTATS;
+    for (int q = 0; q < OBE_STATS_LEN; ++q) gs[q] = 0.0;
+    double acc = 0.0;
+    for (int g = 0; g < world; ++g) {                 // the canonical inter-GPU exclusive scan
+        const double* st = gathered + (long long)g * OBE_STATS_LEN;
+        plan[OBE_PL_PRE_OFF + g] = acc;
+        plan[OBE_PL_PRE_TOT + g] = st[OBE_ST_TOTAL];
+        acc = acc + st[OBE_ST_TOTAL];
+        gs[OBE_ST_SUMSQ] += st[OBE_ST_SUMSQ];
+        gs[OBE_ST_SUMT] += st[OBE_ST_SUMT];
+        gs[OBE_ST_NZERO] += st[OBE_ST_NZERO];
+        for (int j = 0; j < d; ++j) gs[OBE_ST_M1 + j] += st[OBE_ST_M1 + j];
+        for (int j = 0; j < nm2; ++j) gs[OBE_ST_M2 + j] += st[OBE_ST_M2 + j];
+        for (int c = 0; c < OBE_MAX_CH; ++c) gs[OBE_ST_NOISE + c] += st[OBE_ST_NOISE + c];
+    }
+    const double total = acc;
+    for (int j = 0; j < d; ++j) gs[OBE_ST_PIVOT + j] = gathered[OBE_ST_PIVOT + j];
+    gs[OBE_ST_TOTAL] = total;
+    gs[OBE_ST_INVS] = lazy ? 1.0 / total : 1.0;
+    gs[OBE_ST_NEFF] = (total * total) / gs[OBE_ST_SUMSQ];
+    stats_local[OBE_ST_INVS] = gs[OBE_ST_INVS];       // the GLOBAL normaliser for the next update
+    // global mean, Cholesky factor of (1 - a^2) * cov
+    const double st = gs[OBE_ST_SUMT], fact = st - gs[OBE_ST_SUMSQ] / st, shrink = 1.0 - a_param * a_param;
+    double cov[OBE_MAX_DIMS][OBE_MAX_DIMS], L[OBE_MAX_DIMS][OBE_MAX_DIMS];
+    int q = 0;
+    for (int j = 0; j < d; ++j) {
+        plan[OBE_PL_MEAN + j] = gs[OBE_ST_PIVOT + j] + gs[OBE_ST_M1 + j] / st;
+        for (int k = j; k < d; ++k) {
+            const double c = (gs[OBE_ST_M2 + q] - gs[OBE_ST_M1 + j] * gs[OBE_ST_M1 + k] / st) / fact;
+            cov[j][k] = cov[k][j] = shrink * c;
+            ++q;
+        }
+    }
+    for (int j = 0; j < d; ++j)
+        for (int k = 0; k < d; ++k) L[j][k] = 0.0;
+    for (int j = 0; j < d; ++j) {
+        double sdiag = cov[j][j];
+        for (int k = 0; k < j; ++k) sdiag -= L[j][k] * L[j][k];
+        const double dj = sdiag > 0.0 ? sqrt(sdiag) : 0.0;
+        L[j][j] = dj;
+        for (int i = j + 1; i < d; ++i) {
+            double t = cov[i][j];
+            for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+            L[i][j] = dj > 0.0 ? t / dj : 0.0;
+        }
+    }
+    for (int k = 0; k < d; ++k)
+        for (int j = 0; j < d; ++j) plan[OBE_PL_FACTOR + k * d + j] = L[j][k];
+    // slot bounds of every shard: H_0 = 0, H_G = n_total, monotone
+    const double nd = (double)n_total, inv_n = 1.0 / nd, tol = 2e-15 * nd, inv_total = 1.0 / total;
+    long long prev = 0, mine0 = 0, mine1 = n_total;
+    double post_acc = 0.0;
+    const double wv = 1.0 / nd;
+    for (int g = 0; g < world; ++g) {
+        long long end = n_total;
+        if (g + 1 < world) {
+            end = (long long)comb_count_d(obe_mul(plan[OBE_PL_PRE_OFF + g + 1], inv_total), u0, inv_n, nd, tol);
+            end = min(max(end, prev), n_total);
+        }
+        if (g == rank) { mine0 = prev; mine1 = end; }
+        plan[OBE_PL_COUNTS + g] = (double)(end - prev);
+        plan[OBE_PL_POST_OFF + g] = post_acc;
+        plan[OBE_PL_POST_TOT + g] = (double)(end - prev) * wv;
+        post_acc = post_acc + (double)(end - prev) * wv;
+        prev = end;
+    }
+    plan[OBE_PL_POST_TOTAL] = post_acc;
+    plan[OBE_PL_OFFSET] = plan[OBE_PL_PRE_OFF + rank];
+    plan[OBE_PL_TOTAL] = total;
+    plan[OBE_PL_U0] = u0;
+    plan[OBE_PL_NTOTAL] = nd;
+    plan[OBE_PL_SLOT0] = (double)mine0;
+    plan[OBE_PL_SLOT1] = (double)mine1;
+    plan[OBE_PL_LAST] = (rank == world - 1) ? 1.0 : 0.0;
+    plan[OBE_PL_RANK] = (double)rank;
+    plan[OBE_PL_WORLD] = (double)world;
+    long long cnt = mine1 - mine0;
+    plan[OBE_PL_OVERFLOW] = (cnt > cap_out) ? 1.0 : 0.0;
+    if (cnt > cap_out) cnt = cap_out;
+    if (n_out_dev) *n_out_dev = cnt;
 }
 
 #define OBE_DIM_SWITCH(d, KERNEL, grid, st, args)                                     \
@@ -1094,7 +1244,7 @@ static int update_grid(const obe_cloud_t* c) {
 static void base_update_args(const obe_cloud_t* c, ObeUpdateArgs& a, const double* pivot) {
     memset(&a, 0, sizeof(a));
     const Scratch s = scratch_of(c);
-    a.particles = c->particles_dev; a.ld = c->ld; a.n = c->n;
+    a.particles = c->particles_dev; a.ld = c->ld; a.n = c->n; a.n_dev = (const long long*)c->n_dev;
     a.weights = c->weights_dev; a.tile_sums = c->tile_sums_dev;
     a.partials = s.partials; a.counter = s.counter; a.stats = c->stats_dev;
     for (int j = 0; j < OBE_MAX_CH; ++j) a.noise_idx[j] = -1;
@@ -1102,7 +1252,7 @@ static void base_update_args(const obe_cloud_t* c, ObeUpdateArgs& a, const doubl
 }
 static int finish_update(const obe_cloud_t* c, int renorm, cudaStream_t st) {
     k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(c->tile_sums_dev, obe_num_tiles(c->n), c->tile_prefix_dev,
-                                               c->stats_dev, renorm, 0, c->n);
+                                               c->stats_dev, renorm, 0, c->n, (const long long*)c->n_dev);
     OBE_LAUNCH_CHECK("k_tile_scan");
     return 0;
 }
@@ -1129,11 +1279,12 @@ int obe_set_uniform(const obe_cloud_t* c, void* stream) {
     if (check_cloud(c)) return -1;
     cudaStream_t st = (cudaStream_t)stream;
     int grid = obe_sms() * 8;
-    k_fill_uniform<<<grid, 256, 0, st>>>(c->weights_dev, c->tile_sums_dev, c->n, obe_num_tiles(c->n), 1, c->n);
+    k_fill_uniform<<<grid, 256, 0, st>>>(c->weights_dev, c->tile_sums_dev, c->n, obe_num_tiles(c->n), 1, c->n,
+                                         (const long long*)c->n_dev);
     OBE_LAUNCH_CHECK("k_fill_uniform");
     OBE_CUDA(cudaMemsetAsync(c->stats_dev, 0, OBE_STATS_LEN * sizeof(double), st));
     k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(c->tile_sums_dev, obe_num_tiles(c->n), c->tile_prefix_dev,
-                                               c->stats_dev, 0, c->n, c->n);
+                                               c->stats_dev, 0, c->n, c->n, (const long long*)c->n_dev);
     OBE_LAUNCH_CHECK("k_tile_scan");
     return 0;
 }
@@ -1142,11 +1293,12 @@ int obe_set_uniform_total(const obe_cloud_t* c, int64_t n_total, void* stream) {
     if (check_cloud(c)) return -1;
     if (n_total < c->n) return obe_fail("n_total < n%s%s");
     cudaStream_t st = (cudaStream_t)stream;
-    k_fill_uniform<<<obe_sms() * 8, 256, 0, st>>>(c->weights_dev, c->tile_sums_dev, c->n, obe_num_tiles(c->n), 1, n_total);
+    k_fill_uniform<<<obe_sms() * 8, 256, 0, st>>>(c->weights_dev, c->tile_sums_dev, c->n, obe_num_tiles(c->n), 1, n_total,
+                                                  (const long long*)c->n_dev);
     OBE_LAUNCH_CHECK("k_fill_uniform");
     OBE_CUDA(cudaMemsetAsync(c->stats_dev, 0, OBE_STATS_LEN * sizeof(double), st));
     k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(c->tile_sums_dev, obe_num_tiles(c->n), c->tile_prefix_dev,
-                                               c->stats_dev, 0, n_total, c->n);
+                                               c->stats_dev, 0, n_total, c->n, (const long long*)c->n_dev);
     OBE_LAUNCH_CHECK("k_tile_scan");
     return 0;
 }
@@ -1220,7 +1372,8 @@ int obe_fetch_stats(const obe_cloud_t* c, double* stats_host, void* stream) {
 
 int obe_normalized_weights(const obe_cloud_t* c, double* out_dev, void* stream) {
     if (check_cloud(c)) return -1;
-    k_normalized_weights<<<obe_sms() * 8, 256, 0, (cudaStream_t)stream>>>(c->weights_dev, c->stats_dev, out_dev, c->n);
+    k_normalized_weights<<<obe_sms() * 8, 256, 0, (cudaStream_t)stream>>>(c->weights_dev, c->stats_dev, out_dev, c->n,
+                                                                          (const long long*)c->n_dev);
     OBE_LAUNCH_CHECK("k_normalized_weights");
     return 0;
 }
@@ -1248,7 +1401,7 @@ int obe_search(const obe_cloud_t* c, const double* cdf_dev, const double* u_dev,
 
 static int draw_impl(const double* w, const double* prefix, int64_t n, const double* particles, int64_t ld, int d,
                      const double* u_host, int k, double* draws_dev, int64_t* idx_dev, cudaStream_t st,
-                     int ld_draws = 0) {
+                     int ld_draws = 0, const long long* n_dev = nullptr, const double* plan = nullptr, int post = 0) {
     if (k <= 0) return 0;
     for (int off = 0; off < k; off += OBE_MAX_DRAWS) {
         const int kk = (k - off) < OBE_MAX_DRAWS ? (k - off) : OBE_MAX_DRAWS;
@@ -1258,6 +1411,7 @@ static int draw_impl(const double* w, const double* prefix, int64_t n, const dou
         a.draws = draws_dev ? draws_dev + off : nullptr;
         a.idx = idx_dev ? (long long*)idx_dev + off : nullptr;
         a.k = ld_draws > 0 ? ld_draws : k;
+        a.n_dev = n_dev; a.plan = plan; a.post = post;
         for (int i = 0; i < kk; ++i) a.u[i] = u_host[off + i];
         k_draw<<<kk, OBE_THREADS, 0, st>>>(a);
         OBE_LAUNCH_CHECK("k_draw");
@@ -1269,15 +1423,23 @@ int obe_draw(const obe_cloud_t* c, const double* u_host, int k, double* draws_de
     if (check_cloud(c)) return -1;
     if (!u_host || !draws_dev) return obe_fail("null argument%s%s");
     return draw_impl(c->weights_dev, c->tile_prefix_dev, c->n, c->particles_dev, c->ld, c->d, u_host, k, draws_dev,
-                     idx_dev, (cudaStream_t)stream);
+                     idx_dev, (cudaStream_t)stream, 0, (const long long*)c->n_dev);
+}
+
+int obe_draw_planned(const obe_cloud_t* c, const double* u_host, int k, double* draws_dev, const double* plan_dev,
+                     int post, void* stream) {
+    if (check_cloud(c)) return -1;
+    if (!u_host || !draws_dev || !plan_dev) return obe_fail("null argument%s%s");
+    return draw_impl(c->weights_dev, c->tile_prefix_dev, c->n, c->particles_dev, c->ld, c->d, u_host, k, draws_dev,
+                     nullptr, (cudaStream_t)stream, 0, (const long long*)c->n_dev, plan_dev, post);
 }
 
 static int finish_resample(const obe_cloud_t* out, int64_t n_total, cudaStream_t st) {
     k_fill_uniform<<<obe_sms() * 2, 256, 0, st>>>(out->weights_dev, out->tile_sums_dev, out->n, obe_num_tiles(out->n), 0,
-                                                 n_total);
+                                                 n_total, (const long long*)out->n_dev);
     OBE_LAUNCH_CHECK("k_fill_uniform");
     k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(out->tile_sums_dev, obe_num_tiles(out->n), out->tile_prefix_dev,
-                                               out->stats_dev, 0, n_total, out->n);
+                                               out->stats_dev, 0, n_total, out->n, (const long long*)out->n_dev);
     OBE_LAUNCH_CHECK("k_tile_scan");
     return 0;
 }
@@ -1377,6 +1539,44 @@ int obe_resample_systematic_sharded(const obe_cloud_t* in, const obe_cloud_t* ou
     if (slot_begin < 0 || slot_end <= slot_begin || slot_end > n_total) return obe_fail("bad slot range%s%s");
     return resample_systematic_impl(in, out, u0, factor, mean, seed, epoch, a_param, scale, idx_out_dev, z_out_dev, 1,
                                     n_total, slot_begin, slot_end, cdf_offset, cdf_total, last_shard, stream);
+}
+
+int obe_shard_plan(const double* gathered_stats_dev, int rank, int world, int d, double u0, int64_t n_total,
+                   double a_param, int lazy, const obe_cloud_t* local, const obe_cloud_t* out, double* plan_dev,
+                   void* stream) {
+    if (!gathered_stats_dev || !plan_dev || !local) return obe_fail("null argument%s%s");
+    if (world < 1 || world > OBE_MAX_SHARDS || rank < 0 || rank >= world) return obe_fail("bad rank/world%s%s");
+    if (d < 1 || d > OBE_MAX_DIMS) return obe_fail("n_params must be 1..8%s%s");
+    k_shard_plan<<<1, 32, 0, (cudaStream_t)stream>>>(gathered_stats_dev, rank, world, d, u0, n_total, a_param, lazy,
+                                                    out ? out->ld : (1ll << 62), plan_dev, local->stats_dev,
+                                                    out ? (long long*)out->n_dev : nullptr);
+    OBE_LAUNCH_CHECK("k_shard_plan");
+    return 0;
+}
+
+int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* out, const double* plan_dev,
+                                    int64_t n_total, uint64_t seed, uint32_t epoch, double a_param, int scale,
+                                    void* stream) {
+    if (!plan_dev) return obe_fail("null plan%s%s");
+    if (!out || !out->n_dev) return obe_fail("planned resample needs out->n_dev%s%s");
+    ObeResampleArgs a;
+    double dummy[OBE_MAX_DIMS * OBE_MAX_DIMS] = {0};
+    if (fill_resample_args(in, out, dummy, dummy, a_param, scale, seed, epoch, a)) return -1;
+    const Scratch s = scratch_of(in);
+    a.plan_h = s.plan_h; a.unit_start = s.unit_start;
+    a.plan = plan_dev; a.n_dev_in = (const long long*)in->n_dev; a.cap_out = out->ld;
+    a.sharded = 1; a.n_total = n_total;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0, s.plan_h,
+                                              s.unit_start, (const long long*)in->n_dev, plan_dev);
+    OBE_LAUNCH_CHECK("k_sys_plan");
+    int64_t max_units = a.n_tiles + (out->ld + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK;
+    int64_t g = (int64_t)obe_sms() * OBE_BLOCKS_PER_SM;
+    if (g > max_units) g = max_units;
+    const int grid = (int)g;
+    OBE_DIM_SWITCH(in->d, k_sys_resample, grid, st, a)
+    OBE_LAUNCH_CHECK("k_sys_resample");
+    return finish_resample(out, n_total, st);
 }
 
 int64_t obe_comb_count(double c, double u0, int64_t n_total) {

@@ -47,6 +47,29 @@
 #define OBE_STATS_LEN 64
 #define OBE_NACC_MAX (2 + OBE_MAX_DIMS + 36 + OBE_MAX_CH + 1)
 
+// shard plan block (doubles; integers stored exactly), written by k_shard_plan
+#define OBE_PL_OFFSET 0      /* summed weight of the lower-ranked shards */
+#define OBE_PL_TOTAL 1       /* global weight total */
+#define OBE_PL_U0 2
+#define OBE_PL_NTOTAL 3
+#define OBE_PL_SLOT0 4       /* first global comb slot owned by this shard */
+#define OBE_PL_SLOT1 5
+#define OBE_PL_LAST 6        /* 1 on the shard holding the global last particle */
+#define OBE_PL_RANK 7
+#define OBE_PL_WORLD 8
+#define OBE_PL_OVERFLOW 9    /* 1 if a shard outgrew its capacity */
+#define OBE_PL_POST_TOTAL 10 /* sum of the post-resample shard totals */
+#define OBE_PL_FACTOR 16     /* [64] Liu-West factor, z @ F convention */
+#define OBE_PL_MEAN 80       /* [8] */
+#define OBE_PL_PRE_OFF 96    /* [64] shard offsets of the CURRENT weights */
+#define OBE_PL_PRE_TOT 160   /* [64] shard totals of the current weights */
+#define OBE_PL_POST_OFF 224  /* [64] the same after the planned resample (uniform weights) */
+#define OBE_PL_POST_TOT 288  /* [64] */
+#define OBE_PL_GSTATS 352    /* [64] combined stats block (global TOTAL, INVS, SUMSQ, NEFF, M1, M2, ...) */
+#define OBE_PL_COUNTS 416    /* [64] post-resample shard lengths */
+#define OBE_PLAN_LEN 512
+#define OBE_MAX_SHARDS 64
+
 // likelihood source for obe_update_body
 #define OBE_SRC_MODEL 0  /* evaluate the model functor */
 #define OBE_SRC_Y 1      /* y_model supplied (pdf_update(..., y_model_data)) */
@@ -65,6 +88,7 @@ struct ObeUpdateArgs {
     const double* y_model;   // OBE_SRC_Y: (n_channels, ld_y)
     long long ld_y;
     const double* lik;       // OBE_SRC_LIK: (n)
+    const long long* n_dev;  // optional: live particle count on the device (n is then an upper bound)
     int scale_in;            // 1: w_in = nan_to_num(t * stats[INVS]); 0: raw t
     int write_weights;
     int n_lik_channels;      // min(C, len(y_meas), len(sigma))  -- zip truncation
@@ -422,7 +446,7 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const long long n = a.n;
+    const long long n = a.n_dev ? *a.n_dev : a.n;
     const long long n_tiles = (n + OBE_TILE - 1) / OBE_TILE;
     // rows actually staged: weights, D particle rows, then the optional extras
     const int n_rows_live = 1 + D + (SRC == OBE_SRC_Y ? a.n_lik_channels : 0) + (SRC == OBE_SRC_LIK ? 1 : 0);

@@ -183,7 +183,16 @@ class ParticleBuffers:
         other.stats = torch.zeros_like(self.stats)
         other.scratch = torch.zeros_like(self.scratch)
         other._struct = None
+        if getattr(self, 'n_dev', None) is not None:
+            other.n_dev = self.n_dev.clone()
         return other
+
+    def enable_device_count(self):
+        """Keep the live particle count in a device int64 (sharded clouds): `n` becomes a bound."""
+        import torch
+        self.n_dev = torch.tensor([self.n], dtype=torch.int64, device=self.device)
+        self.n = self.ld            # the struct's n is now only the bound the grids are sized for
+        self._struct = None
 
     def resize(self, n):
         """Change the live length (<= capacity); buffers are untouched."""
@@ -194,8 +203,10 @@ class ParticleBuffers:
 
     def struct(self):
         if self._struct is None:
+            n_dev = getattr(self, 'n_dev', None)
             self._struct = _lib.Cloud(self.particles.data_ptr(), self.weights.data_ptr(),
                                       self.tile_sums.data_ptr(), self.tile_prefix.data_ptr(),
                                       self.stats.data_ptr(), self.scratch.data_ptr(),
-                                      self.n, self.ld, self.d, 0)
+                                      self.n, self.ld, self.d, 0,
+                                      None if n_dev is None else n_dev.data_ptr())
         return self._struct

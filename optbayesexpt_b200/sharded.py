@@ -167,12 +167,29 @@ class Comm:
 
 
 # --------------------------------------------------------------------------------------------------
+def gstats_from_plan(plan_host, d, world):
+    """The combined-stats dict (same keys as combine_stats) from a fetched plan block."""
+    g = plan_host[_lib.PLAN_GSTATS:_lib.PLAN_GSTATS + _lib.STATS_LEN]
+    nm2 = d * (d + 1) // 2
+    return dict(totals=plan_host[160:160 + world].copy(), offsets=plan_host[96:96 + world].copy(),
+                total=float(g[_lib.ST_TOTAL]), sumsq=float(g[_lib.ST_SUMSQ]), sumt=float(g[_lib.ST_SUMT]),
+                m1=g[_lib.ST_M1:_lib.ST_M1 + d].copy(), m2=g[_lib.ST_M2:_lib.ST_M2 + nm2].copy(),
+                noise=g[_lib.ST_NOISE:_lib.ST_NOISE + 4].copy(), pivot=g[_lib.ST_PIVOT:_lib.ST_PIVOT + d].copy())
+
+
 class ShardedOptBayesExpt(OptBayesExpt):
     """OptBayesExpt over a cloud sharded across the ranks of a process group.
 
     ``parameter_samples`` is THIS rank's shard (d, n_local); ``setting_values`` is the full grid on
     every rank.  All ranks must pass the same ``seed`` (the comb offset u0 and the K uniforms are
-    drawn from identically seeded Generators so that every rank takes the same decisions)."""
+    drawn from identically seeded Generators so that every rank takes the same decisions).
+
+    After every update the stats blocks are all-gathered and ``k_shard_plan`` turns them, on the
+    device, into the shard plan (global normaliser and moments, Cholesky factor, CDF offsets, comb
+    slot bounds of every shard): ``run_cycle_async`` enqueues update -> all-gather -> plan ->
+    resample -> draws -> all-reduce -> utility with no host synchronisation at all; the
+    reference-shaped ``pdf_update``/``opt_setting`` fetch the plan block only to take the
+    resample decision and to return the argmax."""
 
     def __init__(self, measurement_model, setting_values, parameter_samples, constants, group=None,
                  slack=0.25, seed=0, **kwargs):
@@ -183,71 +200,103 @@ class ShardedOptBayesExpt(OptBayesExpt):
         n_local = parameter_samples.shape[-1]
         self._capacity = int(n_local * (1.0 + slack)) + 2 * _lib.TILE     # shard lengths float
         self._gstats = None
+        self._plan_valid = False
+        self._n_local = None
         OptBayesExpt.__init__(self, measurement_model, setting_values, parameter_samples, constants, **kwargs)
         dev = self._buf.device
-        counts = self._comm.allgather(torch.tensor([self.n_particles], dtype=torch.int64, device=dev))
-        self._counts = counts.cpu().numpy().reshape(-1).astype(np.int64)
-        self.n_total = int(self._counts.sum())
+        self._buf.enable_device_count()
+        self._alt = self._buf.empty_like()
+        counts = self._comm.allgather(torch.tensor([self._n_local], dtype=torch.int64, device=dev))
+        self.n_total = int(counts.sum().item())
+        self._plan = torch.zeros(_lib.PLAN_LEN, dtype=torch.float64, device=dev)
         self._check(self._lib.obe_set_uniform_total(self._cs(), self.n_total, self._stream()))
-        # slice of the setting grid this rank evaluates
         n_set = len(self.setting_indices)
         self._s_lo, self._s_hi = setting_slice(n_set, self._comm.rank, self._comm.world)
-        # a common pivot for the shifted moments: rank 0's estimate
-        piv = torch.from_numpy(self._pivot.copy()).to(dev)
+        piv = torch.from_numpy(self._pivot.copy()).to(dev)     # a common pivot: rank 0's estimate
         self._pivot = self._comm.allgather(piv)[0].cpu().numpy()
+        self._section = 0          # 0: draw with the plan's current-weight totals, 1: post-resample
+        self._make_plan()
+
+    # ---- the live shard length lives on the device
+    @property
+    def n_particles(self):
+        if self._n_local is None:
+            self._n_local = int(self._buf.n_dev.item())
+        return self._n_local
+
+    @n_particles.setter
+    def n_particles(self, value):
+        self._n_local = int(value)
 
     def _invalidate(self, particles=False, weights=True):
         OptBayesExpt._invalidate(self, particles, weights)
         if weights:
             self._gstats = None
+            self._plan_valid = False
 
-    # ---- global stats
-    def _sync_global_stats(self):
-        """all-gather the stats blocks, combine, and install the global normaliser on the device."""
-        gathered = self._comm.allgather(self._buf.stats).cpu().numpy()
-        self._stats = gathered[self._comm.rank].copy()
-        self._gstats = combine_stats(gathered, self.n_dims)
-        self._gmom = moments_from(self._gstats, self.n_dims)
+    # ---- plan
+    def _make_plan(self):
+        """all-gather the stats blocks -> k_shard_plan (device).  Asynchronous."""
+        gathered = self._comm.allgather(self._buf.stats)
+        self._u0 = float(self.rng.random())                 # identical on every rank
+        self._check(self._lib.obe_shard_plan(C.c_void_p(gathered.data_ptr()), self._comm.rank, self._comm.world,
+                                             self.n_dims, self._u0, self.n_total,
+                                             float(self.tuning_parameters['a_param']), 1 if self._weights_lazy else 0,
+                                             self._cs(), self._cs(self._alt), C.c_void_p(self._plan.data_ptr()),
+                                             self._stream()))
+        self._keep = gathered
+        self._plan_valid = True
+        self._section = 0
+        self._gstats = None
+
+    def _fetch_plan(self):
+        """Bring the plan block to the host (synchronises): global stats, counts, overflow flag."""
+        if not self._plan_valid or not self._moments_valid:
+            if not self._moments_valid:
+                ni = self._noise_index
+                self._check(self._lib.obe_refresh(self._cs(), 0, 0, _lib.iarr(ni), 0 if ni is None else len(ni),
+                                                  _lib.darr(self._pivot, _lib.MAX_PARAMS), 0, self._stream()))
+                self._moments_valid = True
+            self._make_plan()
+        if self._gstats is None:
+            ph = self._plan.cpu().numpy()
+            if ph[_lib.PLAN_OVERFLOW] != 0.0:
+                raise RuntimeError('a shard outgrew its buffer capacity in a resample; raise `slack`')
+            self._plan_host = ph
+            self._gstats = gstats_from_plan(ph, self.n_dims, self._comm.world)
+            self._gmom = moments_from(self._gstats, self.n_dims)
+            self._stats = ph[_lib.PLAN_GSTATS:_lib.PLAN_GSTATS + _lib.STATS_LEN].copy()
         return self._gstats
-
-    def _install_global_normaliser(self):
-        gs = self._sync_global_stats()
-        self._buf.stats[_lib.ST_INVS:_lib.ST_INVS + 1].fill_((1.0 / gs['total']) if self._weights_lazy else 1.0)
-        self._moments_valid = True
-        return gs
 
     def _after_update(self):
         self._invalidate()
         self._weights_uniform = False
         self._weights_lazy = True
-        self._install_global_normaliser()
+        self._moments_valid = True
+        self._make_plan()
+        self._fetch_plan()
         self._pivot = self._gmom[0].copy()
         if self.tuning_parameters['auto_resample']:
             self.resample_test()
 
     def _ensure_moments(self):
-        if self._gstats is None:
-            if not self._moments_valid:      # device stats are stale too: one refresh pass
-                ni = self._noise_index
-                self._check(self._lib.obe_refresh(self._cs(), 0, 0, _lib.iarr(ni), 0 if ni is None else len(ni),
-                                                  _lib.darr(self._pivot, _lib.MAX_PARAMS), 0, self._stream()))
-            self._install_global_normaliser()
+        self._fetch_plan()
         return self._stats
 
     def mean(self):
-        self._ensure_moments()
+        self._fetch_plan()
         return self._gmom[0].copy()
 
     def covariance(self):
-        self._ensure_moments()
+        self._fetch_plan()
         return self._gmom[1].copy()
 
     def std(self):
-        self._ensure_moments()
+        self._fetch_plan()
         return np.sqrt(np.maximum(self._gmom[2], 0.0))
 
     def n_eff(self):
-        self._ensure_moments()
+        self._fetch_plan()
         return float(self._gmom[3])
 
     def resample_test(self):
@@ -264,69 +313,41 @@ class ShardedOptBayesExpt(OptBayesExpt):
         else:
             self.just_resampled = False
 
-    # ---- resample: every shard keeps its own offspring
+    # ---- resample: every shard keeps its own offspring; all parameters come from the device plan
     def resample(self):
-        self._ensure_moments()
-        gs = self._gstats
-        a_param = float(self.tuning_parameters['a_param'])
-        scale = 1 if self.tuning_parameters['scale'] else 0
+        if not self._plan_valid or self._section != 0:
+            self._plan_valid = False if self._section != 0 else self._plan_valid
+            self._fetch_plan()
         self._epoch += 1
-        u0 = float(self.rng.random())                       # identical on every rank
-        bounds = shard_slot_bounds(gs['offsets'], gs['total'], u0, self.n_total, self._lib.obe_comb_count)
-        r = self._comm.rank
-        lo, hi = bounds[r], bounds[r + 1]
-        if hi - lo < 1:
-            raise RuntimeError('a shard lost all its particles in a resample; rebalance is not implemented')
-        mean, cov = self._gmom[0], self._gmom[1]
-        newcov = (1.0 - a_param ** 2) * cov
-        try:
-            factor = np.ascontiguousarray(np.linalg.cholesky(newcov).T)
-        except np.linalg.LinAlgError:
-            (uu, ss, _) = np.linalg.svd(newcov)
-            factor = np.ascontiguousarray((uu * np.sqrt(ss)).T)
-        if self._alt is None:
-            self._alt = self._buf.empty_like()
-        self._alt.resize(hi - lo)
-        self._check(self._lib.obe_resample_systematic_sharded(
-            self._cs(), self._cs(self._alt), u0, self.n_total, lo, hi, float(gs['offsets'][r]), float(gs['total']),
-            1 if r == self._comm.world - 1 else 0, _lib.darr(factor.reshape(-1)), _lib.darr(mean),
-            self._philox_seed, self._epoch, a_param, scale, None, None, self._stream()))
+        self._check(self._lib.obe_resample_systematic_planned(
+            self._cs(), self._cs(self._alt), C.c_void_p(self._plan.data_ptr()), self.n_total, self._philox_seed,
+            self._epoch, float(self.tuning_parameters['a_param']), 1 if self.tuning_parameters['scale'] else 0,
+            self._stream()))
         self._buf, self._alt = self._alt, self._buf
-        self.n_particles = self._buf.n
-        self._counts = np.diff(np.asarray(bounds, dtype=np.int64))
-        self._invalidate(particles=True)
+        self._n_local = None
+        OptBayesExpt._invalidate(self, particles=True)
+        self._gstats = None
         self._stats = None
         self._moments_valid = False
         self._weights_uniform = True
         self._weights_lazy = False
+        self._section = 1           # the plan stays valid for draws: its post-resample totals apply
 
-    def _cdf_totals(self):
-        """(offsets, totals, total) of the current weights, for the assignment of the draws."""
-        if self._gstats is None and self._weights_uniform:
-            totals = self._counts.astype(np.float64) * (1.0 / self.n_total)
-            offsets = np.zeros_like(totals)
-            acc = 0.0
-            for r in range(len(totals)):
-                offsets[r] = acc
-                acc = acc + totals[r]
-            return offsets, totals, acc
-        self._ensure_moments()
-        return self._gstats['offsets'], self._gstats['totals'], self._gstats['total']
+    @property
+    def shard_counts(self):
+        """Lengths of all shards (synchronises)."""
+        import torch
+        return self._comm.allgather(self._buf.n_dev).cpu().numpy().reshape(-1)
 
-    # ---- K draws through the sharded CDF
+    # ---- K draws through the sharded CDF: owners write, everyone else adds zeros
     def _randdraw_dev(self, n_draws):
         import torch
+        if not self._plan_valid:
+            self._fetch_plan()
         u = self.rng.random(n_draws)                        # identical on every rank
-        offsets, totals, total = self._cdf_totals()
-        owner, local = assign_draws(u, offsets, totals, total)
-        order = np.argsort(owner, kind='stable')
-        draws = torch.zeros((self.n_dims, n_draws), dtype=torch.float64, device=self._buf.device)
-        mine = order[owner[order] == self._comm.rank]
-        if len(mine):
-            col0 = int(np.sum(owner < self._comm.rank))
-            ptr = C.c_void_p(draws.data_ptr() + 8 * col0)
-            self._check(self._lib.obe_draw_strided(self._cs(), _lib.darr(local[mine]), len(mine), ptr,
-                                                   int(n_draws), None, self._stream()))
+        draws = torch.empty((self.n_dims, n_draws), dtype=torch.float64, device=self._buf.device)
+        self._check(self._lib.obe_draw_planned(self._cs(), _lib.darr(u), int(n_draws), C.c_void_p(draws.data_ptr()),
+                                               C.c_void_p(self._plan.data_ptr()), self._section, self._stream()))
         self._comm.allreduce_sum(draws)
         return draws
 
@@ -392,11 +413,10 @@ class ShardedOptBayesExpt(OptBayesExpt):
         return tuple(self.allsettings[:, goodindex])
 
     def run_cycle_async(self, measurement_record, resample=True, select=True):
-        """Sharded cycle: the update kernels are asynchronous, but the global normaliser, the shard
-        slot bounds and the argmax come from gathered stats on the host (one small collective +
-        one synchronisation per phase)."""
+        """Sharded cycle with NO host synchronisation: update -> all-gather(stats) -> device plan ->
+        planned resample -> owner-written draws -> all-reduce -> utility over this rank's grid slice."""
         OptBayesExpt.run_cycle_async(self, measurement_record, resample=False, select=False)
-        self._install_global_normaliser()
+        self._make_plan()
         if resample:
             self.resample()
             self.just_resampled = True

@@ -42,7 +42,11 @@ def _worker(rank, world, port, out):
             warnings.simplefilter('ignore', RuntimeWarning)
             for eng_ in (eng, ref):
                 eng_.tuning_parameters['auto_resample'] = False
+            def same_stream(seed):
+                eng.rng = np.random.default_rng(seed)
+                ref.rng = np.random.default_rng(seed)
             # design half: same uniforms -> same draws -> same utility -> same argmax
+            same_stream(1)
             s1, s2 = eng.opt_setting(), ref.opt_setting()
             assert eng.last_setting_index == ref.last_setting_index and s1 == s2
             # inference half
@@ -54,9 +58,23 @@ def _worker(rank, world, port, out):
             np.testing.assert_allclose(eng.std(), ref.std(), rtol=1e-10)
             np.testing.assert_allclose(eng.n_eff(), ref.n_eff(), rtol=1e-12)
             np.testing.assert_allclose(eng.particle_weights, ref.particle_weights[lo:hi], rtol=1e-12)
+            # the device-side shard plan against its host restatement
+            from optbayesexpt_b200 import sharded as sh, _lib
+            gs_dev = eng._fetch_plan()
+            gs_host = sh.combine_stats(eng._keep.cpu().numpy(), eng.n_dims)
+            for key in ('totals', 'offsets', 'm1', 'm2', 'pivot'):
+                np.testing.assert_array_equal(gs_dev[key], gs_host[key], err_msg=key)
+            assert gs_dev['total'] == gs_host['total'] and gs_dev['sumsq'] == gs_host['sumsq']
+            bounds = sh.shard_slot_bounds(gs_host['offsets'], gs_host['total'], eng._u0, n, _lib.load().obe_comb_count)
+            np.testing.assert_array_equal(eng._plan_host[_lib.PLAN_COUNTS:_lib.PLAN_COUNTS + world], np.diff(bounds))
+            mean_h, cov_h, _, _ = sh.moments_from(gs_host, eng.n_dims)
+            f_host = np.linalg.cholesky((1 - 0.98 ** 2) * cov_h).T
+            np.testing.assert_allclose(eng._plan_host[16:16 + 9].reshape(3, 3), f_host, rtol=1e-12, atol=1e-300)
+            same_stream(2)
             s1, s2 = eng.opt_setting(), ref.opt_setting()
             assert eng.last_setting_index == ref.last_setting_index
-            np.testing.assert_allclose(eng.utility(), ref.utility(), rtol=1e-9)   # fresh draws, same stream
+            same_stream(3)
+            np.testing.assert_array_equal(eng.utility(), ref.utility())   # same draws -> bit-identical utility
             # second update on lazily normalised weights, then a resample on both
             rec = (s1, 49900.0, 500.0)
             eng.pdf_update(rec)
@@ -66,10 +84,13 @@ def _worker(rank, world, port, out):
             ref.rng = np.random.default_rng(5)
             eng._philox_seed = ref._philox_seed = 4242
             eng._epoch = ref._epoch = 0
+            ref.rng = np.random.default_rng(5)
+            ref.rng.random()                    # the comb offset the sharded plan drew at the update
+            ref.rng = type('R', (), {'random': staticmethod(lambda *a: eng._u0)})()
             eng.resample()
             ref.resample()
         # shard lengths float; together the shards are the single engine's cloud, in order
-        counts = eng._counts
+        counts = eng.shard_counts
         assert counts.sum() == n and eng.n_particles == counts[rank]
         start = int(counts[:rank].sum())
         got = eng.particles
