@@ -218,6 +218,53 @@ int obe_eval_settings(obe_model_t m, const double* settings_dev, int64_t lds, in
                       const double* params, const double* constants, double* y_dev, int64_t ldy,
                       void* stream);
 
+/* ---- batched independent instances (BASELINE config c5: B engines x n particles each) -------- */
+/* One SoA cloud: instance b owns particles [b*np, b*np + n) of (d, ld) arrays, np = n rounded up to
+ * whole tiles, ld >= n_inst*np.  Two buffers; cur_dev[b] says which one holds instance b (a resample
+ * writes the other and flips it).  Per instance: record (setting[4], y_meas[4], sigma[4]), pivot[8],
+ * stats block, CDF prefix row (tiles+1), last chosen setting index, resample flag, Philox epoch.
+ * Every call below is one or two launches over ALL instances; nothing returns to the host. */
+typedef struct obe_batch {
+    double* particles_dev[2];
+    double* weights_dev[2];
+    int32_t* cur_dev;          /* (B)                      */
+    double* tile_sums_dev;     /* (B * tiles)              */
+    double* tile_prefix_dev;   /* (B * (tiles + 1))        */
+    double* stats_dev;         /* (B * OBE_STATS_DOUBLES)  */
+    double* pivot_dev;         /* (B * 8)                  */
+    double* record_dev;        /* (B * 12)                 */
+    int64_t* last_idx_dev;     /* (B)                      */
+    double* best_val_dev;      /* (B)                      */
+    int32_t* flag_dev;         /* (B) 1 = must resample    */
+    int32_t* list_dev;         /* (B) scratch              */
+    int32_t* n_list_dev;       /* (1) scratch              */
+    uint32_t* epoch_dev;       /* (B) resamples so far     */
+    int64_t n_inst, n, np, ld;
+    int32_t d, tiles;
+} obe_batch_t;
+/* weights <- 1/n, buffers/flags reset, tile sums + prefix + moments of every instance. */
+int obe_batch_init(const obe_batch_t* b, const int32_t* noise_index, int n_noise, void* stream);
+/* pdf_update of every instance (obe_base.py:381-394) with its own record; use_last=1 takes each
+ * instance's setting from settings_dev[:, last_idx[b]] (closed loop without a host round-trip).
+ * Writes flag_dev[b] = resample decision of particlepdf.py:243-258 (or 1 when force_resample). */
+int obe_batch_update(obe_model_t m, const obe_batch_t* b, const double* settings_dev, int64_t lds, int use_last,
+                     const double* constants, const int32_t* noise_index, int n_lik_channels, int use_choke,
+                     double choke, double resample_threshold, int force_resample, void* stream);
+/* systematic resample (particlepdf.py:260-310) of the flagged instances; comb offset = uniform number
+ * u0_index of the instance's stream in this cycle; normals from Philox(seed + b, epoch_b); offspring
+ * violating the masks get weight 0 (enforce_parameter_constraints); then their stats are rebuilt. */
+int obe_batch_resample(const obe_batch_t* b, double a_param, int scale, uint64_t seed, uint64_t uniform_seed,
+                       uint32_t cycle, int u0_index, uint32_t mask_le, uint32_t mask_lt, const int32_t* noise_index,
+                       int n_noise, void* stream);
+int obe_batch_refresh(const obe_batch_t* b, uint32_t mask_le, uint32_t mask_lt, const int32_t* noise_index, int n_noise,
+                      void* stream);
+/* opt_setting of every instance (obe_base.py:733-756): K draws (uniforms 0..K-1 of the instance's
+ * stream in this cycle), variance utility, argmax -> last_idx_dev / best_val_dev.  cost_change > 0
+ * applies the sticky cost of demos/lockin/lockin_of_coil.py:135-152. */
+int obe_batch_select(obe_model_t m, const obe_batch_t* b, const double* settings_dev, int64_t lds, int64_t n_settings,
+                     const double* constants, int k, const double* var_noise, double cost_change, uint64_t uniform_seed,
+                     uint32_t cycle, int method, int log_form, double* utility_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,9 +35,20 @@ class Cloud(C.Structure):
                 ('n_dev', C.c_void_p)]
 
 
+class Batch(C.Structure):
+    _fields_ = [('particles_dev', C.c_void_p * 2), ('weights_dev', C.c_void_p * 2), ('cur_dev', C.c_void_p),
+                ('tile_sums_dev', C.c_void_p), ('tile_prefix_dev', C.c_void_p), ('stats_dev', C.c_void_p),
+                ('pivot_dev', C.c_void_p), ('record_dev', C.c_void_p), ('last_idx_dev', C.c_void_p),
+                ('best_val_dev', C.c_void_p), ('flag_dev', C.c_void_p), ('list_dev', C.c_void_p),
+                ('n_list_dev', C.c_void_p), ('epoch_dev', C.c_void_p),
+                ('n_inst', C.c_int64), ('n', C.c_int64), ('np', C.c_int64), ('ld', C.c_int64),
+                ('d', C.c_int32), ('tiles', C.c_int32)]
+
+
 _PD = C.POINTER(C.c_double)
 _PI32 = C.POINTER(C.c_int32)
 _PCLOUD = C.POINTER(Cloud)
+_PBATCH = C.POINTER(Batch)
 _VP = C.c_void_p
 
 # name -> (restype, argtypes); every symbol include/obe_b200.h declares
@@ -82,6 +93,14 @@ SIGNATURES = {
     'obe_utility': (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int64, C.c_int64, _PD, _PD, _VP, _VP, C.c_int,
                               C.c_int, _VP, _VP, _VP, _VP]),
     'obe_pick': (C.c_int, [_VP, C.c_int64, C.c_double, C.c_double, _VP, _VP, _VP]),
+    'obe_batch_init': (C.c_int, [_PBATCH, _PI32, C.c_int, _VP]),
+    'obe_batch_update': (C.c_int, [_VP, _PBATCH, _VP, C.c_int64, C.c_int, _PD, _PI32, C.c_int, C.c_int, C.c_double,
+                                   C.c_double, C.c_int, _VP]),
+    'obe_batch_resample': (C.c_int, [_PBATCH, C.c_double, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int,
+                                     C.c_uint32, C.c_uint32, _PI32, C.c_int, _VP]),
+    'obe_batch_refresh': (C.c_int, [_PBATCH, C.c_uint32, C.c_uint32, _PI32, C.c_int, _VP]),
+    'obe_batch_select': (C.c_int, [_VP, _PBATCH, _VP, C.c_int64, C.c_int64, _PD, C.c_int, _PD, C.c_double,
+                                   C.c_uint64, C.c_uint32, C.c_int, C.c_int, _VP, _VP]),
     'obe_eval_parameters': (C.c_int, [_VP, _PCLOUD, _PD, _PD, _VP, C.c_int64, _VP]),
     'obe_eval_settings': (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _PD, _PD, _VP, C.c_int64, _VP]),
 }

@@ -289,78 +289,6 @@ __global__ void k_normalized_weights(const double* __restrict__ w, const double*
         out[i] = obe_nan_to_num(w[i] * inv);
 }
 
-// ---------------------------------------------------------------------------------------------
-// canonical in-tile scan: thread t owns elements [8t, 8t+8) of the tile.
-//   incl[e] = (sum of earlier warps' totals, sequential) + (exclusive KS scan over lanes) + running
-// The canonical CDF is cdf[j] = (tile_prefix[k] + incl_j) * (1/total), EXCEPT the last valid element
-// of each tile, which is tile_prefix[k+1] * (1/total) by definition (so tile_sums may be reduced in
-// any order), and the very last particle, which is exactly 1.  (One IEEE multiply by the rounded
-// reciprocal instead of a divide per particle: still a fixed, monotone function of the weights that
-// numpy reproduces bit for bit as cdf_unnormalised * (1.0 / total).)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tile_load_blocked(const double* __restrict__ w, long long base, long long n,
-                                                  double (&v)[OBE_EPT]) {
-    const long long i0 = base + (long long)threadIdx.x * OBE_EPT;
-    if (i0 + OBE_EPT <= n) {
-#pragma unroll
-        for (int e = 0; e < OBE_EPT; e += 2) {
-            const double2 x = *reinterpret_cast<const double2*>(w + i0 + e);
-            v[e] = x.x; v[e + 1] = x.y;
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < OBE_EPT; ++e) v[e] = (i0 + e < n) ? w[i0 + e] : 0.0;
-    }
-}
-
-__device__ __forceinline__ void tile_scan_blocked(const double (&v)[OBE_EPT], double (&incl)[OBE_EPT],
-                                                  double* sm /*8*/) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double run = 0.0;
-#pragma unroll
-    for (int e = 0; e < OBE_EPT; ++e) { run += v[e]; incl[e] = run; }
-    double x = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-    }
-    double ex = __shfl_up_sync(0xffffffffu, x, 1);
-    if (lane == 0) ex = 0.0;
-    __syncthreads();
-    if (lane == 31) sm[warp] = x;
-    __syncthreads();
-    double wb = 0.0;
-    for (int w2 = 0; w2 < warp; ++w2) wb += sm[w2];
-    const double base = wb + ex;
-#pragma unroll
-    for (int e = 0; e < OBE_EPT; ++e) incl[e] = base + incl[e];
-}
-
-// normalised canonical CDF values of this thread's 8 elements of tile k
-// Sharded clouds: `offset` is the summed weight of all lower-ranked shards and inv_total the
-// reciprocal of the GLOBAL total; last_shard marks the shard that holds the global last particle.
-__device__ __forceinline__ void tile_cdf_blocked(const double* __restrict__ w, const double* __restrict__ prefix,
-                                                 long long k, long long n, double inv_total,
-                                                 double (&cn)[OBE_EPT], double* sm, double offset = 0.0,
-                                                 bool last_shard = true) {
-    double v[OBE_EPT], incl[OBE_EPT];
-    const long long base = k * OBE_TILE;
-    tile_load_blocked(w, base, n, v);
-    tile_scan_blocked(v, incl, sm);
-    const double p0 = obe_add(offset, prefix[k]);
-    const long long last = min(n, base + OBE_TILE) - 1;
-    const long long i0 = base + (long long)threadIdx.x * OBE_EPT;
-#pragma unroll
-    for (int e = 0; e < OBE_EPT; ++e) cn[e] = obe_mul(obe_add(p0, incl[e]), inv_total);
-    if (i0 + OBE_EPT > last) {                 // only the thread(s) at the end of the tile
-        const double c1 = (last_shard && last == n - 1) ? 1.0 : obe_mul(obe_add(offset, prefix[k + 1]), inv_total);
-#pragma unroll
-        for (int e = 0; e < OBE_EPT; ++e)
-            if (i0 + e >= last) cn[e] = c1;
-    }
-}
-
 __global__ void __launch_bounds__(OBE_THREADS) k_cdf(const double* __restrict__ w, const double* __restrict__ prefix,
                                                      long long n, long long n_tiles, double* __restrict__ cdf) {
     __shared__ double sm[8];
@@ -471,20 +399,8 @@ __global__ void __launch_bounds__(OBE_THREADS) k_draw(const ObeDrawArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 + Box-Muller (restated in oracle/obe_oracle.py:device_normals)
+// Box-Muller normals on top of Philox4x32-10 (obe_device.cuh); restated in oracle/obe_oracle.py
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3,
-                                              unsigned int k0, unsigned int k1, unsigned int (&out)[4]) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
 __device__ __forceinline__ float obe_sqrt_approx(float x) {
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -713,6 +629,150 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
 //  2. every particle that owns at least one slot of the chunk marks the first of them with its
 //     index; a max-scan over the chunk's slots turns the marks into the ancestor of every slot
 //  3. slots are walked in coalesced order: gather the ancestor (L1-resident tile), jitter, store
+// Everything one work unit needs, in registers.  Shared by the single-cloud / sharded kernel and the
+// batched kernel (where it is rebuilt per instance).
+struct SysCtx {
+    const double* w_in;        // weights of this cloud / shard / instance (tile k starts at k * OBE_TILE)
+    const double* prefix;      // its tile prefix row
+    long long n_in;            // its live particle count
+    double inv_total, cdf_offset;
+    bool last_shard;
+    double u0, inv_n, nd, tol, wv;
+    const double* pin; long long ld_in, in_base;      // ancestor j of the cloud is pin[row*ld_in + in_base + j]
+    double* pout; long long ld_out, out_base;         // output slot o goes to pout[row*ld_out + out_base + o]
+    double* w_out;
+    long long slot_begin, cap_out;
+    unsigned long long seed; unsigned int epoch;
+    int jitter, scale;
+    double a_param;
+    long long* idx_out; double* z_out;
+    unsigned int mask_le, mask_lt;                     // batched: constraint applied to the offspring
+};
+
+// One work unit = (input tile k, chunk of <= 2048 consecutive output slots owned by that tile).
+//  1. canonical CDF of the tile (blocked scan) -> end slot hi_j of every particle (comb count),
+//     made monotone by a running max and clamped to the tile's slot range [H_k, H_k+1)
+//  2. every particle that owns at least one slot of the chunk marks the first of them with its
+//     index; a max-scan over the chunk's slots turns the marks into the ancestor of every slot
+//  3. slots are walked in coalesced order: gather the ancestor (L1-resident tile), jitter, store
+template <int D, class FT>
+__device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long Hk, long long Hk1, int rel_begin,
+                                         const FT& F, const double* sMean, double* sm, int* smx,
+                                         unsigned short* anc_s) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int span = (int)(Hk1 - Hk);
+    const int rel_end = min(rel_begin + OBE_OUT_CHUNK, span);
+    // clear the marks (8 per thread, 16-byte store)
+    *reinterpret_cast<uint4*>(&anc_s[tid * OBE_EPT]) = make_uint4(0u, 0u, 0u, 0u);
+    // ---- 1. end slot of every particle of the tile
+    double cn[OBE_EPT];
+    tile_cdf_blocked(c.w_in, c.prefix, k, c.n_in, c.inv_total, cn, sm, c.cdf_offset, c.last_shard);
+    const long long base = k * OBE_TILE;
+    const long long last = min(c.n_in, base + OBE_TILE) - 1;
+    int r[OBE_EPT];
+    int run = 0;
+#pragma unroll
+    for (int e = 0; e < OBE_EPT; ++e) {
+        const long long i = base + (long long)tid * OBE_EPT + e;
+        int h;
+        if (i >= last) h = span;
+        else {
+            const double hd = comb_count_d(cn[e], c.u0, c.inv_n, c.nd, c.tol) - (double)Hk;     // exact: < 2^53
+            h = (hd < 0.0) ? 0 : (hd > (double)span ? span : (int)hd);
+        }
+        run = max(run, h);
+        r[e] = run;
+    }
+    int x = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x = max(x, y);
+    }
+    int ex = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) ex = 0;
+    if (lane == 31) smx[warp] = x;
+    __syncthreads();                       // also orders the clearing of anc_s before the marks
+    for (int w2 = 0; w2 < warp; ++w2) ex = max(ex, smx[w2]);
+    // ---- 2. mark the first owned slot inside the chunk
+    int prev = ex;                         // end slot of the previous particle
+#pragma unroll
+    for (int e = 0; e < OBE_EPT; ++e) {
+        const int end = max(r[e], ex);
+        if (end > prev) {
+            const int head = max(prev, rel_begin);
+            if (head < rel_end && end > rel_begin) anc_s[head - rel_begin] = (unsigned short)(tid * OBE_EPT + e);
+        }
+        prev = end;
+    }
+    __syncthreads();
+    // max-scan of the marks over the chunk's slots (blocked: 8 consecutive slots per thread)
+    int m[OBE_EPT];
+    {
+        const uint4 raw = *reinterpret_cast<const uint4*>(&anc_s[tid * OBE_EPT]);
+        const unsigned int wds[4] = {raw.x, raw.y, raw.z, raw.w};
+        int runm = 0;
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; ++e) {
+            const int v = (int)((wds[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
+            runm = max(runm, v);
+            m[e] = runm;
+        }
+        int xm = runm;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, xm, o);
+            if (lane >= o) xm = max(xm, y);
+        }
+        int exm = __shfl_up_sync(0xffffffffu, xm, 1);
+        if (lane == 0) exm = 0;
+        __syncthreads();                   // smx is reused
+        if (lane == 31) smx[warp] = xm;
+        __syncthreads();
+        for (int w2 = 0; w2 < warp; ++w2) exm = max(exm, smx[w2]);
+        unsigned int packed[4];
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; e += 2) {
+            const unsigned int a0 = (unsigned int)max(m[e], exm), a1v = (unsigned int)max(m[e + 1], exm);
+            packed[e >> 1] = a0 | (a1v << 16);
+        }
+        *reinterpret_cast<uint4*>(&anc_s[tid * OBE_EPT]) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    __syncthreads();
+    // ---- 3. outputs in coalesced order
+    const int n_out = rel_end - rel_begin;
+    for (int q = tid; q < n_out; q += OBE_THREADS) {
+        const long long og = Hk + rel_begin + q;              // global slot: comb tooth, RNG counter
+        const long long o = og - c.slot_begin;                  // position in this shard's output
+        if (o >= c.cap_out) continue;                           // capacity overflow is flagged in the plan
+        const long long anc = base + min((int)anc_s[q], (int)(last - base));
+        double xv[D], z[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) xv[j] = __ldg(c.pin + j * c.ld_in + c.in_base + anc);
+        if (c.jitter) {
+            device_normals<D>(og, c.seed, c.epoch, z);
+            if (c.z_out) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) c.z_out[o * D + j] = z[j];
+            }
+            liu_west<D>(xv, z, F, sMean, c.a_param, c.scale);
+        }
+        double wo = c.wv;
+        if (c.mask_le | c.mask_lt) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                if (((c.mask_le >> j) & 1u) && xv[j] <= 0.0) wo = 0.0;
+                if (((c.mask_lt >> j) & 1u) && xv[j] < 0.0) wo = 0.0;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) c.pout[j * c.ld_out + c.out_base + o] = xv[j];
+        c.w_out[c.out_base + o] = wo;
+        if (c.idx_out) c.idx_out[o] = anc;
+    }
+    __syncthreads();
+}
+
 template <int D>
 __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(const ObeResampleArgs a) {
     __shared__ double sF[D * D];
@@ -721,19 +781,24 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(
     __shared__ int smx[OBE_THREADS / 32];
     __shared__ __align__(16) unsigned short anc_s[OBE_OUT_CHUNK];
     setup_factor<D>(a, sF, sMean);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long n_in = a.n_dev_in ? *a.n_dev_in : a.n;
     const long long n_tiles_in = a.n_dev_in ? (n_in + OBE_TILE - 1) / OBE_TILE : a.n_tiles;
     const bool sharded = a.plan ? true : (a.sharded != 0);
     const double cdf_total = a.plan ? a.plan[OBE_PL_TOTAL] : a.cdf_total;
-    const double u0 = a.plan ? a.plan[OBE_PL_U0] : a.u0;
     const long long n_total = a.plan ? (long long)a.plan[OBE_PL_NTOTAL] : a.n_total;
-    const long long slot_begin = a.plan ? (long long)a.plan[OBE_PL_SLOT0] : a.slot_begin;
-    const double inv_total = 1.0 / (sharded ? cdf_total : a.prefix[n_tiles_in]);
-    const double nd = (double)n_total, inv_n = 1.0 / nd, wv = 1.0 / nd, tol = 2e-15 * nd;
-    const double cdf_offset = a.plan ? a.plan[OBE_PL_OFFSET] : (sharded ? a.cdf_offset : 0.0);
-    const bool last_shard = a.plan ? (a.plan[OBE_PL_LAST] != 0.0) : (sharded ? (a.last_shard != 0) : true);
-    const long long cap_out = a.plan ? a.cap_out : (1ll << 62);
+    SysCtx c;
+    c.w_in = a.w_in; c.prefix = a.prefix; c.n_in = n_in;
+    c.inv_total = 1.0 / (sharded ? cdf_total : a.prefix[n_tiles_in]);
+    c.cdf_offset = a.plan ? a.plan[OBE_PL_OFFSET] : (sharded ? a.cdf_offset : 0.0);
+    c.last_shard = a.plan ? (a.plan[OBE_PL_LAST] != 0.0) : (sharded ? (a.last_shard != 0) : true);
+    c.u0 = a.plan ? a.plan[OBE_PL_U0] : a.u0;
+    c.nd = (double)n_total; c.inv_n = 1.0 / c.nd; c.wv = 1.0 / c.nd; c.tol = 2e-15 * c.nd;
+    c.pin = a.pin; c.ld_in = a.ld_in; c.in_base = 0;
+    c.pout = a.pout; c.ld_out = a.ld_out; c.out_base = 0; c.w_out = a.w_out;
+    c.slot_begin = a.plan ? (long long)a.plan[OBE_PL_SLOT0] : a.slot_begin;
+    c.cap_out = a.plan ? a.cap_out : (1ll << 62);
+    c.seed = a.seed; c.epoch = a.epoch; c.jitter = a.jitter; c.scale = a.scale; c.a_param = a.a_param;
+    c.idx_out = a.idx_out; c.z_out = a.z_out; c.mask_le = 0u; c.mask_lt = 0u;
     // the Liu-West factor in registers when it is small enough
     double Fr[D <= 4 ? D * D : 1];
     if (D <= 4) {
@@ -757,112 +822,121 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(
     for (int unit = unit_lo; unit < unit_hi; ++unit) {
         while (a.unit_start[k32 + 1] <= unit) ++k32;      // largest k with unit_start[k] <= unit
         const long long k = k32;
-        const long long Hk = a.plan_h[k], Hk1 = a.plan_h[k + 1];
-        const int span = (int)(Hk1 - Hk);
         const int rel_begin = (unit - a.unit_start[k]) * OBE_OUT_CHUNK;
-        const int rel_end = min(rel_begin + OBE_OUT_CHUNK, span);
-        // clear the marks (8 per thread, 16-byte store)
-        *reinterpret_cast<uint4*>(&anc_s[tid * OBE_EPT]) = make_uint4(0u, 0u, 0u, 0u);
-        // ---- 1. end slot of every particle of the tile
-        double cn[OBE_EPT];
-        tile_cdf_blocked(a.w_in, a.prefix, k, n_in, inv_total, cn, sm, cdf_offset, last_shard);
-        const long long base = k * OBE_TILE;
-        const long long last = min(n_in, base + OBE_TILE) - 1;
-        int r[OBE_EPT];
-        int run = 0;
-#pragma unroll
-        for (int e = 0; e < OBE_EPT; ++e) {
-            const long long i = base + (long long)tid * OBE_EPT + e;
-            int h;
-            if (i >= last) h = span;
-            else {
-                const double hd = comb_count_d(cn[e], u0, inv_n, nd, tol) - (double)Hk;     // exact: < 2^53
-                h = (hd < 0.0) ? 0 : (hd > (double)span ? span : (int)hd);
+        if (D <= 4) sys_unit<D>(c, k, a.plan_h[k], a.plan_h[k + 1], rel_begin, Fr, sMean, sm, smx, anc_s);
+        else sys_unit<D>(c, k, a.plan_h[k], a.plan_h[k + 1], rel_begin, sF, sMean, sm, smx, anc_s);
+    }
+}
+
+// ---- batched systematic resample: one CTA walks the instances of the compacted list -------------
+struct ObeBResampleArgs {
+    const double* particles[2];
+    double* particles_w[2];
+    double* weights[2];
+    int* cur;                      // (B) flipped for every resampled instance
+    const double* prefix;          // (B * (T + 1))
+    const double* stats;           // (B * OBE_STATS_LEN)
+    unsigned int* epoch;           // (B) resamples so far, the Philox epoch of the next one
+    const int* inst_list; const int* n_list;
+    long long ld, np, n;
+    int tiles;
+    unsigned long long seed;       // instance b uses seed + b for its normals
+    unsigned long long useed;      // key of the uniform streams
+    unsigned int cycle; int u0_index;
+    double a_param; int scale;
+    unsigned int mask_le, mask_lt;
+};
+
+template <int D>
+__global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_bsys_resample(const ObeBResampleArgs a) {
+    __shared__ double sF[D * D];
+    __shared__ double sMean[D];
+    __shared__ double sm[8];
+    __shared__ int smx[OBE_THREADS / 32];
+    __shared__ long long Hs[66];
+    __shared__ __align__(16) unsigned short anc_s[OBE_OUT_CHUNK];
+    const int tid = threadIdx.x;
+    const int T = a.tiles;
+    const int n_list = *a.n_list;
+    for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+        const long long b = a.inst_list[li];
+        const int cb = a.cur[b];
+        const double* pre = a.prefix + b * (T + 1);
+        const double* st = a.stats + b * OBE_STATS_LEN;
+        SysCtx c;
+        c.w_in = a.weights[cb] + b * a.np; c.prefix = pre; c.n_in = a.n;
+        c.inv_total = 1.0 / pre[T]; c.cdf_offset = 0.0; c.last_shard = true;
+        c.u0 = obe_batch_uniform(a.useed, (unsigned int)b, a.cycle, (unsigned int)a.u0_index);
+        c.nd = (double)a.n; c.inv_n = 1.0 / c.nd; c.wv = 1.0 / c.nd; c.tol = 2e-15 * c.nd;
+        c.pin = a.particles[cb]; c.ld_in = a.ld; c.in_base = b * a.np;
+        c.pout = a.particles_w[1 - cb]; c.ld_out = a.ld; c.out_base = b * a.np; c.w_out = a.weights[1 - cb];
+        c.slot_begin = 0; c.cap_out = a.np;
+        c.seed = a.seed + (unsigned long long)b; c.epoch = a.epoch[b] + 1u; c.jitter = 1; c.scale = a.scale;
+        c.a_param = a.a_param; c.idx_out = nullptr; c.z_out = nullptr; c.mask_le = a.mask_le; c.mask_lt = a.mask_lt;
+        if (tid == 0) {
+            // slot bounds of the instance's tiles (monotone), Liu-West factor from its own moments
+            long long run = 0;
+            for (int t = 0; t <= T; ++t) {
+                long long h = (t == 0) ? 0 : (t == T ? a.n : (long long)comb_count_d(obe_mul(pre[t], c.inv_total), c.u0,
+                                                                                     c.inv_n, c.nd, c.tol));
+                run = max(run, min(h, (long long)a.n));
+                Hs[t] = run;
             }
-            run = max(run, h);
-            r[e] = run;
-        }
-        int x = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x = max(x, y);
-        }
-        int ex = __shfl_up_sync(0xffffffffu, x, 1);
-        if (lane == 0) ex = 0;
-        if (lane == 31) smx[warp] = x;
-        __syncthreads();                       // also orders the clearing of anc_s before the marks
-        for (int w2 = 0; w2 < warp; ++w2) ex = max(ex, smx[w2]);
-        // ---- 2. mark the first owned slot inside the chunk
-        int prev = ex;                         // end slot of the previous particle
-#pragma unroll
-        for (int e = 0; e < OBE_EPT; ++e) {
-            const int end = max(r[e], ex);
-            if (end > prev) {
-                const int head = max(prev, rel_begin);
-                if (head < rel_end && end > rel_begin) anc_s[head - rel_begin] = (unsigned short)(tid * OBE_EPT + e);
-            }
-            prev = end;
-        }
-        __syncthreads();
-        // max-scan of the marks over the chunk's slots (blocked: 8 consecutive slots per thread)
-        int m[OBE_EPT];
-        {
-            const uint4 raw = *reinterpret_cast<const uint4*>(&anc_s[tid * OBE_EPT]);
-            const unsigned int wds[4] = {raw.x, raw.y, raw.z, raw.w};
-            int runm = 0;
-#pragma unroll
-            for (int e = 0; e < OBE_EPT; ++e) {
-                const int v = (int)((wds[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
-                runm = max(runm, v);
-                m[e] = runm;
-            }
-            int xm = runm;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, xm, o);
-                if (lane >= o) xm = max(xm, y);
-            }
-            int exm = __shfl_up_sync(0xffffffffu, xm, 1);
-            if (lane == 0) exm = 0;
-            __syncthreads();                   // smx is reused
-            if (lane == 31) smx[warp] = xm;
-            __syncthreads();
-            for (int w2 = 0; w2 < warp; ++w2) exm = max(exm, smx[w2]);
-            unsigned int packed[4];
-#pragma unroll
-            for (int e = 0; e < OBE_EPT; e += 2) {
-                const unsigned int a0 = (unsigned int)max(m[e], exm), a1v = (unsigned int)max(m[e + 1], exm);
-                packed[e >> 1] = a0 | (a1v << 16);
-            }
-            *reinterpret_cast<uint4*>(&anc_s[tid * OBE_EPT]) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        }
-        __syncthreads();
-        // ---- 3. outputs in coalesced order
-        const int n_out = rel_end - rel_begin;
-        for (int q = tid; q < n_out; q += OBE_THREADS) {
-            const long long og = Hk + rel_begin + q;              // global slot: comb tooth, RNG counter
-            const long long o = og - slot_begin;                    // position in this shard's output
-            if (o >= cap_out) continue;                             // capacity overflow is flagged in the plan
-            const long long anc = base + min((int)anc_s[q], (int)(last - base));
-            double xv[D], z[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) xv[j] = __ldg(a.pin + j * a.ld_in + anc);
-            if (a.jitter) {
-                device_normals<D>(og, a.seed, a.epoch, z);
-                if (a.z_out) {
-#pragma unroll
-                    for (int j = 0; j < D; ++j) a.z_out[o * D + j] = z[j];
+            const double stt = st[OBE_ST_SUMT], fact = stt - st[OBE_ST_SUMSQ] / stt;
+            const double shrink = 1.0 - a.a_param * a.a_param;
+            double cov[D][D], L[D][D];
+            int q = 0;
+            for (int j = 0; j < D; ++j) {
+                sMean[j] = st[OBE_ST_PIVOT + j] + st[OBE_ST_M1 + j] / stt;
+                for (int k = j; k < D; ++k) {
+                    const double cc = (st[OBE_ST_M2 + q] - st[OBE_ST_M1 + j] * st[OBE_ST_M1 + k] / stt) / fact;
+                    cov[j][k] = cov[k][j] = shrink * cc;
+                    ++q;
                 }
-                liu_west<D>(xv, z, (D <= 4) ? Fr : sF, sMean, a.a_param, a.scale);
             }
-#pragma unroll
-            for (int j = 0; j < D; ++j) a.pout[j * a.ld_out + o] = xv[j];
-            a.w_out[o] = wv;
-            if (a.idx_out) a.idx_out[o] = anc;
+            for (int j = 0; j < D; ++j)
+                for (int k = 0; k < D; ++k) L[j][k] = 0.0;
+            for (int j = 0; j < D; ++j) {
+                double sdiag = cov[j][j];
+                for (int k = 0; k < j; ++k) sdiag -= L[j][k] * L[j][k];
+                const double dj = sdiag > 0.0 ? sqrt(sdiag) : 0.0;
+                L[j][j] = dj;
+                for (int i = j + 1; i < D; ++i) {
+                    double t2 = cov[i][j];
+                    for (int k = 0; k < j; ++k) t2 -= L[i][k] * L[j][k];
+                    L[i][j] = dj > 0.0 ? t2 / dj : 0.0;
+                }
+            }
+            for (int k = 0; k < D; ++k)
+                for (int j = 0; j < D; ++j) sF[k * D + j] = L[j][k];
         }
+        __syncthreads();
+        for (int t = 0; t < T; ++t) {
+            const long long Hk = Hs[t], Hk1 = Hs[t + 1];
+            for (int rel = 0; rel < (int)(Hk1 - Hk); rel += OBE_OUT_CHUNK)
+                sys_unit<D>(c, t, Hk, Hk1, rel, sF, sMean, sm, smx, anc_s);
+        }
+        __syncthreads();
+        if (tid == 0) { a.cur[b] = 1 - cb; a.epoch[b] = c.epoch; }
         __syncthreads();
     }
+}
+
+// compact the resample flags into a list of instance numbers (order preserved) + its length
+__global__ void __launch_bounds__(OBE_SCAN_THREADS) k_bcompact(const int* __restrict__ flag, long long n_inst,
+                                                               int* __restrict__ list, int* __restrict__ n_list) {
+    __shared__ int smi[34];
+    int carry = 0;
+    for (long long base = 0; base < n_inst; base += OBE_SCAN_THREADS) {
+        const long long b = base + threadIdx.x;
+        const int f = (b < n_inst && flag[b]) ? 1 : 0;
+        int tot;
+        const int ex = block_excl_isum_1024(f, smi, &tot);
+        if (f) list[carry + ex] = (int)b;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_list = carry;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1015,6 +1089,18 @@ template <class M>
 __global__ void __launch_bounds__(OBE_THREADS) k_evals_model(const ObeEvalArgs a) {
     obe_eval_settings_body<M>(a);
 }
+template <class M, int D>
+__global__ void __launch_bounds__(OBE_UPDATE_THREADS, 1) k_bupdate_model(const ObeBatchArgs a) {
+    obe_update_batched_body<M, D, OBE_SRC_MODEL>(a);
+}
+template <int D>
+__global__ void __launch_bounds__(OBE_UPDATE_THREADS, 1) k_brefresh(const ObeBatchArgs a) {
+    obe_update_batched_body<ObeNoModel, D, OBE_SRC_NONE>(a);
+}
+template <class M>
+__global__ void __launch_bounds__(OBE_THREADS) k_bselect_model(const ObeBSelectArgs a) {
+    obe_bselect_body<M>(a);
+}
 
 struct obe_model {
     int ns, np_model, ncons, nch, d;
@@ -1023,6 +1109,8 @@ struct obe_model {
     const void* f_evalp;
     const void* f_utility;
     const void* f_evals;
+    const void* f_bupdate;  // batched instances
+    const void* f_bselect;
     cudaLibrary_t lib;
 };
 
@@ -1034,6 +1122,8 @@ static void fill_model(obe_model* m) {
     m->f_evalp = (const void*)k_evalp_model<M, D>;
     m->f_utility = (const void*)k_utility_model<M>;
     m->f_evals = (const void*)k_evals_model<M>;
+    m->f_bupdate = (const void*)k_bupdate_model<M, D>;
+    m->f_bselect = (const void*)k_bselect_model<M>;
 }
 template <class M>
 static int make_builtin(int d, obe_model* m) {
@@ -1157,8 +1247,9 @@ int obe_model_compile(const char* cuda_source, const char* entry, int n_settings
              "    __device__ static __forceinline__ void eval(const double* s, const double* p, const double* c, double* y) {\n"
              "        %s(s, p, c, y);\n    }\n};\n"
              "OBE_DEFINE_MODEL_KERNELS(ObeUserModel, %d, user)\n"
-             "OBE_DEFINE_GRID_KERNELS(ObeUserModel, user)\n",
-             n_settings, n_model_params, n_constants, n_channels, entry, n_params);
+             "OBE_DEFINE_GRID_KERNELS(ObeUserModel, user)\n"
+             "OBE_DEFINE_BATCH_KERNELS(ObeUserModel, %d, user)\n",
+             n_settings, n_model_params, n_constants, n_channels, entry, n_params, n_params);
     std::string src = "#include \"obe_device.cuh\"\n#include \"obe_models.cuh\"\n";
     src += cuda_source;
     src += tail;
@@ -1191,9 +1282,10 @@ int obe_model_compile(const char* cuda_source, const char* entry, int n_settings
     m->d = n_params; m->user = true;
     cudaError_t e = cudaLibraryLoadData(&m->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e != cudaSuccess) { delete m; return obe_fail("cudaLibraryLoadData: %s%s", cudaGetErrorString(e)); }
-    cudaKernel_t k[4];
-    const char* kn[4] = {"obe_k_update_user", "obe_k_evalp_user", "obe_k_utility_user", "obe_k_evals_user"};
-    for (int i = 0; i < 4; ++i) {
+    cudaKernel_t k[6];
+    const char* kn[6] = {"obe_k_update_user", "obe_k_evalp_user", "obe_k_utility_user", "obe_k_evals_user",
+                         "obe_k_bupdate_user", "obe_k_bselect_user"};
+    for (int i = 0; i < 6; ++i) {
         e = cudaLibraryGetKernel(&k[i], m->lib, kn[i]);
         if (e != cudaSuccess) {
             cudaLibraryUnload(m->lib);
@@ -1203,6 +1295,7 @@ int obe_model_compile(const char* cuda_source, const char* entry, int n_settings
     }
     m->f_update = (const void*)k[0]; m->f_evalp = (const void*)k[1];
     m->f_utility = (const void*)k[2]; m->f_evals = (const void*)k[3];
+    m->f_bupdate = (const void*)k[4]; m->f_bselect = (const void*)k[5];
     *out = m;
     return 0;
 }
@@ -1676,6 +1769,170 @@ int obe_eval_settings(obe_model_t m, const double* settings_dev, int64_t lds, in
     int64_t blocks = (n_settings + OBE_THREADS - 1) / OBE_THREADS;
     if (blocks > (int64_t)obe_sms() * 8) blocks = (int64_t)obe_sms() * 8;
     return launch_kernel(m->f_evals, (int)blocks, 0, (cudaStream_t)stream, &a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched independent instances
+// ---------------------------------------------------------------------------------------------
+__global__ void k_batch_init(double* __restrict__ w0, int* __restrict__ cur, unsigned int* __restrict__ epoch,
+                             long long* __restrict__ last_idx, int* __restrict__ flag, long long n_inst, long long n,
+                             long long np) {
+    const double v = 1.0 / (double)n;
+    const long long total = n_inst * np;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        w0[i] = ((i % np) < n) ? v : 0.0;
+        if (i < n_inst) { cur[i] = 0; epoch[i] = 0u; last_idx[i] = 0; flag[i] = 0; }
+    }
+}
+
+static int check_batch(const obe_batch_t* b) {
+    if (!b || !b->particles_dev[0] || !b->particles_dev[1] || !b->weights_dev[0] || !b->weights_dev[1] || !b->cur_dev ||
+        !b->tile_sums_dev || !b->tile_prefix_dev || !b->stats_dev || !b->pivot_dev || !b->record_dev ||
+        !b->last_idx_dev || !b->best_val_dev || !b->flag_dev || !b->list_dev || !b->n_list_dev || !b->epoch_dev)
+        return obe_fail("batch has null device pointers%s%s");
+    if (b->n_inst < 1 || b->n < 1 || b->d < 1 || b->d > OBE_MAX_DIMS) return obe_fail("batch geometry invalid%s%s");
+    if (b->np % OBE_TILE || b->np < b->n || b->tiles != b->np / OBE_TILE || b->tiles > 64 || b->ld < b->n_inst * b->np)
+        return obe_fail("batch: np must be n rounded up to whole tiles (<= 64 tiles), ld >= n_inst*np%s%s");
+    if (obe_sms() <= 0) return obe_fail("no CUDA device: this library has no CPU fallback%s%s");
+    return 0;
+}
+static void fill_batch_args(const obe_batch_t* b, ObeBatchArgs& a) {
+    memset(&a, 0, sizeof(a));
+    for (int j = 0; j < OBE_MAX_CH; ++j) a.u.noise_idx[j] = -1;
+    a.u.n = b->n; a.u.ld = b->ld;
+    a.particles[0] = b->particles_dev[0]; a.particles[1] = b->particles_dev[1];
+    a.weights[0] = b->weights_dev[0]; a.weights[1] = b->weights_dev[1];
+    a.cur = b->cur_dev; a.tile_sums = b->tile_sums_dev; a.prefix = b->tile_prefix_dev; a.stats = b->stats_dev;
+    a.pivot = b->pivot_dev; a.rec_in = b->record_dev; a.last_idx = (const long long*)b->last_idx_dev;
+    a.flag = b->flag_dev; a.n_inst = b->n_inst; a.np = b->np; a.tiles = b->tiles;
+}
+static int launch_batch_update(const void* f, int d, const ObeBatchArgs& a, int64_t n_inst, cudaStream_t st) {
+    const size_t smem = update_smem_bytes(d, OBE_SRC_MODEL);
+    cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return obe_fail("cudaFuncSetAttribute(max dynamic smem): %s%s", cudaGetErrorString(e));
+    int64_t g = obe_sms();
+    if (g > n_inst) g = n_inst;
+    void* params[1] = {const_cast<ObeBatchArgs*>(&a)};
+    e = cudaLaunchKernel(f, dim3((unsigned)g), dim3(OBE_UPDATE_THREADS), params, smem, st);
+    if (e != cudaSuccess) return obe_fail("launch batched update kernel: %s%s", cudaGetErrorString(e));
+    return 0;
+}
+static int batch_refresh_impl(const obe_batch_t* b, uint32_t mask_le, uint32_t mask_lt, const int32_t* noise_index,
+                              int n_noise, int only_listed, cudaStream_t st) {
+    ObeBatchArgs a;
+    fill_batch_args(b, a);
+    a.u.scale_in = 0; a.u.write_weights = (mask_le | mask_lt) ? 1 : 0;
+    a.u.mask_le = mask_le; a.u.mask_lt = mask_lt;
+    a.flag = nullptr;
+    if (noise_index)
+        for (int j = 0; j < n_noise && j < OBE_MAX_CH; ++j) { a.u.noise_idx[j] = noise_index[j]; a.u.n_noise = j + 1; }
+    if (only_listed) { a.inst_list = b->list_dev; a.n_list = b->n_list_dev; }
+    const void* f = nullptr;
+    switch (b->d) {
+        case 1: f = (const void*)k_brefresh<1>; break;
+        case 2: f = (const void*)k_brefresh<2>; break;
+        case 3: f = (const void*)k_brefresh<3>; break;
+        case 4: f = (const void*)k_brefresh<4>; break;
+        case 5: f = (const void*)k_brefresh<5>; break;
+        case 6: f = (const void*)k_brefresh<6>; break;
+        case 7: f = (const void*)k_brefresh<7>; break;
+        default: f = (const void*)k_brefresh<8>; break;
+    }
+    return launch_batch_update(f, b->d, a, b->n_inst, st);
+}
+
+int obe_batch_init(const obe_batch_t* b, const int32_t* noise_index, int n_noise, void* stream) {
+    if (check_batch(b)) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_batch_init<<<obe_sms() * 8, 256, 0, st>>>(b->weights_dev[0], b->cur_dev, b->epoch_dev, (long long*)b->last_idx_dev,
+                                               b->flag_dev, b->n_inst, b->n, b->np);
+    OBE_LAUNCH_CHECK("k_batch_init");
+    OBE_CUDA(cudaMemsetAsync(b->stats_dev, 0, (size_t)b->n_inst * OBE_STATS_LEN * sizeof(double), st));
+    OBE_CUDA(cudaMemsetAsync(b->pivot_dev, 0, (size_t)b->n_inst * OBE_MAX_DIMS * sizeof(double), st));
+    // two refresh passes: the first finds the means, the second accumulates around them
+    if (batch_refresh_impl(b, 0, 0, noise_index, n_noise, 0, st)) return -1;
+    return batch_refresh_impl(b, 0, 0, noise_index, n_noise, 0, st);
+}
+
+int obe_batch_refresh(const obe_batch_t* b, uint32_t mask_le, uint32_t mask_lt, const int32_t* noise_index, int n_noise,
+                      void* stream) {
+    if (check_batch(b)) return -1;
+    return batch_refresh_impl(b, mask_le, mask_lt, noise_index, n_noise, 0, (cudaStream_t)stream);
+}
+
+int obe_batch_update(obe_model_t m, const obe_batch_t* b, const double* settings_dev, int64_t lds, int use_last,
+                     const double* constants, const int32_t* noise_index, int n_lik_channels, int use_choke,
+                     double choke, double resample_threshold, int force_resample, void* stream) {
+    if (!m) return obe_fail("null model%s%s");
+    if (check_batch(b)) return -1;
+    if (m->d != b->d) return obe_fail("model was built for a different n_params%s%s");
+    if (use_last && !settings_dev) return obe_fail("use_last needs the setting grid%s%s");
+    ObeBatchArgs a;
+    fill_batch_args(b, a);
+    a.u.scale_in = 1; a.u.write_weights = 1;
+    for (int j = 0; j < m->ncons; ++j) a.u.cons[j] = constants[j];
+    if (n_lik_channels < 0 || n_lik_channels > m->nch) return obe_fail("n_lik_channels out of range%s%s");
+    a.u.n_lik_channels = n_lik_channels;
+    if (noise_index)
+        for (int c = 0; c < n_lik_channels; ++c) {
+            if (noise_index[c] < 0 || noise_index[c] >= b->d) return obe_fail("noise_index out of range%s%s");
+            a.u.noise_idx[c] = noise_index[c]; a.u.n_noise = c + 1;
+        }
+    a.u.use_choke = use_choke; a.u.choke = choke;
+    a.settings = settings_dev; a.lds = lds; a.use_last = use_last; a.n_set = m->ns;
+    a.resample_threshold = resample_threshold; a.force_resample = force_resample;
+    return launch_batch_update(m->f_bupdate, b->d, a, b->n_inst, (cudaStream_t)stream);
+}
+
+int obe_batch_resample(const obe_batch_t* b, double a_param, int scale, uint64_t seed, uint64_t uniform_seed,
+                       uint32_t cycle, int u0_index, uint32_t mask_le, uint32_t mask_lt, const int32_t* noise_index,
+                       int n_noise, void* stream) {
+    if (check_batch(b)) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_bcompact<<<1, OBE_SCAN_THREADS, 0, st>>>(b->flag_dev, b->n_inst, b->list_dev, b->n_list_dev);
+    OBE_LAUNCH_CHECK("k_bcompact");
+    ObeBResampleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.particles[0] = b->particles_dev[0]; a.particles[1] = b->particles_dev[1];
+    a.particles_w[0] = b->particles_dev[0]; a.particles_w[1] = b->particles_dev[1];
+    a.weights[0] = b->weights_dev[0]; a.weights[1] = b->weights_dev[1];
+    a.cur = b->cur_dev; a.prefix = b->tile_prefix_dev; a.stats = b->stats_dev; a.epoch = b->epoch_dev;
+    a.inst_list = b->list_dev; a.n_list = b->n_list_dev;
+    a.ld = b->ld; a.np = b->np; a.n = b->n; a.tiles = b->tiles;
+    a.seed = seed; a.useed = uniform_seed; a.cycle = cycle; a.u0_index = u0_index;
+    a.a_param = a_param; a.scale = scale; a.mask_le = mask_le; a.mask_lt = mask_lt;
+    int64_t g = (int64_t)obe_sms() * OBE_BLOCKS_PER_SM;
+    if (g > b->n_inst) g = b->n_inst;
+    const int grid = (int)g;
+    OBE_DIM_SWITCH(b->d, k_bsys_resample, grid, st, a)
+    OBE_LAUNCH_CHECK("k_bsys_resample");
+    // tile sums, CDF prefix, moments and noise sums of the new clouds (only the resampled instances)
+    return batch_refresh_impl(b, 0, 0, noise_index, n_noise, 1, st);
+}
+
+int obe_batch_select(obe_model_t m, const obe_batch_t* b, const double* settings_dev, int64_t lds, int64_t n_settings,
+                     const double* constants, int k, const double* var_noise, double cost_change, uint64_t uniform_seed,
+                     uint32_t cycle, int method, int log_form, double* utility_dev, void* stream) {
+    if (!m || !settings_dev) return obe_fail("null argument%s%s");
+    if (check_batch(b)) return -1;
+    if (k < 1 || k > OBE_MAX_DRAWS) return obe_fail("n_draws must be 1..128 for batched engines%s%s");
+    ObeBSelectArgs a;
+    memset(&a, 0, sizeof(a));
+    a.particles[0] = b->particles_dev[0]; a.particles[1] = b->particles_dev[1];
+    a.weights[0] = b->weights_dev[0]; a.weights[1] = b->weights_dev[1];
+    a.cur = b->cur_dev; a.prefix = b->tile_prefix_dev; a.stats = b->stats_dev;
+    a.settings = settings_dev; a.lds = lds; a.n_settings = n_settings;
+    a.ld = b->ld; a.np = b->np; a.n = b->n; a.n_inst = b->n_inst; a.tiles = b->tiles; a.k = k;
+    a.last_idx = (long long*)b->last_idx_dev; a.best_val = b->best_val_dev; a.utility = utility_dev;
+    a.seed = uniform_seed; a.cycle = cycle;
+    a.noise_from_stats = var_noise ? 0 : 1; a.log_form = log_form; a.method = method; a.cost_change = cost_change;
+    if (var_noise) for (int c = 0; c < m->nch; ++c) a.var_noise[c] = var_noise[c];
+    for (int j = 0; j < m->ncons; ++j) a.cons[j] = constants[j];
+    int64_t g = (int64_t)obe_sms() * 4;
+    if (g > b->n_inst) g = b->n_inst;
+    const size_t smem = (size_t)(OBE_TILE + k * (m->np_model > 0 ? m->np_model : 1)) * sizeof(double);
+    return launch_kernel(m->f_bselect, (int)g, smem, (cudaStream_t)stream, &a);
 }
 
 }  // extern "C"

@@ -324,10 +324,24 @@ struct ObeUpdateEval {
     }
 };
 
-template <class Model, int D, int SRC>
+// record layout of a batched instance (shared memory), see obe_update_batched_body
+#define OBE_REC_SET 0      /* [4] setting        */
+#define OBE_REC_Y 4        /* [4] y_meas         */
+#define OBE_REC_ISIG 8     /* [4] 1/sigma        */
+#define OBE_REC_PIVOT 12   /* [8] pivot          */
+#define OBE_REC_INVS 20
+#define OBE_REC_LEN 24
+
+template <class Model, int D, int SRC, bool BATCHED = false>
 __device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const double (&p)[D], double w_in,
                                                  const double (&yg)[OBE_MAX_CH], double lik_given,
-                                                 double invS, ObeAcc<D>& acc) {
+                                                 double invS, ObeAcc<D>& acc, const double* rec = nullptr) {
+    // single cloud: the record sits in the kernel parameters (constant bank operands);
+    // batched: every instance has its own record, staged in shared memory
+    const double* r_set = BATCHED ? rec + OBE_REC_SET : a.setting;
+    const double* r_y = BATCHED ? rec + OBE_REC_Y : a.y_meas;
+    const double* r_isig = BATCHED ? rec + OBE_REC_ISIG : a.inv_sigma;
+    const double* r_piv = BATCHED ? rec + OBE_REC_PIVOT : a.pivot;
     double t;
     if (SRC == OBE_SRC_NONE) {
         t = w_in;
@@ -342,7 +356,7 @@ __device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const d
             constexpr int NY = (SRC == OBE_SRC_MODEL) ? (Model::NCH > 0 ? Model::NCH : 1) : OBE_MAX_CH;
             double y[NY];
             if (SRC == OBE_SRC_MODEL) {
-                ObeUpdateEval<Model>::eval(a.setting, p, a.cons, y);
+                ObeUpdateEval<Model>::eval(r_set, p, a.cons, y);
             } else {
 #pragma unroll
                 for (int c = 0; c < NY; ++c) y[c] = yg[c];
@@ -353,7 +367,7 @@ __device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const d
                     // exp(-((y - y_meas)/sigma)**2 / 2) / sigma  (obe_base.py:264-271) with the
                     // division by sigma done as a multiplication by its reciprocal: the host's
                     // 1/sigma for a known sigma, one in-kernel reciprocal for a noise parameter
-                    double inv_sig = a.inv_sigma[c];
+                    double inv_sig = r_isig[c];
                     if (a.n_noise > 0) {
                         const int ni = a.noise_idx[c];
                         double sig = 1.0;
@@ -362,7 +376,7 @@ __device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const d
                             if (j == ni) sig = p[j];
                         inv_sig = obe_rcp_fast(sig);
                     }
-                    const double q = (y[c] - a.y_meas[c]) * inv_sig;
+                    const double q = (y[c] - r_y[c]) * inv_sig;
                     lik *= obe_exp_nonpos(-0.5 * (q * q)) * inv_sig;
                 }
             }
@@ -370,7 +384,7 @@ __device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const d
         }
         t = obe_nan_to_num_fast(w * lik);
     }
-    if (SRC == OBE_SRC_NONE && (a.mask_le | a.mask_lt)) {      // constraint masks ride on the refresh pass only
+    if ((SRC == OBE_SRC_NONE || BATCHED) && (a.mask_le | a.mask_lt)) {   // constraint masks: refresh pass / batched
         bool bad = false;
 #pragma unroll
         for (int j = 0; j < D; ++j) {
@@ -386,7 +400,7 @@ __device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const d
     acc.sumt += t;
     double dx[D];
 #pragma unroll
-    for (int j = 0; j < D; ++j) dx[j] = p[j] - a.pivot[j];
+    for (int j = 0; j < D; ++j) dx[j] = p[j] - r_piv[j];
     int q = 0;
 #pragma unroll
     for (int j = 0; j < D; ++j) {
@@ -646,6 +660,340 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Batched independent instances (BASELINE config c5: 4096 lock-in engines x 1e4 particles).
+// One big SoA cloud: instance b owns particles [b*np, b*np + n) of a (d, B*np) array, np = n
+// rounded up to whole tiles (padding particles are never read).  Two buffers; cur[b] says which one
+// holds instance b (a resample writes the other one and flips it, so instances that do not resample
+// are never copied).  Every instance has its own record, pivot, stats block, CDF prefix row,
+// resample flag and RNG streams; nothing returns to the host inside a cycle.
+// ---------------------------------------------------------------------------------------------
+struct ObeBatchArgs {
+    ObeUpdateArgs u;              // the fields shared by all instances (cons, noise_idx, masks, choke, ...)
+    const double* particles[2];   // (d, ld) each, ld = B * np
+    double* weights[2];           // (ld) each
+    int* cur;                     // (B) buffer holding instance b
+    double* tile_sums;            // (B * T)
+    double* prefix;               // (B * (T + 1))
+    double* stats;                // (B * OBE_STATS_LEN)
+    double* pivot;                // (B * OBE_MAX_DIMS)   updated to the new mean by the kernel
+    const double* rec_in;         // (B * 12): setting[4], y_meas[4], sigma[4]
+    const double* settings;       // (s, lds) grid, for use_last
+    long long lds;
+    const long long* last_idx;    // (B) last chosen setting index (use_last)
+    int* flag;                    // (B) out: 1 = this instance must resample
+    long long n_inst, np;         // instances, padded particles per instance
+    int tiles;                    // np / OBE_TILE
+    int use_last;                 // 1: the setting of instance b is settings[:, last_idx[b]]
+    int n_set;                    // number of setting knobs
+    double resample_threshold;
+    int force_resample;
+    const int* inst_list;         // optional compacted list of instances to process ...
+    const int* n_list;            // ... and its length (device)
+};
+
+template <class Model, int D, int SRC>
+__device__ void obe_update_batched_body(const ObeBatchArgs& a) {
+    constexpr int NROWS = 1 + D;
+    using ST = ObeStage<NROWS>;
+    constexpr int SE = ST::ELEMS, NST = ST::NSTAGES, SUB = ST::SUB, EPT = ST::EPT;
+    constexpr int NM2 = D * (D + 1) / 2;
+    constexpr int NACC = 3 + D + NM2 + OBE_MAX_CH;
+    extern __shared__ __align__(128) unsigned char obe_dyn_smem[];
+    double* stage_base = reinterpret_cast<double*>(obe_dyn_smem);
+    unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(obe_dyn_smem + NST * ST::BYTES);
+    unsigned long long* empty_bar = full_bar + NST;
+    __shared__ double red[2][OBE_CONSUMER_WARPS];
+    __shared__ double accsm[OBE_CONSUMER_WARPS][OBE_NACC_MAX];
+    __shared__ double rec_s[2][OBE_REC_LEN];
+    __shared__ double tsum_s[64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long n = a.u.n;                     // real particles per instance
+    const int T = a.tiles;
+    const long long np = a.np;
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            obe_mbar_init(full_bar + s, 1);
+            obe_mbar_init(empty_bar + s, OBE_CONSUMER_WARPS);
+        }
+        obe_mbar_fence_init();
+    }
+    __syncthreads();
+    const long long n_inst = a.inst_list ? (long long)*a.n_list : a.n_inst;
+    const long long my_inst = (n_inst > (long long)blockIdx.x)
+                                  ? (n_inst - 1 - (long long)blockIdx.x) / (long long)gridDim.x + 1 : 0;
+    const unsigned per_inst = (unsigned)(T * SUB);
+    const unsigned total_iters = (unsigned)(my_inst * per_inst);
+    auto produce = [&](unsigned p) {
+        if (p >= total_iters) return;
+        const int s = p % NST;
+        const unsigned k = p / NST;
+        const long long bi = (long long)blockIdx.x + (long long)(p / per_inst) * (long long)gridDim.x;
+        const long long b = a.inst_list ? (long long)a.inst_list[bi] : bi;
+        const long long off = b * np + (long long)((p % per_inst) / SUB) * OBE_TILE + (long long)(p % SUB) * SE;
+        const int cb = a.cur[b];
+        obe_mbar_wait(empty_bar + s, (k & 1u) ^ 1u);
+        const unsigned row_bytes = (unsigned)SE * 8u;
+        obe_mbar_expect_tx(full_bar + s, row_bytes * (unsigned)NROWS);
+        double* dst = stage_base + (size_t)s * (NROWS * SE);
+        obe_bulk_g2s(dst, a.weights[cb] + off, row_bytes, full_bar + s);
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            obe_bulk_g2s(dst + (1 + j) * SE, a.particles[cb] + j * a.u.ld + off, row_bytes, full_bar + s);
+    };
+    if (tid == 0) {
+        for (unsigned p = 0; p + 1 < (unsigned)NST; ++p) produce(p);
+    }
+    const int ct = tid, cwarp = warp;
+    const bool write_weights = a.u.write_weights != 0;
+    unsigned it = 0, tile_par = 0;
+    for (long long ii = 0; ii < my_inst; ++ii) {
+        const long long bi = (long long)blockIdx.x + ii * (long long)gridDim.x;
+        const long long b = a.inst_list ? (long long)a.inst_list[bi] : bi;
+        const int cb = a.cur[b];
+        double* rec = rec_s[ii & 1];
+        // ---- per-instance record into shared memory
+        if (ct < OBE_REC_LEN) {
+            double v = 0.0;
+            if (ct < OBE_REC_Y) {
+                if (ct < a.n_set)
+                    v = a.use_last ? a.settings[ct * a.lds + a.last_idx[b]] : a.rec_in[b * 12 + ct];
+            } else if (ct < OBE_REC_ISIG) {
+                v = a.rec_in[b * 12 + ct];
+            } else if (ct < OBE_REC_PIVOT) {
+                const double sg = a.rec_in[b * 12 + ct];
+                v = (sg != 0.0) ? 1.0 / sg : 1.0;
+            } else if (ct < OBE_REC_INVS) {
+                v = a.pivot[b * OBE_MAX_DIMS + (ct - OBE_REC_PIVOT)];
+            } else if (ct == OBE_REC_INVS) {
+                v = a.u.scale_in ? a.stats[b * OBE_STATS_LEN + OBE_ST_INVS] : 1.0;
+            }
+            rec[ct] = v;
+        }
+        obe_named_bar(1, OBE_CONSUMER_THREADS);
+        const double invS = rec[OBE_REC_INVS];
+        ObeAcc<D> acc;
+        acc.sumsq = 0.0; acc.sumt = 0.0; acc.nzero = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc.m1[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NM2; ++j) acc.m2[j] = 0.0;
+#pragma unroll
+        for (int c = 0; c < OBE_MAX_CH; ++c) acc.noise[c] = 0.0;
+        for (int t = 0; t < T; ++t, tile_par ^= 1u) {
+            double tsum = 0.0;
+#pragma unroll 1
+            for (int sub = 0; sub < SUB; ++sub, ++it) {
+                const int s = it % NST;
+                const unsigned k = it / NST;
+                const long long loc = (long long)t * OBE_TILE + (long long)sub * SE;   // offset in the instance
+                const long long base = b * np + loc;
+                long long nv = n - loc;
+                const int n_valid = nv >= SE ? SE : (nv > 0 ? (int)nv : 0);
+                if (tid == 0) produce(it + NST - 1);
+                obe_mbar_wait(full_bar + s, k & 1u);
+                const double* src = stage_base + (size_t)s * (NROWS * SE);
+                double wv[EPT], pv[D][EPT];
+#pragma unroll
+                for (int q = 0; q < EPT / 2; ++q) {
+                    const int e = 2 * (ct + q * OBE_CONSUMER_THREADS);
+                    const double2 w2 = *reinterpret_cast<const double2*>(src + e);
+                    wv[2 * q] = w2.x; wv[2 * q + 1] = w2.y;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        const double2 p2 = *reinterpret_cast<const double2*>(src + (1 + j) * SE + e);
+                        pv[j][2 * q] = p2.x; pv[j][2 * q + 1] = p2.y;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) obe_mbar_arrive(empty_bar + s);
+#pragma unroll
+                for (int q = 0; q < EPT / 2; ++q) {
+                    const int e0 = 2 * (ct + q * OBE_CONSUMER_THREADS);
+                    double tv[2] = {0.0, 0.0};
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (e0 + h < n_valid) {
+                            double px[D], yg[OBE_MAX_CH] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                            for (int j = 0; j < D; ++j) px[j] = pv[j][2 * q + h];
+                            tv[h] = obe_update_one<Model, D, SRC, true>(a.u, px, wv[2 * q + h], yg, 1.0, invS, acc, rec);
+                        }
+                    }
+                    tsum += tv[0] + tv[1];
+                    if (write_weights) {
+                        if (e0 + 1 < n_valid) obe_st2(a.weights[cb] + base + e0, make_double2(tv[0], tv[1]));
+                        else if (e0 < n_valid) a.weights[cb][base + e0] = tv[0];
+                    }
+                }
+            }
+            tsum = obe_warp_sum(tsum);
+            if (lane == 0) red[tile_par][cwarp] = tsum;
+            obe_named_bar(1, OBE_CONSUMER_THREADS);
+            if (ct == 0) {
+                double s = red[tile_par][0];
+#pragma unroll
+                for (int w = 1; w < OBE_CONSUMER_WARPS; ++w) s += red[tile_par][w];
+                a.tile_sums[b * T + t] = s;
+                tsum_s[t] = s;
+            }
+        }
+        // ---- instance epilogue: stats block, CDF prefix row, resample flag, next pivot
+        double vals[NACC];
+        vals[0] = acc.sumsq; vals[1] = acc.sumt; vals[2] = acc.nzero;
+#pragma unroll
+        for (int j = 0; j < D; ++j) vals[3 + j] = acc.m1[j];
+#pragma unroll
+        for (int j = 0; j < NM2; ++j) vals[3 + D + j] = acc.m2[j];
+#pragma unroll
+        for (int c = 0; c < OBE_MAX_CH; ++c) vals[3 + D + NM2 + c] = acc.noise[c];
+#pragma unroll
+        for (int v = 0; v < NACC; ++v) {
+            const double sv = obe_warp_sum(vals[v]);
+            if (lane == 0) accsm[cwarp][v] = sv;
+        }
+        obe_named_bar(1, OBE_CONSUMER_THREADS);
+        double* st = a.stats + b * OBE_STATS_LEN;
+        if (ct < NACC) {
+            double sv = accsm[0][ct];
+#pragma unroll
+            for (int w = 1; w < OBE_CONSUMER_WARPS; ++w) sv += accsm[w][ct];
+            int dst;
+            if (ct == 0) dst = OBE_ST_SUMSQ;
+            else if (ct == 1) dst = OBE_ST_SUMT;
+            else if (ct == 2) dst = OBE_ST_NZERO;
+            else if (ct < 3 + D) dst = OBE_ST_M1 + (ct - 3);
+            else if (ct < 3 + D + NM2) dst = OBE_ST_M2 + (ct - 3 - D);
+            else dst = OBE_ST_NOISE + (ct - 3 - D - NM2);
+            st[dst] = sv;
+            accsm[0][ct] = sv;        // keep the totals for thread 0 below
+        }
+        obe_named_bar(1, OBE_CONSUMER_THREADS);
+        if (ct == 0) {
+            double run = 0.0;
+            double* pre = a.prefix + b * (T + 1);
+            for (int t = 0; t < T; ++t) { pre[t] = run; run += tsum_s[t]; }
+            pre[T] = run;
+            const double total = run, ssq = accsm[0][0], sumt = accsm[0][1];
+            st[OBE_ST_TOTAL] = total;
+            st[OBE_ST_INVS] = 1.0 / total;
+            const double neff = (total * total) / ssq;
+            st[OBE_ST_NEFF] = neff;
+            for (int j = 0; j < D; ++j) {
+                st[OBE_ST_PIVOT + j] = rec[OBE_REC_PIVOT + j];
+                if (sumt > 0.0) a.pivot[b * OBE_MAX_DIMS + j] = rec[OBE_REC_PIVOT + j] + accsm[0][3 + j] / sumt;
+            }
+            if (a.flag) {
+                const double nn = (double)n;
+                a.flag[b] = (a.force_resample || neff < 0.1 * nn || neff / nn < a.resample_threshold) ? 1 : 0;
+            }
+        }
+        obe_named_bar(1, OBE_CONSUMER_THREADS);
+    }
+}
+
+__device__ __forceinline__ long long obe_min_ll(long long a, long long b) { return a < b ? a : b; }
+
+// ---------------------------------------------------------------------------------------------
+// canonical in-tile scan: thread t owns elements [8t, 8t+8) of the tile.
+//   incl[e] = (sum of earlier warps' totals, sequential) + (exclusive KS scan over lanes) + running
+// The canonical CDF is cdf[j] = (tile_prefix[k] + incl_j) * (1/total), EXCEPT the last valid element
+// of each tile, which is tile_prefix[k+1] * (1/total) by definition (so tile_sums may be reduced in
+// any order), and the very last particle, which is exactly 1.  (One IEEE multiply by the rounded
+// reciprocal instead of a divide per particle: still a fixed, monotone function of the weights that
+// numpy reproduces bit for bit as cdf_unnormalised * (1.0 / total).)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_load_blocked(const double* __restrict__ w, long long base, long long n,
+                                                  double (&v)[OBE_EPT]) {
+    const long long i0 = base + (long long)threadIdx.x * OBE_EPT;
+    if (i0 + OBE_EPT <= n) {
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; e += 2) {
+            const double2 x = *reinterpret_cast<const double2*>(w + i0 + e);
+            v[e] = x.x; v[e + 1] = x.y;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; ++e) v[e] = (i0 + e < n) ? w[i0 + e] : 0.0;
+    }
+}
+
+__device__ __forceinline__ void tile_scan_blocked(const double (&v)[OBE_EPT], double (&incl)[OBE_EPT],
+                                                  double* sm /*8*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double run = 0.0;
+#pragma unroll
+    for (int e = 0; e < OBE_EPT; ++e) { run += v[e]; incl[e] = run; }
+    double x = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    double ex = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) ex = 0.0;
+    __syncthreads();
+    if (lane == 31) sm[warp] = x;
+    __syncthreads();
+    double wb = 0.0;
+    for (int w2 = 0; w2 < warp; ++w2) wb += sm[w2];
+    const double base = wb + ex;
+#pragma unroll
+    for (int e = 0; e < OBE_EPT; ++e) incl[e] = base + incl[e];
+}
+
+// normalised canonical CDF values of this thread's 8 elements of tile k
+// Sharded clouds: `offset` is the summed weight of all lower-ranked shards and inv_total the
+// reciprocal of the GLOBAL total; last_shard marks the shard that holds the global last particle.
+__device__ __forceinline__ void tile_cdf_blocked(const double* __restrict__ w, const double* __restrict__ prefix,
+                                                 long long k, long long n, double inv_total,
+                                                 double (&cn)[OBE_EPT], double* sm, double offset = 0.0,
+                                                 bool last_shard = true) {
+    double v[OBE_EPT], incl[OBE_EPT];
+    const long long base = k * OBE_TILE;
+    tile_load_blocked(w, base, n, v);
+    tile_scan_blocked(v, incl, sm);
+    const double p0 = obe_add(offset, prefix[k]);
+    const long long last = obe_min_ll(n, base + OBE_TILE) - 1;
+    const long long i0 = base + (long long)threadIdx.x * OBE_EPT;
+#pragma unroll
+    for (int e = 0; e < OBE_EPT; ++e) cn[e] = obe_mul(obe_add(p0, incl[e]), inv_total);
+    if (i0 + OBE_EPT > last) {                 // only the thread(s) at the end of the tile
+        const double c1 = (last_shard && last == n - 1) ? 1.0 : obe_mul(obe_add(offset, prefix[k + 1]), inv_total);
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; ++e)
+            if (i0 + e >= last) cn[e] = c1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller (restated in oracle/obe_oracle.py:device_normals)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3,
+                                              unsigned int k0, unsigned int k1, unsigned int (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// uniform double in (0,1) from two Philox words
+__device__ __forceinline__ double obe_u53(unsigned int lo, unsigned int hi) {
+    const unsigned long long x = ((unsigned long long)hi << 32) | lo;
+    return ((double)(x >> 11) + 0.5) * 1.1102230246251565e-16;  // 2^-53
+}
+// the q-th uniform of instance b in cycle `cycle` (batched engines; restated in oracle.batch_uniform)
+__device__ __forceinline__ double obe_batch_uniform(unsigned long long seed, unsigned int b, unsigned int cycle,
+                                                    unsigned int q) {
+    unsigned int r[4];
+    philox4x32_10(q, cycle, b, 0x0B5E0001u, (unsigned int)(seed & 0xffffffffull), (unsigned int)(seed >> 32), r);
+    return obe_u53(r[0], r[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Utility over the setting grid (obe_base.py:463-489, 628-655) fused with the argmax of
 // opt_setting (obe_base.py:748).  One thread per setting; the K drawn parameter sets sit in
 // shared memory and are re-used by every thread.  The (K,C,S) array of the reference
@@ -794,6 +1142,168 @@ __device__ void obe_utility_body(const ObeUtilityArgs& a) {
     *a.counter = 0u;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched design half: for every instance, K weighted draws through its canonical CDF, the
+// variance utility over the setting grid and the argmax -- one CTA per instance, nothing leaves
+// the device.  Same arithmetic as k_draw + obe_utility_body, so an instance reproduces what a
+// single engine fed the same uniforms would choose.
+// ---------------------------------------------------------------------------------------------
+struct ObeBSelectArgs {
+    const double* particles[2];
+    const double* weights[2];
+    const int* cur;
+    const double* prefix;        // (B * (T + 1))
+    const double* stats;         // (B * OBE_STATS_LEN)
+    const double* settings;      // (s, lds)
+    long long lds, n_settings;
+    long long ld, np, n, n_inst;
+    int tiles, k;
+    long long* last_idx;         // (B) in: previous choice (sticky cost), out: new choice
+    double* best_val;            // (B)
+    double* utility;             // (B * S) or null
+    unsigned long long seed;
+    unsigned int cycle;
+    int noise_from_stats, log_form, method;
+    double cost_change;          // > 0: cost = cost_change except 1 at the previous choice
+    double var_noise[OBE_MAX_CH];
+    double cons[OBE_MAX_CONS];
+};
+
+template <class Model>
+__device__ void obe_bselect_body(const ObeBSelectArgs& a) {
+    extern __shared__ double obe_smem[];
+    double* cn_s = obe_smem;                       // [OBE_TILE]
+    double* sdraw = obe_smem + OBE_TILE;           // [K][NP]
+    __shared__ double sm[8];
+    __shared__ double uq_s[OBE_MAX_DRAWS];
+    __shared__ int tq_s[OBE_MAX_DRAWS];
+    __shared__ long long iq_s[OBE_MAX_DRAWS];
+    __shared__ double bval[OBE_THREADS / 32];
+    __shared__ long long bidx[OBE_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = a.k, T = a.tiles;
+    for (long long b = blockIdx.x; b < a.n_inst; b += gridDim.x) {
+        const int cb = a.cur[b];
+        const double* w = a.weights[cb] + b * a.np;
+        const double* pre = a.prefix + b * (T + 1);
+        const double inv_total = 1.0 / pre[T];
+        if (tid < K) {
+            const double u = obe_batch_uniform(a.seed, (unsigned int)b, a.cycle, (unsigned int)tid);
+            int t = 0;
+            for (int tt = 0; tt < T; ++tt) {
+                const double c = (tt == T - 1) ? 1.0 : obe_mul(pre[tt + 1], inv_total);
+                if (c <= u) t = tt + 1;
+            }
+            uq_s[tid] = u;
+            tq_s[tid] = t < T - 1 ? t : T - 1;
+        }
+        __syncthreads();
+        for (int t = 0; t < T; ++t) {
+            double cn[OBE_EPT];
+            tile_cdf_blocked(w, pre, t, a.n, inv_total, cn, sm);
+#pragma unroll
+            for (int e = 0; e < OBE_EPT; ++e) cn_s[tid * OBE_EPT + e] = cn[e];
+            __syncthreads();
+            if (tid < K && tq_s[tid] == t) {
+                const long long base = (long long)t * OBE_TILE;
+                const int cnt = (int)(obe_min_ll(a.n, base + OBE_TILE) - base);
+                const double u = uq_s[tid];
+                int lo = 0, hi = cnt;                 // first j with cn_s[j] > u
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (cn_s[mid] <= u) lo = mid + 1; else hi = mid;
+                }
+                iq_s[tid] = base + (lo < cnt - 1 ? lo : cnt - 1);
+            }
+            __syncthreads();
+        }
+        for (int q = tid; q < K * Model::NP; q += blockDim.x) {
+            const int kq = q / Model::NP, j = q % Model::NP;
+            sdraw[q] = a.particles[cb][j * a.ld + b * a.np + iq_s[kq]];
+        }
+        __syncthreads();
+        double var_n[Model::NCH];
+#pragma unroll
+        for (int c = 0; c < Model::NCH; ++c) {
+            const double* st = a.stats + b * OBE_STATS_LEN;
+            var_n[c] = a.noise_from_stats ? obe_div(st[OBE_ST_NOISE + c], st[OBE_ST_SUMT]) : a.var_noise[c];
+        }
+        const long long prev_choice = a.last_idx[b];
+        const double kd = (double)K;
+        double best = 0.0;
+        long long besti = -1;
+        for (long long s = tid; s < a.n_settings; s += blockDim.x) {
+            double st[Model::NS > 0 ? Model::NS : 1];
+#pragma unroll
+            for (int j = 0; j < Model::NS; ++j) st[j] = a.settings[j * a.lds + s];
+            double y[Model::NCH], mean[Model::NCH], ss[Model::NCH];
+#pragma unroll
+            for (int c = 0; c < Model::NCH; ++c) { mean[c] = 0.0; ss[c] = 0.0; }
+            for (int k = 0; k < K; ++k) {
+                Model::eval(st, sdraw + k * Model::NP, a.cons, y);
+#pragma unroll
+                for (int c = 0; c < Model::NCH; ++c) mean[c] = obe_add(mean[c], y[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < Model::NCH; ++c) mean[c] = obe_div(mean[c], kd);
+            for (int k = 0; k < K; ++k) {
+                Model::eval(st, sdraw + k * Model::NP, a.cons, y);
+#pragma unroll
+                for (int c = 0; c < Model::NCH; ++c) {
+                    const double dlt = obe_sub(y[c], mean[c]);
+                    ss[c] = obe_add(ss[c], obe_mul(dlt, dlt));
+                }
+            }
+            double u = 0.0;
+#pragma unroll
+            for (int c = 0; c < Model::NCH; ++c) {
+                const double r = obe_div(obe_div(ss[c], kd), var_n[c]);
+                u = obe_add(u, a.log_form ? log(obe_add(1.0, r)) : r);
+            }
+            if (a.cost_change > 0.0) u = obe_div(u, (s == prev_choice) ? 1.0 : a.cost_change);
+            if (a.utility) a.utility[b * a.n_settings + s] = u;
+            const bool unan = (u != u), bnan = (best != best);
+            if (besti < 0 || (!bnan && (unan || u > best))) { best = u; besti = s; }
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, m);
+            const long long oi = __shfl_xor_sync(0xffffffffu, besti, m);
+            const bool onan = (ov != ov), bnan = (best != best);
+            bool take = false;
+            if (oi >= 0) {
+                if (besti < 0) take = true;
+                else if (onan && bnan) take = oi < besti;
+                else if (onan) take = true;
+                else if (bnan) take = false;
+                else take = (ov > best) || (ov == best && oi < besti);
+            }
+            if (take) { best = ov; besti = oi; }
+        }
+        if (lane == 0) { bval[warp] = best; bidx[warp] = besti; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w2 = 1; w2 < (int)(blockDim.x >> 5); ++w2) {
+                const double ov = bval[w2];
+                const long long oi = bidx[w2];
+                const bool onan = (ov != ov), bnan = (best != best);
+                bool take = false;
+                if (oi >= 0) {
+                    if (besti < 0) take = true;
+                    else if (onan && bnan) take = oi < besti;
+                    else if (onan) take = true;
+                    else if (bnan) take = false;
+                    else take = (ov > best) || (ov == best && oi < besti);
+                }
+                if (take) { best = ov; besti = oi; }
+            }
+            a.last_idx[b] = besti;
+            a.best_val[b] = best;
+        }
+        __syncthreads();
+    }
+}
+
 // eval_over_all_parameters (obe_base.py:298-320): y[c, i] = model(one_setting, particle_i)
 template <class Model, int D>
 __device__ void obe_eval_params_body(const ObeEvalArgs& a) {
@@ -837,6 +1347,14 @@ struct ObeNoModel {
     }                                                                                                     \
     extern "C" __global__ void __launch_bounds__(OBE_THREADS) obe_k_evalp_##SUFFIX(const ObeEvalArgs a) {  \
         obe_eval_params_body<MODEL, D>(a);                                                                \
+    }
+
+#define OBE_DEFINE_BATCH_KERNELS(MODEL, D, SUFFIX)                                                              \
+    extern "C" __global__ void __launch_bounds__(OBE_UPDATE_THREADS, 1) obe_k_bupdate_##SUFFIX(const ObeBatchArgs a) { \
+        obe_update_batched_body<MODEL, D, OBE_SRC_MODEL>(a);                                                    \
+    }                                                                                                          \
+    extern "C" __global__ void __launch_bounds__(OBE_THREADS) obe_k_bselect_##SUFFIX(const ObeBSelectArgs a) {   \
+        obe_bselect_body<MODEL>(a);                                                                            \
     }
 
 #define OBE_DEFINE_GRID_KERNELS(MODEL, SUFFIX)                                                             \

@@ -577,3 +577,32 @@ class OracleOBE:
 
     def std(self):
         return std_biased(self.particles, self.particle_weights)
+
+
+# ----------------------------------------------------------------------------
+# Uniform streams of the batched engines (restatement of csrc obe_batch_uniform): the q-th
+# uniform of instance b in cycle `cycle` is u53 of Philox4x32-10(ctr=(q, cycle, b, 0x0B5E0001), key=seed).
+# ----------------------------------------------------------------------------
+def batch_uniform(seed, b, cycle, q):
+    q = np.atleast_1d(np.asarray(q, dtype=np.uint32))
+    x = philox4x32_10(q, np.uint32(cycle), np.uint32(b), np.uint32(0x0B5E0001),
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    v = (x[1].astype(np.uint64) << np.uint64(32)) | x[0].astype(np.uint64)
+    return ((v >> np.uint64(11)).astype(np.float64) + 0.5) * (2.0 ** -53)
+
+
+class ReplayRng:
+    """Stands in for a numpy Generator inside a single engine so that it consumes exactly the
+    uniforms instance b of a batched engine uses: random(K) -> uniforms 0..K-1 of the current cycle,
+    random() -> uniform K (the comb offset of a resample).  Call next_cycle() after every cycle."""
+
+    def __init__(self, seed, b, n_draws):
+        self.seed, self.b, self.k, self.cycle = seed, b, n_draws, 0
+
+    def random(self, n=None):
+        if n is None:
+            return float(batch_uniform(self.seed, self.b, self.cycle, self.k)[0])
+        return batch_uniform(self.seed, self.b, self.cycle, np.arange(n))
+
+    def next_cycle(self):
+        self.cycle += 1
