@@ -140,6 +140,90 @@ def cpu_cycle_rate(n_full, n_settings, n_draws, n_sample=1_000_000, budget_s=20.
 
 
 # -------------------------------------------------------------------------------------------------
+def bench_c5(args, rank, world):
+    """BASELINE configs[4]: 4096 independent lock-in engines x 1e4 particles, batched; instances are split over
+    the ranks with no collective at all (weak in nothing: the total is fixed -> strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from optbayesexpt_b200.batched import BatchedOptBayesExpt
+    from oracle import obe_oracle as orc
+    B_total, n = 4096, 10000
+    B = B_total // world
+    g = torch.Generator(device='cuda')
+    g.manual_seed(1001 + rank)
+    prior = torch.empty((B, 4, n), dtype=torch.float64, device='cuda')
+    for j, sc_ in enumerate((1e-3, 10.0, 1e-5, 10.0)):
+        prior[:, j] = torch.empty((B, n), dtype=torch.float64, device='cuda').exponential_(1.0, generator=g) * sc_
+    settings = (2 * np.pi * np.logspace(2, 6, 200),)
+    eng = BatchedOptBayesExpt('lockin_coil', settings, prior, (), noise_parameter_index=(3, 3),
+                              constraint_lt=(0, 1, 2, 3), cost_of_changing_setting=5.0, scale=False, seed=1003)
+    del prior
+    truth = (1.2e-3, 8.0, 0.9e-5)
+    meas = np.random.default_rng(1002 + rank)
+
+    def step(sync):
+        out = eng.opt_setting(sync=sync)
+        if sync:
+            z = orc.model_lockin_coil((out[1][0],), truth, ())
+            y = z.T + 5.0 * meas.standard_normal((B, 2))
+        else:
+            y = step.y
+        eng.pdf_update(y, force_resample=args.force_resample)
+        step.y = y
+    step.y = None
+    for _ in range(max(args.warmup, 3)):
+        step(True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(False)                       # device-resident: records stay on the device
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(True)                        # e2e: chosen settings D2H, measurements H2D every cycle
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(tt[0]), float(tt[1])
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    d = 4
+    b_cycle = 8.0 * n * B_total * ((d + 2) + (args.force_resample and (2 * d + 2) + (d + 1) or 0))
+    line = {'metric': 'batched pdf_update+resample+opt_setting cycles/sec (4096 engines)', 'value': 1e3 / ms,
+            'unit': 'batched cycles/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'batched demos/lockin: 4096 OBE instances x 1e4 particles, d=4, 2 channels, S=200 '
+                                   '(BASELINE configs[4])', 'force_resample': bool(args.force_resample)},
+            'instance_cycles_per_s': B_total * 1e3 / ms,
+            'e2e': {'value': 1.0 / e2e_s, 'unit': 'batched cycles/s', 'h2d_bytes_per_step': B * 12 * 8,
+                    'd2h_bytes_per_step': B * 8},
+            'roofline': {'bound': 'hbm', 'achieved': b_cycle / world / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                         'frac': b_cycle / world / (ms * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
+                         'kernel': 'whole batched cycle (update + resample of flagged instances + select)'},
+            'reference_note': 'one reference instance runs 488 cycles/s on one CPU core (BASELINE.md): 4096 instances '
+                              '~ 8.4 s per batched cycle'}
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -150,6 +234,9 @@ def main():
     ap.add_argument('--settings', type=int, default=100000)
     ap.add_argument('--draws', type=int, default=30)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--force-resample', action='store_true')
+    ap.add_argument('--workload', default='c4', choices=['c4', 'c5'],
+                    help='c4: 1e8-particle Lorentzian cloud (default, the metric); c5: 4096 batched lock-in engines')
     args = ap.parse_args()
     n_total = int(args.particles)
     rank = int(os.environ.get('RANK', 0))
@@ -159,6 +246,8 @@ def main():
               'particles': n_total, 'settings': args.settings, 'n_draws': args.draws, 'n_params': 3,
               'l2': 'inputs (3.2 GB per cycle) exceed the 126 MB L2, no flush needed'}
 
+    if args.workload == 'c5' and args.impl == 'ours':
+        return bench_c5(args, rank, world)
     if args.impl == 'reference':
         if rank != 0:
             return
