@@ -573,7 +573,8 @@ __device__ __forceinline__ double comb_count_d(double c, double u0, double inv_n
     return i;
 }
 
-#define OBE_OUT_CHUNK 2048
+#define OBE_OUT_CHUNK 4096
+#define OBE_SPT (OBE_OUT_CHUNK / OBE_THREADS) /* output slots per thread in the mark scan */
 // plan: H[k] = first output slot owned by tile k (monotone), unit_start[k] = first work unit of
 // tile k, one unit = up to OBE_OUT_CHUNK output slots of one input tile.
 __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __restrict__ prefix, long long n_tiles,
@@ -662,8 +663,10 @@ __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int span = (int)(Hk1 - Hk);
     const int rel_end = min(rel_begin + OBE_OUT_CHUNK, span);
-    // clear the marks (8 per thread, 16-byte store)
-    *reinterpret_cast<uint4*>(&anc_s[tid * OBE_EPT]) = make_uint4(0u, 0u, 0u, 0u);
+    // clear the marks (OBE_SPT per thread, 16-byte stores)
+#pragma unroll
+    for (int v = 0; v < OBE_SPT / 8; ++v)
+        *reinterpret_cast<uint4*>(&anc_s[tid * OBE_SPT + 8 * v]) = make_uint4(0u, 0u, 0u, 0u);
     // ---- 1. end slot of every particle of the tile
     double cn[OBE_EPT];
     tile_cdf_blocked(c.w_in, c.prefix, k, c.n_in, c.inv_total, cn, sm, c.cdf_offset, c.last_shard);
@@ -706,17 +709,20 @@ __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long
         prev = end;
     }
     __syncthreads();
-    // max-scan of the marks over the chunk's slots (blocked: 8 consecutive slots per thread)
-    int m[OBE_EPT];
+    // max-scan of the marks over the chunk's slots (blocked: OBE_SPT consecutive slots per thread)
     {
-        const uint4 raw = *reinterpret_cast<const uint4*>(&anc_s[tid * OBE_EPT]);
-        const unsigned int wds[4] = {raw.x, raw.y, raw.z, raw.w};
+        int m[OBE_SPT];
         int runm = 0;
 #pragma unroll
-        for (int e = 0; e < OBE_EPT; ++e) {
-            const int v = (int)((wds[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
-            runm = max(runm, v);
-            m[e] = runm;
+        for (int v = 0; v < OBE_SPT / 8; ++v) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(&anc_s[tid * OBE_SPT + 8 * v]);
+            const unsigned int wds[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int val = (int)((wds[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
+                runm = max(runm, val);
+                m[8 * v + e] = runm;
+            }
         }
         int xm = runm;
 #pragma unroll
@@ -730,25 +736,42 @@ __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long
         if (lane == 31) smx[warp] = xm;
         __syncthreads();
         for (int w2 = 0; w2 < warp; ++w2) exm = max(exm, smx[w2]);
-        unsigned int packed[4];
 #pragma unroll
-        for (int e = 0; e < OBE_EPT; e += 2) {
-            const unsigned int a0 = (unsigned int)max(m[e], exm), a1v = (unsigned int)max(m[e + 1], exm);
-            packed[e >> 1] = a0 | (a1v << 16);
+        for (int v = 0; v < OBE_SPT / 8; ++v) {
+            unsigned int packed[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                const unsigned int a0 = (unsigned int)max(m[8 * v + e], exm), a1v = (unsigned int)max(m[8 * v + e + 1], exm);
+                packed[e >> 1] = a0 | (a1v << 16);
+            }
+            *reinterpret_cast<uint4*>(&anc_s[tid * OBE_SPT + 8 * v]) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
-        *reinterpret_cast<uint4*>(&anc_s[tid * OBE_EPT]) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
     __syncthreads();
-    // ---- 3. outputs in coalesced order
+    // ---- 3. outputs in coalesced order; the ancestor of the NEXT slot is gathered before the RNG and
+    //         jitter arithmetic of the current one, so the gather latency hides behind ~200 instructions
     const int n_out = rel_end - rel_begin;
+    const int lastrel = (int)(last - base);
+    double xn[D];
+    long long anc_n = 0;
+    if (tid < n_out) {
+        anc_n = base + min((int)anc_s[tid], lastrel);
+#pragma unroll
+        for (int j = 0; j < D; ++j) xn[j] = __ldg(c.pin + j * c.ld_in + c.in_base + anc_n);
+    }
     for (int q = tid; q < n_out; q += OBE_THREADS) {
         const long long og = Hk + rel_begin + q;              // global slot: comb tooth, RNG counter
         const long long o = og - c.slot_begin;                  // position in this shard's output
-        if (o >= c.cap_out) continue;                           // capacity overflow is flagged in the plan
-        const long long anc = base + min((int)anc_s[q], (int)(last - base));
+        const long long anc = anc_n;
         double xv[D], z[D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) xv[j] = __ldg(c.pin + j * c.ld_in + c.in_base + anc);
+        for (int j = 0; j < D; ++j) xv[j] = xn[j];
+        if (q + OBE_THREADS < n_out) {
+            anc_n = base + min((int)anc_s[q + OBE_THREADS], lastrel);
+#pragma unroll
+            for (int j = 0; j < D; ++j) xn[j] = __ldg(c.pin + j * c.ld_in + c.in_base + anc_n);
+        }
+        if (o >= c.cap_out) continue;                           // capacity overflow is flagged in the plan
         if (c.jitter) {
             device_normals<D>(og, c.seed, c.epoch, z);
             if (c.z_out) {
