@@ -656,12 +656,29 @@ struct SysCtx {
 //  2. every particle that owns at least one slot of the chunk marks the first of them with its
 //     index; a max-scan over the chunk's slots turns the marks into the ancestor of every slot
 //  3. slots are walked in coalesced order: gather the ancestor (L1-resident tile), jitter, store
+// Staging (D <= OBE_STAGE_MAX_D): while phases 1-2 run, the TMA engine copies the tile's D particle
+// rows into shared memory (`xs`, one mbarrier), so the ancestor gathers of phase 3 are LDS instead of
+// dependent global loads -- the top stall of the unstaged kernel.
+#define OBE_STAGE_MAX_D 4
 template <int D, class FT>
 __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long Hk, long long Hk1, int rel_begin,
                                          const FT& F, const double* sMean, double* sm, int* smx,
-                                         unsigned short* anc_s) {
+                                         unsigned short* anc_s, double* xs, unsigned long long* bar,
+                                         unsigned int& phase, long long& staged_k) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int span = (int)(Hk1 - Hk);
+    constexpr bool STAGE = (D <= OBE_STAGE_MAX_D);
+    const bool reload = STAGE && (staged_k != k);
+    if (reload && tid == 0) {
+        const long long base0 = k * OBE_TILE;
+        long long cnt = min(c.n_in, base0 + OBE_TILE) - base0;
+        cnt += (cnt & 1);                                  // 16-byte granules; the pad element exists (ld is even)
+        const unsigned row_bytes = (unsigned)cnt * 8u;
+        obe_mbar_expect_tx(bar, row_bytes * (unsigned)D);
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            obe_bulk_g2s(xs + j * OBE_TILE, c.pin + j * c.ld_in + c.in_base + base0, row_bytes, bar);
+    }
     const int rel_end = min(rel_begin + OBE_OUT_CHUNK, span);
     // clear the marks (OBE_SPT per thread, 16-byte stores)
 #pragma unroll
@@ -748,28 +765,40 @@ __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long
         }
     }
     __syncthreads();
-    // ---- 3. outputs in coalesced order; the ancestor of the NEXT slot is gathered before the RNG and
-    //         jitter arithmetic of the current one, so the gather latency hides behind ~200 instructions
+    // ---- 3. outputs in coalesced order.  Staged: gathers are shared-memory reads.  Unstaged: the
+    //         ancestor of the NEXT slot is gathered before the RNG / jitter arithmetic of this one.
     const int n_out = rel_end - rel_begin;
     const int lastrel = (int)(last - base);
+    if (reload) {
+        obe_mbar_wait(bar, phase);
+        phase ^= 1u;
+    }
+    staged_k = k;
     double xn[D];
-    long long anc_n = 0;
-    if (tid < n_out) {
-        anc_n = base + min((int)anc_s[tid], lastrel);
+    int rel_n = 0;
+    if (!STAGE && tid < n_out) {
+        rel_n = min((int)anc_s[tid], lastrel);
 #pragma unroll
-        for (int j = 0; j < D; ++j) xn[j] = __ldg(c.pin + j * c.ld_in + c.in_base + anc_n);
+        for (int j = 0; j < D; ++j) xn[j] = __ldg(c.pin + j * c.ld_in + c.in_base + base + rel_n);
     }
     for (int q = tid; q < n_out; q += OBE_THREADS) {
         const long long og = Hk + rel_begin + q;              // global slot: comb tooth, RNG counter
         const long long o = og - c.slot_begin;                  // position in this shard's output
-        const long long anc = anc_n;
         double xv[D], z[D];
+        int rel;
+        if (STAGE) {
+            rel = min((int)anc_s[q], lastrel);
 #pragma unroll
-        for (int j = 0; j < D; ++j) xv[j] = xn[j];
-        if (q + OBE_THREADS < n_out) {
-            anc_n = base + min((int)anc_s[q + OBE_THREADS], lastrel);
+            for (int j = 0; j < D; ++j) xv[j] = xs[j * OBE_TILE + rel];
+        } else {
+            rel = rel_n;
 #pragma unroll
-            for (int j = 0; j < D; ++j) xn[j] = __ldg(c.pin + j * c.ld_in + c.in_base + anc_n);
+            for (int j = 0; j < D; ++j) xv[j] = xn[j];
+            if (q + OBE_THREADS < n_out) {
+                rel_n = min((int)anc_s[q + OBE_THREADS], lastrel);
+#pragma unroll
+                for (int j = 0; j < D; ++j) xn[j] = __ldg(c.pin + j * c.ld_in + c.in_base + base + rel_n);
+            }
         }
         if (o >= c.cap_out) continue;                           // capacity overflow is flagged in the plan
         if (c.jitter) {
@@ -791,18 +820,24 @@ __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long
 #pragma unroll
         for (int j = 0; j < D; ++j) c.pout[j * c.ld_out + c.out_base + o] = xv[j];
         c.w_out[c.out_base + o] = wo;
-        if (c.idx_out) c.idx_out[o] = anc;
+        if (c.idx_out) c.idx_out[o] = base + rel;
     }
     __syncthreads();
 }
 
 template <int D>
-__global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(const ObeResampleArgs a) {
+__global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 3 : 2)) k_sys_resample(const ObeResampleArgs a) {
     __shared__ double sF[D * D];
     __shared__ double sMean[D];
     __shared__ double sm[8];
     __shared__ int smx[OBE_THREADS / 32];
     __shared__ __align__(16) unsigned short anc_s[OBE_OUT_CHUNK];
+    __shared__ unsigned long long stage_bar;
+    extern __shared__ __align__(128) unsigned char obe_dyn_smem[];
+    double* xs = reinterpret_cast<double*>(obe_dyn_smem);
+    if (threadIdx.x == 0) { obe_mbar_init(&stage_bar, 1); obe_mbar_fence_init(); }
+    unsigned int phase = 0u;
+    long long staged_k = -1;
     setup_factor<D>(a, sF, sMean);
     const long long n_in = a.n_dev_in ? *a.n_dev_in : a.n;
     const long long n_tiles_in = a.n_dev_in ? (n_in + OBE_TILE - 1) / OBE_TILE : a.n_tiles;
@@ -846,8 +881,10 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_sys_resample(
         while (a.unit_start[k32 + 1] <= unit) ++k32;      // largest k with unit_start[k] <= unit
         const long long k = k32;
         const int rel_begin = (unit - a.unit_start[k]) * OBE_OUT_CHUNK;
-        if (D <= 4) sys_unit<D>(c, k, a.plan_h[k], a.plan_h[k + 1], rel_begin, Fr, sMean, sm, smx, anc_s);
-        else sys_unit<D>(c, k, a.plan_h[k], a.plan_h[k + 1], rel_begin, sF, sMean, sm, smx, anc_s);
+        if (D <= 4) sys_unit<D>(c, k, a.plan_h[k], a.plan_h[k + 1], rel_begin, Fr, sMean, sm, smx, anc_s, xs, &stage_bar,
+                                phase, staged_k);
+        else sys_unit<D>(c, k, a.plan_h[k], a.plan_h[k + 1], rel_begin, sF, sMean, sm, smx, anc_s, xs, &stage_bar, phase,
+                         staged_k);
     }
 }
 
@@ -871,13 +908,19 @@ struct ObeBResampleArgs {
 };
 
 template <int D>
-__global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_bsys_resample(const ObeBResampleArgs a) {
+__global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 3 : 2)) k_bsys_resample(const ObeBResampleArgs a) {
     __shared__ double sF[D * D];
     __shared__ double sMean[D];
     __shared__ double sm[8];
     __shared__ int smx[OBE_THREADS / 32];
     __shared__ long long Hs[66];
     __shared__ __align__(16) unsigned short anc_s[OBE_OUT_CHUNK];
+    __shared__ unsigned long long stage_bar;
+    extern __shared__ __align__(128) unsigned char obe_dyn_smem[];
+    double* xs = reinterpret_cast<double*>(obe_dyn_smem);
+    if (threadIdx.x == 0) { obe_mbar_init(&stage_bar, 1); obe_mbar_fence_init(); }
+    unsigned int phase = 0u;
+    __syncthreads();
     const int tid = threadIdx.x;
     const int T = a.tiles;
     const int n_list = *a.n_list;
@@ -934,10 +977,11 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 4 : 2)) k_bsys_resample
                 for (int j = 0; j < D; ++j) sF[k * D + j] = L[j][k];
         }
         __syncthreads();
+        long long staged_k = -1;
         for (int t = 0; t < T; ++t) {
             const long long Hk = Hs[t], Hk1 = Hs[t + 1];
             for (int rel = 0; rel < (int)(Hk1 - Hk); rel += OBE_OUT_CHUNK)
-                sys_unit<D>(c, t, Hk, Hk1, rel, sF, sMean, sm, smx, anc_s);
+                sys_unit<D>(c, t, Hk, Hk1, rel, sF, sMean, sm, smx, anc_s, xs, &stage_bar, phase, staged_k);
         }
         __syncthreads();
         if (tid == 0) { a.cur[b] = 1 - cb; a.epoch[b] = c.epoch; }
@@ -1057,16 +1101,23 @@ __global__ void k_shard_plan(const double* __restrict__ gathered, int rank, int 
     if (n_out_dev) *n_out_dev = cnt;
 }
 
+// the resample kernels stage the tile's particle rows in dynamic shared memory when d <= OBE_STAGE_MAX_D
+#define OBE_DIM_CASE(dd, KERNEL, grid, st, args)                                                          \
+    case dd: {                                                                                            \
+        const size_t smem_ = (dd <= OBE_STAGE_MAX_D) ? (size_t)dd * OBE_TILE * sizeof(double) : 0;        \
+        cudaFuncSetAttribute(KERNEL<dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);         \
+        KERNEL<dd><<<grid, OBE_THREADS, smem_, st>>>(args);                                                \
+    } break;
 #define OBE_DIM_SWITCH(d, KERNEL, grid, st, args)                                     \
     switch (d) {                                                                      \
-        case 1: KERNEL<1><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
-        case 2: KERNEL<2><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
-        case 3: KERNEL<3><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
-        case 4: KERNEL<4><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
-        case 5: KERNEL<5><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
-        case 6: KERNEL<6><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
-        case 7: KERNEL<7><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
-        case 8: KERNEL<8><<<grid, OBE_THREADS, 0, st>>>(args); break;                 \
+        OBE_DIM_CASE(1, KERNEL, grid, st, args)                                       \
+        OBE_DIM_CASE(2, KERNEL, grid, st, args)                                       \
+        OBE_DIM_CASE(3, KERNEL, grid, st, args)                                       \
+        OBE_DIM_CASE(4, KERNEL, grid, st, args)                                       \
+        OBE_DIM_CASE(5, KERNEL, grid, st, args)                                       \
+        OBE_DIM_CASE(6, KERNEL, grid, st, args)                                       \
+        OBE_DIM_CASE(7, KERNEL, grid, st, args)                                       \
+        OBE_DIM_CASE(8, KERNEL, grid, st, args)                                       \
         default: return obe_fail("n_params must be 1..8%s%s");                        \
     }
 
