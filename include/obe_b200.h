@@ -45,7 +45,8 @@ enum {
     OBE_STAT_PIVOT = 48,  /* [8]                                                             */
     OBE_STAT_NOISE = 56,  /* [4]  sum t sigma_c^2                                            */
     OBE_STAT_SUMT = 60,   /* sum t from the same pass as the moments                         */
-    OBE_STAT_NZERO = 61   /* particles newly zeroed by the constraint mask                   */
+    OBE_STAT_NZERO = 61,  /* particles newly zeroed by the constraint mask                   */
+    OBE_STAT_UNIFORM = 62 /* > 0: weights are implicit, every live particle weighs this much */
 };
 
 /* The particle cloud resident in HBM (ParticlePDF state, particlepdf.py:96-126). */
@@ -122,6 +123,9 @@ int obe_refresh(const obe_cloud_t* c, uint32_t mask_le, uint32_t mask_lt, const 
                 int n_noise, const double* pivot, int renormalise, void* stream);
 /* Copy the stats block to host memory (synchronises the stream). */
 int obe_fetch_stats(const obe_cloud_t* c, double* stats_host, void* stream);
+/* After a systematic resample the weights are IMPLICIT (stats[62] = 1/n_total > 0 and weights_dev is
+ * not written: the next update never reads it).  Call this before touching weights_dev directly. */
+int obe_materialize_weights(const obe_cloud_t* c, void* stream);
 /* Normalised weights (t * INVS, nan_to_num) into out_dev (n). particle_weights getter. */
 int obe_normalized_weights(const obe_cloud_t* c, double* out_dev, void* stream);
 

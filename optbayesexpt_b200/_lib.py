@@ -71,6 +71,7 @@ SIGNATURES = {
     'obe_update_from_likelihood': (C.c_int, [_PCLOUD, _VP, _PD, _VP]),
     'obe_refresh': (C.c_int, [_PCLOUD, C.c_uint32, C.c_uint32, _PI32, C.c_int, _PD, C.c_int, _VP]),
     'obe_fetch_stats': (C.c_int, [_PCLOUD, _PD, _VP]),
+    'obe_materialize_weights': (C.c_int, [_PCLOUD, _VP]),
     'obe_normalized_weights': (C.c_int, [_PCLOUD, _VP, _VP]),
     'obe_cdf': (C.c_int, [_PCLOUD, _VP, _VP]),
     'obe_search': (C.c_int, [_PCLOUD, _VP, _VP, C.c_int64, _VP, _VP]),

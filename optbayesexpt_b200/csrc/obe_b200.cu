@@ -229,7 +229,8 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_tile_scan(const double* __
                                                                 long long n_tiles, double* __restrict__ prefix,
                                                                 double* __restrict__ stats, int renormalise,
                                                                 long long uniform, long long n,
-                                                                const long long* __restrict__ n_dev = nullptr) {
+                                                                const long long* __restrict__ n_dev = nullptr,
+                                                                int implicit = 0) {
     __shared__ double sm[34];
     const int t = threadIdx.x;
     if (n_dev) { n = *n_dev; n_tiles = (n + OBE_TILE - 1) / OBE_TILE; }
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_tile_scan(const double* __
                 stats[OBE_ST_SUMSQ] = (double)n * wv * wv;
                 stats[OBE_ST_SUMT] = (double)n * wv;
                 stats[OBE_ST_NEFF] = (double)uniform;
+                stats[OBE_ST_UNIFORM] = implicit ? wv : 0.0;
             } else {
                 stats[OBE_ST_INVS] = renormalise ? 1.0 / total : 1.0;
                 const double ssq = stats[OBE_ST_SUMSQ];
@@ -283,19 +285,21 @@ __global__ void k_fill_uniform(double* __restrict__ w, double* __restrict__ tile
 __global__ void k_normalized_weights(const double* __restrict__ w, const double* __restrict__ stats,
                                      double* __restrict__ out, long long n, const long long* __restrict__ n_dev) {
     if (n_dev) n = *n_dev;
-    const double inv = stats[OBE_ST_INVS];
+    const double inv = stats[OBE_ST_INVS], wuni = stats[OBE_ST_UNIFORM];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x)
-        out[i] = obe_nan_to_num(w[i] * inv);
+        out[i] = obe_nan_to_num((wuni > 0.0 ? wuni : w[i]) * inv);
 }
 
 __global__ void __launch_bounds__(OBE_THREADS) k_cdf(const double* __restrict__ w, const double* __restrict__ prefix,
-                                                     long long n, long long n_tiles, double* __restrict__ cdf) {
+                                                     long long n, long long n_tiles, double* __restrict__ cdf,
+                                                     const double* __restrict__ stats) {
     __shared__ double sm[8];
     const double inv_total = 1.0 / prefix[n_tiles];
+    const double wuni = stats ? stats[OBE_ST_UNIFORM] : 0.0;
     for (long long k = blockIdx.x; k < n_tiles; k += gridDim.x) {
         double cn[OBE_EPT];
-        tile_cdf_blocked(w, prefix, k, n, inv_total, cn, sm);
+        tile_cdf_blocked(w, prefix, k, n, inv_total, cn, sm, 0.0, true, wuni);
         const long long i0 = k * OBE_TILE + (long long)threadIdx.x * OBE_EPT;
 #pragma unroll
         for (int e = 0; e < OBE_EPT; ++e)
@@ -340,6 +344,7 @@ struct ObeDrawArgs {
     double* draws; long long* idx; int k;
     const long long* n_dev;     // optional live count
     const double* plan;         // optional shard plan: this rank draws only the uniforms it owns
+    const double* stats;        // optional: stats block (implicit uniform weights)
     int post;                   // use the post-resample shard totals of the plan
     double u[OBE_MAX_DRAWS];
 };
@@ -376,7 +381,7 @@ __global__ void __launch_bounds__(OBE_THREADS) k_draw(const ObeDrawArgs a) {
     const double inv_total = 1.0 / a.prefix[n_tiles];
     const long long k = find_tile(a.prefix, n_tiles, inv_total, uq);
     double cn[OBE_EPT];
-    tile_cdf_blocked(a.w, a.prefix, k, n, inv_total, cn, sm);
+    tile_cdf_blocked(a.w, a.prefix, k, n, inv_total, cn, sm, 0.0, true, a.stats ? a.stats[OBE_ST_UNIFORM] : 0.0);
     const long long base = k * OBE_TILE;
     int c = 0;
 #pragma unroll
@@ -474,6 +479,7 @@ struct ObeResampleArgs {
     const long long* n_dev_in;     // optional live count of the input shard
     const double* plan;            // optional device-resident shard plan (overrides the by-value shard fields)
     long long cap_out;             // capacity of the output buffers (planned mode)
+    int implicit_out;              // 1: do not write the offspring weights, leave them implicit
     double factor[OBE_MAX_DIMS * OBE_MAX_DIMS];
     double mean[OBE_MAX_DIMS];
 };
@@ -648,6 +654,7 @@ struct SysCtx {
     double a_param;
     long long* idx_out; double* z_out;
     unsigned int mask_le, mask_lt;                     // batched: constraint applied to the offspring
+    double wuni_in;                                    // > 0: the input weights are implicit (uniform)
 };
 
 // One work unit = (input tile k, chunk of <= 2048 consecutive output slots owned by that tile).
@@ -686,7 +693,7 @@ __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long
         *reinterpret_cast<uint4*>(&anc_s[tid * OBE_SPT + 8 * v]) = make_uint4(0u, 0u, 0u, 0u);
     // ---- 1. end slot of every particle of the tile
     double cn[OBE_EPT];
-    tile_cdf_blocked(c.w_in, c.prefix, k, c.n_in, c.inv_total, cn, sm, c.cdf_offset, c.last_shard);
+    tile_cdf_blocked(c.w_in, c.prefix, k, c.n_in, c.inv_total, cn, sm, c.cdf_offset, c.last_shard, c.wuni_in);
     const long long base = k * OBE_TILE;
     const long long last = min(c.n_in, base + OBE_TILE) - 1;
     int r[OBE_EPT];
@@ -819,7 +826,7 @@ __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long
         }
 #pragma unroll
         for (int j = 0; j < D; ++j) c.pout[j * c.ld_out + c.out_base + o] = xv[j];
-        c.w_out[c.out_base + o] = wo;
+        if (c.w_out) c.w_out[c.out_base + o] = wo;
         if (c.idx_out) c.idx_out[o] = base + rel;
     }
     __syncthreads();
@@ -857,6 +864,8 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 3 : 2)) k_sys_resample(
     c.cap_out = a.plan ? a.cap_out : (1ll << 62);
     c.seed = a.seed; c.epoch = a.epoch; c.jitter = a.jitter; c.scale = a.scale; c.a_param = a.a_param;
     c.idx_out = a.idx_out; c.z_out = a.z_out; c.mask_le = 0u; c.mask_lt = 0u;
+    c.wuni_in = a.stats[OBE_ST_UNIFORM];
+    if (a.implicit_out) c.w_out = nullptr;               // offspring weights stay implicit (1/n_total)
     // the Liu-West factor in registers when it is small enough
     double Fr[D <= 4 ? D * D : 1];
     if (D <= 4) {
@@ -939,6 +948,7 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 3 : 2)) k_bsys_resample
         c.slot_begin = 0; c.cap_out = a.np;
         c.seed = a.seed + (unsigned long long)b; c.epoch = a.epoch[b] + 1u; c.jitter = 1; c.scale = a.scale;
         c.a_param = a.a_param; c.idx_out = nullptr; c.z_out = nullptr; c.mask_le = a.mask_le; c.mask_lt = a.mask_lt;
+        c.wuni_in = 0.0;
         if (tid == 0) {
             // slot bounds of the instance's tiles (monotone), Liu-West factor from its own moments
             long long run = 0;
@@ -1545,11 +1555,33 @@ int obe_normalized_weights(const obe_cloud_t* c, double* out_dev, void* stream) 
     return 0;
 }
 
+__global__ void k_materialize(double* __restrict__ w, double* __restrict__ stats, long long n,
+                              const long long* __restrict__ n_dev) {
+    if (n_dev) n = *n_dev;
+    const double wuni = stats[OBE_ST_UNIFORM];
+    if (!(wuni > 0.0)) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        w[i] = wuni;
+}
+__global__ void k_clear_uniform(double* __restrict__ stats) { stats[OBE_ST_UNIFORM] = 0.0; }
+
+int obe_materialize_weights(const obe_cloud_t* c, void* stream) {
+    if (check_cloud(c)) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_materialize<<<obe_sms() * 8, 256, 0, st>>>(c->weights_dev, c->stats_dev, c->n, (const long long*)c->n_dev);
+    OBE_LAUNCH_CHECK("k_materialize");
+    k_clear_uniform<<<1, 1, 0, st>>>(c->stats_dev);
+    OBE_LAUNCH_CHECK("k_clear_uniform");
+    return 0;
+}
+
 int obe_cdf(const obe_cloud_t* c, double* cdf_dev, void* stream) {
     if (check_cloud(c)) return -1;
     const int64_t nt = obe_num_tiles(c->n);
     int grid = (int)(nt < (int64_t)obe_sms() * 8 ? nt : (int64_t)obe_sms() * 8);
-    k_cdf<<<grid, OBE_THREADS, 0, (cudaStream_t)stream>>>(c->weights_dev, c->tile_prefix_dev, c->n, nt, cdf_dev);
+    k_cdf<<<grid, OBE_THREADS, 0, (cudaStream_t)stream>>>(c->weights_dev, c->tile_prefix_dev, c->n, nt, cdf_dev,
+                                                          c->stats_dev);
     OBE_LAUNCH_CHECK("k_cdf");
     return 0;
 }
@@ -1568,7 +1600,8 @@ int obe_search(const obe_cloud_t* c, const double* cdf_dev, const double* u_dev,
 
 static int draw_impl(const double* w, const double* prefix, int64_t n, const double* particles, int64_t ld, int d,
                      const double* u_host, int k, double* draws_dev, int64_t* idx_dev, cudaStream_t st,
-                     int ld_draws = 0, const long long* n_dev = nullptr, const double* plan = nullptr, int post = 0) {
+                     int ld_draws = 0, const long long* n_dev = nullptr, const double* plan = nullptr, int post = 0,
+                     const double* stats = nullptr) {
     if (k <= 0) return 0;
     for (int off = 0; off < k; off += OBE_MAX_DRAWS) {
         const int kk = (k - off) < OBE_MAX_DRAWS ? (k - off) : OBE_MAX_DRAWS;
@@ -1578,7 +1611,7 @@ static int draw_impl(const double* w, const double* prefix, int64_t n, const dou
         a.draws = draws_dev ? draws_dev + off : nullptr;
         a.idx = idx_dev ? (long long*)idx_dev + off : nullptr;
         a.k = ld_draws > 0 ? ld_draws : k;
-        a.n_dev = n_dev; a.plan = plan; a.post = post;
+        a.n_dev = n_dev; a.plan = plan; a.post = post; a.stats = stats;
         for (int i = 0; i < kk; ++i) a.u[i] = u_host[off + i];
         k_draw<<<kk, OBE_THREADS, 0, st>>>(a);
         OBE_LAUNCH_CHECK("k_draw");
@@ -1590,7 +1623,7 @@ int obe_draw(const obe_cloud_t* c, const double* u_host, int k, double* draws_de
     if (check_cloud(c)) return -1;
     if (!u_host || !draws_dev) return obe_fail("null argument%s%s");
     return draw_impl(c->weights_dev, c->tile_prefix_dev, c->n, c->particles_dev, c->ld, c->d, u_host, k, draws_dev,
-                     idx_dev, (cudaStream_t)stream, 0, (const long long*)c->n_dev);
+                     idx_dev, (cudaStream_t)stream, 0, (const long long*)c->n_dev, nullptr, 0, c->stats_dev);
 }
 
 int obe_draw_planned(const obe_cloud_t* c, const double* u_host, int k, double* draws_dev, const double* plan_dev,
@@ -1598,15 +1631,15 @@ int obe_draw_planned(const obe_cloud_t* c, const double* u_host, int k, double* 
     if (check_cloud(c)) return -1;
     if (!u_host || !draws_dev || !plan_dev) return obe_fail("null argument%s%s");
     return draw_impl(c->weights_dev, c->tile_prefix_dev, c->n, c->particles_dev, c->ld, c->d, u_host, k, draws_dev,
-                     nullptr, (cudaStream_t)stream, 0, (const long long*)c->n_dev, plan_dev, post);
+                     nullptr, (cudaStream_t)stream, 0, (const long long*)c->n_dev, plan_dev, post, c->stats_dev);
 }
 
-static int finish_resample(const obe_cloud_t* out, int64_t n_total, cudaStream_t st) {
+static int finish_resample(const obe_cloud_t* out, int64_t n_total, cudaStream_t st, int implicit = 0) {
     k_fill_uniform<<<obe_sms() * 2, 256, 0, st>>>(out->weights_dev, out->tile_sums_dev, out->n, obe_num_tiles(out->n), 0,
                                                  n_total, (const long long*)out->n_dev);
     OBE_LAUNCH_CHECK("k_fill_uniform");
     k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(out->tile_sums_dev, obe_num_tiles(out->n), out->tile_prefix_dev,
-                                               out->stats_dev, 0, n_total, out->n, (const long long*)out->n_dev);
+                                               out->stats_dev, 0, n_total, out->n, (const long long*)out->n_dev, implicit);
     OBE_LAUNCH_CHECK("k_tile_scan");
     return 0;
 }
@@ -1640,7 +1673,7 @@ int obe_draw_strided(const obe_cloud_t* c, const double* u_host, int m, double* 
     if (m == 0) return 0;
     if (!u_host || !draws_dev || ld_draws < m) return obe_fail("bad argument%s%s");
     return draw_impl(c->weights_dev, c->tile_prefix_dev, c->n, c->particles_dev, c->ld, c->d, u_host, m, draws_dev,
-                     idx_dev, (cudaStream_t)stream, ld_draws);
+                     idx_dev, (cudaStream_t)stream, ld_draws, (const long long*)c->n_dev, nullptr, 0, c->stats_dev);
 }
 
 int obe_gather_jitter(const obe_cloud_t* in, const obe_cloud_t* out, const int64_t* idx_dev, const double* factor,
@@ -1673,7 +1706,7 @@ static int resample_systematic_impl(const obe_cloud_t* in, const obe_cloud_t* ou
     if (sharded && !factor) return obe_fail("sharded resample needs the (global) factor from the host%s%s");
     const Scratch s = scratch_of(in);
     a.plan_h = s.plan_h; a.unit_start = s.unit_start; a.u0 = u0;
-    a.idx_out = (long long*)idx_out_dev; a.z_out = z_out_dev;
+    a.idx_out = (long long*)idx_out_dev; a.z_out = z_out_dev; a.implicit_out = 1;
     a.sharded = sharded; a.last_shard = last_shard; a.n_total = n_total;
     a.slot_begin = slot_begin; a.slot_end = slot_end; a.cdf_offset = cdf_offset; a.cdf_total = cdf_total;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1686,7 +1719,7 @@ static int resample_systematic_impl(const obe_cloud_t* in, const obe_cloud_t* ou
     const int grid = (int)g;
     OBE_DIM_SWITCH(in->d, k_sys_resample, grid, st, a)
     OBE_LAUNCH_CHECK("k_sys_resample");
-    return finish_resample(out, n_total, st);
+    return finish_resample(out, n_total, st, 1);
 }
 
 int obe_resample_systematic(const obe_cloud_t* in, const obe_cloud_t* out, double u0, const double* factor,
@@ -1732,7 +1765,7 @@ int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* ou
     const Scratch s = scratch_of(in);
     a.plan_h = s.plan_h; a.unit_start = s.unit_start;
     a.plan = plan_dev; a.n_dev_in = (const long long*)in->n_dev; a.cap_out = out->ld;
-    a.sharded = 1; a.n_total = n_total;
+    a.sharded = 1; a.n_total = n_total; a.implicit_out = 1;
     cudaStream_t st = (cudaStream_t)stream;
     k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0, s.plan_h,
                                               s.unit_start, (const long long*)in->n_dev, plan_dev);
@@ -1743,7 +1776,7 @@ int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* ou
     const int grid = (int)g;
     OBE_DIM_SWITCH(in->d, k_sys_resample, grid, st, a)
     OBE_LAUNCH_CHECK("k_sys_resample");
-    return finish_resample(out, n_total, st);
+    return finish_resample(out, n_total, st, 1);
 }
 
 int64_t obe_comb_count(double c, double u0, int64_t n_total) {

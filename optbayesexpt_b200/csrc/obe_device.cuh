@@ -44,6 +44,9 @@
 #define OBE_ST_NOISE 56  /* [4]  sum t sigma_c^2 (noise-parameter channels) */
 #define OBE_ST_SUMT 60   /* plain (non-canonical) sum of t from the same pass */
 #define OBE_ST_NZERO 61  /* number of particles zeroed by the constraint mask */
+#define OBE_ST_UNIFORM 62 /* > 0: the weights are IMPLICIT, every live particle weighs this much (set by a
+                            systematic resample, which then never writes the weight row; cleared by the
+                            next update, which never reads it) */
 #define OBE_STATS_LEN 64
 #define OBE_NACC_MAX (2 + OBE_MAX_DIMS + 36 + OBE_MAX_CH + 1)
 
@@ -462,8 +465,11 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
     const int warp = tid >> 5, lane = tid & 31;
     const long long n = a.n_dev ? *a.n_dev : a.n;
     const long long n_tiles = (n + OBE_TILE - 1) / OBE_TILE;
+    // implicit uniform weights (left by a systematic resample): the weight row is neither copied nor read
+    const double wuni = a.stats[OBE_ST_UNIFORM];
+    const bool implicit = wuni > 0.0;
     // rows actually staged: weights, D particle rows, then the optional extras
-    const int n_rows_live = 1 + D + (SRC == OBE_SRC_Y ? a.n_lik_channels : 0) + (SRC == OBE_SRC_LIK ? 1 : 0);
+    const int n_rows_live = (implicit ? 0 : 1) + D + (SRC == OBE_SRC_Y ? a.n_lik_channels : 0) + (SRC == OBE_SRC_LIK ? 1 : 0);
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) {
@@ -495,7 +501,7 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
         const unsigned row_bytes = (unsigned)cnt * 8u;
         obe_mbar_expect_tx(full_bar + s, row_bytes * (unsigned)n_rows_live);
         double* dst = stage_base + (size_t)s * (NROWS * SE);
-        obe_bulk_g2s(dst, a.weights + base, row_bytes, full_bar + s);
+        if (!implicit) obe_bulk_g2s(dst, a.weights + base, row_bytes, full_bar + s);
 #pragma unroll
         for (int j = 0; j < D; ++j)
             obe_bulk_g2s(dst + (1 + j) * SE, a.particles + j * a.ld + base, row_bytes, full_bar + s);
@@ -542,7 +548,8 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
 #pragma unroll
                 for (int q = 0; q < EPT / 2; ++q) {
                     const int e = 2 * (ct + q * OBE_CONSUMER_THREADS);
-                    const double2 w2 = *reinterpret_cast<const double2*>(src + e);
+                    double2 w2 = make_double2(wuni, wuni);
+                    if (!implicit) w2 = *reinterpret_cast<const double2*>(src + e);
                     wv[2 * q] = w2.x; wv[2 * q + 1] = w2.y;
 #pragma unroll
                     for (int j = 0; j < D; ++j) {
@@ -563,7 +570,7 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
                     }
                 }
             } else {
-                wv[0] = src[ct];
+                wv[0] = implicit ? wuni : src[ct];
 #pragma unroll
                 for (int j = 0; j < D; ++j) pv[j][0] = src[(1 + j) * SE + ct];
                 if (SRC == OBE_SRC_Y) {
@@ -655,6 +662,7 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
         for (int j = 0; j < D; ++j) { a.stats[OBE_ST_M1 + j] = fin[3 + j]; a.stats[OBE_ST_PIVOT + j] = a.pivot[j]; }
         for (int j = 0; j < NM2; ++j) a.stats[OBE_ST_M2 + j] = fin[3 + D + j];   // packed j<=k over D dims
         for (int c = 0; c < OBE_MAX_CH; ++c) a.stats[OBE_ST_NOISE + c] = fin[3 + D + NM2 + c];
+        if (a.write_weights) a.stats[OBE_ST_UNIFORM] = 0.0;      // the weight row is explicit again
         *a.counter = 0u;
     }
 }
@@ -903,8 +911,13 @@ __device__ __forceinline__ long long obe_min_ll(long long a, long long b) { retu
 // numpy reproduces bit for bit as cdf_unnormalised * (1.0 / total).)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tile_load_blocked(const double* __restrict__ w, long long base, long long n,
-                                                  double (&v)[OBE_EPT]) {
+                                                  double (&v)[OBE_EPT], double wuni = 0.0) {
     const long long i0 = base + (long long)threadIdx.x * OBE_EPT;
+    if (wuni > 0.0) {                      // implicit uniform weights: same values an explicit row would hold
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; ++e) v[e] = (i0 + e < n) ? wuni : 0.0;
+        return;
+    }
     if (i0 + OBE_EPT <= n) {
 #pragma unroll
         for (int e = 0; e < OBE_EPT; e += 2) {
@@ -947,10 +960,10 @@ __device__ __forceinline__ void tile_scan_blocked(const double (&v)[OBE_EPT], do
 __device__ __forceinline__ void tile_cdf_blocked(const double* __restrict__ w, const double* __restrict__ prefix,
                                                  long long k, long long n, double inv_total,
                                                  double (&cn)[OBE_EPT], double* sm, double offset = 0.0,
-                                                 bool last_shard = true) {
+                                                 bool last_shard = true, double wuni = 0.0) {
     double v[OBE_EPT], incl[OBE_EPT];
     const long long base = k * OBE_TILE;
-    tile_load_blocked(w, base, n, v);
+    tile_load_blocked(w, base, n, v, wuni);
     tile_scan_blocked(v, incl, sm);
     const double p0 = obe_add(offset, prefix[k]);
     const long long last = obe_min_ll(n, base + OBE_TILE) - 1;

@@ -180,6 +180,7 @@ class ParticlePDF:
         if value.shape[0] != self.n_particles:
             raise ValueError('Length of weights does not match the number of particles.')
         self._buf.weights[:self.n_particles].copy_(self._torch.from_numpy(np.ascontiguousarray(value)))
+        self._buf.stats[62:63].zero_()          # OBE_ST_UNIFORM: the weight row is explicit
         self._host_weights = None
         self._stats = None
         self._moments_valid = False
@@ -193,7 +194,9 @@ class ParticlePDF:
 
     @property
     def weights_dev(self):
-        """torch view of the UN-normalised device weights; multiply by ``weight_scale``."""
+        """torch view of the UN-normalised device weights; multiply by ``weight_scale``.  (After a
+        systematic resample the weights are implicit on the device; this materialises them.)"""
+        self._check(self._lib.obe_materialize_weights(self._cs(), self._stream()))
         return self._buf.weights[:self.n_particles]
 
     @property

@@ -397,6 +397,10 @@ def test_systematic_resample_matches_oracle(obe, torch, n, scale):
     spread = prior.std(axis=1, keepdims=True)
     err = np.abs(got - want) / (np.abs(want) * 1e-13 + spread * 1e-11)
     assert err.max() <= 1.0, err.max()
+    # the offspring weights are implicit (never written) until something asks for the row
+    assert float(alt.stats[62].item()) == 1.0 / n
+    _lib.check(lib.obe_materialize_weights(C.byref(alt.struct()), pdf._stream()))
+    assert float(alt.stats[62].item()) == 0.0
     assert_array_equal(alt.weights[:n].cpu().numpy(), np.full(n, 1.0 / n))
 
 
