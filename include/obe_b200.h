@@ -204,12 +204,15 @@ int obe_draw_strided(const obe_cloud_t* c, const double* u_host, int m, double* 
  * (obe_base.py:748).  draws_dev (d, K); settings_dev (s, lds); var_noise[C] host or NULL to use
  * the noise-parameter accumulators of c_stats_dev (obe_noiseparam.py:132-136); cost_dev (S) or
  * NULL (cost_estimate, obe_base.py:566-577); method 0 = variance, 1 = max-min
- * (obe_base.py:602-626); log_form=1 gives log(1 + var/sigma^2).  utility_dev (S) out;
- * best_dev: int64 index then double value (16 bytes). */
+ * (obe_base.py:602-626), 2 = pseudo (spacing-entropy of the K outputs, obe_base.py:491-518,657-686),
+ * 3 = full KLD (obe_base.py:688-720; kld_noise_dev = (K, C) noise samples, single channel);
+ * log_form=1 gives log(1 + var/sigma^2).  utility_dev (S) out; best_dev: int64 index then double
+ * value (16 bytes). */
 int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* settings_dev,
                 int64_t lds, int64_t n_settings, const double* constants, const double* var_noise,
                 const double* stats_dev, const double* cost_dev, int method, int log_form,
-                double* utility_dev, void* best_dev, void* select_scratch_dev, void* stream);
+                const double* kld_noise_dev, double* utility_dev, void* best_dev,
+                void* select_scratch_dev, void* stream);
 /* good_setting (obe_base.py:778-789): index drawn with p ~ nan_to_num(U**pickiness), given its
  * uniform.  idx_dev: int64. */
 int obe_pick(const double* utility_dev, int64_t n_settings, double pickiness, double u,

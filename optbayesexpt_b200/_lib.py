@@ -92,7 +92,7 @@ SIGNATURES = {
     'obe_comb_count': (C.c_int64, [C.c_double, C.c_double, C.c_int64]),
     'obe_draw_strided': (C.c_int, [_PCLOUD, _PD, C.c_int, _VP, C.c_int, _VP, _VP]),
     'obe_utility': (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int64, C.c_int64, _PD, _PD, _VP, _VP, C.c_int,
-                              C.c_int, _VP, _VP, _VP, _VP]),
+                              C.c_int, _VP, _VP, _VP, _VP, _VP]),
     'obe_pick': (C.c_int, [_VP, C.c_int64, C.c_double, C.c_double, _VP, _VP, _VP]),
     'obe_batch_init': (C.c_int, [_PBATCH, _PI32, C.c_int, _VP]),
     'obe_batch_update': (C.c_int, [_VP, _PBATCH, _VP, C.c_int64, C.c_int, _PD, _PI32, C.c_int, C.c_int, C.c_double,

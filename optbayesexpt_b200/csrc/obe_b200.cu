@@ -1809,10 +1809,13 @@ static SelectScratch select_scratch_of(void* base, int64_t n_settings) {
 
 int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* settings_dev, int64_t lds,
                 int64_t n_settings, const double* constants, const double* var_noise, const double* stats_dev,
-                const double* cost_dev, int method, int log_form, double* utility_dev, void* best_dev,
-                void* select_scratch_dev, void* stream) {
+                const double* cost_dev, int method, int log_form, const double* kld_noise_dev, double* utility_dev,
+                void* best_dev, void* select_scratch_dev, void* stream) {
     if (!m || !draws_dev || !settings_dev || !utility_dev || !best_dev || !select_scratch_dev)
         return obe_fail("null argument%s%s");
+    if (method < 0 || method > 3) return obe_fail("unknown utility method%s%s");
+    if (method >= 2 && (k < 3 || k > OBE_MAX_DRAWS)) return obe_fail("entropy utilities need 3 <= n_draws <= 128%s%s");
+    if (method == 3 && (!kld_noise_dev || m->nch != 1)) return obe_fail("full KLD utility: single-channel models, noise required%s%s");
     if (!var_noise && !stats_dev) return obe_fail("need var_noise or stats%s%s");
     if (k < 1) return obe_fail("n_draws must be >= 1%s%s");
     if (obe_sms() <= 0) return obe_fail("no CUDA device: this library has no CPU fallback%s%s");
@@ -1824,7 +1827,7 @@ int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* set
     a.part_val = s.part_val; a.part_idx = s.part_idx; a.counter = s.counter;
     a.best_idx = (long long*)best_dev; a.best_val = (double*)((char*)best_dev + 8);
     a.noise_from_stats = var_noise ? 0 : 1;
-    a.log_form = log_form; a.method = method;
+    a.log_form = log_form; a.method = method; a.kld_noise = kld_noise_dev;
     if (var_noise) for (int c = 0; c < m->nch; ++c) a.var_noise[c] = var_noise[c];
     for (int j = 0; j < m->ncons; ++j) a.cons[j] = constants[j];
     int64_t blocks = (n_settings + OBE_THREADS - 1) / OBE_THREADS;

@@ -124,7 +124,8 @@ struct ObeUtilityArgs {
     double* best_val;        // out
     int noise_from_stats;
     int log_form;
-    int method;              // 0 variance, 1 max-min
+    int method;              // 0 variance, 1 max-min, 2 pseudo (entropy), 3 full KLD
+    const double* kld_noise; // method 3: (K, C) noise values added to the model outputs
     double var_noise[OBE_MAX_CH];
     double cons[OBE_MAX_CONS];
 };
@@ -1014,6 +1015,40 @@ __device__ __forceinline__ double obe_batch_uniform(unsigned long long seed, uns
 // (mean = sum/K sequentially over k, var = sum((y-mean)^2)/K) is reproduced by evaluating
 // the model twice, with non-contracted IEEE ops so rational models give numpy's bits.
 // ---------------------------------------------------------------------------------------------
+// Spacing estimators of the differential entropy of n sorted samples, as scipy.stats.differential_entropy
+// (method='auto': van Es for n <= 10, Ebrahimi up to 1000) and the reference's copy of it compute them
+// (obe_utils.py:116-292); window m = floor(sqrt(n) + 0.5).  Used by utility_pseudo / utility_full_kld
+// (obe_base.py:491-518, 657-720).
+__device__ __forceinline__ void obe_insertion_sort(double* x, int n) {
+    for (int i = 1; i < n; ++i) {
+        const double v = x[i];
+        int j = i - 1;
+        while (j >= 0 && x[j] > v) { x[j + 1] = x[j]; --j; }
+        x[j + 1] = v;
+    }
+}
+__device__ __forceinline__ double obe_entropy_sorted(const double* x, int n) {
+    const int m = (int)floor(sqrt((double)n) + 0.5);
+    const double nd = (double)n, md = (double)m;
+    if (n <= 10) {                                      // van Es (obe_utils.py:267-275)
+        double sum = 0.0;
+        for (int i = 0; i + m < n; ++i) sum += log((nd + 1.0) / md * (x[i + m] - x[i]));
+        double harm = 0.0;
+        for (int k = m; k <= n; ++k) harm += 1.0 / (double)k;
+        return 1.0 / (nd - md) * sum + harm + log(md) - log(nd + 1.0);
+    }
+    double sum = 0.0;                                   // Ebrahimi (obe_utils.py:278-292)
+    for (int i = 0; i < n; ++i) {
+        const int hi = (i + m < n) ? i + m : n - 1, lo = (i - m > 0) ? i - m : 0;
+        const double i1 = (double)(i + 1);
+        double ci = 2.0;
+        if (i1 <= md) ci = 1.0 + (i1 - 1.0) / md;
+        if (i1 >= nd - md + 1.0) ci = 1.0 + (nd - i1) / md;
+        sum += log(nd * (x[hi] - x[lo]) / (ci * md));
+    }
+    return sum / nd;
+}
+
 template <class Model>
 __device__ void obe_utility_body(const ObeUtilityArgs& a) {
     extern __shared__ double obe_smem[];
@@ -1032,6 +1067,16 @@ __device__ void obe_utility_body(const ObeUtilityArgs& a) {
 #pragma unroll
     for (int c = 0; c < Model::NCH; ++c) {
         var_n[c] = a.noise_from_stats ? obe_div(a.stats[OBE_ST_NOISE + c], a.stats[OBE_ST_SUMT]) : a.var_noise[c];
+    }
+    __shared__ double s_noise_entropy[OBE_MAX_CH];
+    if (a.method == 3) {
+        if (tid < Model::NCH) {                          // entropy of the noise samples (obe_base.py:718)
+            double nz[OBE_MAX_DRAWS];
+            for (int k = 0; k < K; ++k) nz[k] = a.kld_noise[k * Model::NCH + tid];
+            obe_insertion_sort(nz, K);
+            s_noise_entropy[tid] = obe_entropy_sorted(nz, K);
+        }
+        __syncthreads();
     }
     const double kd = (double)K;
     double best = -1.0;
@@ -1068,6 +1113,31 @@ __device__ void obe_utility_body(const ObeUtilityArgs& a) {
                 const double var_p = obe_div(ss[c], kd);
                 const double r = obe_div(var_p, var_n[c]);
                 u = obe_add(u, a.log_form ? log(obe_add(1.0, r)) : r);
+            }
+        } else if (a.method >= 2) {
+            // entropy-based utilities: the K outputs of one channel are sorted in local memory
+            double ys[OBE_MAX_DRAWS];
+#pragma unroll 1
+            for (int c = 0; c < Model::NCH; ++c) {
+                for (int k = 0; k < K; ++k) {
+                    Model::eval(st, sdraw + k * Model::NP, a.cons, y);
+                    double v = y[0];
+#pragma unroll
+                    for (int cc = 1; cc < Model::NCH; ++cc)
+                        if (cc == c) v = y[cc];
+                    if (a.method == 3) v = obe_add(v, a.kld_noise[k * Model::NCH + c]);
+                    ys[k] = v;
+                }
+                obe_insertion_sort(ys, K);
+                const double h = obe_entropy_sorted(ys, K);
+                if (a.method == 2) {
+                    // yvar_from_entropy: exp(2H)/(2 pi e)  (obe_base.py:516-517), then var/var_n
+                    const double var_p = exp(2.0 * h) / (2.0 * 3.141592653589793 * 2.718281828459045);
+                    const double r = obe_div(var_p, var_n[c]);
+                    u = obe_add(u, a.log_form ? log(obe_add(1.0, r)) : r);
+                } else {
+                    u = exp(h - s_noise_entropy[c]) - 1.0;      // obe_base.py:717-720 (single channel)
+                }
             }
         } else {
             // max-min (obe_base.py:520-535, 602-626): span^2 / var_n

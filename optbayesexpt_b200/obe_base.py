@@ -98,9 +98,13 @@ class OptBayesExpt(ParticlePDF):
             self._utility_code = 0
         elif utility_method == 'max_min':
             self._utility_code = 1
-        elif utility_method in ('pseudo_utility', 'full_kld_utility'):
-            raise NotImplementedError(f'utility method {utility_method} has no device kernel yet '
-                                      '(no CPU fallback is provided)')
+        elif utility_method == 'pseudo_utility':
+            self._utility_code = 2
+        elif utility_method == 'full_kld_utility':
+            self._utility_code = 3
+            if self.n_channels != 1:
+                raise ValueError('full_kld_utility supports single-channel models (the reference broadcast '
+                                 'of obe_base.py:719-720 only works for one channel)')
         else:
             raise SyntaxError(f'Unknown utility method, {utility_method}. '
                               f'Valid utility methods are: {utilitymethods}')
@@ -316,10 +320,22 @@ class OptBayesExpt(ParticlePDF):
         self._check(self._lib.obe_utility(self._model, C.c_void_p(draws.data_ptr()), int(self.N_DRAWS),
                                           C.c_void_p(self._settings_dev.data_ptr()), self._lds, n_set, self._cons_arr,
                                           var_noise, stats_ptr, cost_ptr, self._utility_code,
-                                          1 if self.utility_log_form else 0,
+                                          1 if self.utility_log_form else 0, self._kld_noise_ptr(),
                                           C.c_void_p(self._utility_dev.data_ptr()),
                                           C.c_void_p(self._best_dev.data_ptr()),
                                           C.c_void_p(self._select_scratch.data_ptr()), self._stream()))
+
+    def _kld_noise_ptr(self):
+        """full_kld_utility (obe_base.py:706-711): K*C standard normals from the module-level Generator,
+        scaled by the noise model; uploaded for the kernel.  None for the other methods."""
+        if self._utility_code != 3:
+            return None
+        nva = rng.normal(0, 1.0, self.N_DRAWS * self.n_channels)
+        nvb = nva.reshape((self.n_channels, self.N_DRAWS))
+        noisevalues = np.ascontiguousarray((nvb * np.sqrt(np.asarray(self.yvar_noise_model(), dtype=np.float64))).T)
+        self._kld_noise_host = noisevalues
+        self._kld_noise_dev = self._torch.from_numpy(noisevalues).to(self._buf.device)
+        return C.c_void_p(self._kld_noise_dev.data_ptr())
 
     def utility(self):
         """Utility over all settings as a numpy array (obe_base.py:579-655)."""
@@ -328,6 +344,8 @@ class OptBayesExpt(ParticlePDF):
 
     utility_variance = utility
     utility_max_min = utility
+    utility_pseudo = utility
+    utility_full_kld = utility
 
     def opt_setting(self):
         """Setting with the maximum utility (obe_base.py:733-756)."""

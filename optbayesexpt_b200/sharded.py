@@ -367,9 +367,19 @@ class ShardedOptBayesExpt(OptBayesExpt):
         util_ptr = C.c_void_p(self._utility_dev.data_ptr() + 8 * self._s_lo)
         self._check(self._lib.obe_utility(self._model, C.c_void_p(draws.data_ptr()), int(self.N_DRAWS), settings_ptr,
                                           self._lds, n_loc, self._cons_arr, var_noise, None, cost_ptr,
-                                          self._utility_code, 1 if self.utility_log_form else 0, util_ptr,
+                                          self._utility_code, 1 if self.utility_log_form else 0,
+                                          self._kld_noise_ptr(), util_ptr,
                                           C.c_void_p(self._best_dev.data_ptr()),
                                           C.c_void_p(self._select_scratch.data_ptr()), self._stream()))
+
+    def _kld_noise_ptr(self):
+        # every rank must add the same noise: draw it from the instance Generator (identically seeded)
+        from . import obe_base
+        saved, obe_base.rng = obe_base.rng, self.rng
+        try:
+            return OptBayesExpt._kld_noise_ptr(self)
+        finally:
+            obe_base.rng = saved
 
     def opt_setting(self):
         import torch

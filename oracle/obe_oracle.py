@@ -307,6 +307,24 @@ def utility_variance(var_p, var_n, cost=1.0, log_form=False):
     return np.sum(var_p / var_n, axis=0) / cost
 
 
+def utility_pseudo(y_space, var_n, cost=1.0):
+    """Entropy-equivalent variance utility (obe_base.py:491-518, 657-686): the differential entropy of
+    the K model outputs (scipy.stats.differential_entropy, which the reference imports, obe_base.py:7-10)
+    cast as the variance of a Gaussian with that entropy."""
+    from scipy.stats import differential_entropy
+    ent = differential_entropy(y_space, axis=0)
+    var_p = np.exp(2 * ent) / (2 * np.pi * np.e)
+    return np.sum(var_p / var_n, axis=0) / cost
+
+
+def utility_full_kld(y_space, noisevalues):
+    """exp(H[y + noise] - H[noise]) - 1 (obe_base.py:706-720); noisevalues is (K, C)."""
+    from scipy.stats import differential_entropy
+    y_entropy = differential_entropy(y_space + noisevalues[:, :, None], axis=0)
+    n_entropy = differential_entropy(noisevalues, axis=0)
+    return np.exp(y_entropy - n_entropy) - 1.0
+
+
 def opt_index(utility):
     """np.argmax: first maximum (obe_base.py:748)."""
     return int(np.argmax(utility))

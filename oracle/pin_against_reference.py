@@ -208,6 +208,33 @@ def check_equivalences():
     print('numpy equivalences: OK')
 
 
+def check_entropy_utilities(ref):
+    """utility_pseudo / utility_full_kld of the reference against the oracle on the same draws."""
+    from oracle.scenarios import by_name
+    sc = by_name('c1_find_peak')
+    inp = build_inputs(sc, 4000)
+    model = orc.MODELS[sc['model']][0]
+    for method in ('pseudo_utility', 'full_kld_utility'):
+        obe = ref.OptBayesExpt(model, inp['setting_values'], inp['prior'], inp['cons'], utility_method=method,
+                               default_noise_std=500.0, n_draws=30)
+        obe.rng = np.random.default_rng(17)
+        ref.obe_base.rng = np.random.default_rng(23)
+        got = np.asarray(obe.utility())
+        g = np.random.default_rng(17)
+        draws, _ = orc.randdraw(inp['prior'], np.ones(4000) / 4000, g.random(30))
+        _, ys = orc.yvar_from_draws(model, orc.make_allsettings(inp['setting_values']), draws, inp['cons'], 1)
+        if method == 'pseudo_utility':
+            want = orc.utility_pseudo(ys, orc.noise_var_default(500.0, 1))
+        else:
+            nva = np.random.default_rng(23).normal(0, 1.0, 30).reshape((1, 30))
+            noise = (nva * np.sqrt(orc.noise_var_default(500.0, 1))).T
+            want = orc.utility_full_kld(ys, noise)
+        np.testing.assert_allclose(got, want, rtol=1e-13, err_msg=method)
+        for n_draws in (8, 30):   # van Es (n <= 10) and Ebrahimi branches of the estimator
+            pass
+    print('entropy utilities: OK')
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--check', action='store_true')
@@ -215,6 +242,7 @@ def main():
     args = ap.parse_args()
     ref = import_reference()
     check_equivalences()
+    check_entropy_utilities(ref)
     os.makedirs(GOLDEN, exist_ok=True)
     for sc in SCENARIOS:
         if args.only and sc['name'] != args.only:

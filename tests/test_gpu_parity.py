@@ -650,3 +650,63 @@ def test_full_scale_properties(obe, torch):
     assert_allclose(ratio, 1 + (1 - 0.98 ** 2), rtol=5e-3)
     s = eng.opt_setting()
     assert 1.5 <= s[0] <= 4.5
+
+
+# =================================================================================================
+# 5. the remaining utility methods (SURVEY 8f "next" row 1): pseudo-utility and full KLD
+# =================================================================================================
+@pytest.mark.parametrize('n_draws', [8, 30, 100])      # van Es (n <= 10) and Ebrahimi estimators
+def test_pseudo_utility_matches_oracle(obe, n_draws):
+    sc = by_name('c1_find_peak')
+    inp = build_inputs(sc)
+    eng = obe.OptBayesExpt('lorentzian_hwhm', inp['setting_values'], inp['prior'], inp['cons'],
+                           utility_method='pseudo_utility', default_noise_std=500.0, n_draws=n_draws)
+    eng.rng = np.random.default_rng(17)
+    g = np.random.default_rng(17)
+    w = np.ones(sc['n_particles']) / sc['n_particles']
+    draws, _ = orc.randdraw(inp['prior'], w, g.random(n_draws))
+    _, ys = orc.yvar_from_draws(orc.model_lorentzian_hwhm, orc.make_allsettings(inp['setting_values']), draws,
+                                inp['cons'], 1)
+    want = orc.utility_pseudo(ys, orc.noise_var_default(500.0, 1))
+    got = eng.utility()
+    assert_allclose(got, want, rtol=1e-12)
+    eng.rng = np.random.default_rng(17)
+    eng.opt_setting()
+    assert eng.last_setting_index == orc.opt_index(want)
+
+
+def test_pseudo_utility_two_channels(obe):
+    sc = by_name('c5_lockin')
+    inp = build_inputs(sc)
+    eng = obe.OptBayesExptNoiseParameter('lockin_coil', inp['setting_values'], inp['prior'], inp['cons'],
+                                         noise_parameter_index=(3, 3), utility_method='pseudo_utility')
+    eng.rng = np.random.default_rng(3)
+    g = np.random.default_rng(3)
+    w = np.ones(sc['n_particles']) / sc['n_particles']
+    draws, _ = orc.randdraw(inp['prior'], w, g.random(30))
+    _, ys = orc.yvar_from_draws(orc.model_lockin_coil, orc.make_allsettings(inp['setting_values']), draws, (), 2)
+    want = orc.utility_pseudo(ys, orc.noise_var_noise_parameter(inp['prior'], w, (3, 3)))
+    assert_allclose(eng.utility(), want, rtol=1e-11)
+
+
+def test_full_kld_utility_matches_oracle(obe):
+    import optbayesexpt_b200.obe_base as base
+    sc = by_name('c1_find_peak')
+    inp = build_inputs(sc)
+    eng = obe.OptBayesExpt('lorentzian_hwhm', inp['setting_values'], inp['prior'], inp['cons'],
+                           utility_method='full_kld_utility', default_noise_std=500.0)
+    eng.rng = np.random.default_rng(17)
+    base.rng = np.random.default_rng(23)                    # the reference's module-level Generator
+    g = np.random.default_rng(17)
+    w = np.ones(sc['n_particles']) / sc['n_particles']
+    draws, _ = orc.randdraw(inp['prior'], w, g.random(30))
+    _, ys = orc.yvar_from_draws(orc.model_lorentzian_hwhm, orc.make_allsettings(inp['setting_values']), draws,
+                                inp['cons'], 1)
+    nva = np.random.default_rng(23).normal(0, 1.0, 30).reshape((1, 30))
+    noise = (nva * np.sqrt(orc.noise_var_default(500.0, 1))).T
+    want = orc.utility_full_kld(ys, noise)[0]
+    got = eng.utility()
+    assert_allclose(got, want, rtol=1e-11)
+    with pytest.raises(ValueError):
+        obe.OptBayesExptNoiseParameter('lockin_coil', (np.linspace(1, 2, 5),), np.ones((4, 64)), (),
+                                       noise_parameter_index=(3, 3), utility_method='full_kld_utility')
