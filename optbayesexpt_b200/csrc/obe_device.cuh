@@ -429,6 +429,163 @@ __device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const d
     return t;
 }
 
+// NE elements at once, in one basic block: the per-element chains (reciprocal refinement, the 14-deep exp
+// polynomial, ...) are independent, and written this way ptxas interleaves them, which is what hides the
+// ~8-cycle FP64 latency at 4 warps per SM sub-partition.  (Element-at-a-time code compiled to one serial
+// DFMA chain per particle: ncu showed the FP64 pipe 41 % busy and "wait" the top stall.)
+template <int NE>
+__device__ __forceinline__ void obe_exp_nonpos_vec(const double (&x)[NE], double (&out)[NE]) {
+    double r[NE], p[NE];
+    int k[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const double t = fma(x[e], 1.4426950408889634, 6755399441055744.0);
+        k[e] = __double2loint(t);
+        const double kf = t - 6755399441055744.0;
+        r[e] = fma(kf, -6.93147180369123816490e-01, x[e]);
+        r[e] = fma(kf, -1.90821492927058770002e-10, r[e]);
+        p[e] = obe_exp_c[0];
+    }
+#pragma unroll
+    for (int i = 1; i < 12; ++i) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) p[e] = fma(p[e], r[e], obe_exp_c[i]);
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        p[e] = fma(p[e], r[e], 1.0);
+        p[e] = fma(p[e], r[e], 1.0);
+        const double scale = __hiloint2double((max(k[e], -1022) + 1023) << 20, 0);
+        out[e] = (x[e] < -708.0) ? 0.0 : p[e] * scale;
+    }
+}
+
+template <class Model, int D, int SRC, int NE, bool BATCHED>
+__device__ __forceinline__ void obe_update_vec(const ObeUpdateArgs& a, const double (&p)[NE][D],
+                                               const double (&w_in)[NE], const double (&yg)[NE][OBE_MAX_CH],
+                                               const double (&lik_given)[NE], const bool (&valid)[NE], double invS,
+                                               ObeAcc<D>& acc, const double* rec, double (&t)[NE]) {
+    const double* r_set = BATCHED ? rec + OBE_REC_SET : a.setting;
+    const double* r_y = BATCHED ? rec + OBE_REC_Y : a.y_meas;
+    const double* r_isig = BATCHED ? rec + OBE_REC_ISIG : a.inv_sigma;
+    const double* r_piv = BATCHED ? rec + OBE_REC_PIVOT : a.pivot;
+    if (SRC == OBE_SRC_NONE) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) t[e] = w_in[e];
+    } else {
+        double lik[NE];
+        if (SRC == OBE_SRC_LIK) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) lik[e] = lik_given[e];
+        } else {
+            constexpr int NY = (SRC == OBE_SRC_MODEL) ? (Model::NCH > 0 ? Model::NCH : 1) : OBE_MAX_CH;
+            double y[NE][NY];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                if (SRC == OBE_SRC_MODEL) {
+                    ObeUpdateEval<Model>::eval(r_set, p[e], a.cons, y[e]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NY; ++c) y[e][c] = yg[e][c];
+                }
+                lik[e] = 1.0;
+            }
+            const bool noise = a.n_noise > 0;
+#pragma unroll
+            for (int c = 0; c < NY; ++c) {
+                if (c < a.n_lik_channels) {
+                    // exp(-((y - y_meas)/sigma)**2 / 2) / sigma  (obe_base.py:264-271); the division by sigma
+                    // is a multiplication by its reciprocal (host's 1/sigma, or one refined rcp per particle
+                    // for a noise parameter)
+                    double inv_sig[NE], arg[NE], ex[NE];
+                    const int ni = a.noise_idx[c];
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        inv_sig[e] = r_isig[c];
+                        if (noise) {
+                            double sig = 1.0;
+#pragma unroll
+                            for (int j = 0; j < D; ++j)
+                                if (j == ni) sig = p[e][j];
+                            inv_sig[e] = obe_rcp_fast(sig);
+                        }
+                        const double q = (y[e][c] - r_y[c]) * inv_sig[e];
+                        arg[e] = -0.5 * (q * q);
+                    }
+                    obe_exp_nonpos_vec<NE>(arg, ex);
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) lik[e] *= ex[e] * inv_sig[e];
+                }
+            }
+            if (a.use_choke) {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) lik[e] = pow(lik[e], a.choke);
+            }
+        }
+        // t = nan_to_num(w * lik); w = w_in * invS needs no second nan_to_num (stored weights are finite and
+        // <= total; a NaN from 0 * inf propagates into t and is zeroed here like numpy does)
+        bool any_bad = false;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            t[e] = (w_in[e] * invS) * lik[e];
+            any_bad |= (((unsigned)__double2hiint(t[e])) & 0x7fffffffu) >= 0x7ff00000u;
+        }
+        if (any_bad) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) t[e] = obe_nan_to_num_fast(t[e]);
+        }
+    }
+    if ((SRC == OBE_SRC_NONE || BATCHED) && (a.mask_le | a.mask_lt)) {   // constraint masks: refresh pass / batched
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                if (((a.mask_le >> j) & 1u) && p[e][j] <= 0.0) bad = true;
+                if (((a.mask_lt >> j) & 1u) && p[e][j] < 0.0) bad = true;
+            }
+            if (bad && valid[e]) {
+                if (t[e] != 0.0) acc.nzero += 1.0;
+                t[e] = 0.0;
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) t[e] = valid[e] ? t[e] : 0.0;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        acc.sumsq += t[e] * t[e];
+        acc.sumt += t[e];
+        double dx[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) dx[j] = valid[e] ? p[e][j] - r_piv[j] : 0.0;
+        int q = 0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const double tj = t[e] * dx[j];
+            acc.m1[j] += tj;
+#pragma unroll
+            for (int k = j; k < D; ++k) acc.m2[q++] += tj * dx[k];
+        }
+    }
+    if (a.n_noise > 0) {
+#pragma unroll
+        for (int c = 0; c < OBE_MAX_CH; ++c) {
+            const int ni = a.noise_idx[c];
+            if (ni >= 0) {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    double sig = 0.0;
+#pragma unroll
+                    for (int j = 0; j < D; ++j)
+                        if (j == ni) sig = p[e][j];
+                    acc.noise[c] += valid[e] ? t[e] * (sig * sig) : 0.0;
+                }
+            }
+        }
+    }
+}
+
 // stage geometry as a function of the number of rows staged per particle
 template <int NROWS>
 struct ObeStage {
@@ -583,29 +740,30 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
             }
             __syncwarp();
             if (lane == 0) obe_mbar_arrive(empty_bar + s);   // stage can be refilled
-            // compute + store
+            // compute (all EPT elements of this thread together) + store
+            {
+                double pe[EPT][D], yge[EPT][OBE_MAX_CH], lke[EPT], te[EPT];
+                bool valid[EPT];
 #pragma unroll
-            for (int q = 0; q < (EPT >= 2 ? EPT / 2 : 1); ++q) {
-                const int e0 = (EPT >= 2 ? 2 * (ct + q * OBE_CONSUMER_THREADS) : ct);   // index in the stage
-                double tv[2] = {0.0, 0.0};
+                for (int e = 0; e < EPT; ++e) {
+                    const int idx = (EPT >= 2) ? 2 * (ct + (e >> 1) * OBE_CONSUMER_THREADS) + (e & 1) : ct;
+                    valid[e] = idx < n_valid;
 #pragma unroll
-                for (int h = 0; h < (EPT >= 2 ? 2 : 1); ++h) {
-                    if (e0 + h < n_valid) {
-                        double px[D], yg[OBE_MAX_CH];
+                    for (int j = 0; j < D; ++j) pe[e][j] = pv[j][e];
 #pragma unroll
-                        for (int j = 0; j < D; ++j) px[j] = pv[j][(EPT >= 2 ? 2 * q : 0) + h];
-#pragma unroll
-                        for (int c = 0; c < OBE_MAX_CH; ++c)
-                            yg[c] = (SRC == OBE_SRC_Y) ? yv[SRC == OBE_SRC_Y ? c : 0][(EPT >= 2 ? 2 * q : 0) + h] : 0.0;
-                        tv[h] = obe_update_one<Model, D, SRC>(a, px, wv[(EPT >= 2 ? 2 * q : 0) + h], yg,
-                                                              (SRC == OBE_SRC_LIK) ? lv[(EPT >= 2 ? 2 * q : 0) + h] : 1.0,
-                                                              invS, acc);
-                    }
+                    for (int c = 0; c < OBE_MAX_CH; ++c) yge[e][c] = (SRC == OBE_SRC_Y) ? yv[SRC == OBE_SRC_Y ? c : 0][e] : 0.0;
+                    lke[e] = (SRC == OBE_SRC_LIK) ? lv[e] : 1.0;
                 }
-                tsum += tv[0] + tv[1];
+                obe_update_vec<Model, D, SRC, EPT, false>(a, pe, wv, yge, lke, valid, invS, acc, nullptr, te);
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) tsum += te[e];
                 if (write_weights) {
-                    if (EPT >= 2 && e0 + 1 < n_valid) obe_st2(a.weights + base + e0, make_double2(tv[0], tv[1]));
-                    else if (e0 < n_valid) a.weights[base + e0] = tv[0];
+#pragma unroll
+                    for (int q = 0; q < (EPT >= 2 ? EPT / 2 : 1); ++q) {
+                        const int e0 = (EPT >= 2 ? 2 * (ct + q * OBE_CONSUMER_THREADS) : ct);
+                        if (EPT >= 2 && e0 + 1 < n_valid) obe_st2(a.weights + base + e0, make_double2(te[2 * q], te[2 * q + 1]));
+                        else if (e0 < n_valid) a.weights[base + e0] = te[EPT >= 2 ? 2 * q : 0];
+                    }
                 }
             }
         }
