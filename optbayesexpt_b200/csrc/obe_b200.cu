@@ -442,6 +442,50 @@ __device__ __forceinline__ void device_normals(long long slot, unsigned long lon
     }
 }
 
+// U output slots at once: the Philox rounds of the U counters interleave (one basic block), which hides
+// the integer-multiply latency that a slot-at-a-time loop exposes.
+template <int D, int U>
+__device__ __forceinline__ void device_normals_vec(const long long (&slot)[U], unsigned long long seed,
+                                                   unsigned int epoch, double (&z)[U][D]) {
+    const unsigned int key0 = (unsigned int)(seed & 0xffffffffull), key1 = (unsigned int)(seed >> 32);
+#pragma unroll
+    for (int c = 0; c < (D + 3) / 4; ++c) {
+        unsigned int c0[U], c1[U], c2[U], c3[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            c0[u] = (unsigned int)(slot[u] & 0xffffffffll);
+            c1[u] = (unsigned int)((unsigned long long)slot[u] >> 32);
+            c2[u] = (unsigned int)c; c3[u] = epoch;
+        }
+        unsigned int k0 = key0, k1 = key1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned int hi0 = __umulhi(0xD2511F53u, c0[u]), lo0 = 0xD2511F53u * c0[u];
+                const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2[u]), lo1 = 0xCD9E8D57u * c2[u];
+                const unsigned int n0 = hi1 ^ c1[u] ^ k0, n2 = hi0 ^ c3[u] ^ k1;
+                c0[u] = n0; c1[u] = lo1; c2[u] = n2; c3[u] = lo0;
+            }
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned int r4[4] = {c0[u], c1[u], c2[u], c3[u]};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (4 * c + 2 * h < D) {
+                    const float rad = obe_sqrt_approx(-2.0f * __logf(u24(r4[2 * h])));
+                    float sn, cs;
+                    __sincosf(6.2831853071795865f * u24(r4[2 * h + 1]), &sn, &cs);
+                    z[u][4 * c + 2 * h] = (double)(rad * cs);
+                    if (4 * c + 2 * h + 1 < D) z[u][4 * c + 2 * h + 1] = (double)(rad * sn);
+                }
+            }
+        }
+    }
+}
+
 // Liu-West move of one particle (particlepdf.py:296-307): x + z @ F, optional contraction
 template <int D>
 __device__ __forceinline__ void liu_west(double (&x)[D], const double (&z)[D], const double* __restrict__ F,
@@ -667,6 +711,9 @@ struct SysCtx {
 // rows into shared memory (`xs`, one mbarrier), so the ancestor gathers of phase 3 are LDS instead of
 // dependent global loads -- the top stall of the unstaged kernel.
 #define OBE_STAGE_MAX_D 4
+#ifndef OBE_RES_UNROLL
+#define OBE_RES_UNROLL 1
+#endif
 template <int D, class FT>
 __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long Hk, long long Hk1, int rel_begin,
                                          const FT& F, const double* sMean, double* sm, int* smx,
@@ -781,53 +828,51 @@ __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long
         phase ^= 1u;
     }
     staged_k = k;
-    double xn[D];
-    int rel_n = 0;
-    if (!STAGE && tid < n_out) {
-        rel_n = min((int)anc_s[tid], lastrel);
+    constexpr int U = OBE_RES_UNROLL;                       // output slots per thread per iteration
+    for (int q0 = tid; q0 < n_out; q0 += U * OBE_THREADS) {
+        bool act[U];
+        long long og[U], o[U];
+        int rel[U];
+        double xv[U][D], z[U][D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) xn[j] = __ldg(c.pin + j * c.ld_in + c.in_base + base + rel_n);
-    }
-    for (int q = tid; q < n_out; q += OBE_THREADS) {
-        const long long og = Hk + rel_begin + q;              // global slot: comb tooth, RNG counter
-        const long long o = og - c.slot_begin;                  // position in this shard's output
-        double xv[D], z[D];
-        int rel;
-        if (STAGE) {
-            rel = min((int)anc_s[q], lastrel);
+        for (int u = 0; u < U; ++u) {
+            const int q = q0 + u * OBE_THREADS;
+            act[u] = q < n_out;
+            rel[u] = act[u] ? min((int)anc_s[q], lastrel) : 0;
+            og[u] = Hk + rel_begin + q;                        // global slot: comb tooth, RNG counter
+            o[u] = og[u] - c.slot_begin;                       // position in this shard's output
+            act[u] = act[u] && (o[u] < c.cap_out);             // capacity overflow is flagged in the plan
 #pragma unroll
-            for (int j = 0; j < D; ++j) xv[j] = xs[j * OBE_TILE + rel];
-        } else {
-            rel = rel_n;
-#pragma unroll
-            for (int j = 0; j < D; ++j) xv[j] = xn[j];
-            if (q + OBE_THREADS < n_out) {
-                rel_n = min((int)anc_s[q + OBE_THREADS], lastrel);
-#pragma unroll
-                for (int j = 0; j < D; ++j) xn[j] = __ldg(c.pin + j * c.ld_in + c.in_base + base + rel_n);
-            }
+            for (int j = 0; j < D; ++j)
+                xv[u][j] = STAGE ? xs[j * OBE_TILE + rel[u]] : __ldg(c.pin + j * c.ld_in + c.in_base + base + rel[u]);
         }
-        if (o >= c.cap_out) continue;                           // capacity overflow is flagged in the plan
         if (c.jitter) {
-            device_normals<D>(og, c.seed, c.epoch, z);
-            if (c.z_out) {
+            device_normals_vec<D, U>(og, c.seed, c.epoch, z);
 #pragma unroll
-                for (int j = 0; j < D; ++j) c.z_out[o * D + j] = z[j];
-            }
-            liu_west<D>(xv, z, F, sMean, c.a_param, c.scale);
-        }
-        double wo = c.wv;
-        if (c.mask_le | c.mask_lt) {
+            for (int u = 0; u < U; ++u) {
+                if (c.z_out && act[u]) {
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
-                if (((c.mask_le >> j) & 1u) && xv[j] <= 0.0) wo = 0.0;
-                if (((c.mask_lt >> j) & 1u) && xv[j] < 0.0) wo = 0.0;
+                    for (int j = 0; j < D; ++j) c.z_out[o[u] * D + j] = z[u][j];
+                }
+                liu_west<D>(xv[u], z[u], F, sMean, c.a_param, c.scale);
             }
         }
 #pragma unroll
-        for (int j = 0; j < D; ++j) c.pout[j * c.ld_out + c.out_base + o] = xv[j];
-        if (c.w_out) c.w_out[c.out_base + o] = wo;
-        if (c.idx_out) c.idx_out[o] = base + rel;
+        for (int u = 0; u < U; ++u) {
+            if (!act[u]) continue;
+            double wo = c.wv;
+            if (c.mask_le | c.mask_lt) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    if (((c.mask_le >> j) & 1u) && xv[u][j] <= 0.0) wo = 0.0;
+                    if (((c.mask_lt >> j) & 1u) && xv[u][j] < 0.0) wo = 0.0;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) c.pout[j * c.ld_out + c.out_base + o[u]] = xv[u][j];
+            if (c.w_out) c.w_out[c.out_base + o[u]] = wo;
+            if (c.idx_out) c.idx_out[o[u]] = base + rel[u];
+        }
     }
     __syncthreads();
 }
