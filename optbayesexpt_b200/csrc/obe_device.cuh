@@ -1207,6 +1207,34 @@ __device__ __forceinline__ double obe_entropy_sorted(const double* x, int n) {
     return sum / nd;
 }
 
+// np.argmax semantics for combining candidates: the first maximum wins, NaN counts as the maximum
+__device__ __forceinline__ void obe_argmax_take(double& best, long long& besti, double ov, long long oi) {
+    if (oi < 0) return;
+    const bool onan = (ov != ov), bnan = (best != best);
+    bool take;
+    if (besti < 0) take = true;
+    else if (onan && bnan) take = oi < besti;
+    else if (onan) take = true;
+    else if (bnan) take = false;
+    else take = (ov > best) || (ov == best && oi < besti);
+    if (take) { best = ov; besti = oi; }
+}
+// block-wide argmax; the result is valid in thread 0.  bval/bidx: one slot per warp.
+__device__ __forceinline__ void obe_block_argmax(double& best, long long& besti, double* bval, long long* bidx) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, m);
+        const long long oi = __shfl_xor_sync(0xffffffffu, besti, m);
+        obe_argmax_take(best, besti, ov, oi);
+    }
+    if (lane == 0) { bval[warp] = best; bidx[warp] = besti; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w2 = 1; w2 < (int)(blockDim.x >> 5); ++w2) obe_argmax_take(best, besti, bval[w2], bidx[w2]);
+    }
+}
+
 template <class Model>
 __device__ void obe_utility_body(const ObeUtilityArgs& a) {
     extern __shared__ double obe_smem[];
@@ -1321,66 +1349,29 @@ __device__ void obe_utility_body(const ObeUtilityArgs& a) {
         const bool unan = (u != u), bnan = (best != best);
         if (!have || (!bnan && (unan || u > best))) { best = u; besti = s; have = true; }
     }
-    // ---- block argmax (lowest index among equals), then last-block combine
+    // ---- block argmax (lowest index among equals), then the last block combines the per-block results
     const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, best, m);
-        const long long oi = __shfl_xor_sync(0xffffffffu, besti, m);
-        const bool onan = (ov != ov), bnan = (best != best);
-        bool take = false;
-        if (oi >= 0) {
-            if (besti < 0) take = true;
-            else if (onan && bnan) take = oi < besti;
-            else if (onan) take = true;
-            else if (bnan) take = false;
-            else take = (ov > best) || (ov == best && oi < besti);
-        }
-        if (take) { best = ov; besti = oi; }
-    }
-    if (lane == 0) { bval[warp] = best; bidx[warp] = besti; }
-    __syncthreads();
+    obe_block_argmax(best, besti, bval, bidx);
     if (tid == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-            const double ov = bval[w];
-            const long long oi = bidx[w];
-            const bool onan = (ov != ov), bnan = (best != best);
-            bool take = false;
-            if (oi >= 0) {
-                if (besti < 0) take = true;
-                else if (onan && bnan) take = oi < besti;
-                else if (onan) take = true;
-                else if (bnan) take = false;
-                else take = (ov > best) || (ov == best && oi < besti);
-            }
-            if (take) { best = ov; besti = oi; }
-        }
         a.part_val[blockIdx.x] = best;
         a.part_idx[blockIdx.x] = besti;
         __threadfence();
         is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
-    if (!is_last || tid != 0) return;
+    if (!is_last) return;
     __threadfence();
     best = 0.0; besti = -1;
-    for (unsigned int b = 0; b < gridDim.x; ++b) {
-        const double ov = __ldcg(a.part_val + b);
-        const long long oi = __ldcg(a.part_idx + b);
-        const bool onan = (ov != ov), bnan = (best != best);
-        bool take = false;
-        if (oi >= 0) {
-            if (besti < 0) take = true;
-            else if (onan && bnan) take = oi < besti;
-            else if (onan) take = true;
-            else if (bnan) take = false;
-            else take = (ov > best) || (ov == best && oi < besti);
-        }
-        if (take) { best = ov; besti = oi; }
+    for (unsigned int b = tid; b < gridDim.x; b += blockDim.x)      // all threads: no serial tail
+        obe_argmax_take(best, besti, __ldcg(a.part_val + b), __ldcg(a.part_idx + b));
+    __syncthreads();
+    obe_block_argmax(best, besti, bval, bidx);
+    if (tid == 0) {
+        *a.best_idx = besti;
+        *a.best_val = best;
+        *a.counter = 0u;
     }
-    *a.best_idx = besti;
-    *a.best_val = best;
-    *a.counter = 0u;
+    (void)lane; (void)warp;
 }
 
 // ---------------------------------------------------------------------------------------------
