@@ -373,7 +373,7 @@ def main():
                 'h2d_bytes_per_step': 8 * (1 + 1 + 1 + 8 + 1) + 8 * args.draws,
                 'd2h_bytes_per_step': 8 * 64 + 16,
                 'note': 'record, pivot and uniforms travel as kernel arguments; stats block + argmax come back'},
-        'gpu_launches': 8 * args.steps,
+        'gpu_launches': (5 if world == 1 else 6) * args.steps,   # update, plan, resample, draw, utility (+ shard plan)
         'roofline': {'bound': 'hbm', 'kernel': 'k_sys_resample (+plan/fill/scan helpers inside the bracket)',
                      'achieved': gbs_res, 'peak': peak, 'unit': 'GB/s', 'frac': gbs_res / peak, 'traffic': None,
                      'peak_source': peak_src,

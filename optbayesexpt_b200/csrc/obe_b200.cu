@@ -232,39 +232,8 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_tile_scan(const double* __
                                                                 const long long* __restrict__ n_dev = nullptr,
                                                                 int implicit = 0) {
     __shared__ double sm[34];
-    const int t = threadIdx.x;
     if (n_dev) { n = *n_dev; n_tiles = (n + OBE_TILE - 1) / OBE_TILE; }
-    double carry = 0.0;
-    for (long long base = 0; base < n_tiles; base += OBE_SCAN_THREADS) {
-        const long long k = base + t;
-        const double v = (k < n_tiles) ? tile_sums[k] : 0.0;
-        double tot;
-        const double ex = block_excl_sum_1024(v, sm, &tot);
-        if (k < n_tiles) prefix[k] = carry + ex;
-        carry += tot;
-        __syncthreads();
-    }
-    const double total = carry;
-    if (t == 0) {
-        prefix[n_tiles] = total;
-        if (stats) {
-            stats[OBE_ST_TOTAL] = total;
-            if (uniform) {
-                // weights are exactly 1/n_total: normaliser is exactly 1 (particlepdf.py:309-310);
-                // `uniform` carries n_total (== n for a whole cloud)
-                const double wv = 1.0 / (double)uniform;
-                stats[OBE_ST_INVS] = 1.0;
-                stats[OBE_ST_SUMSQ] = (double)n * wv * wv;
-                stats[OBE_ST_SUMT] = (double)n * wv;
-                stats[OBE_ST_NEFF] = (double)uniform;
-                stats[OBE_ST_UNIFORM] = implicit ? wv : 0.0;
-            } else {
-                stats[OBE_ST_INVS] = renormalise ? 1.0 / total : 1.0;
-                const double ssq = stats[OBE_ST_SUMSQ];
-                stats[OBE_ST_NEFF] = (total * total) / ssq;
-            }
-        }
-    }
+    obe_tile_scan_block<OBE_SCAN_THREADS / 32>(tile_sums, n_tiles, prefix, stats, renormalise, uniform, n, implicit, sm, 0);
 }
 
 __global__ void k_fill_uniform(double* __restrict__ w, double* __restrict__ tile_sums, long long n,
@@ -633,9 +602,14 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
                                                                long long slot_end, long long* __restrict__ H,
                                                                int* __restrict__ unit_start,
                                                                const long long* __restrict__ n_dev = nullptr,
-                                                               const double* __restrict__ plan = nullptr) {
+                                                               const double* __restrict__ plan = nullptr,
+                                                               double* __restrict__ out_tile_sums = nullptr,
+                                                               double* __restrict__ out_prefix = nullptr,
+                                                               double* __restrict__ out_stats = nullptr,
+                                                               int implicit = 0) {
     __shared__ long long sml[34];
     __shared__ int smi[34];
+    __shared__ double smd[34];
     const int t = threadIdx.x;
     if (n_dev) n_tiles = (*n_dev + OBE_TILE - 1) / OBE_TILE;
     if (plan) {
@@ -672,6 +646,21 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
         __syncthreads();
     }
     if (t == 0) unit_start[n_tiles] = icarry;
+    // the offspring cloud has uniform weights 1/n_total: its tile sums, CDF prefix and stats are known
+    // before a single particle is written (saves the fill + scan launches after the resample)
+    if (out_tile_sums) {
+        const long long n_out = slot_end - slot_begin;
+        const long long tiles_out = (n_out + OBE_TILE - 1) / OBE_TILE;
+        const double wv = 1.0 / (double)n_total;
+        for (long long k = t; k < tiles_out; k += OBE_SCAN_THREADS) {
+            const long long cnt = min((long long)OBE_TILE, n_out - k * OBE_TILE);
+            out_tile_sums[k] = (double)cnt * wv;
+        }
+        __threadfence_block();
+        __syncthreads();
+        obe_tile_scan_block<OBE_SCAN_THREADS / 32>(out_tile_sums, tiles_out, out_prefix, out_stats, 0, n_total, n_out,
+                                                  implicit, smd, 0);
+    }
 }
 
 // One work unit = (input tile k, chunk of <= 2048 consecutive output slots owned by that tile).
@@ -1469,14 +1458,12 @@ static void base_update_args(const obe_cloud_t* c, ObeUpdateArgs& a, const doubl
     a.particles = c->particles_dev; a.ld = c->ld; a.n = c->n; a.n_dev = (const long long*)c->n_dev;
     a.weights = c->weights_dev; a.tile_sums = c->tile_sums_dev;
     a.partials = s.partials; a.counter = s.counter; a.stats = c->stats_dev;
+    a.tile_prefix = c->tile_prefix_dev; a.renormalise = 1;
     for (int j = 0; j < OBE_MAX_CH; ++j) a.noise_idx[j] = -1;
     if (pivot) for (int j = 0; j < c->d; ++j) a.pivot[j] = pivot[j];
 }
-static int finish_update(const obe_cloud_t* c, int renorm, cudaStream_t st) {
-    k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(c->tile_sums_dev, obe_num_tiles(c->n), c->tile_prefix_dev,
-                                               c->stats_dev, renorm, 0, c->n, (const long long*)c->n_dev);
-    OBE_LAUNCH_CHECK("k_tile_scan");
-    return 0;
+static int finish_update(const obe_cloud_t*, int, cudaStream_t) {
+    return 0;   // the update kernel's last block scans the tile sums itself (ObeUpdateArgs::tile_prefix)
 }
 static int fill_likelihood_args(ObeUpdateArgs& a, int d, int nch_avail, const double* y_meas, const double* sigma,
                                 const int32_t* noise_index, int n_lik, int use_choke, double choke) {
@@ -1580,6 +1567,7 @@ int obe_refresh(const obe_cloud_t* c, uint32_t mask_le, uint32_t mask_lt, const 
     if (noise_index)
         for (int j = 0; j < n_noise && j < OBE_MAX_CH; ++j) { a.noise_idx[j] = noise_index[j]; a.n_noise = j + 1; }
     cudaStream_t st = (cudaStream_t)stream;
+    a.renormalise = renormalise;
     if (launch_generic<OBE_SRC_NONE>(c->d, a, update_grid(c), st)) return -1;
     return finish_update(c, renormalise, st);
 }
@@ -1756,7 +1744,9 @@ static int resample_systematic_impl(const obe_cloud_t* in, const obe_cloud_t* ou
     a.slot_begin = slot_begin; a.slot_end = slot_end; a.cdf_offset = cdf_offset; a.cdf_total = cdf_total;
     cudaStream_t st = (cudaStream_t)stream;
     k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, u0, sharded ? cdf_offset : 0.0,
-                                              sharded ? cdf_total : 0.0, slot_begin, slot_end, s.plan_h, s.unit_start);
+                                              sharded ? cdf_total : 0.0, slot_begin, slot_end, s.plan_h, s.unit_start,
+                                              nullptr, nullptr, out->tile_sums_dev, out->tile_prefix_dev, out->stats_dev,
+                                              1);
     OBE_LAUNCH_CHECK("k_sys_plan");
     int64_t max_units = a.n_tiles + (out->n + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK;
     int64_t g = (int64_t)obe_sms() * OBE_BLOCKS_PER_SM;
@@ -1764,7 +1754,7 @@ static int resample_systematic_impl(const obe_cloud_t* in, const obe_cloud_t* ou
     const int grid = (int)g;
     OBE_DIM_SWITCH(in->d, k_sys_resample, grid, st, a)
     OBE_LAUNCH_CHECK("k_sys_resample");
-    return finish_resample(out, n_total, st, 1);
+    return 0;
 }
 
 int obe_resample_systematic(const obe_cloud_t* in, const obe_cloud_t* out, double u0, const double* factor,
@@ -1813,7 +1803,8 @@ int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* ou
     a.sharded = 1; a.n_total = n_total; a.implicit_out = 1;
     cudaStream_t st = (cudaStream_t)stream;
     k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0, s.plan_h,
-                                              s.unit_start, (const long long*)in->n_dev, plan_dev);
+                                              s.unit_start, (const long long*)in->n_dev, plan_dev, out->tile_sums_dev,
+                                              out->tile_prefix_dev, out->stats_dev, 1);
     OBE_LAUNCH_CHECK("k_sys_plan");
     int64_t max_units = a.n_tiles + (out->ld + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK;
     int64_t g = (int64_t)obe_sms() * OBE_BLOCKS_PER_SM;
@@ -1821,7 +1812,7 @@ int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* ou
     const int grid = (int)g;
     OBE_DIM_SWITCH(in->d, k_sys_resample, grid, st, a)
     OBE_LAUNCH_CHECK("k_sys_resample");
-    return finish_resample(out, n_total, st, 1);
+    return 0;
 }
 
 int64_t obe_comb_count(double c, double u0, int64_t n_total) {

@@ -92,6 +92,8 @@ struct ObeUpdateArgs {
     long long ld_y;
     const double* lik;       // OBE_SRC_LIK: (n)
     const long long* n_dev;  // optional: live particle count on the device (n is then an upper bound)
+    double* tile_prefix;     // the last block also scans the tile sums into the CDF prefix ...
+    int renormalise;         // ... and sets the normaliser to 1/total (1) or to exactly 1 (0)
     int scale_in;            // 1: w_in = nan_to_num(t * stats[INVS]); 0: raw t
     int write_weights;
     int n_lik_channels;      // min(C, len(y_meas), len(sigma))  -- zip truncation
@@ -586,6 +588,82 @@ __device__ __forceinline__ void obe_update_vec(const ObeUpdateArgs& a, const dou
     }
 }
 
+// Exclusive block scan (sum) of one double per thread for NW warps; total in *tot.  `sm` holds NW + 2 doubles.
+// Uses bar.sync on barrier `bar_id` over NW*32 threads so it also works among the consumers only.
+template <int NW>
+__device__ __forceinline__ double obe_block_excl_sum(double v, double* sm, double* tot, int bar_id) {
+    const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) % NW;
+    double x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    obe_named_bar(bar_id, NW * 32);
+    if (lane == 31) sm[warp] = x;
+    obe_named_bar(bar_id, NW * 32);
+    if (warp == 0) {
+        double xs = (lane < NW) ? sm[lane] : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, xs, o);
+            if (lane >= o) xs += y;
+        }
+        double ex = __shfl_up_sync(0xffffffffu, xs, 1);  // exclusive base of each warp
+        if (lane == 0) ex = 0.0;
+        if (lane < NW) sm[lane] = ex;
+        if (lane == 31) sm[NW] = xs;
+    }
+    obe_named_bar(bar_id, NW * 32);
+    const double base = sm[warp];
+    double ex = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) ex = 0.0;
+    *tot = sm[NW];
+    return base + ex;
+}
+
+// tile_prefix[k] = sum of tile_sums[0..k) in a fixed association (coalesced chunks of NW*32 with a running
+// carry); tile_prefix[n_tiles] is THE total every CDF consumer divides by.  One block.  Also finishes the
+// stats block: canonical total, normaliser, N_eff (and the uniform-weights bookkeeping after a resample).
+template <int NW>
+__device__ __forceinline__ void obe_tile_scan_block(const double* __restrict__ tile_sums, long long n_tiles,
+                                                    double* __restrict__ prefix, double* __restrict__ stats,
+                                                    int renormalise, long long uniform, long long n, int implicit,
+                                                    double* sm, int bar_id) {
+    const int t = threadIdx.x % (NW * 32);
+    double carry = 0.0;
+    for (long long base = 0; base < n_tiles; base += NW * 32) {
+        const long long k = base + t;
+        const double v = (k < n_tiles) ? __ldcg(tile_sums + k) : 0.0;
+        double tot;
+        const double ex = obe_block_excl_sum<NW>(v, sm, &tot, bar_id);
+        if (k < n_tiles) prefix[k] = carry + ex;
+        carry += tot;
+        obe_named_bar(bar_id, NW * 32);
+    }
+    const double total = carry;
+    if (t == 0) {
+        prefix[n_tiles] = total;
+        if (stats) {
+            stats[OBE_ST_TOTAL] = total;
+            if (uniform) {
+                // weights are exactly 1/n_total: normaliser is exactly 1 (particlepdf.py:309-310);
+                // `uniform` carries n_total (== n for a whole cloud)
+                const double wv = 1.0 / (double)uniform;
+                stats[OBE_ST_INVS] = 1.0;
+                stats[OBE_ST_SUMSQ] = (double)n * wv * wv;
+                stats[OBE_ST_SUMT] = (double)n * wv;
+                stats[OBE_ST_NEFF] = (double)uniform;
+                stats[OBE_ST_UNIFORM] = implicit ? wv : 0.0;
+            } else {
+                stats[OBE_ST_INVS] = renormalise ? 1.0 / total : 1.0;
+                const double ssq = stats[OBE_ST_SUMSQ];
+                stats[OBE_ST_NEFF] = (total * total) / ssq;
+            }
+        }
+    }
+}
+
 // stage geometry as a function of the number of rows staged per particle
 template <int NROWS>
 struct ObeStage {
@@ -824,6 +902,11 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
         if (a.write_weights) a.stats[OBE_ST_UNIFORM] = 0.0;      // the weight row is explicit again
         *a.counter = 0u;
     }
+    // the last block also turns the tile sums into the CDF prefix and finishes the stats block (saves a launch)
+    obe_named_bar(1, OBE_CONSUMER_THREADS);
+    __threadfence();
+    obe_tile_scan_block<OBE_CONSUMER_WARPS>(a.tile_sums, n_tiles, a.tile_prefix, a.stats, a.renormalise, 0, n, 0, fin,
+                                            1);
 }
 
 // ---------------------------------------------------------------------------------------------
