@@ -338,99 +338,6 @@ struct ObeUpdateEval {
 #define OBE_REC_INVS 20
 #define OBE_REC_LEN 24
 
-template <class Model, int D, int SRC, bool BATCHED = false>
-__device__ __forceinline__ double obe_update_one(const ObeUpdateArgs& a, const double (&p)[D], double w_in,
-                                                 const double (&yg)[OBE_MAX_CH], double lik_given,
-                                                 double invS, ObeAcc<D>& acc, const double* rec = nullptr) {
-    // single cloud: the record sits in the kernel parameters (constant bank operands);
-    // batched: every instance has its own record, staged in shared memory
-    const double* r_set = BATCHED ? rec + OBE_REC_SET : a.setting;
-    const double* r_y = BATCHED ? rec + OBE_REC_Y : a.y_meas;
-    const double* r_isig = BATCHED ? rec + OBE_REC_ISIG : a.inv_sigma;
-    const double* r_piv = BATCHED ? rec + OBE_REC_PIVOT : a.pivot;
-    double t;
-    if (SRC == OBE_SRC_NONE) {
-        t = w_in;
-    } else {
-        // stored weights are finite and <= total, so w_in * invS needs no second nan_to_num: a NaN
-        // (0 * inf when every weight is zero) propagates into t and is zeroed there like numpy does
-        const double w = w_in * invS;
-        double lik = 1.0;
-        if (SRC == OBE_SRC_LIK) {
-            lik = lik_given;
-        } else {
-            constexpr int NY = (SRC == OBE_SRC_MODEL) ? (Model::NCH > 0 ? Model::NCH : 1) : OBE_MAX_CH;
-            double y[NY];
-            if (SRC == OBE_SRC_MODEL) {
-                ObeUpdateEval<Model>::eval(r_set, p, a.cons, y);
-            } else {
-#pragma unroll
-                for (int c = 0; c < NY; ++c) y[c] = yg[c];
-            }
-#pragma unroll
-            for (int c = 0; c < NY; ++c) {
-                if (c < a.n_lik_channels) {
-                    // exp(-((y - y_meas)/sigma)**2 / 2) / sigma  (obe_base.py:264-271) with the
-                    // division by sigma done as a multiplication by its reciprocal: the host's
-                    // 1/sigma for a known sigma, one in-kernel reciprocal for a noise parameter
-                    double inv_sig = r_isig[c];
-                    if (a.n_noise > 0) {
-                        const int ni = a.noise_idx[c];
-                        double sig = 1.0;
-#pragma unroll
-                        for (int j = 0; j < D; ++j)
-                            if (j == ni) sig = p[j];
-                        inv_sig = obe_rcp_fast(sig);
-                    }
-                    const double q = (y[c] - r_y[c]) * inv_sig;
-                    lik *= obe_exp_nonpos(-0.5 * (q * q)) * inv_sig;
-                }
-            }
-            if (a.use_choke) lik = pow(lik, a.choke);
-        }
-        t = obe_nan_to_num_fast(w * lik);
-    }
-    if ((SRC == OBE_SRC_NONE || BATCHED) && (a.mask_le | a.mask_lt)) {   // constraint masks: refresh pass / batched
-        bool bad = false;
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            if (((a.mask_le >> j) & 1u) && p[j] <= 0.0) bad = true;
-            if (((a.mask_lt >> j) & 1u) && p[j] < 0.0) bad = true;
-        }
-        if (bad) {
-            if (t != 0.0) acc.nzero += 1.0;
-            t = 0.0;
-        }
-    }
-    acc.sumsq += t * t;
-    acc.sumt += t;
-    double dx[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) dx[j] = p[j] - r_piv[j];
-    int q = 0;
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-        const double tj = t * dx[j];
-        acc.m1[j] += tj;
-#pragma unroll
-        for (int k = j; k < D; ++k) acc.m2[q++] += tj * dx[k];
-    }
-    if (a.n_noise > 0) {
-#pragma unroll
-        for (int c = 0; c < OBE_MAX_CH; ++c) {
-            const int ni = a.noise_idx[c];
-            if (ni >= 0) {
-                double sig = 0.0;
-#pragma unroll
-                for (int j = 0; j < D; ++j)
-                    if (j == ni) sig = p[j];
-                acc.noise[c] += t * (sig * sig);
-            }
-        }
-    }
-    return t;
-}
-
 // NE elements at once, in one basic block: the per-element chains (reciprocal refinement, the 14-deep exp
 // polynomial, ...) are independent, and written this way ptxas interleaves them, which is what hides the
 // ~8-cycle FP64 latency at 4 warps per SM sub-partition.  (Element-at-a-time code compiled to one serial
@@ -1056,23 +963,28 @@ __device__ void obe_update_batched_body(const ObeBatchArgs& a) {
                 }
                 __syncwarp();
                 if (lane == 0) obe_mbar_arrive(empty_bar + s);
+                {
+                    double pe[EPT][D], yge[EPT][OBE_MAX_CH], lke[EPT], te[EPT];
+                    bool valid[EPT];
 #pragma unroll
-                for (int q = 0; q < EPT / 2; ++q) {
-                    const int e0 = 2 * (ct + q * OBE_CONSUMER_THREADS);
-                    double tv[2] = {0.0, 0.0};
+                    for (int e = 0; e < EPT; ++e) {
+                        valid[e] = 2 * (ct + (e >> 1) * OBE_CONSUMER_THREADS) + (e & 1) < n_valid;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (e0 + h < n_valid) {
-                            double px[D], yg[OBE_MAX_CH] = {0.0, 0.0, 0.0, 0.0};
+                        for (int j = 0; j < D; ++j) pe[e][j] = pv[j][e];
 #pragma unroll
-                            for (int j = 0; j < D; ++j) px[j] = pv[j][2 * q + h];
-                            tv[h] = obe_update_one<Model, D, SRC, true>(a.u, px, wv[2 * q + h], yg, 1.0, invS, acc, rec);
-                        }
+                        for (int c = 0; c < OBE_MAX_CH; ++c) yge[e][c] = 0.0;
+                        lke[e] = 1.0;
                     }
-                    tsum += tv[0] + tv[1];
+                    obe_update_vec<Model, D, SRC, EPT, true>(a.u, pe, wv, yge, lke, valid, invS, acc, rec, te);
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) tsum += te[e];
                     if (write_weights) {
-                        if (e0 + 1 < n_valid) obe_st2(a.weights[cb] + base + e0, make_double2(tv[0], tv[1]));
-                        else if (e0 < n_valid) a.weights[cb][base + e0] = tv[0];
+#pragma unroll
+                        for (int q = 0; q < EPT / 2; ++q) {
+                            const int e0 = 2 * (ct + q * OBE_CONSUMER_THREADS);
+                            if (e0 + 1 < n_valid) obe_st2(a.weights[cb] + base + e0, make_double2(te[2 * q], te[2 * q + 1]));
+                            else if (e0 < n_valid) a.weights[cb][base + e0] = te[2 * q];
+                        }
                     }
                 }
             }
