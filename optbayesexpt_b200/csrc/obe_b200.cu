@@ -1500,7 +1500,7 @@ int obe_set_uniform(const obe_cloud_t* c, void* stream) {
 
 int obe_set_uniform_total(const obe_cloud_t* c, int64_t n_total, void* stream) {
     if (check_cloud(c)) return -1;
-    if (n_total < c->n) return obe_fail("n_total < n%s%s");
+    if (n_total < 1 || (!c->n_dev && n_total < c->n)) return obe_fail("n_total < n%s%s");
     cudaStream_t st = (cudaStream_t)stream;
     k_fill_uniform<<<obe_sms() * 8, 256, 0, st>>>(c->weights_dev, c->tile_sums_dev, c->n, obe_num_tiles(c->n), 1, n_total,
                                                   (const long long*)c->n_dev);

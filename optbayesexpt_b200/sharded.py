@@ -355,7 +355,16 @@ class ShardedOptBayesExpt(OptBayesExpt):
     def _utility_dev_run(self):
         draws = self._randdraw_dev(self.N_DRAWS)
         n_loc = self._s_hi - self._s_lo
-        var_noise = _lib.darr(np.asarray(self.yvar_noise_model(), dtype=np.float64).reshape(-1), _lib.MAX_CHANNELS)
+        stats_ptr = None
+        if self._noise_from_stats():
+            # weighted mean of sigma^2 from the GLOBAL noise sums the shard plan combined (no host round-trip)
+            if not self._plan_valid or self._section != 0:
+                self._fetch_plan()
+            var_noise = None
+            stats_ptr = C.c_void_p(self._plan.data_ptr() + 8 * _lib.PLAN_GSTATS)
+        else:
+            var_noise = _lib.darr(np.asarray(self.yvar_noise_model(), dtype=np.float64).reshape(-1),
+                                  _lib.MAX_CHANNELS)
         cost = self.cost_estimate()
         cost_ptr = None
         if not (np.isscalar(cost) and float(cost) == 1.0):
@@ -366,7 +375,7 @@ class ShardedOptBayesExpt(OptBayesExpt):
         settings_ptr = C.c_void_p(self._settings_dev.data_ptr() + 8 * self._s_lo)
         util_ptr = C.c_void_p(self._utility_dev.data_ptr() + 8 * self._s_lo)
         self._check(self._lib.obe_utility(self._model, C.c_void_p(draws.data_ptr()), int(self.N_DRAWS), settings_ptr,
-                                          self._lds, n_loc, self._cons_arr, var_noise, None, cost_ptr,
+                                          self._lds, n_loc, self._cons_arr, var_noise, stats_ptr, cost_ptr,
                                           self._utility_code, 1 if self.utility_log_form else 0,
                                           self._kld_noise_ptr(), util_ptr,
                                           C.c_void_p(self._best_dev.data_ptr()),
@@ -422,6 +431,18 @@ class ShardedOptBayesExpt(OptBayesExpt):
         self.last_setting_index = goodindex
         return tuple(self.allsettings[:, goodindex])
 
+    def _apply_constraint_masks(self, mask_le=0, mask_lt=0):
+        """weight <- 0 where the masked parameters are not positive, on every shard, then a new plan (global
+        normaliser and noise sums of the constrained cloud)."""
+        ni = self._noise_index
+        self._check(self._lib.obe_refresh(self._cs(), mask_le, mask_lt, _lib.iarr(ni), 0 if ni is None else len(ni),
+                                          _lib.darr(self._pivot, _lib.MAX_PARAMS), 1, self._stream()))
+        self._invalidate()
+        self._weights_uniform = False
+        self._weights_lazy = True
+        self._moments_valid = True
+        self._make_plan()
+
     def run_cycle_async(self, measurement_record, resample=True, select=True):
         """Sharded cycle with NO host synchronisation: update -> all-gather(stats) -> device plan ->
         planned resample -> owner-written draws -> all-reduce -> utility over this rank's grid slice."""
@@ -430,5 +451,44 @@ class ShardedOptBayesExpt(OptBayesExpt):
         if resample:
             self.resample()
             self.just_resampled = True
+            self.enforce_parameter_constraints()
         if select:
             self._utility_dev_run()
+
+
+class ShardedOptBayesExptNoiseParameter(ShardedOptBayesExpt):
+    """OptBayesExptNoiseParameter (obe_noiseparam.py) over a sharded cloud: sigma is a particle coordinate, the
+    noise variance of the utility is the GLOBAL weighted mean of sigma^2 (combined in the shard plan), and the
+    positivity constraint is applied on every shard after a resample."""
+
+    def __init__(self, measurement_model, setting_values, parameter_samples, constants, noise_parameter_index=None,
+                 **kwargs):
+        ShardedOptBayesExpt.__init__(self, measurement_model, setting_values, parameter_samples, constants, **kwargs)
+        idx = np.atleast_1d(noise_parameter_index)
+        if noise_parameter_index is None or len(idx) != self.n_channels:
+            raise RuntimeError(f'noise_parameter_index is not compatible with {self.n_channels} measurement channels')
+        self.noise_parameter_index = idx.astype(int)
+        self._noise_index = [int(i) for i in self.noise_parameter_index]
+        # the noise sums were not part of the first stats pass
+        self._moments_valid = False
+        self._plan_valid = False
+        self._fetch_plan()
+
+    def _likelihood_spec(self, measurement_record):
+        y_meas = np.atleast_1d(np.asarray(measurement_record[1], dtype=np.float64))
+        n_lik = min(self.n_channels, len(y_meas))
+        return y_meas[:n_lik], None, self._noise_index[:n_lik], n_lik
+
+    def _noise_from_stats(self):
+        return True
+
+    def enforce_parameter_constraints(self):
+        mask = 0
+        for i in self._noise_index:
+            mask |= 1 << i
+        self._apply_constraint_masks(mask_le=mask)
+
+    def yvar_noise_model(self):
+        gs = self._fetch_plan()
+        c = self.n_channels
+        return (gs['noise'][:c] / gs['sumt']).reshape((c, 1))

@@ -114,6 +114,97 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _worker_noise(rank, world, port, out):
+    """noise-parameter engine (config c2): sigma is a particle coordinate, positivity constraint after a resample"""
+    import warnings
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import optbayesexpt_b200 as obe
+        from optbayesexpt_b200.sharded import ShardedOptBayesExptNoiseParameter
+        from oracle.scenarios import build_inputs, by_name
+        sc = by_name('c2_line_noise')
+        n = 40000
+        inp = build_inputs(sc, n)
+        prior = inp['prior'].copy()
+        cut = [0, 17000, n]
+        lo, hi = cut[rank], cut[rank + 1]
+        # a small a_param makes the Liu-West nudge large enough to push some noise parameters below zero
+        kw = dict(scale=False, seed=5, noise_parameter_index=2, a_param=0.5)
+        eng = ShardedOptBayesExptNoiseParameter('line', inp['setting_values'], prior[:, lo:hi], (), **kw)
+        ref = obe.OptBayesExptNoiseParameter('line', inp['setting_values'], prior, (), **kw)
+        for e in (eng, ref):
+            e.tuning_parameters['auto_resample'] = False
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', RuntimeWarning)
+            np.testing.assert_allclose(eng.yvar_noise_model(), ref.yvar_noise_model(), rtol=1e-12)
+            for seed, y in ((1, 0.1), (2, 0.25)):
+                eng.rng = np.random.default_rng(seed)
+                ref.rng = np.random.default_rng(seed)
+                s1, s2 = eng.opt_setting(), ref.opt_setting()
+                assert eng.last_setting_index == ref.last_setting_index
+                eng.rng = np.random.default_rng(seed)
+                ref.rng = np.random.default_rng(seed)
+                np.testing.assert_allclose(eng.utility(), ref.utility(), rtol=1e-11)
+                eng.pdf_update((s1, y))
+                ref.pdf_update((s1, y))
+                np.testing.assert_allclose(eng.particle_weights, ref.particle_weights[lo:hi], rtol=1e-12, atol=1e-300)
+                np.testing.assert_allclose(eng.n_eff(), ref.n_eff(), rtol=1e-12)
+                np.testing.assert_allclose(eng.yvar_noise_model(), ref.yvar_noise_model(), rtol=1e-12)
+            # resample on both with the same comb offset and normals, then the positivity constraint
+            eng._philox_seed = ref._philox_seed = 99
+            eng._epoch = ref._epoch = 0
+            u0 = eng._u0                                     # the comb offset of the current plan
+            ref.rng = type('R', (), {'random': staticmethod(lambda *a: u0)})()
+            eng.resample()
+            eng.enforce_parameter_constraints()
+            ref.resample()
+            ref.enforce_parameter_constraints()
+        counts = eng.shard_counts
+        start = int(counts[:rank].sum())
+        want_w = ref.particle_weights[start:start + eng.n_particles]
+        want_p = ref.particles[:, start:start + eng.n_particles]
+        spread = want_p.std(axis=1, keepdims=True)
+        perr = np.abs(eng.particles - want_p) / (np.abs(want_p) * 1e-12 + spread * 1e-9)
+        assert perr.max() <= 1.0, f'resampled shard differs from the single cloud: {perr.max():.3g} counts {counts}'
+        np.testing.assert_allclose(eng.particle_weights, want_w, rtol=1e-12, atol=0)
+        assert (eng.particle_weights == 0).sum() == (want_w == 0).sum()
+        zeros = eng._comm.allreduce_sum(torch.tensor([float((eng.particle_weights == 0).sum())], dtype=torch.float64))
+        assert zeros.item() > 0, 'the constraint never bit: the test does not exercise it'
+        np.testing.assert_allclose(eng.yvar_noise_model(), ref.yvar_noise_model(), rtol=1e-11)
+        np.testing.assert_allclose(eng.mean(), ref.mean(), rtol=1e-10)
+        out.put((rank, 'ok'))
+    except Exception as exc:  # pragma: no cover
+        import traceback
+        out.put((rank, traceback.format_exc()))
+        raise exc
+    finally:
+        dist.destroy_process_group()
+
+
+def _spawn(worker):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == 'ok', f'rank {rank}: {msg}'
+
+
+def test_two_shards_noise_parameter_engine(obe_lib):
+    _spawn(_worker_noise)
+
+
 def test_two_shards_match_single_cloud(obe_lib):
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
