@@ -373,8 +373,8 @@ def main():
                 'h2d_bytes_per_step': 8 * (1 + 1 + 1 + 8 + 1) + 8 * args.draws,
                 'd2h_bytes_per_step': 8 * 64 + 16,
                 'note': 'record, pivot and uniforms travel as kernel arguments; stats block + argmax come back'},
-        'gpu_launches': (5 if world == 1 else 6) * args.steps,   # update, plan, resample, draw, utility (+ shard plan)
-        'roofline': {'bound': 'hbm', 'kernel': 'k_sys_resample (+plan/fill/scan helpers inside the bracket)',
+        'gpu_launches': (6 if world == 1 else 7) * args.steps,   # update, plan, ancestors, move, draw, utility (+ shard plan)
+        'roofline': {'bound': 'hbm', 'kernel': 'resample step = k_sys_plan + k_sys_ancestors + k_sys_move (one event bracket)',
                      'achieved': gbs_res, 'peak': peak, 'unit': 'GB/s', 'frac': gbs_res / peak, 'traffic': None,
                      'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': b_res / world},

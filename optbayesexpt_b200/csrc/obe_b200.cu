@@ -65,7 +65,10 @@ struct Scratch {
     double* partials;        // OBE_MAX_GRID * OBE_NACC_MAX
     long long* plan_h;       // n_tiles + 1
     int* unit_start;         // n_tiles + 2
+    unsigned int* anc;       // n + 4 (ancestors of the offspring written INTO this cloud)
+    int* unit_tile;          // n_tiles + n / OBE_OUT_CHUNK_HOST + 4 (work unit -> input tile)
 };
+#define OBE_OUT_CHUNK_HOST 4096
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static size_t scratch_bytes(int64_t n) {
     const int64_t nt = (n + OBE_TILE - 1) / OBE_TILE;
@@ -73,6 +76,8 @@ static size_t scratch_bytes(int64_t n) {
     b += align_up((size_t)OBE_MAX_GRID * OBE_NACC_MAX * sizeof(double), 256);
     b += align_up((size_t)(nt + 1) * sizeof(long long), 256);
     b += align_up((size_t)(nt + 2) * sizeof(int), 256);
+    b += align_up((size_t)(n + 4) * sizeof(unsigned int), 256);
+    b += align_up((size_t)(nt + n / OBE_OUT_CHUNK_HOST + 4) * sizeof(int), 256);
     return b;
 }
 static Scratch scratch_of(const obe_cloud_t* c) {
@@ -82,7 +87,9 @@ static Scratch scratch_of(const obe_cloud_t* c) {
     s.counter = (unsigned int*)p; p += 256;
     s.partials = (double*)p; p += align_up((size_t)OBE_MAX_GRID * OBE_NACC_MAX * sizeof(double), 256);
     s.plan_h = (long long*)p; p += align_up((size_t)(nt + 1) * sizeof(long long), 256);
-    s.unit_start = (int*)p;
+    s.unit_start = (int*)p; p += align_up((size_t)(nt + 2) * sizeof(int), 256);
+    s.anc = (unsigned int*)p; p += align_up((size_t)(c->n + 4) * sizeof(unsigned int), 256);
+    s.unit_tile = (int*)p;
     return s;
 }
 
@@ -167,35 +174,6 @@ __device__ __forceinline__ double block_excl_sum_1024(double v, double* sm /*34*
     return base + ex;
 }
 
-// inclusive running max; *tot = max over the block
-__device__ __forceinline__ long long block_incl_max_1024(long long v, long long* sm /*34*/, long long* tot) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    long long x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const long long y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x = max(x, y);
-    }
-    __syncthreads();
-    if (lane == 31) sm[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-        long long xs = sm[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const long long y = __shfl_up_sync(0xffffffffu, xs, o);
-            if (lane >= o) xs = max(xs, y);
-        }
-        long long ex = __shfl_up_sync(0xffffffffu, xs, 1);
-        if (lane == 0) ex = -1;
-        sm[lane] = ex;
-        if (lane == 31) sm[32] = xs;
-    }
-    __syncthreads();
-    *tot = sm[32];
-    return max(sm[warp], x);
-}
-
 __device__ __forceinline__ int block_excl_isum_1024(int v, int* sm /*34*/, int* tot) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int x = v;
@@ -231,7 +209,7 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_tile_scan(const double* __
                                                                 long long uniform, long long n,
                                                                 const long long* __restrict__ n_dev = nullptr,
                                                                 int implicit = 0) {
-    __shared__ double sm[34];
+    __shared__ double sm[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     if (n_dev) { n = *n_dev; n_tiles = (n + OBE_TILE - 1) / OBE_TILE; }
     obe_tile_scan_block<OBE_SCAN_THREADS / 32>(tile_sums, n_tiles, prefix, stats, renormalise, uniform, n, implicit, sm, 0);
 }
@@ -476,7 +454,7 @@ struct ObeResampleArgs {
     double* pout; long long ld_out; double* w_out;
     const long long* idx_in;       // gather mode
     const double* z_in;            // gather mode, optional (n, d)
-    const long long* plan_h; const int* unit_start;  // systematic mode
+    const long long* plan_h; const int* unit_start; const int* unit_tile;  // systematic mode
     const double* stats;
     long long* idx_out; double* z_out;
     double u0, a_param;
@@ -493,6 +471,8 @@ struct ObeResampleArgs {
     const double* plan;            // optional device-resident shard plan (overrides the by-value shard fields)
     long long cap_out;             // capacity of the output buffers (planned mode)
     int implicit_out;              // 1: do not write the offspring weights, leave them implicit
+    unsigned int* anc;             // two-kernel path: ancestor (input index) of every output slot of this shard
+    double* out_tile_sums; double* out_prefix; double* out_stats;   // CDF bookkeeping of the offspring cloud
     double factor[OBE_MAX_DIMS * OBE_MAX_DIMS];
     double mean[OBE_MAX_DIMS];
 };
@@ -583,7 +563,9 @@ __global__ void __launch_bounds__(OBE_THREADS) k_gather_jitter(const ObeResample
 __device__ __forceinline__ double comb_count_d(double c, double u0, double inv_n, double nd, double tol) {
     const double x = fma(c, nd, -u0);
     double i = ceil(x);
-    if (i - x < tol || i - x > 1.0 - tol || !(i > 0.0) || !(i < nd)) {
+    // c is a CDF value in [0, 1 + few ulp], so ceil(x) lies in [0, nd] unless x is within tol of nd,
+    // which the boundary test catches: the fast path needs no range test.
+    if (fabs((i - x) - 0.5) > 0.5 - tol) {
         i = (i < 0.0) ? 0.0 : i;
         i = (i > nd) ? nd : i;
         while (i > 0.0 && obe_mul(obe_add(i - 1.0, u0), inv_n) >= c) i -= 1.0;
@@ -592,7 +574,18 @@ __device__ __forceinline__ double comb_count_d(double c, double u0, double inv_n
     return i;
 }
 
+// exclusive max over the preceding warps of a block of 8 warps (values >= 0), totals in smx[0..8)
+__device__ __forceinline__ int obe_prev_warps_max8(const int* smx, int warp, int lane) {
+    int v = smx[lane & 7];
+    v = ((lane & 7) < warp) ? v : 0;
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    return v;
+}
+
 #define OBE_OUT_CHUNK 4096
+static_assert(OBE_OUT_CHUNK == OBE_OUT_CHUNK_HOST, "scratch sizing");
 #define OBE_SPT (OBE_OUT_CHUNK / OBE_THREADS) /* output slots per thread in the mark scan */
 // plan: H[k] = first output slot owned by tile k (monotone), unit_start[k] = first work unit of
 // tile k, one unit = up to OBE_OUT_CHUNK output slots of one input tile.
@@ -601,15 +594,11 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
                                                                double cdf_total, long long slot_begin,
                                                                long long slot_end, long long* __restrict__ H,
                                                                int* __restrict__ unit_start,
+                                                               int* __restrict__ unit_tile,
                                                                const long long* __restrict__ n_dev = nullptr,
-                                                               const double* __restrict__ plan = nullptr,
-                                                               double* __restrict__ out_tile_sums = nullptr,
-                                                               double* __restrict__ out_prefix = nullptr,
-                                                               double* __restrict__ out_stats = nullptr,
-                                                               int implicit = 0) {
-    __shared__ long long sml[34];
-    __shared__ int smi[34];
-    __shared__ double smd[34];
+                                                               const double* __restrict__ plan = nullptr) {
+    __shared__ long long sml[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
+    __shared__ int smi[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     const int t = threadIdx.x;
     if (n_dev) n_tiles = (*n_dev + OBE_TILE - 1) / OBE_TILE;
     if (plan) {
@@ -619,48 +608,71 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
     }
     const double inv_total = 1.0 / (cdf_total > 0.0 ? cdf_total : prefix[n_tiles]);
     const double nd = (double)n_total, inv_n = 1.0 / nd, tol = 2e-15 * nd;
-    long long carry = -1;
-    for (long long base = 0; base <= n_tiles; base += OBE_SCAN_THREADS) {
-        const long long k = base + t;
-        long long h = -1;
-        if (k <= n_tiles)
-            h = (k == 0) ? slot_begin
-                         : (k == n_tiles ? slot_end
-                                         : (long long)comb_count_d(obe_mul(obe_add(cdf_offset, prefix[k]), inv_total),
-                                                                   u0, inv_n, nd, tol));
-        long long tot;
-        const long long inc = block_incl_max_1024(h, sml, &tot);
-        if (k <= n_tiles) H[k] = min(max(max(inc, carry), slot_begin), slot_end);
-        carry = max(carry, tot);
+    // raw H[k]: elementwise, coalesced, OBE_SCANW loads in flight per thread
+    for (long long base = 0; base <= n_tiles; base += OBE_SCANW * OBE_SCAN_THREADS) {
+        double pk[OBE_SCANW];
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            pk[e] = (k < n_tiles) ? prefix[k] : 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            if (k > n_tiles) continue;
+            long long h = (k == 0) ? slot_begin
+                                   : (k == n_tiles ? slot_end
+                                                   : (long long)comb_count_d(obe_mul(obe_add(cdf_offset, pk[e]), inv_total),
+                                                                             u0, inv_n, nd, tol));
+            H[k] = min(max(h, slot_begin), slot_end);
+        }
+    }
+    __syncthreads();
+    // The prefix can dip by an ulp where two association orders meet, so H is made monotone by a
+    // running max (in place); then unit_start = exclusive scan of the units per tile.  Both scans walk
+    // OBE_SCANW chunks of 1024 tiles per round.
+    constexpr int NWP = OBE_SCAN_THREADS / 32;
+    long long hcarry = slot_begin;
+    for (long long base = 0; base < n_tiles; base += OBE_SCANW * OBE_SCAN_THREADS) {
+        long long h[OBE_SCANW], ex[OBE_SCANW], tot[OBE_SCANW];
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            h[e] = (k < n_tiles) ? H[k] : -1;
+        }
+        obe_block_excl_scanw<long long, NWP>(h, ex, tot, sml, ObeOpMax(), -1ll, 0);
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            if (k < n_tiles) H[k] = max(max(hcarry, ex[e]), h[e]);
+            hcarry = max(hcarry, tot[e]);
+        }
         __syncthreads();
     }
     int icarry = 0;
-    for (long long base = 0; base < n_tiles; base += OBE_SCAN_THREADS) {
-        const long long k = base + t;
-        int units = 0;
-        if (k < n_tiles) units = (int)((H[k + 1] - H[k] + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK);
-        int tot;
-        const int ex = block_excl_isum_1024(units, smi, &tot);
-        if (k < n_tiles) unit_start[k] = icarry + ex;
-        icarry += tot;
-        __syncthreads();
-    }
-    if (t == 0) unit_start[n_tiles] = icarry;
-    // the offspring cloud has uniform weights 1/n_total: its tile sums, CDF prefix and stats are known
-    // before a single particle is written (saves the fill + scan launches after the resample)
-    if (out_tile_sums) {
-        const long long n_out = slot_end - slot_begin;
-        const long long tiles_out = (n_out + OBE_TILE - 1) / OBE_TILE;
-        const double wv = 1.0 / (double)n_total;
-        for (long long k = t; k < tiles_out; k += OBE_SCAN_THREADS) {
-            const long long cnt = min((long long)OBE_TILE, n_out - k * OBE_TILE);
-            out_tile_sums[k] = (double)cnt * wv;
+    for (long long base = 0; base < n_tiles; base += OBE_SCANW * OBE_SCAN_THREADS) {
+        int units[OBE_SCANW], ex[OBE_SCANW], tot[OBE_SCANW];
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            units[e] = (k < n_tiles) ? (int)((max(H[k + 1] - H[k], 0ll) + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK) : 0;
         }
-        __threadfence_block();
+        obe_block_excl_scanw<int, NWP>(units, ex, tot, smi, ObeOpSum(), 0, 0);
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            if (k < n_tiles) {
+                const int first = icarry + ex[e];
+                unit_start[k] = first;
+                if (unit_tile)
+                    for (int u = 0; u < units[e]; ++u) unit_tile[first + u] = (int)k;
+            }
+            icarry += tot[e];
+        }
         __syncthreads();
-        obe_tile_scan_block<OBE_SCAN_THREADS / 32>(out_tile_sums, tiles_out, out_prefix, out_stats, 0, n_total, n_out,
-                                                  implicit, smd, 0);
     }
+    const int total_units = icarry;
+    if (t == 0) unit_start[n_tiles] = total_units;
 }
 
 // One work unit = (input tile k, chunk of <= 2048 consecutive output slots owned by that tile).
@@ -703,45 +715,31 @@ struct SysCtx {
 #ifndef OBE_RES_UNROLL
 #define OBE_RES_UNROLL 1
 #endif
-template <int D, class FT>
-__device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long Hk, long long Hk1, int rel_begin,
-                                         const FT& F, const double* sMean, double* sm, int* smx,
-                                         unsigned short* anc_s, double* xs, unsigned long long* bar,
-                                         unsigned int& phase, long long& staged_k) {
+// Phases 1-2 of a work unit: on return anc_s[q] is the in-tile index of the ancestor of the chunk's
+// slot q (before the clamp to the tile's last live particle), visible to the whole block.
+__device__ __forceinline__ void sys_unit_ancestors(const SysCtx& c, long long k, long long Hk, long long Hk1,
+                                                   int rel_begin, double* sm, int* smx, unsigned short* anc_s) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int span = (int)(Hk1 - Hk);
-    constexpr bool STAGE = (D <= OBE_STAGE_MAX_D);
-    const bool reload = STAGE && (staged_k != k);
-    if (reload && tid == 0) {
-        const long long base0 = k * OBE_TILE;
-        long long cnt = min(c.n_in, base0 + OBE_TILE) - base0;
-        cnt += (cnt & 1);                                  // 16-byte granules; the pad element exists (ld is even)
-        const unsigned row_bytes = (unsigned)cnt * 8u;
-        obe_mbar_expect_tx(bar, row_bytes * (unsigned)D);
-#pragma unroll
-        for (int j = 0; j < D; ++j)
-            obe_bulk_g2s(xs + j * OBE_TILE, c.pin + j * c.ld_in + c.in_base + base0, row_bytes, bar);
-    }
-    const int rel_end = min(rel_begin + OBE_OUT_CHUNK, span);
+    const int n_chunk = min(rel_begin + OBE_OUT_CHUNK, span) - rel_begin;
     // clear the marks (OBE_SPT per thread, 16-byte stores)
 #pragma unroll
     for (int v = 0; v < OBE_SPT / 8; ++v)
         *reinterpret_cast<uint4*>(&anc_s[tid * OBE_SPT + 8 * v]) = make_uint4(0u, 0u, 0u, 0u);
-    // ---- 1. end slot of every particle of the tile
+    // ---- 1. end slot of every particle of the tile, in chunk coordinates [0, n_chunk]
     double cn[OBE_EPT];
     tile_cdf_blocked(c.w_in, c.prefix, k, c.n_in, c.inv_total, cn, sm, c.cdf_offset, c.last_shard, c.wuni_in);
     const long long base = k * OBE_TILE;
-    const long long last = min(c.n_in, base + OBE_TILE) - 1;
+    const int lastrel = (int)(min(c.n_in, base + OBE_TILE) - 1 - base);
+    const double chunk0 = (double)(Hk + rel_begin);          // exact: < 2^53
     int r[OBE_EPT];
     int run = 0;
 #pragma unroll
     for (int e = 0; e < OBE_EPT; ++e) {
-        const long long i = base + (long long)tid * OBE_EPT + e;
-        int h;
-        if (i >= last) h = span;
-        else {
-            const double hd = comb_count_d(cn[e], c.u0, c.inv_n, c.nd, c.tol) - (double)Hk;     // exact: < 2^53
-            h = (hd < 0.0) ? 0 : (hd > (double)span ? span : (int)hd);
+        int h = n_chunk;                                     // the tile's last live particle owns the tail
+        if (tid * OBE_EPT + e < lastrel) {
+            const double hd = comb_count_d(cn[e], c.u0, c.inv_n, c.nd, c.tol) - chunk0;   // |hd| < 2^32
+            h = min(max(__double2int_rz(hd), 0), n_chunk);   // the conversion saturates
         }
         run = max(run, h);
         r[e] = run;
@@ -756,16 +754,13 @@ __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long
     if (lane == 0) ex = 0;
     if (lane == 31) smx[warp] = x;
     __syncthreads();                       // also orders the clearing of anc_s before the marks
-    for (int w2 = 0; w2 < warp; ++w2) ex = max(ex, smx[w2]);
-    // ---- 2. mark the first owned slot inside the chunk
+    ex = max(ex, obe_prev_warps_max8(smx, warp, lane));
+    // ---- 2. a particle that owns slots of the chunk marks the first of them
     int prev = ex;                         // end slot of the previous particle
 #pragma unroll
     for (int e = 0; e < OBE_EPT; ++e) {
         const int end = max(r[e], ex);
-        if (end > prev) {
-            const int head = max(prev, rel_begin);
-            if (head < rel_end && end > rel_begin) anc_s[head - rel_begin] = (unsigned short)(tid * OBE_EPT + e);
-        }
+        if (end > prev) anc_s[prev] = (unsigned short)(tid * OBE_EPT + e);
         prev = end;
     }
     __syncthreads();
@@ -795,7 +790,7 @@ __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long
         __syncthreads();                   // smx is reused
         if (lane == 31) smx[warp] = xm;
         __syncthreads();
-        for (int w2 = 0; w2 < warp; ++w2) exm = max(exm, smx[w2]);
+        exm = max(exm, obe_prev_warps_max8(smx, warp, lane));
 #pragma unroll
         for (int v = 0; v < OBE_SPT / 8; ++v) {
             unsigned int packed[4];
@@ -808,6 +803,31 @@ __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long
         }
     }
     __syncthreads();
+}
+
+template <int D, class FT>
+__device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long Hk, long long Hk1, int rel_begin,
+                                         const FT& F, const double* sMean, double* sm, int* smx,
+                                         unsigned short* anc_s, double* xs, unsigned long long* bar,
+                                         unsigned int& phase, long long& staged_k) {
+    const int tid = threadIdx.x;
+    const int span = (int)(Hk1 - Hk);
+    constexpr bool STAGE = (D <= OBE_STAGE_MAX_D);
+    const bool reload = STAGE && (staged_k != k);
+    if (reload && tid == 0) {
+        const long long base0 = k * OBE_TILE;
+        long long cnt = min(c.n_in, base0 + OBE_TILE) - base0;
+        cnt += (cnt & 1);                                  // 16-byte granules; the pad element exists (ld is even)
+        const unsigned row_bytes = (unsigned)cnt * 8u;
+        obe_mbar_expect_tx(bar, row_bytes * (unsigned)D);
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            obe_bulk_g2s(xs + j * OBE_TILE, c.pin + j * c.ld_in + c.in_base + base0, row_bytes, bar);
+    }
+    const int rel_end = min(rel_begin + OBE_OUT_CHUNK, span);
+    sys_unit_ancestors(c, k, Hk, Hk1, rel_begin, sm, smx, anc_s);
+    const long long base = k * OBE_TILE;
+    const long long last = min(c.n_in, base + OBE_TILE) - 1;
     // ---- 3. outputs in coalesced order.  Staged: gathers are shared-memory reads.  Unstaged: the
     //         ancestor of the NEXT slot is gathered before the RNG / jitter arithmetic of this one.
     const int n_out = rel_end - rel_begin;
@@ -866,22 +886,10 @@ __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long
     __syncthreads();
 }
 
-template <int D>
-__global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 3 : 2)) k_sys_resample(const ObeResampleArgs a) {
-    __shared__ double sF[D * D];
-    __shared__ double sMean[D];
-    __shared__ double sm[8];
-    __shared__ int smx[OBE_THREADS / 32];
-    __shared__ __align__(16) unsigned short anc_s[OBE_OUT_CHUNK];
-    __shared__ unsigned long long stage_bar;
-    extern __shared__ __align__(128) unsigned char obe_dyn_smem[];
-    double* xs = reinterpret_cast<double*>(obe_dyn_smem);
-    if (threadIdx.x == 0) { obe_mbar_init(&stage_bar, 1); obe_mbar_fence_init(); }
-    unsigned int phase = 0u;
-    long long staged_k = -1;
-    setup_factor<D>(a, sF, sMean);
+// The per-launch context of the single-cloud / sharded kernels, from by-value arguments or the device plan.
+__device__ __forceinline__ SysCtx sys_ctx_of(const ObeResampleArgs& a, long long& n_tiles_in) {
     const long long n_in = a.n_dev_in ? *a.n_dev_in : a.n;
-    const long long n_tiles_in = a.n_dev_in ? (n_in + OBE_TILE - 1) / OBE_TILE : a.n_tiles;
+    n_tiles_in = a.n_dev_in ? (n_in + OBE_TILE - 1) / OBE_TILE : a.n_tiles;
     const bool sharded = a.plan ? true : (a.sharded != 0);
     const double cdf_total = a.plan ? a.plan[OBE_PL_TOTAL] : a.cdf_total;
     const long long n_total = a.plan ? (long long)a.plan[OBE_PL_NTOTAL] : a.n_total;
@@ -900,20 +908,60 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 3 : 2)) k_sys_resample(
     c.idx_out = a.idx_out; c.z_out = a.z_out; c.mask_le = 0u; c.mask_lt = 0u;
     c.wuni_in = a.stats[OBE_ST_UNIFORM];
     if (a.implicit_out) c.w_out = nullptr;               // offspring weights stay implicit (1/n_total)
-    // the Liu-West factor in registers when it is small enough
-    double Fr[D <= 4 ? D * D : 1];
-    if (D <= 4) {
-#pragma unroll
-        for (int q = 0; q < D * D; ++q) Fr[D <= 4 ? q : 0] = sF[q];
+    return c;
+}
+
+// ---- two-kernel systematic resample ----------------------------------------------------------
+// A fused kernel (sys_unit, still used by the batched engine whose instances are a few tiles each)
+// spends ~3/4 of its instructions in phase 3 (gather, Philox, Box-Muller, Liu-West, store) but runs
+// it at the occupancy phases 1-2 dictate (barriers, shared-memory marks): 1.62 ms at 1e8 x 3.
+// Splitting at the ancestor array costs 8 bytes per particle of extra traffic (4 written, 4 read) and
+// buys a barrier-free elementwise second kernel at full occupancy with vector stores (0.45 + 0.87 ms):
+//   k_sys_ancestors : work units as above, phases 1-2, ancestors (uint32 input index) to global memory
+//   k_sys_move<D>   : V consecutive output slots per thread: ancestors -> gather -> jitter -> store
+#ifndef OBE_ANC_BLOCKS_PER_SM
+#define OBE_ANC_BLOCKS_PER_SM 5
+#endif
+__global__ void __launch_bounds__(OBE_THREADS, OBE_ANC_BLOCKS_PER_SM) k_sys_ancestors(const ObeResampleArgs a) {
+    __shared__ double sm[8];
+    __shared__ int smx[OBE_THREADS / 32];
+    __shared__ __align__(16) unsigned short anc_s[OBE_OUT_CHUNK];
+    __shared__ SysCtx cs;                  // in shared memory so that nothing of it is recomputed per unit
+    __shared__ int s_units;
+    if (threadIdx.x == 0) {
+        long long n_tiles_in;
+        cs = sys_ctx_of(a, n_tiles_in);
+        s_units = a.unit_start[n_tiles_in];
     }
-    const int n_units = a.unit_start[n_tiles_in];
-    // contiguous range of units per block: one binary search, then a forward walk over the tiles
-    const int per_block = (n_units + (int)gridDim.x - 1) / (int)gridDim.x;
+    __syncthreads();
+    const SysCtx& c = cs;
+    if (blockIdx.x == gridDim.x - 1) {
+        // One extra block, off the critical path: the offspring cloud has uniform weights 1/n_total, so
+        // its tile sums, CDF prefix and stats are known before a single particle is written (saves the
+        // fill + scan launches after the resample).
+        __shared__ double smd[OBE_SCANW * (OBE_THREADS / 32 + 1)];
+        const long long slot_end = a.plan ? (long long)a.plan[OBE_PL_SLOT1] : a.slot_end;
+        const long long n_out = slot_end - c.slot_begin;
+        const long long tiles_out = (n_out + OBE_TILE - 1) / OBE_TILE;
+        const long long n_total = (long long)c.nd;
+        for (long long k = threadIdx.x; k < tiles_out; k += OBE_THREADS) {
+            const long long cnt = min((long long)OBE_TILE, n_out - k * OBE_TILE);
+            a.out_tile_sums[k] = (double)cnt * c.wv;
+        }
+        __threadfence_block();
+        __syncthreads();
+        obe_tile_scan_block<OBE_THREADS / 32>(a.out_tile_sums, tiles_out, a.out_prefix, a.out_stats, 0, n_total, n_out,
+                                              a.implicit_out, smd, 0);
+        return;
+    }
+    const int n_units = s_units;
+    const int n_work_blocks = (int)gridDim.x - 1;
+    const int per_block = (n_units + n_work_blocks - 1) / n_work_blocks;
     const int unit_lo = min((int)blockIdx.x * per_block, n_units);
     const int unit_hi = min(unit_lo + per_block, n_units);
     int k32 = 0;
-    if (unit_lo < unit_hi) {
-        int lo = 0, hi = (int)n_tiles_in;      // first k with unit_start[k] > unit_lo
+    if (!a.unit_tile && unit_lo < unit_hi) {   // no unit -> tile map: binary search, then a forward walk
+        int lo = 0, hi = (int)((c.n_in + OBE_TILE - 1) / OBE_TILE);
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (a.unit_start[mid] <= unit_lo) lo = mid + 1; else hi = mid;
@@ -921,13 +969,104 @@ __global__ void __launch_bounds__(OBE_THREADS, (D <= 4 ? 3 : 2)) k_sys_resample(
         k32 = lo - 1;
     }
     for (int unit = unit_lo; unit < unit_hi; ++unit) {
-        while (a.unit_start[k32 + 1] <= unit) ++k32;      // largest k with unit_start[k] <= unit
-        const long long k = k32;
+        if (a.unit_tile) k32 = a.unit_tile[unit];
+        else while (a.unit_start[k32 + 1] <= unit) ++k32;
+        const int k = k32;
+        const long long Hk = a.plan_h[k], Hk1 = a.plan_h[k + 1];
         const int rel_begin = (unit - a.unit_start[k]) * OBE_OUT_CHUNK;
-        if (D <= 4) sys_unit<D>(c, k, a.plan_h[k], a.plan_h[k + 1], rel_begin, Fr, sMean, sm, smx, anc_s, xs, &stage_bar,
-                                phase, staged_k);
-        else sys_unit<D>(c, k, a.plan_h[k], a.plan_h[k + 1], rel_begin, sF, sMean, sm, smx, anc_s, xs, &stage_bar, phase,
-                         staged_k);
+        sys_unit_ancestors(c, k, Hk, Hk1, rel_begin, sm, smx, anc_s);
+        const unsigned int base = (unsigned int)k * OBE_TILE;
+        const int lastrel = (int)(min(c.n_in, (long long)base + OBE_TILE) - 1 - (long long)base);
+        const long long o0 = Hk + rel_begin - c.slot_begin;
+        const long long room = c.cap_out - o0;                 // capacity overflow is flagged in the plan
+        int n_out = min(rel_begin + OBE_OUT_CHUNK, (int)(Hk1 - Hk)) - rel_begin;
+        if (room < (long long)n_out) n_out = room > 0 ? (int)room : 0;
+        unsigned int* __restrict__ dst = a.anc + o0;
+        for (int q = threadIdx.x; q < n_out; q += OBE_THREADS) dst[q] = base + (unsigned int)min((int)anc_s[q], lastrel);
+        __syncthreads();
+    }
+}
+
+#ifndef OBE_MOVE_V
+#define OBE_MOVE_V 4
+#endif
+#define OBE_MOVE_BLOCKS(d) ((d) <= 3 ? 4 : ((d) == 4 ? 3 : 2))   /* resident CTAs per SM the registers allow */
+template <int D>
+__global__ void __launch_bounds__(OBE_THREADS, OBE_MOVE_BLOCKS(D)) k_sys_move(const ObeResampleArgs a) {
+    constexpr int V = OBE_MOVE_V;
+    __shared__ double sF[D * D];
+    __shared__ double sMean[D];
+    setup_factor<D>(a, sF, sMean);
+    double Fr[D <= 4 ? D * D : 1];
+    if (D <= 4) {
+#pragma unroll
+        for (int q = 0; q < D * D; ++q) Fr[D <= 4 ? q : 0] = sF[q];
+    }
+    const long long slot_begin = a.plan ? (long long)a.plan[OBE_PL_SLOT0] : a.slot_begin;
+    long long n_out = a.plan ? (long long)a.plan[OBE_PL_SLOT1] - slot_begin : a.slot_end - a.slot_begin;
+    if (a.plan && n_out > a.cap_out) n_out = a.cap_out;
+    const long long n_groups = (n_out + V - 1) / V;
+    for (long long g = (long long)blockIdx.x * OBE_THREADS + threadIdx.x; g < n_groups;
+         g += (long long)gridDim.x * OBE_THREADS) {
+        const long long o0 = g * V;
+        const bool full = o0 + V <= n_out;
+        unsigned int anc[V];
+        if (full) {
+            if (V == 2) {
+                const uint2 t = *reinterpret_cast<const uint2*>(a.anc + o0);
+                anc[0] = t.x; anc[V > 1 ? 1 : 0] = t.y;
+            } else if (V == 4) {
+                const uint4 t = *reinterpret_cast<const uint4*>(a.anc + o0);
+                anc[0] = t.x; anc[V > 1 ? 1 : 0] = t.y; anc[V > 2 ? 2 : 0] = t.z; anc[V > 3 ? 3 : 0] = t.w;
+            } else {
+#pragma unroll
+                for (int u = 0; u < V; ++u) anc[u] = a.anc[o0 + u];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < V; ++u) anc[u] = (o0 + u < n_out) ? a.anc[o0 + u] : a.anc[o0];
+        }
+        double xv[V][D], z[V][D];
+        long long og[V];
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            og[u] = slot_begin + o0 + u;
+#pragma unroll
+            for (int j = 0; j < D; ++j) xv[u][j] = __ldg(a.pin + j * a.ld_in + anc[u]);
+        }
+        if (a.jitter) {
+            device_normals_vec<D, V>(og, a.seed, a.epoch, z);
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                if (a.z_out && o0 + u < n_out) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) a.z_out[(o0 + u) * D + j] = z[u][j];
+                }
+                if (D <= 4) liu_west<D>(xv[u], z[u], Fr, sMean, a.a_param, a.scale);
+                else liu_west<D>(xv[u], z[u], sF, sMean, a.a_param, a.scale);
+            }
+        }
+        if (full && (V == 2 || V == 4)) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+#pragma unroll
+                for (int u = 0; u < V; u += 2)
+                    *reinterpret_cast<double2*>(a.pout + j * a.ld_out + o0 + u) = make_double2(xv[u][j], xv[u + 1 < V ? u + 1 : u][j]);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                if (o0 + u < n_out) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) a.pout[j * a.ld_out + o0 + u] = xv[u][j];
+                }
+            }
+        }
+        if (a.idx_out) {
+#pragma unroll
+            for (int u = 0; u < V; ++u)
+                if (o0 + u < n_out) a.idx_out[o0 + u] = (long long)anc[u];
+        }
     }
 }
 
@@ -1162,6 +1301,20 @@ __global__ void k_shard_plan(const double* __restrict__ gathered, int rank, int 
         OBE_DIM_CASE(6, KERNEL, grid, st, args)                                       \
         OBE_DIM_CASE(7, KERNEL, grid, st, args)                                       \
         OBE_DIM_CASE(8, KERNEL, grid, st, args)                                       \
+        default: return obe_fail("n_params must be 1..8%s%s");                        \
+    }
+
+#define OBE_DIM_CASE_PLAIN(dd, KERNEL, grid, st, args) case dd: KERNEL<dd><<<grid, OBE_THREADS, 0, st>>>(args); break;
+#define OBE_DIM_SWITCH_PLAIN(d, KERNEL, grid, st, args)                               \
+    switch (d) {                                                                      \
+        OBE_DIM_CASE_PLAIN(1, KERNEL, grid, st, args)                                 \
+        OBE_DIM_CASE_PLAIN(2, KERNEL, grid, st, args)                                 \
+        OBE_DIM_CASE_PLAIN(3, KERNEL, grid, st, args)                                 \
+        OBE_DIM_CASE_PLAIN(4, KERNEL, grid, st, args)                                 \
+        OBE_DIM_CASE_PLAIN(5, KERNEL, grid, st, args)                                 \
+        OBE_DIM_CASE_PLAIN(6, KERNEL, grid, st, args)                                 \
+        OBE_DIM_CASE_PLAIN(7, KERNEL, grid, st, args)                                 \
+        OBE_DIM_CASE_PLAIN(8, KERNEL, grid, st, args)                                 \
         default: return obe_fail("n_params must be 1..8%s%s");                        \
     }
 
@@ -1721,9 +1874,40 @@ int obe_gather_jitter(const obe_cloud_t* in, const obe_cloud_t* out, const int64
     int64_t blocks = (in->n + OBE_THREADS - 1) / OBE_THREADS;
     if (blocks > (int64_t)obe_sms() * 8) blocks = (int64_t)obe_sms() * 8;
     const int grid = (int)blocks;
-    OBE_DIM_SWITCH(in->d, k_gather_jitter, grid, st, a)
+    OBE_DIM_SWITCH_PLAIN(in->d, k_gather_jitter, grid, st, a)
     OBE_LAUNCH_CHECK("k_gather_jitter");
     return finish_resample(out, out->n, st);
+}
+
+// the unit -> tile map lives in the input cloud's scratch, which is sized for in->n particles
+static bool unit_map_fits(const obe_cloud_t* in, int64_t out_cap) {
+    const int64_t nt = (in->n + OBE_TILE - 1) / OBE_TILE;
+    return nt + (out_cap + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK <= nt + in->n / OBE_OUT_CHUNK_HOST + 4;
+}
+
+// k_sys_ancestors + k_sys_move, after k_sys_plan
+static int launch_sys_resample(const obe_cloud_t* in, const obe_cloud_t* out, ObeResampleArgs& a, int64_t out_cap,
+                               cudaStream_t st) {
+    const int64_t max_units = a.n_tiles + (out_cap + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK;
+    if (in->n >= (1ll << 32)) return obe_fail("systematic resample supports shards of < 2^32 particles%s%s");
+    a.anc = scratch_of(out).anc;
+    a.out_tile_sums = out->tile_sums_dev; a.out_prefix = out->tile_prefix_dev; a.out_stats = out->stats_dev;
+    {
+        int64_t g = (int64_t)obe_sms() * OBE_ANC_BLOCKS_PER_SM;
+        if (g > max_units) g = max_units;
+        k_sys_ancestors<<<(int)g + 1, OBE_THREADS, 0, st>>>(a);    // + the bookkeeping block
+        OBE_LAUNCH_CHECK("k_sys_ancestors");
+    }
+    {
+        int64_t g = (out_cap + (int64_t)OBE_THREADS * OBE_MOVE_V - 1) / ((int64_t)OBE_THREADS * OBE_MOVE_V);
+        const int64_t gmax = (int64_t)obe_sms() * OBE_MOVE_BLOCKS(in->d) * 4;
+        if (g > gmax) g = gmax;
+        if (g < 1) g = 1;
+        const int grid = (int)g;
+        OBE_DIM_SWITCH_PLAIN(in->d, k_sys_move, grid, st, a)
+        OBE_LAUNCH_CHECK("k_sys_move");
+    }
+    return 0;
 }
 
 static int resample_systematic_impl(const obe_cloud_t* in, const obe_cloud_t* out, double u0, const double* factor,
@@ -1739,22 +1923,16 @@ static int resample_systematic_impl(const obe_cloud_t* in, const obe_cloud_t* ou
     if (sharded && !factor) return obe_fail("sharded resample needs the (global) factor from the host%s%s");
     const Scratch s = scratch_of(in);
     a.plan_h = s.plan_h; a.unit_start = s.unit_start; a.u0 = u0;
+    a.unit_tile = unit_map_fits(in, out->n) ? s.unit_tile : nullptr;
     a.idx_out = (long long*)idx_out_dev; a.z_out = z_out_dev; a.implicit_out = 1;
     a.sharded = sharded; a.last_shard = last_shard; a.n_total = n_total;
     a.slot_begin = slot_begin; a.slot_end = slot_end; a.cdf_offset = cdf_offset; a.cdf_total = cdf_total;
     cudaStream_t st = (cudaStream_t)stream;
     k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, u0, sharded ? cdf_offset : 0.0,
                                               sharded ? cdf_total : 0.0, slot_begin, slot_end, s.plan_h, s.unit_start,
-                                              nullptr, nullptr, out->tile_sums_dev, out->tile_prefix_dev, out->stats_dev,
-                                              1);
+                                              (int*)a.unit_tile, nullptr, nullptr);
     OBE_LAUNCH_CHECK("k_sys_plan");
-    int64_t max_units = a.n_tiles + (out->n + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK;
-    int64_t g = (int64_t)obe_sms() * OBE_BLOCKS_PER_SM;
-    if (g > max_units) g = max_units;
-    const int grid = (int)g;
-    OBE_DIM_SWITCH(in->d, k_sys_resample, grid, st, a)
-    OBE_LAUNCH_CHECK("k_sys_resample");
-    return 0;
+    return launch_sys_resample(in, out, a, out->n, st);
 }
 
 int obe_resample_systematic(const obe_cloud_t* in, const obe_cloud_t* out, double u0, const double* factor,
@@ -1799,20 +1977,14 @@ int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* ou
     if (fill_resample_args(in, out, dummy, dummy, a_param, scale, seed, epoch, a)) return -1;
     const Scratch s = scratch_of(in);
     a.plan_h = s.plan_h; a.unit_start = s.unit_start;
+    a.unit_tile = unit_map_fits(in, out->ld) ? s.unit_tile : nullptr;
     a.plan = plan_dev; a.n_dev_in = (const long long*)in->n_dev; a.cap_out = out->ld;
     a.sharded = 1; a.n_total = n_total; a.implicit_out = 1;
     cudaStream_t st = (cudaStream_t)stream;
     k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0, s.plan_h,
-                                              s.unit_start, (const long long*)in->n_dev, plan_dev, out->tile_sums_dev,
-                                              out->tile_prefix_dev, out->stats_dev, 1);
+                                              s.unit_start, (int*)a.unit_tile, (const long long*)in->n_dev, plan_dev);
     OBE_LAUNCH_CHECK("k_sys_plan");
-    int64_t max_units = a.n_tiles + (out->ld + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK;
-    int64_t g = (int64_t)obe_sms() * OBE_BLOCKS_PER_SM;
-    if (g > max_units) g = max_units;
-    const int grid = (int)g;
-    OBE_DIM_SWITCH(in->d, k_sys_resample, grid, st, a)
-    OBE_LAUNCH_CHECK("k_sys_resample");
-    return 0;
+    return launch_sys_resample(in, out, a, out->ld, st);
 }
 
 int64_t obe_comb_count(double c, double u0, int64_t n_total) {

@@ -529,23 +529,84 @@ __device__ __forceinline__ double obe_block_excl_sum(double v, double* sm, doubl
     return base + ex;
 }
 
+// W chunks of NW*32 consecutive elements scanned at once: ex[e] = exclusive scan of v[e] over the
+// block's threads within chunk e (Kogge-Stone over lanes, then over the warp totals), tot[e] = the
+// chunk's total.  One set of barriers serves all W chunks, so a single block walks a long array in
+// 1/W of the latency-bound rounds.  sm: W * (NW + 1) elements.  Needs NW >= W.
+#define OBE_SCANW 8
+struct ObeOpSum { template <class T> __device__ __forceinline__ T operator()(T a, T b) const { return a + b; } };
+struct ObeOpMax { template <class T> __device__ __forceinline__ T operator()(T a, T b) const { return a > b ? a : b; } };
+template <class T, int NW, class Op>
+__device__ __forceinline__ void obe_block_excl_scanw(const T (&v)[OBE_SCANW], T (&ex)[OBE_SCANW], T (&tot)[OBE_SCANW],
+                                                     T* sm, Op op, T ident, int bar_id) {
+    constexpr int W = OBE_SCANW;
+    const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) % NW;
+    T x[W];
+#pragma unroll
+    for (int e = 0; e < W; ++e) x[e] = v[e];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+            const T y = __shfl_up_sync(0xffffffffu, x[e], o);
+            if (lane >= o) x[e] = op(x[e], y);
+        }
+    }
+    obe_named_bar(bar_id, NW * 32);
+    if (lane == 31) {
+#pragma unroll
+        for (int e = 0; e < W; ++e) sm[e * (NW + 1) + warp] = x[e];
+    }
+    obe_named_bar(bar_id, NW * 32);
+    if (warp < W) {
+        T* row = sm + warp * (NW + 1);
+        T xs = (lane < NW) ? row[lane] : ident;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const T y = __shfl_up_sync(0xffffffffu, xs, o);
+            if (lane >= o) xs = op(xs, y);
+        }
+        T exs = __shfl_up_sync(0xffffffffu, xs, 1);      // exclusive base of each warp
+        if (lane == 0) exs = ident;
+        if (lane < NW) row[lane] = exs;
+        if (lane == 31) row[NW] = xs;
+    }
+    obe_named_bar(bar_id, NW * 32);
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+        T exl = __shfl_up_sync(0xffffffffu, x[e], 1);
+        if (lane == 0) exl = ident;
+        ex[e] = op(sm[e * (NW + 1) + warp], exl);
+        tot[e] = sm[e * (NW + 1) + NW];
+    }
+}
+
 // tile_prefix[k] = sum of tile_sums[0..k) in a fixed association (coalesced chunks of NW*32 with a running
-// carry); tile_prefix[n_tiles] is THE total every CDF consumer divides by.  One block.  Also finishes the
-// stats block: canonical total, normaliser, N_eff (and the uniform-weights bookkeeping after a resample).
+// carry, OBE_SCANW chunks per round); tile_prefix[n_tiles] is THE total every CDF consumer divides by.
+// One block.  Also finishes the stats block: canonical total, normaliser, N_eff (and the uniform-weights
+// bookkeeping after a resample).  sm: OBE_SCANW * (NW + 1) doubles.
 template <int NW>
 __device__ __forceinline__ void obe_tile_scan_block(const double* __restrict__ tile_sums, long long n_tiles,
                                                     double* __restrict__ prefix, double* __restrict__ stats,
                                                     int renormalise, long long uniform, long long n, int implicit,
                                                     double* sm, int bar_id) {
-    const int t = threadIdx.x % (NW * 32);
+    constexpr int T_ = NW * 32;
+    const int t = threadIdx.x % T_;
     double carry = 0.0;
-    for (long long base = 0; base < n_tiles; base += NW * 32) {
-        const long long k = base + t;
-        const double v = (k < n_tiles) ? __ldcg(tile_sums + k) : 0.0;
-        double tot;
-        const double ex = obe_block_excl_sum<NW>(v, sm, &tot, bar_id);
-        if (k < n_tiles) prefix[k] = carry + ex;
-        carry += tot;
+    for (long long base = 0; base < n_tiles; base += OBE_SCANW * T_) {
+        double v[OBE_SCANW], ex[OBE_SCANW], tot[OBE_SCANW];
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * T_ + t;
+            v[e] = (k < n_tiles) ? __ldcg(tile_sums + k) : 0.0;
+        }
+        obe_block_excl_scanw<double, NW>(v, ex, tot, sm, ObeOpSum(), 0.0, bar_id);
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * T_ + t;
+            if (k < n_tiles) prefix[k] = carry + ex[e];
+            carry += tot[e];
+        }
         obe_named_bar(bar_id, NW * 32);
     }
     const double total = carry;
@@ -812,8 +873,8 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
     // the last block also turns the tile sums into the CDF prefix and finishes the stats block (saves a launch)
     obe_named_bar(1, OBE_CONSUMER_THREADS);
     __threadfence();
-    obe_tile_scan_block<OBE_CONSUMER_WARPS>(a.tile_sums, n_tiles, a.tile_prefix, a.stats, a.renormalise, 0, n, 0, fin,
-                                            1);
+    obe_tile_scan_block<OBE_CONSUMER_WARPS>(a.tile_sums, n_tiles, a.tile_prefix, a.stats, a.renormalise, 0, n, 0,
+                                            &accsm[0][0], 1);
 }
 
 // ---------------------------------------------------------------------------------------------
