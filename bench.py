@@ -359,7 +359,10 @@ def main():
         return
     peak, peak_src = measured_peak()
     d = 3
-    b_upd = 8.0 * n_total * (d + 2)
+    # The resample is forced every cycle, so the update always finds the offspring's implicit uniform weights
+    # (never stored, never read): it moves d particle rows in and one weight row out, 8N(d+1), not the 8N(d+2)
+    # of an update that follows an update.
+    b_upd = 8.0 * n_total * (d + 1)
     b_res = 8.0 * n_total * (2 * d + 2)
     b_sel = 8.0 * args.settings * 2
     b_cycle = b_upd + b_res + b_sel
@@ -375,7 +378,10 @@ def main():
                 'note': 'record, pivot and uniforms travel as kernel arguments; stats block + argmax come back'},
         'gpu_launches': (6 if world == 1 else 7) * args.steps,   # update, plan, ancestors, move, draw, utility (+ shard plan)
         'roofline': {'bound': 'hbm', 'kernel': 'resample step = k_sys_plan + k_sys_ancestors + k_sys_move (one event bracket)',
-                     'achieved': gbs_res, 'peak': peak, 'unit': 'GB/s', 'frac': gbs_res / peak, 'traffic': None,
+                     'achieved': gbs_res, 'peak': peak, 'unit': 'GB/s', 'frac': gbs_res / peak,
+                     # dram__bytes_read+write of the three kernels, ncu --set full (profiles/r1_final_ncu_summary.md):
+                     # 63.8 bytes per particle at d = 3
+                     'traffic': 63.8 * n_total / world if d == 3 else None,
                      'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': b_res / world},
         'kernels_ms': {'update': t_upd, 'resample': t_res, 'draw+utility+argmax': t_sel},

@@ -148,8 +148,10 @@ int obe_draw(const obe_cloud_t* c, const double* u_host, int k, double* draws_de
 int obe_gather_jitter(const obe_cloud_t* in, const obe_cloud_t* out, const int64_t* idx_dev,
                       const double* factor, const double* mean, const double* z_dev, uint64_t seed,
                       uint32_t epoch, double a_param, int scale, void* stream);
-/* Fused systematic resample (fast path): comb u_i = (i + u0)/n searched in the canonical CDF,
- * gather, jitter, weight reset, in one pass and with coalesced writes.  factor/mean NULL =>
+/* Systematic resample (fast path): comb u_i = (i + u0)/n searched in the canonical CDF (plan +
+ * ancestors kernels; the uint32 ancestors live in out->scratch_dev), then gather, jitter, implicit
+ * weight reset in one elementwise kernel with coalesced writes.  Shards of < 2^32 particles.
+ * factor/mean NULL =>
  * Cholesky factor of (1-a^2)*cov and the mean are taken from in->stats_dev on the device.
  * idx_out_dev / z_out_dev (optional) receive the ancestors and the normals used. */
 int obe_resample_systematic(const obe_cloud_t* in, const obe_cloud_t* out, double u0,
@@ -158,7 +160,7 @@ int obe_resample_systematic(const obe_cloud_t* in, const obe_cloud_t* out, doubl
                             void* stream);
 
 /* ---- sharded clouds (one process per GPU; particles split into contiguous shards) ---------- */
-/* The same fused kernel for one shard of a cloud of n_total particles: this shard's particles own
+/* The same kernels for one shard of a cloud of n_total particles: this shard's particles own
  * the global comb slots [slot_begin, slot_end) (= out->n of them, which may differ from in->n: shard
  * lengths float, no particle ever crosses NVLink); cdf_offset = summed weight of the lower-ranked
  * shards, cdf_total = global weight; factor/mean are the GLOBAL Liu-West factor and mean (host).
