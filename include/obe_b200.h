@@ -219,6 +219,15 @@ int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* set
  * uniform.  idx_dev: int64. */
 int obe_pick(const double* utility_dev, int64_t n_settings, double pickiness, double u,
              int64_t* idx_dev, void* select_scratch_dev, void* stream);
+/* Sweeper selection (demos/sweeper/obe_sweeper.py:118-162, sweep_utility + opt_setting): cumsum of the
+ * point utility along the swept setting; every (start, stop) pair of setting indices is worth
+ * (cum[stop] - cum[start]) / ((stop - start) + cost_of_new_sweep); argmax with np.argmax semantics.
+ * pairs_dev: (n_pairs, 2) int32 = start_stop_indices; cumsum_dev: (n_settings) out;
+ * pair_utility_dev: (n_pairs) out or NULL; best_dev: int64 pair index then double value (16 bytes).
+ * The pair utilities are a plain device vector: obe_pick on them is the sweeper's good_setting. */
+int obe_sweep_utility(const double* utility_dev, int64_t n_settings, const int32_t* pairs_dev,
+                      int64_t n_pairs, double cost_of_new_sweep, double* cumsum_dev,
+                      double* pair_utility_dev, void* best_dev, void* select_scratch_dev, void* stream);
 /* eval_over_all_parameters (obe_base.py:298-320) -> y_dev (C, ldy) */
 int obe_eval_parameters(obe_model_t m, const obe_cloud_t* c, const double* setting,
                         const double* constants, double* y_dev, int64_t ldy, void* stream);

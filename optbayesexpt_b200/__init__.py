@@ -9,5 +9,6 @@ from .models import DeviceModel, builtin, cuda_source  # noqa: F401
 from .particlepdf import ParticlePDF  # noqa: F401
 from .obe_base import OptBayesExpt  # noqa: F401
 from .obe_noiseparam import OptBayesExptNoiseParameter  # noqa: F401
+from .obe_sweeper import OptBayesExptSweeper  # noqa: F401
 
 __version__ = '0.1.0'

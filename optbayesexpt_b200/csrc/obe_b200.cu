@@ -1319,6 +1319,73 @@ __global__ void k_shard_plan(const double* __restrict__ gathered, int rank, int 
     }
 
 // ---------------------------------------------------------------------------------------------
+// Sweeper selection (demos/sweeper/obe_sweeper.py:118-162): a sweep from setting index `start` to
+// `stop` is worth the point utility integrated along the sweep, divided by its cost:
+//   cum = cumsum(U);  U_pair = (cum[stop] - cum[start]) / ((stop - start) + cost_of_new_sweep)
+// k_cumsum: one CTA, inclusive scan in coalesced chunks (fixed association, 8 chunks per round).
+// k_sweep_pairs: one thread per (start, stop) pair + fused argmax (np.argmax semantics).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OBE_SCAN_THREADS) k_cumsum(const double* __restrict__ v_in, long long n,
+                                                             double* __restrict__ cum) {
+    __shared__ double sm[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
+    const int t = threadIdx.x;
+    double carry = 0.0;
+    for (long long base = 0; base < n; base += OBE_SCANW * OBE_SCAN_THREADS) {
+        double v[OBE_SCANW], ex[OBE_SCANW], tot[OBE_SCANW];
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            v[e] = (k < n) ? v_in[k] : 0.0;
+        }
+        obe_block_excl_scanw<double, OBE_SCAN_THREADS / 32>(v, ex, tot, sm, ObeOpSum(), 0.0, 0);
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            if (k < n) cum[k] = (carry + ex[e]) + v[e];
+            carry += tot[e];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(OBE_THREADS) k_sweep_pairs(const double* __restrict__ cum, long long n_settings,
+                                                             const int* __restrict__ pairs, long long n_pairs,
+                                                             double cost_new, double* __restrict__ pair_utility,
+                                                             double* part_val, long long* part_idx,
+                                                             unsigned int* counter, long long* best_idx,
+                                                             double* best_val) {
+    __shared__ double bval[OBE_THREADS / 32];
+    __shared__ long long bidx[OBE_THREADS / 32];
+    __shared__ unsigned int is_last;
+    const int tid = threadIdx.x;
+    double best = 0.0;
+    long long besti = -1;
+    for (long long p = (long long)blockIdx.x * OBE_THREADS + tid; p < n_pairs; p += (long long)gridDim.x * OBE_THREADS) {
+        const int2 se = *reinterpret_cast<const int2*>(pairs + 2 * p);
+        const double cost = obe_add((double)(se.y - se.x), cost_new);
+        const double u = obe_div(obe_sub(cum[se.y], cum[se.x]), cost);
+        if (pair_utility) pair_utility[p] = u;
+        obe_argmax_take(best, besti, u, p);
+    }
+    obe_block_argmax(best, besti, bval, bidx);
+    if (tid == 0) {
+        part_val[blockIdx.x] = best;
+        part_idx[blockIdx.x] = besti;
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    best = 0.0; besti = -1;
+    for (unsigned int b = tid; b < gridDim.x; b += blockDim.x)
+        obe_argmax_take(best, besti, __ldcg(part_val + b), __ldcg(part_idx + b));
+    __syncthreads();
+    obe_block_argmax(best, besti, bval, bidx);
+    if (tid == 0) { *best_idx = besti; *best_val = best; *counter = 0u; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // good_setting: p_j = nan_to_num(U_j ** pickiness) as a weight vector with tile sums
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(OBE_THREADS) k_pick_weights(const double* __restrict__ util, long long n,
@@ -2058,6 +2125,26 @@ int obe_pick(const double* utility_dev, int64_t n_settings, double pickiness, do
     k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(s.tile_sums, nt, s.prefix, nullptr, 0, 0, n_settings);
     OBE_LAUNCH_CHECK("k_tile_scan");
     return draw_impl(s.p, s.prefix, n_settings, nullptr, 0, 0, &u, 1, nullptr, idx_dev, st);
+}
+
+int obe_sweep_utility(const double* utility_dev, int64_t n_settings, const int32_t* pairs_dev, int64_t n_pairs,
+                      double cost_of_new_sweep, double* cumsum_dev, double* pair_utility_dev, void* best_dev,
+                      void* select_scratch_dev, void* stream) {
+    if (!utility_dev || !pairs_dev || !cumsum_dev || !best_dev || !select_scratch_dev)
+        return obe_fail("null argument%s%s");
+    if (n_settings < 1 || n_pairs < 1) return obe_fail("sweep utility: empty settings or pairs%s%s");
+    if (obe_sms() <= 0) return obe_fail("no CUDA device: this library has no CPU fallback%s%s");
+    const SelectScratch s = select_scratch_of(select_scratch_dev, n_settings);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_cumsum<<<1, OBE_SCAN_THREADS, 0, st>>>(utility_dev, n_settings, cumsum_dev);
+    OBE_LAUNCH_CHECK("k_cumsum");
+    int64_t blocks = (n_pairs + OBE_THREADS - 1) / OBE_THREADS;
+    if (blocks > (int64_t)obe_sms() * 8) blocks = (int64_t)obe_sms() * 8;
+    k_sweep_pairs<<<(int)blocks, OBE_THREADS, 0, st>>>(cumsum_dev, n_settings, pairs_dev, n_pairs, cost_of_new_sweep,
+                                                      pair_utility_dev, s.part_val, s.part_idx, s.counter,
+                                                      (long long*)best_dev, (double*)((char*)best_dev + 8));
+    OBE_LAUNCH_CHECK("k_sweep_pairs");
+    return 0;
 }
 
 int obe_eval_parameters(obe_model_t m, const obe_cloud_t* c, const double* setting, const double* constants,

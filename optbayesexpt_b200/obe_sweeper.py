@@ -1,0 +1,138 @@
+"""OptBayesExptSweeper on the GPU (reference: demos/sweeper/obe_sweeper.py, v1.2.0).
+
+For instruments that sweep a setting: the design half proposes (start, stop) index pairs into the
+first setting array, the inference half digests the array of values a sweep returned.  The point
+utility never leaves the device: ``obe_sweep_utility`` integrates it along the swept setting
+(cumsum), evaluates every (start, stop) pair and takes the argmax in two launches.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .obe_noiseparam import OptBayesExptNoiseParameter
+
+try:
+    rng = np.random.default_rng()        # module-level Generator, as in the reference (obe_sweeper.py:3-6)
+except AttributeError:                   # pragma: no cover
+    rng = np.random
+
+
+class OptBayesExptSweeper(OptBayesExptNoiseParameter):
+    """An OptBayesExpt class for instruments that sweep a parameter (obe_sweeper.py:9-85).
+
+    Same constructor as the reference.  Attributes: ``sweep_settings``, ``start_stop_subsample`` (3),
+    ``start_stop_indices`` (P, 2), ``start_stop_choice_indices``, ``start_stop_values``,
+    ``cost_of_new_sweep`` (5.0).
+    """
+
+    def __init__(self, model_function, setting_values, parameter_samples, constants, noise_parameter_index,
+                 **kwargs):
+        OptBayesExptNoiseParameter.__init__(self, model_function, setting_values, parameter_samples, constants,
+                                            noise_parameter_index=noise_parameter_index, **kwargs)
+        self.sweep_settings = np.asarray(setting_values[0])
+        self.start_stop_subsample = 3
+        self.start_stop_indices = self._generate_start_stop_indices()
+        self.start_stop_choice_indices = np.arange(len(self.start_stop_indices), dtype=int)
+        self.start_stop_values = self.sweep_settings[self.start_stop_indices]
+        self.cost_of_new_sweep = 5.
+        self._pairs_host = None
+        self._pairs_dev = None
+
+    # ---- inference half
+    def pdf_update(self, measurement_record):
+        """One noise-parameter ``pdf_update`` per point of the sweep (obe_sweeper.py:87-101); the resample
+        test runs after every point, exactly as in the reference."""
+        (setting_values,), result_values = measurement_record
+        out = None
+        for setting, result in zip(setting_values, result_values):
+            out = OptBayesExptNoiseParameter.pdf_update(self, ((setting,), result))
+        return out
+
+    # ---- design half
+    def cost_estimate(self):
+        """Pointwise costs are uniform along the sweep (obe_sweeper.py:103-105)."""
+        return 1.0
+
+    def sweep_cost_estimate(self):
+        """(stop - start) + cost_of_new_sweep per pair (obe_sweeper.py:107-121)."""
+        return self.start_stop_indices[:, 1] - self.start_stop_indices[:, 0] + self.cost_of_new_sweep
+
+    def _sync_pairs(self):
+        """Device copy of ``start_stop_indices`` (int32), refreshed when the attribute was replaced."""
+        torch = self._torch
+        pairs = np.ascontiguousarray(np.asarray(self.start_stop_indices, dtype=np.int32))
+        if pairs.ndim != 2 or pairs.shape[1] != 2 or len(pairs) == 0:
+            raise ValueError('start_stop_indices must have shape (n_pairs, 2)')
+        n_set = len(self.setting_indices)
+        if pairs.min() < 0 or pairs.max() >= n_set:
+            raise ValueError('start_stop_indices out of range of the swept setting')
+        if self._pairs_host is None or self._pairs_host.shape != pairs.shape or not np.array_equal(self._pairs_host, pairs):
+            dev = self._buf.device
+            self._pairs_host = pairs.copy()
+            self._pairs_dev = torch.from_numpy(pairs).to(dev)
+            self._cumsum_dev = torch.empty(n_set, dtype=torch.float64, device=dev)
+            self._pair_utility_dev = torch.empty(len(pairs), dtype=torch.float64, device=dev)
+            self._pair_best_dev = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._pair_best_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+            self._pair_pick_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._pair_scratch = torch.zeros(int(self._lib.obe_select_scratch_bytes(len(pairs))), dtype=torch.uint8,
+                                             device=dev)
+        return len(pairs)
+
+    def _sweep_utility_dev_run(self):
+        """point utility -> cumsum -> pair utilities + argmax, all on the device."""
+        n_pairs = self._sync_pairs()
+        self._utility_dev_run()
+        self._check(self._lib.obe_sweep_utility(
+            C.c_void_p(self._utility_dev.data_ptr()), len(self.setting_indices), C.c_void_p(self._pairs_dev.data_ptr()),
+            n_pairs, float(self.cost_of_new_sweep), C.c_void_p(self._cumsum_dev.data_ptr()),
+            C.c_void_p(self._pair_utility_dev.data_ptr()), C.c_void_p(self._pair_best_dev.data_ptr()),
+            C.c_void_p(self._select_scratch.data_ptr()), self._stream()))
+        return n_pairs
+
+    def sweep_utility(self):
+        """Utility of every (start, stop) pair as a numpy array (obe_sweeper.py:123-151)."""
+        self._sweep_utility_dev_run()
+        return self._pair_utility_dev.cpu().numpy()
+
+    def opt_setting(self):
+        """The (start, stop) index pair with the maximum utility (obe_sweeper.py:153-169)."""
+        self._sweep_utility_dev_run()
+        self._pair_best_host.copy_(self._pair_best_dev, non_blocking=True)
+        self._torch.cuda.current_stream().synchronize()
+        index = int(self._pair_best_host[0])
+        self.last_setting_index = index
+        return self.start_stop_indices[index]
+
+    def good_setting(self, pickiness=None):
+        """Pair drawn with probability ~ sweep_utility**pickiness (obe_sweeper.py:171-198; the reference
+        ignores its argument and uses ``self.pickiness``, which is also the default here)."""
+        if pickiness is None:
+            pickiness = self.pickiness
+        n_pairs = self._sweep_utility_dev_run()
+        u = float(rng.random())
+        self._check(self._lib.obe_pick(C.c_void_p(self._pair_utility_dev.data_ptr()), n_pairs, float(pickiness), u,
+                                       C.c_void_p(self._pair_pick_dev.data_ptr()),
+                                       C.c_void_p(self._pair_scratch.data_ptr()), self._stream()))
+        index = int(self._pair_pick_dev.item())
+        self.last_setting_index = index
+        return self.start_stop_indices[index]
+
+    def random_setting(self):
+        """Uniformly random (start, stop) pair (obe_sweeper.py:200-211)."""
+        index = rng.choice(self.start_stop_choice_indices)
+        self.last_setting_index = index
+        return self.start_stop_indices[index]
+
+    def _generate_start_stop_indices(self):
+        """Valid [start, stop] index combinations, stop > start, on every ``start_stop_subsample``-th
+        setting plus the last one (obe_sweeper.py:213-232)."""
+        raw_length = len(self.sweep_settings)
+        sub = list(range(0, raw_length, int(self.start_stop_subsample)))
+        if sub[-1] != raw_length - 1:
+            sub.append(raw_length - 1)
+        m = len(sub)
+        i, j = np.triu_indices(m, k=1)
+        sub = np.asarray(sub, dtype=np.int64)
+        return np.stack((sub[i], sub[j]), axis=1)

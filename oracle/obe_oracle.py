@@ -598,6 +598,55 @@ class OracleOBE:
 
 
 # ----------------------------------------------------------------------------
+# Sweeper workload (demos/sweeper/obe_sweeper.py): settings are (start, stop) index pairs into the
+# swept setting array; a sweep is worth the point utility integrated along it, per unit cost.
+# ----------------------------------------------------------------------------
+def sweep_start_stop_indices(n_settings, subsample=3):
+    """All [start, stop] pairs, stop > start, on every `subsample`-th setting index plus the last
+    one (obe_sweeper.py:213-232)."""
+    sub = list(range(0, n_settings, subsample))
+    if sub[-1] != n_settings - 1:
+        sub.append(n_settings - 1)
+    pairs = [[a, b] for i, a in enumerate(sub[:-1]) for b in sub[i + 1:]]
+    return np.array(pairs, dtype=np.int64)
+
+
+def sweep_utility(point_utility, start_stop, cost_of_new_sweep):
+    """(cumsum(U)[stop] - cumsum(U)[start]) / ((stop - start) + cost_of_new_sweep)
+    (obe_sweeper.py:103-145)."""
+    cum = np.cumsum(point_utility)
+    ends = cum[start_stop]
+    cost = start_stop[:, 1] - start_stop[:, 0] + cost_of_new_sweep
+    return (ends[:, 1] - ends[:, 0]) / cost
+
+
+class OracleSweeper(OracleOBE):
+    """OptBayesExptSweeper (obe_sweeper.py:9-211) over OracleOBE: pdf_update runs one noise-parameter
+    update per point of the sweep, the design half picks a (start, stop) pair."""
+
+    def __init__(self, *a, start_stop_subsample=3, cost_of_new_sweep=5.0, **k):
+        OracleOBE.__init__(self, *a, **k)
+        self.start_stop_indices = sweep_start_stop_indices(self.allsettings.shape[1], start_stop_subsample)
+        self.cost_of_new_sweep = cost_of_new_sweep
+        self.last_sweep_utility = None
+
+    def pdf_update(self, record, forced_resample=False):
+        (setting_values,), result_values = record
+        for setting, result in zip(setting_values, result_values):
+            OracleOBE.pdf_update(self, ((setting,), result), forced_resample)
+        return self.particles, self.particle_weights
+
+    def sweep_utility(self):
+        self.last_sweep_utility = sweep_utility(self.utility(), self.start_stop_indices, self.cost_of_new_sweep)
+        return self.last_sweep_utility
+
+    def opt_setting(self):
+        index = opt_index(self.sweep_utility())
+        self.last_setting_index = index
+        return self.start_stop_indices[index]
+
+
+# ----------------------------------------------------------------------------
 # Uniform streams of the batched engines (restatement of csrc obe_batch_uniform): the q-th
 # uniform of instance b in cycle `cycle` is u53 of Philox4x32-10(ctr=(q, cycle, b, 0x0B5E0001), key=seed).
 # ----------------------------------------------------------------------------

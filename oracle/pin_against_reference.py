@@ -183,6 +183,90 @@ def run_lockstep(ref, sc):
     return out
 
 
+def import_reference_sweeper():
+    """demos/sweeper/obe_sweeper.py from the scratch copy.  The file imports matplotlib (absent here and
+    irrelevant to the class): an empty stand-in module is registered first."""
+    import importlib.util
+    import types
+    for name in ('matplotlib', 'matplotlib.pyplot'):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    path = os.path.join(tempfile.gettempdir(), 'obe_refcopy', 'demos', 'sweeper', 'obe_sweeper.py')
+    spec = importlib.util.spec_from_file_location('ref_obe_sweeper', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.OptBayesExptSweeper
+
+
+def run_sweeper_lockstep():
+    """Closed loop of the sweeper demo (opt_setting -> sweep -> one pdf_update per point), reference
+    against OracleSweeper, same seeds."""
+    from oracle.scenarios import SWEEPER as sc
+    RefSweeper = import_reference_sweeper()
+    inp = build_inputs(sc)
+    model = orc.MODELS[sc['model']][0]
+    robe = RefSweeper(model, inp['setting_values'], inp['prior'], inp['cons'],
+                      noise_parameter_index=sc['noise_parameter_index'], n_draws=sc['n_draws'], scale=sc['scale'],
+                      a_param=sc['a_param'], resample_threshold=sc['resample_threshold'])
+    robe.rng = np.random.default_rng(sc['seed_rng'])
+    assert robe.start_stop_subsample == sc['start_stop_subsample'] and robe.cost_of_new_sweep == sc['cost_of_new_sweep']
+    oobe = orc.OracleSweeper(model, inp['setting_values'], inp['prior'], inp['cons'], n_channels=1,
+                             n_draws=sc['n_draws'], a_param=sc['a_param'], resample_threshold=sc['resample_threshold'],
+                             scale=sc['scale'], noise_parameter_index=sc['noise_parameter_index'],
+                             start_stop_subsample=sc['start_stop_subsample'],
+                             cost_of_new_sweep=sc['cost_of_new_sweep'], rng=np.random.default_rng(sc['seed_rng']))
+    assert np.array_equal(robe.start_stop_indices, oobe.start_stop_indices)
+    meas_rng = np.random.default_rng(sc['seed_meas'])
+    xvals = inp['setting_values'][0]
+    T = sc['n_sweeps']
+    P = len(oobe.start_stop_indices)
+    d = robe.particles.shape[0]
+    out = dict(pair_index=np.zeros(T, dtype=np.int64), pairs=np.zeros((T, 2), dtype=np.int64),
+               sweep_utility=np.zeros((T, P)), point_utility=np.zeros((T, len(xvals))),
+               mean=np.zeros((T, d)), std=np.zeros((T, d)), n_resamples=np.zeros(T, dtype=np.int64),
+               start_stop_indices=np.array(oobe.start_stop_indices))
+    ys = []
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', RuntimeWarning)
+        for t in range(T):
+            state = robe.rng.bit_generator.state
+            r_util = robe.sweep_utility()                 # consumes K uniforms
+            robe.rng.bit_generator.state = state
+            rpair = robe.opt_setting()
+            opair = oobe.opt_setting()
+            assert robe.last_setting_index == oobe.last_setting_index, (t, 'pair index')
+            assert tuple(rpair) == tuple(opair)
+            seen = t > 0
+            np.testing.assert_allclose(oobe.last_sweep_utility, r_util, rtol=sc['traj_rtol'] if seen else 1e-12)
+            out['pair_index'][t] = oobe.last_setting_index
+            out['pairs'][t] = opair
+            out['sweep_utility'][t] = oobe.last_sweep_utility
+            out['point_utility'][t] = oobe.last_utility
+            start, stop = int(rpair[0]), int(rpair[1])
+            sweep_x = xvals[start:stop]
+            y_true = model((sweep_x,), sc['true_pars'], inp['cons'])
+            y = y_true + sc['noise'] * meas_rng.standard_normal(len(sweep_x))
+            ys.append(y)
+            n_res = 0
+            # the reference's pdf_update loops over the points; count its resamples point by point
+            for xs, yv in zip(sweep_x, y):
+                robe.pdf_update(((np.array([xs]),), np.array([yv])))
+                oobe.pdf_update(((np.array([xs]),), np.array([yv])))
+                assert bool(robe.just_resampled) == bool(oobe.just_resampled), (t, 'resample flag')
+                n_res += int(robe.just_resampled)
+            out['n_resamples'][t] = n_res
+            out['mean'][t] = robe.mean()
+            out['std'][t] = robe.std()
+            np.testing.assert_allclose(oobe.mean(), out['mean'][t], rtol=sc['traj_rtol'])
+            np.testing.assert_allclose(oobe.particle_weights, robe.particle_weights, rtol=sc['traj_rtol'],
+                                       atol=1e-15 * robe.particle_weights.max())
+    out['y_concat'] = np.concatenate(ys)
+    out['y_lengths'] = np.array([len(v) for v in ys], dtype=np.int64)
+    out['prior'] = np.array(inp['prior'])
+    out['final_particles'] = np.array(robe.particles)
+    out['final_weights'] = np.array(robe.particle_weights)
+    return out
+
+
 def check_equivalences():
     """The numpy identities the oracle relies on, re-verified against this numpy."""
     rng = np.random.default_rng(7)
@@ -256,6 +340,12 @@ def main():
                 keep.pop('prior')
                 keep.pop('pre_resample_particles', None)
             np.savez_compressed(os.path.join(GOLDEN, f"{sc['name']}.npz"), **keep)
+    if not args.only or args.only == 'sweeper_lorentzian':
+        out = run_sweeper_lockstep()
+        print(f"sweeper_lorentzian: lock-step OK over {len(out['pair_index'])} sweeps "
+              f"({int(out['y_lengths'].sum())} point updates, {int(out['n_resamples'].sum())} resamples)")
+        if not args.check:
+            np.savez_compressed(os.path.join(GOLDEN, 'sweeper_lorentzian.npz'), **out)
     print('all scenarios pinned')
 
 

@@ -61,7 +61,24 @@ SCENARIOS = [
 ]
 
 
+def _sweeper_prior(rng, n):
+    # demos/sweeper/sweeper.py:60-69
+    return np.array([rng.uniform(2, 4, n), rng.uniform(400, 2000, n), rng.normal(500, 1000, n),
+                     rng.exponential(500, n)])
+
+
+# demos/sweeper/sweeper.py: Lorentzian peak, unknown noise, settings are (start, stop) sweeps
+SWEEPER = dict(name='sweeper_lorentzian', kind='sweeper', model='lorentzian_hwhm', n_particles=10000,
+               prior=_sweeper_prior, settings=lambda: (np.linspace(1.5, 4.5, 100),), cons=(0.1,),
+               true_pars=(3.2, 1500.0, 300.0), noise=300.0, noise_parameter_index=3,
+               n_sweeps=10, n_draws=30, scale=False, a_param=0.98, resample_threshold=0.5,
+               start_stop_subsample=3, cost_of_new_sweep=5.0, traj_rtol=1e-8,
+               seed_prior=1001, seed_meas=1002, seed_rng=1003)
+
+
 def by_name(name):
+    if name == SWEEPER['name']:
+        return SWEEPER
     for sc in SCENARIOS:
         if sc['name'] == name:
             return sc

@@ -168,3 +168,42 @@ def test_oracle_replays_reference_golden(sc):
             assert_allclose(eng.mean(), g['mean'][t], rtol=tol if seen else 1e-12)
     assert_allclose(eng.particle_weights, g['final_weights'], rtol=max(tol, 1e-9),
                     atol=1e-15 * g['final_weights'].max())
+
+
+# ---- sweeper workload (demos/sweeper/obe_sweeper.py), SURVEY 8(f) row 2 ------------------------------
+def test_sweep_pairs_and_utility_known_answer():
+    pairs = orc.sweep_start_stop_indices(8, 3)              # subsamples 0, 3, 6 + the last index 7
+    assert_array_equal(pairs, [[0, 3], [0, 6], [0, 7], [3, 6], [3, 7], [6, 7]])
+    u = np.arange(1.0, 9.0)                                 # cumsum = 1, 3, 6, 10, 15, 21, 28, 36
+    su = orc.sweep_utility(u, pairs, 5.0)
+    assert_allclose(su, [(10 - 1) / 8, (28 - 1) / 11, (36 - 1) / 12, (28 - 10) / 8, (36 - 10) / 9, (36 - 28) / 6],
+                    rtol=1e-15)
+
+
+def test_oracle_sweeper_replays_reference_golden():
+    from oracle.scenarios import SWEEPER as sc
+    g = np.load(os.path.join(GOLDEN, sc['name'] + '.npz'))
+    inp = build_inputs(sc)
+    assert_array_equal(inp['prior'], g['prior'])
+    model = orc.MODELS[sc['model']][0]
+    eng = orc.OracleSweeper(model, inp['setting_values'], inp['prior'], inp['cons'], n_channels=1,
+                            n_draws=sc['n_draws'], a_param=sc['a_param'], resample_threshold=sc['resample_threshold'],
+                            scale=sc['scale'], noise_parameter_index=sc['noise_parameter_index'],
+                            start_stop_subsample=sc['start_stop_subsample'], cost_of_new_sweep=sc['cost_of_new_sweep'],
+                            rng=np.random.default_rng(sc['seed_rng']))
+    assert_array_equal(eng.start_stop_indices, g['start_stop_indices'])
+    xvals = inp['setting_values'][0]
+    ofs = np.concatenate(([0], np.cumsum(g['y_lengths'])))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', RuntimeWarning)
+        for t in range(sc['n_sweeps']):
+            pair = eng.opt_setting()
+            assert eng.last_setting_index == g['pair_index'][t], f't={t}'
+            assert_array_equal(pair, g['pairs'][t])
+            assert_allclose(eng.last_sweep_utility, g['sweep_utility'][t], rtol=sc['traj_rtol'] if t else 1e-12)
+            y = g['y_concat'][ofs[t]:ofs[t + 1]]
+            eng.pdf_update(((xvals[pair[0]:pair[1]],), y))
+            assert_allclose(eng.mean(), g['mean'][t], rtol=sc['traj_rtol'])
+    assert_allclose(eng.particle_weights, g['final_weights'], rtol=sc['traj_rtol'],
+                    atol=1e-15 * g['final_weights'].max())
