@@ -180,15 +180,19 @@ def bench_c5(args, rank, world):
         eng.pdf_update(y, force_resample=args.force_resample)
         step.y = y
     step.y = None
+    # device-resident leg: the on-device MeasurementSimulator writes every instance's record (no H2D at all)
+    eng.set_simulator(np.tile(np.array(truth), (B, 1)), 5.0, seed=1002 + rank)
     for _ in range(max(args.warmup, 3)):
         step(True)
+    for _ in range(3):
+        eng.closed_loop_cycle(force_resample=args.force_resample)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
     e0.record()
     for _ in range(args.steps):
-        step(False)                       # device-resident: records stay on the device
+        eng.closed_loop_cycle(force_resample=args.force_resample)   # select -> simulate -> update/resample, no host
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps

@@ -282,6 +282,16 @@ int obe_batch_refresh(const obe_batch_t* b, uint32_t mask_le, uint32_t mask_lt, 
 int obe_batch_select(obe_model_t m, const obe_batch_t* b, const double* settings_dev, int64_t lds, int64_t n_settings,
                      const double* constants, int k, const double* var_noise, double cost_change, uint64_t uniform_seed,
                      uint32_t cycle, int method, int log_form, double* utility_dev, void* stream);
+/* On-device MeasurementSimulator (obe_utils.py:8-53) for the batched engines: instance b measures at the
+ * setting it chose last, y_c = model_c(setting, true_params[:, b], constants) + noise_c * z_c, with z the
+ * library's Philox/Box-Muller normals (counter b, key seed, epoch cycle), and its record row is filled in
+ * on the device (setting, y, and sigma = noise level when write_sigma != 0).  true_params_dev: (np_model,
+ * ld_true) SoA; noise_level: host array of n_channels, or noise_level_dev: (B) per instance.  Followed by
+ * obe_batch_update(use_last = 1) a closed loop never touches the host. */
+int obe_batch_simulate(obe_model_t m, const obe_batch_t* b, const double* settings_dev, int64_t lds,
+                       const double* true_params_dev, int64_t ld_true, const double* constants,
+                       const double* noise_level, const double* noise_level_dev, uint64_t seed,
+                       uint32_t cycle, int write_sigma, void* stream);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,8 @@ SIGNATURES = {
     'obe_utility': (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int64, C.c_int64, _PD, _PD, _VP, _VP, C.c_int,
                               C.c_int, _VP, _VP, _VP, _VP, _VP]),
     'obe_pick': (C.c_int, [_VP, C.c_int64, C.c_double, C.c_double, _VP, _VP, _VP]),
+    'obe_batch_simulate': (C.c_int, [_VP, _PBATCH, _VP, C.c_int64, _VP, C.c_int64, _PD, _PD, _VP, C.c_uint64,
+                                     C.c_uint32, C.c_int, _VP]),
     'obe_sweep_utility': (C.c_int, [_VP, C.c_int64, _VP, C.c_int64, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     'obe_batch_init': (C.c_int, [_PBATCH, _PI32, C.c_int, _VP]),
     'obe_batch_update': (C.c_int, [_VP, _PBATCH, _VP, C.c_int64, C.c_int, _PD, _PI32, C.c_int, C.c_int, C.c_double,

@@ -172,9 +172,12 @@ class BatchedOptBayesExpt:
             st = np.asarray(settings, dtype=np.float64).reshape(B, -1)
             rec[:, :st.shape[1]] = st
         self._record.copy_(torch.from_numpy(rec))
+        self._update_from_record(0 if settings is not None else 1, n_lik, force_resample)
+
+    def _update_from_record(self, use_last, n_lik, force_resample):
         auto = bool(self.tuning_parameters['auto_resample'])
         self._check(self._lib.obe_batch_update(self._model, self._bs(), C.c_void_p(self._settings_dev.data_ptr()),
-                                               self._lds, 0 if settings is not None else 1, self._cons_arr,
+                                               self._lds, use_last, self._cons_arr,
                                                _lib.iarr(self._noise_index), n_lik, 0 if self.choke is None else 1,
                                                0.0 if self.choke is None else float(self.choke),
                                                float(self.tuning_parameters['resample_threshold']) if auto else -1.0,
@@ -187,6 +190,48 @@ class BatchedOptBayesExpt:
                                                      0 if self._noise_index is None else len(self._noise_index),
                                                      self._stream()))
         self.cycle += 1
+
+    # ---- on-device MeasurementSimulator (obe_utils.py:8-53), SURVEY 8(f) row 4
+    def set_simulator(self, true_params, noise_level, seed=12345):
+        """Install the simulated experiment of every instance: ``true_params`` (B, n_model_params) (or one
+        set for all), ``noise_level`` a scalar, one value per channel, or (B,) per instance."""
+        torch = self._torch
+        B = self.n_instances
+        npm = self.model_function.n_model_params
+        tp = np.asarray(true_params, dtype=np.float64)
+        if tp.ndim == 1:
+            tp = np.broadcast_to(tp[:npm], (B, npm))
+        if tp.shape[0] != B or tp.shape[1] < npm:
+            raise ValueError(f'true_params must have shape ({B}, >= {npm})')
+        self._sim_true = torch.from_numpy(np.ascontiguousarray(tp[:, :npm].T)).to(self._dev)       # (npm, B) SoA
+        nl = np.atleast_1d(np.asarray(noise_level, dtype=np.float64))
+        self._sim_noise_dev = None
+        self._sim_noise = None
+        if nl.shape == (B,) and B != self.n_channels and B != 1:
+            self._sim_noise_dev = torch.from_numpy(np.ascontiguousarray(nl)).to(self._dev)
+        else:
+            self._sim_noise = _lib.darr(np.broadcast_to(nl, (self.n_channels,)), _lib.MAX_CHANNELS)
+        self._sim_seed = int(seed)
+
+    def simulate_measurement(self):
+        """Instance b measures at the setting it chose last; the record rows are written on the device.
+        Returns the device record tensor (B, 12): [0:4) setting, [4:8) y, [8:12) sigma."""
+        if getattr(self, '_sim_true', None) is None:
+            raise RuntimeError('call set_simulator(true_params, noise_level) first')
+        self._check(self._lib.obe_batch_simulate(
+            self._model, self._bs(), C.c_void_p(self._settings_dev.data_ptr()), self._lds,
+            C.c_void_p(self._sim_true.data_ptr()), self.n_instances, self._cons_arr, self._sim_noise,
+            None if self._sim_noise_dev is None else C.c_void_p(self._sim_noise_dev.data_ptr()),
+            self._sim_seed, self.cycle, 1 if self._noise_index is None else 0, self._stream()))
+        return self._record
+
+    def closed_loop_cycle(self, force_resample=False):
+        """opt_setting -> simulated measurement -> pdf_update of every instance, without any host
+        round trip (no synchronisation, no H2D/D2H): the fit_vs_obe study's inner loop
+        (demos/fit_vs_obe/fit_vs_obe_makedata.py:149-194) for all runs at once."""
+        self.opt_setting(sync=False)
+        self.simulate_measurement()
+        self._update_from_record(1, self.n_channels, force_resample)
 
     @property
     def just_resampled(self):

@@ -350,45 +350,6 @@ __global__ void __launch_bounds__(OBE_THREADS) k_draw(const ObeDrawArgs a) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Box-Muller normals on top of Philox4x32-10 (obe_device.cuh); restated in oracle/obe_oracle.py
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float obe_sqrt_approx(float x) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-// uniform in (0,1): ((x >> 9) + 0.5) * 2^-23, exact in fp32
-__device__ __forceinline__ float u24(unsigned int x) {
-    // [1,2) from the top 23 bits, minus (1 - 2^-24): 23-bit uniform on the half-integers of 2^-23
-    return __uint_as_float(0x3f800000u | (x >> 9)) - 0.99999994039535522461f;
-}
-// Standard normals for the Liu-West jitter of output slot `slot`: one Philox4x32-10 call yields
-// four 24-bit uniforms -> two Box-Muller pairs evaluated in fp32 (the jitter is a random nudge of
-// scale sqrt(1-a^2)*sigma; its *value* needs no fp64 accuracy, its arithmetic after this point is
-// fp64).  ctr = (slot_lo, slot_hi, call, epoch), key = seed.
-template <int D>
-__device__ __forceinline__ void device_normals(long long slot, unsigned long long seed, unsigned int epoch,
-                                               double (&z)[D]) {
-#pragma unroll
-    for (int c = 0; c < (D + 3) / 4; ++c) {
-        unsigned int r[4];
-        philox4x32_10((unsigned int)(slot & 0xffffffffll), (unsigned int)((unsigned long long)slot >> 32),
-                      (unsigned int)c, epoch, (unsigned int)(seed & 0xffffffffull), (unsigned int)(seed >> 32), r);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (4 * c + 2 * h < D) {
-                // MUFU.LG2 / MUFU.RSQ-class approximations: ~1e-6 absolute, ample for a random nudge
-                const float rad = obe_sqrt_approx(-2.0f * __logf(u24(r[2 * h])));
-                float sn, cs;
-                __sincosf(6.2831853071795865f * u24(r[2 * h + 1]), &sn, &cs);
-                z[4 * c + 2 * h] = (double)(rad * cs);
-                if (4 * c + 2 * h + 1 < D) z[4 * c + 2 * h + 1] = (double)(rad * sn);
-            }
-        }
-    }
-}
-
 // U output slots at once: the Philox rounds of the U counters interleave (one basic block), which hides
 // the integer-multiply latency that a slot-at-a-time loop exposes.
 template <int D, int U>
@@ -1440,6 +1401,11 @@ __global__ void __launch_bounds__(OBE_THREADS) k_bselect_model(const ObeBSelectA
     obe_bselect_body<M>(a);
 }
 
+template <class M>
+__global__ void __launch_bounds__(OBE_THREADS) k_bsim_model(const ObeBSimArgs a) {
+    obe_bsimulate_body<M>(a);
+}
+
 struct obe_model {
     int ns, np_model, ncons, nch, d;
     bool user;
@@ -1449,6 +1415,7 @@ struct obe_model {
     const void* f_evals;
     const void* f_bupdate;  // batched instances
     const void* f_bselect;
+    const void* f_bsim;
     cudaLibrary_t lib;
 };
 
@@ -1462,6 +1429,7 @@ static void fill_model(obe_model* m) {
     m->f_evals = (const void*)k_evals_model<M>;
     m->f_bupdate = (const void*)k_bupdate_model<M, D>;
     m->f_bselect = (const void*)k_bselect_model<M>;
+    m->f_bsim = (const void*)k_bsim_model<M>;
 }
 template <class M>
 static int make_builtin(int d, obe_model* m) {
@@ -1620,10 +1588,10 @@ int obe_model_compile(const char* cuda_source, const char* entry, int n_settings
     m->d = n_params; m->user = true;
     cudaError_t e = cudaLibraryLoadData(&m->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e != cudaSuccess) { delete m; return obe_fail("cudaLibraryLoadData: %s%s", cudaGetErrorString(e)); }
-    cudaKernel_t k[6];
-    const char* kn[6] = {"obe_k_update_user", "obe_k_evalp_user", "obe_k_utility_user", "obe_k_evals_user",
-                         "obe_k_bupdate_user", "obe_k_bselect_user"};
-    for (int i = 0; i < 6; ++i) {
+    cudaKernel_t k[7];
+    const char* kn[7] = {"obe_k_update_user", "obe_k_evalp_user", "obe_k_utility_user", "obe_k_evals_user",
+                         "obe_k_bupdate_user", "obe_k_bselect_user", "obe_k_bsim_user"};
+    for (int i = 0; i < 7; ++i) {
         e = cudaLibraryGetKernel(&k[i], m->lib, kn[i]);
         if (e != cudaSuccess) {
             cudaLibraryUnload(m->lib);
@@ -1633,7 +1601,7 @@ int obe_model_compile(const char* cuda_source, const char* entry, int n_settings
     }
     m->f_update = (const void*)k[0]; m->f_evalp = (const void*)k[1];
     m->f_utility = (const void*)k[2]; m->f_evals = (const void*)k[3];
-    m->f_bupdate = (const void*)k[4]; m->f_bselect = (const void*)k[5];
+    m->f_bupdate = (const void*)k[4]; m->f_bselect = (const void*)k[5]; m->f_bsim = (const void*)k[6];
     *out = m;
     return 0;
 }
@@ -2125,6 +2093,25 @@ int obe_pick(const double* utility_dev, int64_t n_settings, double pickiness, do
     k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(s.tile_sums, nt, s.prefix, nullptr, 0, 0, n_settings);
     OBE_LAUNCH_CHECK("k_tile_scan");
     return draw_impl(s.p, s.prefix, n_settings, nullptr, 0, 0, &u, 1, nullptr, idx_dev, st);
+}
+
+int obe_batch_simulate(obe_model_t m, const obe_batch_t* b, const double* settings_dev, int64_t lds,
+                       const double* true_params_dev, int64_t ld_true, const double* constants,
+                       const double* noise_level, const double* noise_level_dev, uint64_t seed, uint32_t cycle,
+                       int write_sigma, void* stream) {
+    if (!m || !b || !settings_dev || !true_params_dev) return obe_fail("null argument%s%s");
+    if (!noise_level && !noise_level_dev) return obe_fail("simulate: need a noise level%s%s");
+    if (ld_true < b->n_inst) return obe_fail("simulate: ld_true < n_inst%s%s");
+    if (obe_sms() <= 0) return obe_fail("no CUDA device: this library has no CPU fallback%s%s");
+    ObeBSimArgs a;
+    memset(&a, 0, sizeof(a));
+    a.true_pars = true_params_dev; a.ld_true = ld_true; a.settings = settings_dev; a.lds = lds;
+    a.last_idx = (const long long*)b->last_idx_dev; a.record = b->record_dev; a.n_inst = b->n_inst;
+    a.noise_dev = noise_level_dev; a.seed = seed; a.cycle = cycle; a.write_sigma = write_sigma;
+    if (noise_level) for (int c = 0; c < m->nch; ++c) a.noise[c] = noise_level[c];
+    for (int j = 0; j < m->ncons; ++j) a.cons[j] = constants[j];
+    const int blocks = (int)((b->n_inst + OBE_THREADS - 1) / OBE_THREADS);
+    return launch_kernel(m->f_bsim, blocks, 0, (cudaStream_t)stream, &a);
 }
 
 int obe_sweep_utility(const double* utility_dev, int64_t n_settings, const int32_t* pairs_dev, int64_t n_pairs,

@@ -1208,6 +1208,46 @@ __device__ __forceinline__ void philox4x32_10(unsigned int c0, unsigned int c1, 
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Box-Muller normals on top of Philox4x32-10 (obe_device.cuh); restated in oracle/obe_oracle.py
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float obe_sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// uniform in (0,1): ((x >> 9) + 0.5) * 2^-23, exact in fp32
+__device__ __forceinline__ float u24(unsigned int x) {
+    // [1,2) from the top 23 bits, minus (1 - 2^-24): 23-bit uniform on the half-integers of 2^-23
+    return __uint_as_float(0x3f800000u | (x >> 9)) - 0.99999994039535522461f;
+}
+// Standard normals for the Liu-West jitter of output slot `slot`: one Philox4x32-10 call yields
+// four 24-bit uniforms -> two Box-Muller pairs evaluated in fp32 (the jitter is a random nudge of
+// scale sqrt(1-a^2)*sigma; its *value* needs no fp64 accuracy, its arithmetic after this point is
+// fp64).  ctr = (slot_lo, slot_hi, call, epoch), key = seed.
+template <int D>
+__device__ __forceinline__ void device_normals(long long slot, unsigned long long seed, unsigned int epoch,
+                                               double (&z)[D]) {
+#pragma unroll
+    for (int c = 0; c < (D + 3) / 4; ++c) {
+        unsigned int r[4];
+        philox4x32_10((unsigned int)(slot & 0xffffffffll), (unsigned int)((unsigned long long)slot >> 32),
+                      (unsigned int)c, epoch, (unsigned int)(seed & 0xffffffffull), (unsigned int)(seed >> 32), r);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (4 * c + 2 * h < D) {
+                // MUFU.LG2 / MUFU.RSQ-class approximations: ~1e-6 absolute, ample for a random nudge
+                const float rad = obe_sqrt_approx(-2.0f * __logf(u24(r[2 * h])));
+                float sn, cs;
+                __sincosf(6.2831853071795865f * u24(r[2 * h + 1]), &sn, &cs);
+                z[4 * c + 2 * h] = (double)(rad * cs);
+                if (4 * c + 2 * h + 1 < D) z[4 * c + 2 * h + 1] = (double)(rad * sn);
+            }
+        }
+    }
+}
+
 // uniform double in (0,1) from two Philox words
 __device__ __forceinline__ double obe_u53(unsigned int lo, unsigned int hi) {
     const unsigned long long x = ((unsigned long long)hi << 32) | lo;
@@ -1622,6 +1662,53 @@ __device__ void obe_eval_settings_body(const ObeEvalArgs& a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// On-device MeasurementSimulator for the batched engines (obe_utils.py:8-53: model at the "true"
+// parameters + Gaussian noise), so that a closed loop of B instances never touches the host:
+// instance b measures at the setting it chose last, y_c = model_c + noise_c * z_c with
+// z = device_normals(counter b, key seed, epoch cycle), and the record row of b is filled in.
+// ---------------------------------------------------------------------------------------------
+struct ObeBSimArgs {
+    const double* true_pars;     // (NP, ld_true): true parameters of every instance, SoA
+    long long ld_true;
+    const double* settings;      // (s, lds)
+    long long lds;
+    const long long* last_idx;   // (B)
+    double* record;              // (B * 12): [0:4) setting, [4:8) y, [8:12) sigma
+    long long n_inst;
+    const double* noise_dev;     // optional (B): per-instance noise level (all channels)
+    unsigned long long seed;
+    unsigned int cycle;
+    int write_sigma;             // 1: also write the noise level into the sigma slots (known-sigma models)
+    double noise[OBE_MAX_CH];
+    double cons[OBE_MAX_CONS];
+};
+
+template <class Model>
+__device__ void obe_bsimulate_body(const ObeBSimArgs& a) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.n_inst) return;
+    constexpr int NS = Model::NS > 0 ? Model::NS : 1, NP = Model::NP > 0 ? Model::NP : 1;
+    constexpr int NCH = Model::NCH > 0 ? Model::NCH : 1;
+    double s[NS], p[NP], y[NCH], z[NCH];
+    const long long idx = a.last_idx[b];
+#pragma unroll
+    for (int j = 0; j < Model::NS; ++j) s[j] = a.settings[j * a.lds + idx];
+#pragma unroll
+    for (int j = 0; j < Model::NP; ++j) p[j] = a.true_pars[j * a.ld_true + b];
+    Model::eval(s, p, a.cons, y);
+    device_normals<NCH>(b, a.seed, a.cycle, z);
+    double* rec = a.record + b * 12;
+#pragma unroll
+    for (int j = 0; j < Model::NS; ++j) rec[j] = s[j];
+#pragma unroll
+    for (int c = 0; c < Model::NCH; ++c) {
+        const double nl = a.noise_dev ? a.noise_dev[b] : a.noise[c];
+        rec[4 + c] = obe_add(y[c], obe_mul(nl, z[c]));
+        if (a.write_sigma) rec[8 + c] = nl;
+    }
+}
+
 // A model that is never evaluated: instantiates the update body for the OBE_SRC_Y /
 // OBE_SRC_LIK / OBE_SRC_NONE sources (moments, tile sums, constraint mask).
 struct ObeNoModel {
@@ -1643,6 +1730,9 @@ struct ObeNoModel {
     }                                                                                                          \
     extern "C" __global__ void __launch_bounds__(OBE_THREADS) obe_k_bselect_##SUFFIX(const ObeBSelectArgs a) {   \
         obe_bselect_body<MODEL>(a);                                                                            \
+    }                                                                                                          \
+    extern "C" __global__ void __launch_bounds__(OBE_THREADS) obe_k_bsim_##SUFFIX(const ObeBSimArgs a) {         \
+        obe_bsimulate_body<MODEL>(a);                                                                          \
     }
 
 #define OBE_DEFINE_GRID_KERNELS(MODEL, SUFFIX)                                                             \

@@ -646,6 +646,22 @@ class OracleSweeper(OracleOBE):
         return self.start_stop_indices[index]
 
 
+def simulate_batch_measurement(model, settings_b, true_pars_b, cons, noise_level, seed, cycle, n_channels):
+    """On-device MeasurementSimulator of the batched engines (csrc obe_bsimulate_body; the reference's
+    obe_utils.py:8-53 with the library's counter-based normals): instance b measures at settings_b[b],
+    y_c = model_c(setting, true_pars_b[b], cons) + noise_c * z_c, z = device_normals(counter b, key seed,
+    epoch cycle).  settings_b (B, s), true_pars_b (B, p), noise_level scalar, (C,) or (B,).  -> (B, C)"""
+    B = len(settings_b)
+    z = device_normals(B, n_channels, seed, cycle)
+    nl = np.asarray(noise_level, dtype=np.float64)
+    y = np.empty((B, n_channels))
+    for b in range(B):
+        yb = np.atleast_1d(np.asarray(model(tuple(settings_b[b]), tuple(true_pars_b[b]), cons), dtype=np.float64))
+        lvl = nl[b] if nl.shape == (B,) and B != n_channels else np.broadcast_to(nl, (n_channels,))
+        y[b] = yb + lvl * z[b]
+    return y
+
+
 # ----------------------------------------------------------------------------
 # Uniform streams of the batched engines (restatement of csrc obe_batch_uniform): the q-th
 # uniform of instance b in cycle `cycle` is u53 of Philox4x32-10(ctr=(q, cycle, b, 0x0B5E0001), key=seed).

@@ -7,6 +7,7 @@ import warnings
 
 import numpy as np
 import pytest
+from numpy.testing import assert_allclose, assert_array_equal
 
 from oracle import obe_oracle as orc
 from oracle.scenarios import build_inputs, by_name
@@ -134,3 +135,68 @@ def test_batched_full_config_c5_runs():
     assert np.all(np.isfinite(mean))
     err = np.abs(mean[:, 1] - truth[1]) / std[:, 1]
     assert np.median(err) < 2.0 and np.mean(err < 5.0) > 0.95
+
+
+# ---- on-device MeasurementSimulator (obe_utils.py:8-53), SURVEY 8(f) row 4 ------------------------------
+def test_batched_simulator_matches_oracle():
+    """The simulated records of one cycle against the numpy restatement: model value to 1e-12, the noise to the
+    float32 accuracy of the device normals; known-sigma models also get sigma written."""
+    from optbayesexpt_b200.batched import BatchedOptBayesExpt
+    sc = by_name('c1_find_peak')
+    B, n = 96, 2048
+    inp = build_inputs(sc, n)
+    rng = np.random.default_rng(8)
+    prior = np.stack([sc['prior'](rng, n) for _ in range(B)])
+    truths = np.stack([rng.uniform(2.2, 3.8, B), rng.uniform(-1800, -600, B), rng.normal(50000, 500, B)], axis=1)
+    beng = BatchedOptBayesExpt('lorentzian_hwhm', inp['setting_values'], prior, inp['cons'], scale=False,
+                               default_noise_std=500.0, seed=4)
+    beng.set_simulator(truths, 500.0, seed=99)
+    for cycle in range(3):
+        idx, settings = beng.opt_setting()
+        rec = beng.simulate_measurement().cpu().numpy()
+        want = orc.simulate_batch_measurement(orc.model_lorentzian_hwhm, settings.T, truths, inp['cons'], 500.0,
+                                              99, beng.cycle, 1)
+        assert_array_equal(rec[:, 0], settings[0])
+        assert_allclose(rec[:, 4], want[:, 0], rtol=0, atol=500.0 * 1e-5)
+        assert_array_equal(rec[:, 8], np.full(B, 500.0))
+        noise_free = np.array([orc.model_lorentzian_hwhm((settings[0, b],), truths[b], inp['cons']) for b in range(B)])
+        z = (rec[:, 4] - noise_free) / 500.0
+        assert abs(z.mean()) < 0.5 and 0.6 < z.std() < 1.4            # it is noise, and of the right size
+        beng._update_from_record(1, 1, False)                           # consume the simulated record
+    # per-instance noise levels, two channels (lock-in): sigma is a particle coordinate, not written
+    sc5 = by_name('c5_lockin')
+    inp5 = build_inputs(sc5, 2048)
+    prior5 = np.stack([sc5['prior'](rng, 2048) for _ in range(8)])
+    b5 = BatchedOptBayesExpt('lockin_coil', inp5['setting_values'], prior5, (), noise_parameter_index=(3, 3),
+                             constraint_lt=(0, 1, 2, 3), scale=False, seed=2)
+    levels = np.linspace(1.0, 8.0, 8)
+    truths5 = np.tile(np.array(sc5['true_pars']), (8, 1))
+    b5.set_simulator(truths5, levels, seed=7)
+    idx, settings = b5.opt_setting()
+    rec = b5.simulate_measurement().cpu().numpy()
+    want = orc.simulate_batch_measurement(orc.model_lockin_coil, settings.T, truths5, (), levels, 7, b5.cycle, 2)
+    assert_allclose(rec[:, 4:6], want, rtol=1e-12, atol=8.0 * 1e-5)
+    assert_array_equal(rec[:, 8:10], 0.0)
+
+
+def test_batched_closed_loop_on_device_converges():
+    """opt_setting -> simulated measurement -> pdf_update without a host round trip: every instance's
+    posterior lands on its own truth."""
+    from optbayesexpt_b200.batched import BatchedOptBayesExpt
+    sc = by_name('c1_find_peak')
+    B, n = 64, 10000
+    inp = build_inputs(sc, n)
+    rng = np.random.default_rng(18)
+    prior = np.stack([sc['prior'](rng, n) for _ in range(B)])
+    truths = np.stack([rng.uniform(2.3, 3.7, B), rng.uniform(-1800, -800, B), rng.normal(50000, 500, B)], axis=1)
+    beng = BatchedOptBayesExpt('lorentzian_hwhm', inp['setting_values'], prior, inp['cons'], scale=False,
+                               default_noise_std=500.0, seed=6)
+    beng.set_simulator(truths, 500.0, seed=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', RuntimeWarning)
+        for _ in range(150):
+            beng.closed_loop_cycle()
+    mean, std = beng.mean(), beng.std()
+    err = np.abs(mean - truths) / std
+    assert np.mean(err[:, 0] < 5.0) > 0.95, err[:, 0]
+    assert np.median(std[:, 0]) < 0.02
