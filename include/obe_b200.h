@@ -219,6 +219,22 @@ int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* set
  * uniform.  idx_dev: int64. */
 int obe_pick(const double* utility_dev, int64_t n_settings, double pickiness, double u,
              int64_t* idx_dev, void* select_scratch_dev, void* stream);
+/* Multi-point update (the sweeper's pdf_update, demos/sweeper/obe_sweeper.py:87-101: one Bayesian update
+ * per point of a sweep, resample test after each): n_points <= 128 records in ONE pass over the cloud.
+ * records_dev: (n_points, 12) doubles, row = [0:4) setting, [4:8) y, [8:12) 1/sigma (known-sigma models;
+ * ignored when noise_index selects sigma from the particles).  The un-normalised product of the
+ * likelihoods goes to weights_out_dev (another row of c->ld doubles, NOT c->weights_dev); lik_scale[c]
+ * (may be NULL) multiplies every point's likelihood of channel c -- a particle-independent factor that
+ * keeps long sweeps from underflowing.  sums_dev: (n_points, 2) out = sum t_m, sum t_m^2 after every
+ * point; result_dev: 2 doubles out = index of the FIRST point after which N_eff / n_total < threshold
+ * (the reference's resample test, particlepdf.py:236-258; -1 if none, threshold <= 0 disables) and that
+ * ratio.  The caller commits weights_out when result is -1 or n_points-1 (swap the rows, obe_refresh)
+ * and otherwise re-runs the first result+1 points, resamples, and continues. */
+int obe_update_multi(obe_model_t m, const obe_cloud_t* c, double* weights_out_dev,
+                     const double* records_dev, int n_points, const double* constants,
+                     const int32_t* noise_index, int n_lik_channels, const double* lik_scale,
+                     int use_choke, double choke, double threshold, int64_t n_total,
+                     double* sums_dev, double* result_dev, void* stream);
 /* Sweeper selection (demos/sweeper/obe_sweeper.py:118-162, sweep_utility + opt_setting): cumsum of the
  * point utility along the swept setting; every (start, stop) pair of setting indices is worth
  * (cum[stop] - cum[start]) / ((stop - start) + cost_of_new_sweep); argmax with np.argmax semantics.

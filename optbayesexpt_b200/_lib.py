@@ -20,7 +20,8 @@ MAX_SETTINGS = 4
 MAX_CONSTANTS = 8
 
 ST_TOTAL, ST_INVS, ST_SUMSQ, ST_NEFF = 0, 1, 2, 3
-ST_M1, ST_M2, ST_PIVOT, ST_NOISE, ST_SUMT, ST_NZERO = 4, 12, 48, 56, 60, 61
+ST_M1, ST_M2, ST_PIVOT, ST_NOISE, ST_SUMT, ST_NZERO, ST_UNIFORM = 4, 12, 48, 56, 60, 61, 62
+MULTI_MAX = 128
 
 
 class ObeError(RuntimeError):
@@ -96,6 +97,8 @@ SIGNATURES = {
     'obe_pick': (C.c_int, [_VP, C.c_int64, C.c_double, C.c_double, _VP, _VP, _VP]),
     'obe_batch_simulate': (C.c_int, [_VP, _PBATCH, _VP, C.c_int64, _VP, C.c_int64, _PD, _PD, _VP, C.c_uint64,
                                      C.c_uint32, C.c_int, _VP]),
+    'obe_update_multi': (C.c_int, [_VP, _PCLOUD, _VP, _VP, C.c_int, _PD, _PI32, C.c_int, _PD, C.c_int, C.c_double,
+                                   C.c_double, C.c_int64, _VP, _VP, _VP]),
     'obe_sweep_utility': (C.c_int, [_VP, C.c_int64, _VP, C.c_int64, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     'obe_batch_init': (C.c_int, [_PBATCH, _PI32, C.c_int, _VP]),
     'obe_batch_update': (C.c_int, [_VP, _PBATCH, _VP, C.c_int64, C.c_int, _PD, _PI32, C.c_int, C.c_int, C.c_double,

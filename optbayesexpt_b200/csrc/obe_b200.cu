@@ -1401,6 +1401,10 @@ __global__ void __launch_bounds__(OBE_THREADS) k_bselect_model(const ObeBSelectA
     obe_bselect_body<M>(a);
 }
 
+template <class M, int D>
+__global__ void __launch_bounds__(OBE_THREADS) k_multi_model(const ObeMultiArgs a) {
+    obe_update_multi_body<M, D>(a);
+}
 template <class M>
 __global__ void __launch_bounds__(OBE_THREADS) k_bsim_model(const ObeBSimArgs a) {
     obe_bsimulate_body<M>(a);
@@ -1416,6 +1420,7 @@ struct obe_model {
     const void* f_bupdate;  // batched instances
     const void* f_bselect;
     const void* f_bsim;
+    const void* f_multi;    // multi-point (sweep) update
     cudaLibrary_t lib;
 };
 
@@ -1430,6 +1435,7 @@ static void fill_model(obe_model* m) {
     m->f_bupdate = (const void*)k_bupdate_model<M, D>;
     m->f_bselect = (const void*)k_bselect_model<M>;
     m->f_bsim = (const void*)k_bsim_model<M>;
+    m->f_multi = (const void*)k_multi_model<M, D>;
 }
 template <class M>
 static int make_builtin(int d, obe_model* m) {
@@ -1588,10 +1594,10 @@ int obe_model_compile(const char* cuda_source, const char* entry, int n_settings
     m->d = n_params; m->user = true;
     cudaError_t e = cudaLibraryLoadData(&m->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e != cudaSuccess) { delete m; return obe_fail("cudaLibraryLoadData: %s%s", cudaGetErrorString(e)); }
-    cudaKernel_t k[7];
-    const char* kn[7] = {"obe_k_update_user", "obe_k_evalp_user", "obe_k_utility_user", "obe_k_evals_user",
-                         "obe_k_bupdate_user", "obe_k_bselect_user", "obe_k_bsim_user"};
-    for (int i = 0; i < 7; ++i) {
+    cudaKernel_t k[8];
+    const char* kn[8] = {"obe_k_update_user", "obe_k_evalp_user", "obe_k_utility_user", "obe_k_evals_user",
+                         "obe_k_bupdate_user", "obe_k_bselect_user", "obe_k_bsim_user", "obe_k_multi_user"};
+    for (int i = 0; i < 8; ++i) {
         e = cudaLibraryGetKernel(&k[i], m->lib, kn[i]);
         if (e != cudaSuccess) {
             cudaLibraryUnload(m->lib);
@@ -1602,6 +1608,7 @@ int obe_model_compile(const char* cuda_source, const char* entry, int n_settings
     m->f_update = (const void*)k[0]; m->f_evalp = (const void*)k[1];
     m->f_utility = (const void*)k[2]; m->f_evals = (const void*)k[3];
     m->f_bupdate = (const void*)k[4]; m->f_bselect = (const void*)k[5]; m->f_bsim = (const void*)k[6];
+    m->f_multi = (const void*)k[7];
     *out = m;
     return 0;
 }
@@ -2093,6 +2100,36 @@ int obe_pick(const double* utility_dev, int64_t n_settings, double pickiness, do
     k_tile_scan<<<1, OBE_SCAN_THREADS, 0, st>>>(s.tile_sums, nt, s.prefix, nullptr, 0, 0, n_settings);
     OBE_LAUNCH_CHECK("k_tile_scan");
     return draw_impl(s.p, s.prefix, n_settings, nullptr, 0, 0, &u, 1, nullptr, idx_dev, st);
+}
+
+int obe_update_multi(obe_model_t m, const obe_cloud_t* c, double* weights_out_dev, const double* records_dev,
+                     int n_points, const double* constants, const int32_t* noise_index, int n_lik_channels,
+                     const double* lik_scale, int use_choke, double choke, double threshold, int64_t n_total,
+                     double* sums_dev, double* result_dev, void* stream) {
+    if (!m || !weights_out_dev || !records_dev || !sums_dev || !result_dev) return obe_fail("null argument%s%s");
+    if (check_cloud(c)) return -1;
+    if (m->d != c->d) return obe_fail("model was built for a different n_params%s%s");
+    if (n_points < 1 || n_points > OBE_MULTI_MAX) return obe_fail("multi-point update takes 1..128 points per call%s%s");
+    if (weights_out_dev == c->weights_dev) return obe_fail("multi-point update is out of place: pass another weight row%s%s");
+    ObeMultiArgs a;
+    memset(&a, 0, sizeof(a));
+    a.particles = c->particles_dev; a.ld = c->ld; a.n = c->n; a.n_dev = (const long long*)c->n_dev;
+    a.w_in = c->weights_dev; a.w_out = weights_out_dev; a.stats = c->stats_dev; a.records = records_dev;
+    a.m_points = n_points; a.n_lik_channels = n_lik_channels; a.use_choke = use_choke; a.choke = choke;
+    for (int ch = 0; ch < OBE_MAX_CH; ++ch) { a.noise_idx[ch] = -1; a.lik_scale[ch] = 1.0; }
+    if (noise_index)
+        for (int j = 0; j < n_lik_channels && j < OBE_MAX_CH; ++j) { a.noise_idx[j] = noise_index[j]; a.n_noise = j + 1; }
+    if (lik_scale) for (int j = 0; j < m->nch; ++j) a.lik_scale[j] = lik_scale[j];
+    for (int j = 0; j < m->ncons; ++j) a.cons[j] = constants[j];
+    const Scratch s = scratch_of(c);
+    a.partials = s.partials; a.counter = s.counter + 8;
+    a.sums = sums_dev; a.result = result_dev; a.threshold = threshold; a.n_total = n_total;
+    int64_t blocks = (c->n + 2 * OBE_THREADS - 1) / (2 * OBE_THREADS);
+    int64_t cap = (int64_t)obe_sms() * 4;
+    const int64_t fit = ((int64_t)OBE_MAX_GRID * OBE_NACC_MAX) / (2 * OBE_MULTI_MAX);
+    if (cap > fit) cap = fit;
+    if (blocks > cap) blocks = cap;
+    return launch_kernel(m->f_multi, (int)blocks, 0, (cudaStream_t)stream, &a);
 }
 
 int obe_batch_simulate(obe_model_t m, const obe_batch_t* b, const double* settings_dev, int64_t lds,

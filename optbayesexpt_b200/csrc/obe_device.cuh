@@ -1709,6 +1709,138 @@ __device__ void obe_bsimulate_body(const ObeBSimArgs& a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-point update: the Bayesian updates of M measurement records (a sweep,
+// demos/sweeper/obe_sweeper.py:87-101) in ONE pass over the cloud.  Per particle the running product
+// t_m = nan_to_num(t_{m-1} * L_m) is carried through the M points in registers; per point the sums
+// S1_m = sum t_m and S2_m = sum t_m^2 are reduced (warp shuffle -> per-warp shared rows -> per-CTA
+// partials -> last CTA, all in fixed order), which gives N_eff after every point, so the last CTA
+// can report the FIRST point at which the reference's resample test (particlepdf.py:236-258) would
+// fire.  The caller commits the weights when no point fires (or the last one does) and otherwise
+// re-runs the points up to the firing one.  The per-point normalisation of the reference is a
+// particle-independent factor and is dropped (lazy normalisation); `lik_scale` removes the
+// particle-independent part of 1/sigma so that long sweeps cannot underflow.
+// Compute-bound (M model evaluations per particle): plain coalesced loads, no staging.
+// ---------------------------------------------------------------------------------------------
+#define OBE_MULTI_MAX 128
+struct ObeMultiArgs {
+    const double* particles; long long ld; long long n; const long long* n_dev;
+    const double* w_in; double* w_out;
+    const double* stats;            // of the input weights: normaliser, implicit-uniform value
+    const double* records;          // (M, 12): [0:4) setting, [4:8) y, [8:12) 1/sigma (known sigma)
+    int m_points, n_lik_channels, n_noise, use_choke;
+    int noise_idx[OBE_MAX_CH];
+    double choke;
+    double lik_scale[OBE_MAX_CH];
+    double cons[OBE_MAX_CONS];
+    double* partials;               // (grid, 2 * OBE_MULTI_MAX)
+    unsigned int* counter;
+    double* sums;                   // (M, 2) out: S1_m, S2_m
+    double* result;                 // out: [0] first firing point or -1, [1] its N_eff / n_total
+    double threshold;               // fire when N_eff / n_total < threshold (<= 0: never)
+    long long n_total;
+};
+
+template <class Model, int D>
+__device__ void obe_update_multi_body(const ObeMultiArgs& a) {
+    __shared__ double rec_s[OBE_MULTI_MAX * 12];
+    __shared__ double acc_s[OBE_THREADS / 32][2 * OBE_MULTI_MAX];
+    __shared__ unsigned int is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = a.m_points;
+    for (int q = tid; q < M * 12; q += OBE_THREADS) rec_s[q] = a.records[q];
+    for (int q = lane; q < 2 * M; q += 32) acc_s[warp][q] = 0.0;
+    __syncthreads();
+    const long long n = a.n_dev ? *a.n_dev : a.n;
+    const double invS = a.stats[OBE_ST_INVS], wuni = a.stats[OBE_ST_UNIFORM];
+    constexpr int NE = 2;
+    constexpr int NY = Model::NCH > 0 ? Model::NCH : 1;
+    for (long long base = (long long)blockIdx.x * (NE * OBE_THREADS); base < n;
+         base += (long long)gridDim.x * (NE * OBE_THREADS)) {
+        double p[NE][D], t[NE];
+        bool valid[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const long long i = base + e * OBE_THREADS + tid;
+            valid[e] = i < n;
+            const long long ii = valid[e] ? i : 0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) p[e][j] = a.particles[j * a.ld + ii];
+            const double w = (wuni > 0.0) ? wuni : a.w_in[ii];
+            t[e] = valid[e] ? w * invS : 0.0;
+        }
+        for (int m = 0; m < M; ++m) {
+            const double* r = rec_s + m * 12;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                double y[NY];
+                ObeUpdateEval<Model>::eval(r, p[e], a.cons, y);
+                double lik = 1.0;
+#pragma unroll
+                for (int c = 0; c < NY; ++c) {
+                    if (c < a.n_lik_channels) {
+                        double isg = r[8 + c];
+                        if (a.n_noise > 0) {
+                            const int ni = a.noise_idx[c];
+                            double sig = 1.0;
+#pragma unroll
+                            for (int j = 0; j < D; ++j)
+                                if (j == ni) sig = p[e][j];
+                            isg = obe_rcp_fast(sig);
+                        }
+                        const double q = (y[c] - r[4 + c]) * isg;
+                        lik *= obe_exp_nonpos(-0.5 * (q * q)) * (isg * a.lik_scale[c]);
+                    }
+                }
+                if (a.use_choke) lik = pow(lik, a.choke);
+                t[e] = obe_nan_to_num_fast(t[e] * lik);
+            }
+            double s1 = t[0] + t[1], s2 = t[0] * t[0] + t[1] * t[1];
+            s1 = obe_warp_sum(s1);
+            s2 = obe_warp_sum(s2);
+            if (lane == 0) { acc_s[warp][2 * m] += s1; acc_s[warp][2 * m + 1] += s2; }
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const long long i = base + e * OBE_THREADS + tid;
+            if (valid[e]) a.w_out[i] = t[e];
+        }
+    }
+    __syncthreads();
+    for (int q = tid; q < 2 * M; q += OBE_THREADS) {
+        double v = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < OBE_THREADS / 32; ++w2) v += acc_s[w2][q];
+        a.partials[(long long)blockIdx.x * (2 * OBE_MULTI_MAX) + q] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int q = tid; q < 2 * M; q += OBE_THREADS) {
+        double v = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) v += __ldcg(a.partials + (long long)b * (2 * OBE_MULTI_MAX) + q);
+        a.sums[q] = v;
+        rec_s[q] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double first = -1.0, ratio = 0.0;
+        if (a.threshold > 0.0) {
+            for (int m = 0; m < M; ++m) {
+                const double s1 = rec_s[2 * m], s2 = rec_s[2 * m + 1];
+                const double frac = (s1 * s1) / s2 / (double)a.n_total;      // N_eff / n  (particlepdf.py:243-244)
+                if (frac < a.threshold) { first = (double)m; ratio = frac; break; }
+            }
+        }
+        a.result[0] = first;
+        a.result[1] = ratio;
+        *a.counter = 0u;
+    }
+}
+
 // A model that is never evaluated: instantiates the update body for the OBE_SRC_Y /
 // OBE_SRC_LIK / OBE_SRC_NONE sources (moments, tile sums, constraint mask).
 struct ObeNoModel {
@@ -1722,6 +1854,9 @@ struct ObeNoModel {
     }                                                                                                     \
     extern "C" __global__ void __launch_bounds__(OBE_THREADS) obe_k_evalp_##SUFFIX(const ObeEvalArgs a) {  \
         obe_eval_params_body<MODEL, D>(a);                                                                \
+    }                                                                                                     \
+    extern "C" __global__ void __launch_bounds__(OBE_THREADS) obe_k_multi_##SUFFIX(const ObeMultiArgs a) { \
+        obe_update_multi_body<MODEL, D>(a);                                                               \
     }
 
 #define OBE_DEFINE_BATCH_KERNELS(MODEL, D, SUFFIX)                                                              \

@@ -36,18 +36,111 @@ class OptBayesExptSweeper(OptBayesExptNoiseParameter):
         self.start_stop_choice_indices = np.arange(len(self.start_stop_indices), dtype=int)
         self.start_stop_values = self.sweep_settings[self.start_stop_indices]
         self.cost_of_new_sweep = 5.
+        #: True: a sweep is digested by the multi-point kernel (one pass over the cloud per segment between
+        #: resamples); False: one update launch per point, literally as the reference loops.
+        self.fused_sweep = True
         self._pairs_host = None
         self._pairs_dev = None
+        self._multi_w = None
+        self._sigma_ref = None
 
     # ---- inference half
     def pdf_update(self, measurement_record):
-        """One noise-parameter ``pdf_update`` per point of the sweep (obe_sweeper.py:87-101); the resample
-        test runs after every point, exactly as in the reference."""
+        """Bayesian inference on a swept measurement (obe_sweeper.py:87-101): one noise-parameter update per
+        point of the sweep, the resample test after every point, exactly as in the reference.  With
+        ``fused_sweep`` (default) the points between two resamples are one pass over the cloud."""
         (setting_values,), result_values = measurement_record
+        if self.fused_sweep and len(setting_values) > 1:
+            return self._pdf_update_fused(np.asarray(setting_values, dtype=np.float64), result_values)
         out = None
         for setting, result in zip(setting_values, result_values):
             out = OptBayesExptNoiseParameter.pdf_update(self, ((setting,), result))
         return out
+
+    def _multi_update(self, xs, ys):
+        """Launch the multi-point kernel on points (xs, ys) -> (first firing point or -1, its N_eff/n)."""
+        torch = self._torch
+        m = len(xs)
+        rec = np.zeros((m, 12))
+        rec[:, 0] = xs
+        y = np.asarray(ys, dtype=np.float64).reshape(m, -1)
+        n_lik = min(self.n_channels, y.shape[1])
+        rec[:, 4:4 + n_lik] = y[:, :n_lik]
+        dev = self._buf.device
+        if self._multi_w is None:
+            self._multi_w = torch.zeros(self._buf.ld, dtype=torch.float64, device=dev)
+            self._multi_rec = torch.zeros((_lib.MULTI_MAX, 12), dtype=torch.float64, device=dev)
+            self._multi_sums = torch.zeros((_lib.MULTI_MAX, 2), dtype=torch.float64, device=dev)
+            self._multi_res = torch.zeros(2, dtype=torch.float64, device=dev)
+            self._multi_res_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+        self._multi_rec[:m].copy_(torch.from_numpy(rec))
+        # particle-independent scale of 1/sigma: the rms noise estimate of the last committed cloud
+        if self._sigma_ref is None:
+            self._sigma_ref = self._rms_noise(self._ensure_moments())
+        scale = self._sigma_ref
+        thr = 0.0
+        if self.tuning_parameters['auto_resample']:
+            thr = max(0.1, float(self.tuning_parameters['resample_threshold']))
+        self._check(self._lib.obe_update_multi(
+            self._model, self._cs(), C.c_void_p(self._multi_w.data_ptr()), C.c_void_p(self._multi_rec.data_ptr()), m,
+            self._cons_arr, _lib.iarr(self._noise_index[:n_lik]), n_lik, _lib.darr(scale, _lib.MAX_CHANNELS),
+            0 if self.choke is None else 1, 0.0 if self.choke is None else float(self.choke), thr,
+            self.n_particles, C.c_void_p(self._multi_sums.data_ptr()), C.c_void_p(self._multi_res.data_ptr()),
+            self._stream()))
+        self._multi_res_host.copy_(self._multi_res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return int(self._multi_res_host[0]), float(self._multi_res_host[1])
+
+    def _commit_multi(self):
+        """The row the multi-point kernel wrote becomes the cloud's weight row; stats, CDF prefix and moments
+        are rebuilt from it (one refresh pass)."""
+        self._buf.weights, self._multi_w = self._multi_w, self._buf.weights
+        self._buf._struct = None
+        self._buf.stats[_lib.ST_UNIFORM] = 0.0          # the weight row is explicit
+        self._invalidate()
+        self._stats = None
+        self._weights_uniform = False
+        self._weights_lazy = True
+        self._moments_valid = False
+        self._sigma_ref = self._rms_noise(self._refresh(renormalise=1))
+
+    def _rms_noise(self, st):
+        """sqrt of the weighted mean of sigma^2 per channel (obe_noiseparam.py:132-136), 1 where undefined."""
+        scale = np.ones(_lib.MAX_CHANNELS)
+        c = self.n_channels
+        with np.errstate(all='ignore'):
+            s2 = st[_lib.ST_NOISE:_lib.ST_NOISE + c] / st[_lib.ST_SUMT]
+        ok = np.isfinite(s2) & (s2 > 0)
+        scale[:c][ok] = np.sqrt(s2[ok])
+        return scale
+
+    def _pdf_update_fused(self, xs, ys):
+        import warnings
+        ys = list(ys)
+        i, m_total = 0, len(xs)
+        while i < m_total:
+            j = min(i + _lib.MULTI_MAX, m_total)
+            first, ratio = self._multi_update(xs[i:j], ys[i:j])
+            if first < 0:
+                self._commit_multi()
+                self.just_resampled = False
+                i = j
+                continue
+            if first != j - i - 1:                      # the weights on the device ran past the resample point
+                again, ratio = self._multi_update(xs[i:i + first + 1], ys[i:i + first + 1])
+                if again != first:
+                    raise RuntimeError('multi-point update is not reproducible')
+            self._commit_multi()
+            if ratio < 0.1:
+                warnings.warn("\nParticle filter rejected > 90 % of particles. "
+                              f"N_eff = {ratio * self.n_particles:.2f}. "
+                              "Particle impoverishment may lead to errors.", RuntimeWarning)
+            self.resample()
+            self.just_resampled = True
+            self.enforce_parameter_constraints()
+            i += first + 1
+        from .obe_base import LazyDeviceArray
+        return (LazyDeviceArray(lambda: self.particles), LazyDeviceArray(lambda: self.particle_weights))
 
     # ---- design half
     def cost_estimate(self):

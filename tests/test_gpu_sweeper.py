@@ -86,12 +86,16 @@ def test_sweep_utility_kernel_matches_oracle(obe):
     assert int(best[0].item()) == int(np.argmax(got))           # first maximum
 
 
-def test_sweeper_golden_trajectory(obe):
+@pytest.mark.parametrize('fused', [False, True], ids=['point_by_point', 'fused_multi_point'])
+def test_sweeper_golden_trajectory(obe, fused):
     """Seeded like the reference run: every chosen (start, stop) pair identical, sweep utility, moments and
-    final weights within the condition-aware tolerance."""
+    final weights within the condition-aware tolerance -- with one launch per point as the reference loops,
+    and with the multi-point kernel (one pass per segment between resamples)."""
     sc = SWEEPER
     g = np.load(os.path.join(GOLDEN, sc['name'] + '.npz'))
     eng, inp = _sweeper(obe)
+    eng.fused_sweep = fused
+    n_res = 0
     xvals = inp['setting_values'][0]
     ofs = np.concatenate(([0], np.cumsum(g['y_lengths'])))
     tol = sc['traj_rtol']
@@ -106,7 +110,9 @@ def test_sweeper_golden_trajectory(obe):
                             atol=1e-13 * np.sum(g['point_utility'][t]) / 8.0, err_msg=f'sweep utility t={t}')
             assert_allclose(eng._utility_dev.cpu().numpy(), g['point_utility'][t], rtol=tol if t else 1e-12)
             y = g['y_concat'][ofs[t]:ofs[t + 1]]
+            e0 = eng._epoch
             eng.pdf_update(((xvals[pair[0]:pair[1]],), y))
+            assert eng._epoch - e0 == g['n_resamples'][t], f'number of resamples in sweep {t}'
             assert_allclose(eng.mean(), g['mean'][t], rtol=tol, err_msg=f'mean t={t}')
             assert_allclose(eng.std(), g['std'][t], rtol=1e-6, err_msg=f'std t={t}')
     w = eng.particle_weights
@@ -146,3 +152,38 @@ def test_sweeper_default_systematic_converges(obe):
     truth = np.array(list(sc['true_pars']) + [sc['noise']])
     err = np.abs(eng.mean() - truth) / eng.std()
     assert np.all(err < 5), (eng.mean(), eng.std())
+
+
+def test_multi_point_update_matches_point_by_point(obe):
+    """obe_update_multi against M single updates on the same cloud (no resample in between): weights to
+    1e-12 after normalisation, per-point N_eff from the kernel's sums against the engine's own."""
+    import ctypes as C
+    import torch
+    from optbayesexpt_b200 import _lib
+    sc = SWEEPER
+    inp = build_inputs(sc, 300_000)
+    xs = inp['setting_values'][0][20:75]
+    model = orc.MODELS[sc['model']][0]
+    ys = model((xs,), sc['true_pars'], inp['cons']) + sc['noise'] * np.random.default_rng(3).standard_normal(len(xs))
+    a = obe.OptBayesExptSweeper(sc['model'], inp['setting_values'], inp['prior'], inp['cons'], noise_parameter_index=3,
+                                scale=False, seed=1, auto_resample=False)
+    b = obe.OptBayesExptSweeper(sc['model'], inp['setting_values'], inp['prior'], inp['cons'], noise_parameter_index=3,
+                                scale=False, seed=1, auto_resample=False)
+    a.fused_sweep, b.fused_sweep = True, False
+    neff = []
+    for x, y in zip(xs, ys):
+        b.pdf_update(((np.array([x]),), np.array([y])))
+        neff.append(b.n_eff())
+    a.pdf_update(((xs,), ys))
+    wa, wb = a.particle_weights, b.particle_weights
+    assert_allclose(wa, wb, rtol=1e-11, atol=1e-15 * wb.max())
+    assert_allclose(a.mean(), b.mean(), rtol=1e-11)
+    assert_allclose(a.std(), b.std(), rtol=1e-8)
+    sums = a._multi_sums.cpu().numpy()[:len(xs)]
+    assert_allclose(sums[:, 0] ** 2 / sums[:, 1], neff, rtol=1e-10)
+    # with the resample test on, the kernel reports the first point whose N_eff falls below the threshold
+    c = obe.OptBayesExptSweeper(sc['model'], inp['setting_values'], inp['prior'], inp['cons'], noise_parameter_index=3,
+                                scale=False, seed=1)
+    first, ratio = c._multi_update(xs, ys)
+    want = int(np.argmax(np.array(neff) / 300_000 < 0.5))
+    assert first == want and abs(ratio - neff[want] / 300_000) < 1e-10
