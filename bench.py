@@ -228,6 +228,67 @@ def bench_c5(args, rank, world):
 
 
 # -------------------------------------------------------------------------------------------------
+def bench_sweeper(args):
+    """the sweeper's inference half.  One sweep = 64 measured points digested by
+    OptBayesExptSweeper.pdf_update on 1e7 particles (d = 4, sigma unknown); fused multi-point kernel against the
+    reference's loop of one update per point.  Resample test on (threshold 0.5), systematic resampling."""
+    import torch
+    import __graft_entry__
+    __graft_entry__.build()
+    import optbayesexpt_b200 as obe
+    from oracle import obe_oracle as orc
+    n, m = int(args.particles) if args.particles < 1e8 else 10_000_000, 64
+    g = torch.Generator(device='cuda')
+    g.manual_seed(1001)
+    f64 = dict(dtype=torch.float64, device='cuda')
+    xvals = np.linspace(1.5, 4.5, 1000)
+    truth, noise = (3.2, 1500.0, 300.0), 300.0
+
+    def make():
+        prior = torch.empty((4, n), **f64)
+        prior[0] = 2 + 2 * torch.rand(n, generator=g, **f64)
+        prior[1] = 400 + 1600 * torch.rand(n, generator=g, **f64)
+        prior[2] = 500 + 1000 * torch.randn(n, generator=g, **f64)
+        prior[3] = torch.empty(n, **f64).exponential_(1.0, generator=g) * 500
+        return obe.OptBayesExptSweeper('lorentzian_hwhm', (xvals,), prior, (0.1,), noise_parameter_index=3,
+                                       scale=False, seed=7)
+    meas = np.random.default_rng(1002)
+    out = {}
+    for mode in ('fused', 'point_by_point'):
+        eng = make()
+        eng.fused_sweep = (mode == 'fused')
+        times, n_res = [], 0
+        for it in range(args.warmup + args.steps):
+            start = int(meas.integers(0, len(xvals) - m))
+            xs = xvals[start:start + m]
+            ys = orc.model_lorentzian_hwhm((xs,), truth, (0.1,)) + noise * meas.standard_normal(m)
+            e0 = eng._epoch
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            eng.pdf_update(((xs,), ys))
+            torch.cuda.synchronize()
+            if it >= args.warmup:
+                times.append(time.perf_counter() - t0)
+                n_res += eng._epoch - e0
+        out[mode] = (float(np.mean(times)), n_res / max(1, args.steps))
+        del eng
+        torch.cuda.empty_cache()
+    t_f, r_f = out['fused']
+    t_p, r_p = out['point_by_point']
+    line = {'metric': 'sweeper pdf_update: measured points digested per second', 'value': m / t_f, 'unit': 'points/s',
+            'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t_f * 1e3, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'demos/sweeper inference half: {n:.0e} particles, d=4, sweeps of {m} points, '
+                                   'resample test after every point (threshold 0.5)'},
+            'point_by_point': {'value': m / t_p, 'unit': 'points/s', 'ms_per_sweep': t_p * 1e3,
+                               'resamples_per_sweep': r_p},
+            'resamples_per_sweep': r_f, 'speedup_vs_point_by_point': t_p / t_f,
+            'e2e': {'value': m / t_f, 'unit': 'points/s', 'h2d_bytes_per_step': m * 96, 'd2h_bytes_per_step': 16},
+            'note': 'wall clock around pdf_update incl. host synchronisation (the resample decisions are host-side)'}
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -239,8 +300,9 @@ def main():
     ap.add_argument('--draws', type=int, default=30)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--force-resample', action='store_true')
-    ap.add_argument('--workload', default='c4', choices=['c4', 'c5'],
-                    help='c4: 1e8-particle Lorentzian cloud (default, the metric); c5: 4096 batched lock-in engines')
+    ap.add_argument('--workload', default='c4', choices=['c4', 'c5', 'sweeper'],
+                    help='c4: 1e8-particle Lorentzian cloud (default, the metric); c5: 4096 batched lock-in engines; '
+                         'sweeper: the sweeper demo\'s multi-point inference (1 GPU)')
     args = ap.parse_args()
     n_total = int(args.particles)
     rank = int(os.environ.get('RANK', 0))
@@ -252,6 +314,8 @@ def main():
 
     if args.workload == 'c5' and args.impl == 'ours':
         return bench_c5(args, rank, world)
+    if args.workload == 'sweeper' and args.impl == 'ours':
+        return bench_sweeper(args) if rank == 0 else None
     if args.impl == 'reference':
         if rank != 0:
             return

@@ -2124,7 +2124,7 @@ int obe_update_multi(obe_model_t m, const obe_cloud_t* c, double* weights_out_de
     const Scratch s = scratch_of(c);
     a.partials = s.partials; a.counter = s.counter + 8;
     a.sums = sums_dev; a.result = result_dev; a.threshold = threshold; a.n_total = n_total;
-    int64_t blocks = (c->n + 2 * OBE_THREADS - 1) / (2 * OBE_THREADS);
+    int64_t blocks = (c->n + OBE_MULTI_NE * OBE_THREADS - 1) / (OBE_MULTI_NE * OBE_THREADS);
     int64_t cap = (int64_t)obe_sms() * 4;
     const int64_t fit = ((int64_t)OBE_MAX_GRID * OBE_NACC_MAX) / (2 * OBE_MULTI_MAX);
     if (cap > fit) cap = fit;

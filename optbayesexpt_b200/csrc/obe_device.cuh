@@ -1723,6 +1723,7 @@ __device__ void obe_bsimulate_body(const ObeBSimArgs& a) {
 // Compute-bound (M model evaluations per particle): plain coalesced loads, no staging.
 // ---------------------------------------------------------------------------------------------
 #define OBE_MULTI_MAX 128
+#define OBE_MULTI_NE 4
 struct ObeMultiArgs {
     const double* particles; long long ld; long long n; const long long* n_dev;
     const double* w_in; double* w_out;
@@ -1753,7 +1754,7 @@ __device__ void obe_update_multi_body(const ObeMultiArgs& a) {
     __syncthreads();
     const long long n = a.n_dev ? *a.n_dev : a.n;
     const double invS = a.stats[OBE_ST_INVS], wuni = a.stats[OBE_ST_UNIFORM];
-    constexpr int NE = 2;
+    constexpr int NE = OBE_MULTI_NE;   // particles per thread and round: amortises the two warp reductions per point
     constexpr int NY = Model::NCH > 0 ? Model::NCH : 1;
     for (long long base = (long long)blockIdx.x * (NE * OBE_THREADS); base < n;
          base += (long long)gridDim.x * (NE * OBE_THREADS)) {
@@ -1795,7 +1796,9 @@ __device__ void obe_update_multi_body(const ObeMultiArgs& a) {
                 if (a.use_choke) lik = pow(lik, a.choke);
                 t[e] = obe_nan_to_num_fast(t[e] * lik);
             }
-            double s1 = t[0] + t[1], s2 = t[0] * t[0] + t[1] * t[1];
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) { s1 += t[e]; s2 += t[e] * t[e]; }
             s1 = obe_warp_sum(s1);
             s2 = obe_warp_sum(s2);
             if (lane == 0) { acc_s[warp][2 * m] += s1; acc_s[warp][2 * m + 1] += s2; }

@@ -43,6 +43,7 @@ class OptBayesExptSweeper(OptBayesExptNoiseParameter):
         self._pairs_dev = None
         self._multi_w = None
         self._sigma_ref = None
+        self._sweep_chunk = 16
 
     # ---- inference half
     def pdf_update(self, measurement_record):
@@ -115,21 +116,26 @@ class OptBayesExptSweeper(OptBayesExptNoiseParameter):
         return scale
 
     def _pdf_update_fused(self, xs, ys):
+        """Segments of the sweep between resamples, each one multi-point launch.  A launch that ran past the
+        point where the resample test fires is wasted work (it is redone up to that point), so the number of
+        points per launch follows the distance between resamples seen so far."""
         import warnings
         ys = list(ys)
         i, m_total = 0, len(xs)
         while i < m_total:
-            j = min(i + _lib.MULTI_MAX, m_total)
+            j = min(i + max(1, min(self._sweep_chunk, _lib.MULTI_MAX)), m_total)
             first, ratio = self._multi_update(xs[i:j], ys[i:j])
             if first < 0:
                 self._commit_multi()
                 self.just_resampled = False
+                self._sweep_chunk = min(2 * self._sweep_chunk, _lib.MULTI_MAX)
                 i = j
                 continue
             if first != j - i - 1:                      # the weights on the device ran past the resample point
                 again, ratio = self._multi_update(xs[i:i + first + 1], ys[i:i + first + 1])
                 if again != first:
                     raise RuntimeError('multi-point update is not reproducible')
+                self._sweep_chunk = max(4, first + 1)
             self._commit_multi()
             if ratio < 0.1:
                 warnings.warn("\nParticle filter rejected > 90 % of particles. "
