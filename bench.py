@@ -252,9 +252,10 @@ def bench_sweeper(args):
         prior[3] = torch.empty(n, **f64).exponential_(1.0, generator=g) * 500
         return obe.OptBayesExptSweeper('lorentzian_hwhm', (xvals,), prior, (0.1,), noise_parameter_index=3,
                                        scale=False, seed=7)
-    meas = np.random.default_rng(1002)
     out = {}
     for mode in ('fused', 'point_by_point'):
+        g.manual_seed(1001)                       # same cloud, same sweeps, same noise for both modes
+        meas = np.random.default_rng(1002)
         eng = make()
         eng.fused_sweep = (mode == 'fused')
         times, n_res = [], 0

@@ -353,17 +353,22 @@ def test_multinomial_resample_matches_oracle(obe, scale):
     assert pdf.rng.random() == g.random()                        # identical Generator state afterwards
 
 
-@pytest.mark.parametrize('n', [4096, 10000, 250001])
+@pytest.mark.parametrize('n,d', [(4096, 3), (10000, 3), (250001, 3), (1, 2), (2, 2), (5, 1), (2047, 2), (2049, 2),
+                                 (4097, 1), (10000, 1), (30011, 4), (10000, 6), (6151, 8)])
 @pytest.mark.parametrize('scale', [False, True])
-def test_systematic_resample_matches_oracle(obe, torch, n, scale):
-    """Fused systematic kernel: ancestors == searchsorted(cdf_gpu, comb) bit-exact; normals are the
-    restated Philox/Box-Muller stream; particles == Liu-West with the Cholesky factor."""
+def test_systematic_resample_matches_oracle(obe, torch, n, d, scale):
+    """Systematic resample (plan + ancestors + move kernels): ancestors == searchsorted(cdf_gpu, comb)
+    bit-exact; normals are the restated Philox/Box-Muller stream; particles == Liu-West with the Cholesky
+    factor.  Sizes around the tile boundaries, every register/shared-memory variant of the move kernel (d)."""
     from optbayesexpt_b200 import _lib
-    d = 3
     rng = np.random.default_rng(n)
-    prior = np.array([rng.uniform(2, 4, n), rng.uniform(-2000, -400, n), rng.normal(5e4, 1e3, n)])
+    rows = [rng.uniform(2, 4, n), rng.uniform(-2000, -400, n), rng.normal(5e4, 1e3, n), rng.exponential(3.0, n),
+            rng.normal(0, 1e-3, n), rng.uniform(-1, 1, n), rng.normal(7, 2, n), rng.uniform(0, 1e6, n)]
+    prior = np.array(rows[:d])
     w = rng.random(n) ** 6
     w[rng.random(n) < 0.3] = 0.0                                  # runs of dead particles
+    if w.sum() == 0.0:
+        w[:] = 1.0
     w /= w.sum()
     pdf = obe.ParticlePDF(prior, scale=scale, resampling='systematic', seed=11)
     pdf.particle_weights = w
@@ -390,8 +395,11 @@ def test_systematic_resample_matches_oracle(obe, torch, n, scale):
     # Liu-West arithmetic downstream is then checked exactly, GIVEN the normals the kernel used
     z = zout.cpu().numpy()
     assert_allclose(z, orc.device_normals(n, d, seed, epoch), rtol=0, atol=1e-4)
-    assert abs(z.mean()) < 5 / np.sqrt(n * d) and abs(z.std() - 1) < 5 / np.sqrt(n * d)
-    f = orc.mvn_factor_cholesky((1 - 0.98 ** 2) * cov)
+    if n * d >= 1000:
+        assert abs(z.mean()) < 5 / np.sqrt(n * d) and abs(z.std() - 1) < 5 / np.sqrt(n * d)
+    if n < 3:
+        return                                                    # no covariance to speak of
+    f = orc.mvn_factor_cholesky((1 - 0.98 ** 2) * np.atleast_2d(cov))
     want = orc.liu_west(prior[:, want_idx], z, f, 0.98, scale, mean)
     got = alt.particles[:, :n].cpu().numpy()
     spread = prior.std(axis=1, keepdims=True)

@@ -170,6 +170,7 @@ def test_multi_point_update_matches_point_by_point(obe):
     b = obe.OptBayesExptSweeper(sc['model'], inp['setting_values'], inp['prior'], inp['cons'], noise_parameter_index=3,
                                 scale=False, seed=1, auto_resample=False)
     a.fused_sweep, b.fused_sweep = True, False
+    a._sweep_chunk = 128                                        # the whole sweep in one launch
     neff = []
     for x, y in zip(xs, ys):
         b.pdf_update(((np.array([x]),), np.array([y])))
@@ -184,6 +185,6 @@ def test_multi_point_update_matches_point_by_point(obe):
     # with the resample test on, the kernel reports the first point whose N_eff falls below the threshold
     c = obe.OptBayesExptSweeper(sc['model'], inp['setting_values'], inp['prior'], inp['cons'], noise_parameter_index=3,
                                 scale=False, seed=1)
-    first, ratio = c._multi_update(xs, ys)
+    first, ratio = c._multi_update(xs, ys)                      # (one launch regardless of the chunk policy)
     want = int(np.argmax(np.array(neff) / 300_000 < 0.5))
     assert first == want and abs(ratio - neff[want] / 300_000) < 1e-10
