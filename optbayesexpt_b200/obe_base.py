@@ -158,6 +158,12 @@ class OptBayesExpt(ParticlePDF):
         y = self._eval_parameters_dev(onesettingset)
         return y[:, :self.n_particles].cpu().numpy()
 
+    def eval_over_all_parameters_dev(self, onesettingset):
+        """The model over all particles at one setting, left on the device: pass the result as
+        ``pdf_update(record, y_model_data=...)`` to overlap the model pass with the instrument's measurement
+        (obe_base.py:374-385) without a host round trip."""
+        return self._eval_parameters_dev(onesettingset)
+
     def _eval_parameters_dev(self, onesettingset):
         y = self._torch.empty((self.n_channels, self._buf.ld), dtype=self._torch.float64, device=self._buf.device)
         self._check(self._lib.obe_eval_parameters(self._model, self._cs(),
@@ -204,10 +210,19 @@ class OptBayesExpt(ParticlePDF):
                                              None if sigma is None else _lib.darr(sigma, _lib.MAX_CHANNELS),
                                              _lib.iarr(noise_index), n_lik, use_choke, choke, pivot, self._stream()))
         else:
-            y = self._torch.zeros((self.n_channels, self._buf.ld), dtype=self._torch.float64,
-                                  device=self._buf.device)
-            y[:, :self.n_particles].copy_(self._torch.as_tensor(
-                np.ascontiguousarray(np.asarray(y_model_data, dtype=np.float64).reshape(self.n_channels, -1))))
+            torch = self._torch
+            if isinstance(y_model_data, torch.Tensor) and y_model_data.is_cuda and y_model_data.dtype == torch.float64 \
+                    and y_model_data.dim() == 2 and y_model_data.shape == (self.n_channels, self._buf.ld) \
+                    and y_model_data.is_contiguous():
+                y = y_model_data          # eval_over_all_parameters_dev: the model pass was prefetched on the device
+            else:
+                y = torch.zeros((self.n_channels, self._buf.ld), dtype=torch.float64, device=self._buf.device)
+                if isinstance(y_model_data, torch.Tensor):
+                    src = y_model_data.to(dtype=torch.float64, device=self._buf.device).reshape(self.n_channels, -1)
+                else:
+                    src = torch.as_tensor(np.ascontiguousarray(
+                        np.asarray(y_model_data, dtype=np.float64).reshape(self.n_channels, -1)))
+                y[:, :self.n_particles].copy_(src[:, :self.n_particles])
             self._check(self._lib.obe_update_from_y(self._cs(), C.c_void_p(y.data_ptr()), self._buf.ld,
                                                     self.n_channels, _lib.darr(y_meas, _lib.MAX_CHANNELS),
                                                     None if sigma is None else _lib.darr(sigma, _lib.MAX_CHANNELS),

@@ -120,6 +120,9 @@ def reduce_best(pairs):
     return best_i, best_v
 
 
+REPLICATE_GRID_MAX = 131072
+
+
 def setting_slice(n_settings, rank, world):
     lo = n_settings * rank // world
     hi = n_settings * (rank + 1) // world
@@ -211,7 +214,14 @@ class ShardedOptBayesExpt(OptBayesExpt):
         self._plan = torch.zeros(_lib.PLAN_LEN, dtype=torch.float64, device=dev)
         self._check(self._lib.obe_set_uniform_total(self._cs(), self.n_total, self._stream()))
         n_set = len(self.setting_indices)
-        self._s_lo, self._s_hi = setting_slice(n_set, self._comm.rank, self._comm.world)
+        # The utility kernel is latency-bound (one thread per setting, ~30 us) up to ~1e5 settings: below that
+        # every rank evaluates the whole grid -- same draws, same settings, so the same argmax everywhere --
+        # and the selection needs no collective at all.  Larger grids are sliced over the ranks.
+        self._replicate_grid = n_set <= REPLICATE_GRID_MAX
+        if self._replicate_grid:
+            self._s_lo, self._s_hi = 0, n_set
+        else:
+            self._s_lo, self._s_hi = setting_slice(n_set, self._comm.rank, self._comm.world)
         piv = torch.from_numpy(self._pivot.copy()).to(dev)     # a common pivot: rank 0's estimate
         self._pivot = self._comm.allgather(piv)[0].cpu().numpy()
         self._section = 0          # 0: draw with the plan's current-weight totals, 1: post-resample
@@ -393,6 +403,10 @@ class ShardedOptBayesExpt(OptBayesExpt):
     def opt_setting(self):
         import torch
         self._utility_dev_run()
+        if self._replicate_grid:
+            best = int(self._best_dev.cpu()[0])
+            self.last_setting_index = best
+            return tuple(self.allsettings[:, best])
         pairs = self._comm.allgather(self._best_dev).cpu()
         vals = pairs[:, 1].contiguous().view(torch.float64).numpy()
         idxs = pairs[:, 0].numpy()
@@ -407,6 +421,8 @@ class ShardedOptBayesExpt(OptBayesExpt):
         self._utility_dev_run()
         n_set = len(self.setting_indices)
         world = self._comm.world
+        if self._replicate_grid:
+            return self._utility_dev[:n_set].cpu().numpy()
         width = max(setting_slice(n_set, r, world)[1] - setting_slice(n_set, r, world)[0] for r in range(world))
         buf = torch.zeros(width, dtype=torch.float64, device=self._buf.device)
         buf[:self._s_hi - self._s_lo] = self._utility_dev[self._s_lo:self._s_hi]

@@ -133,6 +133,12 @@ def test_ref_optbayesexpt_likelihood_and_update(obe):           # tests/test_opt
     eng2 = _fake_obe(obe)
     eng2.pdf_update(((1,), 5.0, 1.0), y_model_data=ymodel)
     assert_allclose(eng2.particle_weights, lkl / np.sum(lkl), rtol=1e-15)
+    # ... and with the model pass prefetched on the device (no host round trip)
+    eng3 = _fake_obe(obe)
+    ydev = eng3.eval_over_all_parameters_dev((1,))
+    assert ydev.is_cuda and ydev.shape[0] == 1
+    eng3.pdf_update(((1,), 5.0, 1.0), y_model_data=ydev)
+    assert_allclose(eng3.particle_weights, lkl / np.sum(lkl), rtol=1e-15)
 
 
 def test_ref_zinference_infer(obe):                             # tests/test_zinference.py:89-108

@@ -27,8 +27,10 @@ def _worker(rank, world, port, out):
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         import optbayesexpt_b200 as obe
+        from optbayesexpt_b200 import sharded as _sh
         from optbayesexpt_b200.sharded import ShardedOptBayesExpt
         from oracle.scenarios import build_inputs, by_name
+        _sh.REPLICATE_GRID_MAX = 0      # this test slices the setting grid over the ranks (the other replicates it)
         sc = by_name('c1_find_peak')
         n = 50000
         inp = build_inputs(sc, n)
