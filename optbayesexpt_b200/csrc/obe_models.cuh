@@ -125,4 +125,21 @@ struct ObeLockinCoil {
     }
 };
 
+// update-pass variant: 1/(a + ib) = (a - ib) / (a^2 + b^2) with Newton-refined reciprocals instead of the
+// four IEEE divisions and two branches of numpy's complex division (the utility pass keeps the exact
+// functor above, where bit-equality with the reference decides the argmax).  2-3 ulp on y.
+template <>
+struct ObeUpdateEval<ObeLockinCoil> {
+    __device__ static __forceinline__ void eval(const double* s, const double* p, const double*, double* y) {
+        const double w = s[0], L = p[0], R = p[1], C = p[2];
+        const double wl = w * L;
+        const double i1 = obe_rcp_fast(fma(R, R, wl * wl));
+        const double tr = R * i1;                       // Re 1/(R + i wL)
+        const double ti = fma(w, C, -wl * i1);          // Im 1/(R + i wL) + wC
+        const double i2 = obe_rcp_fast(fma(tr, tr, ti * ti));
+        y[0] = tr * i2;
+        y[1] = -ti * i2;
+    }
+};
+
 #endif  // OBE_MODELS_CUH
