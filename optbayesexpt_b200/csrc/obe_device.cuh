@@ -495,40 +495,6 @@ __device__ __forceinline__ void obe_update_vec(const ObeUpdateArgs& a, const dou
     }
 }
 
-// Exclusive block scan (sum) of one double per thread for NW warps; total in *tot.  `sm` holds NW + 2 doubles.
-// Uses bar.sync on barrier `bar_id` over NW*32 threads so it also works among the consumers only.
-template <int NW>
-__device__ __forceinline__ double obe_block_excl_sum(double v, double* sm, double* tot, int bar_id) {
-    const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) % NW;
-    double x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-    }
-    obe_named_bar(bar_id, NW * 32);
-    if (lane == 31) sm[warp] = x;
-    obe_named_bar(bar_id, NW * 32);
-    if (warp == 0) {
-        double xs = (lane < NW) ? sm[lane] : 0.0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double y = __shfl_up_sync(0xffffffffu, xs, o);
-            if (lane >= o) xs += y;
-        }
-        double ex = __shfl_up_sync(0xffffffffu, xs, 1);  // exclusive base of each warp
-        if (lane == 0) ex = 0.0;
-        if (lane < NW) sm[lane] = ex;
-        if (lane == 31) sm[NW] = xs;
-    }
-    obe_named_bar(bar_id, NW * 32);
-    const double base = sm[warp];
-    double ex = __shfl_up_sync(0xffffffffu, x, 1);
-    if (lane == 0) ex = 0.0;
-    *tot = sm[NW];
-    return base + ex;
-}
-
 // W chunks of NW*32 consecutive elements scanned at once: ex[e] = exclusive scan of v[e] over the
 // block's threads within chunk e (Kogge-Stone over lanes, then over the warp totals), tot[e] = the
 // chunk's total.  One set of barriers serves all W chunks, so a single block walks a long array in
