@@ -680,16 +680,24 @@ struct SysCtx {
 // slot q (before the clamp to the tile's last live particle), visible to the whole block.
 __device__ __forceinline__ void sys_unit_ancestors(const SysCtx& c, long long k, long long Hk, long long Hk1,
                                                    int rel_begin, double* sm, int* smx, unsigned short* anc_s) {
+    // Barrier budget per unit: 5.  Every small shared array (sm, smx) and anc_s is written only after a barrier
+    // that follows its previous readers, INCLUDING the readers of the previous unit (the caller's loop has no
+    // barrier of its own): sm after (e) of the previous unit, the anc_s clear after (a), smx after (a)/(c).
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int span = (int)(Hk1 - Hk);
     const int n_chunk = min(rel_begin + OBE_OUT_CHUNK, span) - rel_begin;
-    // clear the marks (OBE_SPT per thread, 16-byte stores)
-#pragma unroll
-    for (int v = 0; v < OBE_SPT / 8; ++v)
-        *reinterpret_cast<uint4*>(&anc_s[tid * OBE_SPT + 8 * v]) = make_uint4(0u, 0u, 0u, 0u);
     // ---- 1. end slot of every particle of the tile, in chunk coordinates [0, n_chunk]
     double cn[OBE_EPT];
-    tile_cdf_blocked(c.w_in, c.prefix, k, c.n_in, c.inv_total, cn, sm, c.cdf_offset, c.last_shard, c.wuni_in);
+    tile_cdf_blocked<false>(c.w_in, c.prefix, k, c.n_in, c.inv_total, cn, sm, c.cdf_offset, c.last_shard,
+                            c.wuni_in);                                                        // barrier (a)
+    // clear the marks of the slots in use (OBE_SPT per thread, 16-byte stores); the previous unit's readers of
+    // anc_s are behind barrier (a)
+    const bool my_slots_live = tid * OBE_SPT < n_chunk;
+    if (my_slots_live) {
+#pragma unroll
+        for (int v = 0; v < OBE_SPT / 8; ++v)
+            *reinterpret_cast<uint4*>(&anc_s[tid * OBE_SPT + 8 * v]) = make_uint4(0u, 0u, 0u, 0u);
+    }
     const long long base = k * OBE_TILE;
     const int lastrel = (int)(min(c.n_in, base + OBE_TILE) - 1 - base);
     const double chunk0 = (double)(Hk + rel_begin);          // exact: < 2^53
@@ -714,7 +722,7 @@ __device__ __forceinline__ void sys_unit_ancestors(const SysCtx& c, long long k,
     int ex = __shfl_up_sync(0xffffffffu, x, 1);
     if (lane == 0) ex = 0;
     if (lane == 31) smx[warp] = x;
-    __syncthreads();                       // also orders the clearing of anc_s before the marks
+    __syncthreads();                                         // barrier (b): smx; the cleared marks
     ex = max(ex, obe_prev_warps_max8(smx, warp, lane));
     // ---- 2. a particle that owns slots of the chunk marks the first of them
     int prev = ex;                         // end slot of the previous particle
@@ -724,20 +732,23 @@ __device__ __forceinline__ void sys_unit_ancestors(const SysCtx& c, long long k,
         if (end > prev) anc_s[prev] = (unsigned short)(tid * OBE_EPT + e);
         prev = end;
     }
-    __syncthreads();
-    // max-scan of the marks over the chunk's slots (blocked: OBE_SPT consecutive slots per thread)
+    __syncthreads();                                         // barrier (c): the marks
+    // max-scan of the marks over the chunk's slots (blocked: OBE_SPT consecutive slots per thread); threads
+    // whose slots lie beyond the chunk only take part in the shuffles
     {
         int m[OBE_SPT];
         int runm = 0;
+        if (my_slots_live) {
 #pragma unroll
-        for (int v = 0; v < OBE_SPT / 8; ++v) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(&anc_s[tid * OBE_SPT + 8 * v]);
-            const unsigned int wds[4] = {raw.x, raw.y, raw.z, raw.w};
+            for (int v = 0; v < OBE_SPT / 8; ++v) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(&anc_s[tid * OBE_SPT + 8 * v]);
+                const unsigned int wds[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int val = (int)((wds[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
-                runm = max(runm, val);
-                m[8 * v + e] = runm;
+                for (int e = 0; e < 8; ++e) {
+                    const int val = (int)((wds[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
+                    runm = max(runm, val);
+                    m[8 * v + e] = runm;
+                }
             }
         }
         int xm = runm;
@@ -748,22 +759,23 @@ __device__ __forceinline__ void sys_unit_ancestors(const SysCtx& c, long long k,
         }
         int exm = __shfl_up_sync(0xffffffffu, xm, 1);
         if (lane == 0) exm = 0;
-        __syncthreads();                   // smx is reused
-        if (lane == 31) smx[warp] = xm;
-        __syncthreads();
+        if (lane == 31) smx[warp] = xm;                      // (the readers of smx are behind barrier (c))
+        __syncthreads();                                     // barrier (d)
         exm = max(exm, obe_prev_warps_max8(smx, warp, lane));
+        if (my_slots_live) {
 #pragma unroll
-        for (int v = 0; v < OBE_SPT / 8; ++v) {
-            unsigned int packed[4];
+            for (int v = 0; v < OBE_SPT / 8; ++v) {
+                unsigned int packed[4];
 #pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-                const unsigned int a0 = (unsigned int)max(m[8 * v + e], exm), a1v = (unsigned int)max(m[8 * v + e + 1], exm);
-                packed[e >> 1] = a0 | (a1v << 16);
+                for (int e = 0; e < 8; e += 2) {
+                    const unsigned int a0 = (unsigned int)max(m[8 * v + e], exm), a1v = (unsigned int)max(m[8 * v + e + 1], exm);
+                    packed[e >> 1] = a0 | (a1v << 16);
+                }
+                *reinterpret_cast<uint4*>(&anc_s[tid * OBE_SPT + 8 * v]) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
-            *reinterpret_cast<uint4*>(&anc_s[tid * OBE_SPT + 8 * v]) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
     }
-    __syncthreads();
+    __syncthreads();                                         // barrier (e): the ancestors
 }
 
 template <int D, class FT>
@@ -937,14 +949,14 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_ANC_BLOCKS_PER_SM) k_sys_ance
         const int rel_begin = (unit - a.unit_start[k]) * OBE_OUT_CHUNK;
         sys_unit_ancestors(c, k, Hk, Hk1, rel_begin, sm, smx, anc_s);
         const unsigned int base = (unsigned int)k * OBE_TILE;
-        const int lastrel = (int)(min(c.n_in, (long long)base + OBE_TILE) - 1 - (long long)base);
         const long long o0 = Hk + rel_begin - c.slot_begin;
         const long long room = c.cap_out - o0;                 // capacity overflow is flagged in the plan
         int n_out = min(rel_begin + OBE_OUT_CHUNK, (int)(Hk1 - Hk)) - rel_begin;
         if (room < (long long)n_out) n_out = room > 0 ? (int)room : 0;
         unsigned int* __restrict__ dst = a.anc + o0;
-        for (int q = threadIdx.x; q < n_out; q += OBE_THREADS) dst[q] = base + (unsigned int)min((int)anc_s[q], lastrel);
-        __syncthreads();
+        // (marks are indices of live particles, so no clamp; the next unit touches anc_s only behind its first
+        // barrier, so no barrier here either)
+        for (int q = threadIdx.x; q < n_out; q += OBE_THREADS) dst[q] = base + (unsigned int)anc_s[q];
     }
 }
 

@@ -1111,6 +1111,9 @@ __device__ __forceinline__ void tile_load_blocked(const double* __restrict__ w, 
     }
 }
 
+// PRE_SYNC = false: the caller guarantees that a block barrier separates the previous readers of `sm`
+// from this call (saves one barrier per tile in loops that have their own).
+template <bool PRE_SYNC = true>
 __device__ __forceinline__ void tile_scan_blocked(const double (&v)[OBE_EPT], double (&incl)[OBE_EPT],
                                                   double* sm /*8*/) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1125,7 +1128,7 @@ __device__ __forceinline__ void tile_scan_blocked(const double (&v)[OBE_EPT], do
     }
     double ex = __shfl_up_sync(0xffffffffu, x, 1);
     if (lane == 0) ex = 0.0;
-    __syncthreads();
+    if (PRE_SYNC) __syncthreads();
     if (lane == 31) sm[warp] = x;
     __syncthreads();
     double wb = 0.0;
@@ -1138,6 +1141,7 @@ __device__ __forceinline__ void tile_scan_blocked(const double (&v)[OBE_EPT], do
 // normalised canonical CDF values of this thread's 8 elements of tile k
 // Sharded clouds: `offset` is the summed weight of all lower-ranked shards and inv_total the
 // reciprocal of the GLOBAL total; last_shard marks the shard that holds the global last particle.
+template <bool PRE_SYNC = true>
 __device__ __forceinline__ void tile_cdf_blocked(const double* __restrict__ w, const double* __restrict__ prefix,
                                                  long long k, long long n, double inv_total,
                                                  double (&cn)[OBE_EPT], double* sm, double offset = 0.0,
@@ -1145,7 +1149,7 @@ __device__ __forceinline__ void tile_cdf_blocked(const double* __restrict__ w, c
     double v[OBE_EPT], incl[OBE_EPT];
     const long long base = k * OBE_TILE;
     tile_load_blocked(w, base, n, v, wuni);
-    tile_scan_blocked(v, incl, sm);
+    tile_scan_blocked<PRE_SYNC>(v, incl, sm);
     const double p0 = obe_add(offset, prefix[k]);
     const long long last = obe_min_ll(n, base + OBE_TILE) - 1;
     const long long i0 = base + (long long)threadIdx.x * OBE_EPT;
