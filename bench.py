@@ -403,6 +403,22 @@ def main():
         ms_total, t_upd, t_res, t_sel = [float(v) for v in tt.cpu()]
     ms_step = ms_total / args.steps
 
+    # ---------------- the cycle without a resample (cycle_noresample) ------------------
+    # update + select only; the weight row is explicit here, so the update moves 8N(d+2) bytes.  Single GPU
+    # only (the sharded plan kernel would need a no-op resample to keep the ranks in step).
+    ms_nores = None
+    if world == 1:
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for t in range(3):
+            eng.run_cycle_async(fixed[t], resample=False, select=True)
+        n0.record()
+        for t in range(args.steps):
+            eng.run_cycle_async(fixed[args.warmup + t], resample=False, select=True)
+        n1.record()
+        torch.cuda.synchronize()
+        ms_nores = n0.elapsed_time(n1) / args.steps
+        eng.resample()                       # back to a healthy cloud for the closed loop below
+
     # ---------------- end to end through the reference-shaped API, closed loop -------------------
     x = eng.opt_setting()
     for _ in range(max(3, args.warmup // 2)):
@@ -456,6 +472,9 @@ def main():
         'kernels_ms': {'update': t_upd, 'resample': t_res, 'draw+utility+argmax': t_sel},
         'kernels_gbs': {'update': b_upd / world / (t_upd * 1e-3) / 1e9, 'resample': gbs_res},
         'cycle_hbm_frac': b_cycle / world / (ms_step * 1e-3) / 1e9 / peak,
+        'cycle_noresample': None if ms_nores is None else {
+            'ms_per_step': ms_nores, 'cycles_per_s': 1e3 / ms_nores,
+            'hbm_frac': (8.0 * n_total * (d + 2) + b_sel) / (ms_nores * 1e-3) / 1e9 / peak},
         'clocks': clocks,
     }
     if not args.no_cpu_baseline:

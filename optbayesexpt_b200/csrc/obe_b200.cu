@@ -2092,10 +2092,21 @@ int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* set
     a.log_form = log_form; a.method = method; a.kld_noise = kld_noise_dev;
     if (var_noise) for (int c = 0; c < m->nch; ++c) a.var_noise[c] = var_noise[c];
     for (int j = 0; j < m->ncons; ++j) a.cons[j] = constants[j];
-    int64_t blocks = (n_settings + OBE_THREADS - 1) / OBE_THREADS;
-    if (blocks > (int64_t)obe_sms() * 8) blocks = (int64_t)obe_sms() * 8;
-    const size_t smem = (size_t)k * (m->np_model > 0 ? m->np_model : 1) * sizeof(double);
+    size_t smem = (size_t)k * (m->np_model > 0 ? m->np_model : 1) * sizeof(double);
     if (smem > 48 * 1024) return obe_fail("n_draws too large for shared memory%s%s");
+    // variance utility: several lanes per setting while the grid is too small to fill the GPU anyway (the
+    // one-thread-per-setting walk is pure latency there; on a large grid the idle lanes of the sequential sums
+    // would cost throughput: 1e5 settings take 42 us with one lane, 60 us with eight) and the K curves of a
+    // CTA's settings fit in shared memory
+    a.lanes = 1;
+    const int64_t resident = (int64_t)obe_sms() * 8 * OBE_THREADS;
+    for (int lanes = 8; lanes >= 2 && method == 0 && k >= 8; lanes >>= 1) {
+        const size_t split = smem + (size_t)(OBE_THREADS / lanes) * m->nch * k * sizeof(double);
+        if (n_settings * lanes <= resident / 2 && split <= 48 * 1024) { a.lanes = lanes; smem = split; break; }
+    }
+    const int64_t per_block = OBE_THREADS / a.lanes;
+    int64_t blocks = (n_settings + per_block - 1) / per_block;
+    if (blocks > (int64_t)obe_sms() * 8) blocks = (int64_t)obe_sms() * 8;
     return launch_kernel(m->f_utility, (int)blocks, smem, (cudaStream_t)stream, &a);
 }
 

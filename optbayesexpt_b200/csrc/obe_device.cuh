@@ -127,6 +127,7 @@ struct ObeUtilityArgs {
     int noise_from_stats;
     int log_form;
     int method;              // 0 variance, 1 max-min, 2 pseudo (entropy), 3 full KLD
+    int lanes;               // variance utility: lanes per setting (1: one thread walks all K draws)
     const double* kld_noise; // method 3: (K, C) noise values added to the model outputs
     double var_noise[OBE_MAX_CH];
     double cons[OBE_MAX_CONS];
@@ -1334,6 +1335,52 @@ __device__ void obe_utility_body(const ObeUtilityArgs& a) {
     double best = -1.0;
     long long besti = -1;
     bool have = false;
+    if (a.method == 0 && a.lanes > 1) {
+        // Variance utility, `lanes` threads per setting.  One thread per setting walks 2K dependent model
+        // evaluations (~30 us of pure latency at K = 30, whatever the grid size).  Here the lanes of a group
+        // evaluate the K curves of their setting side by side into shared memory, ONCE, and the group's first
+        // lane does numpy's two sequential passes over the stored values: same operations in the same order
+        // (bit-identical utility), a critical path of K/lanes evaluations plus 2K additions.
+        const int G = a.lanes, spb = (int)blockDim.x / G;
+        const int sl = tid / G, g = tid % G;
+        double* yv = sdraw + K * Model::NP + (long long)sl * Model::NCH * K;       // [NCH][K] of this setting
+        for (long long s0 = (long long)blockIdx.x * spb; s0 < a.n_settings; s0 += (long long)gridDim.x * spb) {
+            const long long s = s0 + sl;
+            const bool valid = s < a.n_settings;
+            if (valid) {
+                double st[Model::NS > 0 ? Model::NS : 1], y[Model::NCH];
+#pragma unroll
+                for (int j = 0; j < Model::NS; ++j) st[j] = a.settings[j * a.lds + s];
+                for (int k = g; k < K; k += G) {
+                    Model::eval(st, sdraw + k * Model::NP, a.cons, y);
+#pragma unroll
+                    for (int c = 0; c < Model::NCH; ++c) yv[c * K + k] = y[c];
+                }
+            }
+            __syncwarp();
+            if (valid && g == 0) {
+                double u = 0.0;
+#pragma unroll
+                for (int c = 0; c < Model::NCH; ++c) {
+                    const double* yc = yv + c * K;
+                    double mean = 0.0, ss = 0.0;
+                    for (int k = 0; k < K; ++k) mean = obe_add(mean, yc[k]);
+                    mean = obe_div(mean, kd);
+                    for (int k = 0; k < K; ++k) {
+                        const double dlt = obe_sub(yc[k], mean);
+                        ss = obe_add(ss, obe_mul(dlt, dlt));
+                    }
+                    const double r = obe_div(obe_div(ss, kd), var_n[c]);
+                    u = obe_add(u, a.log_form ? log(obe_add(1.0, r)) : r);
+                }
+                if (a.cost) u = obe_div(u, a.cost[s]);
+                a.utility[s] = u;
+                const bool unan = (u != u), bnan = (best != best);
+                if (!have || (!bnan && (unan || u > best))) { best = u; besti = s; have = true; }
+            }
+            __syncwarp();
+        }
+    } else
     for (long long s = (long long)blockIdx.x * blockDim.x + tid; s < a.n_settings;
          s += (long long)gridDim.x * blockDim.x) {
         double st[Model::NS > 0 ? Model::NS : 1];
