@@ -7,6 +7,8 @@ raises, it never falls back.
 import ctypes as C
 import os
 
+import numpy as np
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('OBE_B200_LIB', os.path.join(HERE, 'libobe_b200.so'))   # override: A/B builds
 
@@ -140,13 +142,29 @@ def check(rc):
 
 
 def darr(values, n=None):
-    """Host double array for a by-value kernel argument (or None)."""
+    """Host double array for a by-value kernel argument (or None), zero-padded to n entries."""
     if values is None:
         return None
-    vals = [float(v) for v in values]
-    if n is not None and len(vals) < n:
-        vals = vals + [0.0] * (n - len(vals))
-    return (C.c_double * max(len(vals), 1))(*vals) if vals else (C.c_double * 1)(0.0)
+    a = np.ascontiguousarray(values, dtype=np.float64).reshape(-1)
+    m = a.shape[0]
+    out = (C.c_double * max(m, n or 0, 1))()
+    if m:
+        C.memmove(out, a.ctypes.data, 8 * m)
+    return out
+
+
+def dptr(array):
+    """Pointer to a contiguous float64 numpy array (no copy; the array must outlive the call)."""
+    return array.ctypes.data_as(_PD)
+
+
+def raw_stream(torch):
+    """The current CUDA stream as a void*; uses torch's raw accessor when it exists (it is several times
+    cheaper than going through torch.cuda.current_stream(), and this runs four times per cycle)."""
+    get = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+    if get is not None:
+        return C.c_void_p(get(torch.cuda.current_device()))
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def iarr(values):

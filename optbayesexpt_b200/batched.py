@@ -112,7 +112,7 @@ class BatchedOptBayesExpt:
 
     # ---- plumbing
     def _stream(self):
-        return C.c_void_p(self._torch.cuda.current_stream().cuda_stream)
+        return _lib.raw_stream(self._torch)
 
     def _bs(self):
         return C.byref(self._batch)

@@ -314,7 +314,10 @@ class OptBayesExpt(ParticlePDF):
     def _utility_dev_run(self):
         """draws -> utility over the grid -> argmax, all on the device; returns nothing."""
         torch = self._torch
-        draws = self._randdraw_dev(self.N_DRAWS)
+        dd = getattr(self, '_draws_dev', None)
+        if dd is None or dd.shape[1] != self.N_DRAWS:
+            dd = self._draws_dev = torch.empty((self.n_dims, self.N_DRAWS), dtype=torch.float64, device=self._buf.device)
+        draws = self._randdraw_dev(self.N_DRAWS, out=dd)
         n_set = len(self.setting_indices)
         if self._noise_from_stats():
             self._ensure_moments()

@@ -69,7 +69,7 @@ class ParticlePDF:
         self._pivot = p[:, :min(self.n_particles, 65536)].mean(dim=1).cpu().numpy().astype(np.float64)
 
     def _stream(self):
-        return C.c_void_p(self._torch.cuda.current_stream().cuda_stream)
+        return _lib.raw_stream(self._torch)
 
     def _cs(self, buf=None):
         return C.byref((buf or self._buf).struct())
@@ -85,9 +85,13 @@ class ParticlePDF:
             self._host_weights = None
 
     def _fetch_stats(self):
-        out = (C.c_double * _lib.STATS_LEN)()
-        self._check(self._lib.obe_fetch_stats(self._cs(), out, self._stream()))
-        self._stats = np.frombuffer(out, dtype=np.float64).copy()
+        pin = getattr(self, '_stats_pin', None)
+        if pin is None:                       # pinned landing buffer: the D2H copy is a real async DMA
+            pin = self._stats_pin = self._torch.zeros(_lib.STATS_LEN, dtype=self._torch.float64).pin_memory()
+            self._stats_pin_np = pin.numpy()
+            self._stats_pin_ptr = C.cast(pin.data_ptr(), C.POINTER(C.c_double))
+        self._check(self._lib.obe_fetch_stats(self._cs(), self._stats_pin_ptr, self._stream()))
+        self._stats = self._stats_pin_np.copy()
         return self._stats
 
     def _refresh(self, mask_le=0, mask_lt=0, renormalise=0):
@@ -328,10 +332,11 @@ class ParticlePDF:
         """(n_dims, n_draws) weighted random draws (particlepdf.py:312-345)."""
         return self._randdraw_dev(n_draws).cpu().numpy()
 
-    def _randdraw_dev(self, n_draws):
+    def _randdraw_dev(self, n_draws, out=None):
         u = self.rng.random(n_draws)
-        draws = self._torch.empty((self.n_dims, n_draws), dtype=self._torch.float64, device=self._buf.device)
-        self._check(self._lib.obe_draw(self._cs(), _lib.darr(u), int(n_draws), C.c_void_p(draws.data_ptr()),
+        draws = out if out is not None else self._torch.empty((self.n_dims, n_draws), dtype=self._torch.float64,
+                                                               device=self._buf.device)
+        self._check(self._lib.obe_draw(self._cs(), _lib.dptr(u), int(n_draws), C.c_void_p(draws.data_ptr()),
                                        None, self._stream()))
         return draws
 
