@@ -71,7 +71,11 @@ typedef struct obe_model* obe_model_t; /* opaque device functor for model_functi
 /* ---- library ---------------------------------------------------------------------------- */
 int obe_abi_version(void);
 const char* obe_last_error(void);
-int obe_device_count(void);                 /* 0 without a usable CUDA device                */
+int obe_device_count(void);
+/* Tuning knobs for tests and A/B runs.  "plan_cluster_min_tiles": tile count (2048 particles each) above
+ * which the resample plan runs on a thread-block cluster of 8 CTAs instead of one CTA (default 8192).
+ * Returns 0, or -1 for an unknown name. */
+int obe_set_option(const char* name, int64_t value);                 /* 0 without a usable CUDA device                */
 int64_t obe_num_tiles(int64_t n);
 size_t obe_scratch_bytes(int64_t n);        /* per-cloud scratch (partials, plans, counters) */
 size_t obe_select_scratch_bytes(int64_t n_settings);

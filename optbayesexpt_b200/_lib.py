@@ -59,6 +59,7 @@ SIGNATURES = {
     'obe_abi_version': (C.c_int, []),
     'obe_last_error': (C.c_char_p, []),
     'obe_device_count': (C.c_int, []),
+    'obe_set_option': (C.c_int, [C.c_char_p, C.c_int64]),
     'obe_num_tiles': (C.c_int64, [C.c_int64]),
     'obe_scratch_bytes': (C.c_size_t, [C.c_int64]),
     'obe_select_scratch_bytes': (C.c_size_t, [C.c_int64]),

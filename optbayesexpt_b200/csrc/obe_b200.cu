@@ -10,6 +10,7 @@
 //   obe_base.py:463-489,628-655,748                               -> obe_utility_body (obe_device.cuh)
 //   obe_base.py:778-789 good_setting                              -> k_pick_weights + k_tile_scan + k_draw
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <nvrtc.h>
 #include <dlfcn.h>
 #include <stdint.h>
@@ -634,6 +635,133 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
     }
     const int total_units = icarry;
     if (t == 0) unit_start[n_tiles] = total_units;
+}
+
+// The same plan for large clouds on a thread-block cluster of 8 CTAs: every CTA takes a contiguous
+// segment of the tiles (48 829 tiles at 1e8 particles -> one round of 8 x 1024 per CTA instead of six rounds
+// of a single CTA per pass), scans it locally, and the eight segment totals (running max of H, units) are
+// exchanged through distributed shared memory -- each CTA writes its total into every CTA's copy, one
+// cluster barrier, then every CTA folds the totals of the segments before it into its own results.
+#define OBE_PLAN_CLUSTER 8
+static int64_t g_plan_cluster_min_tiles = 8192;   /* obe_set_option("plan_cluster_min_tiles") */
+#ifndef OBE_PLAN_CLUSTER_MIN_TILES
+#define OBE_PLAN_CLUSTER_MIN_TILES 8192     /* below: one CTA does every pass in a single round anyway */
+#endif
+__global__ void __cluster_dims__(OBE_PLAN_CLUSTER, 1, 1) __launch_bounds__(OBE_SCAN_THREADS)
+k_sys_plan_cluster(const double* __restrict__ prefix, long long n_tiles, long long n_total, double u0,
+                   double cdf_offset, double cdf_total, long long slot_begin, long long slot_end,
+                   long long* __restrict__ H, int* __restrict__ unit_start, int* __restrict__ unit_tile,
+                   const long long* __restrict__ n_dev, const double* __restrict__ plan) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = (int)cluster.block_rank();
+    __shared__ long long sml[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
+    __shared__ int smi[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
+    __shared__ long long xmax[OBE_PLAN_CLUSTER];     // segment maxima of H, every CTA holds all eight
+    __shared__ int xsum[OBE_PLAN_CLUSTER];           // segment unit counts
+    __shared__ long long s_next;                     // raw H of the first tile after this segment
+    const int t = threadIdx.x;
+    if (n_dev) n_tiles = (*n_dev + OBE_TILE - 1) / OBE_TILE;
+    if (plan) {
+        n_total = (long long)plan[OBE_PL_NTOTAL]; u0 = plan[OBE_PL_U0];
+        cdf_offset = plan[OBE_PL_OFFSET]; cdf_total = plan[OBE_PL_TOTAL];
+        slot_begin = (long long)plan[OBE_PL_SLOT0]; slot_end = (long long)plan[OBE_PL_SLOT1];
+    }
+    const double inv_total = 1.0 / (cdf_total > 0.0 ? cdf_total : prefix[n_tiles]);
+    const double nd = (double)n_total, inv_n = 1.0 / nd, tol = 2e-15 * nd;
+    const long long seg = (n_tiles + OBE_PLAN_CLUSTER - 1) / OBE_PLAN_CLUSTER;
+    const long long k_lo = min((long long)r * seg, n_tiles), k_hi = min(k_lo + seg, n_tiles);   // tiles [k_lo, k_hi)
+    auto raw_h = [&](long long k, double pk) -> long long {
+        const long long h = (k == 0) ? slot_begin
+                                     : (k >= n_tiles ? slot_end
+                                                     : (long long)comb_count_d(obe_mul(obe_add(cdf_offset, pk), inv_total),
+                                                                               u0, inv_n, nd, tol));
+        return min(max(h, slot_begin), slot_end);
+    };
+    constexpr int NWP = OBE_SCAN_THREADS / 32;
+    constexpr long long ROUND = (long long)OBE_SCANW * OBE_SCAN_THREADS;
+    // ---- raw H of the segment + local running max (first sweep; the carry starts at the identity)
+    if (t == 0) {
+        s_next = raw_h(k_hi, k_hi < n_tiles ? prefix[k_hi] : 0.0);
+        if (k_hi == n_tiles) H[n_tiles] = slot_end;
+    }
+    long long hcarry = -1;
+    for (long long base = k_lo; base < k_hi; base += ROUND) {
+        double pk[OBE_SCANW];
+        long long h[OBE_SCANW], ex[OBE_SCANW], tot[OBE_SCANW];
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            pk[e] = (k < k_hi) ? prefix[k] : 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            h[e] = (k < k_hi) ? raw_h(k, pk[e]) : -1;
+        }
+        obe_block_excl_scanw<long long, NWP>(h, ex, tot, sml, ObeOpMax(), -1ll, 0);
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            if (k < k_hi) H[k] = max(max(hcarry, ex[e]), h[e]);
+            hcarry = max(hcarry, tot[e]);
+        }
+        __syncthreads();
+    }
+    if (t < OBE_PLAN_CLUSTER) *cluster.map_shared_rank(&xmax[r], t) = hcarry;
+    cluster.sync();
+    long long floor_h = slot_begin;                  // running max of everything before this segment
+    for (int j = 0; j < r; ++j) floor_h = max(floor_h, xmax[j]);
+    const long long next_h = max(max(floor_h, hcarry), s_next);         // final H[k_hi]
+    // ---- fold the floor in, count the units of every tile, local exclusive scan (second sweep)
+    int icarry = 0;
+    for (long long base = k_lo; base < k_hi; base += ROUND) {
+        long long hf[OBE_SCANW];
+        int units[OBE_SCANW], ex[OBE_SCANW], tot[OBE_SCANW];
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            hf[e] = (k < k_hi) ? max(H[k], floor_h) : 0;
+        }
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            units[e] = 0;
+            if (k < k_hi) {
+                // H[k+1] of this segment still lacks the floor; the last tile's neighbour is next_h
+                const long long h1 = (k + 1 < k_hi) ? max(H[k + 1], floor_h) : next_h;
+                units[e] = (int)((max(h1 - hf[e], 0ll) + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK);
+            }
+        }
+        __syncthreads();                             // all reads of the un-floored H precede the writes below
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            if (k < k_hi) H[k] = hf[e];
+        }
+        obe_block_excl_scanw<int, NWP>(units, ex, tot, smi, ObeOpSum(), 0, 0);
+#pragma unroll
+        for (int e = 0; e < OBE_SCANW; ++e) {
+            const long long k = base + e * OBE_SCAN_THREADS + t;
+            if (k < k_hi) unit_start[k] = icarry + ex[e];           // segment-local; the offset follows
+            icarry += tot[e];
+        }
+        __syncthreads();
+    }
+    if (t < OBE_PLAN_CLUSTER) *cluster.map_shared_rank(&xsum[r], t) = icarry;
+    cluster.sync();
+    int off = 0, total = 0;
+    for (int j = 0; j < OBE_PLAN_CLUSTER; ++j) { if (j < r) off += xsum[j]; total += xsum[j]; }
+    // ---- third sweep: global unit numbers, unit -> tile map
+    for (long long k = k_lo + t; k < k_hi; k += OBE_SCAN_THREADS) {
+        const int first = unit_start[k] + off;
+        const long long h1 = (k + 1 < k_hi) ? H[k + 1] : next_h;
+        const int units = (int)((max(h1 - H[k], 0ll) + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK);
+        unit_start[k] = first;
+        if (unit_tile)
+            for (int u = 0; u < units; ++u) unit_tile[first + u] = (int)k;
+    }
+    if (r == 0 && t == 0) unit_start[n_tiles] = total;
 }
 
 // One work unit = (input tile k, chunk of <= 2048 consecutive output slots owned by that tile).
@@ -1536,6 +1664,13 @@ size_t obe_select_scratch_bytes(int64_t n_settings) {
     return b;
 }
 
+int obe_set_option(const char* name, int64_t value) {
+    if (!name) return obe_fail("null argument%s%s");
+    const std::string s(name);
+    if (s == "plan_cluster_min_tiles") { g_plan_cluster_min_tiles = value < 0 ? 0 : value; return 0; }
+    return obe_fail("unknown option '%s'%s", name);
+}
+
 int obe_model_builtin(const char* name, int n_params, obe_model_t* out) {
     if (!name || !out) return obe_fail("null argument%s%s");
     obe_model* m = new obe_model();
@@ -1982,9 +2117,14 @@ static int resample_systematic_impl(const obe_cloud_t* in, const obe_cloud_t* ou
     a.sharded = sharded; a.last_shard = last_shard; a.n_total = n_total;
     a.slot_begin = slot_begin; a.slot_end = slot_end; a.cdf_offset = cdf_offset; a.cdf_total = cdf_total;
     cudaStream_t st = (cudaStream_t)stream;
-    k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, u0, sharded ? cdf_offset : 0.0,
-                                              sharded ? cdf_total : 0.0, slot_begin, slot_end, s.plan_h, s.unit_start,
-                                              (int*)a.unit_tile, nullptr, nullptr);
+    if (a.n_tiles > g_plan_cluster_min_tiles)
+        k_sys_plan_cluster<<<OBE_PLAN_CLUSTER, OBE_SCAN_THREADS, 0, st>>>(
+            in->tile_prefix_dev, a.n_tiles, n_total, u0, sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0,
+            slot_begin, slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr);
+    else
+        k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, u0,
+                                                  sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0, slot_begin,
+                                                  slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr);
     OBE_LAUNCH_CHECK("k_sys_plan");
     return launch_sys_resample(in, out, a, out->n, st);
 }
@@ -2035,8 +2175,14 @@ int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* ou
     a.plan = plan_dev; a.n_dev_in = (const long long*)in->n_dev; a.cap_out = out->ld;
     a.sharded = 1; a.n_total = n_total; a.implicit_out = 1;
     cudaStream_t st = (cudaStream_t)stream;
-    k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0, s.plan_h,
-                                              s.unit_start, (int*)a.unit_tile, (const long long*)in->n_dev, plan_dev);
+    if (a.n_tiles > g_plan_cluster_min_tiles)
+        k_sys_plan_cluster<<<OBE_PLAN_CLUSTER, OBE_SCAN_THREADS, 0, st>>>(
+            in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0, s.plan_h, s.unit_start, (int*)a.unit_tile,
+            (const long long*)in->n_dev, plan_dev);
+    else
+        k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0,
+                                                  s.plan_h, s.unit_start, (int*)a.unit_tile,
+                                                  (const long long*)in->n_dev, plan_dev);
     OBE_LAUNCH_CHECK("k_sys_plan");
     return launch_sys_resample(in, out, a, out->ld, st);
 }

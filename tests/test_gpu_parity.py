@@ -362,10 +362,21 @@ def test_multinomial_resample_matches_oracle(obe, scale):
 @pytest.mark.parametrize('n,d', [(4096, 3), (10000, 3), (250001, 3), (1, 2), (2, 2), (5, 1), (2047, 2), (2049, 2),
                                  (4097, 1), (10000, 1), (30011, 4), (10000, 6), (6151, 8)])
 @pytest.mark.parametrize('scale', [False, True])
-def test_systematic_resample_matches_oracle(obe, torch, n, d, scale):
+@pytest.mark.parametrize('plan', ['one_cta', 'cluster'])
+def test_systematic_resample_matches_oracle(obe, torch, n, d, scale, plan):
     """Systematic resample (plan + ancestors + move kernels): ancestors == searchsorted(cdf_gpu, comb)
     bit-exact; normals are the restated Philox/Box-Muller stream; particles == Liu-West with the Cholesky
     factor.  Sizes around the tile boundaries, every register/shared-memory variant of the move kernel (d)."""
+    from optbayesexpt_b200 import _lib
+    # the resample plan on one CTA, or on the cluster of 8 CTAs that large clouds (> 8192 tiles) get
+    _lib.check(_lib.load().obe_set_option(b'plan_cluster_min_tiles', 0 if plan == 'cluster' else 1 << 40))
+    try:
+        _systematic_case(obe, torch, n, d, scale)
+    finally:
+        _lib.check(_lib.load().obe_set_option(b'plan_cluster_min_tiles', 8192))
+
+
+def _systematic_case(obe, torch, n, d, scale):
     from optbayesexpt_b200 import _lib
     rng = np.random.default_rng(n)
     rows = [rng.uniform(2, 4, n), rng.uniform(-2000, -400, n), rng.normal(5e4, 1e3, n), rng.exponential(3.0, n),
