@@ -74,6 +74,8 @@ const char* obe_last_error(void);
 int obe_device_count(void);
 /* Tuning knobs for tests and A/B runs.  "plan_cluster_min_tiles": tile count (2048 particles each) above
  * which the resample plan runs on a thread-block cluster of 8 CTAs instead of one CTA (default 8192).
+ * "utility_lane_fill": the variance utility uses 8/4/2 lanes per setting while n_settings * lanes stays
+ * below this percentage of the resident thread count (default 50; 0 = always one thread per setting).
  * Returns 0, or -1 for an unknown name. */
 int obe_set_option(const char* name, int64_t value);                 /* 0 without a usable CUDA device                */
 int64_t obe_num_tiles(int64_t n);

@@ -643,6 +643,7 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
 // exchanged through distributed shared memory -- each CTA writes its total into every CTA's copy, one
 // cluster barrier, then every CTA folds the totals of the segments before it into its own results.
 #define OBE_PLAN_CLUSTER 8
+static int64_t g_utility_lane_fill = 50;          /* obe_set_option("utility_lane_fill"), percent of resident threads */
 static int64_t g_plan_cluster_min_tiles = 8192;   /* obe_set_option("plan_cluster_min_tiles") */
 #ifndef OBE_PLAN_CLUSTER_MIN_TILES
 #define OBE_PLAN_CLUSTER_MIN_TILES 8192     /* below: one CTA does every pass in a single round anyway */
@@ -1668,6 +1669,7 @@ int obe_set_option(const char* name, int64_t value) {
     if (!name) return obe_fail("null argument%s%s");
     const std::string s(name);
     if (s == "plan_cluster_min_tiles") { g_plan_cluster_min_tiles = value < 0 ? 0 : value; return 0; }
+    if (s == "utility_lane_fill") { g_utility_lane_fill = value < 0 ? 0 : value; return 0; }
     return obe_fail("unknown option '%s'%s", name);
 }
 
@@ -2248,7 +2250,7 @@ int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* set
     const int64_t resident = (int64_t)obe_sms() * 8 * OBE_THREADS;
     for (int lanes = 8; lanes >= 2 && method == 0 && k >= 8; lanes >>= 1) {
         const size_t split = smem + (size_t)(OBE_THREADS / lanes) * m->nch * k * sizeof(double);
-        if (n_settings * lanes <= resident / 2 && split <= 48 * 1024) { a.lanes = lanes; smem = split; break; }
+        if (n_settings * lanes <= resident * g_utility_lane_fill / 100 && split <= 48 * 1024) { a.lanes = lanes; smem = split; break; }
     }
     const int64_t per_block = OBE_THREADS / a.lanes;
     int64_t blocks = (n_settings + per_block - 1) / per_block;
