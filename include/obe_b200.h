@@ -189,6 +189,26 @@ int obe_resample_systematic_sharded(const obe_cloud_t* in, const obe_cloud_t* ou
 int obe_shard_plan(const double* gathered_stats_dev, int rank, int world, int d, double u0,
                    int64_t n_total, double a_param, int lazy, const obe_cloud_t* local,
                    const obe_cloud_t* out, double* plan_dev, void* stream);
+/* ---- peer exchange over NVLink (optional replacement of the small NCCL collectives) -------------
+ * Every rank owns one buffer of obe_peer_bytes() (cudaMalloc + CUDA IPC); peer_bufs[g] is rank g's buffer as
+ * mapped into THIS process (peer_bufs[rank] = the local one).  Producing kernels write their few doubles
+ * straight into every peer's buffer and raise a system-scope flag carrying `epoch`; consumers spin on their
+ * own buffer (3 s timeout -> the plan's overflow word reads 2).  `epoch` is a per-kind counter starting at 1
+ * that every rank advances identically; slots are double-buffered by its parity.  1..16 ranks. */
+size_t obe_peer_bytes(void);
+int obe_peer_alloc(void** dev_ptr, unsigned char* handle64);         /* handle64: cudaIpcMemHandle_t bytes */
+int obe_peer_open(const unsigned char* handle64, void** dev_ptr);
+int obe_peer_close(void* dev_ptr);
+int obe_peer_free(void* dev_ptr);
+/* obe_shard_plan with the stats all-gather fused in: publish local->stats_dev to every peer, wait, plan. */
+int obe_shard_plan_peer(void* const* peer_bufs, int rank, int world, uint64_t epoch, int d, double u0,
+                        int64_t n_total, double a_param, int lazy, const obe_cloud_t* local,
+                        const obe_cloud_t* out, double* plan_dev, void* stream);
+/* obe_draw_planned with the exchange fused in: owners write their draws into every rank's buffer; a
+ * one-CTA kernel then waits for all ranks and copies the (d, k) draws into draws_dev.  k * d <= 1024. */
+int obe_draw_planned_peer(const obe_cloud_t* c, const double* u_host, int k, void* const* peer_bufs,
+                          int rank, int world, uint64_t epoch, const double* plan_dev, int post,
+                          double* draws_dev, void* stream);
 /* obe_resample_systematic_sharded with every shard parameter read from plan_dev on the device. */
 int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* out, const double* plan_dev,
                                     int64_t n_total, uint64_t seed, uint32_t epoch, double a_param,

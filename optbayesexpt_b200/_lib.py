@@ -92,6 +92,15 @@ SIGNATURES = {
     'obe_resample_systematic_planned': (C.c_int, [_PCLOUD, _PCLOUD, _VP, C.c_int64, C.c_uint64, C.c_uint32,
                                                   C.c_double, C.c_int, _VP]),
     'obe_draw_planned': (C.c_int, [_PCLOUD, _PD, C.c_int, _VP, _VP, C.c_int, _VP]),
+    'obe_peer_bytes': (C.c_size_t, []),
+    'obe_peer_alloc': (C.c_int, [C.POINTER(_VP), C.c_char_p]),
+    'obe_peer_open': (C.c_int, [C.c_char_p, C.POINTER(_VP)]),
+    'obe_peer_close': (C.c_int, [_VP]),
+    'obe_peer_free': (C.c_int, [_VP]),
+    'obe_shard_plan_peer': (C.c_int, [C.POINTER(_VP), C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_double, C.c_int64,
+                                      C.c_double, C.c_int, _PCLOUD, _PCLOUD, _VP, _VP]),
+    'obe_draw_planned_peer': (C.c_int, [_PCLOUD, _PD, C.c_int, C.POINTER(_VP), C.c_int, C.c_int, C.c_uint64, _VP, C.c_int,
+                                        _VP, _VP]),
     'obe_set_uniform_total': (C.c_int, [_PCLOUD, C.c_int64, _VP]),
     'obe_comb_count': (C.c_int64, [C.c_double, C.c_double, C.c_int64]),
     'obe_draw_strided': (C.c_int, [_PCLOUD, _PD, C.c_int, _VP, C.c_int, _VP, _VP]),

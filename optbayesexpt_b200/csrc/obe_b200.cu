@@ -286,6 +286,44 @@ __global__ void k_search(const double* __restrict__ cdf, const double* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer exchange over NVLink (sharded engines, one process per GPU): every rank owns one small buffer
+// (cudaMalloc + CUDA IPC, mapped by all peers).  The producing kernels write their few doubles straight
+// into every peer's buffer, then a system-scope release store of an epoch number; consumers spin on
+// their OWN buffer (acquire loads) -- no NCCL launch, no stream hop.  Slots are double-buffered by the
+// parity of the epoch: a rank can run at most one exchange ahead of the slowest one, because passing
+// exchange e needs every peer's flag e, which a peer raises only after it has consumed e-1.
+// Layout in 8-byte words:
+// ---------------------------------------------------------------------------------------------
+#define OBE_PEER_MAX 16
+#define OBE_PEER_STATS 0                                  /* [2][OBE_PEER_MAX][64] stats blocks        */
+#define OBE_PEER_DRAWS (2 * OBE_PEER_MAX * OBE_STATS_LEN)  /* [2][1024]  draws (d, K), d*K <= 1024      */
+#define OBE_PEER_FLAGS (OBE_PEER_DRAWS + 2 * 1024)         /* [2 kinds][2][OBE_PEER_MAX] uint64 epochs  */
+#define OBE_PEER_ERR (OBE_PEER_FLAGS + 4 * OBE_PEER_MAX)   /* != 0: a wait timed out                    */
+#define OBE_PEER_WORDS (OBE_PEER_ERR + 8)
+struct ObePeers { double* p[OBE_PEER_MAX]; };
+
+__device__ __forceinline__ void obe_flag_store(unsigned long long* addr, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long obe_flag_load(const unsigned long long* addr) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
+    return v;
+}
+// false after ~3 s: a peer died or the ranks fell out of step; the caller flags it, nothing hangs
+__device__ __forceinline__ bool obe_flag_wait(const unsigned long long* flag, unsigned long long epoch) {
+    const long long t0 = clock64();
+    while (obe_flag_load(flag) < epoch) {
+        __nanosleep(40);
+        if (clock64() - t0 > 6000000000ll) return false;
+    }
+    return true;
+}
+__device__ __forceinline__ unsigned long long* obe_peer_flags(double* buf, int kind, int parity) {
+    return reinterpret_cast<unsigned long long*>(buf + OBE_PEER_FLAGS) + (kind * 2 + parity) * OBE_PEER_MAX;
+}
+
 struct ObeDrawArgs {
     const double* w; const double* prefix; long long n; long long n_tiles;
     const double* particles; long long ld; int d;
@@ -294,6 +332,12 @@ struct ObeDrawArgs {
     const double* plan;         // optional shard plan: this rank draws only the uniforms it owns
     const double* stats;        // optional: stats block (implicit uniform weights)
     int post;                   // use the post-resample shard totals of the plan
+    // peer mode (peer_world > 0): the owner of a draw writes it into EVERY rank's buffer, the last CTA raises
+    // this rank's flag there (instead of zeros + all-reduce)
+    int peer_world, peer_rank;
+    unsigned long long peer_epoch;
+    unsigned int* peer_counter;
+    ObePeers peers;
     double u[OBE_MAX_DRAWS];
 };
 // one block per draw: tile by binary search on the prefix, element by a canonical scan + count
@@ -304,9 +348,10 @@ __global__ void __launch_bounds__(OBE_THREADS) k_draw(const ObeDrawArgs a) {
     double uq = a.u[q];
     const long long n = a.n_dev ? *a.n_dev : a.n;
     const long long n_tiles = a.n_dev ? (n + OBE_TILE - 1) / OBE_TILE : a.n_tiles;
+    bool mine = true;
     if (a.plan) {
         // sharded cloud: owner of u is the shard whose [offset, offset+total) holds u*T; the others
-        // contribute zeros to the all-reduce that follows
+        // contribute zeros to the all-reduce that follows (NCCL mode) or nothing at all (peer mode)
         const int world = (int)a.plan[OBE_PL_WORLD], rank = (int)a.plan[OBE_PL_RANK];
         const double* off = a.plan + (a.post ? OBE_PL_POST_OFF : OBE_PL_PRE_OFF);
         const double* tot = a.plan + (a.post ? OBE_PL_POST_TOT : OBE_PL_PRE_TOT);
@@ -316,39 +361,75 @@ __global__ void __launch_bounds__(OBE_THREADS) k_draw(const ObeDrawArgs a) {
             if (off[g] + tot[g] <= target) owner = g + 1;
         owner = min(owner, world - 1);
         while (owner > 0 && !(tot[owner] > 0.0)) --owner;
-        if (owner != rank) {
-            if (threadIdx.x == 0) {
+        mine = (owner == rank);
+        if (!mine) {
+            if (threadIdx.x == 0 && a.peer_world == 0) {
                 if (a.idx) a.idx[q] = -1;
                 for (int j = 0; j < a.d; ++j) a.draws[(long long)j * a.k + q] = 0.0;
             }
-            return;
+        } else {
+            uq = (target - off[rank]) / tot[rank];
+            uq = uq < 0.0 ? 0.0 : (uq > 0.99999999999999989 ? 0.99999999999999989 : uq);
         }
-        uq = (target - off[rank]) / tot[rank];
-        uq = uq < 0.0 ? 0.0 : (uq > 0.99999999999999989 ? 0.99999999999999989 : uq);
     }
-    const double inv_total = 1.0 / a.prefix[n_tiles];
-    const long long k = find_tile(a.prefix, n_tiles, inv_total, uq);
-    double cn[OBE_EPT];
-    tile_cdf_blocked(a.w, a.prefix, k, n, inv_total, cn, sm, 0.0, true, a.stats ? a.stats[OBE_ST_UNIFORM] : 0.0);
-    const long long base = k * OBE_TILE;
-    int c = 0;
+    if (mine) {                                    // (uniform over the block)
+        const double inv_total = 1.0 / a.prefix[n_tiles];
+        const long long k = find_tile(a.prefix, n_tiles, inv_total, uq);
+        double cn[OBE_EPT];
+        tile_cdf_blocked(a.w, a.prefix, k, n, inv_total, cn, sm, 0.0, true, a.stats ? a.stats[OBE_ST_UNIFORM] : 0.0);
+        const long long base = k * OBE_TILE;
+        int c = 0;
 #pragma unroll
-    for (int e = 0; e < OBE_EPT; ++e) {
-        const long long i = base + (long long)threadIdx.x * OBE_EPT + e;
-        if (i < n && cn[e] <= uq) ++c;
+        for (int e = 0; e < OBE_EPT; ++e) {
+            const long long i = base + (long long)threadIdx.x * OBE_EPT + e;
+            if (i < n && cn[e] <= uq) ++c;
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+        if ((threadIdx.x & 31) == 0) cnt[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w2 = 0; w2 < OBE_THREADS / 32; ++w2) tot += cnt[w2];
+            const long long last = min(n, base + OBE_TILE) - 1;
+            const long long i = min(base + tot, last);
+            if (a.idx) a.idx[q] = i;
+            if (a.peer_world > 0) {
+                const int parity = (int)(a.peer_epoch & 1ull);
+                for (int j = 0; j < a.d; ++j) {
+                    const double v = a.particles[j * a.ld + i];
+                    for (int g = 0; g < a.peer_world; ++g)
+                        a.peers.p[g][OBE_PEER_DRAWS + parity * 1024 + j * a.k + q] = v;
+                }
+            } else {
+                for (int j = 0; j < a.d; ++j) a.draws[(long long)j * a.k + q] = a.particles[j * a.ld + i];
+            }
+        }
     }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
-    if ((threadIdx.x & 31) == 0) cnt[threadIdx.x >> 5] = c;
+    if (a.peer_world > 0 && threadIdx.x == 0) {
+        // every CTA reports in; the last one raises this rank's flag in every peer's buffer
+        __threadfence_system();
+        if (atomicAdd(a.peer_counter, 1u) == gridDim.x - 1) {
+            __threadfence_system();
+            const int parity = (int)(a.peer_epoch & 1ull);
+            for (int g = 0; g < a.peer_world; ++g)
+                obe_flag_store(obe_peer_flags(a.peers.p[g], 1, parity) + a.peer_rank, a.peer_epoch);
+            *a.peer_counter = 0u;
+        }
+    }
+}
+
+// consumer side of the draw exchange: wait for every rank's flag of this epoch, then copy the (d, K) draws
+// out of the local buffer
+__global__ void k_peer_collect_draws(double* mine, int world, unsigned long long epoch, double* __restrict__ draws,
+                                     int n_values) {
+    const int parity = (int)(epoch & 1ull);
+    bool ok = true;
+    if ((int)threadIdx.x < world) ok = obe_flag_wait(obe_peer_flags(mine, 1, parity) + threadIdx.x, epoch);
+    if (!ok) mine[OBE_PEER_ERR] = 1.0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int tot = 0;
-        for (int w2 = 0; w2 < OBE_THREADS / 32; ++w2) tot += cnt[w2];
-        const long long last = min(n, base + OBE_TILE) - 1;
-        const long long i = min(base + tot, last);
-        if (a.idx) a.idx[q] = i;
-        for (int j = 0; j < a.d; ++j) a.draws[(long long)j * a.k + q] = a.particles[j * a.ld + i];
-    }
+    __threadfence_system();
+    for (int q = threadIdx.x; q < n_values; q += blockDim.x) draws[q] = mine[OBE_PEER_DRAWS + parity * 1024 + q];
 }
 
 // U output slots at once: the Philox rounds of the U counters interleave (one basic block), which hides
@@ -1298,11 +1379,10 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_bcompact(const int* __rest
 // optbayesexpt_b200/sharded.py (combine_stats, moments_from, shard_slot_bounds), which the tests
 // compare it with.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_shard_plan(const double* __restrict__ gathered, int rank, int world, int d, double u0,
-                             long long n_total, double a_param, int lazy, long long cap_out,
-                             double* __restrict__ plan, double* __restrict__ stats_local,
-                             long long* __restrict__ n_out_dev) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void shard_plan_body(const double* __restrict__ gathered, int rank, int world, int d, double u0,
+                                long long n_total, double a_param, int lazy, long long cap_out,
+                                double* __restrict__ plan, double* __restrict__ stats_local,
+                                long long* __restrict__ n_out_dev) {
     const int nm2 = d * (d + 1) / 2;
     double* gs = plan + OBE_PL_GSTATS;
     for (int q = 0; q < OBE_STATS_LEN; ++q) gs[q] = 0.0;
@@ -1384,6 +1464,42 @@ __global__ void k_shard_plan(const double* __restrict__ gathered, int rank, int 
     plan[OBE_PL_OVERFLOW] = (cnt > cap_out) ? 1.0 : 0.0;
     if (cnt > cap_out) cnt = cap_out;
     if (n_out_dev) *n_out_dev = cnt;
+}
+
+__global__ void k_shard_plan(const double* __restrict__ gathered, int rank, int world, int d, double u0,
+                             long long n_total, double a_param, int lazy, long long cap_out,
+                             double* __restrict__ plan, double* __restrict__ stats_local,
+                             long long* __restrict__ n_out_dev) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    shard_plan_body(gathered, rank, world, d, u0, n_total, a_param, lazy, cap_out, plan, stats_local, n_out_dev);
+}
+
+// The stats exchange fused into the plan kernel: publish this rank's stats block into every peer's buffer,
+// raise the flag, wait for everybody's flag in the local buffer, plan.  One launch, no collective.
+__global__ void __launch_bounds__(OBE_STATS_LEN) k_shard_plan_peer(const ObePeers peers, int rank, int world,
+                                                                   unsigned long long epoch, int d, double u0,
+                                                                   long long n_total, double a_param, int lazy,
+                                                                   long long cap_out, double* __restrict__ plan,
+                                                                   double* __restrict__ stats_local,
+                                                                   long long* __restrict__ n_out_dev) {
+    __shared__ int ok;
+    const int t = threadIdx.x, parity = (int)(epoch & 1ull);
+    double* mine = peers.p[rank];
+    const double v = stats_local[t];
+    for (int g = 0; g < world; ++g) peers.p[g][OBE_PEER_STATS + (parity * OBE_PEER_MAX + rank) * OBE_STATS_LEN + t] = v;
+    if (t == 0) ok = 1;
+    __threadfence_system();
+    __syncthreads();
+    if (t < world) {
+        obe_flag_store(obe_peer_flags(peers.p[t], 0, parity) + rank, epoch);
+        if (!obe_flag_wait(obe_peer_flags(mine, 0, parity) + t, epoch)) ok = 0;
+    }
+    __syncthreads();
+    if (t != 0) return;
+    __threadfence_system();
+    shard_plan_body(mine + OBE_PEER_STATS + parity * OBE_PEER_MAX * OBE_STATS_LEN, rank, world, d, u0, n_total, a_param,
+                    lazy, cap_out, plan, stats_local, n_out_dev);
+    if (!ok) { plan[OBE_PL_OVERFLOW] = 2.0; mine[OBE_PEER_ERR] = 1.0; }
 }
 
 // the resample kernels stage the tile's particle rows in dynamic shared memory when d <= OBE_STAGE_MAX_D
@@ -1975,14 +2091,20 @@ int obe_search(const obe_cloud_t* c, const double* cdf_dev, const double* u_dev,
     return 0;
 }
 
+struct ObePeerDraw { const ObePeers* peers; int rank, world; unsigned long long epoch; unsigned int* counter; };
 static int draw_impl(const double* w, const double* prefix, int64_t n, const double* particles, int64_t ld, int d,
                      const double* u_host, int k, double* draws_dev, int64_t* idx_dev, cudaStream_t st,
                      int ld_draws = 0, const long long* n_dev = nullptr, const double* plan = nullptr, int post = 0,
-                     const double* stats = nullptr) {
+                     const double* stats = nullptr, const ObePeerDraw* peer = nullptr) {
     if (k <= 0) return 0;
     for (int off = 0; off < k; off += OBE_MAX_DRAWS) {
         const int kk = (k - off) < OBE_MAX_DRAWS ? (k - off) : OBE_MAX_DRAWS;
         ObeDrawArgs a;
+        memset(&a, 0, sizeof(a));
+        if (peer) {
+            a.peers = *peer->peers; a.peer_rank = peer->rank; a.peer_world = peer->world; a.peer_epoch = peer->epoch;
+            a.peer_counter = peer->counter;
+        }
         a.w = w; a.prefix = prefix; a.n = n; a.n_tiles = obe_num_tiles(n);
         a.particles = particles; a.ld = ld; a.d = d;
         a.draws = draws_dev ? draws_dev + off : nullptr;
@@ -2148,6 +2270,84 @@ int obe_resample_systematic_sharded(const obe_cloud_t* in, const obe_cloud_t* ou
     if (slot_begin < 0 || slot_end <= slot_begin || slot_end > n_total) return obe_fail("bad slot range%s%s");
     return resample_systematic_impl(in, out, u0, factor, mean, seed, epoch, a_param, scale, idx_out_dev, z_out_dev, 1,
                                     n_total, slot_begin, slot_end, cdf_offset, cdf_total, last_shard, stream);
+}
+
+// ---- peer exchange (CUDA IPC) -----------------------------------------------------------------
+size_t obe_peer_bytes(void) { return (size_t)OBE_PEER_WORDS * 8; }
+
+int obe_peer_alloc(void** dev_ptr, unsigned char* handle64) {
+    if (!dev_ptr || !handle64) return obe_fail("null argument%s%s");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    OBE_CUDA(cudaMalloc(&p, obe_peer_bytes()));
+    OBE_CUDA(cudaMemset(p, 0, obe_peer_bytes()));
+    OBE_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return obe_fail("cudaIpcGetMemHandle: %s%s", cudaGetErrorString(e)); }
+    memcpy(handle64, &h, 64);
+    *dev_ptr = p;
+    return 0;
+}
+int obe_peer_open(const unsigned char* handle64, void** dev_ptr) {
+    if (!dev_ptr || !handle64) return obe_fail("null argument%s%s");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    OBE_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int obe_peer_close(void* dev_ptr) {
+    if (dev_ptr) OBE_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+int obe_peer_free(void* dev_ptr) {
+    if (dev_ptr) OBE_CUDA(cudaFree(dev_ptr));
+    return 0;
+}
+static int fill_peers(void* const* peer_bufs, int rank, int world, ObePeers& pp) {
+    if (!peer_bufs) return obe_fail("null peer buffers%s%s");
+    if (world < 1 || world > OBE_PEER_MAX || rank < 0 || rank >= world) return obe_fail("peer exchange: 1..16 ranks%s%s");
+    memset(&pp, 0, sizeof(pp));
+    for (int g = 0; g < world; ++g) {
+        if (!peer_bufs[g]) return obe_fail("null peer buffer%s%s");
+        pp.p[g] = (double*)peer_bufs[g];
+    }
+    return 0;
+}
+
+int obe_shard_plan_peer(void* const* peer_bufs, int rank, int world, uint64_t epoch, int d, double u0, int64_t n_total,
+                        double a_param, int lazy, const obe_cloud_t* local, const obe_cloud_t* out, double* plan_dev,
+                        void* stream) {
+    if (!plan_dev || !local) return obe_fail("null argument%s%s");
+    if (d < 1 || d > OBE_MAX_DIMS) return obe_fail("n_params must be 1..8%s%s");
+    if (epoch == 0) return obe_fail("peer exchange epochs start at 1%s%s");
+    ObePeers pp;
+    if (fill_peers(peer_bufs, rank, world, pp)) return -1;
+    k_shard_plan_peer<<<1, OBE_STATS_LEN, 0, (cudaStream_t)stream>>>(pp, rank, world, epoch, d, u0, n_total, a_param, lazy,
+                                                                      out ? out->ld : (1ll << 62), plan_dev,
+                                                                      local->stats_dev,
+                                                                      out ? (long long*)out->n_dev : nullptr);
+    OBE_LAUNCH_CHECK("k_shard_plan_peer");
+    return 0;
+}
+
+int obe_draw_planned_peer(const obe_cloud_t* c, const double* u_host, int k, void* const* peer_bufs, int rank, int world,
+                          uint64_t epoch, const double* plan_dev, int post, double* draws_dev, void* stream) {
+    if (check_cloud(c)) return -1;
+    if (!u_host || !draws_dev || !plan_dev) return obe_fail("null argument%s%s");
+    if (k < 1 || k > OBE_MAX_DRAWS || (int64_t)k * c->d > 1024) return obe_fail("peer draws: n_draws * n_params <= 1024%s%s");
+    if (epoch == 0) return obe_fail("peer exchange epochs start at 1%s%s");
+    ObePeers pp;
+    if (fill_peers(peer_bufs, rank, world, pp)) return -1;
+    const Scratch s = scratch_of(c);
+    ObePeerDraw pd = {&pp, rank, world, epoch, s.counter + 16};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (draw_impl(c->weights_dev, c->tile_prefix_dev, c->n, c->particles_dev, c->ld, c->d, u_host, k, nullptr, nullptr, st, 0,
+                  (const long long*)c->n_dev, plan_dev, post, c->stats_dev, &pd))
+        return -1;
+    k_peer_collect_draws<<<1, 128, 0, st>>>(pp.p[rank], world, epoch, draws_dev, k * c->d);
+    OBE_LAUNCH_CHECK("k_peer_collect_draws");
+    return 0;
 }
 
 int obe_shard_plan(const double* gathered_stats_dev, int rank, int world, int d, double u0, int64_t n_total,

@@ -13,6 +13,7 @@ capacity.  The host-side decisions are pure functions (combine_stats, shard_slot
 assign_draws, reduce_best) so they can be tested without a GPU (gloo).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -121,6 +122,7 @@ def reduce_best(pairs):
 
 
 REPLICATE_GRID_MAX = 131072
+PEER_EXCHANGE_DEFAULT = '0'      # '1': stats and draws travel by peer writes over NVLink instead of NCCL
 
 
 def setting_slice(n_settings, rank, world):
@@ -169,6 +171,47 @@ class Comm:
         return t
 
 
+class PeerLink:
+    """The ranks' exchange buffers, mapped into this process through CUDA IPC (one process per GPU on one node;
+    NVLink peer access is enabled lazily by the driver).  Built collectively: every rank must construct it."""
+
+    def __init__(self, comm, lib, device):
+        import torch
+        self.lib, self.rank, self.world = lib, comm.rank, comm.world
+        if self.world > 16:
+            raise _lib.ObeError('peer exchange supports up to 16 ranks')
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _lib.check(lib.obe_peer_alloc(C.byref(own), handle))
+        self._own = own
+        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=device)
+        handles = comm.allgather(mine).cpu().numpy()
+        self.ptrs = (C.c_void_p * self.world)()
+        self._opened = []
+        for g in range(self.world):
+            if g == self.rank:
+                self.ptrs[g] = own.value
+            else:
+                p = C.c_void_p()
+                _lib.check(lib.obe_peer_open(bytes(bytearray(handles[g].tolist())), C.byref(p)))
+                self.ptrs[g] = p.value
+                self._opened.append(p)
+        comm.allgather(torch.zeros(1, dtype=torch.float64, device=device))     # everybody has mapped everybody
+        self.epoch = [0, 0]            # stats exchanges, draw exchanges
+
+    def next_epoch(self, kind):
+        self.epoch[kind] += 1
+        return self.epoch[kind]
+
+    def close(self):
+        for p in self._opened:
+            self.lib.obe_peer_close(p)
+        self._opened = []
+        if self._own is not None:
+            self.lib.obe_peer_free(self._own)
+            self._own = None
+
+
 # --------------------------------------------------------------------------------------------------
 def gstats_from_plan(plan_host, d, world):
     """The combined-stats dict (same keys as combine_stats) from a fetched plan block."""
@@ -195,9 +238,13 @@ class ShardedOptBayesExpt(OptBayesExpt):
     resample decision and to return the argmax."""
 
     def __init__(self, measurement_model, setting_values, parameter_samples, constants, group=None,
-                 slack=0.25, seed=0, **kwargs):
+                 slack=0.25, seed=0, peer_exchange=None, **kwargs):
         import torch
         self._comm = Comm(group)
+        if peer_exchange is None:
+            peer_exchange = os.environ.get('OBE_PEER_EXCHANGE', PEER_EXCHANGE_DEFAULT) == '1'
+        self._want_peer = bool(peer_exchange)
+        self._peer = None
         kwargs['resampling'] = 'systematic'
         kwargs['seed'] = seed
         n_local = parameter_samples.shape[-1]
@@ -225,6 +272,8 @@ class ShardedOptBayesExpt(OptBayesExpt):
         piv = torch.from_numpy(self._pivot.copy()).to(dev)     # a common pivot: rank 0's estimate
         self._pivot = self._comm.allgather(piv)[0].cpu().numpy()
         self._section = 0          # 0: draw with the plan's current-weight totals, 1: post-resample
+        if self._want_peer and self._comm.world <= 16:
+            self._peer = PeerLink(self._comm, self._lib, dev)
         self._make_plan()
 
     # ---- the live shard length lives on the device
@@ -247,13 +296,22 @@ class ShardedOptBayesExpt(OptBayesExpt):
     # ---- plan
     def _make_plan(self):
         """all-gather the stats blocks -> k_shard_plan (device).  Asynchronous."""
-        gathered = self._comm.allgather(self._buf.stats)
         self._u0 = float(self.rng.random())                 # identical on every rank
-        self._check(self._lib.obe_shard_plan(C.c_void_p(gathered.data_ptr()), self._comm.rank, self._comm.world,
-                                             self.n_dims, self._u0, self.n_total,
-                                             float(self.tuning_parameters['a_param']), 1 if self._weights_lazy else 0,
-                                             self._cs(), self._cs(self._alt), C.c_void_p(self._plan.data_ptr()),
-                                             self._stream()))
+        if self._peer is not None:
+            # stats exchange fused into the plan kernel: peer writes over NVLink + flags, no collective
+            self._check(self._lib.obe_shard_plan_peer(
+                self._peer.ptrs, self._comm.rank, self._comm.world, self._peer.next_epoch(0), self.n_dims, self._u0,
+                self.n_total, float(self.tuning_parameters['a_param']), 1 if self._weights_lazy else 0,
+                self._cs(), self._cs(self._alt), C.c_void_p(self._plan.data_ptr()), self._stream()))
+            gathered = None
+        else:
+            gathered = self._comm.allgather(self._buf.stats)
+            self._check(self._lib.obe_shard_plan(C.c_void_p(gathered.data_ptr()), self._comm.rank, self._comm.world,
+                                                 self.n_dims, self._u0, self.n_total,
+                                                 float(self.tuning_parameters['a_param']),
+                                                 1 if self._weights_lazy else 0,
+                                                 self._cs(), self._cs(self._alt), C.c_void_p(self._plan.data_ptr()),
+                                                 self._stream()))
         self._keep = gathered
         self._plan_valid = True
         self._section = 0
@@ -356,7 +414,14 @@ class ShardedOptBayesExpt(OptBayesExpt):
             self._fetch_plan()
         u = self.rng.random(n_draws)                        # identical on every rank
         draws = torch.empty((self.n_dims, n_draws), dtype=torch.float64, device=self._buf.device)
-        self._check(self._lib.obe_draw_planned(self._cs(), _lib.darr(u), int(n_draws), C.c_void_p(draws.data_ptr()),
+        if self._peer is not None and n_draws <= 128 and n_draws * self.n_dims <= 1024:
+            # owners write their draws into every rank's buffer; one small kernel waits and collects
+            self._check(self._lib.obe_draw_planned_peer(
+                self._cs(), _lib.dptr(u), int(n_draws), self._peer.ptrs, self._comm.rank, self._comm.world,
+                self._peer.next_epoch(1), C.c_void_p(self._plan.data_ptr()), self._section,
+                C.c_void_p(draws.data_ptr()), self._stream()))
+            return draws
+        self._check(self._lib.obe_draw_planned(self._cs(), _lib.dptr(u), int(n_draws), C.c_void_p(draws.data_ptr()),
                                                C.c_void_p(self._plan.data_ptr()), self._section, self._stream()))
         self._comm.allreduce_sum(draws)
         return draws

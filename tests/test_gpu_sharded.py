@@ -63,7 +63,10 @@ def _worker(rank, world, port, out):
             # the device-side shard plan against its host restatement
             from optbayesexpt_b200 import sharded as sh, _lib
             gs_dev = eng._fetch_plan()
-            gs_host = sh.combine_stats(eng._keep.cpu().numpy(), eng.n_dims)
+            # (peer-exchange mode keeps no gathered copy: gather the local blocks again; combine_stats does not
+            # read the normaliser word the plan has overwritten since)
+            gathered = eng._keep if eng._keep is not None else eng._comm.allgather(eng._buf.stats)
+            gs_host = sh.combine_stats(gathered.cpu().numpy(), eng.n_dims)
             for key in ('totals', 'offsets', 'm1', 'm2', 'pivot'):
                 np.testing.assert_array_equal(gs_dev[key], gs_host[key], err_msg=key)
             assert gs_dev['total'] == gs_host['total'] and gs_dev['sumsq'] == gs_host['sumsq']
@@ -188,35 +191,32 @@ def _worker_noise(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def _spawn(worker):
+def _spawn(worker, peer):
+    """Two ranks on the one GPU (gloo carries the host-side collectives).  peer='1': the stats and the draws travel
+    by peer writes into CUDA-IPC-mapped buffers + flags instead of collectives (the NVLink path of a real node)."""
     import torch.multiprocessing as mp
-    ctx = mp.get_context('spawn')
-    out = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=worker, args=(r, 2, port, out)) for r in range(2)]
-    for p in procs:
-        p.start()
-    results = [out.get(timeout=600) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
+    os.environ['OBE_PEER_EXCHANGE'] = peer          # inherited by the spawned ranks
+    try:
+        ctx = mp.get_context('spawn')
+        out = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=worker, args=(r, 2, port, out)) for r in range(2)]
+        for p in procs:
+            p.start()
+        results = [out.get(timeout=600) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+    finally:
+        os.environ.pop('OBE_PEER_EXCHANGE', None)
     for rank, msg in results:
         assert msg == 'ok', f'rank {rank}: {msg}'
 
 
-def test_two_shards_noise_parameter_engine(obe_lib):
-    _spawn(_worker_noise)
+@pytest.mark.parametrize('peer', ['0', '1'], ids=['collectives', 'peer_exchange'])
+def test_two_shards_noise_parameter_engine(obe_lib, peer):
+    _spawn(_worker_noise, peer)
 
 
-def test_two_shards_match_single_cloud(obe_lib):
-    import torch.multiprocessing as mp
-    ctx = mp.get_context('spawn')
-    out = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
-    for p in procs:
-        p.start()
-    results = [out.get(timeout=600) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-    for rank, msg in results:
-        assert msg == 'ok', f'rank {rank}: {msg}'
+@pytest.mark.parametrize('peer', ['0', '1'], ids=['collectives', 'peer_exchange'])
+def test_two_shards_match_single_cloud(obe_lib, peer):
+    _spawn(_worker, peer)
