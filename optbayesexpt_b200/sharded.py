@@ -176,27 +176,35 @@ class PeerLink:
     NVLink peer access is enabled lazily by the driver).  Built collectively: every rank must construct it."""
 
     def __init__(self, comm, lib, device):
+        """Collective and exception-free: every rank runs the same two all-gathers whatever fails locally;
+        ``self.ok`` says whether ALL ranks mapped ALL buffers (otherwise nobody may use the link)."""
         import torch
         self.lib, self.rank, self.world = lib, comm.rank, comm.world
-        if self.world > 16:
-            raise _lib.ObeError('peer exchange supports up to 16 ranks')
-        own = C.c_void_p()
+        self._own, self._opened, self.error = None, [], None
+        self.ptrs = (C.c_void_p * self.world)()
         handle = C.create_string_buffer(64)
-        _lib.check(lib.obe_peer_alloc(C.byref(own), handle))
-        self._own = own
+        try:
+            own = C.c_void_p()
+            _lib.check(lib.obe_peer_alloc(C.byref(own), handle))
+            self._own = own
+        except Exception as exc:              # noqa: BLE001
+            self.error = exc
         mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=device)
         handles = comm.allgather(mine).cpu().numpy()
-        self.ptrs = (C.c_void_p * self.world)()
-        self._opened = []
-        for g in range(self.world):
-            if g == self.rank:
-                self.ptrs[g] = own.value
-            else:
-                p = C.c_void_p()
-                _lib.check(lib.obe_peer_open(bytes(bytearray(handles[g].tolist())), C.byref(p)))
-                self.ptrs[g] = p.value
-                self._opened.append(p)
-        comm.allgather(torch.zeros(1, dtype=torch.float64, device=device))     # everybody has mapped everybody
+        if self.error is None:
+            try:
+                for g in range(self.world):
+                    if g == self.rank:
+                        self.ptrs[g] = self._own.value
+                    else:
+                        p = C.c_void_p()
+                        _lib.check(lib.obe_peer_open(bytes(bytearray(handles[g].tolist())), C.byref(p)))
+                        self.ptrs[g] = p.value
+                        self._opened.append(p)
+            except Exception as exc:          # noqa: BLE001
+                self.error = exc
+        good = comm.allgather(torch.tensor([1.0 if self.error is None else 0.0], dtype=torch.float64, device=device))
+        self.ok = bool((good > 0.5).all().item())      # also the barrier: everybody has mapped everybody
         self.epoch = [0, 0]            # stats exchanges, draw exchanges
 
     def next_epoch(self, kind):
@@ -242,7 +250,9 @@ class ShardedOptBayesExpt(OptBayesExpt):
         import torch
         self._comm = Comm(group)
         if peer_exchange is None:
-            peer_exchange = os.environ.get('OBE_PEER_EXCHANGE', PEER_EXCHANGE_DEFAULT) == '1'
+            # default: on for a real multi-GPU job (nccl backend), off otherwise; OBE_PEER_EXCHANGE=0/1 overrides
+            default = '1' if (self._comm.backend == 'nccl' and self._comm.world > 1) else PEER_EXCHANGE_DEFAULT
+            peer_exchange = os.environ.get('OBE_PEER_EXCHANGE', default) == '1'
         self._want_peer = bool(peer_exchange)
         self._peer = None
         kwargs['resampling'] = 'systematic'
@@ -273,7 +283,15 @@ class ShardedOptBayesExpt(OptBayesExpt):
         self._pivot = self._comm.allgather(piv)[0].cpu().numpy()
         self._section = 0          # 0: draw with the plan's current-weight totals, 1: post-resample
         if self._want_peer and self._comm.world <= 16:
-            self._peer = PeerLink(self._comm, self._lib, dev)
+            # collective and all-or-nothing: if the IPC mapping fails on any rank, every rank stays on NCCL
+            link = PeerLink(self._comm, self._lib, dev)
+            if link.ok:
+                self._peer = link
+            else:
+                link.close()
+                if self._comm.rank == 0:
+                    import warnings
+                    warnings.warn(f'peer exchange unavailable ({link.error}); using NCCL collectives', RuntimeWarning)
         self._make_plan()
 
     # ---- the live shard length lives on the device
