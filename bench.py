@@ -461,7 +461,8 @@ def main():
                 'h2d_bytes_per_step': 8 * (1 + 1 + 1 + 8 + 1) + 8 * args.draws,
                 'd2h_bytes_per_step': 8 * 64 + 16,
                 'note': 'record, pivot and uniforms travel as kernel arguments; stats block + argmax come back'},
-        'gpu_launches': (6 if world == 1 else 7) * args.steps,   # update, plan, ancestors, move, draw, utility (+ shard plan)
+        # update, plan, ancestors, move, draw, utility; sharded: + shard plan (peer exchange fused in) + draw collect
+        'gpu_launches': (6 if world == 1 else (8 if getattr(eng, '_peer', None) is not None else 7)) * args.steps,
         'roofline': {'bound': 'hbm', 'kernel': 'resample step = k_sys_plan + k_sys_ancestors + k_sys_move (one event bracket)',
                      'achieved': gbs_res, 'peak': peak, 'unit': 'GB/s', 'frac': gbs_res / peak,
                      # dram__bytes_read+write of the three kernels, ncu --set full (profiles/r1_final_ncu_summary.md):
@@ -471,6 +472,8 @@ def main():
                      'algorithmic_bytes_per_launch': b_res / world},
         'kernels_ms': {'update': t_upd, 'resample': t_res, 'draw+utility+argmax': t_sel},
         'kernels_gbs': {'update': b_upd / world / (t_upd * 1e-3) / 1e9, 'resample': gbs_res},
+        'exchange': None if world == 1 else ('peer (CUDA IPC over NVLink)' if getattr(eng, '_peer', None) is not None
+                                             else 'nccl'),
         'cycle_hbm_frac': b_cycle / world / (ms_step * 1e-3) / 1e9 / peak,
         'cycle_noresample': None if ms_nores is None else {
             'ms_per_step': ms_nores, 'cycles_per_s': 1e3 / ms_nores,

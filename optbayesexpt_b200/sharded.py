@@ -1,12 +1,14 @@
 """Particle cloud sharded over the GPUs of one node: one process per GPU (torch.distributed).
 
-Particles are exchangeable, so every O(N) step is local to a shard; the setting grid is sliced for
-the utility pass.  Only small vectors cross NVLink, through NCCL:
-  * after the update: one all-gather of the 64-double stats blocks -> global normaliser, N_eff,
+Particles are exchangeable, so every O(N) step is local to a shard; large setting grids are sliced for
+the utility pass.  Only small vectors cross NVLink -- by peer writes into CUDA-IPC-mapped buffers with
+system-scope flags (PeerLink, the default on an NCCL job) or through NCCL/gloo collectives:
+  * after the update: the 64-double stats blocks of all ranks -> global normaliser, N_eff,
     mean, covariance, and the exclusive scan of shard weight totals (the inter-GPU CDF offsets);
-  * the K drawn parameter sets: each shard writes the draws it owns into a zeroed (d, K) buffer,
-    one all-reduce(sum) makes them global;
-  * the argmax: one all-gather of (value, index) pairs, lowest global index wins ties.
+  * the K drawn parameter sets: each shard produces the draws it owns (peer mode: stores them into
+    every rank's buffer; collective mode: zeroed (d, K) buffer + one all-reduce(sum));
+  * the argmax of a sliced grid: one all-gather of (value, index) pairs, lowest global index wins ties
+    (grids up to 131072 settings are evaluated whole on every rank: no exchange).
 Resampling needs NO particle exchange: shard g's particles own the global comb slots
 [H_g, H_g+1), so shard lengths float by a fraction of a percent per resample inside a slack
 capacity.  The host-side decisions are pure functions (combine_stats, shard_slot_bounds,
