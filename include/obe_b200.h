@@ -193,7 +193,7 @@ int obe_shard_plan(const double* gathered_stats_dev, int rank, int world, int d,
  * Every rank owns one buffer of obe_peer_bytes() (cudaMalloc + CUDA IPC); peer_bufs[g] is rank g's buffer as
  * mapped into THIS process (peer_bufs[rank] = the local one).  Producing kernels write their few doubles
  * straight into every peer's buffer and raise a system-scope flag carrying `epoch`; consumers spin on their
- * own buffer (3 s timeout -> the plan's overflow word reads 2).  `epoch` is a per-kind counter starting at 1
+ * own buffer (~20 s timeout -> the plan's overflow word reads 2).  `epoch` is a per-kind counter starting at 1
  * that every rank advances identically; slots are double-buffered by its parity.  1..16 ranks. */
 size_t obe_peer_bytes(void);
 int obe_peer_alloc(void** dev_ptr, unsigned char* handle64);         /* handle64: cudaIpcMemHandle_t bytes */

@@ -311,12 +311,12 @@ __device__ __forceinline__ unsigned long long obe_flag_load(const unsigned long 
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
     return v;
 }
-// false after ~3 s: a peer died or the ranks fell out of step; the caller flags it, nothing hangs
+// false after ~20 s: a peer died or the ranks fell out of step; the caller flags it, nothing hangs
 __device__ __forceinline__ bool obe_flag_wait(const unsigned long long* flag, unsigned long long epoch) {
     const long long t0 = clock64();
     while (obe_flag_load(flag) < epoch) {
         __nanosleep(40);
-        if (clock64() - t0 > 6000000000ll) return false;
+        if (clock64() - t0 > 40000000000ll) return false;
     }
     return true;
 }

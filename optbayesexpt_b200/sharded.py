@@ -348,6 +348,8 @@ class ShardedOptBayesExpt(OptBayesExpt):
             self._make_plan()
         if self._gstats is None:
             ph = self._plan.cpu().numpy()
+            if ph[_lib.PLAN_OVERFLOW] == 2.0:
+                raise RuntimeError('peer exchange timed out: a rank died or the ranks fell out of step')
             if ph[_lib.PLAN_OVERFLOW] != 0.0:
                 raise RuntimeError('a shard outgrew its buffer capacity in a resample; raise `slack`')
             self._plan_host = ph
