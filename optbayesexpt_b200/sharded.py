@@ -296,6 +296,21 @@ class ShardedOptBayesExpt(OptBayesExpt):
                     warnings.warn(f'peer exchange unavailable ({link.error}); using NCCL collectives', RuntimeWarning)
         self._make_plan()
 
+    def close(self):
+        """Unmap the peers' exchange buffers and free the local one (collective in spirit: call it on every rank
+        once no rank launches another exchange)."""
+        if getattr(self, '_peer', None) is not None:
+            self._torch.cuda.synchronize()
+            self._peer.close()
+            self._peer = None
+
+    def __del__(self):
+        try:
+            if getattr(self, '_peer', None) is not None:
+                self._peer.close()
+        except Exception:       # noqa: BLE001 -- interpreter shutdown
+            pass
+
     # ---- the live shard length lives on the device
     @property
     def n_particles(self):
