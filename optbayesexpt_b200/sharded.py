@@ -297,19 +297,13 @@ class ShardedOptBayesExpt(OptBayesExpt):
         self._make_plan()
 
     def close(self):
-        """Unmap the peers' exchange buffers and free the local one (collective in spirit: call it on every rank
-        once no rank launches another exchange)."""
+        """Unmap the peers' exchange buffers and free the local one.  Call it on every rank, after a barrier: a
+        peer that is still running a cycle would store into freed memory.  (Not done implicitly on deletion for
+        that reason; process exit releases everything.)"""
         if getattr(self, '_peer', None) is not None:
             self._torch.cuda.synchronize()
             self._peer.close()
             self._peer = None
-
-    def __del__(self):
-        try:
-            if getattr(self, '_peer', None) is not None:
-                self._peer.close()
-        except Exception:       # noqa: BLE001 -- interpreter shutdown
-            pass
 
     # ---- the live shard length lives on the device
     @property
