@@ -1787,6 +1787,22 @@ __device__ void obe_update_multi_body(const ObeMultiArgs& a) {
             const double w = (wuni > 0.0) ? wuni : a.w_in[ii];
             t[e] = valid[e] ? w * invS : 0.0;
         }
+        // a noise parameter is a particle coordinate: its reciprocal does not depend on the point
+        double isg_p[NE][NY];
+        if (a.n_noise > 0) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+#pragma unroll
+                for (int c = 0; c < NY; ++c) {
+                    const int ni = a.noise_idx[c];
+                    double sig = 1.0;
+#pragma unroll
+                    for (int j = 0; j < D; ++j)
+                        if (j == ni) sig = p[e][j];
+                    isg_p[e][c] = obe_rcp_fast(sig);
+                }
+            }
+        }
         for (int m = 0; m < M; ++m) {
             const double* r = rec_s + m * 12;
 #pragma unroll
@@ -1797,15 +1813,7 @@ __device__ void obe_update_multi_body(const ObeMultiArgs& a) {
 #pragma unroll
                 for (int c = 0; c < NY; ++c) {
                     if (c < a.n_lik_channels) {
-                        double isg = r[8 + c];
-                        if (a.n_noise > 0) {
-                            const int ni = a.noise_idx[c];
-                            double sig = 1.0;
-#pragma unroll
-                            for (int j = 0; j < D; ++j)
-                                if (j == ni) sig = p[e][j];
-                            isg = obe_rcp_fast(sig);
-                        }
+                        const double isg = (a.n_noise > 0) ? isg_p[e][c] : r[8 + c];
                         const double q = (y[c] - r[4 + c]) * isg;
                         lik *= obe_exp_nonpos(-0.5 * (q * q)) * (isg * a.lik_scale[c]);
                     }
