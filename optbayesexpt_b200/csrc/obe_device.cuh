@@ -370,6 +370,27 @@ __device__ __forceinline__ void obe_exp_nonpos_vec(const double (&x)[NE], double
     }
 }
 
+// Row `ni` of NE particles held in registers.  `ni` is a kernel argument, uniform over the grid: one branch
+// and NE moves instead of a select chain per element.
+template <int D, int NE>
+__device__ __forceinline__ void obe_pick_rows(const double (&p)[NE][D], int ni, double (&out)[NE], double dflt) {
+#define OBE_PICK_CASE(J)                                           \
+    case J:                                                        \
+        if (J < D) {                                               \
+            _Pragma("unroll") for (int e = 0; e < NE; ++e) out[e] = p[e][J < D ? J : 0]; \
+            return;                                                \
+        }                                                          \
+        break;
+    switch (ni) {
+        OBE_PICK_CASE(0) OBE_PICK_CASE(1) OBE_PICK_CASE(2) OBE_PICK_CASE(3)
+        OBE_PICK_CASE(4) OBE_PICK_CASE(5) OBE_PICK_CASE(6) OBE_PICK_CASE(7)
+        default: break;
+    }
+#undef OBE_PICK_CASE
+#pragma unroll
+    for (int e = 0; e < NE; ++e) out[e] = dflt;
+}
+
 template <class Model, int D, int SRC, int NE, bool BATCHED>
 __device__ __forceinline__ void obe_update_vec(const ObeUpdateArgs& a, const double (&p)[NE][D],
                                                const double (&w_in)[NE], const double (&yg)[NE][OBE_MAX_CH],
@@ -400,32 +421,48 @@ __device__ __forceinline__ void obe_update_vec(const ObeUpdateArgs& a, const dou
                 }
                 lik[e] = 1.0;
             }
+            // prod_c exp(-((y_c - y_meas_c)/sigma_c)**2 / 2) / sigma_c  (obe_base.py:264-271, 453-455) as ONE
+            // exponential of the summed arguments times the product of the reciprocals: the division by sigma
+            // is a multiplication by its reciprocal (host's 1/sigma, or one refined rcp per particle for a
+            // noise parameter, shared by the channels that name the same row).  For one channel this is the
+            // same sequence of operations as exp(arg) * (1/sigma).
             const bool noise = a.n_noise > 0;
+            double argsum[NE], isprod[NE], inv_prev[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) { argsum[e] = 0.0; isprod[e] = 1.0; inv_prev[e] = 1.0; }
+            int ni_prev = -2;
 #pragma unroll
             for (int c = 0; c < NY; ++c) {
                 if (c < a.n_lik_channels) {
-                    // exp(-((y - y_meas)/sigma)**2 / 2) / sigma  (obe_base.py:264-271); the division by sigma
-                    // is a multiplication by its reciprocal (host's 1/sigma, or one refined rcp per particle
-                    // for a noise parameter)
-                    double inv_sig[NE], arg[NE], ex[NE];
                     const int ni = a.noise_idx[c];
+                    double inv_sig[NE];
+                    if (!noise) {
+#pragma unroll
+                        for (int e = 0; e < NE; ++e) inv_sig[e] = r_isig[c];
+                    } else if (ni == ni_prev) {
+#pragma unroll
+                        for (int e = 0; e < NE; ++e) inv_sig[e] = inv_prev[e];
+                    } else {
+                        double sig[NE];
+                        obe_pick_rows<D, NE>(p, ni, sig, 1.0);
+#pragma unroll
+                        for (int e = 0; e < NE; ++e) inv_sig[e] = obe_rcp_fast(sig[e]);
+                    }
 #pragma unroll
                     for (int e = 0; e < NE; ++e) {
-                        inv_sig[e] = r_isig[c];
-                        if (noise) {
-                            double sig = 1.0;
-#pragma unroll
-                            for (int j = 0; j < D; ++j)
-                                if (j == ni) sig = p[e][j];
-                            inv_sig[e] = obe_rcp_fast(sig);
-                        }
                         const double q = (y[e][c] - r_y[c]) * inv_sig[e];
-                        arg[e] = -0.5 * (q * q);
+                        argsum[e] = fma(-0.5 * q, q, argsum[e]);
+                        isprod[e] *= inv_sig[e];
+                        inv_prev[e] = inv_sig[e];
                     }
-                    obe_exp_nonpos_vec<NE>(arg, ex);
-#pragma unroll
-                    for (int e = 0; e < NE; ++e) lik[e] *= ex[e] * inv_sig[e];
+                    ni_prev = ni;
                 }
+            }
+            {
+                double ex[NE];
+                obe_exp_nonpos_vec<NE>(argsum, ex);
+#pragma unroll
+                for (int e = 0; e < NE; ++e) lik[e] = ex[e] * isprod[e];
             }
             if (a.use_choke) {
 #pragma unroll
@@ -483,14 +520,10 @@ __device__ __forceinline__ void obe_update_vec(const ObeUpdateArgs& a, const dou
         for (int c = 0; c < OBE_MAX_CH; ++c) {
             const int ni = a.noise_idx[c];
             if (ni >= 0) {
+                double sig[NE];
+                obe_pick_rows<D, NE>(p, ni, sig, 0.0);
 #pragma unroll
-                for (int e = 0; e < NE; ++e) {
-                    double sig = 0.0;
-#pragma unroll
-                    for (int j = 0; j < D; ++j)
-                        if (j == ni) sig = p[e][j];
-                    acc.noise[c] += valid[e] ? t[e] * (sig * sig) : 0.0;
-                }
+                for (int e = 0; e < NE; ++e) acc.noise[c] += valid[e] ? t[e] * (sig[e] * sig[e]) : 0.0;
             }
         }
     }
