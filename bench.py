@@ -480,7 +480,7 @@ def main():
             'hbm_frac': (8.0 * n_total * (d + 2) + b_sel) / (ms_nores * 1e-3) / 1e9 / peak},
         'clocks': clocks,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:       # the CPU arm is timed at N = 1 only
         line['cpu_baseline'] = cpu_cycle_rate(n_total, args.settings, args.draws)
     print(json.dumps(line))
     if world > 1:
