@@ -164,6 +164,34 @@ class OptBayesExpt(ParticlePDF):
         (obe_base.py:374-385) without a host round trip."""
         return self._eval_parameters_dev(onesettingset)
 
+    def prefetch_model(self, onesettingset):
+        """Start the model pass for the setting the instrument is about to measure (obe_base.py:374-385: "the
+        model evaluation can be done while waiting for measurement results").  Enqueued on a side stream, so it
+        overlaps whatever else the device is doing; the next ``pdf_update`` for the same setting picks the result up
+        (unless the cloud was resampled or replaced in between) instead of evaluating the model in its own pass."""
+        torch = self._torch
+        side = getattr(self, '_prefetch_stream', None)
+        if side is None:
+            side = self._prefetch_stream = torch.cuda.Stream(device=self._buf.device)
+        key = tuple(float(v) for v in np.atleast_1d(onesettingset))
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            y = self._eval_parameters_dev(onesettingset)
+        done = torch.cuda.Event()
+        done.record(side)
+        self._prefetched = (key, y, done, self._cloud_version)
+
+    def _take_prefetched(self, onesetting):
+        pre = getattr(self, '_prefetched', None)
+        self._prefetched = None
+        if pre is None:
+            return None
+        key, y, done, version = pre
+        if version != self._cloud_version or key != tuple(float(v) for v in np.atleast_1d(onesetting)):
+            return None
+        self._torch.cuda.current_stream().wait_event(done)
+        return y
+
     def _eval_parameters_dev(self, onesettingset):
         y = self._torch.empty((self.n_channels, self._buf.ld), dtype=self._torch.float64, device=self._buf.device)
         self._check(self._lib.obe_eval_parameters(self._model, self._cs(),
@@ -203,6 +231,8 @@ class OptBayesExpt(ParticlePDF):
         use_choke = 0 if self.choke is None else 1
         choke = 0.0 if self.choke is None else float(self.choke)
         pivot = _lib.darr(self._pivot, _lib.MAX_PARAMS)
+        if y_model_data is None:
+            y_model_data = self._take_prefetched(onesetting)
         if y_model_data is None:
             self._check(self._lib.obe_update(self._model, self._cs(),
                                              _lib.darr(np.atleast_1d(onesetting), _lib.MAX_SETTINGS), self._cons_arr,

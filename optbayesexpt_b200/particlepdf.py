@@ -44,6 +44,7 @@ class ParticlePDF:
             self.rng = np.random
         self._philox_seed = int(np.random.default_rng(seed).integers(0, 2 ** 63 - 1))
         self._epoch = 0
+        self._cloud_version = 0        # bumped whenever the particle coordinates change
         self._device = device
         self._install(prior)
         self._check(self._lib.obe_set_uniform(self._cs(), self._stream()))
@@ -165,6 +166,7 @@ class ParticlePDF:
         self._buf.particles[:, :self.n_particles].copy_(self._torch.from_numpy(np.ascontiguousarray(value)))
         self._host_particles = None
         self._moments_valid = False
+        self._cloud_version = getattr(self, '_cloud_version', 0) + 1
 
     @property
     def particle_weights(self):
@@ -210,6 +212,7 @@ class ParticlePDF:
     def set_pdf(self, samples, weights=None):
         """Re-initialise the distribution (particlepdf.py:147-171)."""
         self._install(samples)
+        self._cloud_version = getattr(self, '_cloud_version', 0) + 1
         if weights is None:
             self._check(self._lib.obe_set_uniform(self._cs(), self._stream()))
             self._weights_uniform = True
@@ -322,6 +325,7 @@ class ParticlePDF:
                                                           None, None, self._stream()))
             self._last_ancestors = None
         self._buf, self._alt = self._alt, self._buf
+        self._cloud_version += 1
         self._invalidate(particles=True)
         self._stats = None
         self._moments_valid = False

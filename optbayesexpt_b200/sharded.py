@@ -423,6 +423,7 @@ class ShardedOptBayesExpt(OptBayesExpt):
             self._epoch, float(self.tuning_parameters['a_param']), 1 if self.tuning_parameters['scale'] else 0,
             self._stream()))
         self._buf, self._alt = self._alt, self._buf
+        self._cloud_version += 1
         self._n_local = None
         OptBayesExpt._invalidate(self, particles=True)
         self._gstats = None

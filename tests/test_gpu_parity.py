@@ -141,6 +141,34 @@ def test_ref_optbayesexpt_likelihood_and_update(obe):           # tests/test_opt
     assert_allclose(eng3.particle_weights, lkl / np.sum(lkl), rtol=1e-15)
 
 
+def test_prefetched_model_pass_equals_fused_update(obe):
+    """prefetch_model(setting) -> pdf_update(record) uses the model values computed ahead (side stream) and gives
+    the same posterior as the fused pass; a resample in between invalidates the prefetch."""
+    sc = by_name('c1_find_peak')
+    inp = build_inputs(sc, 50000)
+    kw = dict(scale=False, default_noise_std=500.0, seed=5)
+    a = obe.OptBayesExpt(sc['model'], inp['setting_values'], inp['prior'], inp['cons'], **kw)
+    b = obe.OptBayesExpt(sc['model'], inp['setting_values'], inp['prior'], inp['cons'], **kw)
+    rec = ((3.05,), 49500.0, 500.0)
+    a.prefetch_model(rec[0])
+    assert a._prefetched is not None
+    a.pdf_update(rec)
+    assert a._prefetched is None
+    b.pdf_update(rec)
+    # the prefetch evaluates the exact functor, the fused pass the update-pass variant: last-bit differences
+    wclose(a.particle_weights, b.particle_weights, 1e-12)
+    assert_allclose(a.mean(), b.mean(), rtol=1e-12)
+    # stale prefetch: wrong setting, or the cloud changed
+    a.prefetch_model((2.0,))
+    a.pdf_update(rec)
+    b.pdf_update(rec)
+    wclose(a.particle_weights, b.particle_weights, 1e-12)
+    a.prefetch_model(rec[0])
+    a.resample()
+    b.resample()
+    assert a._take_prefetched(rec[0]) is None
+
+
 def test_ref_zinference_infer(obe):                             # tests/test_zinference.py:89-108
     n, true_mean, true_sigma = 5000, 1.0, 1.0
     src = '__device__ void ident(const double* s, const double* p, const double* c, double* y) { y[0] = p[0]; }'
