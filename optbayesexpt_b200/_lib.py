@@ -142,6 +142,11 @@ def load():
         fn.argtypes = args
     if lib.obe_abi_version() != 1:
         raise ObeError('libobe_b200.so ABI version mismatch: rebuild')
+    # tuning knobs from the environment: OBE_OPT_PLAN_CLUSTER_MIN_TILES=..., OBE_OPT_UTILITY_LANE_FILL=...
+    for key, val in os.environ.items():
+        if key.startswith('OBE_OPT_'):
+            if lib.obe_set_option(key[8:].lower().encode(), int(val)) != 0:
+                raise ObeError(lib.obe_last_error().decode(errors='replace'))
     _lib = lib
     return lib
 
