@@ -1,20 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- full pdf_update + resample + opt_setting cycles per second.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c1|c2|c3|c5|sweeper]
 
-Workload (BASELINE.json configs[3], fits one B200): synthetic Lorentzian cloud, 1e8 particles x
+Default workload c4 (BASELINE.json configs[3], fits one B200): synthetic Lorentzian cloud, 1e8 particles x
 3 parameters, 1e5 settings, n_draws = 30, resample forced every cycle (resample_threshold > 1).
-A "step" is one full cycle.  Prints ONE JSON line (rank 0).
+c1 / c2 / c3 are the reference's own demo shapes with their real models (Lorentzian / line + unknown sigma /
+Rabi on the 101 x 101 grid), c5 the 4096 batched lock-in engines.  A "step" is one full cycle.  ONE JSON line.
 
   value      cycles/s with everything resident in HBM, no host synchronisation inside the timed
              region (run_cycle_async), CUDA events, max over ranks
   e2e        the same cycle through the reference-shaped API (pdf_update(record) -> opt_setting()),
              closed loop: the record goes host->device every step, the stats block and the chosen
              index come back every step
-  roofline   dominant kernel (the fused systematic resample) against the measured HBM peak
-  cpu_baseline / --impl reference: the numpy restatement of the reference (oracle/), timed on the
-             host on a bounded sample and scaled linearly in N to the full workload.
+  roofline   dominant kernel (the one-kernel systematic resample) against the measured HBM peak
+  cpu_baseline / --impl reference: the UNMODIFIED reference (baseline/_ref, see baseline/reference_arm.py)
+             timed on the host: c1-c3 at their full size; c4 measured at 1e6 and 1e7 particles and extrapolated
+             to 1e8 with the fitted exponent (labelled).  Falls back to the numpy port (oracle/) only when the
+             reference is not installed.
 """
 import argparse
 import json
@@ -90,9 +93,11 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------------------------------------
-# CPU baseline: the numpy restatement of the reference, bounded sample, scaled to the workload
+# CPU arm: the unmodified reference (baseline/reference_arm.py); the numpy port only as a fallback
 # -------------------------------------------------------------------------------------------------
-def cpu_cycle_rate(n_full, n_settings, n_draws, n_sample=1_000_000, budget_s=20.0, max_cycles=8):
+def port_cycle_rate(n_full, n_settings, n_draws, n_sample=1_000_000, budget_s=20.0, max_cycles=8):
+    """Fallback when baseline/_ref is missing: the numpy restatement of the reference (oracle/), bounded sample,
+    O(N) part scaled linearly.  kind = "port"."""
     from oracle import obe_oracle as orc
     rng = np.random.default_rng(1001)
     prior = np.array([rng.uniform(2, 4, n_sample), rng.uniform(-2000, -400, n_sample),
@@ -108,10 +113,8 @@ def cpu_cycle_rate(n_full, n_settings, n_draws, n_sample=1_000_000, budget_s=20.
         warnings.simplefilter('ignore', RuntimeWarning)
         while cycles < max_cycles and (time.perf_counter() - t_start) < budget_s:
             t0 = time.perf_counter()
-            # design half: the O(N) weighted draw ...
             draws, _ = orc.randdraw(eng.particles, eng.particle_weights, eng.rng.random(n_draws))
             t1 = time.perf_counter()
-            # ... and the O(K S) grid evaluation + argmax
             var_p, _ = orc.yvar_from_draws(eng.model, eng.allsettings, draws, CONS, 1)
             util = orc.utility_variance(var_p, orc.noise_var_default(SIGMA, 1))
             best = orc.opt_index(util)
@@ -126,17 +129,178 @@ def cpu_cycle_rate(n_full, n_settings, n_draws, n_sample=1_000_000, budget_s=20.
             cycles += 1
     per_cycle_sample = (t_n + t_grid) / cycles
     per_cycle_full = (t_n / cycles) * (n_full / n_sample) + t_grid / cycles
-    import threadpoolctl
-    blas = sum(i.get('num_threads', 0) for i in threadpoolctl.threadpool_info() if i.get('user_api') == 'blas')
     return {
         'value': 1.0 / per_cycle_full, 'unit': 'cycles/s', 'cores': 1, 'kind': 'port',
-        'sample': (f'oracle (numpy restatement of the reference, multinomial resample as the reference does) on '
-                   f'{n_sample} particles x {n_settings} settings, {cycles} full cycles, '
-                   f'{per_cycle_sample * 1e3:.1f} ms/cycle measured; O(N) part scaled x{n_full / n_sample:g} to '
-                   f'{n_full} particles. numpy elementwise/cumsum/searchsorted are single-threaded (1 core; '
-                   f'BLAS threads available to cov/matmul: {blas}); host has {os.cpu_count()} logical cores'),
-        'ms_per_cycle_sample': per_cycle_sample * 1e3,
+        'sample': (f'FALLBACK (baseline/_ref missing): numpy port of the reference (oracle/) on {n_sample} particles x '
+                   f'{n_settings} settings, {cycles} full cycles, {per_cycle_sample * 1e3:.1f} ms/cycle measured; O(N) part '
+                   f'scaled x{n_full / n_sample:g} linearly'),
+        'measured': [dict(n=n_sample, cycles=cycles, s_per_cycle=per_cycle_sample)], 'extrapolated': True,
+        'ms_per_cycle': per_cycle_full * 1e3, 'timed_s': per_cycle_sample * cycles,
     }
+
+
+def cpu_arm(workload, args, warmup, steps, budget_s, forced=True):
+    """cpu_baseline object: the unmodified reference when it is installed (kind "reference"), else the port (c4)."""
+    from baseline import reference_arm as ra
+    out = ra.reference_rate(workload, forced=forced, warmup=warmup, steps=steps, budget_s=budget_s,
+                            n_draws=args.draws, settings=args.settings)
+    if 'unavailable' in out and workload == 'c4':
+        why = out['unavailable']
+        out = port_cycle_rate(int(args.particles), args.settings, args.draws, max_cycles=max(1, min(steps, 8)))
+        out['reference_unavailable'] = why
+    return out
+
+
+def workload_config(workload, args):
+    from baseline import reference_arm as ra
+    wl = ra.WORKLOADS[workload]
+    n_set = int(np.prod([len(v) for v in wl['settings']()])) if workload != 'c4' else args.settings
+    n = wl['n_particles'] if workload != 'c4' else int(args.particles)
+    d = len(wl['prior'](np.random.default_rng(0), 2))
+    return {'workload': f'{wl["label"]} (BASELINE configs[{wl["config_index"]}])' if workload != 'c4' else
+            f'synthetic Lorentzian scale-out: {n:.0e} particles x {n_set} settings, n_draws={args.draws}, d=3, '
+            f'resample forced every cycle (BASELINE configs[3])',
+            'particles': n, 'settings': n_set, 'n_draws': args.draws, 'n_params': d}
+
+
+def reference_line(args):
+    """--impl reference: the unmodified reference on the host cores, this arm's config/metric/unit.
+    Each timed step is one closed-loop cycle of the reference on a bounded sample of the workload (c4: 1e6
+    particles, then 2 cycles at 1e7 for the scaling exponent; c1-c3: the full workload); `value` is the rate at the
+    workload's full size, `ms_per_step` what a step actually took."""
+    wl = args.workload if args.workload in ('c1', 'c2', 'c3', 'c4') else 'c4'
+    base = cpu_arm(wl, args, warmup=max(1, args.warmup), steps=max(1, args.steps), budget_s=240.0)
+    if 'unavailable' in base:
+        print(json.dumps({'impl': 'reference', 'unavailable': base['unavailable']}))
+        return
+    first = base['measured'][0]
+    config = workload_config(wl, args)
+    config['l2'] = 'n/a (host run)'
+    line = {'impl': 'reference', 'metric': 'pdf_update+resample+opt_setting cycles/sec', 'value': base['value'],
+            'unit': 'cycles/s', 'n_gpus': 0, 'steps': first['cycles'], 'warmup': max(1, args.warmup),
+            'ms_per_step': first['s_per_cycle'] * 1e3,
+            'ms_per_step_note': (f'a timed step is one reference cycle at {first["n"]:.0e} particles (what actually ran); '
+                                 f'`value` is the rate at the full workload size'
+                                 + (' (extrapolated, see cpu_baseline)' if base.get('extrapolated') else '')),
+            'ms_per_cycle_full_workload': base['ms_per_cycle'],
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': config, 'cpu_baseline': base,
+            'e2e': {'value': base['value'], 'unit': 'cycles/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------------------------
+# c1 / c2 / c3: the reference's own demo shapes with their real models (one GPU)
+# -------------------------------------------------------------------------------------------------
+def bench_small(args):
+    import torch
+    import __graft_entry__
+    __graft_entry__.build()
+    import optbayesexpt_b200 as obe
+    from baseline import reference_arm as ra
+    wl = ra.WORKLOADS[args.workload]
+    n = wl['n_particles']
+    prior = wl['prior'](np.random.default_rng(1001), n)
+    d = prior.shape[0]
+    settings = wl['settings']()
+    n_set = int(np.prod([len(v) for v in settings]))
+    n_knobs = len(settings)
+
+    def make(threshold):
+        kw = dict(n_draws=args.draws, scale=False, seed=1003, resample_threshold=threshold)
+        if wl['kind'] == 'noise':
+            return obe.OptBayesExptNoiseParameter(wl['device_model'], settings, prior, wl['cons'],
+                                                  noise_parameter_index=wl['noise_parameter_index'], **kw)
+        return obe.OptBayesExpt(wl['device_model'], settings, prior, wl['cons'],
+                                default_noise_std=wl['default_noise_std'], **kw)
+
+    meas = np.random.default_rng(1002)
+    import warnings
+    warnings.simplefilter('ignore', RuntimeWarning)
+    # ---- device-resident leg, resample forced every cycle, records prepared in advance, no host sync
+    eng = make(2.0)
+    xs = eng.allsettings
+    recs = [ra.simulate(wl, tuple(xs[:, (7919 * t + n_set // 2) % n_set]), meas) for t in range(args.warmup + args.steps)]
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device='cuda')      # 256 MB > the 126 MB L2
+    for t in range(max(args.warmup, 3)):
+        eng.run_cycle_async(recs[t % len(recs)])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for t in range(args.steps):
+        flush.zero_()                                   # cold L2 for every timed cycle (outside the bracket)
+        ev[t][0].record()
+        eng.run_cycle_async(recs[args.warmup + t])
+        ev[t][1].record()
+    torch.cuda.synchronize()
+    ms_cold = float(np.sum([a.elapsed_time(b) for a, b in ev])) / args.steps
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for t in range(args.steps):
+        eng.run_cycle_async(recs[args.warmup + t])
+    b1.record()
+    torch.cuda.synchronize()
+    ms_warm = b0.elapsed_time(b1) / args.steps
+
+    # ---- end to end through pdf_update / opt_setting, closed loop: forced and natural resampling
+    def closed_loop(threshold, steps):
+        e = make(threshold)
+        x = e.opt_setting()
+        for _ in range(max(3, args.warmup)):
+            e.pdf_update(ra.simulate(wl, x, meas))
+            x = e.opt_setting()
+        torch.cuda.synchronize()
+        n_res = 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e.pdf_update(ra.simulate(wl, x, meas))
+            n_res += 1 if e.just_resampled else 0
+            x = e.opt_setting()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / steps, n_res / steps
+    e2e_steps = max(args.steps, 200 if n <= 100_000 else 50)
+    s_forced, r_forced = closed_loop(2.0, e2e_steps)
+    s_natural, r_natural = closed_loop(0.5, e2e_steps)
+    clocks = sampler.stop()
+    peak, peak_src = measured_peak()
+    c_ch = 1
+    b_cycle = 8.0 * n * (3 * d + 5 - 1) + 8.0 * n_set * (n_knobs + 1)      # SURVEY 8(d), offspring weights implicit
+    config = workload_config(args.workload, args)
+    config['l2'] = (f'working set {(8.0 * n * (2 * d + 2)) / 1e6:.1f} MB fits the 126 MB L2: `value` is measured with the L2 '
+                    f'flushed (256 MB write) before every timed cycle, per-cycle CUDA events; `l2_resident` is the same '
+                    f'loop back to back without the flush')
+    config['resample'] = 'forced every cycle (value, e2e); natural rate in e2e_natural'
+    line = {
+        'metric': 'pdf_update+resample+opt_setting cycles/sec', 'value': 1e3 / ms_cold, 'unit': 'cycles/s', 'n_gpus': 1,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_cold, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config,
+        'l2_resident': {'ms_per_step': ms_warm, 'cycles_per_s': 1e3 / ms_warm},
+        'e2e': {'value': 1.0 / s_forced, 'unit': 'cycles/s', 'steps': e2e_steps, 'resamples_per_cycle': r_forced,
+                'h2d_bytes_per_step': 8 * (n_knobs + 2 * c_ch + d + 1) + 8 * args.draws, 'd2h_bytes_per_step': 8 * 64 + 16,
+                'note': 'record, pivot and uniforms travel as kernel arguments; stats block + argmax come back'},
+        'e2e_natural': {'value': 1.0 / s_natural, 'unit': 'cycles/s', 'steps': e2e_steps,
+                        'resamples_per_cycle': r_natural, 'resample_threshold': 0.5},
+        'gpu_launches': 5 * args.steps + (args.steps if wl['kind'] == 'noise' else 0),
+        'roofline': {'bound': 'hbm', 'kernel': 'whole cycle (update + plan + one-kernel resample + draw + utility)',
+                     'achieved': b_cycle / (ms_cold * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                     'frac': b_cycle / (ms_cold * 1e-3) / 1e9 / peak, 'traffic': None,
+                     'traffic_source': 'not captured for this shape (launch-latency-bound: 5 launches per cycle)',
+                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': b_cycle},
+        'clocks': clocks,
+    }
+    if not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_arm(args.workload, args, warmup=2, steps=20 if n <= 100_000 else 8, budget_s=12.0)
+        line['cpu_baseline_natural'] = cpu_arm(args.workload, args, warmup=2, steps=20 if n <= 100_000 else 8,
+                                               budget_s=12.0, forced=False)
+    print(json.dumps(line))
+
+
+def lockin_model(w, pars):
+    """(Re Z, Im Z) of R-L in parallel with C (demos/lockin/lockin_of_coil.py:63-102), for the simulated instrument."""
+    L, R, Cc = pars[:3]
+    z = 1 / (1 / (R + 1j * w * L) + 1j * w * Cc)
+    return np.array((np.real(z), np.imag(z)))
 
 
 # -------------------------------------------------------------------------------------------------
@@ -155,7 +319,6 @@ def bench_c5(args, rank, world):
     if world > 1:
         dist.barrier()
     from optbayesexpt_b200.batched import BatchedOptBayesExpt
-    from oracle import obe_oracle as orc
     B_total, n = 4096, 10000
     B = B_total // world
     g = torch.Generator(device='cuda')
@@ -173,7 +336,7 @@ def bench_c5(args, rank, world):
     def step(sync):
         out = eng.opt_setting(sync=sync)
         if sync:
-            z = orc.model_lockin_coil((out[1][0],), truth, ())
+            z = lockin_model(out[1][0], truth)
             y = z.T + 5.0 * meas.standard_normal((B, 2))
         else:
             y = step.y
@@ -236,7 +399,6 @@ def bench_sweeper(args):
     import __graft_entry__
     __graft_entry__.build()
     import optbayesexpt_b200 as obe
-    from oracle import obe_oracle as orc
     n, m = int(args.particles) if args.particles < 1e8 else 10_000_000, 64
     g = torch.Generator(device='cuda')
     g.manual_seed(1001)
@@ -262,7 +424,7 @@ def bench_sweeper(args):
         for it in range(args.warmup + args.steps):
             start = int(meas.integers(0, len(xvals) - m))
             xs = xvals[start:start + m]
-            ys = orc.model_lorentzian_hwhm((xs,), truth, (0.1,)) + noise * meas.standard_normal(m)
+            ys = lorentz(xs, truth) + noise * meas.standard_normal(m)
             e0 = eng._epoch
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -290,6 +452,75 @@ def bench_sweeper(args):
 
 
 # -------------------------------------------------------------------------------------------------
+def invariance_check(world, rank, torch, obe):
+    """the results must not depend on the number of GPUs.  A 1e6-particle side problem (outside every
+    timed region): the cloud sharded over the `world` ranks against the single-cloud engine on the same GPU, same
+    seeds -- chosen setting index identical; N_eff / mean to 1e-12 (the global sums are combined in rank order, a
+    different association than one pass, so they agree to rounding, not to the bit); after a forced resample with
+    the same comb offset and Philox stream every shard equals its slice of the single cloud's offspring (ancestors
+    and jitter; tolerance 1e-12 relative + 1e-9 of the spread, the Cholesky factor inherits the rounding of the
+    moments); shard lengths sum to n; the plan's overflow word is 0."""
+    from optbayesexpt_b200 import _lib
+    from optbayesexpt_b200.sharded import ShardedOptBayesExpt
+    import warnings
+    n, n_set = 1_000_000, 2000
+    g = np.random.default_rng(4242)
+    prior = np.array([g.uniform(2, 4, n), g.uniform(-2000, -400, n), g.normal(50000, 1000, n)])
+    settings = (np.linspace(1.5, 4.5, n_set),)
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    kw = dict(n_draws=30, scale=False, default_noise_std=SIGMA, seed=99)
+    sh = ShardedOptBayesExpt('lorentzian_hwhm', settings, prior[:, lo:hi], CONS, **kw)
+    one = obe.OptBayesExpt('lorentzian_hwhm', settings, prior, CONS, **kw)
+    out = dict(n=n, cycles=3, chosen_index_equal=True, n_eff_rel=0.0, mean_rel=0.0, particles_err_in_tol_units=0.0,
+               counts_sum_ok=True, overflow=0.0)
+    meas = np.random.default_rng(700)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for e in (sh, one):
+            e.tuning_parameters['auto_resample'] = False
+        for t in range(out['cycles']):
+            sh.rng, one.rng = np.random.default_rng(500 + t), np.random.default_rng(500 + t)
+            xs, x1 = sh.opt_setting(), one.opt_setting()
+            out['chosen_index_equal'] &= bool(sh.last_setting_index == one.last_setting_index and xs == x1)
+            rec = (xs, float(lorentz(xs[0], TRUE_PARS) + SIGMA * meas.standard_normal()), SIGMA)
+            sh.pdf_update(rec)
+            one.pdf_update(rec)
+            out['n_eff_rel'] = max(out['n_eff_rel'], abs(sh.n_eff() - one.n_eff()) / one.n_eff())
+            out['mean_rel'] = max(out['mean_rel'], float(np.max(np.abs(sh.mean() - one.mean()) / np.abs(one.mean()))))
+            sh._philox_seed = one._philox_seed = 4242 + t
+            sh._epoch = one._epoch = t
+            u0 = sh._u0                                    # the comb offset of the current shard plan
+            saved, one.rng = one.rng, type('U0', (), {'random': staticmethod(lambda *a: u0)})()
+            sh.resample()
+            one.resample()
+            one.rng = saved
+            counts = sh.shard_counts
+            out['counts_sum_ok'] &= bool(int(counts.sum()) == n)
+            start = int(counts[:rank].sum())
+            got = sh.particles
+            want = one.particles[:, start:start + got.shape[1]]
+            spread = want.std(axis=1, keepdims=True)
+            err = np.abs(got - want) / (np.abs(want) * 1e-12 + spread * 1e-9)
+            out['particles_err_in_tol_units'] = max(out['particles_err_in_tol_units'], float(err.max()))
+            out['overflow'] = max(out['overflow'], float(sh._plan[_lib.PLAN_OVERFLOW].item()))
+            out['shard_counts'] = [int(c) for c in counts]
+    ok = (out['chosen_index_equal'] and out['n_eff_rel'] < 1e-12 and out['mean_rel'] < 1e-12
+          and out['particles_err_in_tol_units'] <= 1.0 and out['counts_sum_ok'] and out['overflow'] == 0.0)
+    import torch.distributed as dist
+    flags = torch.tensor([1.0 if ok else 0.0, out['n_eff_rel'], out['mean_rel'], out['particles_err_in_tol_units']],
+                         dtype=torch.float64, device='cuda')
+    worst = flags.clone()
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    out['ok'] = bool(flags[0].item() > 0.5)
+    out['n_eff_rel'], out['mean_rel'], out['particles_err_in_tol_units'] = [float(v) for v in worst[1:]]
+    out['tolerances'] = {'chosen_index': 'identical', 'n_eff_rel': 1e-12, 'mean_rel': 1e-12,
+                         'particles': '1e-12 relative + 1e-9 of the spread (1.0 = at tolerance)'}
+    sh.close()
+    return out
+
+
+# -------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -301,34 +532,29 @@ def main():
     ap.add_argument('--draws', type=int, default=30)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--force-resample', action='store_true')
-    ap.add_argument('--workload', default='c4', choices=['c4', 'c5', 'sweeper'],
-                    help='c4: 1e8-particle Lorentzian cloud (default, the metric); c5: 4096 batched lock-in engines; '
+    ap.add_argument('--workload', default='c4', choices=['c4', 'c1', 'c2', 'c3', 'c5', 'sweeper'],
+                    help='c4: 1e8-particle Lorentzian cloud (default, the metric); c1/c2/c3: the reference demo shapes '
+                         'with their real models (find_peak / line+noise / pipulse); c5: 4096 batched lock-in engines; '
                          'sweeper: the sweeper demo\'s multi-point inference (1 GPU)')
+    ap.add_argument('--no-multinomial', action='store_true', help='c4: skip the like-for-like multinomial line')
+    ap.add_argument('--no-invariance', action='store_true', help='multi-GPU: skip the G-invariance side check')
     args = ap.parse_args()
     n_total = int(args.particles)
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
-    config = {'workload': f'synthetic Lorentzian scale-out: {n_total:.0e} particles x {args.settings} settings, '
-                          f'n_draws={args.draws}, d=3, resample forced every cycle (BASELINE configs[3])',
-              'particles': n_total, 'settings': args.settings, 'n_draws': args.draws, 'n_params': 3,
-              'l2': 'inputs (3.2 GB per cycle) exceed the 126 MB L2, no flush needed'}
-
-    if args.workload == 'c5' and args.impl == 'ours':
-        return bench_c5(args, rank, world)
-    if args.workload == 'sweeper' and args.impl == 'ours':
-        return bench_sweeper(args) if rank == 0 else None
     if args.impl == 'reference':
-        if rank != 0:
-            return
-        base = cpu_cycle_rate(n_total, args.settings, args.draws, max_cycles=max(args.steps, 1) if args.steps < 8 else 8)
-        line = {'impl': 'reference', 'metric': 'pdf_update+resample+opt_setting cycles/sec', 'value': base['value'],
-                'unit': 'cycles/s', 'n_gpus': 0, 'steps': args.steps, 'warmup': args.warmup,
-                'ms_per_step': 1e3 / base['value'], 'higher_is_better': True, 'scaling': 'strong',
-                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config,
-                'cpu_baseline': base,
-                'e2e': {'value': base['value'], 'unit': 'cycles/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
-        return
+        return reference_line(args) if rank == 0 else None
+    if args.workload == 'c5':
+        return bench_c5(args, rank, world)
+    if args.workload == 'sweeper':
+        return bench_sweeper(args) if rank == 0 else None
+    if args.workload in ('c1', 'c2', 'c3'):
+        return bench_small(args) if rank == 0 else None      # replicas only: these shapes do not shard
+    config = workload_config('c4', args)
+    shard_mb = 8.0 * n_total * 4 / world / 1e6
+    config['l2'] = (f'inputs ({shard_mb / 1e3:.2f} GB per GPU and cycle) exceed the 126 MB L2, no flush needed'
+                    if shard_mb > 4 * 126 else f'per-GPU working set {shard_mb:.0f} MB is within reach of the 126 MB L2: '
+                    'L2-resident number, no flush')
 
     import torch
     import torch.distributed as dist
@@ -437,6 +663,38 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- outside every timed region: sanity of the sharded run, G-invariance side problem --------
+    invariance = None
+    if world > 1:
+        from optbayesexpt_b200 import _lib as _obe_lib
+        counts = eng.shard_counts
+        assert int(counts.sum()) == n_total, f'shard lengths {counts} do not sum to {n_total}'
+        eng._fetch_plan()
+        assert float(eng._plan[_obe_lib.PLAN_OVERFLOW].item()) == 0.0, 'a shard overflowed its capacity / exchange timed out'
+        if not args.no_invariance:
+            invariance = invariance_check(world, rank, torch, obe)
+            invariance['bench_shard_counts'] = [int(c) for c in counts]
+
+    # ---------------- like for like: the reference's multinomial algorithm on the device (N = 1) --------------
+    multinomial = None
+    if world == 1 and not args.no_multinomial:
+        eng.resampling = 'multinomial_device'
+        k_m = max(3, min(10, args.steps))
+        for t in range(2):
+            eng.run_cycle_async(fixed[t])
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for t in range(k_m):
+            eng.run_cycle_async(fixed[t % len(fixed)])
+        m1.record()
+        torch.cuda.synchronize()
+        ms_m = m0.elapsed_time(m1) / k_m
+        multinomial = {'ms_per_step': ms_m, 'cycles_per_s': 1e3 / ms_m, 'steps': k_m,
+                       'note': 'same ALGORITHM as the reference (N i.i.d. uniforms -> CDF -> searchsorted -> gather -> '
+                               'Liu-West), all on the device: k_cdf + k_search + k_gather_jitter, uniforms from torch\'s CUDA '
+                               'generator, Philox normals; the systematic comb above is the default fast path'}
+        eng.resampling = 'systematic'
 
     if rank != 0:
         if world > 1:

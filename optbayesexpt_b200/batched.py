@@ -32,7 +32,8 @@ class BatchedOptBayesExpt:
         if not isinstance(measurement_model, DeviceModel):
             raise TypeError('measurement_model must be a DeviceModel; there is no CPU fallback')
         self.model_function = measurement_model
-        dev = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+        from .models import resolve_device
+        dev = resolve_device(device)
         self._dev = dev
         if isinstance(parameter_samples, torch.Tensor):
             src = parameter_samples.to(dtype=torch.float64, device=dev)
@@ -162,8 +163,10 @@ class BatchedOptBayesExpt:
         rec = np.zeros((B, 12))
         y = np.asarray(y_meas, dtype=np.float64).reshape(B, -1)
         n_lik = min(self.n_channels, y.shape[1])
-        rec[:, 4:4 + y.shape[1]] = y
+        rec[:, 4:4 + n_lik] = y[:, :n_lik]
         if self._noise_index is None:
+            if sigma is None:
+                raise ValueError('sigma is required: this engine has no noise_parameter_index (known-sigma model)')
             sg = np.asarray(sigma, dtype=np.float64)
             if sg.ndim == 1 and sg.shape[0] == B:
                 sg = sg.reshape(B, 1)

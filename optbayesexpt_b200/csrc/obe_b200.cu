@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/obe_b200.h"
@@ -46,14 +47,14 @@ static int obe_fail(const char* fmt, const char* a = "", const char* b = "") {
         if (e_ != cudaSuccess) return obe_fail("launch %s: %s", what, cudaGetErrorString(e_)); \
     } while (0)
 
-static int g_sms = 0;
+static int g_sms[64] = {0};            // per device: a process may drive several (the current device decides)
 static int obe_sms() {
-    if (g_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-        if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_sms = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    if (g_sms[dev] == 0) {
+        if (cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_sms[dev] = 0;
     }
-    return g_sms;
+    return g_sms[dev];
 }
 #define OBE_BLOCKS_PER_SM 4
 #define OBE_MAX_GRID 4096
@@ -726,6 +727,8 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
 #define OBE_PLAN_CLUSTER 8
 static int64_t g_utility_lane_fill = 50;          /* obe_set_option("utility_lane_fill"), percent of resident threads */
 static int64_t g_plan_cluster_min_tiles = 8192;   /* obe_set_option("plan_cluster_min_tiles") */
+static int64_t g_resample_fused = 1;              /* obe_set_option("resample_fused"): 1 = k_sys_resample_warp, 0 = ancestors + move */
+static int64_t g_resample_blocks = 0;             /* obe_set_option("resample_blocks"): CTAs per SM of the fused kernel (0: default) */
 #ifndef OBE_PLAN_CLUSTER_MIN_TILES
 #define OBE_PLAN_CLUSTER_MIN_TILES 8192     /* below: one CTA does every pass in a single round anyway */
 #endif
@@ -1253,6 +1256,311 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_MOVE_BLOCKS(D)) k_sys_move(co
     }
 }
 
+// ---- one-kernel systematic resample, warp-autonomous -------------------------------------------
+// The two-kernel path above pays for the ancestor array twice (4 B written + 4 B read per particle) and its
+// ancestors kernel is barrier/latency-bound (5 block barriers per unit, 87 instructions per particle, 0.43 of
+// HBM).  Here ONE WARP owns a work unit (input tile k, <= OBE_OUT_CHUNK output slots) from the weights to the
+// stores, so nothing in the unit needs a block barrier and the ancestors never leave the SM:
+//   phase A  the warp walks the tile's eight canonical 256-particle segments in order (lane t owns particles
+//            [8t, 8t+8) of the segment: the same blocked layout, Kogge-Stone lane scan and SEQUENTIAL carry over
+//            the segments that tile_scan_blocked uses, so every CDF value has the canonical bits; the next
+//            segment's weights are in flight while this one is scanned), turns the CDF values into end slots
+//            (comb count, running max carried across segments in a register), and every particle that owns
+//            slots of the chunk marks the first of them in the warp's private array of ushort marks;
+//   phase B  the chunk's slots are emitted in groups of 128: 4 consecutive slots per lane, the marks are
+//            max-scanned in registers (carry across groups in a register), ancestors gathered through L1
+//            (monotone ancestors: the gathers walk the tile almost sequentially), Philox / Box-Muller /
+//            Liu-West, 16-byte stores of 32 contiguous bytes per lane and row.  Groups are aligned to 4 output
+//            slots in GLOBAL output coordinates (the chunk is shifted by A = o_base & 3), so every full group
+//            stores whole 32-byte sectors.
+// Same arithmetic as sys_unit_ancestors + k_sys_move, so the ancestors and the offspring are bit-identical to
+// the two-kernel path's.  Algorithmic traffic 8N(2d+1) instead of 8N(2d+2).
+#define OBE_WR_GROUP 128
+#define OBE_WR_MARKS (OBE_OUT_CHUNK + OBE_WR_GROUP)      /* shifted chunk coordinates: A + n_chunk <= 4099 */
+#define OBE_WR_SMEM ((OBE_THREADS / 32) * OBE_WR_MARKS * 2)
+#ifndef OBE_WR_BLOCKS
+#define OBE_WR_BLOCKS(d) ((d) <= 4 ? 3 : 2)              /* resident CTAs per SM: 66 KB of marks each; registers */
+#endif
+
+__device__ __forceinline__ void wr_load_segment(const double* __restrict__ wt, int i0, int cnt_tile, double wuni,
+                                                double (&v)[OBE_EPT]) {
+    if (wuni > 0.0) {
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; ++e) v[e] = (i0 + e < cnt_tile) ? wuni : 0.0;
+    } else if (i0 + OBE_EPT <= cnt_tile) {
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; e += 2) {
+            const double2 x2 = *reinterpret_cast<const double2*>(wt + i0 + e);
+            v[e] = x2.x; v[e + 1] = x2.y;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; ++e) v[e] = (i0 + e < cnt_tile) ? wt[i0 + e] : 0.0;
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_warp(const ObeResampleArgs a) {
+    constexpr int NWARP = OBE_THREADS / 32;
+    extern __shared__ __align__(16) unsigned short wr_marks[];     // [NWARP][OBE_WR_MARKS]
+    __shared__ double sF[D * D];
+    __shared__ double sMean[D];
+    __shared__ SysCtx cs;
+    __shared__ int s_units;
+    __shared__ long long s_tiles_in;
+    if (threadIdx.x == 0) {
+        long long n_tiles_in;
+        cs = sys_ctx_of(a, n_tiles_in);
+        s_units = a.unit_start[n_tiles_in];
+        s_tiles_in = n_tiles_in;
+    }
+    for (int q = threadIdx.x; q < NWARP * OBE_WR_MARKS / 2; q += OBE_THREADS)
+        reinterpret_cast<unsigned int*>(wr_marks)[q] = 0u;
+    setup_factor<D>(a, sF, sMean);                       // ends with a block barrier
+    const SysCtx& c = cs;
+    if (blockIdx.x == gridDim.x - 1) {
+        // bookkeeping block (as in k_sys_ancestors): tile sums, CDF prefix and stats of the offspring cloud
+        __shared__ double smd[OBE_SCANW * (OBE_THREADS / 32 + 1)];
+        const long long slot_end = a.plan ? (long long)a.plan[OBE_PL_SLOT1] : a.slot_end;
+        long long n_out = slot_end - c.slot_begin;
+        if (n_out > c.cap_out) n_out = c.cap_out;
+        const long long tiles_out = (n_out + OBE_TILE - 1) / OBE_TILE;
+        const long long n_total = (long long)c.nd;
+        for (long long k = threadIdx.x; k < tiles_out; k += OBE_THREADS) {
+            const long long cnt = min((long long)OBE_TILE, n_out - k * OBE_TILE);
+            a.out_tile_sums[k] = (double)cnt * c.wv;
+        }
+        __threadfence_block();
+        __syncthreads();
+        obe_tile_scan_block<OBE_THREADS / 32>(a.out_tile_sums, tiles_out, a.out_prefix, a.out_stats, 0, n_total, n_out,
+                                              a.implicit_out, smd, 0);
+        return;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned short* marks = wr_marks + warp * OBE_WR_MARKS;
+    const int n_units = s_units;
+    const int n_warps = ((int)gridDim.x - 1) * NWARP;
+#pragma unroll 1
+    for (int unit = (int)blockIdx.x * NWARP + warp; unit < n_units; unit += n_warps) {
+        int k;
+        if (a.unit_tile) {
+            k = a.unit_tile[unit];
+        } else {                                          // no unit -> tile map: last k with unit_start[k] <= unit
+            int lo = 0, hi = (int)s_tiles_in;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (a.unit_start[mid] <= unit) lo = mid + 1; else hi = mid;
+            }
+            k = lo - 1;
+        }
+        const long long Hk = a.plan_h[k], Hk1 = a.plan_h[k + 1];
+        const int rel_begin = (unit - a.unit_start[k]) * OBE_OUT_CHUNK;
+        const int n_chunk = min(rel_begin + OBE_OUT_CHUNK, (int)(Hk1 - Hk)) - rel_begin;
+        const long long chunk0 = Hk + rel_begin;                      // global slot of the chunk's first output
+        const long long o_base = chunk0 - c.slot_begin;               // its position in this shard's output
+        const int A = (int)(o_base & 3);                              // shifted chunk coordinate q' = q + A
+        const int q_end = A + n_chunk;
+        const long long base = (long long)k * OBE_TILE;
+        const int cnt_tile = (int)(min(c.n_in, base + OBE_TILE) - base);
+        const int lastrel = cnt_tile - 1;
+        // ---------------------------------------------------------------- phase A: marks
+        {
+            const double inv_total = c.inv_total, nd = c.nd, u0 = c.u0;
+            const double wuni = c.wuni_in;
+            const double p0 = obe_add(c.cdf_offset, c.prefix[k]);
+            const double* __restrict__ wt = c.w_in + base;
+            // fast comb count: x2 = c*n - u0 + 1/2 in ONE fma of the un-normalised CDF value with K = n/total, rounded to
+            // the nearest integer by the 1.5*2^52 trick (the low word of x2 + M IS the integer: no FRND / F2I), which is
+            // ceil(c*n - u0) unless c*n - u0 lies within `tolw` of an integer.  The estimate carries 4 more roundings
+            // than comb_count_d's (K, the fused normalisation, the pre-added prefix, the +1/2): <= 1e-15*n in all
+            // against tolw = 3e-15*n, so outside the window it equals the exact comb count; a thread that sees ANY of
+            // its 8 particles inside the window (probability ~5e-14*n) redoes all 8 the canonical way.
+            const double K = nd * inv_total, c_half = 0.5 - u0, tolh = 0.5 - 3e-15 * nd;
+            const double MAGIC = 6755399441055744.0;
+            const int c0a = (int)(unsigned int)(unsigned long long)(chunk0 - A);   // wraps: differences stay < 2^31
+            double wb = 0.0;                  // canonical sum of the totals of the segments before this one
+            int carry_end = A;                // end slot of the last particle walked so far
+            double vn[OBE_EPT];
+            wr_load_segment(wt, lane * OBE_EPT, cnt_tile, wuni, vn);
+#pragma unroll 1
+            for (int seg = 0; seg < OBE_TILE / 256; ++seg) {
+                if (seg * 256 > lastrel || carry_end >= q_end) break;
+                const int i0 = seg * 256 + lane * OBE_EPT;
+                double incl[OBE_EPT];
+                double run = 0.0;
+#pragma unroll
+                for (int e = 0; e < OBE_EPT; ++e) { run += vn[e]; incl[e] = run; }
+                if ((seg + 1) * 256 <= lastrel) wr_load_segment(wt, i0 + 256, cnt_tile, wuni, vn);   // in flight below
+                // canonical scan of the segment (tile_scan_blocked with the warp loop made sequential in time)
+                double x = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double y = __shfl_up_sync(0xffffffffu, x, o);
+                    if (lane >= o) x += y;
+                }
+                double ex = __shfl_up_sync(0xffffffffu, x, 1);
+                if (lane == 0) ex = 0.0;
+                const double seg_total = __shfl_sync(0xffffffffu, x, 31);
+                const double bs = wb + ex;
+                // end slot of every particle in shifted chunk coordinates (the running max supplies the lower clamp)
+                int h[OBE_EPT];
+                {
+                    const double bsp = p0 + bs;
+                    bool near = false;
+#pragma unroll
+                    for (int e = 0; e < OBE_EPT; ++e) {
+                        const double x2 = fma(bsp + incl[e], K, c_half);
+                        const double tt = x2 + MAGIC;
+                        const double dd = x2 - (tt - MAGIC);
+                        near |= !(fabs(dd) <= tolh);
+                        h[e] = __double2loint(tt) - c0a;
+                    }
+                    if (near) {                                  // rare: the canonical CDF value and the exact comb count
+                        const double chunk0d = (double)chunk0;
+#pragma unroll
+                        for (int e = 0; e < OBE_EPT; ++e) {
+                            const double cn = obe_mul(obe_add(p0, bs + incl[e]), inv_total);
+                            const double hd = comb_count_d(cn, u0, c.inv_n, nd, c.tol) - chunk0d;   // |hd| < 2^32
+                            h[e] = min(max(__double2int_rz(hd), 0), n_chunk) + A;             // the conversion saturates
+                        }
+                    }
+                    if (i0 + OBE_EPT > lastrel) {                // the tile's last live particle owns the tail
+#pragma unroll
+                        for (int e = 0; e < OBE_EPT; ++e)
+                            if (i0 + e >= lastrel) h[e] = q_end;
+                    }
+                }
+                int runm = A;
+#pragma unroll
+                for (int e = 0; e < OBE_EPT; ++e) {
+                    runm = max(runm, min(h[e], q_end));
+                    h[e] = runm;
+                }
+                int xm = runm;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, xm, o);
+                    if (lane >= o) xm = max(xm, y);
+                }
+                int exm = __shfl_up_sync(0xffffffffu, xm, 1);
+                if (lane == 0) exm = A;
+                exm = max(exm, carry_end);
+                // a particle that owns slots marks the first of them with its in-tile index + 1
+                if (runm > exm) {
+                    int prev = exm;
+#pragma unroll
+                    for (int e = 0; e < OBE_EPT; ++e) {
+                        const int end = max(h[e], exm);
+                        if (end > prev) marks[prev] = (unsigned short)(i0 + e + 1);
+                        prev = end;
+                    }
+                }
+                carry_end = max(carry_end, __shfl_sync(0xffffffffu, xm, 31));
+                wb = wb + seg_total;
+            }
+        }
+        __syncwarp();
+        // ---------------------------------------------------------------- phase B: emission
+        {
+            const long long room = c.cap_out - o_base;                // capacity overflow is flagged in the plan
+            const int n_emit = room < (long long)n_chunk ? (room > 0 ? (int)room : 0) : n_chunk;
+            const int q_emit_end = A + n_emit;
+            const long long o_al = o_base - A;                        // output position of q' = 0 (multiple of 4)
+            const long long og_al = chunk0 - A;                       // global slot of q' = 0
+            const double* __restrict__ pin = c.pin + base;
+            const long long ld_in = c.ld_in, ld_out = c.ld_out;
+            int last_anc = 0;                 // mark of the owner of the last slot of the previous group
+            // FULL: every slot of the group is a live output of this unit (warp-uniform): no per-slot predicates
+            auto emit = [&](auto full_tag, const int emit_pos) {
+                constexpr bool FULL = decltype(full_tag)::value;
+                const int q0 = emit_pos + lane * 4;
+                unsigned int* rp = reinterpret_cast<unsigned int*>(marks + q0);
+                const uint2 raw = *reinterpret_cast<const uint2*>(rp);
+                *reinterpret_cast<uint2*>(rp) = make_uint2(0u, 0u);
+                int m[4];
+                m[0] = (int)(raw.x & 0xffffu);
+                m[1] = max(m[0], (int)(raw.x >> 16));
+                m[2] = max(m[1], (int)(raw.y & 0xffffu));
+                m[3] = max(m[2], (int)(raw.y >> 16));
+                int xs = m[3];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, xs, o);
+                    if (lane >= o) xs = max(xs, y);
+                }
+                int exs = __shfl_up_sync(0xffffffffu, xs, 1);
+                if (lane == 0) exs = 0;
+                exs = max(exs, last_anc);
+                last_anc = max(last_anc, __shfl_sync(0xffffffffu, xs, 31));
+                bool ok[4];
+                int rel[4];
+                long long og[4];
+                double xv[4][D], z[4][D];
+                bool any = false, all = true;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int qq = q0 + u;
+                    ok[u] = FULL || (qq >= A && qq < q_emit_end);
+                    any |= ok[u];
+                    all &= ok[u];
+                    // (marks are indices of live particles + 1: no clamp to the tile's last live particle needed)
+                    rel[u] = FULL ? max(m[u], exs) - 1 : min(max(max(m[u], exs) - 1, 0), lastrel);
+                    og[u] = og_al + (long long)qq;
+                }
+                if (!FULL && !any) return;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) xv[u][j] = __ldg(pin + j * ld_in + rel[u]);
+                }
+                const long long o0 = o_al + q0;
+                if (c.jitter) {
+                    device_normals_vec<D, 4>(og, c.seed, c.epoch, z);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (c.z_out && ok[u]) {
+#pragma unroll
+                            for (int j = 0; j < D; ++j) c.z_out[(o0 + u) * D + j] = z[u][j];
+                        }
+                        liu_west<D>(xv[u], z[u], sF, sMean, c.a_param, c.scale);
+                    }
+                }
+                if (FULL || all) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        double* dst = c.pout + j * ld_out + o0;
+                        *reinterpret_cast<double2*>(dst) = make_double2(xv[0][j], xv[1][j]);
+                        *reinterpret_cast<double2*>(dst + 2) = make_double2(xv[2][j], xv[3][j]);
+                    }
+                    if (c.w_out) {
+                        *reinterpret_cast<double2*>(c.w_out + o0) = make_double2(c.wv, c.wv);
+                        *reinterpret_cast<double2*>(c.w_out + o0 + 2) = make_double2(c.wv, c.wv);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (!ok[u]) continue;
+#pragma unroll
+                        for (int j = 0; j < D; ++j) c.pout[j * ld_out + o0 + u] = xv[u][j];
+                        if (c.w_out) c.w_out[o0 + u] = c.wv;
+                    }
+                }
+                if (c.idx_out) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (ok[u]) c.idx_out[o0 + u] = base + rel[u];
+                }
+            };
+#pragma unroll 1
+            for (int emit_pos = 0; emit_pos < q_end; emit_pos += OBE_WR_GROUP) {
+                if (emit_pos >= A && emit_pos + OBE_WR_GROUP <= q_emit_end) emit(std::true_type{}, emit_pos);
+                else emit(std::false_type{}, emit_pos);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ---- batched systematic resample: one CTA walks the instances of the compacted list -------------
 struct ObeBResampleArgs {
     const double* particles[2];
@@ -1536,6 +1844,20 @@ __global__ void __launch_bounds__(OBE_STATS_LEN) k_shard_plan_peer(const ObePeer
         default: return obe_fail("n_params must be 1..8%s%s");                        \
     }
 
+#define OBE_DIM_CASE_WR(dd, grid, st, args)                                                               \
+    case dd:                                                                                              \
+        cudaFuncSetAttribute(k_sys_resample_warp<dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBE_WR_SMEM); \
+        k_sys_resample_warp<dd><<<grid, OBE_THREADS, OBE_WR_SMEM, st>>>(args);                              \
+        break;
+#define OBE_DIM_SWITCH_WR(d, grid, st, args)                                          \
+    switch (d) {                                                                      \
+        OBE_DIM_CASE_WR(1, grid, st, args) OBE_DIM_CASE_WR(2, grid, st, args)         \
+        OBE_DIM_CASE_WR(3, grid, st, args) OBE_DIM_CASE_WR(4, grid, st, args)         \
+        OBE_DIM_CASE_WR(5, grid, st, args) OBE_DIM_CASE_WR(6, grid, st, args)         \
+        OBE_DIM_CASE_WR(7, grid, st, args) OBE_DIM_CASE_WR(8, grid, st, args)         \
+        default: return obe_fail("n_params must be 1..8%s%s");                        \
+    }
+
 // ---------------------------------------------------------------------------------------------
 // Sweeper selection (demos/sweeper/obe_sweeper.py:118-162): a sweep from setting index `start` to
 // `stop` is worth the point utility integrated along the sweep, divided by its cost:
@@ -1786,6 +2108,8 @@ int obe_set_option(const char* name, int64_t value) {
     const std::string s(name);
     if (s == "plan_cluster_min_tiles") { g_plan_cluster_min_tiles = value < 0 ? 0 : value; return 0; }
     if (s == "utility_lane_fill") { g_utility_lane_fill = value < 0 ? 0 : value; return 0; }
+    if (s == "resample_fused") { g_resample_fused = value ? 1 : 0; return 0; }
+    if (s == "resample_blocks") { g_resample_blocks = value < 0 ? 0 : value; return 0; }
     return obe_fail("unknown option '%s'%s", name);
 }
 
@@ -2205,6 +2529,19 @@ static int launch_sys_resample(const obe_cloud_t* in, const obe_cloud_t* out, Ob
     if (in->n >= (1ll << 32)) return obe_fail("systematic resample supports shards of < 2^32 particles%s%s");
     a.anc = scratch_of(out).anc;
     a.out_tile_sums = out->tile_sums_dev; a.out_prefix = out->tile_prefix_dev; a.out_stats = out->stats_dev;
+    if (g_resample_fused) {
+        // one kernel: every warp owns work units from the weights to the stores (+ the bookkeeping block)
+        const int per_sm = (g_resample_blocks > 0 && g_resample_blocks < OBE_WR_BLOCKS(in->d)) ? (int)g_resample_blocks
+                                                                                              : OBE_WR_BLOCKS(in->d);
+        int64_t g = (int64_t)obe_sms() * per_sm;
+        const int64_t need = (max_units + OBE_THREADS / 32 - 1) / (OBE_THREADS / 32);
+        if (g > need) g = need;
+        if (g < 1) g = 1;
+        const int grid = (int)g + 1;
+        OBE_DIM_SWITCH_WR(in->d, grid, st, a)
+        OBE_LAUNCH_CHECK("k_sys_resample_warp");
+        return 0;
+    }
     {
         int64_t g = (int64_t)obe_sms() * OBE_ANC_BLOCKS_PER_SM;
         if (g > max_units) g = max_units;

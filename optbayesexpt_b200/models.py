@@ -136,6 +136,22 @@ def cuda_source(source, entry, n_settings, n_params, n_constants=0, n_channels=1
     return DeviceModel(f'user:{entry}', n_settings, n_params, n_constants, n_channels, source=source, entry=entry)
 
 
+def resolve_device(device=None):
+    """The CUDA device an engine lives on.  The C library launches on the CURRENT device and its streams (one
+    process per GPU is the design), so an explicit ``device=`` must name the current device: anything else would
+    run GPU-0 kernels on GPU-1 memory.  Select the GPU with ``torch.cuda.set_device`` before building an engine."""
+    import torch
+    cur = torch.cuda.current_device()
+    dev = torch.device(device if device is not None else f'cuda:{cur}')
+    if dev.type != 'cuda':
+        raise ValueError(f'optbayesexpt_b200 engines live on a CUDA device, got {dev}')
+    index = cur if dev.index is None else dev.index
+    if index != cur:
+        raise ValueError(f'device={dev} is not the current CUDA device (cuda:{cur}): call torch.cuda.set_device({index}) '
+                         'first -- the kernels are launched on the current device and its stream')
+    return torch.device('cuda', index)
+
+
 class ParticleBuffers:
     """Device buffers of one particle cloud + the obe_cloud_t that describes them."""
 
@@ -152,7 +168,7 @@ class ParticleBuffers:
             raise ValueError(f'n_dims must be 1..{_lib.MAX_PARAMS}, got {d}')
         if n < 1:
             raise ValueError('empty particle cloud')
-        self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+        self.device = resolve_device(device)
         self.n, self.d = int(n), int(d)
         cap = max(int(capacity or 0), self.n)      # shards of a multi-GPU cloud change length
         self.ld = cap + (cap & 1)

@@ -282,10 +282,11 @@ class OptBayesExpt(ParticlePDF):
         self._moments_valid = True      # on the device: the resample kernel reads them there
         self._weights_lazy = True
         if resample:
-            if self.resampling != 'systematic':
-                raise ValueError('run_cycle_async needs resampling="systematic"')
+            if self.resampling == 'multinomial':
+                raise ValueError('run_cycle_async needs a device-side resampler (systematic or multinomial_device)')
             self.resample()
             self.just_resampled = True
+            self._enforce_constraints_async()
         if select:
             self._utility_dev_run()
 
@@ -299,11 +300,30 @@ class OptBayesExpt(ParticlePDF):
         see ``_apply_constraint_masks``."""
         pass
 
-    def _apply_constraint_masks(self, mask_le=0, mask_lt=0):
-        """weight <- 0 where x_j <= 0 (mask_le bit j) or x_j < 0 (mask_lt bit j), renormalise."""
-        self._refresh(mask_le=mask_le, mask_lt=mask_lt, renormalise=1)
+    def _apply_constraint_masks(self, mask_le=0, mask_lt=0, sync=True):
+        """weight <- 0 where x_j <= 0 (mask_le bit j) or x_j < 0 (mask_lt bit j), renormalise.
+        ``sync=False`` only enqueues the masking pass (run_cycle_async): the stats stay on the device."""
+        if sync:
+            self._refresh(mask_le=mask_le, mask_lt=mask_lt, renormalise=1)
+        else:
+            ni = self._noise_index
+            self._check(self._lib.obe_refresh(self._cs(), mask_le, mask_lt, _lib.iarr(ni), 0 if ni is None else len(ni),
+                                              _lib.darr(self._pivot, _lib.MAX_PARAMS), 1, self._stream()))
+            self._stats = None
+            self._moments_valid = True      # on the device
+            self._weights_uniform = False
         self._weights_lazy = True
         self._invalidate()
+
+    def _constraint_masks(self):
+        """(mask_le, mask_lt) of the constraint enforce_parameter_constraints applies; (0, 0): none."""
+        return 0, 0
+
+    def _enforce_constraints_async(self):
+        """enforce_parameter_constraints without a host synchronisation (the masks are data)."""
+        le, lt = self._constraint_masks()
+        if le | lt:
+            self._apply_constraint_masks(mask_le=le, mask_lt=lt, sync=False)
 
     def likelihood(self, y_model, measurement_record):
         """Likelihood of the record for every particle (obe_base.py:418-461), on the device."""
@@ -350,7 +370,8 @@ class OptBayesExpt(ParticlePDF):
         draws = self._randdraw_dev(self.N_DRAWS, out=dd)
         n_set = len(self.setting_indices)
         if self._noise_from_stats():
-            self._ensure_moments()
+            if not self._moments_valid:     # (valid-on-device is enough: the kernel reads the stats block itself)
+                self._ensure_moments()
             var_noise = None
             stats_ptr = C.c_void_p(self._buf.stats.data_ptr())
         else:
@@ -390,10 +411,32 @@ class OptBayesExpt(ParticlePDF):
         self._utility_dev_run()
         return self._utility_dev.cpu().numpy()
 
-    utility_variance = utility
-    utility_max_min = utility
-    utility_pseudo = utility
-    utility_full_kld = utility
+    def _utility_as(self, code):
+        """The utility of method `code` whatever ``utility_method`` the engine was built with."""
+        if code == 3 and self.n_channels != 1:
+            raise ValueError('full_kld_utility supports single-channel models')
+        saved = self._utility_code
+        self._utility_code = code
+        try:
+            return self.utility()
+        finally:
+            self._utility_code = saved
+
+    def utility_variance(self):
+        """Variance-based utility (obe_base.py:628-655)."""
+        return self._utility_as(0)
+
+    def utility_max_min(self):
+        """(max - min over the draws)^2 / noise variance (obe_base.py:602-626)."""
+        return self._utility_as(1)
+
+    def utility_pseudo(self):
+        """Entropy-based pseudo-variance utility (obe_base.py:657-686)."""
+        return self._utility_as(2)
+
+    def utility_full_kld(self):
+        """Full Kullback-Leibler utility (obe_base.py:688-720)."""
+        return self._utility_as(3)
 
     def opt_setting(self):
         """Setting with the maximum utility (obe_base.py:733-756)."""

@@ -30,12 +30,15 @@ class OptBayesExptNoiseParameter(OptBayesExpt):
         OptBayesExpt.set_pdf(self, samples, weights)
         self._moments_valid = False
 
-    def enforce_parameter_constraints(self):
-        """Zero the weight of particles whose noise parameter is <= 0 (obe_noiseparam.py:57-79)."""
+    def _constraint_masks(self):
         mask = 0
         for i in self._noise_index:
             mask |= 1 << i
-        self._apply_constraint_masks(mask_le=mask)
+        return mask, 0
+
+    def enforce_parameter_constraints(self):
+        """Zero the weight of particles whose noise parameter is <= 0 (obe_noiseparam.py:57-79)."""
+        self._apply_constraint_masks(mask_le=self._constraint_masks()[0])
 
     def _likelihood_spec(self, measurement_record):
         """sigma comes from the particles; the record is (settings, y, ...) (obe_noiseparam.py:110-113)."""

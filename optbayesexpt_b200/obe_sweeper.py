@@ -45,6 +45,13 @@ class OptBayesExptSweeper(OptBayesExptNoiseParameter):
         self._sigma_ref = None
         self._sweep_chunk = 16
 
+    def _install(self, samples):
+        # a new cloud (set_pdf) invalidates everything sized or scaled for the old one: the spare weight row of
+        # the multi-point kernel and the noise scale taken from the last committed cloud
+        OptBayesExptNoiseParameter._install(self, samples)
+        self._multi_w = None
+        self._sigma_ref = None
+
     # ---- inference half
     def pdf_update(self, measurement_record):
         """Bayesian inference on a swept measurement (obe_sweeper.py:87-101): one noise-parameter update per

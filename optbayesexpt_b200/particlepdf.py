@@ -34,8 +34,8 @@ class ParticlePDF:
         #: dict: resampling knobs, live-mutable as in the reference (particlepdf.py:96-99)
         self.tuning_parameters = {'a_param': a_param, 'resample_threshold': resample_threshold,
                                   'auto_resample': auto_resample, 'scale': scale}
-        if resampling not in ('systematic', 'multinomial'):
-            raise ValueError("resampling must be 'systematic' or 'multinomial'")
+        if resampling not in ('systematic', 'multinomial', 'multinomial_device'):
+            raise ValueError("resampling must be 'systematic', 'multinomial' or 'multinomial_device'")
         self.resampling = resampling
         self.just_resampled = False
         try:
@@ -315,6 +315,31 @@ class ParticlePDF:
             self._check(self._lib.obe_gather_jitter(self._cs(), self._cs(self._alt), C.c_void_p(idx.data_ptr()),
                                                     _lib.darr(factor.reshape(-1)), _lib.darr(center),
                                                     C.c_void_p(z.data_ptr()), 0, 0, a_param, scale, self._stream()))
+            self._last_ancestors = idx
+        elif self.resampling == 'multinomial_device':
+            # the reference's ALGORITHM (N i.i.d. uniforms -> cumsum/searchsorted -> gather -> jitter,
+            # particlepdf.py:286-310) with the randomness made on the device: uniforms from torch's CUDA
+            # generator, normals from the Philox stream, Cholesky factor from the device moments.  No host
+            # round trip; this is the like-for-like arm of the bench (same algorithm as the CPU reference).
+            if not self._moments_valid:
+                self._ensure_moments()
+            gen = getattr(self, '_torch_gen', None)
+            if gen is None:
+                gen = self._torch_gen = torch.Generator(device=self._buf.device)
+                gen.manual_seed(self._philox_seed & 0x7fffffffffffffff)
+            mb = getattr(self, '_multinomial_bufs', None)
+            if mb is None or mb[0].numel() != n:
+                mb = self._multinomial_bufs = (torch.empty(n, dtype=torch.float64, device=self._buf.device),
+                                               torch.empty(n, dtype=torch.float64, device=self._buf.device),
+                                               torch.empty(n, dtype=torch.int64, device=self._buf.device))
+            u, cdf, idx = mb
+            torch.rand(n, generator=gen, dtype=torch.float64, device=self._buf.device, out=u)
+            self._check(self._lib.obe_cdf(self._cs(), C.c_void_p(cdf.data_ptr()), self._stream()))
+            self._check(self._lib.obe_search(self._cs(), C.c_void_p(cdf.data_ptr()), C.c_void_p(u.data_ptr()),
+                                             n, C.c_void_p(idx.data_ptr()), self._stream()))
+            self._check(self._lib.obe_gather_jitter(self._cs(), self._cs(self._alt), C.c_void_p(idx.data_ptr()),
+                                                    None, None, None, self._philox_seed, self._epoch, a_param, scale,
+                                                    self._stream()))
             self._last_ancestors = idx
         else:
             if not self._moments_valid:

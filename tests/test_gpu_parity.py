@@ -391,17 +391,61 @@ def test_multinomial_resample_matches_oracle(obe, scale):
                                  (4097, 1), (10000, 1), (30011, 4), (10000, 6), (6151, 8)])
 @pytest.mark.parametrize('scale', [False, True])
 @pytest.mark.parametrize('plan', ['one_cta', 'cluster'])
-def test_systematic_resample_matches_oracle(obe, torch, n, d, scale, plan):
-    """Systematic resample (plan + ancestors + move kernels): ancestors == searchsorted(cdf_gpu, comb)
-    bit-exact; normals are the restated Philox/Box-Muller stream; particles == Liu-West with the Cholesky
-    factor.  Sizes around the tile boundaries, every register/shared-memory variant of the move kernel (d)."""
+@pytest.mark.parametrize('kernel', ['warp_fused', 'two_kernel'])
+def test_systematic_resample_matches_oracle(obe, torch, n, d, scale, plan, kernel):
+    """Systematic resample (plan + the warp-autonomous fused kernel, or plan + ancestors + move): ancestors ==
+    searchsorted(cdf_gpu, comb) bit-exact; normals are the restated Philox/Box-Muller stream; particles ==
+    Liu-West with the Cholesky factor.  Sizes around the tile boundaries, every register variant of the kernels (d)."""
     from optbayesexpt_b200 import _lib
     # the resample plan on one CTA, or on the cluster of 8 CTAs that large clouds (> 8192 tiles) get
     _lib.check(_lib.load().obe_set_option(b'plan_cluster_min_tiles', 0 if plan == 'cluster' else 1 << 40))
+    _lib.check(_lib.load().obe_set_option(b'resample_fused', 1 if kernel == 'warp_fused' else 0))
     try:
         _systematic_case(obe, torch, n, d, scale)
     finally:
         _lib.check(_lib.load().obe_set_option(b'plan_cluster_min_tiles', 8192))
+        _lib.check(_lib.load().obe_set_option(b'resample_fused', 1))
+
+
+@pytest.mark.parametrize('n,d,heavy', [(3_000_001, 3, False), (1_000_003, 2, True), (700_001, 5, False),
+                                       (2_000_000, 1, True)])
+def test_fused_resample_equals_two_kernel(obe, torch, n, d, heavy):
+    """The one-kernel (warp-autonomous) systematic resample and the ancestors + move pair are the same function:
+    identical ancestors, identical normals, bit-identical offspring -- at sizes with many work units per warp, with
+    heavy particles that own many chunks of output slots, and with runs of dead particles."""
+    from optbayesexpt_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device='cuda')
+    g.manual_seed(n)
+    prior = torch.randn((d, n), generator=g, dtype=torch.float64, device='cuda') * 3 + 1
+    w = torch.rand(n, generator=g, dtype=torch.float64, device='cuda') ** 4
+    w[torch.rand(n, generator=g, dtype=torch.float64, device='cuda') < 0.25] = 0.0
+    if heavy:
+        w[12345] = w.sum() * 0.3                                   # owns ~23 % of the slots: hundreds of chunks
+        w[n - 7] = w.sum() * 0.05
+        w[2048 * 100: 2048 * 140] = 0.0                            # forty dead tiles in a row
+    w /= w.sum()
+    out = {}
+    for fused in (1, 0):
+        pdf = obe.ParticlePDF(prior, scale=True, resampling='systematic', seed=5)
+        pdf.particle_weights = w.cpu().numpy()
+        pdf._ensure_moments()
+        alt = pdf._buf.empty_like()
+        idx = torch.empty(n, dtype=torch.int64, device='cuda')
+        _lib.check(lib.obe_set_option(b'resample_fused', fused))
+        try:
+            _lib.check(lib.obe_resample_systematic(pdf._cs(), C.byref(alt.struct()), 0.61803, None, None, 42, 7, 0.98, 1,
+                                                   C.c_void_p(idx.data_ptr()), None, pdf._stream()))
+        finally:
+            _lib.check(lib.obe_set_option(b'resample_fused', 1))
+        out[fused] = (idx.clone(), alt.particles[:, :n].clone(), alt.stats.clone(), alt.tile_prefix.clone())
+    assert torch.equal(out[1][0], out[0][0])
+    assert torch.equal(out[1][1], out[0][1])
+    assert torch.equal(out[1][2], out[0][2]) and torch.equal(out[1][3], out[0][3])
+    idx = out[1][0]
+    assert bool((idx[1:] >= idx[:-1]).all()) and int(idx[0]) >= 0 and int(idx[-1]) < n
+    counts = torch.bincount(idx, minlength=n).to(torch.float64)
+    assert float((counts - n * w).abs().max()) < 1.0 + 1e-6
 
 
 def _systematic_case(obe, torch, n, d, scale):
