@@ -706,10 +706,13 @@ def main():
     # (never stored, never read): it moves d particle rows in and one weight row out, 8N(d+1), not the 8N(d+2)
     # of an update that follows an update.
     b_upd = 8.0 * n_total * (d + 1)
-    b_res = 8.0 * n_total * (2 * d + 2)
+    b_res = 8.0 * n_total * (2 * d + 2)                # read w, gather d rows, write d rows, write w
+    b_res_moved = 8.0 * n_total * (2 * d + 1)          # what this build has to move: the offspring weights stay implicit
     b_sel = 8.0 * args.settings * 2
     b_cycle = b_upd + b_res + b_sel
     gbs_res = b_res / world / (t_res * 1e-3) / 1e9
+    fused = os.environ.get('OBE_OPT_RESAMPLE_FUSED', '1') != '0'
+    sharded_launches = 0 if world == 1 else (3 if getattr(eng, '_peer', None) is not None else 2)
     line = {
         'metric': 'pdf_update+resample+opt_setting cycles/sec', 'value': 1e3 / ms_step, 'unit': 'cycles/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
@@ -719,15 +722,23 @@ def main():
                 'h2d_bytes_per_step': 8 * (1 + 1 + 1 + 8 + 1) + 8 * args.draws,
                 'd2h_bytes_per_step': 8 * 64 + 16,
                 'note': 'record, pivot and uniforms travel as kernel arguments; stats block + argmax come back'},
-        # update, plan, ancestors, move, draw, utility; sharded: + shard plan (peer exchange fused in) + draw collect
-        'gpu_launches': (6 if world == 1 else (8 if getattr(eng, '_peer', None) is not None else 7)) * args.steps,
-        'roofline': {'bound': 'hbm', 'kernel': 'resample step = k_sys_plan + k_sys_ancestors + k_sys_move (one event bracket)',
+        # update, plan, resample (one kernel; two on the ancestors + move path), draw, utility;
+        # sharded: + shard plan (peer exchange fused in) + draw collect
+        'gpu_launches': ((5 if fused else 6) + sharded_launches) * args.steps,
+        'roofline': {'bound': 'hbm',
+                     'kernel': ('resample step = k_sys_plan + k_sys_resample_warp (one event bracket)' if fused else
+                                'resample step = k_sys_plan + k_sys_ancestors + k_sys_move (one event bracket)'),
                      'achieved': gbs_res, 'peak': peak, 'unit': 'GB/s', 'frac': gbs_res / peak,
-                     # dram__bytes_read+write of the three kernels, ncu --set full (profiles/r1_final_ncu_summary.md):
-                     # 63.8 bytes per particle at d = 3
-                     'traffic': 63.8 * n_total / world if d == 3 else None,
-                     'peak_source': peak_src,
-                     'algorithmic_bytes_per_launch': b_res / world},
+                     'algorithmic_bytes_per_launch': b_res / world,
+                     'algorithmic_note': 'SURVEY 8(d): 8N(2d+2) (read w, gather d rows, write d rows, write w)',
+                     'moved_bytes_per_launch': b_res_moved / world,
+                     'frac_of_moved_bytes': b_res_moved / world / (t_res * 1e-3) / 1e9 / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the resample kernels from the ncu --set full capture
+                     # of this build (profiles/r2_ncu_summary.md): bytes per particle at d = 3, scaled to this launch
+                     'traffic': (53.3 if fused else 63.8) * n_total / world if d == 3 else None,
+                     'traffic_source': 'profiles/r2_ncu_summary.md (ncu --set full of the same build and workload; '
+                                       'per-particle figure x particles of this launch, not re-measured in this run)',
+                     'peak_source': peak_src},
         'kernels_ms': {'update': t_upd, 'resample': t_res, 'draw+utility+argmax': t_sel},
         'kernels_gbs': {'update': b_upd / world / (t_upd * 1e-3) / 1e9, 'resample': gbs_res},
         'exchange': None if world == 1 else ('peer (CUDA IPC over NVLink)' if getattr(eng, '_peer', None) is not None
@@ -738,8 +749,17 @@ def main():
             'hbm_frac': (8.0 * n_total * (d + 2) + b_sel) / (ms_nores * 1e-3) / 1e9 / peak},
         'clocks': clocks,
     }
+    if multinomial is not None:
+        line['multinomial_device'] = multinomial
+    if invariance is not None:
+        line['invariance'] = invariance
+    try:
+        fp = json.load(open(os.path.join(ROOT, 'profiles', 'fp64_peak.json')))
+        line['fp64_peak_tflops'] = fp.get('fp64_tflops')
+    except Exception:
+        pass
     if not args.no_cpu_baseline and world == 1:       # the CPU arm is timed at N = 1 only
-        line['cpu_baseline'] = cpu_cycle_rate(n_total, args.settings, args.draws)
+        line['cpu_baseline'] = cpu_arm('c4', args, warmup=1, steps=5, budget_s=30.0)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -39,21 +39,25 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """``defines`` / ``out``: A/B builds of tuning variants (-DNAME=VALUE ..., written next to the library;
+    select one at run time with OBE_B200_LIB=<path>)."""
+    if not force and not defines and not needs_build():
         return LIB
     _embed('obe_device.cuh')
     _embed('obe_models.cuh')
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
-        ['-o', LIB, os.path.join(CSRC, 'obe_b200.cu'), '-ldl']
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + [f'-D{d}' for d in defines] + \
+        ['-o', out or LIB, os.path.join(CSRC, 'obe_b200.cu'), '-ldl']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith('-D')]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith('--out=')]
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, defines=defs, out=outs[0] if outs else None))

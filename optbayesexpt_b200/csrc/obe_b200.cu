@@ -68,9 +68,12 @@ struct Scratch {
     long long* plan_h;       // n_tiles + 1
     int* unit_start;         // n_tiles + 2
     unsigned int* anc;       // n + 4 (ancestors of the offspring written INTO this cloud)
-    int* unit_tile;          // n_tiles + n / OBE_OUT_CHUNK_HOST + 4 (work unit -> input tile)
+    int* unit_tile;          // n_tiles + n / OBE_WR_CHUNK + 4 (work unit -> input tile)
 };
 #define OBE_OUT_CHUNK_HOST 4096
+#ifndef OBE_WR_CHUNK
+#define OBE_WR_CHUNK 3200   /* output slots per work unit of the one-kernel resample (k_sys_resample_warp) */
+#endif
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static size_t scratch_bytes(int64_t n) {
     const int64_t nt = (n + OBE_TILE - 1) / OBE_TILE;
@@ -79,7 +82,7 @@ static size_t scratch_bytes(int64_t n) {
     b += align_up((size_t)(nt + 1) * sizeof(long long), 256);
     b += align_up((size_t)(nt + 2) * sizeof(int), 256);
     b += align_up((size_t)(n + 4) * sizeof(unsigned int), 256);
-    b += align_up((size_t)(nt + n / OBE_OUT_CHUNK_HOST + 4) * sizeof(int), 256);
+    b += align_up((size_t)(nt + n / OBE_WR_CHUNK + 4) * sizeof(int), 256);
     return b;
 }
 static Scratch scratch_of(const obe_cloud_t* c) {
@@ -477,6 +480,53 @@ __device__ __forceinline__ void device_normals_vec(const long long (&slot)[U], u
     }
 }
 
+// Packed normal stream of the streaming resample kernels (k_sys_resample_warp, k_sys_move): the jitter normals of
+// the whole cloud form ONE sequence, normal m = D * slot + j, four per Philox call (two Box-Muller pairs): call
+// q = m >> 2, word m & 3.  A thread that owns 4 consecutive output slots starting at a multiple of 4 needs exactly
+// the calls (slot0 / 4) * D ... + D - 1: D calls per 4 slots whatever D, none of the 128 bits wasted (the per-slot
+// stream of device_normals spends 4 * ceil(D / 4) calls).  ctr = (q_lo, q_hi, 0x80000000 | D, epoch), key = seed.
+// Slots are GLOBAL comb slots, so the jitter does not depend on how the cloud is sharded.  Restated in
+// oracle/obe_oracle.py:device_normals_packed.
+template <int D>
+__device__ __forceinline__ void packed_normals4(long long slot0, unsigned long long seed, unsigned int epoch,
+                                                double (&z)[4][D]) {
+    const unsigned int key0 = (unsigned int)(seed & 0xffffffffull), key1 = (unsigned int)(seed >> 32);
+    const unsigned long long q0 = (unsigned long long)(slot0 >> 2) * (unsigned long long)D;
+    unsigned int c0[D], c1[D], c2[D], c3[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        const unsigned long long q = q0 + (unsigned long long)c;
+        c0[c] = (unsigned int)(q & 0xffffffffull);
+        c1[c] = (unsigned int)(q >> 32);
+        c2[c] = 0x80000000u | (unsigned int)D; c3[c] = epoch;
+    }
+    unsigned int k0 = key0, k1 = key1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const unsigned int hi0 = __umulhi(0xD2511F53u, c0[c]), lo0 = 0xD2511F53u * c0[c];
+            const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2[c]), lo1 = 0xCD9E8D57u * c2[c];
+            const unsigned int n0 = hi1 ^ c1[c] ^ k0, n2 = hi0 ^ c3[c] ^ k1;
+            c0[c] = n0; c1[c] = lo1; c2[c] = n2; c3[c] = lo0;
+        }
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        const unsigned int r4[4] = {c0[c], c1[c], c2[c], c3[c]};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float rad = obe_sqrt_approx(-2.0f * __logf(u24(r4[2 * h])));
+            float sn, cs;
+            __sincosf(6.2831853071795865f * u24(r4[2 * h + 1]), &sn, &cs);
+            const int f = 4 * c + 2 * h;                     // compile-time after unrolling
+            z[f / D][f % D] = (double)(rad * cs);
+            z[(f + 1) / D][(f + 1) % D] = (double)(rad * sn);
+        }
+    }
+}
+
 // Liu-West move of one particle (particlepdf.py:296-307): x + z @ F, optional contraction
 template <int D>
 __device__ __forceinline__ void liu_west(double (&x)[D], const double (&z)[D], const double* __restrict__ F,
@@ -489,6 +539,67 @@ __device__ __forceinline__ void liu_west(double (&x)[D], const double (&z)[D], c
         double v = x[j] + nud;
         if (scale) v = obe_add(obe_mul(v, a_param), obe_mul(mean[j], obe_sub(1.0, a_param)));
         x[j] = v;
+    }
+}
+
+// Liu-West move of 4 consecutive output slots (global slots slot0 .. slot0+3, slot0 a multiple of 4) with the packed
+// normal stream, STREAMING: every normal is folded into the D coordinates it nudges as soon as Box-Muller produces it
+// (x_j <- fma(z_k, F[k][j], x_j)), so the 4*D normals are never all live -- 2*4*D registers less than building z
+// first, which is what lets the resample kernels keep their gathers and the Philox state in registers.  z_out
+// (tests): the normals are also stored, (n, D) row-major at output position o0 + u.
+template <int D>
+__device__ __forceinline__ void jitter_group4(double (&xv)[4][D], long long slot0, unsigned long long seed,
+                                              unsigned int epoch, const double* __restrict__ F,
+                                              const double* __restrict__ mean, double a_param, int scale,
+                                              double* __restrict__ z_out, long long o0, const bool (&ok)[4]) {
+    const unsigned int key0 = (unsigned int)(seed & 0xffffffffull), key1 = (unsigned int)(seed >> 32);
+    const unsigned long long q0 = (unsigned long long)(slot0 >> 2) * (unsigned long long)D;
+    unsigned int c0[D], c1[D], c2[D], c3[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        const unsigned long long q = q0 + (unsigned long long)c;
+        c0[c] = (unsigned int)(q & 0xffffffffull);
+        c1[c] = (unsigned int)(q >> 32);
+        c2[c] = 0x80000000u | (unsigned int)D; c3[c] = epoch;
+    }
+    unsigned int k0 = key0, k1 = key1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const unsigned int hi0 = __umulhi(0xD2511F53u, c0[c]), lo0 = 0xD2511F53u * c0[c];
+            const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2[c]), lo1 = 0xCD9E8D57u * c2[c];
+            const unsigned int n0 = hi1 ^ c1[c] ^ k0, n2 = hi0 ^ c3[c] ^ k1;
+            c0[c] = n0; c1[c] = lo1; c2[c] = n2; c3[c] = lo0;
+        }
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        const unsigned int r4[4] = {c0[c], c1[c], c2[c], c3[c]};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float rad = obe_sqrt_approx(-2.0f * __logf(u24(r4[2 * h])));
+            float sn, cs;
+            __sincosf(6.2831853071795865f * u24(r4[2 * h + 1]), &sn, &cs);
+            const double zz[2] = {(double)(rad * cs), (double)(rad * sn)};
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const int f = 4 * c + 2 * h + w;                 // compile-time after unrolling
+                const int u = f / D, k = f % D;
+                if (z_out && ok[u]) z_out[(o0 + u) * D + k] = zz[w];
+#pragma unroll
+                for (int j = 0; j < D; ++j) xv[u][j] = fma(zz[w], F[k * D + j], xv[u][j]);
+            }
+        }
+    }
+    if (scale) {
+        const double b = obe_sub(1.0, a_param);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) xv[u][j] = obe_add(obe_mul(xv[u][j], a_param), obe_mul(mean[j], b));
+        }
     }
 }
 
@@ -640,7 +751,8 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
                                                                int* __restrict__ unit_start,
                                                                int* __restrict__ unit_tile,
                                                                const long long* __restrict__ n_dev = nullptr,
-                                                               const double* __restrict__ plan = nullptr) {
+                                                               const double* __restrict__ plan = nullptr,
+                                                               int chunk = OBE_OUT_CHUNK) {
     __shared__ long long sml[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     __shared__ int smi[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     const int t = threadIdx.x;
@@ -699,7 +811,7 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
 #pragma unroll
         for (int e = 0; e < OBE_SCANW; ++e) {
             const long long k = base + e * OBE_SCAN_THREADS + t;
-            units[e] = (k < n_tiles) ? (int)((max(H[k + 1] - H[k], 0ll) + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK) : 0;
+            units[e] = (k < n_tiles) ? (int)((max(H[k + 1] - H[k], 0ll) + chunk - 1) / chunk) : 0;
         }
         obe_block_excl_scanw<int, NWP>(units, ex, tot, smi, ObeOpSum(), 0, 0);
 #pragma unroll
@@ -727,6 +839,7 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
 #define OBE_PLAN_CLUSTER 8
 static int64_t g_utility_lane_fill = 50;          /* obe_set_option("utility_lane_fill"), percent of resident threads */
 static int64_t g_plan_cluster_min_tiles = 8192;   /* obe_set_option("plan_cluster_min_tiles") */
+static int64_t g_utility_cache = 1;               /* obe_set_option("utility_cache"): park the K curves in shared memory */
 static int64_t g_resample_fused = 1;              /* obe_set_option("resample_fused"): 1 = k_sys_resample_warp, 0 = ancestors + move */
 static int64_t g_resample_blocks = 0;             /* obe_set_option("resample_blocks"): CTAs per SM of the fused kernel (0: default) */
 #ifndef OBE_PLAN_CLUSTER_MIN_TILES
@@ -736,7 +849,7 @@ __global__ void __cluster_dims__(OBE_PLAN_CLUSTER, 1, 1) __launch_bounds__(OBE_S
 k_sys_plan_cluster(const double* __restrict__ prefix, long long n_tiles, long long n_total, double u0,
                    double cdf_offset, double cdf_total, long long slot_begin, long long slot_end,
                    long long* __restrict__ H, int* __restrict__ unit_start, int* __restrict__ unit_tile,
-                   const long long* __restrict__ n_dev, const double* __restrict__ plan) {
+                   const long long* __restrict__ n_dev, const double* __restrict__ plan, int chunk) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int r = (int)cluster.block_rank();
@@ -815,7 +928,7 @@ k_sys_plan_cluster(const double* __restrict__ prefix, long long n_tiles, long lo
             if (k < k_hi) {
                 // H[k+1] of this segment still lacks the floor; the last tile's neighbour is next_h
                 const long long h1 = (k + 1 < k_hi) ? max(H[k + 1], floor_h) : next_h;
-                units[e] = (int)((max(h1 - hf[e], 0ll) + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK);
+                units[e] = (int)((max(h1 - hf[e], 0ll) + chunk - 1) / chunk);
             }
         }
         __syncthreads();                             // all reads of the un-floored H precede the writes below
@@ -841,7 +954,7 @@ k_sys_plan_cluster(const double* __restrict__ prefix, long long n_tiles, long lo
     for (long long k = k_lo + t; k < k_hi; k += OBE_SCAN_THREADS) {
         const int first = unit_start[k] + off;
         const long long h1 = (k + 1 < k_hi) ? H[k + 1] : next_h;
-        const int units = (int)((max(h1 - H[k], 0ll) + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK);
+        const int units = (int)((max(h1 - H[k], 0ll) + chunk - 1) / chunk);
         unit_start[k] = first;
         if (unit_tile)
             for (int u = 0; u < units; ++u) unit_tile[first + u] = (int)k;
@@ -1173,9 +1286,7 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_ANC_BLOCKS_PER_SM) k_sys_ance
     }
 }
 
-#ifndef OBE_MOVE_V
 #define OBE_MOVE_V 4
-#endif
 #define OBE_MOVE_BLOCKS(d) ((d) <= 3 ? 4 : ((d) == 4 ? 3 : 2))   /* resident CTAs per SM the registers allow */
 template <int D>
 __global__ void __launch_bounds__(OBE_THREADS, OBE_MOVE_BLOCKS(D)) k_sys_move(const ObeResampleArgs a) {
@@ -1183,66 +1294,52 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_MOVE_BLOCKS(D)) k_sys_move(co
     __shared__ double sF[D * D];
     __shared__ double sMean[D];
     setup_factor<D>(a, sF, sMean);
-    double Fr[D <= 4 ? D * D : 1];
-    if (D <= 4) {
-#pragma unroll
-        for (int q = 0; q < D * D; ++q) Fr[D <= 4 ? q : 0] = sF[q];
-    }
     const long long slot_begin = a.plan ? (long long)a.plan[OBE_PL_SLOT0] : a.slot_begin;
     long long n_out = a.plan ? (long long)a.plan[OBE_PL_SLOT1] - slot_begin : a.slot_end - a.slot_begin;
     if (a.plan && n_out > a.cap_out) n_out = a.cap_out;
-    const long long n_groups = (n_out + V - 1) / V;
+    // groups of 4 consecutive GLOBAL slots starting at a multiple of 4 (the packed normal stream); the first group
+    // of a shard whose slot_begin is not a multiple of 4 is partial
+    const int sh = (int)(slot_begin & 3);
+    const long long n_groups = (n_out + sh + V - 1) / V;
     for (long long g = (long long)blockIdx.x * OBE_THREADS + threadIdx.x; g < n_groups;
          g += (long long)gridDim.x * OBE_THREADS) {
-        const long long o0 = g * V;
-        const bool full = o0 + V <= n_out;
+        const long long o0 = g * V - sh;                         // position of the group in this shard's output
+        const bool full = o0 >= 0 && o0 + V <= n_out;
         unsigned int anc[V];
-        if (full) {
-            if (V == 2) {
-                const uint2 t = *reinterpret_cast<const uint2*>(a.anc + o0);
-                anc[0] = t.x; anc[V > 1 ? 1 : 0] = t.y;
-            } else if (V == 4) {
-                const uint4 t = *reinterpret_cast<const uint4*>(a.anc + o0);
-                anc[0] = t.x; anc[V > 1 ? 1 : 0] = t.y; anc[V > 2 ? 2 : 0] = t.z; anc[V > 3 ? 3 : 0] = t.w;
-            } else {
-#pragma unroll
-                for (int u = 0; u < V; ++u) anc[u] = a.anc[o0 + u];
-            }
+        if (full && sh == 0) {
+            const uint4 t = *reinterpret_cast<const uint4*>(a.anc + o0);
+            anc[0] = t.x; anc[1] = t.y; anc[2] = t.z; anc[3] = t.w;
         } else {
+            bool any = false;
+            long long ofirst = 0;
 #pragma unroll
-            for (int u = 0; u < V; ++u) anc[u] = (o0 + u < n_out) ? a.anc[o0 + u] : a.anc[o0];
+            for (int u = V - 1; u >= 0; --u)
+                if (o0 + u >= 0 && o0 + u < n_out) { any = true; ofirst = o0 + u; }
+            if (!any) continue;
+#pragma unroll
+            for (int u = 0; u < V; ++u) anc[u] = (o0 + u >= 0 && o0 + u < n_out) ? a.anc[o0 + u] : a.anc[ofirst];
         }
-        double xv[V][D], z[V][D];
-        long long og[V];
+        double xv[V][D];
+        bool ok[V];
 #pragma unroll
         for (int u = 0; u < V; ++u) {
-            og[u] = slot_begin + o0 + u;
+            ok[u] = o0 + u >= 0 && o0 + u < n_out;
 #pragma unroll
             for (int j = 0; j < D; ++j) xv[u][j] = __ldg(a.pin + j * a.ld_in + anc[u]);
         }
-        if (a.jitter) {
-            device_normals_vec<D, V>(og, a.seed, a.epoch, z);
-#pragma unroll
-            for (int u = 0; u < V; ++u) {
-                if (a.z_out && o0 + u < n_out) {
-#pragma unroll
-                    for (int j = 0; j < D; ++j) a.z_out[(o0 + u) * D + j] = z[u][j];
-                }
-                if (D <= 4) liu_west<D>(xv[u], z[u], Fr, sMean, a.a_param, a.scale);
-                else liu_west<D>(xv[u], z[u], sF, sMean, a.a_param, a.scale);
-            }
-        }
-        if (full && (V == 2 || V == 4)) {
+        if (a.jitter)
+            jitter_group4<D>(xv, slot_begin + o0, a.seed, a.epoch, sF, sMean, a.a_param, a.scale, a.z_out, o0, ok);
+        if (full && (sh & 1) == 0) {
 #pragma unroll
             for (int j = 0; j < D; ++j) {
 #pragma unroll
                 for (int u = 0; u < V; u += 2)
-                    *reinterpret_cast<double2*>(a.pout + j * a.ld_out + o0 + u) = make_double2(xv[u][j], xv[u + 1 < V ? u + 1 : u][j]);
+                    *reinterpret_cast<double2*>(a.pout + j * a.ld_out + o0 + u) = make_double2(xv[u][j], xv[u + 1][j]);
             }
         } else {
 #pragma unroll
             for (int u = 0; u < V; ++u) {
-                if (o0 + u < n_out) {
+                if (o0 + u >= 0 && o0 + u < n_out) {
 #pragma unroll
                     for (int j = 0; j < D; ++j) a.pout[j * a.ld_out + o0 + u] = xv[u][j];
                 }
@@ -1251,7 +1348,7 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_MOVE_BLOCKS(D)) k_sys_move(co
         if (a.idx_out) {
 #pragma unroll
             for (int u = 0; u < V; ++u)
-                if (o0 + u < n_out) a.idx_out[o0 + u] = (long long)anc[u];
+                if (o0 + u >= 0 && o0 + u < n_out) a.idx_out[o0 + u] = (long long)anc[u];
         }
     }
 }
@@ -1276,11 +1373,23 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_MOVE_BLOCKS(D)) k_sys_move(co
 // Same arithmetic as sys_unit_ancestors + k_sys_move, so the ancestors and the offspring are bit-identical to
 // the two-kernel path's.  Algorithmic traffic 8N(2d+1) instead of 8N(2d+2).
 #define OBE_WR_GROUP 128
-#define OBE_WR_MARKS (OBE_OUT_CHUNK + OBE_WR_GROUP)      /* shifted chunk coordinates: A + n_chunk <= 4099 */
+#define OBE_WR_MARKS (OBE_WR_CHUNK + OBE_WR_GROUP)       /* shifted chunk coordinates: A + n_chunk <= 3203 */
 #define OBE_WR_SMEM ((OBE_THREADS / 32) * OBE_WR_MARKS * 2)
-#ifndef OBE_WR_BLOCKS
-#define OBE_WR_BLOCKS(d) ((d) <= 4 ? 3 : 2)              /* resident CTAs per SM: 66 KB of marks each; registers */
+#ifndef OBE_WR_MINB
+#define OBE_WR_MINB 3     /* measured: 3 CTAs x 80 registers beat 4 x 64 (spills) -- 1.08 vs 1.38 ms at 1e8 x 3 */
 #endif
+#ifndef OBE_WR_BLOCKS
+/* resident CTAs per SM: 52 KB of marks each (4 would fit in the 227 KB of an SM); the registers decide */
+#define OBE_WR_BLOCKS(d) ((d) <= 3 ? OBE_WR_MINB : ((d) == 4 ? 3 : 2))
+#endif
+#ifndef OBE_WR_SPLIT
+#define OBE_WR_SPLIT 1      /* 1: the mark scan is its own pass (B1), the emission loop (B2) has no shuffles */
+#endif
+#ifndef OBE_WR_PREFETCH
+#define OBE_WR_PREFETCH 1   /* B2 prefetches the next group's ancestor lines into L2 while this group is computed */
+#endif
+
+struct WrUnit { long long og_al, o_al, base; int q_emit_end, A, lastrel, pad; };
 
 __device__ __forceinline__ void wr_load_segment(const double* __restrict__ wt, int i0, int cnt_tile, double wuni,
                                                 double (&v)[OBE_EPT]) {
@@ -1306,6 +1415,7 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
     __shared__ double sF[D * D];
     __shared__ double sMean[D];
     __shared__ SysCtx cs;
+    __shared__ WrUnit wu[NWARP];
     __shared__ int s_units;
     __shared__ long long s_tiles_in;
     if (threadIdx.x == 0) {
@@ -1354,11 +1464,12 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
             k = lo - 1;
         }
         const long long Hk = a.plan_h[k], Hk1 = a.plan_h[k + 1];
-        const int rel_begin = (unit - a.unit_start[k]) * OBE_OUT_CHUNK;
-        const int n_chunk = min(rel_begin + OBE_OUT_CHUNK, (int)(Hk1 - Hk)) - rel_begin;
+        const int rel_begin = (unit - a.unit_start[k]) * OBE_WR_CHUNK;
+        const int n_chunk = min(rel_begin + OBE_WR_CHUNK, (int)(Hk1 - Hk)) - rel_begin;
         const long long chunk0 = Hk + rel_begin;                      // global slot of the chunk's first output
         const long long o_base = chunk0 - c.slot_begin;               // its position in this shard's output
-        const int A = (int)(o_base & 3);                              // shifted chunk coordinate q' = q + A
+        const int A = (int)(chunk0 & 3);                              // shifted chunk coordinate q' = q + A: groups of
+                                                                      // 4 slots start at multiples of 4 GLOBAL slots
         const int q_end = A + n_chunk;
         const long long base = (long long)k * OBE_TILE;
         const int cnt_tile = (int)(min(c.n_in, base + OBE_TILE) - base);
@@ -1461,15 +1572,56 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
         }
         __syncwarp();
         // ---------------------------------------------------------------- phase B: emission
+        // The per-unit scalars live in the warp's slot of `wu` (shared memory) and are re-read where they are used:
+        // held in registers across the emission loop they pushed it over the 80-register budget of 3 CTAs per SM and
+        // the spilled ones (local memory, long scoreboard) were the top stall of the loop.
         {
             const long long room = c.cap_out - o_base;                // capacity overflow is flagged in the plan
             const int n_emit = room < (long long)n_chunk ? (room > 0 ? (int)room : 0) : n_chunk;
-            const int q_emit_end = A + n_emit;
-            const long long o_al = o_base - A;                        // output position of q' = 0 (multiple of 4)
-            const long long og_al = chunk0 - A;                       // global slot of q' = 0
+            if (lane == 0) {
+                WrUnit& w = wu[warp];
+                w.og_al = chunk0 - A;                                 // global slot of q' = 0 (multiple of 4)
+                w.o_al = chunk0 - A - c.slot_begin;                   // its position in this shard's output
+                w.base = base;
+                w.q_emit_end = A + n_emit; w.A = A; w.lastrel = lastrel;
+            }
+            __syncwarp();
+            const volatile WrUnit& vu = wu[warp];
+            const volatile SysCtx& vc = cs;
+            const bool vec_ok = (c.slot_begin & 1) == 0;              // 16-byte aligned stores (launch-uniform)
             const double* __restrict__ pin = c.pin + base;
             const long long ld_in = c.ld_in, ld_out = c.ld_out;
+#if OBE_WR_SPLIT
+            // B1: marks -> ancestors (index + 1) in place: max-scan over the chunk, the carry in a register
+            {
+                int last_anc = 0;
+#pragma unroll 1
+                for (int g0 = 0; g0 < q_end; g0 += OBE_WR_GROUP) {
+                    unsigned int* rp = reinterpret_cast<unsigned int*>(marks + g0 + lane * 4);
+                    const uint2 raw = *reinterpret_cast<const uint2*>(rp);
+                    int m0 = (int)(raw.x & 0xffffu);
+                    int m1 = max(m0, (int)(raw.x >> 16));
+                    int m2 = max(m1, (int)(raw.y & 0xffffu));
+                    int m3 = max(m2, (int)(raw.y >> 16));
+                    int xs = m3;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int y = __shfl_up_sync(0xffffffffu, xs, o);
+                        if (lane >= o) xs = max(xs, y);
+                    }
+                    int exs = __shfl_up_sync(0xffffffffu, xs, 1);
+                    if (lane == 0) exs = 0;
+                    exs = max(exs, last_anc);
+                    last_anc = max(last_anc, __shfl_sync(0xffffffffu, xs, 31));
+                    m0 = max(m0, exs); m1 = max(m1, exs); m2 = max(m2, exs); m3 = max(m3, exs);
+                    *reinterpret_cast<uint2*>(rp) = make_uint2((unsigned int)m0 | ((unsigned int)m1 << 16),
+                                                               (unsigned int)m2 | ((unsigned int)m3 << 16));
+                }
+            }
+            // (every lane reads back only the four entries it wrote: no warp barrier needed)
+#else
             int last_anc = 0;                 // mark of the owner of the last slot of the previous group
+#endif
             // FULL: every slot of the group is a live output of this unit (warp-uniform): no per-slot predicates
             auto emit = [&](auto full_tag, const int emit_pos) {
                 constexpr bool FULL = decltype(full_tag)::value;
@@ -1478,6 +1630,18 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
                 const uint2 raw = *reinterpret_cast<const uint2*>(rp);
                 *reinterpret_cast<uint2*>(rp) = make_uint2(0u, 0u);
                 int m[4];
+#if OBE_WR_SPLIT
+                m[0] = (int)(raw.x & 0xffffu); m[1] = (int)(raw.x >> 16);
+                m[2] = (int)(raw.y & 0xffffu); m[3] = (int)(raw.y >> 16);
+#if OBE_WR_PREFETCH
+                if (emit_pos + OBE_WR_GROUP < q_end) {               // the next group's first ancestor of this lane:
+                    const int nxt = (int)marks[q0 + OBE_WR_GROUP];   // its lines will be in L2 when the loads come
+                    const double* pf = pin + max(nxt - 1, 0);
+#pragma unroll
+                    for (int j = 0; j < D; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + j * ld_in));
+                }
+#endif
+#else
                 m[0] = (int)(raw.x & 0xffffu);
                 m[1] = max(m[0], (int)(raw.x >> 16));
                 m[2] = max(m[1], (int)(raw.y & 0xffffu));
@@ -1492,20 +1656,21 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
                 if (lane == 0) exs = 0;
                 exs = max(exs, last_anc);
                 last_anc = max(last_anc, __shfl_sync(0xffffffffu, xs, 31));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) m[u] = max(m[u], exs);
+#endif
                 bool ok[4];
                 int rel[4];
-                long long og[4];
-                double xv[4][D], z[4][D];
+                double xv[4][D];
                 bool any = false, all = true;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int qq = q0 + u;
-                    ok[u] = FULL || (qq >= A && qq < q_emit_end);
+                    ok[u] = FULL || (qq >= vu.A && qq < vu.q_emit_end);
                     any |= ok[u];
                     all &= ok[u];
                     // (marks are indices of live particles + 1: no clamp to the tile's last live particle needed)
-                    rel[u] = FULL ? max(m[u], exs) - 1 : min(max(max(m[u], exs) - 1, 0), lastrel);
-                    og[u] = og_al + (long long)qq;
+                    rel[u] = FULL ? m[u] - 1 : min(max(m[u] - 1, 0), vu.lastrel);
                 }
                 if (!FULL && !any) return;
 #pragma unroll
@@ -1513,47 +1678,43 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
 #pragma unroll
                     for (int j = 0; j < D; ++j) xv[u][j] = __ldg(pin + j * ld_in + rel[u]);
                 }
-                const long long o0 = o_al + q0;
-                if (c.jitter) {
-                    device_normals_vec<D, 4>(og, c.seed, c.epoch, z);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (c.z_out && ok[u]) {
-#pragma unroll
-                            for (int j = 0; j < D; ++j) c.z_out[(o0 + u) * D + j] = z[u][j];
-                        }
-                        liu_west<D>(xv[u], z[u], sF, sMean, c.a_param, c.scale);
-                    }
-                }
-                if (FULL || all) {
+                if (vc.jitter)
+                    jitter_group4<D>(xv, vu.og_al + q0, vc.seed, vc.epoch, sF, sMean, vc.a_param, vc.scale, vc.z_out,
+                                     vu.o_al + q0, ok);
+                const long long o0 = vu.o_al + q0;
+                double* __restrict__ pout = vc.pout;
+                double* __restrict__ w_out = vc.w_out;
+                if ((FULL || all) && vec_ok) {
 #pragma unroll
                     for (int j = 0; j < D; ++j) {
-                        double* dst = c.pout + j * ld_out + o0;
+                        double* dst = pout + j * ld_out + o0;
                         *reinterpret_cast<double2*>(dst) = make_double2(xv[0][j], xv[1][j]);
                         *reinterpret_cast<double2*>(dst + 2) = make_double2(xv[2][j], xv[3][j]);
                     }
-                    if (c.w_out) {
-                        *reinterpret_cast<double2*>(c.w_out + o0) = make_double2(c.wv, c.wv);
-                        *reinterpret_cast<double2*>(c.w_out + o0 + 2) = make_double2(c.wv, c.wv);
+                    if (w_out) {
+                        const double wv = vc.wv;
+                        *reinterpret_cast<double2*>(w_out + o0) = make_double2(wv, wv);
+                        *reinterpret_cast<double2*>(w_out + o0 + 2) = make_double2(wv, wv);
                     }
                 } else {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         if (!ok[u]) continue;
 #pragma unroll
-                        for (int j = 0; j < D; ++j) c.pout[j * ld_out + o0 + u] = xv[u][j];
-                        if (c.w_out) c.w_out[o0 + u] = c.wv;
+                        for (int j = 0; j < D; ++j) pout[j * ld_out + o0 + u] = xv[u][j];
+                        if (w_out) w_out[o0 + u] = vc.wv;
                     }
                 }
-                if (c.idx_out) {
+                long long* idx_out = vc.idx_out;
+                if (idx_out) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (ok[u]) c.idx_out[o0 + u] = base + rel[u];
+                        if (ok[u]) idx_out[o0 + u] = vu.base + rel[u];
                 }
             };
 #pragma unroll 1
             for (int emit_pos = 0; emit_pos < q_end; emit_pos += OBE_WR_GROUP) {
-                if (emit_pos >= A && emit_pos + OBE_WR_GROUP <= q_emit_end) emit(std::true_type{}, emit_pos);
+                if (emit_pos >= vu.A && emit_pos + OBE_WR_GROUP <= vu.q_emit_end) emit(std::true_type{}, emit_pos);
                 else emit(std::false_type{}, emit_pos);
             }
         }
@@ -2108,6 +2269,7 @@ int obe_set_option(const char* name, int64_t value) {
     const std::string s(name);
     if (s == "plan_cluster_min_tiles") { g_plan_cluster_min_tiles = value < 0 ? 0 : value; return 0; }
     if (s == "utility_lane_fill") { g_utility_lane_fill = value < 0 ? 0 : value; return 0; }
+    if (s == "utility_cache") { g_utility_cache = value ? 1 : 0; return 0; }
     if (s == "resample_fused") { g_resample_fused = value ? 1 : 0; return 0; }
     if (s == "resample_blocks") { g_resample_blocks = value < 0 ? 0 : value; return 0; }
     return obe_fail("unknown option '%s'%s", name);
@@ -2517,15 +2679,16 @@ int obe_gather_jitter(const obe_cloud_t* in, const obe_cloud_t* out, const int64
 }
 
 // the unit -> tile map lives in the input cloud's scratch, which is sized for in->n particles
+static int plan_chunk() { return g_resample_fused ? OBE_WR_CHUNK : OBE_OUT_CHUNK; }
 static bool unit_map_fits(const obe_cloud_t* in, int64_t out_cap) {
     const int64_t nt = (in->n + OBE_TILE - 1) / OBE_TILE;
-    return nt + (out_cap + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK <= nt + in->n / OBE_OUT_CHUNK_HOST + 4;
+    return nt + (out_cap + plan_chunk() - 1) / plan_chunk() <= nt + in->n / OBE_WR_CHUNK + 4;
 }
 
 // k_sys_ancestors + k_sys_move, after k_sys_plan
 static int launch_sys_resample(const obe_cloud_t* in, const obe_cloud_t* out, ObeResampleArgs& a, int64_t out_cap,
                                cudaStream_t st) {
-    const int64_t max_units = a.n_tiles + (out_cap + OBE_OUT_CHUNK - 1) / OBE_OUT_CHUNK;
+    const int64_t max_units = a.n_tiles + (out_cap + plan_chunk() - 1) / plan_chunk();
     if (in->n >= (1ll << 32)) return obe_fail("systematic resample supports shards of < 2^32 particles%s%s");
     a.anc = scratch_of(out).anc;
     a.out_tile_sums = out->tile_sums_dev; a.out_prefix = out->tile_prefix_dev; a.out_stats = out->stats_dev;
@@ -2549,7 +2712,7 @@ static int launch_sys_resample(const obe_cloud_t* in, const obe_cloud_t* out, Ob
         OBE_LAUNCH_CHECK("k_sys_ancestors");
     }
     {
-        int64_t g = (out_cap + (int64_t)OBE_THREADS * OBE_MOVE_V - 1) / ((int64_t)OBE_THREADS * OBE_MOVE_V);
+        int64_t g = (out_cap + 3 + (int64_t)OBE_THREADS * OBE_MOVE_V - 1) / ((int64_t)OBE_THREADS * OBE_MOVE_V);
         const int64_t gmax = (int64_t)obe_sms() * OBE_MOVE_BLOCKS(in->d) * 4;
         if (g > gmax) g = gmax;
         if (g < 1) g = 1;
@@ -2581,11 +2744,12 @@ static int resample_systematic_impl(const obe_cloud_t* in, const obe_cloud_t* ou
     if (a.n_tiles > g_plan_cluster_min_tiles)
         k_sys_plan_cluster<<<OBE_PLAN_CLUSTER, OBE_SCAN_THREADS, 0, st>>>(
             in->tile_prefix_dev, a.n_tiles, n_total, u0, sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0,
-            slot_begin, slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr);
+            slot_begin, slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr, plan_chunk());
     else
         k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, u0,
                                                   sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0, slot_begin,
-                                                  slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr);
+                                                  slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr,
+                                                  plan_chunk());
     OBE_LAUNCH_CHECK("k_sys_plan");
     return launch_sys_resample(in, out, a, out->n, st);
 }
@@ -2717,11 +2881,11 @@ int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* ou
     if (a.n_tiles > g_plan_cluster_min_tiles)
         k_sys_plan_cluster<<<OBE_PLAN_CLUSTER, OBE_SCAN_THREADS, 0, st>>>(
             in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0, s.plan_h, s.unit_start, (int*)a.unit_tile,
-            (const long long*)in->n_dev, plan_dev);
+            (const long long*)in->n_dev, plan_dev, plan_chunk());
     else
         k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0,
                                                   s.plan_h, s.unit_start, (int*)a.unit_tile,
-                                                  (const long long*)in->n_dev, plan_dev);
+                                                  (const long long*)in->n_dev, plan_dev, plan_chunk());
     OBE_LAUNCH_CHECK("k_sys_plan");
     return launch_sys_resample(in, out, a, out->ld, st);
 }
@@ -2792,6 +2956,16 @@ int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* set
     const int64_t per_block = OBE_THREADS / a.lanes;
     int64_t blocks = (n_settings + per_block - 1) / per_block;
     if (blocks > (int64_t)obe_sms() * 8) blocks = (int64_t)obe_sms() * 8;
+    if (a.lanes == 1 && method == 0 && g_utility_cache) {
+        // one thread per setting: park the K x NCH model values in shared memory between the two variance passes
+        const size_t with_cache = smem + (size_t)k * m->nch * OBE_THREADS * sizeof(double);
+        if (with_cache <= 100 * 1024) {
+            if (with_cache > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(m->f_utility, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_cache);
+                if (e != cudaSuccess) { (void)cudaGetLastError(); } else { a.cache = 1; smem = with_cache; }
+            } else { a.cache = 1; smem = with_cache; }
+        }
+    }
     return launch_kernel(m->f_utility, (int)blocks, smem, (cudaStream_t)stream, &a);
 }
 

@@ -128,6 +128,8 @@ struct ObeUtilityArgs {
     int log_form;
     int method;              // 0 variance, 1 max-min, 2 pseudo (entropy), 3 full KLD
     int lanes;               // variance utility: lanes per setting (1: one thread walks all K draws)
+    int cache;               // lanes == 1: the K x NCH model values of a thread's setting are kept in shared memory
+                             // between the two passes of the variance (1) instead of being evaluated twice (0)
     const double* kld_noise; // method 3: (K, C) noise values added to the model outputs
     double var_noise[OBE_MAX_CH];
     double cons[OBE_MAX_CONS];
@@ -1425,15 +1427,28 @@ __device__ void obe_utility_body(const ObeUtilityArgs& a) {
             double mean[Model::NCH], ss[Model::NCH];
 #pragma unroll
             for (int c = 0; c < Model::NCH; ++c) { mean[c] = 0.0; ss[c] = 0.0; }
+            // numpy's two-pass variance needs every model value twice.  With `cache` the thread parks its K x NCH
+            // values in shared memory (column tid of a [K*NCH][blockDim] array: conflict-free) and the second pass
+            // reads them back -- the same values in the same order, half the model evaluations (this kernel is
+            // FP64-issue-bound on large grids).
+            double* ycol = sdraw + K * Model::NP + tid;
             for (int k = 0; k < K; ++k) {
                 Model::eval(st, sdraw + k * Model::NP, a.cons, y);
 #pragma unroll
-                for (int c = 0; c < Model::NCH; ++c) mean[c] = obe_add(mean[c], y[c]);
+                for (int c = 0; c < Model::NCH; ++c) {
+                    mean[c] = obe_add(mean[c], y[c]);
+                    if (a.cache) ycol[(k * Model::NCH + c) * blockDim.x] = y[c];
+                }
             }
 #pragma unroll
             for (int c = 0; c < Model::NCH; ++c) mean[c] = obe_div(mean[c], kd);
             for (int k = 0; k < K; ++k) {
-                Model::eval(st, sdraw + k * Model::NP, a.cons, y);
+                if (a.cache) {
+#pragma unroll
+                    for (int c = 0; c < Model::NCH; ++c) y[c] = ycol[(k * Model::NCH + c) * blockDim.x];
+                } else {
+                    Model::eval(st, sdraw + k * Model::NP, a.cons, y);
+                }
 #pragma unroll
                 for (int c = 0; c < Model::NCH; ++c) {
                     const double dlt = obe_sub(y[c], mean[c]);

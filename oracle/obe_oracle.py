@@ -479,6 +479,25 @@ def device_normals(n, d, seed, epoch):
     return z
 
 
+def device_normals_packed(n, d, seed, epoch, slot_begin=0):
+    """(n, d) standard normals of output slots slot_begin .. slot_begin+n-1 as the STREAMING resample kernels draw
+    them (csrc/obe_b200.cu packed_normals4): the jitter normals of the whole cloud are one sequence, normal
+    m = d*slot + j, four per Philox call: ctr = (q_lo, q_hi, 0x80000000 | d, epoch) with q = m >> 2, word m & 3;
+    words (0,1) and (2,3) are two float32 Box-Muller pairs (cos, sin).  Same accuracy caveat as device_normals."""
+    m = np.arange(n * d, dtype=np.uint64) + np.uint64(d) * np.uint64(slot_begin)
+    q = m >> np.uint64(2)
+    uq, inv = np.unique(q, return_inverse=True)
+    x = philox4x32_10((uq & np.uint64(0xFFFFFFFF)).astype(np.uint32), (uq >> np.uint64(32)).astype(np.uint32),
+                      np.uint32(0x80000000 | d), np.uint32(epoch), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    four = np.empty((len(uq), 4))
+    for h in range(2):
+        rad = np.sqrt(np.float32(-2.0) * np.log(_u24(x[2 * h])))
+        ang = np.float32(2.0) * _u24(x[2 * h + 1]).astype(np.float64) * np.pi
+        four[:, 2 * h] = (rad * np.cos(ang).astype(np.float32)).astype(np.float64)
+        four[:, 2 * h + 1] = (rad * np.sin(ang).astype(np.float32)).astype(np.float64)
+    return four[inv, (m & np.uint64(3)).astype(np.int64)].reshape(n, d)
+
+
 # ----------------------------------------------------------------------------
 # A whole engine, consuming a numpy Generator in the reference's order.
 # Used for closed-loop parity and as bench.py's CPU baseline ("port").

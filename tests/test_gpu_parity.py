@@ -483,7 +483,7 @@ def _systematic_case(obe, torch, n, d, scale):
     # the normals: the restated Philox + float32 Box-Muller stream, to float32 accuracy; the
     # Liu-West arithmetic downstream is then checked exactly, GIVEN the normals the kernel used
     z = zout.cpu().numpy()
-    assert_allclose(z, orc.device_normals(n, d, seed, epoch), rtol=0, atol=1e-4)
+    assert_allclose(z, orc.device_normals_packed(n, d, seed, epoch), rtol=0, atol=1e-4)
     if n * d >= 1000:
         assert abs(z.mean()) < 5 / np.sqrt(n * d) and abs(z.std() - 1) < 5 / np.sqrt(n * d)
     if n < 3:

@@ -128,6 +128,19 @@ def test_device_normals_are_standard_normal():
     assert abs(np.corrcoef(z.T)[0, 1]) < 0.01
 
 
+def test_packed_device_normals():
+    """The packed stream of the streaming resample kernels: standard normal, independent of how the slots are cut
+    into ranges (sharding invariance), and every Philox word used exactly once."""
+    z = orc.device_normals_packed(200000, 3, 12345, 1)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    assert abs(np.corrcoef(z.T)[0, 1]) < 0.01 and abs(np.corrcoef(z[:-1, 2], z[1:, 0])[0, 1]) < 0.01
+    for d in (1, 2, 3, 5, 8):
+        whole = orc.device_normals_packed(1000, d, 99, 4)
+        assert_array_equal(whole[337:911], orc.device_normals_packed(911 - 337, d, 99, 4, slot_begin=337))
+        assert len(np.unique(whole)) >= whole.size - 4          # (23-bit uniforms: a chance collision is possible)
+    assert not np.array_equal(orc.device_normals_packed(64, 3, 99, 4), orc.device_normals_packed(64, 3, 99, 5))
+
+
 def test_mvn_factors_reproduce_covariance():
     cov = np.array([[2.0, 0.3, 0.1], [0.3, 1.0, -0.2], [0.1, -0.2, 0.5]])
     for f in (orc.mvn_factor_svd(cov), orc.mvn_factor_cholesky(cov)):
