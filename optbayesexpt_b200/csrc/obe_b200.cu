@@ -68,12 +68,14 @@ struct Scratch {
     long long* plan_h;       // n_tiles + 1
     int* unit_start;         // n_tiles + 2
     unsigned int* anc;       // n + 4 (ancestors of the offspring written INTO this cloud)
-    int* unit_tile;          // n_tiles + n / OBE_WR_CHUNK + 4 (work unit -> input tile)
+    int* unit_tile;          // n_tiles + n / OBE_WR_MIN_CHUNK + 4 (work unit -> input tile)
 };
 #define OBE_OUT_CHUNK_HOST 4096
 #ifndef OBE_WR_CHUNK
-#define OBE_WR_CHUNK 3200   /* output slots per work unit of the one-kernel resample (k_sys_resample_warp) */
+#define OBE_WR_CHUNK 3200   /* most output slots per work unit of the one-kernel resample (k_sys_resample_warp) */
 #endif
+#define OBE_WR_GROUP_HOST 128
+#define OBE_WR_MIN_CHUNK 128  /* small clouds get smaller units so that every SM has warps to run */
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static size_t scratch_bytes(int64_t n) {
     const int64_t nt = (n + OBE_TILE - 1) / OBE_TILE;
@@ -82,7 +84,7 @@ static size_t scratch_bytes(int64_t n) {
     b += align_up((size_t)(nt + 1) * sizeof(long long), 256);
     b += align_up((size_t)(nt + 2) * sizeof(int), 256);
     b += align_up((size_t)(n + 4) * sizeof(unsigned int), 256);
-    b += align_up((size_t)(nt + n / OBE_WR_CHUNK + 4) * sizeof(int), 256);
+    b += align_up((size_t)(nt + n / OBE_WR_MIN_CHUNK + 4) * sizeof(int), 256);
     return b;
 }
 static Scratch scratch_of(const obe_cloud_t* c) {
@@ -272,6 +274,30 @@ __device__ __forceinline__ long long find_tile(const double* __restrict__ prefix
     return min(lo, n_tiles - 1);
 }
 
+// The same search by a whole block: every round the blockDim.x threads probe evenly spaced tiles and a block-wide
+// count narrows the range by a factor blockDim.x -- 2 rounds (two dependent loads) for 65 536 tiles where the
+// sequential search walks 16.  All threads must call it (block barriers inside); same answer in every thread.
+__device__ __forceinline__ long long find_tile_block(const double* __restrict__ prefix, long long n_tiles,
+                                                     double inv_total, double u) {
+    long long lo = 0, hi = n_tiles;  // first k in [lo, hi) whose end-of-tile CDF value is > u, else hi
+    while (lo < hi) {
+        const long long span = hi - lo;
+        const long long step = (span + blockDim.x - 1) / blockDim.x;
+        const long long k = lo + (long long)threadIdx.x * step;
+        bool le = false;
+        if (k < hi) {
+            const double c = (k == n_tiles - 1) ? 1.0 : obe_mul(prefix[k + 1], inv_total);
+            le = c <= u;
+        }
+        const long long cnt = __syncthreads_count(le);           // the probes with c <= u are a prefix (monotone CDF)
+        if (cnt == 0) { hi = lo; break; }
+        const long long next = lo + cnt * step;                  // first probe with c > u (if it exists)
+        lo = lo + (cnt - 1) * step + 1;
+        hi = next < hi ? next : hi;
+    }
+    return min(lo, n_tiles - 1);
+}
+
 __global__ void k_search(const double* __restrict__ cdf, const double* __restrict__ prefix, long long n,
                          long long n_tiles, const double* __restrict__ u, long long m,
                          long long* __restrict__ idx) {
@@ -378,7 +404,7 @@ __global__ void __launch_bounds__(OBE_THREADS) k_draw(const ObeDrawArgs a) {
     }
     if (mine) {                                    // (uniform over the block)
         const double inv_total = 1.0 / a.prefix[n_tiles];
-        const long long k = find_tile(a.prefix, n_tiles, inv_total, uq);
+        const long long k = find_tile_block(a.prefix, n_tiles, inv_total, uq);
         double cn[OBE_EPT];
         tile_cdf_blocked(a.w, a.prefix, k, n, inv_total, cn, sm, 0.0, true, a.stats ? a.stats[OBE_ST_UNIFORM] : 0.0);
         const long long base = k * OBE_TILE;
@@ -436,97 +462,13 @@ __global__ void k_peer_collect_draws(double* mine, int world, unsigned long long
     for (int q = threadIdx.x; q < n_values; q += blockDim.x) draws[q] = mine[OBE_PEER_DRAWS + parity * 1024 + q];
 }
 
-// U output slots at once: the Philox rounds of the U counters interleave (one basic block), which hides
-// the integer-multiply latency that a slot-at-a-time loop exposes.
-template <int D, int U>
-__device__ __forceinline__ void device_normals_vec(const long long (&slot)[U], unsigned long long seed,
-                                                   unsigned int epoch, double (&z)[U][D]) {
-    const unsigned int key0 = (unsigned int)(seed & 0xffffffffull), key1 = (unsigned int)(seed >> 32);
-#pragma unroll
-    for (int c = 0; c < (D + 3) / 4; ++c) {
-        unsigned int c0[U], c1[U], c2[U], c3[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            c0[u] = (unsigned int)(slot[u] & 0xffffffffll);
-            c1[u] = (unsigned int)((unsigned long long)slot[u] >> 32);
-            c2[u] = (unsigned int)c; c3[u] = epoch;
-        }
-        unsigned int k0 = key0, k1 = key1;
-#pragma unroll
-        for (int r = 0; r < 10; ++r) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const unsigned int hi0 = __umulhi(0xD2511F53u, c0[u]), lo0 = 0xD2511F53u * c0[u];
-                const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2[u]), lo1 = 0xCD9E8D57u * c2[u];
-                const unsigned int n0 = hi1 ^ c1[u] ^ k0, n2 = hi0 ^ c3[u] ^ k1;
-                c0[u] = n0; c1[u] = lo1; c2[u] = n2; c3[u] = lo0;
-            }
-            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const unsigned int r4[4] = {c0[u], c1[u], c2[u], c3[u]};
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (4 * c + 2 * h < D) {
-                    const float rad = obe_sqrt_approx(-2.0f * __logf(u24(r4[2 * h])));
-                    float sn, cs;
-                    __sincosf(6.2831853071795865f * u24(r4[2 * h + 1]), &sn, &cs);
-                    z[u][4 * c + 2 * h] = (double)(rad * cs);
-                    if (4 * c + 2 * h + 1 < D) z[u][4 * c + 2 * h + 1] = (double)(rad * sn);
-                }
-            }
-        }
-    }
-}
-
 // Packed normal stream of the streaming resample kernels (k_sys_resample_warp, k_sys_move): the jitter normals of
 // the whole cloud form ONE sequence, normal m = D * slot + j, four per Philox call (two Box-Muller pairs): call
 // q = m >> 2, word m & 3.  A thread that owns 4 consecutive output slots starting at a multiple of 4 needs exactly
 // the calls (slot0 / 4) * D ... + D - 1: D calls per 4 slots whatever D, none of the 128 bits wasted (the per-slot
 // stream of device_normals spends 4 * ceil(D / 4) calls).  ctr = (q_lo, q_hi, 0x80000000 | D, epoch), key = seed.
 // Slots are GLOBAL comb slots, so the jitter does not depend on how the cloud is sharded.  Restated in
-// oracle/obe_oracle.py:device_normals_packed.
-template <int D>
-__device__ __forceinline__ void packed_normals4(long long slot0, unsigned long long seed, unsigned int epoch,
-                                                double (&z)[4][D]) {
-    const unsigned int key0 = (unsigned int)(seed & 0xffffffffull), key1 = (unsigned int)(seed >> 32);
-    const unsigned long long q0 = (unsigned long long)(slot0 >> 2) * (unsigned long long)D;
-    unsigned int c0[D], c1[D], c2[D], c3[D];
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-        const unsigned long long q = q0 + (unsigned long long)c;
-        c0[c] = (unsigned int)(q & 0xffffffffull);
-        c1[c] = (unsigned int)(q >> 32);
-        c2[c] = 0x80000000u | (unsigned int)D; c3[c] = epoch;
-    }
-    unsigned int k0 = key0, k1 = key1;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-            const unsigned int hi0 = __umulhi(0xD2511F53u, c0[c]), lo0 = 0xD2511F53u * c0[c];
-            const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2[c]), lo1 = 0xCD9E8D57u * c2[c];
-            const unsigned int n0 = hi1 ^ c1[c] ^ k0, n2 = hi0 ^ c3[c] ^ k1;
-            c0[c] = n0; c1[c] = lo1; c2[c] = n2; c3[c] = lo0;
-        }
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-        const unsigned int r4[4] = {c0[c], c1[c], c2[c], c3[c]};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const float rad = obe_sqrt_approx(-2.0f * __logf(u24(r4[2 * h])));
-            float sn, cs;
-            __sincosf(6.2831853071795865f * u24(r4[2 * h + 1]), &sn, &cs);
-            const int f = 4 * c + 2 * h;                     // compile-time after unrolling
-            z[f / D][f % D] = (double)(rad * cs);
-            z[(f + 1) / D][(f + 1) % D] = (double)(rad * sn);
-        }
-    }
-}
-
+// oracle/obe_oracle.py:device_normals_packed.  Implementations: jitter_group4 (4 aligned slots), packed_normals_slot.
 // Liu-West move of one particle (particlepdf.py:296-307): x + z @ F, optional contraction
 template <int D>
 __device__ __forceinline__ void liu_west(double (&x)[D], const double (&z)[D], const double* __restrict__ F,
@@ -539,6 +481,40 @@ __device__ __forceinline__ void liu_west(double (&x)[D], const double (&z)[D], c
         double v = x[j] + nud;
         if (scale) v = obe_add(obe_mul(v, a_param), obe_mul(mean[j], obe_sub(1.0, a_param)));
         x[j] = v;
+    }
+}
+
+// The D normals of ONE output slot out of the packed stream (kernels that walk slots one at a time: the batched
+// engines' sys_unit): normals m = D*slot .. D*slot + D-1 live in calls (D*slot) >> 2 .. (D*slot + D-1) >> 2, at most
+// (D + 6) / 4 of them.  Same values as jitter_group4 uses for that slot.
+template <int D>
+__device__ __forceinline__ void packed_normals_slot(long long slot, unsigned long long seed, unsigned int epoch,
+                                                    double (&z)[D]) {
+    constexpr int NC = (D + 6) / 4;
+    const unsigned long long m0 = (unsigned long long)slot * (unsigned long long)D;
+    const unsigned long long q0 = m0 >> 2;
+    const int w0 = (int)(m0 & 3ull);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        if (4 * c >= w0 + D) break;                              // (warp-divergent only through slot & 3)
+        const unsigned long long q = q0 + (unsigned long long)c;
+        unsigned int r[4];
+        philox4x32_10((unsigned int)(q & 0xffffffffull), (unsigned int)(q >> 32), 0x80000000u | (unsigned int)D, epoch,
+                      (unsigned int)(seed & 0xffffffffull), (unsigned int)(seed >> 32), r);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float rad = obe_sqrt_approx(-2.0f * __logf(u24(r[2 * h])));
+            float sn, cs;
+            __sincosf(6.2831853071795865f * u24(r[2 * h + 1]), &sn, &cs);
+            const double zz[2] = {(double)(rad * cs), (double)(rad * sn)};
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const int k = 4 * c + 2 * h + w - w0;            // coordinate this normal belongs to
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                    if (j == k) z[j] = zz[w];
+            }
+        }
     }
 }
 
@@ -626,6 +602,7 @@ struct ObeResampleArgs {
     const double* plan;            // optional device-resident shard plan (overrides the by-value shard fields)
     long long cap_out;             // capacity of the output buffers (planned mode)
     int implicit_out;              // 1: do not write the offspring weights, leave them implicit
+    int chunk;                     // output slots per work unit the plan was made with
     unsigned int* anc;             // two-kernel path: ancestor (input index) of every output slot of this shard
     double* out_tile_sums; double* out_prefix; double* out_stats;   // CDF bookkeeping of the offspring cloud
     double factor[OBE_MAX_DIMS * OBE_MAX_DIMS];
@@ -1155,7 +1132,8 @@ __device__ __forceinline__ void sys_unit(const SysCtx& c, long long k, long long
                 xv[u][j] = STAGE ? xs[j * OBE_TILE + rel[u]] : __ldg(c.pin + j * c.ld_in + c.in_base + base + rel[u]);
         }
         if (c.jitter) {
-            device_normals_vec<D, U>(og, c.seed, c.epoch, z);
+#pragma unroll
+            for (int u = 0; u < U; ++u) packed_normals_slot<D>(og[u], c.seed, c.epoch, z[u]);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (c.z_out && act[u]) {
@@ -1464,8 +1442,8 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
             k = lo - 1;
         }
         const long long Hk = a.plan_h[k], Hk1 = a.plan_h[k + 1];
-        const int rel_begin = (unit - a.unit_start[k]) * OBE_WR_CHUNK;
-        const int n_chunk = min(rel_begin + OBE_WR_CHUNK, (int)(Hk1 - Hk)) - rel_begin;
+        const int rel_begin = (unit - a.unit_start[k]) * a.chunk;
+        const int n_chunk = min(rel_begin + a.chunk, (int)(Hk1 - Hk)) - rel_begin;
         const long long chunk0 = Hk + rel_begin;                      // global slot of the chunk's first output
         const long long o_base = chunk0 - c.slot_begin;               // its position in this shard's output
         const int A = (int)(chunk0 & 3);                              // shifted chunk coordinate q' = q + A: groups of
@@ -2679,16 +2657,28 @@ int obe_gather_jitter(const obe_cloud_t* in, const obe_cloud_t* out, const int64
 }
 
 // the unit -> tile map lives in the input cloud's scratch, which is sized for in->n particles
-static int plan_chunk() { return g_resample_fused ? OBE_WR_CHUNK : OBE_OUT_CHUNK; }
+// Output slots per work unit.  Two-kernel path: 4096 (the CTA-wide mark scan is built for it).  One-kernel path: one
+// WARP owns a unit, so a cloud of a few tiles would keep a handful of warps busy for thousands of slots each; the
+// chunk shrinks (multiples of the 128-slot emission group) until there are ~16 units per SM, at the price of one
+// more CDF walk of the tile per extra unit.
+static int plan_chunk(int64_t out_cap) {
+    if (!g_resample_fused) return OBE_OUT_CHUNK;
+    int64_t c = out_cap / ((int64_t)obe_sms() * 16);
+    c = (c + OBE_WR_GROUP_HOST - 1) / OBE_WR_GROUP_HOST * OBE_WR_GROUP_HOST;
+    if (c < OBE_WR_MIN_CHUNK) c = OBE_WR_MIN_CHUNK;
+    if (c > OBE_WR_CHUNK) c = OBE_WR_CHUNK;
+    return (int)c;
+}
 static bool unit_map_fits(const obe_cloud_t* in, int64_t out_cap) {
     const int64_t nt = (in->n + OBE_TILE - 1) / OBE_TILE;
-    return nt + (out_cap + plan_chunk() - 1) / plan_chunk() <= nt + in->n / OBE_WR_CHUNK + 4;
+    const int chunk = plan_chunk(out_cap);
+    return nt + (out_cap + chunk - 1) / chunk <= nt + in->n / OBE_WR_MIN_CHUNK + 4;
 }
 
 // k_sys_ancestors + k_sys_move, after k_sys_plan
 static int launch_sys_resample(const obe_cloud_t* in, const obe_cloud_t* out, ObeResampleArgs& a, int64_t out_cap,
                                cudaStream_t st) {
-    const int64_t max_units = a.n_tiles + (out_cap + plan_chunk() - 1) / plan_chunk();
+    const int64_t max_units = a.n_tiles + (out_cap + a.chunk - 1) / a.chunk;
     if (in->n >= (1ll << 32)) return obe_fail("systematic resample supports shards of < 2^32 particles%s%s");
     a.anc = scratch_of(out).anc;
     a.out_tile_sums = out->tile_sums_dev; a.out_prefix = out->tile_prefix_dev; a.out_stats = out->stats_dev;
@@ -2741,15 +2731,16 @@ static int resample_systematic_impl(const obe_cloud_t* in, const obe_cloud_t* ou
     a.sharded = sharded; a.last_shard = last_shard; a.n_total = n_total;
     a.slot_begin = slot_begin; a.slot_end = slot_end; a.cdf_offset = cdf_offset; a.cdf_total = cdf_total;
     cudaStream_t st = (cudaStream_t)stream;
+    a.chunk = plan_chunk(out->n);
     if (a.n_tiles > g_plan_cluster_min_tiles)
         k_sys_plan_cluster<<<OBE_PLAN_CLUSTER, OBE_SCAN_THREADS, 0, st>>>(
             in->tile_prefix_dev, a.n_tiles, n_total, u0, sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0,
-            slot_begin, slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr, plan_chunk());
+            slot_begin, slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr, a.chunk);
     else
         k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, u0,
                                                   sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0, slot_begin,
                                                   slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr,
-                                                  plan_chunk());
+                                                  a.chunk);
     OBE_LAUNCH_CHECK("k_sys_plan");
     return launch_sys_resample(in, out, a, out->n, st);
 }
@@ -2878,14 +2869,15 @@ int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* ou
     a.plan = plan_dev; a.n_dev_in = (const long long*)in->n_dev; a.cap_out = out->ld;
     a.sharded = 1; a.n_total = n_total; a.implicit_out = 1;
     cudaStream_t st = (cudaStream_t)stream;
+    a.chunk = plan_chunk(out->ld);
     if (a.n_tiles > g_plan_cluster_min_tiles)
         k_sys_plan_cluster<<<OBE_PLAN_CLUSTER, OBE_SCAN_THREADS, 0, st>>>(
             in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0, s.plan_h, s.unit_start, (int*)a.unit_tile,
-            (const long long*)in->n_dev, plan_dev, plan_chunk());
+            (const long long*)in->n_dev, plan_dev, a.chunk);
     else
         k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0,
                                                   s.plan_h, s.unit_start, (int*)a.unit_tile,
-                                                  (const long long*)in->n_dev, plan_dev, plan_chunk());
+                                                  (const long long*)in->n_dev, plan_dev, a.chunk);
     OBE_LAUNCH_CHECK("k_sys_plan");
     return launch_sys_resample(in, out, a, out->ld, st);
 }

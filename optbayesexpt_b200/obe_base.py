@@ -130,6 +130,14 @@ class OptBayesExpt(ParticlePDF):
                                            device=self._buf.device)
         self._cost_dev = None
         self._best_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self._best_host_np = self._best_host.numpy()
+        # reusable by-value argument arrays (a small-cloud cycle is host-bound: no allocations per call)
+        self._a_setting = _lib.ArgArray(_lib.MAX_SETTINGS)
+        self._a_y = _lib.ArgArray(_lib.MAX_CHANNELS)
+        self._a_sigma = _lib.ArgArray(_lib.MAX_CHANNELS)
+        self._a_pivot = _lib.ArgArray(_lib.MAX_PARAMS)
+        self._a_u = None
+        self._var_noise_cache = None
 
     # -- the reference rebinds `parameters` to `particles` in pdf_update (obe_base.py:185,395);
     #    here it is a live alias, which removes the stale-alias quirk after resample()/set_pdf()
@@ -230,15 +238,15 @@ class OptBayesExpt(ParticlePDF):
         y_meas, sigma, noise_index, n_lik = self._likelihood_spec(measurement_record)
         use_choke = 0 if self.choke is None else 1
         choke = 0.0 if self.choke is None else float(self.choke)
-        pivot = _lib.darr(self._pivot, _lib.MAX_PARAMS)
-        if y_model_data is None:
+        pivot = self._a_pivot.fill(self._pivot)
+        if y_model_data is None and getattr(self, '_prefetched', None) is not None:
             y_model_data = self._take_prefetched(onesetting)
         if y_model_data is None:
-            self._check(self._lib.obe_update(self._model, self._cs(),
-                                             _lib.darr(np.atleast_1d(onesetting), _lib.MAX_SETTINGS), self._cons_arr,
-                                             _lib.darr(y_meas, _lib.MAX_CHANNELS),
-                                             None if sigma is None else _lib.darr(sigma, _lib.MAX_CHANNELS),
-                                             _lib.iarr(noise_index), n_lik, use_choke, choke, pivot, self._stream()))
+            self._check(self._lib.obe_update(self._model, self._cs(), self._a_setting.fill(onesetting), self._cons_arr,
+                                             self._a_y.fill(y_meas),
+                                             None if sigma is None else self._a_sigma.fill(sigma),
+                                             self._noise_iarr(noise_index), n_lik, use_choke, choke, pivot,
+                                             self._stream()))
         else:
             torch = self._torch
             if isinstance(y_model_data, torch.Tensor) and y_model_data.is_cuda and y_model_data.dtype == torch.float64 \
@@ -262,6 +270,16 @@ class OptBayesExpt(ParticlePDF):
         if self.just_resampled:
             self.enforce_parameter_constraints()
         return (LazyDeviceArray(lambda: self.particles), LazyDeviceArray(lambda: self.particle_weights))
+
+    def _noise_iarr(self, noise_index):
+        """ctypes int array of the noise-parameter rows (cached: it never changes for an engine)."""
+        if noise_index is None:
+            return None
+        key = tuple(noise_index)
+        cached = getattr(self, '_noise_iarr_cache', None)
+        if cached is None or cached[0] != key:
+            cached = self._noise_iarr_cache = (key, _lib.iarr(noise_index))
+        return cached[1]
 
     def run_cycle_async(self, measurement_record, resample=True, select=True):
         """One full cycle -- pdf_update, (forced) systematic resample, utility + argmax -- enqueued
@@ -375,12 +393,16 @@ class OptBayesExpt(ParticlePDF):
             var_noise = None
             stats_ptr = C.c_void_p(self._buf.stats.data_ptr())
         else:
-            var_noise = _lib.darr(np.asarray(self.yvar_noise_model(), dtype=np.float64).reshape(-1),
-                                  _lib.MAX_CHANNELS)
+            vn = np.asarray(self.yvar_noise_model(), dtype=np.float64)
+            key = vn.tobytes()
+            cache = self._var_noise_cache
+            if cache is None or cache[0] != key:
+                cache = self._var_noise_cache = (key, _lib.darr(vn.reshape(-1), _lib.MAX_CHANNELS))
+            var_noise = cache[1]
             stats_ptr = None
         cost = self.cost_estimate()
         cost_ptr = None
-        if not (np.isscalar(cost) and float(cost) == 1.0):
+        if not (isinstance(cost, float) and cost == 1.0) and not (np.isscalar(cost) and float(cost) == 1.0):
             cost_arr = np.array(np.broadcast_to(np.asarray(cost, dtype=np.float64), (n_set,)))
             if self._cost_dev is None:
                 self._cost_dev = torch.empty(n_set, dtype=torch.float64, device=self._buf.device)
@@ -443,7 +465,7 @@ class OptBayesExpt(ParticlePDF):
         self._utility_dev_run()
         self._best_host.copy_(self._best_dev, non_blocking=True)
         self._torch.cuda.current_stream().synchronize()
-        bestindex = int(self._best_host[0])
+        bestindex = int(self._best_host_np[0])
         self.last_setting_index = bestindex
         return tuple(self.allsettings[:, bestindex])
 

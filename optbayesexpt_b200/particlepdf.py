@@ -55,6 +55,7 @@ class ParticlePDF:
     # ------------------------------------------------------------------------------------------
     def _install(self, samples):
         self._buf = ParticleBuffers(samples, self._device, capacity=getattr(self, '_capacity', None))
+        self._dev_index = self._buf.device.index
         self._alt = None
         self.n_particles = self._buf.n
         self.n_dims = self._buf.d
@@ -70,7 +71,7 @@ class ParticlePDF:
         self._pivot = p[:, :min(self.n_particles, 65536)].mean(dim=1).cpu().numpy().astype(np.float64)
 
     def _stream(self):
-        return _lib.raw_stream(self._torch)
+        return _lib.raw_stream(self._torch, self._dev_index)
 
     def _cs(self, buf=None):
         return C.byref((buf or self._buf).struct())

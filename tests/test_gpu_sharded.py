@@ -17,14 +17,26 @@ def _free_port():
     return port
 
 
+def _init_group(rank, world):
+    """OBE_TEST_BACKEND=nccl: one GPU per rank, NCCL collectives and real NVLink peer buffers (boxes with >= 2 GPUs);
+    default: both ranks on cuda:0 with gloo staging the collectives through the host."""
+    import torch
+    import torch.distributed as dist
+    if os.environ.get('OBE_TEST_BACKEND') == 'nccl':
+        torch.cuda.set_device(rank)
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    else:
+        torch.cuda.set_device(0)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+
+
 def _worker(rank, world, port, out):
     import warnings
     import torch
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
-    torch.cuda.set_device(0)
-    dist.init_process_group('gloo', rank=rank, world_size=world)
+    _init_group(rank, world)
     try:
         import optbayesexpt_b200 as obe
         from optbayesexpt_b200 import sharded as _sh
@@ -126,8 +138,7 @@ def _worker_noise(rank, world, port, out):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
-    torch.cuda.set_device(0)
-    dist.init_process_group('gloo', rank=rank, world_size=world)
+    _init_group(rank, world)
     try:
         import optbayesexpt_b200 as obe
         from optbayesexpt_b200.sharded import ShardedOptBayesExptNoiseParameter
@@ -191,11 +202,13 @@ def _worker_noise(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def _spawn(worker, peer):
+def _spawn(worker, peer, backend='gloo'):
     """Two ranks on the one GPU (gloo carries the host-side collectives).  peer='1': the stats and the draws travel
-    by peer writes into CUDA-IPC-mapped buffers + flags instead of collectives (the NVLink path of a real node)."""
+    by peer writes into CUDA-IPC-mapped buffers + flags instead of collectives (the NVLink path of a real node).
+    backend='nccl': one GPU per rank."""
     import torch.multiprocessing as mp
     os.environ['OBE_PEER_EXCHANGE'] = peer          # inherited by the spawned ranks
+    os.environ['OBE_TEST_BACKEND'] = backend
     try:
         ctx = mp.get_context('spawn')
         out = ctx.Queue()
@@ -208,6 +221,7 @@ def _spawn(worker, peer):
             p.join(timeout=60)
     finally:
         os.environ.pop('OBE_PEER_EXCHANGE', None)
+        os.environ.pop('OBE_TEST_BACKEND', None)
     for rank, msg in results:
         assert msg == 'ok', f'rank {rank}: {msg}'
 
@@ -220,3 +234,19 @@ def test_two_shards_noise_parameter_engine(obe_lib, peer):
 @pytest.mark.parametrize('peer', ['0', '1'], ids=['collectives', 'peer_exchange'])
 def test_two_shards_match_single_cloud(obe_lib, peer):
     _spawn(_worker, peer)
+
+
+def _two_gpus():
+    import torch
+    return torch.cuda.is_available() and torch.cuda.device_count() >= 2
+
+
+@pytest.mark.parametrize('peer', ['0', '1'], ids=['nccl_collectives', 'nvlink_peer_exchange'])
+@pytest.mark.parametrize('worker', ['base', 'noise'])
+def test_two_gpus_nccl(obe_lib, peer, worker):
+    """The same two-shard comparisons on TWO GPUs: NCCL collectives / peer buffers mapped over NVLink (CUDA IPC between
+    devices).  Skipped on a one-GPU box (the driver's GPU test box); bench.py --gpus N runs the same invariance check
+    on every multi-GPU run (`invariance` in its JSON line)."""
+    if not _two_gpus():
+        pytest.skip('needs >= 2 GPUs')
+    _spawn(_worker if worker == 'base' else _worker_noise, peer, backend='nccl')
