@@ -246,6 +246,7 @@ def bench_small(args):
     # ---- end to end through pdf_update / opt_setting, closed loop: forced and natural resampling
     def closed_loop(threshold, steps):
         e = make(threshold)
+        e.eager_select = True
         x = e.opt_setting()
         for _ in range(max(3, args.warmup)):
             e.pdf_update(ra.simulate(wl, x, meas))
@@ -604,29 +605,50 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    early = bool(eng._early_select_ok())
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e_start.record()
     for t in range(args.steps):
         rec = fixed[args.warmup + t]
         ev[t][0].record()
-        eng.run_cycle_async(rec, resample=False, select=False)
+        eng.run_cycle_async(rec, resample=False, select=False)     # update (+ stats exchange and shard plan when sharded)
         ev[t][1].record()
-        eng.resample()
+        eng.resample_select_async()     # plan -> [pick K draws, utility, argmax] || [streaming resample] -> join
         ev[t][2].record()
-        eng._utility_dev_run()
-        ev[t][3].record()
     e_stop.record()
     barrier()
     ms_total = e_start.elapsed_time(e_stop)
     t_upd = float(np.mean([ev[t][0].elapsed_time(ev[t][1]) for t in range(args.steps)]))
     t_res = float(np.mean([ev[t][1].elapsed_time(ev[t][2]) for t in range(args.steps)]))
-    t_sel = float(np.mean([ev[t][2].elapsed_time(ev[t][3]) for t in range(args.steps)]))
+    # the same cycle with the selection serialised after the resample (early select off): the per-phase split
+    eng.early_select = False
+    sv = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    for t in range(2):
+        eng.run_cycle_async(fixed[t])
+    barrier()
+    s_start, s_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_start.record()
+    for t in range(args.steps):
+        rec = fixed[args.warmup + t]
+        sv[t][0].record()
+        eng.run_cycle_async(rec, resample=False, select=False)
+        sv[t][1].record()
+        eng.resample_select_async(True, False)
+        sv[t][2].record()
+        eng.resample_select_async(False, True)
+        sv[t][3].record()
+    s_stop.record()
+    barrier()
+    eng.early_select = True
+    ser = [float(np.mean([sv[t][i].elapsed_time(sv[t][i + 1]) for t in range(args.steps)])) for i in range(3)]
+    ser.append(s_start.elapsed_time(s_stop) / args.steps)
     if world > 1:
-        tt = torch.tensor([ms_total, t_upd, t_res, t_sel], dtype=torch.float64, device='cuda')
+        tt = torch.tensor([ms_total, t_upd, t_res] + ser, dtype=torch.float64, device='cuda')
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total, t_upd, t_res, t_sel = [float(v) for v in tt.cpu()]
+        vals = [float(v) for v in tt.cpu()]
+        ms_total, t_upd, t_res, ser = vals[0], vals[1], vals[2], vals[3:]
     ms_step = ms_total / args.steps
 
     # ---------------- the cycle without a resample (cycle_noresample) ------------------
@@ -646,6 +668,7 @@ def main():
         eng.resample()                       # back to a healthy cloud for the closed loop below
 
     # ---------------- end to end through the reference-shaped API, closed loop -------------------
+    eng.eager_select = True              # the resample inside pdf_update starts the selection opt_setting() asks for
     x = eng.opt_setting()
     for _ in range(max(3, args.warmup // 2)):
         eng.pdf_update(record_for(x[0]))
@@ -712,7 +735,7 @@ def main():
     b_cycle = b_upd + b_res + b_sel
     gbs_res = b_res / world / (t_res * 1e-3) / 1e9
     fused = os.environ.get('OBE_OPT_RESAMPLE_FUSED', '1') != '0'
-    sharded_launches = 0 if world == 1 else (3 if getattr(eng, '_peer', None) is not None else 2)
+    sharded_launches = 0 if world == 1 else (2 if getattr(eng, '_peer', None) is not None else 1)
     line = {
         'metric': 'pdf_update+resample+opt_setting cycles/sec', 'value': 1e3 / ms_step, 'unit': 'cycles/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
@@ -722,12 +745,13 @@ def main():
                 'h2d_bytes_per_step': 8 * (1 + 1 + 1 + 8 + 1) + 8 * args.draws,
                 'd2h_bytes_per_step': 8 * 64 + 16,
                 'note': 'record, pivot and uniforms travel as kernel arguments; stats block + argmax come back'},
-        # update, plan, resample (one kernel; two on the ancestors + move path), draw, utility;
-        # sharded: + shard plan (peer exchange fused in) + draw collect
+        # update, plan, pick (the K draws, from the plan), utility, streaming resample (two kernels on the ancestors +
+        # move path, which also draws with k_draw); sharded: + shard plan (peer exchange fused in) + draw collect
         'gpu_launches': ((5 if fused else 6) + sharded_launches) * args.steps,
         'roofline': {'bound': 'hbm',
-                     'kernel': ('resample step = k_sys_plan + k_sys_resample_warp (one event bracket)' if fused else
-                                'resample step = k_sys_plan + k_sys_ancestors + k_sys_move (one event bracket)'),
+                     'kernel': ('resample step = k_sys_plan + k_sys_resample_warp (one event bracket; the K-draw pick, '
+                                'utility and argmax kernels run inside the same bracket on the selection stream)' if fused
+                                else 'resample step = k_sys_plan + k_sys_ancestors + k_sys_move (one event bracket)'),
                      'achieved': gbs_res, 'peak': peak, 'unit': 'GB/s', 'frac': gbs_res / peak,
                      'algorithmic_bytes_per_launch': b_res / world,
                      'algorithmic_note': 'SURVEY 8(d): 8N(2d+2) (read w, gather d rows, write d rows, write w)',
@@ -739,7 +763,11 @@ def main():
                      'traffic_source': 'profiles/r2_ncu_summary.md (ncu --set full of the same build and workload; '
                                        'per-particle figure x particles of this launch, not re-measured in this run)',
                      'peak_source': peak_src},
-        'kernels_ms': {'update': t_upd, 'resample': t_res, 'draw+utility+argmax': t_sel},
+        'kernels_ms': {'update': t_upd, 'resample || draw+utility+argmax': t_res},
+        'early_select': early,
+        'serialised_cycle': {'note': 'same cycle, selection AFTER the resample on one stream (early select off)',
+                             'ms_per_step': ser[3],
+                             'kernels_ms': {'update': ser[0], 'resample': ser[1], 'draw+utility+argmax': ser[2]}},
         'kernels_gbs': {'update': b_upd / world / (t_upd * 1e-3) / 1e9, 'resample': gbs_res},
         'exchange': None if world == 1 else ('peer (CUDA IPC over NVLink)' if getattr(eng, '_peer', None) is not None
                                              else 'nccl'),

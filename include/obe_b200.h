@@ -213,6 +213,24 @@ int obe_draw_planned_peer(const obe_cloud_t* c, const double* u_host, int k, voi
 int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* out, const double* plan_dev,
                                     int64_t n_total, uint64_t seed, uint32_t epoch, double a_param,
                                     int scale, void* stream);
+/* Early select (obe_base.py:733-756 opt_setting right after particlepdf.py:260-310 resample): the K draws of the
+ * design half are offspring of the resample, so they can be produced from the resample PLAN before the cloud is
+ * streamed, and the utility pass can overlap the resample on a second stream.
+ *   obe_resample_defer(1)   the calling thread's next obe_resample_systematic[_sharded|_planned] call launches only
+ *                           its plan kernel and parks the streaming kernel (0 disarms / drops a parked one);
+ *   obe_resample_pick       draw q = the offspring in global slot min(floor(u[q] * n_total), n_total - 1), computed by
+ *                           the work unit that owns the slot; (d, k) row-major into draws_dev.  Values are bit-identical
+ *                           to what obe_resample_emit stores in that slot.  Sharded: peer_bufs != NULL exchanges the
+ *                           draws by peer writes (as obe_draw_planned_peer); peer_bufs == NULL writes zeros for draws
+ *                           other shards own (all-reduce(sum) completes them);
+ *   obe_resample_emit       launches the parked streaming kernel.
+ *   obe_stream_fork/join    side waits for main / main waits for side (cached events, no host synchronisation). */
+int obe_resample_defer(int on);
+int obe_resample_pick(const double* u_host, int k, double* draws_dev, void* const* peer_bufs, int rank, int world,
+                      uint64_t epoch, void* stream);
+int obe_resample_emit(void* stream);
+int obe_stream_fork(void* main_stream, void* side_stream);
+int obe_stream_join(void* main_stream, void* side_stream);
 /* randdraw(K) over a sharded cloud: this rank writes the draws it owns (per plan_dev; post=1 uses the
  * post-resample shard totals) and zeros elsewhere; an all-reduce(sum) of draws_dev completes it. */
 int obe_draw_planned(const obe_cloud_t* c, const double* u_host, int k, double* draws_dev,

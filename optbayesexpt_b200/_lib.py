@@ -17,6 +17,7 @@ STATS_LEN = 64
 PLAN_LEN = 512
 PLAN_GSTATS, PLAN_COUNTS, PLAN_OVERFLOW = 352, 416, 9
 MAX_PARAMS = 8
+MAX_DRAWS = 128
 MAX_CHANNELS = 4
 MAX_SETTINGS = 4
 MAX_CONSTANTS = 8
@@ -99,6 +100,11 @@ SIGNATURES = {
     'obe_peer_free': (C.c_int, [_VP]),
     'obe_shard_plan_peer': (C.c_int, [C.POINTER(_VP), C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_double, C.c_int64,
                                       C.c_double, C.c_int, _PCLOUD, _PCLOUD, _VP, _VP]),
+    'obe_resample_defer': (C.c_int, [C.c_int]),
+    'obe_resample_pick': (C.c_int, [_PD, C.c_int, _VP, C.POINTER(_VP), C.c_int, C.c_int, C.c_uint64, _VP]),
+    'obe_resample_emit': (C.c_int, [_VP]),
+    'obe_stream_fork': (C.c_int, [_VP, _VP]),
+    'obe_stream_join': (C.c_int, [_VP, _VP]),
     'obe_draw_planned_peer': (C.c_int, [_PCLOUD, _PD, C.c_int, C.POINTER(_VP), C.c_int, C.c_int, C.c_uint64, _VP, C.c_int,
                                         _VP, _VP]),
     'obe_set_uniform_total': (C.c_int, [_PCLOUD, C.c_int64, _VP]),

@@ -603,6 +603,7 @@ struct ObeResampleArgs {
     long long cap_out;             // capacity of the output buffers (planned mode)
     int implicit_out;              // 1: do not write the offspring weights, leave them implicit
     int chunk;                     // output slots per work unit the plan was made with
+    unsigned int* unit_counter;    // one-kernel path: next unit to hand out (zeroed by the plan kernel); null: static stride
     unsigned int* anc;             // two-kernel path: ancestor (input index) of every output slot of this shard
     double* out_tile_sums; double* out_prefix; double* out_stats;   // CDF bookkeeping of the offspring cloud
     double factor[OBE_MAX_DIMS * OBE_MAX_DIMS];
@@ -729,10 +730,12 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
                                                                int* __restrict__ unit_tile,
                                                                const long long* __restrict__ n_dev = nullptr,
                                                                const double* __restrict__ plan = nullptr,
-                                                               int chunk = OBE_OUT_CHUNK) {
+                                                               int chunk = OBE_OUT_CHUNK,
+                                                               unsigned int* __restrict__ unit_counter = nullptr) {
     __shared__ long long sml[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     __shared__ int smi[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     const int t = threadIdx.x;
+    if (t == 0 && unit_counter) *unit_counter = 0u;        // the streaming kernel hands its units out dynamically
     if (n_dev) n_tiles = (*n_dev + OBE_TILE - 1) / OBE_TILE;
     if (plan) {
         n_total = (long long)plan[OBE_PL_NTOTAL]; u0 = plan[OBE_PL_U0];
@@ -818,6 +821,9 @@ static int64_t g_utility_lane_fill = 50;          /* obe_set_option("utility_lan
 static int64_t g_plan_cluster_min_tiles = 8192;   /* obe_set_option("plan_cluster_min_tiles") */
 static int64_t g_utility_cache = 1;               /* obe_set_option("utility_cache"): park the K curves in shared memory */
 static int64_t g_resample_fused = 1;              /* obe_set_option("resample_fused"): 1 = k_sys_resample_warp, 0 = ancestors + move */
+static int64_t g_resample_units_per_sm = 16;      /* obe_set_option("resample_units_per_sm"): work units per SM the chunk size aims at */
+static int64_t g_resample_reserve = 0;            /* obe_set_option("resample_reserve_ctas"): CTA slots an early-select resample leaves to the selection kernels */
+static int64_t g_resample_dynamic = 1;            /* obe_set_option("resample_dynamic"): units handed out by an atomic counter */
 static int64_t g_resample_blocks = 0;             /* obe_set_option("resample_blocks"): CTAs per SM of the fused kernel (0: default) */
 #ifndef OBE_PLAN_CLUSTER_MIN_TILES
 #define OBE_PLAN_CLUSTER_MIN_TILES 8192     /* below: one CTA does every pass in a single round anyway */
@@ -826,10 +832,12 @@ __global__ void __cluster_dims__(OBE_PLAN_CLUSTER, 1, 1) __launch_bounds__(OBE_S
 k_sys_plan_cluster(const double* __restrict__ prefix, long long n_tiles, long long n_total, double u0,
                    double cdf_offset, double cdf_total, long long slot_begin, long long slot_end,
                    long long* __restrict__ H, int* __restrict__ unit_start, int* __restrict__ unit_tile,
-                   const long long* __restrict__ n_dev, const double* __restrict__ plan, int chunk) {
+                   const long long* __restrict__ n_dev, const double* __restrict__ plan, int chunk,
+                   unsigned int* __restrict__ unit_counter) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int r = (int)cluster.block_rank();
+    if (r == 0 && threadIdx.x == 0 && unit_counter) *unit_counter = 0u;
     __shared__ long long sml[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     __shared__ int smi[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     __shared__ long long xmax[OBE_PLAN_CLUSTER];     // segment maxima of H, every CTA holds all eight
@@ -1369,6 +1377,69 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_MOVE_BLOCKS(D)) k_sys_move(co
 
 struct WrUnit { long long og_al, o_al, base; int q_emit_end, A, lastrel, pad; };
 
+// ---- the comb arithmetic of one work unit, shared by the streaming kernel and the early-select pick kernel (so the
+// ancestor of a slot is the same bits wherever it is computed)
+// fast comb count: x2 = c*n - u0 + 1/2 in ONE fma of the un-normalised CDF value with K = n/total, rounded to
+// the nearest integer by the 1.5*2^52 trick (the low word of x2 + M IS the integer: no FRND / F2I), which is
+// ceil(c*n - u0) unless c*n - u0 lies within `tolw` of an integer.  The estimate carries 4 more roundings
+// than comb_count_d's (K, the fused normalisation, the pre-added prefix, the +1/2): <= 1e-15*n in all
+// against tolw = 3e-15*n, so outside the window it equals the exact comb count; a thread that sees ANY of
+// its 8 particles inside the window (probability ~5e-14*n) redoes all 8 the canonical way.
+struct WrComb {
+    double p0, K, c_half, tolh, chunk0d;
+    int c0a, n_chunk, A, q_end, lastrel;
+};
+__device__ __forceinline__ WrComb wr_comb_of(const SysCtx& c, double prefix_k, long long chunk0, int A, int n_chunk,
+                                             int lastrel) {
+    WrComb w;
+    w.p0 = obe_add(c.cdf_offset, prefix_k);
+    w.K = c.nd * c.inv_total; w.c_half = 0.5 - c.u0; w.tolh = 0.5 - 3e-15 * c.nd;
+    w.chunk0d = (double)chunk0;
+    w.c0a = (int)(unsigned int)(unsigned long long)(chunk0 - A);   // wraps: differences stay < 2^31
+    w.n_chunk = n_chunk; w.A = A; w.q_end = A + n_chunk; w.lastrel = lastrel;
+    return w;
+}
+// Kogge-Stone scan of the lanes' sums of one 256-particle segment: exclusive base of this lane, segment total
+__device__ __forceinline__ void wr_segment_scan(double run, int lane, double& ex, double& seg_total) {
+    double x = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    ex = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) ex = 0.0;
+    seg_total = __shfl_sync(0xffffffffu, x, 31);
+}
+// end slot (shifted chunk coordinates, NOT yet monotone) of this lane's 8 particles i0 .. i0+7 of the tile
+__device__ __forceinline__ void wr_end_slots(const WrComb& w, const SysCtx& c, const double (&incl)[OBE_EPT], double bs,
+                                             int i0, int (&h)[OBE_EPT]) {
+    const double MAGIC = 6755399441055744.0;
+    const double bsp = w.p0 + bs;
+    bool near = false;
+#pragma unroll
+    for (int e = 0; e < OBE_EPT; ++e) {
+        const double x2 = fma(bsp + incl[e], w.K, w.c_half);
+        const double tt = x2 + MAGIC;
+        const double dd = x2 - (tt - MAGIC);
+        near |= !(fabs(dd) <= w.tolh);
+        h[e] = __double2loint(tt) - w.c0a;
+    }
+    if (near) {                                  // rare: the canonical CDF value and the exact comb count
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; ++e) {
+            const double cn = obe_mul(obe_add(w.p0, bs + incl[e]), c.inv_total);
+            const double hd = comb_count_d(cn, c.u0, c.inv_n, c.nd, c.tol) - w.chunk0d;   // |hd| < 2^32
+            h[e] = min(max(__double2int_rz(hd), 0), w.n_chunk) + w.A;             // the conversion saturates
+        }
+    }
+    if (i0 + OBE_EPT > w.lastrel) {                // the tile's last live particle owns the tail
+#pragma unroll
+        for (int e = 0; e < OBE_EPT; ++e)
+            if (i0 + e >= w.lastrel) h[e] = w.q_end;
+    }
+}
+
 __device__ __forceinline__ void wr_load_segment(const double* __restrict__ wt, int i0, int cnt_tile, double wuni,
                                                 double (&v)[OBE_EPT]) {
     if (wuni > 0.0) {
@@ -1406,8 +1477,11 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
         reinterpret_cast<unsigned int*>(wr_marks)[q] = 0u;
     setup_factor<D>(a, sF, sMean);                       // ends with a block barrier
     const SysCtx& c = cs;
-    if (blockIdx.x == gridDim.x - 1) {
-        // bookkeeping block (as in k_sys_ancestors): tile sums, CDF prefix and stats of the offspring cloud
+    if (blockIdx.x == 0) {
+        // bookkeeping block: tile sums, CDF prefix and stats of the offspring cloud.  It is block 0 of a grid that
+        // fits the machine in ONE wave, so it is resident from the start and its single-CTA scan (24 rounds at 1e8
+        // particles) hides behind the workers; as the LAST block of a grid one larger than the wave it could only
+        // start when a worker retired, i.e. it ran as a serial tail after the whole resample.
         __shared__ double smd[OBE_SCANW * (OBE_THREADS / 32 + 1)];
         const long long slot_end = a.plan ? (long long)a.plan[OBE_PL_SLOT1] : a.slot_end;
         long long n_out = slot_end - c.slot_begin;
@@ -1428,8 +1502,18 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
     unsigned short* marks = wr_marks + warp * OBE_WR_MARKS;
     const int n_units = s_units;
     const int n_warps = ((int)gridDim.x - 1) * NWARP;
+    // Units are handed out DYNAMICALLY (one atomic per unit, lane 0): the selection kernels of an early select share
+    // the SMs with this kernel for its first ~30 us, so some CTAs start late, and with a static stride (unit_counter
+    // == nullptr: warp w walks units w, w + n_warps, ...) the whole launch waited for them.
+    const bool dynamic = a.unit_counter != nullptr;
+    auto next_unit = [&](int prev) -> int {
+        if (!dynamic) return prev + n_warps;
+        int v = 0;
+        if (lane == 0) v = (int)atomicAdd(a.unit_counter, 1u);
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
 #pragma unroll 1
-    for (int unit = (int)blockIdx.x * NWARP + warp; unit < n_units; unit += n_warps) {
+    for (int unit = dynamic ? next_unit(0) : ((int)blockIdx.x - 1) * NWARP + warp; unit < n_units; unit = next_unit(unit)) {
         int k;
         if (a.unit_tile) {
             k = a.unit_tile[unit];
@@ -1454,19 +1538,9 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
         const int lastrel = cnt_tile - 1;
         // ---------------------------------------------------------------- phase A: marks
         {
-            const double inv_total = c.inv_total, nd = c.nd, u0 = c.u0;
             const double wuni = c.wuni_in;
-            const double p0 = obe_add(c.cdf_offset, c.prefix[k]);
             const double* __restrict__ wt = c.w_in + base;
-            // fast comb count: x2 = c*n - u0 + 1/2 in ONE fma of the un-normalised CDF value with K = n/total, rounded to
-            // the nearest integer by the 1.5*2^52 trick (the low word of x2 + M IS the integer: no FRND / F2I), which is
-            // ceil(c*n - u0) unless c*n - u0 lies within `tolw` of an integer.  The estimate carries 4 more roundings
-            // than comb_count_d's (K, the fused normalisation, the pre-added prefix, the +1/2): <= 1e-15*n in all
-            // against tolw = 3e-15*n, so outside the window it equals the exact comb count; a thread that sees ANY of
-            // its 8 particles inside the window (probability ~5e-14*n) redoes all 8 the canonical way.
-            const double K = nd * inv_total, c_half = 0.5 - u0, tolh = 0.5 - 3e-15 * nd;
-            const double MAGIC = 6755399441055744.0;
-            const int c0a = (int)(unsigned int)(unsigned long long)(chunk0 - A);   // wraps: differences stay < 2^31
+            const WrComb cw = wr_comb_of(c, c.prefix[k], chunk0, A, n_chunk, lastrel);
             double wb = 0.0;                  // canonical sum of the totals of the segments before this one
             int carry_end = A;                // end slot of the last particle walked so far
             double vn[OBE_EPT];
@@ -1481,44 +1555,12 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
                 for (int e = 0; e < OBE_EPT; ++e) { run += vn[e]; incl[e] = run; }
                 if ((seg + 1) * 256 <= lastrel) wr_load_segment(wt, i0 + 256, cnt_tile, wuni, vn);   // in flight below
                 // canonical scan of the segment (tile_scan_blocked with the warp loop made sequential in time)
-                double x = run;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double y = __shfl_up_sync(0xffffffffu, x, o);
-                    if (lane >= o) x += y;
-                }
-                double ex = __shfl_up_sync(0xffffffffu, x, 1);
-                if (lane == 0) ex = 0.0;
-                const double seg_total = __shfl_sync(0xffffffffu, x, 31);
+                double ex, seg_total;
+                wr_segment_scan(run, lane, ex, seg_total);
                 const double bs = wb + ex;
                 // end slot of every particle in shifted chunk coordinates (the running max supplies the lower clamp)
                 int h[OBE_EPT];
-                {
-                    const double bsp = p0 + bs;
-                    bool near = false;
-#pragma unroll
-                    for (int e = 0; e < OBE_EPT; ++e) {
-                        const double x2 = fma(bsp + incl[e], K, c_half);
-                        const double tt = x2 + MAGIC;
-                        const double dd = x2 - (tt - MAGIC);
-                        near |= !(fabs(dd) <= tolh);
-                        h[e] = __double2loint(tt) - c0a;
-                    }
-                    if (near) {                                  // rare: the canonical CDF value and the exact comb count
-                        const double chunk0d = (double)chunk0;
-#pragma unroll
-                        for (int e = 0; e < OBE_EPT; ++e) {
-                            const double cn = obe_mul(obe_add(p0, bs + incl[e]), inv_total);
-                            const double hd = comb_count_d(cn, u0, c.inv_n, nd, c.tol) - chunk0d;   // |hd| < 2^32
-                            h[e] = min(max(__double2int_rz(hd), 0), n_chunk) + A;             // the conversion saturates
-                        }
-                    }
-                    if (i0 + OBE_EPT > lastrel) {                // the tile's last live particle owns the tail
-#pragma unroll
-                        for (int e = 0; e < OBE_EPT; ++e)
-                            if (i0 + e >= lastrel) h[e] = q_end;
-                    }
-                }
+                wr_end_slots(cw, c, incl, bs, i0, h);
                 int runm = A;
 #pragma unroll
                 for (int e = 0; e < OBE_EPT; ++e) {
@@ -1697,6 +1739,150 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
             }
         }
         __syncwarp();
+    }
+}
+
+// ---- early select: the K draws of the design half, straight from the resample plan -----------------------------
+// The parameter draws opt_setting / good_setting ask for right after a resample are particles of the OFFSPRING cloud
+// (uniform weights): draw q is the offspring in global output slot s_q = min(floor(u_q * n_total), n_total - 1).
+// That offspring is a function of the PLAN alone: its ancestor is the first particle of the owning tile whose comb
+// end slot exceeds s_q (what the marks + max-scan of the streaming kernel compute for every slot at once), and its
+// jitter comes from the slot-indexed Philox stream.  One warp per draw: 32-ary search of H for the tile, the same
+// segment walk / comb arithmetic as the streaming kernel (wr_segment_scan, wr_end_slots), stop at the first segment
+// that holds the ancestor, gather, jitter_group4 on the aligned group of four slots, store d doubles.  The values are
+// bit-identical to what k_sys_resample_warp stores in slot s_q (tests/test_gpu_early_select.py), but they exist
+// ~10 us after the plan instead of after the whole resample, so the utility pass can overlap the streaming kernel.
+// Sharded: a rank produces the draws whose slots it owns; the others store nothing (peer exchange: the owner writes
+// into every rank's buffer and the last CTA raises the flags) or zeros (collective mode: an all-reduce follows).
+struct ObePickArgs {
+    int k; int ldk; double* out;
+    int peer_world, peer_rank;
+    unsigned long long peer_epoch;
+    unsigned int* peer_counter;
+    ObePeers peers;
+    double u[OBE_MAX_DRAWS];
+};
+#define OBE_PICK_WARPS 2
+template <int D>
+__global__ void __launch_bounds__(OBE_PICK_WARPS * 32) k_sys_pick(const ObeResampleArgs a, const ObePickArgs pk) {
+    __shared__ double sF[D * D];
+    __shared__ double sMean[D];
+    __shared__ SysCtx cs;
+    __shared__ long long s_tiles_in;
+    if (threadIdx.x == 0) {
+        long long n_tiles_in;
+        cs = sys_ctx_of(a, n_tiles_in);
+        s_tiles_in = n_tiles_in;
+    }
+    setup_factor<D>(a, sF, sMean);                       // ends with a block barrier
+    const SysCtx& c = cs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = (int)blockIdx.x * OBE_PICK_WARPS + warp;
+    if (q < pk.k) {
+        const long long n_total = (long long)c.nd;
+        const long long slot_end = a.plan ? (long long)a.plan[OBE_PL_SLOT1] : a.slot_end;
+        long long s = (long long)(pk.u[q] * c.nd);
+        s = s < 0 ? 0 : (s >= n_total ? n_total - 1 : s);
+        const bool mine = s >= c.slot_begin && s < slot_end && s - c.slot_begin < c.cap_out;
+        if (!mine) {
+            if (pk.peer_world == 0 && lane < D) pk.out[(long long)lane * pk.ldk + q] = 0.0;
+        } else {
+            // last tile k with H[k] <= s (H is monotone): 32 probes per round
+            int lo = 0, hi = (int)s_tiles_in;             // the answer lies in [lo, hi)
+            while (hi - lo > 1) {
+                const int step = (hi - lo + 31) / 32;
+                const int probe = lo + (lane + 1) * step;
+                const bool le = probe < hi && a.plan_h[probe] <= s;
+                const int cnt = __popc(__ballot_sync(0xffffffffu, le));
+                lo += cnt * step;
+                hi = min(lo + step, hi);
+            }
+            const int k = lo;
+            const long long Hk = a.plan_h[k], Hk1 = a.plan_h[k + 1];
+            const int rel_begin = (int)((s - Hk) / a.chunk) * a.chunk;
+            const int n_chunk = min(rel_begin + a.chunk, (int)(Hk1 - Hk)) - rel_begin;
+            const long long chunk0 = Hk + rel_begin;
+            const int A = (int)(chunk0 & 3);
+            const int qs = A + (int)(s - chunk0);          // the slot in shifted chunk coordinates, A <= qs < A + n_chunk
+            const long long base = (long long)k * OBE_TILE;
+            const int cnt_tile = (int)(min(c.n_in, base + OBE_TILE) - base);
+            const int lastrel = cnt_tile - 1;
+            const WrComb cw = wr_comb_of(c, c.prefix[k], chunk0, A, n_chunk, lastrel);
+            const double* __restrict__ wt = c.w_in + base;
+            double wb = 0.0;
+            int anc = lastrel;
+            double vn[OBE_EPT];
+            wr_load_segment(wt, lane * OBE_EPT, cnt_tile, c.wuni_in, vn);
+#pragma unroll 1
+            for (int seg = 0; seg < OBE_TILE / 256; ++seg) {
+                if (seg * 256 > lastrel) break;
+                const int i0 = seg * 256 + lane * OBE_EPT;
+                double incl[OBE_EPT];
+                double run = 0.0;
+#pragma unroll
+                for (int e = 0; e < OBE_EPT; ++e) { run += vn[e]; incl[e] = run; }
+                if ((seg + 1) * 256 <= lastrel) wr_load_segment(wt, i0 + 256, cnt_tile, c.wuni_in, vn);
+                double ex, seg_total;
+                wr_segment_scan(run, lane, ex, seg_total);
+                const double bs = wb + ex;
+                int h[OBE_EPT];
+                wr_end_slots(cw, c, incl, bs, i0, h);
+                // the ancestor of slot qs is the first particle (in tile order) whose end slot exceeds it
+                int first = 1 << 30;
+#pragma unroll
+                for (int e = OBE_EPT - 1; e >= 0; --e)
+                    if (h[e] > qs) first = i0 + e;
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, m));
+                if (first < (1 << 30)) { anc = first; break; }
+                wb = wb + seg_total;
+            }
+            anc = min(anc, lastrel);
+            if (lane == 0) {
+                const int us = (int)(s & 3);
+                double xv[4][D];
+                bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ok[u] = true;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) xv[u][j] = __ldg(c.pin + j * c.ld_in + base + anc);
+                }
+                if (c.jitter)
+                    jitter_group4<D>(xv, s - us, c.seed, c.epoch, sF, sMean, c.a_param, c.scale, nullptr, 0, ok);
+                double val[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    val[j] = xv[0][j];
+#pragma unroll
+                    for (int u = 1; u < 4; ++u) val[j] = (us == u) ? xv[u][j] : val[j];
+                }
+                if (pk.peer_world > 0) {
+                    const int parity = (int)(pk.peer_epoch & 1ull);
+#pragma unroll
+                    for (int j = 0; j < D; ++j)
+                        for (int g = 0; g < pk.peer_world; ++g)
+                            pk.peers.p[g][OBE_PEER_DRAWS + parity * 1024 + j * pk.ldk + q] = val[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) pk.out[(long long)j * pk.ldk + q] = val[j];
+                }
+            }
+        }
+    }
+    if (pk.peer_world > 0) {
+        // every CTA reports in; the last one raises this rank's flag in every rank's buffer (as k_draw does)
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(pk.peer_counter, 1u) == gridDim.x - 1) {
+                __threadfence_system();
+                const int parity = (int)(pk.peer_epoch & 1ull);
+                for (int g = 0; g < pk.peer_world; ++g)
+                    obe_flag_store(obe_peer_flags(pk.peers.p[g], 1, parity) + pk.peer_rank, pk.peer_epoch);
+                *pk.peer_counter = 0u;
+            }
+        }
     }
 }
 
@@ -2250,6 +2436,9 @@ int obe_set_option(const char* name, int64_t value) {
     if (s == "utility_cache") { g_utility_cache = value ? 1 : 0; return 0; }
     if (s == "resample_fused") { g_resample_fused = value ? 1 : 0; return 0; }
     if (s == "resample_blocks") { g_resample_blocks = value < 0 ? 0 : value; return 0; }
+    if (s == "resample_reserve_ctas") { g_resample_reserve = value < 0 ? 0 : value; return 0; }
+    if (s == "resample_dynamic") { g_resample_dynamic = value ? 1 : 0; return 0; }
+    if (s == "resample_units_per_sm") { g_resample_units_per_sm = value < 1 ? 1 : value; return 0; }
     return obe_fail("unknown option '%s'%s", name);
 }
 
@@ -2663,7 +2852,7 @@ int obe_gather_jitter(const obe_cloud_t* in, const obe_cloud_t* out, const int64
 // more CDF walk of the tile per extra unit.
 static int plan_chunk(int64_t out_cap) {
     if (!g_resample_fused) return OBE_OUT_CHUNK;
-    int64_t c = out_cap / ((int64_t)obe_sms() * 16);
+    int64_t c = out_cap / ((int64_t)obe_sms() * g_resample_units_per_sm);
     c = (c + OBE_WR_GROUP_HOST - 1) / OBE_WR_GROUP_HOST * OBE_WR_GROUP_HOST;
     if (c < OBE_WR_MIN_CHUNK) c = OBE_WR_MIN_CHUNK;
     if (c > OBE_WR_CHUNK) c = OBE_WR_CHUNK;
@@ -2675,6 +2864,20 @@ static bool unit_map_fits(const obe_cloud_t* in, int64_t out_cap) {
     return nt + (out_cap + chunk - 1) / chunk <= nt + in->n / OBE_WR_MIN_CHUNK + 4;
 }
 
+// ---- early select: plan now, pick the K draws, stream the cloud later -------------------------------------
+// obe_resample_defer(1) arms the calling thread: its next systematic resample call (whole cloud, sharded or planned)
+// launches only the plan kernel and PARKS the streaming kernel's arguments; obe_resample_pick() then produces the K
+// parameter draws of the design half straight from the plan (k_sys_resample_warp<D, true>), and obe_resample_emit()
+// launches the parked streaming kernel.  The caller may put the pick + utility pass and the emission on different
+// streams (obe_stream_fork / obe_stream_join), which hides the whole selection behind the resample.
+struct ObeParked {
+    bool armed, parked;
+    ObeResampleArgs a;
+    int d, grid;
+    unsigned int* counter;
+};
+static thread_local ObeParked g_parked = {};
+
 // k_sys_ancestors + k_sys_move, after k_sys_plan
 static int launch_sys_resample(const obe_cloud_t* in, const obe_cloud_t* out, ObeResampleArgs& a, int64_t out_cap,
                                cudaStream_t st) {
@@ -2682,19 +2885,27 @@ static int launch_sys_resample(const obe_cloud_t* in, const obe_cloud_t* out, Ob
     if (in->n >= (1ll << 32)) return obe_fail("systematic resample supports shards of < 2^32 particles%s%s");
     a.anc = scratch_of(out).anc;
     a.out_tile_sums = out->tile_sums_dev; a.out_prefix = out->tile_prefix_dev; a.out_stats = out->stats_dev;
+    a.unit_counter = g_resample_dynamic ? scratch_of(in).counter + 18 : nullptr;
     if (g_resample_fused) {
         // one kernel: every warp owns work units from the weights to the stores (+ the bookkeeping block)
         const int per_sm = (g_resample_blocks > 0 && g_resample_blocks < OBE_WR_BLOCKS(in->d)) ? (int)g_resample_blocks
                                                                                               : OBE_WR_BLOCKS(in->d);
-        int64_t g = (int64_t)obe_sms() * per_sm;
+        int64_t g = (int64_t)obe_sms() * per_sm - 1;          // workers; + the bookkeeping block = one full wave
         const int64_t need = (max_units + OBE_THREADS / 32 - 1) / (OBE_THREADS / 32);
         if (g > need) g = need;
         if (g < 1) g = 1;
         const int grid = (int)g + 1;
+        if (g_parked.armed) {                                  // early select: the emission waits for obe_resample_emit
+            g_parked.armed = false; g_parked.parked = true;
+            g_parked.a = a; g_parked.d = in->d; g_parked.grid = grid;
+            g_parked.counter = scratch_of(in).counter + 17;
+            return 0;
+        }
         OBE_DIM_SWITCH_WR(in->d, grid, st, a)
         OBE_LAUNCH_CHECK("k_sys_resample_warp");
         return 0;
     }
+    if (g_parked.armed) { g_parked.armed = false; return obe_fail("deferred emission needs the one-kernel resample (resample_fused=1)%s%s"); }
     {
         int64_t g = (int64_t)obe_sms() * OBE_ANC_BLOCKS_PER_SM;
         if (g > max_units) g = max_units;
@@ -2735,12 +2946,12 @@ static int resample_systematic_impl(const obe_cloud_t* in, const obe_cloud_t* ou
     if (a.n_tiles > g_plan_cluster_min_tiles)
         k_sys_plan_cluster<<<OBE_PLAN_CLUSTER, OBE_SCAN_THREADS, 0, st>>>(
             in->tile_prefix_dev, a.n_tiles, n_total, u0, sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0,
-            slot_begin, slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr, a.chunk);
+            slot_begin, slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr, a.chunk, s.counter + 18);
     else
         k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, u0,
                                                   sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0, slot_begin,
                                                   slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr,
-                                                  a.chunk);
+                                                  a.chunk, s.counter + 18);
     OBE_LAUNCH_CHECK("k_sys_plan");
     return launch_sys_resample(in, out, a, out->n, st);
 }
@@ -2873,14 +3084,81 @@ int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* ou
     if (a.n_tiles > g_plan_cluster_min_tiles)
         k_sys_plan_cluster<<<OBE_PLAN_CLUSTER, OBE_SCAN_THREADS, 0, st>>>(
             in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0, s.plan_h, s.unit_start, (int*)a.unit_tile,
-            (const long long*)in->n_dev, plan_dev, a.chunk);
+            (const long long*)in->n_dev, plan_dev, a.chunk, s.counter + 18);
     else
         k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0,
                                                   s.plan_h, s.unit_start, (int*)a.unit_tile,
-                                                  (const long long*)in->n_dev, plan_dev, a.chunk);
+                                                  (const long long*)in->n_dev, plan_dev, a.chunk, s.counter + 18);
     OBE_LAUNCH_CHECK("k_sys_plan");
     return launch_sys_resample(in, out, a, out->ld, st);
 }
+
+int obe_resample_defer(int on) {
+    g_parked.armed = on != 0;
+    if (!on) g_parked.parked = false;
+    return 0;
+}
+
+#define OBE_DIM_CASE_PICK(dd) case dd: k_sys_pick<dd><<<grid, OBE_PICK_WARPS * 32, 0, st>>>(g_parked.a, pk); break;
+
+int obe_resample_pick(const double* u_host, int k, double* draws_dev, void* const* peer_bufs, int rank, int world,
+                      uint64_t epoch, void* stream) {
+    if (!g_parked.parked) return obe_fail("obe_resample_pick: no parked resample (obe_resample_defer + a systematic resample first)%s%s");
+    if (!u_host || k < 1 || k > OBE_MAX_DRAWS) return obe_fail("obe_resample_pick: 1..128 draws%s%s");
+    ObePickArgs pk;
+    memset(&pk, 0, sizeof(pk));
+    pk.k = k; pk.ldk = k; pk.out = draws_dev;
+    if (peer_bufs) {
+        if ((int64_t)k * g_parked.d > 1024) return obe_fail("peer draws: n_draws * n_params <= 1024%s%s");
+        if (epoch == 0) return obe_fail("peer exchange epochs start at 1%s%s");
+        if (fill_peers(peer_bufs, rank, world, pk.peers)) return -1;
+        pk.peer_world = world; pk.peer_rank = rank; pk.peer_epoch = epoch; pk.peer_counter = g_parked.counter;
+    } else if (!draws_dev) {
+        return obe_fail("null argument%s%s");
+    }
+    for (int i = 0; i < k; ++i) pk.u[i] = u_host[i];
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (k + OBE_PICK_WARPS - 1) / OBE_PICK_WARPS;
+    switch (g_parked.d) {
+        OBE_DIM_CASE_PICK(1) OBE_DIM_CASE_PICK(2) OBE_DIM_CASE_PICK(3) OBE_DIM_CASE_PICK(4)
+        OBE_DIM_CASE_PICK(5) OBE_DIM_CASE_PICK(6) OBE_DIM_CASE_PICK(7) OBE_DIM_CASE_PICK(8)
+        default: return obe_fail("n_params must be 1..8%s%s");
+    }
+    OBE_LAUNCH_CHECK("k_sys_pick");
+    if (peer_bufs && draws_dev) {
+        k_peer_collect_draws<<<1, 128, 0, st>>>(pk.peers.p[rank], world, epoch, draws_dev, k * g_parked.d);
+        OBE_LAUNCH_CHECK("k_peer_collect_draws");
+    }
+    return 0;
+}
+
+int obe_resample_emit(void* stream) {
+    if (!g_parked.parked) return obe_fail("obe_resample_emit: no parked resample%s%s");
+    g_parked.parked = false;
+    cudaStream_t st = (cudaStream_t)stream;
+    // The streaming kernel is persistent and fills every CTA slot of the machine; the selection kernels of the other
+    // stream get in while it ramps up (pick) and as soon as its first CTAs run out of units (utility) -- the units are
+    // handed out dynamically, so CTAs retire one by one over the last ~30 us instead of all at once.  Leaving slots
+    // free from the start (resample_reserve_ctas > 0) was measured and costs more than it hides: 0 / 24 / 48 slots ->
+    // 1.611 / 1.629 / 1.648 ms per cycle at 1e8 particles, 0.2783 / 0.2789 / 0.2800 ms at 1.25e7.
+    int grid = g_parked.grid;
+    if (grid == obe_sms() * OBE_WR_BLOCKS(g_parked.d)) grid -= (int)g_resample_reserve;
+    if (grid < 2) grid = 2;
+    OBE_DIM_SWITCH_WR(g_parked.d, grid, st, g_parked.a)
+    OBE_LAUNCH_CHECK("k_sys_resample_warp");
+    return 0;
+}
+
+// `to` waits for everything enqueued on `from` so far (one cached event per thread and direction)
+static thread_local cudaEvent_t g_fork_ev[2] = {nullptr, nullptr};
+static int stream_edge(int which, void* from, void* to) {
+    if (!g_fork_ev[which]) OBE_CUDA(cudaEventCreateWithFlags(&g_fork_ev[which], cudaEventDisableTiming));
+    OBE_CUDA(cudaEventRecord(g_fork_ev[which], (cudaStream_t)from));
+    OBE_CUDA(cudaStreamWaitEvent((cudaStream_t)to, g_fork_ev[which], 0));
+    return 0;
+}
+int obe_stream_fork(void* main_stream, void* side_stream) { return stream_edge(0, main_stream, side_stream); }
+int obe_stream_join(void* main_stream, void* side_stream) { return stream_edge(1, side_stream, main_stream); }
 
 int64_t obe_comb_count(double c, double u0, int64_t n_total) {
     // host twin of the device comb count: #{i in [0,n) : (i + u0) * (1/n) < c}, same IEEE operations

@@ -138,6 +138,15 @@ class OptBayesExpt(ParticlePDF):
         self._a_pivot = _lib.ArgArray(_lib.MAX_PARAMS)
         self._a_u = None
         self._var_noise_cache = None
+        #: early select: when a systematic resample is followed by the selection (run_cycle_async, or pdf_update
+        #: with ``eager_select``), the K draws are taken from the resample PLAN (offspring slot floor(u*N)) before
+        #: the cloud is streamed, and the utility pass overlaps the resample on a second stream
+        self.early_select = True
+        #: pdf_update: a resample also starts the selection the next opt_setting()/good_setting() will ask for
+        #: (the K uniforms are drawn from ``self.rng`` at that moment instead of inside opt_setting)
+        self.eager_select = False
+        self._select_ready = False
+        self._side = None                 # (torch stream object, raw handle) of the selection stream
 
     # -- the reference rebinds `parameters` to `particles` in pdf_update (obe_base.py:185,395);
     #    here it is a live alias, which removes the stale-alias quirk after resample()/set_pdf()
@@ -145,8 +154,13 @@ class OptBayesExpt(ParticlePDF):
     def parameters(self):
         return self.particles
 
+    def _invalidate(self, particles=False, weights=True):
+        ParticlePDF._invalidate(self, particles, weights)
+        self._select_ready = False        # a prefetched selection belongs to the cloud it was drawn from
+
     def set_n_draws(self, n_draws=None):
         """obe_base.py:274-296."""
+        self._select_ready = False
         if n_draws == 'default':
             self.N_DRAWS = DEFAULT_N_DRAWS
         elif n_draws:
@@ -154,6 +168,7 @@ class OptBayesExpt(ParticlePDF):
         return self.N_DRAWS
 
     def set_pdf(self, samples, weights=None):
+        self._select_ready = False
         noise_index = self._noise_index
         ParticlePDF.set_pdf(self, samples, weights)
         self._noise_index = noise_index
@@ -299,14 +314,81 @@ class OptBayesExpt(ParticlePDF):
         self._stats = None
         self._moments_valid = True      # on the device: the resample kernel reads them there
         self._weights_lazy = True
+        self.resample_select_async(resample, select)
+
+    def resample_select_async(self, resample=True, select=True):
+        """The part of run_cycle_async after the update: (forced) resample and selection, enqueued without a host
+        synchronisation.  With both on and early select available the K draws come from the resample plan and the
+        utility pass overlaps the resample on the selection stream."""
         if resample:
             if self.resampling == 'multinomial':
                 raise ValueError('run_cycle_async needs a device-side resampler (systematic or multinomial_device)')
+            if select and self._early_select_ok():
+                self._resample_with_select()
+                self._select_ready = False          # (the result is the caller's: best_index_dev)
+                self.just_resampled = True
+                return
             self.resample()
             self.just_resampled = True
             self._enforce_constraints_async()
         if select:
             self._utility_dev_run()
+
+    # ---- early select -------------------------------------------------------------------------
+    def _early_select_ok(self):
+        """Can the selection be taken from the resample plan?  Needs the one-kernel systematic resample, offspring
+        that keep their uniform weights (no constraint mask), a utility that reads nothing the resample changes
+        (no noise parameter), and no host-side upload inside the utility call (full KLD noise)."""
+        if not self.early_select or self.resampling != 'systematic' or self._utility_code == 3:
+            return False
+        if not (1 <= self.N_DRAWS <= _lib.MAX_DRAWS) or self._noise_from_stats():
+            return False
+        return self._constraint_masks() == (0, 0)
+
+    def _side_stream(self):
+        side = self._side
+        if side is None:
+            st = self._torch.cuda.Stream(device=self._buf.device, priority=-1)
+            side = self._side = (st, C.c_void_p(st.cuda_stream))
+        return side
+
+    def _pick_draws(self, u, draws, side_raw):
+        """K offspring of the parked resample -> draws (d, K), on the selection stream."""
+        self._check(self._lib.obe_resample_pick(_lib.dptr(u), int(len(u)), C.c_void_p(draws.data_ptr()), None, 0, 0, 0,
+                                                side_raw))
+
+    def _resample_with_select(self):
+        """resample() with the following selection started from its plan: plan kernel -> [selection stream: pick the
+        K draws, utility, argmax] || [main stream: stream the cloud] -> join.  No host synchronisation."""
+        lib = self._lib
+        main = self._stream()
+        side_obj, side = self._side_stream()
+        lib.obe_resample_defer(1)
+        try:
+            self.resample()                          # plan kernel only: the streaming kernel is parked
+        except Exception:
+            lib.obe_resample_defer(0)
+            raise
+        self._check(lib.obe_stream_fork(main, side))
+        dd = self._draws_buffer()
+        u = self.rng.random(self.N_DRAWS)
+        self._pick_draws(u, dd, side)
+        self._stream_override = side
+        try:
+            self._utility_dev_run(draws=dd, side=side_obj)
+        finally:
+            self._stream_override = None
+        # (the streaming kernel leaves a few CTA slots free -- resample_reserve_ctas -- through which the selection
+        # kernels run while it streams; it is persistent and would otherwise keep them out until it ends)
+        self._check(lib.obe_resample_emit(main))
+        self._check(lib.obe_stream_join(main, side))
+        self._select_ready = True
+
+    def _do_resample(self):
+        if self.eager_select and self._early_select_ok():
+            self._resample_with_select()
+        else:
+            self.resample()
 
     @property
     def best_index_dev(self):
@@ -379,13 +461,19 @@ class OptBayesExpt(ParticlePDF):
     def _noise_from_stats(self):
         return False
 
-    def _utility_dev_run(self):
-        """draws -> utility over the grid -> argmax, all on the device; returns nothing."""
-        torch = self._torch
+    def _draws_buffer(self):
         dd = getattr(self, '_draws_dev', None)
         if dd is None or dd.shape[1] != self.N_DRAWS:
-            dd = self._draws_dev = torch.empty((self.n_dims, self.N_DRAWS), dtype=torch.float64, device=self._buf.device)
-        draws = self._randdraw_dev(self.N_DRAWS, out=dd)
+            dd = self._draws_dev = self._torch.empty((self.n_dims, self.N_DRAWS), dtype=self._torch.float64,
+                                                     device=self._buf.device)
+        return dd
+
+    def _utility_dev_run(self, draws=None, side=None):
+        """draws -> utility over the grid -> argmax, all on the device; returns nothing.  ``draws``: already on the
+        device (early select); ``side``: the torch stream the kernels go to when it is not the current one."""
+        torch = self._torch
+        if draws is None:
+            draws = self._randdraw_dev(self.N_DRAWS, out=self._draws_buffer())
         n_set = len(self.setting_indices)
         if self._noise_from_stats():
             if not self._moments_valid:     # (valid-on-device is enough: the kernel reads the stats block itself)
@@ -406,7 +494,11 @@ class OptBayesExpt(ParticlePDF):
             cost_arr = np.array(np.broadcast_to(np.asarray(cost, dtype=np.float64), (n_set,)))
             if self._cost_dev is None:
                 self._cost_dev = torch.empty(n_set, dtype=torch.float64, device=self._buf.device)
-            self._cost_dev.copy_(torch.from_numpy(np.ascontiguousarray(cost_arr)))
+            if side is not None:
+                with torch.cuda.stream(side):            # the upload must precede the kernel on ITS stream
+                    self._cost_dev.copy_(torch.from_numpy(np.ascontiguousarray(cost_arr)))
+            else:
+                self._cost_dev.copy_(torch.from_numpy(np.ascontiguousarray(cost_arr)))
             cost_ptr = C.c_void_p(self._cost_dev.data_ptr())
         self._check(self._lib.obe_utility(self._model, C.c_void_p(draws.data_ptr()), int(self.N_DRAWS),
                                           C.c_void_p(self._settings_dev.data_ptr()), self._lds, n_set, self._cons_arr,
@@ -462,7 +554,10 @@ class OptBayesExpt(ParticlePDF):
 
     def opt_setting(self):
         """Setting with the maximum utility (obe_base.py:733-756)."""
-        self._utility_dev_run()
+        if self._select_ready:
+            self._select_ready = False          # started by the resample (eager_select): only the argmax is fetched
+        else:
+            self._utility_dev_run()
         self._best_host.copy_(self._best_dev, non_blocking=True)
         self._torch.cuda.current_stream().synchronize()
         bestindex = int(self._best_host_np[0])
@@ -473,7 +568,10 @@ class OptBayesExpt(ParticlePDF):
         """Setting drawn with probability ~ utility**pickiness (obe_base.py:758-789)."""
         if pickiness is None:
             pickiness = self.pickiness
-        self._utility_dev_run()
+        if self._select_ready:
+            self._select_ready = False
+        else:
+            self._utility_dev_run()
         u = float(self.rng.random())
         self._check(self._lib.obe_pick(C.c_void_p(self._utility_dev.data_ptr()), len(self.setting_indices),
                                        float(pickiness), u, C.c_void_p(self._pick_dev.data_ptr()),

@@ -56,6 +56,7 @@ class ParticlePDF:
     def _install(self, samples):
         self._buf = ParticleBuffers(samples, self._device, capacity=getattr(self, '_capacity', None))
         self._dev_index = self._buf.device.index
+        self._stream_override = None      # raw stream handle the C calls go to instead of torch's current stream
         self._alt = None
         self.n_particles = self._buf.n
         self.n_dims = self._buf.d
@@ -71,6 +72,9 @@ class ParticlePDF:
         self._pivot = p[:, :min(self.n_particles, 65536)].mean(dim=1).cpu().numpy().astype(np.float64)
 
     def _stream(self):
+        over = self._stream_override
+        if over is not None:
+            return over
         return _lib.raw_stream(self._torch, self._dev_index)
 
     def _cs(self, buf=None):
@@ -278,13 +282,17 @@ class ParticlePDF:
             warnings.warn("\nParticle filter rejected > 90 % of particles. "
                           f"N_eff = {n_eff:.2f}. "
                           "Particle impoverishment may lead to errors.", RuntimeWarning)
-            self.resample()
+            self._do_resample()
             self.just_resampled = True
         elif n_eff / self.n_particles < self.tuning_parameters['resample_threshold']:
-            self.resample()
+            self._do_resample()
             self.just_resampled = True
         else:
             self.just_resampled = False
+
+    def _do_resample(self):
+        """The resample the test decided on (a hook: OptBayesExpt may start the selection with it)."""
+        self.resample()
 
     # ------------------------------------------------------------------------------------------
     # resampling (particlepdf.py:260-345)

@@ -404,10 +404,10 @@ class ShardedOptBayesExpt(OptBayesExpt):
         if n_eff < 0.1 * self.n_total:
             warnings.warn(f"\nParticle filter rejected > 90 % of particles. N_eff = {n_eff:.2f}. "
                           "Particle impoverishment may lead to errors.", RuntimeWarning)
-            self.resample()
+            self._do_resample()
             self.just_resampled = True
         elif n_eff / self.n_total < self.tuning_parameters['resample_threshold']:
-            self.resample()
+            self._do_resample()
             self.just_resampled = True
         else:
             self.just_resampled = False
@@ -458,9 +458,24 @@ class ShardedOptBayesExpt(OptBayesExpt):
         self._comm.allreduce_sum(draws)
         return draws
 
+    def _pick_draws(self, u, draws, side_raw):
+        """Early select over the sharded cloud: every rank produces the offspring it owns.  Peer mode: the owners store
+        into every rank's buffer and a one-CTA kernel collects; collective mode: zeros elsewhere + all-reduce, both on
+        the selection stream."""
+        if self._peer is not None and len(u) * self.n_dims <= 1024:
+            self._check(self._lib.obe_resample_pick(_lib.dptr(u), int(len(u)), C.c_void_p(draws.data_ptr()),
+                                                    self._peer.ptrs, self._comm.rank, self._comm.world,
+                                                    self._peer.next_epoch(1), side_raw))
+            return
+        self._check(self._lib.obe_resample_pick(_lib.dptr(u), int(len(u)), C.c_void_p(draws.data_ptr()), None, 0, 0, 0,
+                                                side_raw))
+        with self._torch.cuda.stream(self._side_stream()[0]):
+            self._comm.allreduce_sum(draws)
+
     # ---- utility over this rank's slice of the grid
-    def _utility_dev_run(self):
-        draws = self._randdraw_dev(self.N_DRAWS)
+    def _utility_dev_run(self, draws=None, side=None):
+        if draws is None:
+            draws = self._randdraw_dev(self.N_DRAWS)
         n_loc = self._s_hi - self._s_lo
         stats_ptr = None
         if self._noise_from_stats():
@@ -477,7 +492,11 @@ class ShardedOptBayesExpt(OptBayesExpt):
         if not (np.isscalar(cost) and float(cost) == 1.0):
             import torch
             cost_arr = np.array(np.broadcast_to(np.asarray(cost, dtype=np.float64), (len(self.setting_indices),)))
-            self._cost_dev = torch.from_numpy(cost_arr[self._s_lo:self._s_hi].copy()).to(self._buf.device)
+            if side is not None:
+                with torch.cuda.stream(side):
+                    self._cost_dev = torch.from_numpy(cost_arr[self._s_lo:self._s_hi].copy()).to(self._buf.device)
+            else:
+                self._cost_dev = torch.from_numpy(cost_arr[self._s_lo:self._s_hi].copy()).to(self._buf.device)
             cost_ptr = C.c_void_p(self._cost_dev.data_ptr())
         settings_ptr = C.c_void_p(self._settings_dev.data_ptr() + 8 * self._s_lo)
         util_ptr = C.c_void_p(self._utility_dev.data_ptr() + 8 * self._s_lo)
@@ -499,7 +518,10 @@ class ShardedOptBayesExpt(OptBayesExpt):
 
     def opt_setting(self):
         import torch
-        self._utility_dev_run()
+        if self._select_ready:
+            self._select_ready = False
+        else:
+            self._utility_dev_run()
         if self._replicate_grid:
             best = int(self._best_dev.cpu()[0])
             self.last_setting_index = best
@@ -515,7 +537,10 @@ class ShardedOptBayesExpt(OptBayesExpt):
 
     def utility(self):
         import torch
-        self._utility_dev_run()
+        if self._select_ready:
+            self._select_ready = False
+        else:
+            self._utility_dev_run()
         n_set = len(self.setting_indices)
         world = self._comm.world
         if self._replicate_grid:
@@ -561,6 +586,14 @@ class ShardedOptBayesExpt(OptBayesExpt):
         planned resample -> owner-written draws -> all-reduce -> utility over this rank's grid slice."""
         OptBayesExpt.run_cycle_async(self, measurement_record, resample=False, select=False)
         self._make_plan()
+        self.resample_select_async(resample, select)
+
+    def resample_select_async(self, resample=True, select=True):
+        if resample and select and self._early_select_ok():
+            self._resample_with_select()
+            self._select_ready = False
+            self.just_resampled = True
+            return
         if resample:
             self.resample()
             self.just_resampled = True

@@ -202,6 +202,67 @@ def _worker_noise(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _worker_early(rank, world, port, out):
+    """early select over two shards: run_cycle_async takes the K draws from the resample plan (every rank the slots it
+    owns, exchanged by peer writes or an all-reduce) and overlaps the utility pass with the resample"""
+    import warnings
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    _init_group(rank, world)
+    try:
+        import optbayesexpt_b200 as obe
+        from optbayesexpt_b200.sharded import ShardedOptBayesExpt
+        from oracle.scenarios import build_inputs, by_name
+        sc = by_name('c1_find_peak')
+        n = 60000
+        inp = build_inputs(sc, n)
+        cut = [0, 26000, n]
+        lo, hi = cut[rank], cut[rank + 1]
+        kw = dict(scale=False, default_noise_std=500.0, seed=77)
+        eng = ShardedOptBayesExpt('lorentzian_hwhm', inp['setting_values'], inp['prior'][:, lo:hi], inp['cons'], **kw)
+        ref = obe.OptBayesExpt('lorentzian_hwhm', inp['setting_values'], inp['prior'], inp['cons'], **kw)
+        assert eng._early_select_ok() and ref._early_select_ok()
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', RuntimeWarning)
+            for cycle, y in enumerate((49600.0, 49900.0, 50100.0)):
+                rec = ((3.0 + 0.1 * cycle,), y, 500.0)
+                eng.rng = np.random.default_rng(40 + cycle)
+                ref.rng = np.random.default_rng(40 + cycle)
+                twin = np.random.default_rng(40 + cycle)
+                eng._philox_seed = ref._philox_seed = 4242 + cycle
+                eng._epoch = ref._epoch = cycle
+                eng.run_cycle_async(rec)
+                ref.run_cycle_async(rec)
+                twin.random()
+                u = twin.random(eng.N_DRAWS)
+                slots = np.minimum((u * n).astype(np.int64), n - 1)
+                counts = eng.shard_counts
+                assert counts.sum() == n
+                start = int(counts[:rank].sum())
+                draws = eng._draws_dev.cpu().numpy()
+                mine = (slots >= start) & (slots < start + counts[rank])
+                # the draws this rank owns are ITS offspring, bit for bit; all ranks hold all draws
+                np.testing.assert_array_equal(draws[:, mine], eng.particles[:, slots[mine] - start])
+                want = ref._draws_dev.cpu().numpy()
+                spread = ref.particles.std(axis=1, keepdims=True)
+                err = np.abs(draws - want) / (np.abs(want) * 1e-12 + spread * 1e-9)
+                assert err.max() <= 1.0, f'sharded draws differ from the single cloud: {err.max():.3g}'
+                assert int(eng.best_index_dev.cpu()[0]) == int(ref.best_index_dev.cpu()[0])
+                got, wantp = eng.particles, ref.particles[:, start:start + eng.n_particles]
+                perr = np.abs(got - wantp) / (np.abs(wantp) * 1e-12 + spread * 1e-9)
+                assert perr.max() <= 1.0
+        eng._fetch_plan()
+        out.put((rank, 'ok'))
+    except Exception as exc:  # pragma: no cover
+        import traceback
+        out.put((rank, traceback.format_exc()))
+        raise exc
+    finally:
+        dist.destroy_process_group()
+
+
 def _spawn(worker, peer, backend='gloo'):
     """Two ranks on the one GPU (gloo carries the host-side collectives).  peer='1': the stats and the draws travel
     by peer writes into CUDA-IPC-mapped buffers + flags instead of collectives (the NVLink path of a real node).
@@ -236,17 +297,22 @@ def test_two_shards_match_single_cloud(obe_lib, peer):
     _spawn(_worker, peer)
 
 
+@pytest.mark.parametrize('peer', ['0', '1'], ids=['collectives', 'peer_exchange'])
+def test_two_shards_early_select(obe_lib, peer):
+    _spawn(_worker_early, peer)
+
+
 def _two_gpus():
     import torch
     return torch.cuda.is_available() and torch.cuda.device_count() >= 2
 
 
 @pytest.mark.parametrize('peer', ['0', '1'], ids=['nccl_collectives', 'nvlink_peer_exchange'])
-@pytest.mark.parametrize('worker', ['base', 'noise'])
+@pytest.mark.parametrize('worker', ['base', 'noise', 'early'])
 def test_two_gpus_nccl(obe_lib, peer, worker):
     """The same two-shard comparisons on TWO GPUs: NCCL collectives / peer buffers mapped over NVLink (CUDA IPC between
     devices).  Skipped on a one-GPU box (the driver's GPU test box); bench.py --gpus N runs the same invariance check
     on every multi-GPU run (`invariance` in its JSON line)."""
     if not _two_gpus():
         pytest.skip('needs >= 2 GPUs')
-    _spawn(_worker if worker == 'base' else _worker_noise, peer, backend='nccl')
+    _spawn({'base': _worker, 'noise': _worker_noise, 'early': _worker_early}[worker], peer, backend='nccl')
