@@ -624,7 +624,7 @@ def main():
     t_res = float(np.mean([ev[t][1].elapsed_time(ev[t][2]) for t in range(args.steps)]))
     # the same cycle with the selection serialised after the resample (early select off): the per-phase split
     eng.early_select = False
-    sv = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    sv = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     for t in range(2):
         eng.run_cycle_async(fixed[t])
     barrier()
@@ -633,7 +633,13 @@ def main():
     for t in range(args.steps):
         rec = fixed[args.warmup + t]
         sv[t][0].record()
-        eng.run_cycle_async(rec, resample=False, select=False)
+        if world > 1:                    # the update kernel alone, then the stats exchange + shard plan
+            obe.OptBayesExpt.run_cycle_async(eng, rec, resample=False, select=False)
+            sv[t][4].record()
+            eng._make_plan()
+        else:
+            eng.run_cycle_async(rec, resample=False, select=False)
+            sv[t][4].record()
         sv[t][1].record()
         eng.resample_select_async(True, False)
         sv[t][2].record()
@@ -644,6 +650,7 @@ def main():
     eng.early_select = True
     ser = [float(np.mean([sv[t][i].elapsed_time(sv[t][i + 1]) for t in range(args.steps)])) for i in range(3)]
     ser.append(s_start.elapsed_time(s_stop) / args.steps)
+    ser.append(float(np.mean([sv[t][4].elapsed_time(sv[t][1]) for t in range(args.steps)])))   # exchange + shard plan
     if world > 1:
         tt = torch.tensor([ms_total, t_upd, t_res] + ser, dtype=torch.float64, device='cuda')
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -767,7 +774,8 @@ def main():
         'early_select': early,
         'serialised_cycle': {'note': 'same cycle, selection AFTER the resample on one stream (early select off)',
                              'ms_per_step': ser[3],
-                             'kernels_ms': {'update': ser[0], 'resample': ser[1], 'draw+utility+argmax': ser[2]}},
+                             'kernels_ms': {'update': ser[0], 'resample': ser[1], 'draw+utility+argmax': ser[2]},
+                             'stats_exchange_and_shard_plan_ms': ser[4] if world > 1 else None},
         'kernels_gbs': {'update': b_upd / world / (t_upd * 1e-3) / 1e9, 'resample': gbs_res},
         'exchange': None if world == 1 else ('peer (CUDA IPC over NVLink)' if getattr(eng, '_peer', None) is not None
                                              else 'nccl'),

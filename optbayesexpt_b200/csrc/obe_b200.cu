@@ -2012,70 +2012,94 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_bcompact(const int* __rest
 // optbayesexpt_b200/sharded.py (combine_stats, moments_from, shard_slot_bounds), which the tests
 // compare it with.
 // ---------------------------------------------------------------------------------------------
-__device__ void shard_plan_body(const double* __restrict__ gathered, int rank, int world, int d, double u0,
-                                long long n_total, double a_param, int lazy, long long cap_out,
-                                double* __restrict__ plan, double* __restrict__ stats_local,
-                                long long* __restrict__ n_out_dev) {
+// A block of OBE_STATS_LEN (64) threads.  Thread t sums column t of the gathered blocks in rank order (the same
+// association as the host's combine_stats), the comb counts of the shard boundaries run one per thread on the
+// second warp while thread 0 does the Cholesky factor, and only the short sequential pieces (the exclusive scan of
+// G totals, the monotone clamp of the G bounds) are left to one thread -- reading shared memory, not global: the
+// first version walked everything with a single thread through global read-modify-writes, ~40 us at 8 ranks.
+__device__ void shard_plan_block(const double* __restrict__ gathered, int rank, int world, int d, double u0,
+                                 long long n_total, double a_param, int lazy, long long cap_out,
+                                 double* __restrict__ plan, double* __restrict__ stats_local,
+                                 long long* __restrict__ n_out_dev) {
+    __shared__ double gs_s[OBE_STATS_LEN];
+    __shared__ double tot_s[OBE_MAX_SHARDS], off_s[OBE_MAX_SHARDS + 1];
+    __shared__ long long end_s[OBE_MAX_SHARDS];
+    const int t = threadIdx.x;
     const int nm2 = d * (d + 1) / 2;
-    double* gs = plan + OBE_PL_GSTATS;
-    for (int q = 0; q < OBE_STATS_LEN; ++q) gs[q] = 0.0;
-    double acc = 0.0;
-    for (int g = 0; g < world; ++g) {                 // the canonical inter-GPU exclusive scan
-        const double* st = gathered + (long long)g * OBE_STATS_LEN;
-        plan[OBE_PL_PRE_OFF + g] = acc;
-        plan[OBE_PL_PRE_TOT + g] = st[OBE_ST_TOTAL];
-        acc = acc + st[OBE_ST_TOTAL];
-        gs[OBE_ST_SUMSQ] += st[OBE_ST_SUMSQ];
-        gs[OBE_ST_SUMT] += st[OBE_ST_SUMT];
-        gs[OBE_ST_NZERO] += st[OBE_ST_NZERO];
-        for (int j = 0; j < d; ++j) gs[OBE_ST_M1 + j] += st[OBE_ST_M1 + j];
-        for (int j = 0; j < nm2; ++j) gs[OBE_ST_M2 + j] += st[OBE_ST_M2 + j];
-        for (int c = 0; c < OBE_MAX_CH; ++c) gs[OBE_ST_NOISE + c] += st[OBE_ST_NOISE + c];
+    {
+        double acc = 0.0;
+        for (int g = 0; g < world; ++g) acc = acc + gathered[(long long)g * OBE_STATS_LEN + t];
+        const bool summed = t == OBE_ST_SUMSQ || t == OBE_ST_SUMT || t == OBE_ST_NZERO ||
+                            (t >= OBE_ST_M1 && t < OBE_ST_M1 + d) || (t >= OBE_ST_M2 && t < OBE_ST_M2 + nm2) ||
+                            (t >= OBE_ST_NOISE && t < OBE_ST_NOISE + OBE_MAX_CH);
+        double v = summed ? acc : 0.0;
+        if (t >= OBE_ST_PIVOT && t < OBE_ST_PIVOT + d) v = gathered[t];          // rank 0's pivot (common to all)
+        gs_s[t] = v;
+        for (int g = t; g < world; g += OBE_STATS_LEN) tot_s[g] = gathered[(long long)g * OBE_STATS_LEN + OBE_ST_TOTAL];
     }
-    const double total = acc;
-    for (int j = 0; j < d; ++j) gs[OBE_ST_PIVOT + j] = gathered[OBE_ST_PIVOT + j];
-    gs[OBE_ST_TOTAL] = total;
-    gs[OBE_ST_INVS] = lazy ? 1.0 / total : 1.0;
-    gs[OBE_ST_NEFF] = (total * total) / gs[OBE_ST_SUMSQ];
-    stats_local[OBE_ST_INVS] = gs[OBE_ST_INVS];       // the GLOBAL normaliser for the next update
-    // global mean, Cholesky factor of (1 - a^2) * cov
-    const double st = gs[OBE_ST_SUMT], fact = st - gs[OBE_ST_SUMSQ] / st, shrink = 1.0 - a_param * a_param;
-    double cov[OBE_MAX_DIMS][OBE_MAX_DIMS], L[OBE_MAX_DIMS][OBE_MAX_DIMS];
-    int q = 0;
-    for (int j = 0; j < d; ++j) {
-        plan[OBE_PL_MEAN + j] = gs[OBE_ST_PIVOT + j] + gs[OBE_ST_M1 + j] / st;
-        for (int k = j; k < d; ++k) {
-            const double c = (gs[OBE_ST_M2 + q] - gs[OBE_ST_M1 + j] * gs[OBE_ST_M1 + k] / st) / fact;
-            cov[j][k] = cov[k][j] = shrink * c;
-            ++q;
+    __syncthreads();
+    if (t == 0) {
+        double acc = 0.0;
+        for (int g = 0; g < world; ++g) {                 // the canonical inter-GPU exclusive scan
+            off_s[g] = acc;
+            acc = acc + tot_s[g];
         }
+        off_s[world] = acc;
+        gs_s[OBE_ST_TOTAL] = acc;
+        gs_s[OBE_ST_INVS] = lazy ? 1.0 / acc : 1.0;
+        gs_s[OBE_ST_NEFF] = (acc * acc) / gs_s[OBE_ST_SUMSQ];
     }
-    for (int j = 0; j < d; ++j)
-        for (int k = 0; k < d; ++k) L[j][k] = 0.0;
-    for (int j = 0; j < d; ++j) {
-        double sdiag = cov[j][j];
-        for (int k = 0; k < j; ++k) sdiag -= L[j][k] * L[j][k];
-        const double dj = sdiag > 0.0 ? sqrt(sdiag) : 0.0;
-        L[j][j] = dj;
-        for (int i = j + 1; i < d; ++i) {
-            double t = cov[i][j];
-            for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
-            L[i][j] = dj > 0.0 ? t / dj : 0.0;
-        }
+    __syncthreads();
+    const double total = off_s[world];
+    plan[OBE_PL_GSTATS + t] = gs_s[t];
+    for (int g = t; g < world; g += OBE_STATS_LEN) {
+        plan[OBE_PL_PRE_OFF + g] = off_s[g];
+        plan[OBE_PL_PRE_TOT + g] = tot_s[g];
     }
-    for (int k = 0; k < d; ++k)
-        for (int j = 0; j < d; ++j) plan[OBE_PL_FACTOR + k * d + j] = L[j][k];
-    // slot bounds of every shard: H_0 = 0, H_G = n_total, monotone
     const double nd = (double)n_total, inv_n = 1.0 / nd, tol = 2e-15 * nd, inv_total = 1.0 / total;
+    if (t >= 32) {                                        // raw slot bound between shards g and g+1
+        for (int g = t - 32; g + 1 < world; g += 32)
+            end_s[g] = (long long)comb_count_d(obe_mul(off_s[g + 1], inv_total), u0, inv_n, nd, tol);
+    }
+    if (t == 0) {
+        stats_local[OBE_ST_INVS] = gs_s[OBE_ST_INVS];     // the GLOBAL normaliser for the next update
+        // global mean, Cholesky factor of (1 - a^2) * cov
+        const double st = gs_s[OBE_ST_SUMT], fact = st - gs_s[OBE_ST_SUMSQ] / st, shrink = 1.0 - a_param * a_param;
+        double cov[OBE_MAX_DIMS][OBE_MAX_DIMS], L[OBE_MAX_DIMS][OBE_MAX_DIMS];
+        int q = 0;
+        for (int j = 0; j < d; ++j) {
+            plan[OBE_PL_MEAN + j] = gs_s[OBE_ST_PIVOT + j] + gs_s[OBE_ST_M1 + j] / st;
+            for (int k = j; k < d; ++k) {
+                const double c = (gs_s[OBE_ST_M2 + q] - gs_s[OBE_ST_M1 + j] * gs_s[OBE_ST_M1 + k] / st) / fact;
+                cov[j][k] = cov[k][j] = shrink * c;
+                ++q;
+            }
+        }
+        for (int j = 0; j < d; ++j)
+            for (int k = 0; k < d; ++k) L[j][k] = 0.0;
+        for (int j = 0; j < d; ++j) {
+            double sdiag = cov[j][j];
+            for (int k = 0; k < j; ++k) sdiag -= L[j][k] * L[j][k];
+            const double dj = sdiag > 0.0 ? sqrt(sdiag) : 0.0;
+            L[j][j] = dj;
+            for (int i = j + 1; i < d; ++i) {
+                double tt = cov[i][j];
+                for (int k = 0; k < j; ++k) tt -= L[i][k] * L[j][k];
+                L[i][j] = dj > 0.0 ? tt / dj : 0.0;
+            }
+        }
+        for (int k = 0; k < d; ++k)
+            for (int j = 0; j < d; ++j) plan[OBE_PL_FACTOR + k * d + j] = L[j][k];
+    }
+    __syncthreads();
+    if (t != 0) return;
+    // slot bounds of every shard: H_0 = 0, H_G = n_total, monotone
     long long prev = 0, mine0 = 0, mine1 = n_total;
     double post_acc = 0.0;
     const double wv = 1.0 / nd;
     for (int g = 0; g < world; ++g) {
         long long end = n_total;
-        if (g + 1 < world) {
-            end = (long long)comb_count_d(obe_mul(plan[OBE_PL_PRE_OFF + g + 1], inv_total), u0, inv_n, nd, tol);
-            end = min(max(end, prev), n_total);
-        }
+        if (g + 1 < world) end = min(max(end_s[g], prev), n_total);
         if (g == rank) { mine0 = prev; mine1 = end; }
         plan[OBE_PL_COUNTS + g] = (double)(end - prev);
         plan[OBE_PL_POST_OFF + g] = post_acc;
@@ -2084,7 +2108,7 @@ __device__ void shard_plan_body(const double* __restrict__ gathered, int rank, i
         prev = end;
     }
     plan[OBE_PL_POST_TOTAL] = post_acc;
-    plan[OBE_PL_OFFSET] = plan[OBE_PL_PRE_OFF + rank];
+    plan[OBE_PL_OFFSET] = off_s[rank];
     plan[OBE_PL_TOTAL] = total;
     plan[OBE_PL_U0] = u0;
     plan[OBE_PL_NTOTAL] = nd;
@@ -2099,12 +2123,12 @@ __device__ void shard_plan_body(const double* __restrict__ gathered, int rank, i
     if (n_out_dev) *n_out_dev = cnt;
 }
 
-__global__ void k_shard_plan(const double* __restrict__ gathered, int rank, int world, int d, double u0,
-                             long long n_total, double a_param, int lazy, long long cap_out,
-                             double* __restrict__ plan, double* __restrict__ stats_local,
-                             long long* __restrict__ n_out_dev) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    shard_plan_body(gathered, rank, world, d, u0, n_total, a_param, lazy, cap_out, plan, stats_local, n_out_dev);
+__global__ void __launch_bounds__(OBE_STATS_LEN) k_shard_plan(const double* __restrict__ gathered, int rank, int world,
+                                                              int d, double u0, long long n_total, double a_param,
+                                                              int lazy, long long cap_out, double* __restrict__ plan,
+                                                              double* __restrict__ stats_local,
+                                                              long long* __restrict__ n_out_dev) {
+    shard_plan_block(gathered, rank, world, d, u0, n_total, a_param, lazy, cap_out, plan, stats_local, n_out_dev);
 }
 
 // The stats exchange fused into the plan kernel: publish this rank's stats block into every peer's buffer,
@@ -2128,11 +2152,10 @@ __global__ void __launch_bounds__(OBE_STATS_LEN) k_shard_plan_peer(const ObePeer
         if (!obe_flag_wait(obe_peer_flags(mine, 0, parity) + t, epoch)) ok = 0;
     }
     __syncthreads();
-    if (t != 0) return;
     __threadfence_system();
-    shard_plan_body(mine + OBE_PEER_STATS + parity * OBE_PEER_MAX * OBE_STATS_LEN, rank, world, d, u0, n_total, a_param,
-                    lazy, cap_out, plan, stats_local, n_out_dev);
-    if (!ok) { plan[OBE_PL_OVERFLOW] = 2.0; mine[OBE_PEER_ERR] = 1.0; }
+    shard_plan_block(mine + OBE_PEER_STATS + parity * OBE_PEER_MAX * OBE_STATS_LEN, rank, world, d, u0, n_total, a_param,
+                     lazy, cap_out, plan, stats_local, n_out_dev);
+    if (t == 0 && !ok) { plan[OBE_PL_OVERFLOW] = 2.0; mine[OBE_PEER_ERR] = 1.0; }
 }
 
 // the resample kernels stage the tile's particle rows in dynamic shared memory when d <= OBE_STAGE_MAX_D
@@ -3059,7 +3082,7 @@ int obe_shard_plan(const double* gathered_stats_dev, int rank, int world, int d,
     if (!gathered_stats_dev || !plan_dev || !local) return obe_fail("null argument%s%s");
     if (world < 1 || world > OBE_MAX_SHARDS || rank < 0 || rank >= world) return obe_fail("bad rank/world%s%s");
     if (d < 1 || d > OBE_MAX_DIMS) return obe_fail("n_params must be 1..8%s%s");
-    k_shard_plan<<<1, 32, 0, (cudaStream_t)stream>>>(gathered_stats_dev, rank, world, d, u0, n_total, a_param, lazy,
+    k_shard_plan<<<1, OBE_STATS_LEN, 0, (cudaStream_t)stream>>>(gathered_stats_dev, rank, world, d, u0, n_total, a_param, lazy,
                                                     out ? out->ld : (1ll << 62), plan_dev, local->stats_dev,
                                                     out ? (long long*)out->n_dev : nullptr);
     OBE_LAUNCH_CHECK("k_shard_plan");

@@ -120,7 +120,8 @@ def _worker(rank, world, port, out):
         # and it keeps going
         s1 = eng.opt_setting()
         eng.pdf_update((s1, 50000.0, 500.0))
-        assert abs(eng._comm.allreduce_sum(torch.tensor([eng.particle_weights.sum()], dtype=torch.float64)).item()
+        assert abs(eng._comm.allreduce_sum(torch.tensor([eng.particle_weights.sum()], dtype=torch.float64,
+                                                        device=eng._buf.device)).item()
                    - 1.0) < 1e-12
         out.put((rank, 'ok'))
     except Exception as exc:  # pragma: no cover
@@ -189,7 +190,8 @@ def _worker_noise(rank, world, port, out):
         assert perr.max() <= 1.0, f'resampled shard differs from the single cloud: {perr.max():.3g} counts {counts}'
         np.testing.assert_allclose(eng.particle_weights, want_w, rtol=1e-12, atol=0)
         assert (eng.particle_weights == 0).sum() == (want_w == 0).sum()
-        zeros = eng._comm.allreduce_sum(torch.tensor([float((eng.particle_weights == 0).sum())], dtype=torch.float64))
+        zeros = eng._comm.allreduce_sum(torch.tensor([float((eng.particle_weights == 0).sum())], dtype=torch.float64,
+                                                     device=eng._buf.device))
         assert zeros.item() > 0, 'the constraint never bit: the test does not exercise it'
         np.testing.assert_allclose(eng.yvar_noise_model(), ref.yvar_noise_model(), rtol=1e-11)
         np.testing.assert_allclose(eng.mean(), ref.mean(), rtol=1e-10)
