@@ -231,6 +231,61 @@ int obe_resample_pick(const double* u_host, int k, double* draws_dev, void* cons
 int obe_resample_emit(void* stream);
 int obe_stream_fork(void* main_stream, void* side_stream);
 int obe_stream_join(void* main_stream, void* side_stream);
+/* One whole cycle in one call: pdf_update (obe_base.py:340-399) -> [forced systematic resample,
+ * particlepdf.py:260-310] -> [enforce_parameter_constraints as masks] -> utility + argmax of opt_setting
+ * (obe_base.py:628-655,733-756), enqueued with no host work between the launches (a small-cloud cycle is bound by
+ * the host, not by the GPU).  It chains the entry points above exactly as the Python classes do:
+ *   obe_update
+ *   [plan_dev: obe_shard_plan_peer]                                (sharded cloud, peer exchange)
+ *   resample != 0: obe_resample_systematic / _planned;  with select != 0 and no constraint mask the emission is
+ *                  deferred and the K draws are picked from the plan (obe_resample_pick) so that obe_utility runs
+ *                  on side_stream while the cloud streams on `stream`;
+ *                  mask_le | mask_lt != 0: obe_refresh(alt, masks) after the resample
+ *   select != 0 (not early): obe_draw / obe_draw_planned_peer on the live cloud, then obe_utility.
+ * `cloud` is the live buffer, `alt` the output of the resample (the CALLER swaps them after a resampling cycle).
+ * The struct is plain data: fill it once, update the per-cycle fields (setting, y_meas, sigma, pivot, u0, epoch,
+ * u[], peer epochs) and call. */
+typedef struct obe_cycle {
+    obe_model_t model;
+    const obe_cloud_t* cloud;
+    const obe_cloud_t* alt;
+    const double* constants;            /* host */
+    double setting[OBE_MAX_SETTINGS];
+    double y_meas[OBE_MAX_CHANNELS];
+    double sigma[OBE_MAX_CHANNELS];     /* used when has_sigma */
+    double pivot[OBE_MAX_PARAMS];
+    int32_t noise_index[OBE_MAX_CHANNELS];
+    int32_t has_sigma, has_noise_index, n_lik_channels, use_choke;
+    double choke;
+    int32_t resample, scale;            /* resample: 0 = no, 1 = forced systematic */
+    double u0, a_param;
+    uint64_t seed;
+    uint32_t epoch, mask_le, mask_lt;
+    int32_t n_noise;                    /* rows of noise_index the refresh accumulates (noise-parameter engines) */
+    /* sharded (plan_dev != NULL): peer exchange only */
+    double* plan_dev;
+    void* const* peer_bufs;
+    int32_t rank, world;
+    uint64_t epoch_stats, epoch_draws;
+    int64_t n_total;
+    /* selection */
+    int32_t select, k;
+    double u[128];
+    double* draws_dev;                  /* (d, k) */
+    const double* settings_dev;
+    int64_t lds, n_settings;
+    double var_noise[OBE_MAX_CHANNELS];
+    int32_t noise_from_stats;           /* 1: var_noise is ignored, the noise sums of the live stats block are used */
+    int32_t method, log_form, pad0;
+    const double* cost_dev;
+    const double* kld_noise_dev;
+    double* utility_dev;
+    void* best_dev;
+    void* select_scratch_dev;
+    void* stream;
+    void* side_stream;                  /* NULL: no overlap, everything on `stream` */
+} obe_cycle_t;
+int obe_cycle(const obe_cycle_t* c);
 /* randdraw(K) over a sharded cloud: this rank writes the draws it owns (per plan_dev; post=1 uses the
  * post-resample shard totals) and zeros elsewhere; an all-reduce(sum) of draws_dev completes it. */
 int obe_draw_planned(const obe_cloud_t* c, const double* u_host, int k, double* draws_dev,

@@ -49,6 +49,29 @@ class Batch(C.Structure):
                 ('d', C.c_int32), ('tiles', C.c_int32)]
 
 
+class Cycle(C.Structure):
+    """obe_cycle_t (include/obe_b200.h): one whole cycle in one C call."""
+    _fields_ = [('model', C.c_void_p), ('cloud', C.POINTER(Cloud)), ('alt', C.POINTER(Cloud)),
+                ('constants', C.POINTER(C.c_double)),
+                ('setting', C.c_double * MAX_SETTINGS), ('y_meas', C.c_double * MAX_CHANNELS),
+                ('sigma', C.c_double * MAX_CHANNELS), ('pivot', C.c_double * MAX_PARAMS),
+                ('noise_index', C.c_int32 * MAX_CHANNELS),
+                ('has_sigma', C.c_int32), ('has_noise_index', C.c_int32), ('n_lik_channels', C.c_int32),
+                ('use_choke', C.c_int32), ('choke', C.c_double),
+                ('resample', C.c_int32), ('scale', C.c_int32), ('u0', C.c_double), ('a_param', C.c_double),
+                ('seed', C.c_uint64), ('epoch', C.c_uint32), ('mask_le', C.c_uint32), ('mask_lt', C.c_uint32),
+                ('n_noise', C.c_int32),
+                ('plan_dev', C.c_void_p), ('peer_bufs', C.POINTER(C.c_void_p)), ('rank', C.c_int32), ('world', C.c_int32),
+                ('epoch_stats', C.c_uint64), ('epoch_draws', C.c_uint64), ('n_total', C.c_int64),
+                ('select', C.c_int32), ('k', C.c_int32), ('u', C.c_double * 128), ('draws_dev', C.c_void_p),
+                ('settings_dev', C.c_void_p), ('lds', C.c_int64), ('n_settings', C.c_int64),
+                ('var_noise', C.c_double * MAX_CHANNELS), ('noise_from_stats', C.c_int32),
+                ('method', C.c_int32), ('log_form', C.c_int32), ('pad0', C.c_int32),
+                ('cost_dev', C.c_void_p), ('kld_noise_dev', C.c_void_p), ('utility_dev', C.c_void_p),
+                ('best_dev', C.c_void_p), ('select_scratch_dev', C.c_void_p),
+                ('stream', C.c_void_p), ('side_stream', C.c_void_p)]
+
+
 _PD = C.POINTER(C.c_double)
 _PI32 = C.POINTER(C.c_int32)
 _PCLOUD = C.POINTER(Cloud)
@@ -100,6 +123,7 @@ SIGNATURES = {
     'obe_peer_free': (C.c_int, [_VP]),
     'obe_shard_plan_peer': (C.c_int, [C.POINTER(_VP), C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_double, C.c_int64,
                                       C.c_double, C.c_int, _PCLOUD, _PCLOUD, _VP, _VP]),
+    'obe_cycle': (C.c_int, [C.POINTER(Cycle)]),
     'obe_resample_defer': (C.c_int, [C.c_int]),
     'obe_resample_pick': (C.c_int, [_PD, C.c_int, _VP, C.POINTER(_VP), C.c_int, C.c_int, C.c_uint64, _VP]),
     'obe_resample_emit': (C.c_int, [_VP]),

@@ -3183,6 +3183,65 @@ static int stream_edge(int which, void* from, void* to) {
 int obe_stream_fork(void* main_stream, void* side_stream) { return stream_edge(0, main_stream, side_stream); }
 int obe_stream_join(void* main_stream, void* side_stream) { return stream_edge(1, side_stream, main_stream); }
 
+int obe_cycle(const obe_cycle_t* c) {
+    if (!c || !c->cloud || !c->model) return obe_fail("obe_cycle: null argument%s%s");
+    void* st = c->stream;
+    const obe_cloud_t* live = c->cloud;
+    const int sharded = c->plan_dev != nullptr;
+    if (sharded && !c->peer_bufs) return obe_fail("obe_cycle: a sharded cycle needs the peer exchange%s%s");
+    if (obe_update(c->model, live, c->setting, c->constants, c->y_meas, c->has_sigma ? c->sigma : nullptr,
+                   c->has_noise_index ? c->noise_index : nullptr, c->n_lik_channels, c->use_choke, c->choke, c->pivot, st))
+        return -1;
+    if (sharded &&
+        obe_shard_plan_peer(c->peer_bufs, c->rank, c->world, c->epoch_stats, live->d, c->u0, c->n_total, c->a_param, 1,
+                            live, c->alt, c->plan_dev, st))
+        return -1;
+    const bool masks = (c->mask_le | c->mask_lt) != 0u;
+    const bool early = c->resample && c->select && !masks && !c->noise_from_stats && c->side_stream && c->method != 3 &&
+                       c->k >= 1 && c->k <= OBE_MAX_DRAWS && g_resample_fused;
+    const double* stats_for_utility = nullptr;
+    if (c->resample) {
+        if (!c->alt) return obe_fail("obe_cycle: resample needs the second buffer%s%s");
+        if (early) obe_resample_defer(1);
+        const int rc = sharded ? obe_resample_systematic_planned(live, c->alt, c->plan_dev, c->n_total, c->seed, c->epoch,
+                                                                 c->a_param, c->scale, st)
+                               : obe_resample_systematic(live, c->alt, c->u0, nullptr, nullptr, c->seed, c->epoch,
+                                                         c->a_param, c->scale, nullptr, nullptr, st);
+        if (rc) { obe_resample_defer(0); return -1; }
+        if (early) {
+            void* side = c->side_stream;
+            if (obe_stream_fork(st, side)) return -1;
+            if (obe_resample_pick(c->u, c->k, c->draws_dev, sharded ? c->peer_bufs : nullptr, c->rank, c->world,
+                                  c->epoch_draws, side))
+                return -1;
+            if (obe_utility(c->model, c->draws_dev, c->k, c->settings_dev, c->lds, c->n_settings, c->constants,
+                            c->var_noise, nullptr, c->cost_dev, c->method, c->log_form, c->kld_noise_dev, c->utility_dev,
+                            c->best_dev, c->select_scratch_dev, side))
+                return -1;
+            if (obe_resample_emit(st)) return -1;
+            return obe_stream_join(st, side);
+        }
+        live = c->alt;
+        if (masks) {
+            if (sharded) return obe_fail("obe_cycle: constraint masks on a sharded cloud need a re-plan (not supported here)%s%s");
+            if (obe_refresh(live, c->mask_le, c->mask_lt, c->n_noise > 0 ? c->noise_index : nullptr, c->n_noise, c->pivot, 1, st))
+                return -1;
+        }
+    }
+    if (!c->select) return 0;
+    if (c->noise_from_stats) stats_for_utility = live->stats_dev;
+    if (sharded) {
+        if (obe_draw_planned_peer(live, c->u, c->k, c->peer_bufs, c->rank, c->world, c->epoch_draws, c->plan_dev,
+                                  c->resample ? 1 : 0, c->draws_dev, st))
+            return -1;
+    } else if (obe_draw(live, c->u, c->k, c->draws_dev, nullptr, st)) {
+        return -1;
+    }
+    return obe_utility(c->model, c->draws_dev, c->k, c->settings_dev, c->lds, c->n_settings, c->constants,
+                       c->noise_from_stats ? nullptr : c->var_noise, stats_for_utility, c->cost_dev, c->method, c->log_form,
+                       c->kld_noise_dev, c->utility_dev, c->best_dev, c->select_scratch_dev, st);
+}
+
 int64_t obe_comb_count(double c, double u0, int64_t n_total) {
     // host twin of the device comb count: #{i in [0,n) : (i + u0) * (1/n) < c}, same IEEE operations
     const double nd = (double)n_total, inv_n = 1.0 / nd;

@@ -301,6 +301,8 @@ class OptBayesExpt(ParticlePDF):
         on the current stream with NO host synchronisation: the resample decision is the
         caller's, the chosen index stays in ``best_index_dev``.  For pipelined / benchmark use;
         ``pdf_update`` + ``opt_setting`` is the synchronous, reference-shaped API."""
+        if self._cycle_c_ok(resample, select):
+            return self._run_cycle_c(measurement_record, resample, select)
         onesetting = measurement_record[0]
         y_meas, sigma, noise_index, n_lik = self._likelihood_spec(measurement_record)
         self._check(self._lib.obe_update(self._model, self._cs(),
@@ -315,6 +317,122 @@ class OptBayesExpt(ParticlePDF):
         self._moments_valid = True      # on the device: the resample kernel reads them there
         self._weights_lazy = True
         self.resample_select_async(resample, select)
+
+    # ---- the whole cycle as ONE C call (obe_cycle): no Python between the launches ---------------
+    #: run_cycle_async goes through obe_cycle when the engine's configuration allows it
+    use_cycle_entry = True
+
+    def _cycle_c_ok(self, resample, select):
+        if not self.use_cycle_entry or (resample and self.resampling != 'systematic'):
+            return False
+        if select and (self._utility_code == 3 or not (1 <= self.N_DRAWS <= _lib.MAX_DRAWS)):
+            return False
+        if select:
+            cost = self.cost_estimate()
+            if not (np.isscalar(cost) and float(cost) == 1.0):
+                return False
+        return True
+
+    def _cycle_struct(self):
+        cy = getattr(self, '_cy', None)
+        if cy is None:
+            cy = self._cy = _lib.Cycle()
+            cy.model = self._model
+            cy.constants = C.cast(self._cons_arr, C.POINTER(C.c_double))
+            cy.settings_dev = self._settings_dev.data_ptr()
+            cy.lds = self._lds
+            cy.n_settings = len(self.setting_indices)
+            cy.utility_dev = self._utility_dev.data_ptr()
+            cy.best_dev = self._best_dev.data_ptr()
+            cy.select_scratch_dev = self._select_scratch.data_ptr()
+            self._cy_u = np.frombuffer(cy, dtype=np.float64, count=128, offset=_lib.Cycle.u.offset)
+        return cy
+
+    def _fill_cycle(self, cy, measurement_record, resample, select):
+        """The per-cycle fields of the obe_cycle_t; consumes self.rng in the order resample() / opt_setting() do."""
+        onesetting = measurement_record[0]
+        y_meas, sigma, noise_index, n_lik = self._likelihood_spec(measurement_record)
+        cy.model = self._model
+        st = np.atleast_1d(onesetting)
+        for i in range(min(len(st), _lib.MAX_SETTINGS)):
+            cy.setting[i] = st[i]
+        for i in range(len(y_meas)):
+            cy.y_meas[i] = y_meas[i]
+        cy.has_sigma = 0 if sigma is None else 1
+        if sigma is not None:
+            for i in range(len(sigma)):
+                cy.sigma[i] = sigma[i]
+        cy.has_noise_index = 0 if noise_index is None else 1
+        ni = self._noise_index
+        if noise_index is not None:
+            for i in range(len(noise_index)):
+                cy.noise_index[i] = noise_index[i]
+        elif ni is not None:
+            for i in range(len(ni)):
+                cy.noise_index[i] = ni[i]
+        cy.n_noise = 0 if ni is None else len(ni)
+        cy.n_lik_channels = n_lik
+        cy.use_choke = 0 if self.choke is None else 1
+        cy.choke = 0.0 if self.choke is None else float(self.choke)
+        piv = self._pivot
+        for i in range(self.n_dims):
+            cy.pivot[i] = piv[i]
+        cy.cloud = C.pointer(self._buf.struct())
+        cy.resample = 1 if resample else 0
+        if resample:
+            if self._alt is None:
+                self._alt = self._buf.empty_like()
+            cy.alt = C.pointer(self._alt.struct())
+            cy.scale = 1 if self.tuning_parameters['scale'] else 0
+            cy.a_param = float(self.tuning_parameters['a_param'])
+            cy.seed = self._philox_seed
+            cy.epoch = self._epoch + 1
+            cy.mask_le, cy.mask_lt = self._constraint_masks()
+        cy.select = 1 if select else 0
+        cy.noise_from_stats = 1 if self._noise_from_stats() else 0
+        if select:
+            k = int(self.N_DRAWS)
+            cy.k = k
+            cy.draws_dev = self._draws_buffer().data_ptr()
+            cy.method = self._utility_code
+            cy.log_form = 1 if self.utility_log_form else 0
+            if not cy.noise_from_stats:
+                vn = np.asarray(self.yvar_noise_model(), dtype=np.float64).reshape(-1)
+                for i in range(min(len(vn), _lib.MAX_CHANNELS)):
+                    cy.var_noise[i] = vn[i]
+        cy.stream = self._stream().value
+        cy.side_stream = self._side_stream()[1].value if (self.early_select and resample and select) else None
+
+    def _run_cycle_c(self, measurement_record, resample, select):
+        cy = self._cycle_struct()
+        self._fill_cycle(cy, measurement_record, resample, select)
+        if resample:
+            cy.u0 = float(self.rng.random())
+        if select:
+            self._cy_u[:cy.k] = self.rng.random(cy.k)
+        self._check(self._lib.obe_cycle(C.byref(cy)))
+        self._after_cycle_c(resample)
+
+    def _after_cycle_c(self, resample):
+        """Host bookkeeping of run_cycle_async + resample() (+ the asynchronous constraint pass)."""
+        self._invalidate()
+        self._stats = None
+        self._moments_valid = True
+        self._weights_lazy = True
+        if resample:
+            self._epoch += 1
+            self._last_ancestors = None
+            self._buf, self._alt = self._alt, self._buf
+            self._cloud_version += 1
+            self._invalidate(particles=True)
+            self._moments_valid = False
+            self._weights_uniform = True
+            self._weights_lazy = False
+            self.just_resampled = True
+            if self._cy.mask_le | self._cy.mask_lt:
+                self._moments_valid = True
+                self._weights_uniform = False
+                self._weights_lazy = True
 
     def resample_select_async(self, resample=True, select=True):
         """The part of run_cycle_async after the update: (forced) resample and selection, enqueued without a host

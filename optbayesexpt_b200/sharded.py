@@ -584,9 +584,52 @@ class ShardedOptBayesExpt(OptBayesExpt):
     def run_cycle_async(self, measurement_record, resample=True, select=True):
         """Sharded cycle with NO host synchronisation: update -> all-gather(stats) -> device plan ->
         planned resample -> owner-written draws -> all-reduce -> utility over this rank's grid slice."""
+        if (resample and self._peer is not None and self._replicate_grid and self._cycle_c_ok(resample, select)
+                and not self._noise_from_stats() and self._constraint_masks() == (0, 0)
+                and self.N_DRAWS * self.n_dims <= 1024):
+            return self._run_cycle_c(measurement_record, resample, select)
         OptBayesExpt.run_cycle_async(self, measurement_record, resample=False, select=False)
         self._make_plan()
         self.resample_select_async(resample, select)
+
+    def _run_cycle_c(self, measurement_record, resample, select):
+        """The sharded cycle through obe_cycle: update -> stats exchange + shard plan -> plan -> [pick + exchange of the
+        draws + utility] || [streaming resample], one C call.  Also used for the bare update (resample=select=False)
+        by the step-wise path, where it is the single-cloud entry."""
+        if not resample:
+            return OptBayesExpt._run_cycle_c(self, measurement_record, resample, select)
+        cy = self._cycle_struct()
+        self._fill_cycle(cy, measurement_record, resample, select)
+        self._u0 = float(self.rng.random())                 # identical on every rank
+        cy.u0 = self._u0
+        cy.plan_dev = self._plan.data_ptr()
+        cy.peer_bufs = C.cast(self._peer.ptrs, C.POINTER(C.c_void_p))
+        cy.rank, cy.world = self._comm.rank, self._comm.world
+        cy.epoch_stats = self._peer.next_epoch(0)
+        cy.n_total = self.n_total
+        if select:
+            cy.epoch_draws = self._peer.next_epoch(1)
+            self._cy_u[:cy.k] = self.rng.random(cy.k)
+        try:
+            self._check(self._lib.obe_cycle(C.byref(cy)))
+        finally:
+            cy.plan_dev = None                              # the bare-update use of the struct is unsharded
+        # host bookkeeping of the update, _make_plan() and resample()
+        OptBayesExpt._invalidate(self)
+        self._keep = None
+        self._epoch += 1
+        self._buf, self._alt = self._alt, self._buf
+        self._cloud_version += 1
+        self._n_local = None
+        OptBayesExpt._invalidate(self, particles=True)
+        self._gstats = None
+        self._stats = None
+        self._plan_valid = True
+        self._moments_valid = False
+        self._weights_uniform = True
+        self._weights_lazy = False
+        self._section = 1
+        self.just_resampled = True
 
     def resample_select_async(self, resample=True, select=True):
         if resample and select and self._early_select_ok():

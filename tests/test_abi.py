@@ -75,3 +75,22 @@ def test_product_does_not_import_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text, f
+
+
+def test_cycle_struct_layout_matches_the_header(obe_lib, tmp_path):
+    """obe_cycle_t is plain data shared between C and ctypes: sizes and offsets must agree with the C compiler's."""
+    import subprocess
+    from optbayesexpt_b200 import _lib
+    fields = [name for name, _ in _lib.Cycle._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "obe_b200.h"', 'int main(void) {',
+            '  printf("%zu\\n", sizeof(obe_cycle_t));']
+    prog += [f'  printf("%zu\\n", offsetof(obe_cycle_t, {f}));' for f in fields]
+    prog += ['  printf("%zu\\n", sizeof(obe_cloud_t));', '  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(prog))
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), '-o', str(exe), str(src)])
+    nums = [int(v) for v in subprocess.check_output([str(exe)]).decode().split()]
+    assert nums[0] == C.sizeof(_lib.Cycle)
+    assert nums[1:-1] == [getattr(_lib.Cycle, f).offset for f in fields]
+    assert nums[-1] == C.sizeof(_lib.Cloud)

@@ -141,3 +141,43 @@ def test_noise_parameter_engine_keeps_the_classic_order(obe):
         warnings.simplefilter('ignore', RuntimeWarning)
         eng.run_cycle_async(((0.3,), 0.2))
     assert abs(eng.particle_weights.sum() - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize('kind', ['base', 'noise', 'base_classic_select'])
+def test_cycle_entry_equals_the_stepwise_path(obe, kind):
+    """run_cycle_async through the one-call C entry (obe_cycle) against the same cycle enqueued step by step from
+    Python: identical clouds, weights, draws, utilities and argmax, for every resample/select combination."""
+    g = np.random.default_rng(8)
+    n = 30_000
+
+    def make():
+        if kind == 'noise':
+            prior = np.array([g0.normal(0, 2, n), g0.normal(0, 2, n), g0.exponential(1.0, n)])
+            return obe.OptBayesExptNoiseParameter('line', (np.linspace(-1, 1, 101),), prior, (),
+                                                  noise_parameter_index=2, scale=False, seed=4, a_param=0.6)
+        eng, _, _ = _engine(obe, n)
+        if kind == 'base_classic_select':
+            eng.early_select = False
+        return eng
+    g0 = np.random.default_rng(21)
+    a = make()
+    g0 = np.random.default_rng(21)
+    b = make()
+    b.use_cycle_entry = False
+    rec = ((0.3,), 0.2) if kind == 'noise' else ((3.05,), 49700.0, 400.0)
+    combos = [(True, True), (False, True), (True, False), (False, False), (True, True)]
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', RuntimeWarning)
+        for t, (res, sel) in enumerate(combos):
+            a.rng = np.random.default_rng(60 + t)
+            b.rng = np.random.default_rng(60 + t)
+            a.run_cycle_async(rec, resample=res, select=sel)
+            b.run_cycle_async(rec, resample=res, select=sel)
+            np.testing.assert_array_equal(a.particles, b.particles)
+            np.testing.assert_array_equal(a.particle_weights, b.particle_weights)
+            if sel:
+                np.testing.assert_array_equal(a._draws_dev.cpu().numpy(), b._draws_dev.cpu().numpy())
+                np.testing.assert_array_equal(a._utility_dev.cpu().numpy(), b._utility_dev.cpu().numpy())
+                assert int(a.best_index_dev.cpu()[0]) == int(b.best_index_dev.cpu()[0])
+            np.testing.assert_allclose(a.mean(), b.mean(), rtol=1e-14)
+            assert a.just_resampled == b.just_resampled or not res
