@@ -603,6 +603,7 @@ struct ObeResampleArgs {
     long long cap_out;             // capacity of the output buffers (planned mode)
     int implicit_out;              // 1: do not write the offspring weights, leave them implicit
     int chunk;                     // output slots per work unit the plan was made with
+    int shift_stores;              // one-kernel path: odd first slot -> lanes funnel their values into aligned 16-byte stores
     unsigned int* unit_counter;    // one-kernel path: next unit to hand out (zeroed by the plan kernel); null: static stride
     unsigned int* anc;             // two-kernel path: ancestor (input index) of every output slot of this shard
     double* out_tile_sums; double* out_prefix; double* out_stats;   // CDF bookkeeping of the offspring cloud
@@ -823,6 +824,7 @@ static int64_t g_utility_cache = 1;               /* obe_set_option("utility_cac
 static int64_t g_resample_fused = 1;              /* obe_set_option("resample_fused"): 1 = k_sys_resample_warp, 0 = ancestors + move */
 static int64_t g_resample_units_per_sm = 16;      /* obe_set_option("resample_units_per_sm"): work units per SM the chunk size aims at */
 static int64_t g_resample_reserve = 0;            /* obe_set_option("resample_reserve_ctas"): CTA slots an early-select resample leaves to the selection kernels */
+static int64_t g_resample_shift_stores = 1;       /* obe_set_option("resample_shift_stores"): aligned stores for shards with an odd first slot */
 static int64_t g_resample_dynamic = 1;            /* obe_set_option("resample_dynamic"): units handed out by an atomic counter */
 static int64_t g_resample_blocks = 0;             /* obe_set_option("resample_blocks"): CTAs per SM of the fused kernel (0: default) */
 #ifndef OBE_PLAN_CLUSTER_MIN_TILES
@@ -1609,6 +1611,7 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
             const volatile WrUnit& vu = wu[warp];
             const volatile SysCtx& vc = cs;
             const bool vec_ok = (c.slot_begin & 1) == 0;              // 16-byte aligned stores (launch-uniform)
+            const bool shift_ok = !vec_ok && a.shift_stores != 0;
             const double* __restrict__ pin = c.pin + base;
             const long long ld_in = c.ld_in, ld_out = c.ld_out;
 #if OBE_WR_SPLIT
@@ -1715,6 +1718,26 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
                         const double wv = vc.wv;
                         *reinterpret_cast<double2*>(w_out + o0) = make_double2(wv, wv);
                         *reinterpret_cast<double2*>(w_out + o0 + 2) = make_double2(wv, wv);
+                    }
+                } else if (FULL && shift_ok) {
+                    // A shard whose first slot is ODD: the groups are aligned to 4 GLOBAL slots (the Philox counters),
+                    // so every lane's 4 outputs start at an odd element and 16-byte stores would be misaligned.  Funnel
+                    // the lanes instead of falling back to 8-byte stores (4x the store instructions, partial sectors:
+                    // measured +35 % on the whole kernel): lane L takes the LAST value of lane L-1 and stores
+                    // [left, v0] [v1, v2]; only lane 0's v0 and lane 31's v3 go out as single doubles.
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        const double left = __shfl_up_sync(0xffffffffu, xv[3][j], 1);
+                        double* dst = pout + j * ld_out + o0;
+                        if (lane == 0) dst[0] = xv[0][j];
+                        else *reinterpret_cast<double2*>(dst - 1) = make_double2(left, xv[0][j]);
+                        *reinterpret_cast<double2*>(dst + 1) = make_double2(xv[1][j], xv[2][j]);
+                        if (lane == 31) dst[3] = xv[3][j];
+                    }
+                    if (w_out) {
+                        const double wv = vc.wv;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) w_out[o0 + u] = wv;
                     }
                 } else {
 #pragma unroll
@@ -2460,6 +2483,7 @@ int obe_set_option(const char* name, int64_t value) {
     if (s == "resample_fused") { g_resample_fused = value ? 1 : 0; return 0; }
     if (s == "resample_blocks") { g_resample_blocks = value < 0 ? 0 : value; return 0; }
     if (s == "resample_reserve_ctas") { g_resample_reserve = value < 0 ? 0 : value; return 0; }
+    if (s == "resample_shift_stores") { g_resample_shift_stores = value ? 1 : 0; return 0; }
     if (s == "resample_dynamic") { g_resample_dynamic = value ? 1 : 0; return 0; }
     if (s == "resample_units_per_sm") { g_resample_units_per_sm = value < 1 ? 1 : value; return 0; }
     return obe_fail("unknown option '%s'%s", name);
@@ -2909,6 +2933,7 @@ static int launch_sys_resample(const obe_cloud_t* in, const obe_cloud_t* out, Ob
     a.anc = scratch_of(out).anc;
     a.out_tile_sums = out->tile_sums_dev; a.out_prefix = out->tile_prefix_dev; a.out_stats = out->stats_dev;
     a.unit_counter = g_resample_dynamic ? scratch_of(in).counter + 18 : nullptr;
+    a.shift_stores = (int)g_resample_shift_stores;
     if (g_resample_fused) {
         // one kernel: every warp owns work units from the weights to the stores (+ the bookkeeping block)
         const int per_sm = (g_resample_blocks > 0 && g_resample_blocks < OBE_WR_BLOCKS(in->d)) ? (int)g_resample_blocks

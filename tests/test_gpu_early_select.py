@@ -181,3 +181,51 @@ def test_cycle_entry_equals_the_stepwise_path(obe, kind):
                 assert int(a.best_index_dev.cpu()[0]) == int(b.best_index_dev.cpu()[0])
             np.testing.assert_allclose(a.mean(), b.mean(), rtol=1e-14)
             assert a.just_resampled == b.just_resampled or not res
+
+
+@pytest.mark.parametrize('slot_begin', [1, 2, 3, 5, 4098])
+@pytest.mark.parametrize('d', [1, 3, 4])
+def test_shard_with_an_odd_first_slot_stores_the_same_cloud(obe, slot_begin, d):
+    """A shard whose first global slot is odd cannot use plain 16-byte stores (the emission groups are aligned to 4
+    GLOBAL slots); the lanes funnel their values into aligned stores instead.  Same offspring, bit for bit, as the
+    8-byte store path (resample_shift_stores = 0), ancestors included."""
+    import ctypes as C
+    import torch
+    from optbayesexpt_b200 import _lib
+    lib = _lib.load()
+    n = 300_001
+    g = np.random.default_rng(17)
+    prior = g.normal(0, 1, (d, n))
+    w = g.exponential(1.0, n)
+    w[1000:5000] *= 50.0
+    w /= w.sum()
+    pdf = obe.ParticlePDF(prior, scale=False, resampling='systematic', seed=5)
+    pdf.particle_weights = w
+    pdf._ensure_moments()
+    cov, mean = pdf.covariance(), pdf.mean()
+    factor = np.ascontiguousarray(np.linalg.cholesky((1 - 0.98 ** 2) * np.atleast_2d(cov)).T)
+    total = float(pdf._fetch_stats()[_lib.ST_TOTAL])
+    # the cloud as the LAST shard of a bigger one: slot_begin virtual offspring belong to the shards before it
+    n_total = n + slot_begin
+    cdf_total = total / (1.0 - slot_begin / n_total)
+    cdf_offset = cdf_total - total
+    out = {}
+    for shift in (1, 0):
+        alt = pdf._buf.empty_like()
+        idx = torch.full((n,), -1, dtype=torch.int64, device='cuda')
+        _lib.check(lib.obe_set_option(b'resample_shift_stores', shift))
+        try:
+            _lib.check(lib.obe_resample_systematic_sharded(
+                pdf._cs(), C.byref(alt.struct()), 0.4142, n_total, slot_begin, n_total, cdf_offset, cdf_total, 1,
+                _lib.darr(factor.reshape(-1)), _lib.darr(mean), 99, 3, 0.98, 0, C.c_void_p(idx.data_ptr()), None,
+                pdf._stream()))
+        finally:
+            _lib.check(lib.obe_set_option(b'resample_shift_stores', 1))
+        out[shift] = (alt.particles[:, :n].clone(), idx.clone())
+    assert torch.equal(out[1][1], out[0][1])
+    assert torch.equal(out[1][0], out[0][0])
+    idx = out[1][1]
+    assert int(idx.min()) >= 0 and int(idx.max()) < n and bool((idx[1:] >= idx[:-1]).all())
+    # the jitter really happened and is small: offspring stay within a few factor-widths of their ancestors
+    moved = (out[1][0] - torch.from_numpy(prior).cuda()[:, idx]).abs().max().item()
+    assert 0.0 < moved < 10.0 * float(np.abs(factor).max()) + 1e-12
