@@ -247,6 +247,7 @@ def bench_small(args):
     def closed_loop(threshold, steps):
         e = make(threshold)
         e.eager_select = True
+        e.async_update = True            # (only takes effect where the resample decision is known: the forced loop)
         x = e.opt_setting()
         for _ in range(max(3, args.warmup)):
             e.pdf_update(ra.simulate(wl, x, meas))
@@ -684,6 +685,7 @@ def main():
 
     # ---------------- end to end through the reference-shaped API, closed loop -------------------
     eng.eager_select = True              # the resample inside pdf_update starts the selection opt_setting() asks for
+    eng.async_update = True              # forced resampling: the decision does not need N_eff, pdf_update does not sync
     x = eng.opt_setting()
     for _ in range(max(3, args.warmup // 2)):
         eng.pdf_update(record_for(x[0]))

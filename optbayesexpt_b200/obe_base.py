@@ -145,6 +145,10 @@ class OptBayesExpt(ParticlePDF):
         #: pdf_update: a resample also starts the selection the next opt_setting()/good_setting() will ask for
         #: (the K uniforms are drawn from ``self.rng`` at that moment instead of inside opt_setting)
         self.eager_select = False
+        #: pdf_update does not wait for the stats block when the resample decision does not depend on it
+        #: (auto_resample off, or resample_threshold > 1): one C call, no synchronisation; the pivot of the moment
+        #: accumulators and the impoverishment warning then lag one update behind
+        self.async_update = False
         self._select_ready = False
         self._side = None                 # (torch stream object, raw handle) of the selection stream
 
@@ -249,6 +253,10 @@ class OptBayesExpt(ParticlePDF):
         Returns ``(particles, particle_weights)`` as lazy, numpy-convertible handles: nothing is
         copied off the GPU unless the caller looks at them.
         """
+        if self.async_update and y_model_data is None and getattr(self, '_prefetched', None) is None:
+            decision = self._resample_decision_known()
+            if decision is not None and self._cycle_c_ok(decision, bool(self.eager_select)):
+                return self._pdf_update_async(measurement_record, decision)
         onesetting = measurement_record[0]
         y_meas, sigma, noise_index, n_lik = self._likelihood_spec(measurement_record)
         use_choke = 0 if self.choke is None else 1
@@ -285,6 +293,66 @@ class OptBayesExpt(ParticlePDF):
         if self.just_resampled:
             self.enforce_parameter_constraints()
         return (LazyDeviceArray(lambda: self.particles), LazyDeviceArray(lambda: self.particle_weights))
+
+    # ---- pdf_update without a host synchronisation ------------------------------------------------
+    def _resample_decision_known(self):
+        """True / False when the resample test of particlepdf.py:236-258 does not depend on N_eff (auto_resample
+        off, or a threshold above 1: N_eff / N <= 1 always), None when the host has to look at N_eff."""
+        tp = self.tuning_parameters
+        if not tp['auto_resample']:
+            return False
+        if tp['resample_threshold'] > 1.0:
+            return True
+        return None
+
+    def _pdf_update_async(self, measurement_record, resample):
+        """pdf_update as ONE C call and no synchronisation (``async_update``): the resample decision is known
+        beforehand, so nothing has to come back before the kernels are enqueued.  The stats block follows in an
+        asynchronous copy and is adopted by the NEXT update (pivot of the moment accumulators; the particle
+        impoverishment warning of particlepdf.py:245-250 is therefore issued one update late)."""
+        self._adopt_async_stats()
+        select = bool(self.eager_select)
+        self.run_cycle_async(measurement_record, resample=resample, select=select)
+        self._select_ready = select
+        self.just_resampled = bool(resample)
+        self._post_async_stats(resample)
+        if resample and self._constraint_masks() == (0, 0):
+            self.enforce_parameter_constraints()          # (mask constraints were applied inside the cycle)
+        return (LazyDeviceArray(lambda: self.particles), LazyDeviceArray(lambda: self.particle_weights))
+
+    def _async_stats_source(self, resample):
+        """Device block holding the stats of the update that just ran (the resample swapped the buffers)."""
+        return (self._alt if resample else self._buf).stats
+
+    def _post_async_stats(self, resample):
+        torch = self._torch
+        pin = getattr(self, '_async_pin', None)
+        if pin is None:
+            pin = self._async_pin = torch.zeros(_lib.STATS_LEN, dtype=torch.float64).pin_memory()
+            self._async_pin_np = pin.numpy()
+            self._async_ev = torch.cuda.Event()
+        pin.copy_(self._async_stats_source(resample), non_blocking=True)
+        self._async_ev.record()
+        self._async_pending = True
+
+    def _adopt_async_stats(self):
+        if not getattr(self, '_async_pending', False):
+            return
+        self._async_pending = False
+        self._async_ev.synchronize()            # (already complete in a closed loop: opt_setting synchronised since)
+        st = self._async_pin_np.copy()
+        mean = self._mean_from(st)
+        if np.all(np.isfinite(mean)):
+            self._pivot = mean
+        n_eff = self._n_eff_from(st)
+        if n_eff < 0.1 * self._n_total_for_test():
+            import warnings
+            warnings.warn("\nParticle filter rejected > 90 % of particles. "
+                          f"N_eff = {n_eff:.2f}. "
+                          "Particle impoverishment may lead to errors.", RuntimeWarning)
+
+    def _n_total_for_test(self):
+        return self.n_particles
 
     def _noise_iarr(self, noise_index):
         """ctypes int array of the noise-parameter rows (cached: it never changes for an engine)."""

@@ -592,6 +592,21 @@ class ShardedOptBayesExpt(OptBayesExpt):
         self._make_plan()
         self.resample_select_async(resample, select)
 
+    def _async_stats_source(self, resample):
+        return self._plan[_lib.PLAN_GSTATS:_lib.PLAN_GSTATS + _lib.STATS_LEN]      # the combined (global) block
+
+    def _n_total_for_test(self):
+        return self.n_total
+
+    def _pdf_update_async(self, measurement_record, resample):
+        if not resample:        # (the unsharded entry would skip the stats exchange: keep the synchronous path)
+            self.async_update, saved = False, self.async_update
+            try:
+                return self.pdf_update(measurement_record)
+            finally:
+                self.async_update = saved
+        return OptBayesExpt._pdf_update_async(self, measurement_record, resample)
+
     def _run_cycle_c(self, measurement_record, resample, select):
         """The sharded cycle through obe_cycle: update -> stats exchange + shard plan -> plan -> [pick + exchange of the
         draws + utility] || [streaming resample], one C call.  Also used for the bare update (resample=select=False)

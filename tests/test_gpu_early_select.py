@@ -229,3 +229,38 @@ def test_shard_with_an_odd_first_slot_stores_the_same_cloud(obe, slot_begin, d):
     # the jitter really happened and is small: offspring stay within a few factor-widths of their ancestors
     moved = (out[1][0] - torch.from_numpy(prior).cuda()[:, idx]).abs().max().item()
     assert 0.0 < moved < 10.0 * float(np.abs(factor).max()) + 1e-12
+
+
+@pytest.mark.parametrize('forced', [True, False], ids=['forced_resample', 'no_auto_resample'])
+def test_async_update_closed_loop(obe, forced):
+    """pdf_update with ``async_update`` (one C call, no synchronisation; the resample decision is known beforehand)
+    against the synchronous engine: same chosen settings, same clouds.  The pivot of the moment accumulators lags one
+    update behind, which moves the moments by rounding only."""
+    n = 40_000
+    kw = dict(resample_threshold=2.0) if forced else dict(auto_resample=False)
+    a, _, _ = _engine(obe, n, **kw)
+    b, _, _ = _engine(obe, n, **kw)
+    a.eager_select = a.async_update = True
+    a.rng = np.random.default_rng(5)
+    b.rng = np.random.default_rng(5)
+    meas = np.random.default_rng(9)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', RuntimeWarning)
+        xa, xb = a.opt_setting(), b.opt_setting()
+        for t in range(12):
+            assert xa == xb and a.last_setting_index == b.last_setting_index, f'cycle {t}'
+            y = 50400.0 - 1200.0 / (((xa[0] - 3.14) / 0.1) ** 2 + 1) + 500.0 * meas.standard_normal()
+            a.pdf_update((xa, y, 500.0))
+            b.pdf_update((xb, y, 500.0))
+            assert a.just_resampled == b.just_resampled == forced
+            xa, xb = a.opt_setting(), b.opt_setting()
+        if forced:
+            # (same ancestors; the Liu-West factor comes from moments accumulated around a one-update-older pivot)
+            spread = b.particles.std(axis=1, keepdims=True)
+            err = np.abs(a.particles - b.particles) / (np.abs(b.particles) * 1e-12 + spread * 1e-9)
+            assert err.max() <= 1.0
+        else:
+            np.testing.assert_array_equal(a.particles, b.particles)
+            np.testing.assert_allclose(a.particle_weights, b.particle_weights, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(a.mean(), b.mean(), rtol=1e-10)
+        np.testing.assert_allclose(a.n_eff(), b.n_eff(), rtol=1e-9)
