@@ -776,7 +776,7 @@ def main():
                      'frac_of_moved_bytes': b_res_moved / world / (t_res * 1e-3) / 1e9 / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of the resample kernels from the ncu --set full capture
                      # of this build (profiles/r2_ncu_summary.md): bytes per particle at d = 3, scaled to this launch
-                     'traffic': (53.3 if fused else 63.8) * n_total / world if d == 3 else None,
+                     'traffic': (56.3 if fused else 63.8) * n_total / world if d == 3 else None,
                      'traffic_source': 'profiles/r2_ncu_summary.md (ncu --set full of the same build and workload; '
                                        'per-particle figure x particles of this launch, not re-measured in this run)',
                      'peak_source': peak_src},
