@@ -3619,26 +3619,10 @@ int obe_batch_select(obe_model_t m, const obe_batch_t* b, const double* settings
     for (int j = 0; j < m->ncons; ++j) a.cons[j] = constants[j];
     int64_t g = (int64_t)obe_sms() * 4;
     if (g > b->n_inst) g = b->n_inst;
-    size_t smem = (size_t)(OBE_TILE + k * (m->np_model > 0 ? m->np_model : 1)) * sizeof(double);
-    if (g_utility_cache) {
-        // the in-tile CDF (OBE_TILE doubles) is dead once the draws are taken: the value cache reuses that region
-        int64_t stride = (n_settings + 31) / 32 * 32;
-        if (stride > OBE_THREADS) stride = OBE_THREADS;
-        a.cache_stride = (int)stride;
-        const size_t cache_doubles = (size_t)k * m->nch * (size_t)stride;
-        const size_t with_cache = ((cache_doubles > OBE_TILE ? cache_doubles : (size_t)OBE_TILE) +
-                                   (size_t)k * (m->np_model > 0 ? m->np_model : 1)) * sizeof(double);
-        if (with_cache <= 200 * 1024) {
-            cudaError_t e = cudaSuccess;
-            if (with_cache > 48 * 1024)
-                e = cudaFuncSetAttribute(m->f_bselect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_cache);
-            if (e != cudaSuccess) { (void)cudaGetLastError(); } else { a.cache = 1; smem = with_cache; }
-        }
-    }
-    if (a.cache) {                                  // one resident CTA per SM is all the cache leaves room for
-        g = (int64_t)obe_sms() * (smem > 110 * 1024 ? 1 : 2);
-        if (g > b->n_inst) g = b->n_inst;
-    }
+    // (parking the K x NCH model values of a setting in shared memory, as obe_utility does, was measured here and
+    // lost: 108 KB per CTA leaves 2 CTAs per SM and the kernel went from 0.44 to 0.57 ms -- occupancy matters more
+    // than the second evaluation for this FP64-latency-bound body)
+    const size_t smem = (size_t)(OBE_TILE + k * (m->np_model > 0 ? m->np_model : 1)) * sizeof(double);
     return launch_kernel(m->f_bselect, (int)g, smem, (cudaStream_t)stream, &a);
 }
 

@@ -1560,15 +1560,13 @@ struct ObeBSelectArgs {
     double cost_change;          // > 0: cost = cost_change except 1 at the previous choice
     double var_noise[OBE_MAX_CH];
     double cons[OBE_MAX_CONS];
-    int cache;                   // the K x NCH model values of a thread's setting are parked in shared memory
-    int cache_stride;            // threads that own a setting (rounded up to whole warps): row stride of that cache
 };
 
 template <class Model>
 __device__ void obe_bselect_body(const ObeBSelectArgs& a) {
     extern __shared__ double obe_smem[];
-    double* sdraw = obe_smem;                      // [K][NP]
-    double* cn_s = obe_smem + a.k * Model::NP;     // [OBE_TILE] during the draws, then the [K*NCH][blockDim] value cache
+    double* cn_s = obe_smem;                       // [OBE_TILE]
+    double* sdraw = obe_smem + OBE_TILE;           // [K][NP]
     __shared__ double sm[8];
     __shared__ double uq_s[OBE_MAX_DRAWS];
     __shared__ int tq_s[OBE_MAX_DRAWS];
@@ -1634,27 +1632,15 @@ __device__ void obe_bselect_body(const ObeBSelectArgs& a) {
             double y[Model::NCH], mean[Model::NCH], ss[Model::NCH];
 #pragma unroll
             for (int c = 0; c < Model::NCH; ++c) { mean[c] = 0.0; ss[c] = 0.0; }
-            // numpy's two-pass variance needs every model value twice: with `cache` the second pass reads the values
-            // of the first back from shared memory (column tid of a [K*NCH][blockDim] array: conflict-free) -- the
-            // same values in the same order, half the model evaluations of a kernel that is FP64-issue-bound.
-            double* ycol = cn_s + tid;
             for (int k = 0; k < K; ++k) {
                 Model::eval(st, sdraw + k * Model::NP, a.cons, y);
 #pragma unroll
-                for (int c = 0; c < Model::NCH; ++c) {
-                    mean[c] = obe_add(mean[c], y[c]);
-                    if (a.cache) ycol[(k * Model::NCH + c) * a.cache_stride] = y[c];
-                }
+                for (int c = 0; c < Model::NCH; ++c) mean[c] = obe_add(mean[c], y[c]);
             }
 #pragma unroll
             for (int c = 0; c < Model::NCH; ++c) mean[c] = obe_div(mean[c], kd);
             for (int k = 0; k < K; ++k) {
-                if (a.cache) {
-#pragma unroll
-                    for (int c = 0; c < Model::NCH; ++c) y[c] = ycol[(k * Model::NCH + c) * a.cache_stride];
-                } else {
-                    Model::eval(st, sdraw + k * Model::NP, a.cons, y);
-                }
+                Model::eval(st, sdraw + k * Model::NP, a.cons, y);
 #pragma unroll
                 for (int c = 0; c < Model::NCH; ++c) {
                     const double dlt = obe_sub(y[c], mean[c]);
