@@ -523,16 +523,23 @@ __device__ __forceinline__ void packed_normals_slot(long long slot, unsigned lon
 // (x_j <- fma(z_k, F[k][j], x_j)), so the 4*D normals are never all live -- 2*4*D registers less than building z
 // first, which is what lets the resample kernels keep their gathers and the Philox state in registers.  z_out
 // (tests): the normals are also stored, (n, D) row-major at output position o0 + u.
-template <int D>
-__device__ __forceinline__ void jitter_group4(double (&xv)[4][D], long long slot0, unsigned long long seed,
-                                              unsigned int epoch, const double* __restrict__ F,
-                                              const double* __restrict__ mean, double a_param, int scale,
-                                              double* __restrict__ z_out, long long o0, const bool (&ok)[4]) {
+// R = slot0 & 3 (compile time): the 4 slots need the 4*D consecutive normals m = D*slot0 .. D*slot0 + 4*D - 1 of the
+// packed stream, which start at word W = (D*R) & 3 of call (D*slot0) >> 2 and span D calls when W == 0, D + 1 otherwise.
+// A shard whose first global slot is not a multiple of 4 aligns its emission groups to its OUTPUT (whole 32-byte
+// sectors, plain 16-byte stores) and pays the one extra Philox call per 4 slots instead of shuffling values between
+// lanes; the normals of a slot do not depend on the grouping, so the offspring are the same bits either way.
+template <int D, int R>
+__device__ __forceinline__ void jitter_group4_w(double (&xv)[4][D], long long slot0, unsigned long long seed,
+                                                unsigned int epoch, const double* __restrict__ F,
+                                                const double* __restrict__ mean, double a_param, int scale,
+                                                double* __restrict__ z_out, long long o0, const bool (&ok)[4]) {
+    constexpr int W = (D * R) & 3;
+    constexpr int NC = D + (W ? 1 : 0);
     const unsigned int key0 = (unsigned int)(seed & 0xffffffffull), key1 = (unsigned int)(seed >> 32);
-    const unsigned long long q0 = (unsigned long long)(slot0 >> 2) * (unsigned long long)D;
-    unsigned int c0[D], c1[D], c2[D], c3[D];
+    const unsigned long long q0 = ((unsigned long long)slot0 * (unsigned long long)D) >> 2;
+    unsigned int c0[NC], c1[NC], c2[NC], c3[NC];
 #pragma unroll
-    for (int c = 0; c < D; ++c) {
+    for (int c = 0; c < NC; ++c) {
         const unsigned long long q = q0 + (unsigned long long)c;
         c0[c] = (unsigned int)(q & 0xffffffffull);
         c1[c] = (unsigned int)(q >> 32);
@@ -542,7 +549,7 @@ __device__ __forceinline__ void jitter_group4(double (&xv)[4][D], long long slot
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) {
+        for (int c = 0; c < NC; ++c) {
             const unsigned int hi0 = __umulhi(0xD2511F53u, c0[c]), lo0 = 0xD2511F53u * c0[c];
             const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2[c]), lo1 = 0xCD9E8D57u * c2[c];
             const unsigned int n0 = hi1 ^ c1[c] ^ k0, n2 = hi0 ^ c3[c] ^ k1;
@@ -551,17 +558,20 @@ __device__ __forceinline__ void jitter_group4(double (&xv)[4][D], long long slot
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
 #pragma unroll
-    for (int c = 0; c < D; ++c) {
+    for (int c = 0; c < NC; ++c) {
         const unsigned int r4[4] = {c0[c], c1[c], c2[c], c3[c]};
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+            const int f0 = 4 * c + 2 * h - W;                    // compile-time after unrolling: first of the pair
+            if (f0 + 1 < 0 || f0 >= 4 * D) continue;             // both normals of the pair lie outside the 4 slots
             const float rad = obe_sqrt_approx(-2.0f * __logf(u24(r4[2 * h])));
             float sn, cs;
             __sincosf(6.2831853071795865f * u24(r4[2 * h + 1]), &sn, &cs);
             const double zz[2] = {(double)(rad * cs), (double)(rad * sn)};
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
-                const int f = 4 * c + 2 * h + w;                 // compile-time after unrolling
+                const int f = f0 + w;
+                if (f < 0 || f >= 4 * D) continue;
                 const int u = f / D, k = f % D;
                 if (z_out && ok[u]) z_out[(o0 + u) * D + k] = zz[w];
 #pragma unroll
@@ -577,6 +587,13 @@ __device__ __forceinline__ void jitter_group4(double (&xv)[4][D], long long slot
             for (int j = 0; j < D; ++j) xv[u][j] = obe_add(obe_mul(xv[u][j], a_param), obe_mul(mean[j], b));
         }
     }
+}
+template <int D>
+__device__ __forceinline__ void jitter_group4(double (&xv)[4][D], long long slot0, unsigned long long seed,
+                                              unsigned int epoch, const double* __restrict__ F,
+                                              const double* __restrict__ mean, double a_param, int scale,
+                                              double* __restrict__ z_out, long long o0, const bool (&ok)[4]) {
+    jitter_group4_w<D, 0>(xv, slot0, seed, epoch, F, mean, a_param, scale, z_out, o0, ok);
 }
 
 struct ObeResampleArgs {
@@ -603,7 +620,6 @@ struct ObeResampleArgs {
     long long cap_out;             // capacity of the output buffers (planned mode)
     int implicit_out;              // 1: do not write the offspring weights, leave them implicit
     int chunk;                     // output slots per work unit the plan was made with
-    int shift_stores;              // one-kernel path: odd first slot -> lanes funnel their values into aligned 16-byte stores
     unsigned int* unit_counter;    // one-kernel path: next unit to hand out (zeroed by the plan kernel); null: static stride
     unsigned int* anc;             // two-kernel path: ancestor (input index) of every output slot of this shard
     double* out_tile_sums; double* out_prefix; double* out_stats;   // CDF bookkeeping of the offspring cloud
@@ -824,7 +840,6 @@ static int64_t g_utility_cache = 1;               /* obe_set_option("utility_cac
 static int64_t g_resample_fused = 1;              /* obe_set_option("resample_fused"): 1 = k_sys_resample_warp, 0 = ancestors + move */
 static int64_t g_resample_units_per_sm = 16;      /* obe_set_option("resample_units_per_sm"): work units per SM the chunk size aims at */
 static int64_t g_resample_reserve = 0;            /* obe_set_option("resample_reserve_ctas"): CTA slots an early-select resample leaves to the selection kernels */
-static int64_t g_resample_shift_stores = 1;       /* obe_set_option("resample_shift_stores"): aligned stores for shards with an odd first slot */
 static int64_t g_resample_dynamic = 1;            /* obe_set_option("resample_dynamic"): units handed out by an atomic counter */
 static int64_t g_resample_blocks = 0;             /* obe_set_option("resample_blocks"): CTAs per SM of the fused kernel (0: default) */
 #ifndef OBE_PLAN_CLUSTER_MIN_TILES
@@ -1355,9 +1370,10 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_MOVE_BLOCKS(D)) k_sys_move(co
 //   phase B  the chunk's slots are emitted in groups of 128: 4 consecutive slots per lane, the marks are
 //            max-scanned in registers (carry across groups in a register), ancestors gathered through L1
 //            (monotone ancestors: the gathers walk the tile almost sequentially), Philox / Box-Muller /
-//            Liu-West, 16-byte stores of 32 contiguous bytes per lane and row.  Groups are aligned to 4 output
-//            slots in GLOBAL output coordinates (the chunk is shifted by A = o_base & 3), so every full group
-//            stores whole 32-byte sectors.
+//            Liu-West, 16-byte stores of 32 contiguous bytes per lane and row.  Groups are aligned to 4 slots of
+//            the shard's OUTPUT (the chunk is shifted by A = o_base & 3), so every full group stores whole 32-byte
+//            sectors; on a shard whose first global slot is not a multiple of 4 the groups then straddle the 4-slot
+//            blocks of the packed normal stream and take one more Philox call (jitter_group4_w).
 // Same arithmetic as sys_unit_ancestors + k_sys_move, so the ancestors and the offspring are bit-identical to
 // the two-kernel path's.  Algorithmic traffic 8N(2d+1) instead of 8N(2d+2).
 #define OBE_WR_GROUP 128
@@ -1532,8 +1548,8 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
         const int n_chunk = min(rel_begin + a.chunk, (int)(Hk1 - Hk)) - rel_begin;
         const long long chunk0 = Hk + rel_begin;                      // global slot of the chunk's first output
         const long long o_base = chunk0 - c.slot_begin;               // its position in this shard's output
-        const int A = (int)(chunk0 & 3);                              // shifted chunk coordinate q' = q + A: groups of
-                                                                      // 4 slots start at multiples of 4 GLOBAL slots
+        const int A = (int)(o_base & 3);                              // shifted chunk coordinate q' = q + A: groups of
+                                                                      // 4 slots start at multiples of 4 OUTPUT positions
         const int q_end = A + n_chunk;
         const long long base = (long long)k * OBE_TILE;
         const int cnt_tile = (int)(min(c.n_in, base + OBE_TILE) - base);
@@ -1602,16 +1618,18 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
             const int n_emit = room < (long long)n_chunk ? (room > 0 ? (int)room : 0) : n_chunk;
             if (lane == 0) {
                 WrUnit& w = wu[warp];
-                w.og_al = chunk0 - A;                                 // global slot of q' = 0 (multiple of 4)
-                w.o_al = chunk0 - A - c.slot_begin;                   // its position in this shard's output
+                w.og_al = chunk0 - A;                                 // global slot of q' = 0 (= slot_begin mod 4)
+                w.o_al = chunk0 - A - c.slot_begin;                   // its position in this shard's output (multiple of 4)
                 w.base = base;
                 w.q_emit_end = A + n_emit; w.A = A; w.lastrel = lastrel;
             }
             __syncwarp();
             const volatile WrUnit& vu = wu[warp];
             const volatile SysCtx& vc = cs;
-            const bool vec_ok = (c.slot_begin & 1) == 0;              // 16-byte aligned stores (launch-uniform)
-            const bool shift_ok = !vec_ok && a.shift_stores != 0;
+            // Groups are aligned to the shard's OUTPUT, so every full group stores whole 32-byte sectors whatever
+            // the shard's first global slot is; a shard with slot_begin % 4 != 0 draws the normals of its groups from
+            // one more Philox call (jitter_group4_w) -- the normals of a slot do not depend on the grouping.
+            const int rr = (int)(c.slot_begin & 3);                   // launch-uniform
             const double* __restrict__ pin = c.pin + base;
             const long long ld_in = c.ld_in, ld_out = c.ld_out;
 #if OBE_WR_SPLIT
@@ -1701,13 +1719,22 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
 #pragma unroll
                     for (int j = 0; j < D; ++j) xv[u][j] = __ldg(pin + j * ld_in + rel[u]);
                 }
-                if (vc.jitter)
-                    jitter_group4<D>(xv, vu.og_al + q0, vc.seed, vc.epoch, sF, sMean, vc.a_param, vc.scale, vc.z_out,
-                                     vu.o_al + q0, ok);
+                if (vc.jitter) {
+                    switch (rr) {
+                        case 0: jitter_group4_w<D, 0>(xv, vu.og_al + q0, vc.seed, vc.epoch, sF, sMean, vc.a_param, vc.scale,
+                                                      vc.z_out, vu.o_al + q0, ok); break;
+                        case 1: jitter_group4_w<D, 1>(xv, vu.og_al + q0, vc.seed, vc.epoch, sF, sMean, vc.a_param, vc.scale,
+                                                      vc.z_out, vu.o_al + q0, ok); break;
+                        case 2: jitter_group4_w<D, 2>(xv, vu.og_al + q0, vc.seed, vc.epoch, sF, sMean, vc.a_param, vc.scale,
+                                                      vc.z_out, vu.o_al + q0, ok); break;
+                        default: jitter_group4_w<D, 3>(xv, vu.og_al + q0, vc.seed, vc.epoch, sF, sMean, vc.a_param, vc.scale,
+                                                       vc.z_out, vu.o_al + q0, ok); break;
+                    }
+                }
                 const long long o0 = vu.o_al + q0;
                 double* __restrict__ pout = vc.pout;
                 double* __restrict__ w_out = vc.w_out;
-                if ((FULL || all) && vec_ok) {
+                if (FULL || all) {
 #pragma unroll
                     for (int j = 0; j < D; ++j) {
                         double* dst = pout + j * ld_out + o0;
@@ -1718,26 +1745,6 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
                         const double wv = vc.wv;
                         *reinterpret_cast<double2*>(w_out + o0) = make_double2(wv, wv);
                         *reinterpret_cast<double2*>(w_out + o0 + 2) = make_double2(wv, wv);
-                    }
-                } else if (FULL && shift_ok) {
-                    // A shard whose first slot is ODD: the groups are aligned to 4 GLOBAL slots (the Philox counters),
-                    // so every lane's 4 outputs start at an odd element and 16-byte stores would be misaligned.  Funnel
-                    // the lanes instead of falling back to 8-byte stores (4x the store instructions, partial sectors:
-                    // measured +35 % on the whole kernel): lane L takes the LAST value of lane L-1 and stores
-                    // [left, v0] [v1, v2]; only lane 0's v0 and lane 31's v3 go out as single doubles.
-#pragma unroll
-                    for (int j = 0; j < D; ++j) {
-                        const double left = __shfl_up_sync(0xffffffffu, xv[3][j], 1);
-                        double* dst = pout + j * ld_out + o0;
-                        if (lane == 0) dst[0] = xv[0][j];
-                        else *reinterpret_cast<double2*>(dst - 1) = make_double2(left, xv[0][j]);
-                        *reinterpret_cast<double2*>(dst + 1) = make_double2(xv[1][j], xv[2][j]);
-                        if (lane == 31) dst[3] = xv[3][j];
-                    }
-                    if (w_out) {
-                        const double wv = vc.wv;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) w_out[o0 + u] = wv;
                     }
                 } else {
 #pragma unroll
@@ -2483,7 +2490,6 @@ int obe_set_option(const char* name, int64_t value) {
     if (s == "resample_fused") { g_resample_fused = value ? 1 : 0; return 0; }
     if (s == "resample_blocks") { g_resample_blocks = value < 0 ? 0 : value; return 0; }
     if (s == "resample_reserve_ctas") { g_resample_reserve = value < 0 ? 0 : value; return 0; }
-    if (s == "resample_shift_stores") { g_resample_shift_stores = value ? 1 : 0; return 0; }
     if (s == "resample_dynamic") { g_resample_dynamic = value ? 1 : 0; return 0; }
     if (s == "resample_units_per_sm") { g_resample_units_per_sm = value < 1 ? 1 : value; return 0; }
     return obe_fail("unknown option '%s'%s", name);
@@ -2933,7 +2939,6 @@ static int launch_sys_resample(const obe_cloud_t* in, const obe_cloud_t* out, Ob
     a.anc = scratch_of(out).anc;
     a.out_tile_sums = out->tile_sums_dev; a.out_prefix = out->tile_prefix_dev; a.out_stats = out->stats_dev;
     a.unit_counter = g_resample_dynamic ? scratch_of(in).counter + 18 : nullptr;
-    a.shift_stores = (int)g_resample_shift_stores;
     if (g_resample_fused) {
         // one kernel: every warp owns work units from the weights to the stores (+ the bookkeeping block)
         const int per_sm = (g_resample_blocks > 0 && g_resample_blocks < OBE_WR_BLOCKS(in->d)) ? (int)g_resample_blocks

@@ -185,10 +185,11 @@ def test_cycle_entry_equals_the_stepwise_path(obe, kind):
 
 @pytest.mark.parametrize('slot_begin', [1, 2, 3, 5, 4098])
 @pytest.mark.parametrize('d', [1, 3, 4])
-def test_shard_with_an_odd_first_slot_stores_the_same_cloud(obe, slot_begin, d):
-    """A shard whose first global slot is odd cannot use plain 16-byte stores (the emission groups are aligned to 4
-    GLOBAL slots); the lanes funnel their values into aligned stores instead.  Same offspring, bit for bit, as the
-    8-byte store path (resample_shift_stores = 0), ancestors included."""
+def test_shard_whose_first_slot_is_not_a_multiple_of_4(obe, slot_begin, d):
+    """The one-kernel resample aligns its emission groups to the shard's OUTPUT; on a shard whose first global slot is
+    not a multiple of 4 the groups straddle the 4-slot blocks of the packed normal stream (jitter_group4_w, one more
+    Philox call).  Same offspring, bit for bit, as the two-kernel path (k_sys_ancestors + k_sys_move, which groups by
+    GLOBAL slots), ancestors included -- the normals of a slot must not depend on the grouping."""
     import ctypes as C
     import torch
     from optbayesexpt_b200 import _lib
@@ -210,57 +211,27 @@ def test_shard_with_an_odd_first_slot_stores_the_same_cloud(obe, slot_begin, d):
     cdf_total = total / (1.0 - slot_begin / n_total)
     cdf_offset = cdf_total - total
     out = {}
-    for shift in (1, 0):
+    for fused in (1, 0):
         alt = pdf._buf.empty_like()
         idx = torch.full((n,), -1, dtype=torch.int64, device='cuda')
-        _lib.check(lib.obe_set_option(b'resample_shift_stores', shift))
+        zout = torch.zeros((n, d), dtype=torch.float64, device='cuda')
+        _lib.check(lib.obe_set_option(b'resample_fused', fused))
         try:
             _lib.check(lib.obe_resample_systematic_sharded(
                 pdf._cs(), C.byref(alt.struct()), 0.4142, n_total, slot_begin, n_total, cdf_offset, cdf_total, 1,
-                _lib.darr(factor.reshape(-1)), _lib.darr(mean), 99, 3, 0.98, 0, C.c_void_p(idx.data_ptr()), None,
-                pdf._stream()))
+                _lib.darr(factor.reshape(-1)), _lib.darr(mean), 99, 3, 0.98, 0, C.c_void_p(idx.data_ptr()),
+                C.c_void_p(zout.data_ptr()), pdf._stream()))
         finally:
-            _lib.check(lib.obe_set_option(b'resample_shift_stores', 1))
-        out[shift] = (alt.particles[:, :n].clone(), idx.clone())
+            _lib.check(lib.obe_set_option(b'resample_fused', 1))
+        out[fused] = (alt.particles[:, :n].clone(), idx.clone(), zout.clone())
     assert torch.equal(out[1][1], out[0][1])
+    assert torch.equal(out[1][2], out[0][2])
     assert torch.equal(out[1][0], out[0][0])
     idx = out[1][1]
     assert int(idx.min()) >= 0 and int(idx.max()) < n and bool((idx[1:] >= idx[:-1]).all())
-    # the jitter really happened and is small: offspring stay within a few factor-widths of their ancestors
+    # the normals are the packed stream indexed by GLOBAL slot (restated in the oracle)
+    from oracle import obe_oracle as orc
+    want = orc.device_normals_packed(n, d, 99, 3, slot_begin=slot_begin)
+    np.testing.assert_allclose(out[1][2].cpu().numpy(), want, rtol=0, atol=1e-4)
     moved = (out[1][0] - torch.from_numpy(prior).cuda()[:, idx]).abs().max().item()
     assert 0.0 < moved < 10.0 * float(np.abs(factor).max()) + 1e-12
-
-
-@pytest.mark.parametrize('forced', [True, False], ids=['forced_resample', 'no_auto_resample'])
-def test_async_update_closed_loop(obe, forced):
-    """pdf_update with ``async_update`` (one C call, no synchronisation; the resample decision is known beforehand)
-    against the synchronous engine: same chosen settings, same clouds.  The pivot of the moment accumulators lags one
-    update behind, which moves the moments by rounding only."""
-    n = 40_000
-    kw = dict(resample_threshold=2.0) if forced else dict(auto_resample=False)
-    a, _, _ = _engine(obe, n, **kw)
-    b, _, _ = _engine(obe, n, **kw)
-    a.eager_select = a.async_update = True
-    a.rng = np.random.default_rng(5)
-    b.rng = np.random.default_rng(5)
-    meas = np.random.default_rng(9)
-    with warnings.catch_warnings():
-        warnings.simplefilter('ignore', RuntimeWarning)
-        xa, xb = a.opt_setting(), b.opt_setting()
-        for t in range(12):
-            assert xa == xb and a.last_setting_index == b.last_setting_index, f'cycle {t}'
-            y = 50400.0 - 1200.0 / (((xa[0] - 3.14) / 0.1) ** 2 + 1) + 500.0 * meas.standard_normal()
-            a.pdf_update((xa, y, 500.0))
-            b.pdf_update((xb, y, 500.0))
-            assert a.just_resampled == b.just_resampled == forced
-            xa, xb = a.opt_setting(), b.opt_setting()
-        if forced:
-            # (same ancestors; the Liu-West factor comes from moments accumulated around a one-update-older pivot)
-            spread = b.particles.std(axis=1, keepdims=True)
-            err = np.abs(a.particles - b.particles) / (np.abs(b.particles) * 1e-12 + spread * 1e-9)
-            assert err.max() <= 1.0
-        else:
-            np.testing.assert_array_equal(a.particles, b.particles)
-            np.testing.assert_allclose(a.particle_weights, b.particle_weights, rtol=1e-12, atol=1e-300)
-        np.testing.assert_allclose(a.mean(), b.mean(), rtol=1e-10)
-        np.testing.assert_allclose(a.n_eff(), b.n_eff(), rtol=1e-9)

@@ -1,6 +1,6 @@
 """Cost of a shard whose first global slot is odd/even in the one-kernel systematic resample (one GPU).
     python tools/bench_odd_shard.py [n]
-Times obe_resample_systematic_sharded for slot_begin in (0, 1, 2, 3) with the funnel stores on and off."""
+Times obe_resample_systematic_sharded for slot_begin in (0, 1, 2, 3)."""
 import ctypes as C
 import json
 import os
@@ -28,10 +28,9 @@ def main():
     mean = np.zeros(3)
     alt = pdf._buf.empty_like()
     for begin in (0, 1, 2, 3):
-        for shift in (1, 0):
+        for shift in (1,):
             n_total = n + begin
             cdf_total = total / (1.0 - begin / n_total)
-            lib.obe_set_option(b'resample_shift_stores', shift)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(22)]
             for t in range(21):
                 ev[t].record()
@@ -41,8 +40,7 @@ def main():
             ev[21].record()
             torch.cuda.synchronize()
             ms = float(np.median([ev[t].elapsed_time(ev[t + 1]) for t in range(1, 21)]))
-            print(json.dumps({'n': n, 'slot_begin': begin, 'shift_stores': shift, 'resample_ms': round(ms, 4)}), flush=True)
-    lib.obe_set_option(b'resample_shift_stores', 1)
+            print(json.dumps({'n': n, 'slot_begin': begin, 'resample_ms': round(ms, 4)}), flush=True)
 
 
 if __name__ == '__main__':
