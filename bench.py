@@ -355,12 +355,28 @@ def bench_c5(args, rank, world):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     e0.record()
     for _ in range(args.steps):
         eng.closed_loop_cycle(force_resample=args.force_resample)   # select -> simulate -> update/resample, no host
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
+    # per-phase split of the same cycle (events between the phases; outside the timed region)
+    pe = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    for t in range(args.steps):
+        pe[t][0].record()
+        eng.opt_setting(sync=False)
+        pe[t][1].record()
+        eng.simulate_measurement()
+        pe[t][2].record()
+        eng._update_from_record(1, eng.n_channels, args.force_resample)
+        pe[t][3].record()
+    torch.cuda.synchronize()
+    split = [float(np.mean([pe[t][i].elapsed_time(pe[t][i + 1]) for t in range(args.steps)])) for i in range(3)]
+    clocks = sampler.stop() if rank == 0 else None
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step(True)                        # e2e: chosen settings D2H, measurements H2D every cycle
@@ -382,6 +398,10 @@ def bench_c5(args, rank, world):
             'config': {'workload': 'batched demos/lockin: 4096 OBE instances x 1e4 particles, d=4, 2 channels, S=200 '
                                    '(BASELINE configs[4])', 'force_resample': bool(args.force_resample)},
             'instance_cycles_per_s': B_total * 1e3 / ms,
+            'kernels_ms': {'select (draws + utility + argmax)': split[0], 'simulate measurement': split[1],
+                           'update + resample of the flagged instances': split[2]},
+            'gpu_launches': 6 * args.steps, 'clocks': clocks,
+            'fp64_note': 'update and select are FP64-throughput-bound (lock-in model, 2 channels): see DESIGN 6b',
             'e2e': {'value': 1.0 / e2e_s, 'unit': 'batched cycles/s', 'h2d_bytes_per_step': B * 12 * 8,
                     'd2h_bytes_per_step': B * 8},
             'roofline': {'bound': 'hbm', 'achieved': b_cycle / world / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',

@@ -163,6 +163,16 @@ class Comm:
             self.dist.all_gather_into_tensor(out.view(-1), src, group=self.group)
         return out.view((self.world,) + tuple(vec.shape)).to(vec.device)
 
+    def alltoall_rows(self, dst, src, recv_sizes, send_sizes):
+        """all-to-all-v of one contiguous row: src is cut into send_sizes (one piece per rank, in rank order), dst is
+        filled with the recv_sizes pieces in rank order."""
+        if self.backend == 'gloo':
+            out = dst.cpu()
+            self.dist.all_to_all_single(out, src.cpu().contiguous(), list(recv_sizes), list(send_sizes), group=self.group)
+            dst.copy_(out)
+        else:
+            self.dist.all_to_all_single(dst, src, list(recv_sizes), list(send_sizes), group=self.group)
+
     def allreduce_sum(self, t):
         if self._staged(t):
             c = t.cpu()
@@ -270,6 +280,7 @@ class ShardedOptBayesExpt(OptBayesExpt):
         self._alt = self._buf.empty_like()
         counts = self._comm.allgather(torch.tensor([self._n_local], dtype=torch.int64, device=dev))
         self.n_total = int(counts.sum().item())
+        self._caps = self._comm.allgather(torch.tensor([self._buf.ld], dtype=torch.int64, device=dev)).cpu().numpy().reshape(-1)
         self._plan = torch.zeros(_lib.PLAN_LEN, dtype=torch.float64, device=dev)
         self._check(self._lib.obe_set_uniform_total(self._cs(), self.n_total, self._stream()))
         n_set = len(self.setting_indices)
@@ -359,8 +370,12 @@ class ShardedOptBayesExpt(OptBayesExpt):
             ph = self._plan.cpu().numpy()
             if ph[_lib.PLAN_OVERFLOW] == 2.0:
                 raise RuntimeError('peer exchange timed out: a rank died or the ranks fell out of step')
-            if ph[_lib.PLAN_OVERFLOW] != 0.0:
-                raise RuntimeError('a shard outgrew its buffer capacity in a resample; raise `slack`')
+            # (checked against every rank's capacity, so that all ranks raise together and nobody walks into the
+            # next collective alone; the device-side word only knows the local buffer)
+            counts = ph[_lib.PLAN_COUNTS:_lib.PLAN_COUNTS + self._comm.world]
+            if ph[_lib.PLAN_OVERFLOW] != 0.0 or np.any(counts > self._caps):
+                raise RuntimeError('a shard outgrew its buffer capacity in a resample; raise `slack` '
+                                   '(or call rebalance() before the lengths drift that far)')
             self._plan_host = ph
             self._gstats = gstats_from_plan(ph, self.n_dims, self._comm.world)
             self._gmom = moments_from(self._gstats, self.n_dims)
@@ -432,6 +447,65 @@ class ShardedOptBayesExpt(OptBayesExpt):
         self._weights_uniform = True
         self._weights_lazy = False
         self._section = 1           # the plan stays valid for draws: its post-resample totals apply
+
+    # ---- rebalancing (SURVEY hard part 10): shard lengths drift by a fraction of a percent per resample
+    def rebalance(self, force=False, threshold=0.9):
+        """Equalise the shard lengths with one all-to-all-v per particle row.  Collective (every rank must call it) and
+        synchronising.  Shards are contiguous pieces of the global cloud in rank order, so the cloud's order -- and
+        with it every later result -- is unchanged; only the cut points move back to n_total*g/G.  Without ``force``
+        nothing moves unless some shard has grown beyond ``threshold`` of its buffer capacity (the decision is taken
+        from the all-gathered lengths and capacities, identically on every rank).  Returns True if particles moved.
+
+        A SINGLE resample that concentrates more than the slack allows on one shard still overflows (the plan flags
+        it and the next host look raises): counts can only be balanced after the offspring exist."""
+        import torch
+        comm, dev = self._comm, self._buf.device
+        G, r = comm.world, comm.rank
+        info = comm.allgather(torch.tensor([float(self.n_particles), float(self._buf.ld)], dtype=torch.float64,
+                                           device=dev)).cpu().numpy()
+        counts, caps = info[:, 0].astype(np.int64), info[:, 1].astype(np.int64)
+        if not force and not np.any(counts > threshold * caps):
+            return False
+        n = int(counts.sum())
+        starts = np.concatenate([[0], np.cumsum(counts)])
+        targets = np.array([n * g // G for g in range(G + 1)], dtype=np.int64)
+        if np.any(np.diff(targets) > caps):
+            raise RuntimeError('rebalance: an equal share does not fit a shard buffer; raise `slack`')
+
+        def overlap(a0, a1, b0, b1):
+            return int(max(0, min(a1, b1) - max(a0, b0)))
+        send = [overlap(starts[r], starts[r + 1], targets[p], targets[p + 1]) for p in range(G)]
+        recv = [overlap(starts[p], starts[p + 1], targets[r], targets[r + 1]) for p in range(G)]
+        c_old, c_new = int(counts[r]), int(targets[r + 1] - targets[r])
+        uniform = bool(self._weights_uniform)
+        if not uniform:
+            self._check(self._lib.obe_materialize_weights(self._cs(), self._stream()))
+        torch.cuda.synchronize()
+        for j in range(self.n_dims):
+            comm.alltoall_rows(self._alt.particles[j, :c_new], self._buf.particles[j, :c_old], recv, send)
+        if not uniform:
+            comm.alltoall_rows(self._alt.weights[:c_new], self._buf.weights[:c_old], recv, send)
+            self._alt.stats.copy_(self._buf.stats)             # the normaliser INVS travels with the weights
+        self._buf, self._alt = self._alt, self._buf
+        self._buf.n_dev.fill_(c_new)
+        self._alt.n_dev.fill_(c_new)
+        self._n_local = c_new
+        self._cloud_version += 1
+        OptBayesExpt._invalidate(self, particles=True)
+        self._stats = None
+        if uniform:
+            self._check(self._lib.obe_set_uniform_total(self._cs(), self.n_total, self._stream()))
+            self._weights_lazy = False
+            self._moments_valid = False
+        else:
+            ni = self._noise_index
+            self._check(self._lib.obe_refresh(self._cs(), 0, 0, _lib.iarr(ni), 0 if ni is None else len(ni),
+                                              _lib.darr(self._pivot, _lib.MAX_PARAMS), 0, self._stream()))
+            self._moments_valid = True
+        self._gstats = None
+        self._plan_valid = False
+        self._make_plan()
+        return True
 
     @property
     def shard_counts(self):

@@ -265,6 +265,102 @@ def _worker_early(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _worker_rebalance(rank, world, port, out):
+    """rebalance(): one all-to-all-v per row moves the cut points back to n_total*g/G; the global cloud (order, values,
+    weights) is unchanged and the engine carries on as the single-cloud engine does.  Also the failure mode: a shard
+    that outgrows its buffer in ONE resample is flagged and the next host look raises."""
+    import warnings
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    _init_group(rank, world)
+    try:
+        import optbayesexpt_b200 as obe
+        from optbayesexpt_b200.sharded import ShardedOptBayesExpt
+        from oracle.scenarios import build_inputs, by_name
+        sc = by_name('c1_find_peak')
+        n = 50000
+        inp = build_inputs(sc, n)
+        cut = [0, 31000, n]
+        lo, hi = cut[rank], cut[rank + 1]
+        kw = dict(scale=False, default_noise_std=500.0, seed=77, auto_resample=False)
+        eng = ShardedOptBayesExpt('lorentzian_hwhm', inp['setting_values'], inp['prior'][:, lo:hi], inp['cons'],
+                                  slack=0.5, **kw)
+        ref = obe.OptBayesExpt('lorentzian_hwhm', inp['setting_values'], inp['prior'], inp['cons'], **kw)
+
+        def global_cloud(e):
+            cap = n                               # (the same shape on every rank: the collective needs it)
+            pad = torch.zeros((e.n_dims + 1, cap), dtype=torch.float64, device=e._buf.device)
+            m = e.n_particles
+            pad[:e.n_dims, :m] = torch.from_numpy(e.particles).to(pad.device)
+            pad[e.n_dims, :m] = torch.from_numpy(e.particle_weights).to(pad.device)
+            allp = e._comm.allgather(pad).cpu().numpy()
+            counts = e.shard_counts
+            return np.concatenate([allp[g][:, :counts[g]] for g in range(world)], axis=1), counts
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', RuntimeWarning)
+            assert eng.rebalance() is False                       # nothing near its capacity: no-op without force
+            # (1) explicit, non-uniform weights travel with their particles
+            rec = ((3.0,), 49700.0, 500.0)
+            eng.pdf_update(rec)
+            ref.pdf_update(rec)
+            before, c0 = global_cloud(eng)
+            assert list(c0) == [31000, 19000]
+            assert eng.rebalance(force=True) is True
+            after, c1 = global_cloud(eng)
+            assert list(c1) == [25000, 25000] and eng.n_particles == 25000
+            np.testing.assert_array_equal(after, before)
+            np.testing.assert_allclose(after[-1], ref.particle_weights, rtol=1e-12, atol=1e-300)
+            np.testing.assert_allclose(eng.mean(), ref.mean(), rtol=1e-12)
+            np.testing.assert_allclose(eng.n_eff(), ref.n_eff(), rtol=1e-12)
+            eng.rng = np.random.default_rng(3)
+            ref.rng = np.random.default_rng(3)
+            s1, s2 = eng.opt_setting(), ref.opt_setting()
+            assert eng.last_setting_index == ref.last_setting_index
+            # (2) after a resample: implicit uniform weights, lengths drifted again
+            rec = (s1, 49900.0, 500.0)
+            eng.pdf_update(rec)
+            ref.pdf_update(rec)
+            eng.resample()
+            before, c2 = global_cloud(eng)
+            assert c2.sum() == n and c2[0] != c2[1]
+            assert eng.rebalance(force=True) is True
+            after, c3 = global_cloud(eng)
+            assert list(c3) == [25000, 25000]
+            np.testing.assert_array_equal(after, before)
+            np.testing.assert_array_equal(after[-1], np.full(n, 1.0 / n))
+            # and the engine carries on: update + resample + selection
+            eng.pdf_update((s1, 50100.0, 500.0))
+            eng.resample()
+            eng.opt_setting()
+            assert eng.shard_counts.sum() == n
+        # (3) failure mode: no slack at all and all the weight on rank 0's particles -> rank 0 must hold every offspring
+        tight = ShardedOptBayesExpt('lorentzian_hwhm', inp['setting_values'], inp['prior'][:, lo:hi], inp['cons'],
+                                    slack=0.0, **kw)
+        w = np.zeros(hi - lo)
+        if rank == 0:
+            w[:] = 1.0 / (hi - lo)
+        tight.particle_weights = w
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', RuntimeWarning)
+            tight._plan_valid = False
+            tight._moments_valid = False
+            try:
+                tight._fetch_plan()
+                raised = False
+            except RuntimeError as exc:
+                raised = 'raise `slack`' in str(exc)
+        assert raised, 'a shard that cannot hold its offspring must be reported'
+        out.put((rank, 'ok'))
+    except Exception as exc:  # pragma: no cover
+        import traceback
+        out.put((rank, traceback.format_exc()))
+        raise exc
+    finally:
+        dist.destroy_process_group()
+
+
 def _spawn(worker, peer, backend='gloo'):
     """Two ranks on the one GPU (gloo carries the host-side collectives).  peer='1': the stats and the draws travel
     by peer writes into CUDA-IPC-mapped buffers + flags instead of collectives (the NVLink path of a real node).
@@ -279,10 +375,21 @@ def _spawn(worker, peer, backend='gloo'):
         procs = [ctx.Process(target=worker, args=(r, 2, port, out)) for r in range(2)]
         for p in procs:
             p.start()
-        results = [out.get(timeout=600) for _ in procs]
-        for p in procs:
-            p.join(timeout=60)
+        results = []
+        try:
+            for _ in procs:
+                results.append(out.get(timeout=240))
+                if results[-1][1] != 'ok':
+                    break                        # the peer of a failed rank would wait in a collective for ever
+        except Exception:                        # queue.Empty: a rank hangs
+            results.append((-1, 'timeout: a rank did not report within 240 s'))
+        if all(msg == 'ok' for _, msg in results):
+            for p in procs:
+                p.join(timeout=60)
     finally:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
         os.environ.pop('OBE_PEER_EXCHANGE', None)
         os.environ.pop('OBE_TEST_BACKEND', None)
     for rank, msg in results:
@@ -304,17 +411,22 @@ def test_two_shards_early_select(obe_lib, peer):
     _spawn(_worker_early, peer)
 
 
+@pytest.mark.parametrize('peer', ['0', '1'], ids=['collectives', 'peer_exchange'])
+def test_two_shards_rebalance(obe_lib, peer):
+    _spawn(_worker_rebalance, peer)
+
+
 def _two_gpus():
     import torch
     return torch.cuda.is_available() and torch.cuda.device_count() >= 2
 
 
 @pytest.mark.parametrize('peer', ['0', '1'], ids=['nccl_collectives', 'nvlink_peer_exchange'])
-@pytest.mark.parametrize('worker', ['base', 'noise', 'early'])
+@pytest.mark.parametrize('worker', ['base', 'noise', 'early', 'rebalance'])
 def test_two_gpus_nccl(obe_lib, peer, worker):
     """The same two-shard comparisons on TWO GPUs: NCCL collectives / peer buffers mapped over NVLink (CUDA IPC between
     devices).  Skipped on a one-GPU box (the driver's GPU test box); bench.py --gpus N runs the same invariance check
     on every multi-GPU run (`invariance` in its JSON line)."""
     if not _two_gpus():
         pytest.skip('needs >= 2 GPUs')
-    _spawn({'base': _worker, 'noise': _worker_noise, 'early': _worker_early}[worker], peer, backend='nccl')
+    _spawn({'base': _worker, 'noise': _worker_noise, 'early': _worker_early, 'rebalance': _worker_rebalance}[worker], peer, backend='nccl')
