@@ -375,6 +375,7 @@ __global__ void __launch_bounds__(OBE_THREADS) k_draw(const ObeDrawArgs a) {
     __shared__ double sm[8];
     __shared__ int cnt[OBE_THREADS / 32];
     const int q = blockIdx.x;
+    obe_grid_dep_launch();
     double uq = a.u[q];
     const long long n = a.n_dev ? *a.n_dev : a.n;
     const long long n_tiles = a.n_dev ? (n + OBE_TILE - 1) / OBE_TILE : a.n_tiles;
@@ -752,6 +753,8 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
     __shared__ long long sml[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     __shared__ int smi[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     const int t = threadIdx.x;
+    obe_grid_dep_launch();
+    obe_grid_dep_wait();
     if (t == 0 && unit_counter) *unit_counter = 0u;        // the streaming kernel hands its units out dynamically
     if (n_dev) n_tiles = (*n_dev + OBE_TILE - 1) / OBE_TILE;
     if (plan) {
@@ -834,6 +837,20 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
 // exchanged through distributed shared memory -- each CTA writes its total into every CTA's copy, one
 // cluster barrier, then every CTA folds the totals of the segments before it into its own results.
 #define OBE_PLAN_CLUSTER 8
+// Launch with the programmatic-stream-serialization attribute (obe_grid_dep_wait in the kernel): the launch latency and
+// the prologue of a dependent kernel overlap the tail of its predecessor in the stream.
+static int64_t g_pdl = 1;                         /* obe_set_option("pdl") */
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static int64_t g_utility_lane_fill = 50;          /* obe_set_option("utility_lane_fill"), percent of resident threads */
 static int64_t g_plan_cluster_min_tiles = 8192;   /* obe_set_option("plan_cluster_min_tiles") */
 static int64_t g_utility_cache = 1;               /* obe_set_option("utility_cache"): park the K curves in shared memory */
@@ -854,6 +871,8 @@ k_sys_plan_cluster(const double* __restrict__ prefix, long long n_tiles, long lo
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int r = (int)cluster.block_rank();
+    obe_grid_dep_launch();
+    obe_grid_dep_wait();
     if (r == 0 && threadIdx.x == 0 && unit_counter) *unit_counter = 0u;
     __shared__ long long sml[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     __shared__ int smi[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
@@ -1485,14 +1504,15 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
     __shared__ WrUnit wu[NWARP];
     __shared__ int s_units;
     __shared__ long long s_tiles_in;
+    for (int q = threadIdx.x; q < NWARP * OBE_WR_MARKS / 2; q += OBE_THREADS)
+        reinterpret_cast<unsigned int*>(wr_marks)[q] = 0u;
+    obe_grid_dep_wait();                                 // (programmatic dependent launch: the plan kernel is done)
     if (threadIdx.x == 0) {
         long long n_tiles_in;
         cs = sys_ctx_of(a, n_tiles_in);
         s_units = a.unit_start[n_tiles_in];
         s_tiles_in = n_tiles_in;
     }
-    for (int q = threadIdx.x; q < NWARP * OBE_WR_MARKS / 2; q += OBE_THREADS)
-        reinterpret_cast<unsigned int*>(wr_marks)[q] = 0u;
     setup_factor<D>(a, sF, sMean);                       // ends with a block barrier
     const SysCtx& c = cs;
     if (blockIdx.x == 0) {
@@ -1804,6 +1824,7 @@ __global__ void __launch_bounds__(OBE_PICK_WARPS * 32) k_sys_pick(const ObeResam
         cs = sys_ctx_of(a, n_tiles_in);
         s_tiles_in = n_tiles_in;
     }
+    obe_grid_dep_launch();                               // the utility kernel may be scheduled; it waits for this grid
     setup_factor<D>(a, sF, sMean);                       // ends with a block barrier
     const SysCtx& c = cs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -2171,6 +2192,8 @@ __global__ void __launch_bounds__(OBE_STATS_LEN) k_shard_plan_peer(const ObePeer
                                                                    long long* __restrict__ n_out_dev) {
     __shared__ int ok;
     const int t = threadIdx.x, parity = (int)(epoch & 1ull);
+    obe_grid_dep_launch();
+    obe_grid_dep_wait();
     double* mine = peers.p[rank];
     const double v = stats_local[t];
     for (int g = 0; g < world; ++g) peers.p[g][OBE_PEER_STATS + (parity * OBE_PEER_MAX + rank) * OBE_STATS_LEN + t] = v;
@@ -2225,7 +2248,7 @@ __global__ void __launch_bounds__(OBE_STATS_LEN) k_shard_plan_peer(const ObePeer
 #define OBE_DIM_CASE_WR(dd, grid, st, args)                                                               \
     case dd:                                                                                              \
         cudaFuncSetAttribute(k_sys_resample_warp<dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBE_WR_SMEM); \
-        k_sys_resample_warp<dd><<<grid, OBE_THREADS, OBE_WR_SMEM, st>>>(args);                              \
+        launch_pdl(k_sys_resample_warp<dd>, dim3(grid), dim3(OBE_THREADS), OBE_WR_SMEM, st, args);           \
         break;
 #define OBE_DIM_SWITCH_WR(d, grid, st, args)                                          \
     switch (d) {                                                                      \
@@ -2403,9 +2426,20 @@ static int make_builtin(int d, obe_model* m) {
     return obe_fail("built-in model supports n_params in [NP, NP+2]; compile it from source for other sizes%s%s");
 }
 
-static int launch_kernel(const void* f, int grid, size_t smem, cudaStream_t st, const void* args_struct) {
+static int launch_kernel(const void* f, int grid, size_t smem, cudaStream_t st, const void* args_struct, bool pdl = false) {
     void* params[1] = {const_cast<void*>(args_struct)};
-    cudaError_t e = cudaLaunchKernel(f, dim3(grid), dim3(OBE_THREADS), params, smem, st);
+    cudaError_t e;
+    if (pdl) {                                   // the kernel calls obe_grid_dep_wait() before it reads anything
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(OBE_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        e = cudaLaunchKernelExC(&cfg, f, params);
+    } else {
+        e = cudaLaunchKernel(f, dim3(grid), dim3(OBE_THREADS), params, smem, st);
+    }
     if (e != cudaSuccess) return obe_fail("cudaLaunchKernel: %s%s", cudaGetErrorString(e));
     return 0;
 }
@@ -2490,6 +2524,7 @@ int obe_set_option(const char* name, int64_t value) {
     if (s == "resample_fused") { g_resample_fused = value ? 1 : 0; return 0; }
     if (s == "resample_blocks") { g_resample_blocks = value < 0 ? 0 : value; return 0; }
     if (s == "resample_reserve_ctas") { g_resample_reserve = value < 0 ? 0 : value; return 0; }
+    if (s == "pdl") { g_pdl = value ? 1 : 0; return 0; }
     if (s == "resample_dynamic") { g_resample_dynamic = value ? 1 : 0; return 0; }
     if (s == "resample_units_per_sm") { g_resample_units_per_sm = value < 1 ? 1 : value; return 0; }
     return obe_fail("unknown option '%s'%s", name);
@@ -2997,14 +3032,16 @@ static int resample_systematic_impl(const obe_cloud_t* in, const obe_cloud_t* ou
     cudaStream_t st = (cudaStream_t)stream;
     a.chunk = plan_chunk(out->n);
     if (a.n_tiles > g_plan_cluster_min_tiles)
-        k_sys_plan_cluster<<<OBE_PLAN_CLUSTER, OBE_SCAN_THREADS, 0, st>>>(
-            in->tile_prefix_dev, a.n_tiles, n_total, u0, sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0,
-            slot_begin, slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr, a.chunk, s.counter + 18);
+        launch_pdl(k_sys_plan_cluster, dim3(OBE_PLAN_CLUSTER), dim3(OBE_SCAN_THREADS), 0, st,
+                   (const double*)in->tile_prefix_dev, (long long)a.n_tiles, (long long)n_total, u0,
+                   sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0, (long long)slot_begin, (long long)slot_end,
+                   s.plan_h, s.unit_start, (int*)a.unit_tile, (const long long*)nullptr, (const double*)nullptr, a.chunk,
+                   s.counter + 18);
     else
-        k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, u0,
-                                                  sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0, slot_begin,
-                                                  slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile, nullptr, nullptr,
-                                                  a.chunk, s.counter + 18);
+        launch_pdl(k_sys_plan, dim3(1), dim3(OBE_SCAN_THREADS), 0, st, (const double*)in->tile_prefix_dev,
+                   (long long)a.n_tiles, (long long)n_total, u0, sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0,
+                   (long long)slot_begin, (long long)slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile,
+                   (const long long*)nullptr, (const double*)nullptr, a.chunk, s.counter + 18);
     OBE_LAUNCH_CHECK("k_sys_plan");
     return launch_sys_resample(in, out, a, out->n, st);
 }
@@ -3079,10 +3116,9 @@ int obe_shard_plan_peer(void* const* peer_bufs, int rank, int world, uint64_t ep
     if (epoch == 0) return obe_fail("peer exchange epochs start at 1%s%s");
     ObePeers pp;
     if (fill_peers(peer_bufs, rank, world, pp)) return -1;
-    k_shard_plan_peer<<<1, OBE_STATS_LEN, 0, (cudaStream_t)stream>>>(pp, rank, world, epoch, d, u0, n_total, a_param, lazy,
-                                                                      out ? out->ld : (1ll << 62), plan_dev,
-                                                                      local->stats_dev,
-                                                                      out ? (long long*)out->n_dev : nullptr);
+    launch_pdl(k_shard_plan_peer, dim3(1), dim3(OBE_STATS_LEN), 0, (cudaStream_t)stream, pp, rank, world,
+               (unsigned long long)epoch, d, u0, (long long)n_total, a_param, lazy, out ? (long long)out->ld : (1ll << 62),
+               plan_dev, local->stats_dev, out ? (long long*)out->n_dev : (long long*)nullptr);
     OBE_LAUNCH_CHECK("k_shard_plan_peer");
     return 0;
 }
@@ -3135,13 +3171,14 @@ int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* ou
     cudaStream_t st = (cudaStream_t)stream;
     a.chunk = plan_chunk(out->ld);
     if (a.n_tiles > g_plan_cluster_min_tiles)
-        k_sys_plan_cluster<<<OBE_PLAN_CLUSTER, OBE_SCAN_THREADS, 0, st>>>(
-            in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0, s.plan_h, s.unit_start, (int*)a.unit_tile,
-            (const long long*)in->n_dev, plan_dev, a.chunk, s.counter + 18);
+        launch_pdl(k_sys_plan_cluster, dim3(OBE_PLAN_CLUSTER), dim3(OBE_SCAN_THREADS), 0, st,
+                   (const double*)in->tile_prefix_dev, (long long)a.n_tiles, (long long)n_total, 0.0, 0.0, 1.0, 0ll, 0ll,
+                   s.plan_h, s.unit_start, (int*)a.unit_tile, (const long long*)in->n_dev, plan_dev, a.chunk,
+                   s.counter + 18);
     else
-        k_sys_plan<<<1, OBE_SCAN_THREADS, 0, st>>>(in->tile_prefix_dev, a.n_tiles, n_total, 0.0, 0.0, 1.0, 0, 0,
-                                                  s.plan_h, s.unit_start, (int*)a.unit_tile,
-                                                  (const long long*)in->n_dev, plan_dev, a.chunk, s.counter + 18);
+        launch_pdl(k_sys_plan, dim3(1), dim3(OBE_SCAN_THREADS), 0, st, (const double*)in->tile_prefix_dev,
+                   (long long)a.n_tiles, (long long)n_total, 0.0, 0.0, 1.0, 0ll, 0ll, s.plan_h, s.unit_start,
+                   (int*)a.unit_tile, (const long long*)in->n_dev, plan_dev, a.chunk, s.counter + 18);
     OBE_LAUNCH_CHECK("k_sys_plan");
     return launch_sys_resample(in, out, a, out->ld, st);
 }
@@ -3348,7 +3385,7 @@ int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* set
             } else { a.cache = 1; smem = with_cache; }
         }
     }
-    return launch_kernel(m->f_utility, (int)blocks, smem, (cudaStream_t)stream, &a);
+    return launch_kernel(m->f_utility, (int)blocks, smem, (cudaStream_t)stream, &a, true);
 }
 
 int obe_pick(const double* utility_dev, int64_t n_settings, double pickiness, double u, int64_t* idx_dev,

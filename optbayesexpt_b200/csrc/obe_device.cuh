@@ -248,6 +248,14 @@ __device__ __forceinline__ void obe_bulk_g2s(void* dst_smem, const void* src_gme
 __device__ __forceinline__ void obe_named_bar(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still running; it must call obe_grid_dep_wait() before it touches
+// anything the predecessor writes (the call returns once the predecessor grid has completed and its writes are
+// visible; a no-op for a normal launch).  obe_grid_dep_launch() in the predecessor lets the dependents be scheduled
+// from that point on instead of at its exit.  Used along the cycle's chain of small dependent kernels (update ->
+// shard plan -> resample plan -> streaming resample) to take their launch latency and prologues off the critical path.
+__device__ __forceinline__ void obe_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void obe_grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // The fused Bayesian update: a persistent, warp-specialised kernel, one CTA per SM.
@@ -827,6 +835,7 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
         }
     }
 
+    obe_grid_dep_launch();       // the (tiny) dependents may be scheduled now; they wait for this grid to complete
     // ---- per-block partials, then the last block to arrive combines them in block order
     double vals[NACC];
     vals[0] = acc.sumsq; vals[1] = acc.sumt; vals[2] = acc.nzero;
@@ -1346,6 +1355,7 @@ __device__ void obe_utility_body(const ObeUtilityArgs& a) {
     __shared__ unsigned int is_last;
     const int tid = threadIdx.x;
     const int K = a.k;
+    obe_grid_dep_wait();         // (programmatic dependent launch: the kernel that produces the draws is done)
     for (int q = tid; q < K * Model::NP; q += blockDim.x) {
         const int k = q / Model::NP, j = q % Model::NP;
         sdraw[q] = a.draws[(long long)j * K + k];

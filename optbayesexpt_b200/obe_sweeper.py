@@ -129,8 +129,12 @@ class OptBayesExptSweeper(OptBayesExptNoiseParameter):
         import warnings
         ys = list(ys)
         i, m_total = 0, len(xs)
+        # Without the resample test (auto_resample off) nothing renormalises the running product inside a launch --
+        # the reference renormalises after every point -- so a launch is kept to a few points: the product of 8
+        # particle-independent-scaled likelihoods cannot underflow for every particle at once, 128 of them can.
+        cap = _lib.MULTI_MAX if self.tuning_parameters['auto_resample'] else 8
         while i < m_total:
-            j = min(i + max(1, min(self._sweep_chunk, _lib.MULTI_MAX)), m_total)
+            j = min(i + max(1, min(self._sweep_chunk, cap)), m_total)
             first, ratio = self._multi_update(xs[i:j], ys[i:j])
             if first < 0:
                 self._commit_multi()

@@ -629,6 +629,13 @@ class ShardedOptBayesExpt(OptBayesExpt):
             out[lo:hi] = allu[r, :hi - lo]
         return out
 
+    def random_setting(self):
+        """Uniformly random setting (obe_base.py:791-805), drawn from the instance Generator: identically seeded on
+        every rank, so all ranks measure at the same setting (the module-level Generator of the base class is not)."""
+        settingindex = int(self.rng.choice(self.setting_indices))
+        self.last_setting_index = settingindex
+        return self.allsettings[:, settingindex]
+
     def good_setting(self, pickiness=None):
         import torch
         if pickiness is None:
