@@ -170,7 +170,7 @@ def test_multi_point_update_matches_point_by_point(obe):
     b = obe.OptBayesExptSweeper(sc['model'], inp['setting_values'], inp['prior'], inp['cons'], noise_parameter_index=3,
                                 scale=False, seed=1, auto_resample=False)
     a.fused_sweep, b.fused_sweep = True, False
-    a._sweep_chunk = 128                                        # the whole sweep in one launch
+    a._sweep_chunk = 128               # (without the resample test a launch is capped at 8 points: 7 launches)
     neff = []
     for x, y in zip(xs, ys):
         b.pdf_update(((np.array([x]),), np.array([y])))
@@ -180,7 +180,12 @@ def test_multi_point_update_matches_point_by_point(obe):
     assert_allclose(wa, wb, rtol=1e-11, atol=1e-15 * wb.max())
     assert_allclose(a.mean(), b.mean(), rtol=1e-11)
     assert_allclose(a.std(), b.std(), rtol=1e-8)
-    sums = a._multi_sums.cpu().numpy()[:len(xs)]
+    # the whole sweep in ONE launch (the kernel entry itself, below the chunk policy): per-point sums -> N_eff
+    d = obe.OptBayesExptSweeper(sc['model'], inp['setting_values'], inp['prior'], inp['cons'], noise_parameter_index=3,
+                                scale=False, seed=1, auto_resample=False)
+    first, _ = d._multi_update(xs, ys)
+    assert first == -1
+    sums = d._multi_sums.cpu().numpy()[:len(xs)]
     assert_allclose(sums[:, 0] ** 2 / sums[:, 1], neff, rtol=1e-10)
     # with the resample test on, the kernel reports the first point whose N_eff falls below the threshold
     c = obe.OptBayesExptSweeper(sc['model'], inp['setting_values'], inp['prior'], inp['cons'], noise_parameter_index=3,
