@@ -46,7 +46,8 @@ enum {
     OBE_STAT_NOISE = 56,  /* [4]  sum t sigma_c^2                                            */
     OBE_STAT_SUMT = 60,   /* sum t from the same pass as the moments                         */
     OBE_STAT_NZERO = 61,  /* particles newly zeroed by the constraint mask                   */
-    OBE_STAT_UNIFORM = 62 /* > 0: weights are implicit, every live particle weighs this much */
+    OBE_STAT_UNIFORM = 62, /* > 0: weights are implicit, every live particle weighs this much */
+    OBE_STAT_FIRED = 63   /* 1: the device-side resample test of that update fired (obe_cycle, resample == 2) */
 };
 
 /* The particle cloud resident in HBM (ParticlePDF state, particlepdf.py:96-126). */
@@ -257,7 +258,7 @@ typedef struct obe_cycle {
     int32_t noise_index[OBE_MAX_CHANNELS];
     int32_t has_sigma, has_noise_index, n_lik_channels, use_choke;
     double choke;
-    int32_t resample, scale;            /* resample: 0 = no, 1 = forced systematic */
+    int32_t resample, scale;            /* resample: 0 = no, 1 = forced systematic, 2 = decided on the device (below) */
     double u0, a_param;
     uint64_t seed;
     uint32_t epoch, mask_le, mask_lt;
@@ -284,8 +285,24 @@ typedef struct obe_cycle {
     void* select_scratch_dev;
     void* stream;
     void* side_stream;                  /* NULL: no overlap, everything on `stream` */
+    /* resample == 2: the resample test of particlepdf.py:236-258 is decided ON THE DEVICE by the update kernel
+     * (stats[OBE_STAT_FIRED] = N_eff < 0.1 N || N_eff / N < resample_threshold); plan, pick and streaming resample run
+     * gated on it, the plain K draws on its complement, the utility pass on whichever draws exist.  Whole clouds only,
+     * select != 0, no constraint masks.  The caller reads the outcome from stats_host[OBE_STAT_FIRED] after it has
+     * synchronised, and swaps cloud / alt if it fired. */
+    double resample_threshold;
+    /* optional PINNED host blocks, filled by asynchronous copies behind the cycle's kernels on `stream`:
+     * stats_host (64 doubles) <- the stats block the update wrote (stats_src_dev, default cloud->stats_dev);
+     * best_host (16 bytes) <- (int64 index, double value) of the argmax, when select != 0.  Valid after
+     * obe_stream_sync(stream). */
+    void* stats_host;
+    const double* stats_src_dev;
+    void* best_host;
 } obe_cycle_t;
 int obe_cycle(const obe_cycle_t* c);
+/* cudaStreamSynchronize(stream): what a closed loop waits on before it reads best_host / stats_host
+ * (the reference's opt_setting returns a host value, obe_base.py:733-756). */
+int obe_stream_sync(void* stream);
 /* randdraw(K) over a sharded cloud: this rank writes the draws it owns (per plan_dev; post=1 uses the
  * post-resample shard totals) and zeros elsewhere; an all-reduce(sum) of draws_dev completes it. */
 int obe_draw_planned(const obe_cloud_t* c, const double* u_host, int k, double* draws_dev,

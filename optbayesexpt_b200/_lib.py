@@ -23,7 +23,7 @@ MAX_SETTINGS = 4
 MAX_CONSTANTS = 8
 
 ST_TOTAL, ST_INVS, ST_SUMSQ, ST_NEFF = 0, 1, 2, 3
-ST_M1, ST_M2, ST_PIVOT, ST_NOISE, ST_SUMT, ST_NZERO, ST_UNIFORM = 4, 12, 48, 56, 60, 61, 62
+ST_M1, ST_M2, ST_PIVOT, ST_NOISE, ST_SUMT, ST_NZERO, ST_UNIFORM, ST_FIRED = 4, 12, 48, 56, 60, 61, 62, 63
 MULTI_MAX = 128
 
 
@@ -69,7 +69,9 @@ class Cycle(C.Structure):
                 ('method', C.c_int32), ('log_form', C.c_int32), ('pad0', C.c_int32),
                 ('cost_dev', C.c_void_p), ('kld_noise_dev', C.c_void_p), ('utility_dev', C.c_void_p),
                 ('best_dev', C.c_void_p), ('select_scratch_dev', C.c_void_p),
-                ('stream', C.c_void_p), ('side_stream', C.c_void_p)]
+                ('stream', C.c_void_p), ('side_stream', C.c_void_p),
+                ('resample_threshold', C.c_double), ('stats_host', C.c_void_p), ('stats_src_dev', C.c_void_p),
+                ('best_host', C.c_void_p)]
 
 
 _PD = C.POINTER(C.c_double)
@@ -124,6 +126,7 @@ SIGNATURES = {
     'obe_shard_plan_peer': (C.c_int, [C.POINTER(_VP), C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_double, C.c_int64,
                                       C.c_double, C.c_int, _PCLOUD, _PCLOUD, _VP, _VP]),
     'obe_cycle': (C.c_int, [C.POINTER(Cycle)]),
+    'obe_stream_sync': (C.c_int, [_VP]),
     'obe_resample_defer': (C.c_int, [C.c_int]),
     'obe_resample_pick': (C.c_int, [_PD, C.c_int, _VP, C.POINTER(_VP), C.c_int, C.c_int, C.c_uint64, _VP]),
     'obe_resample_emit': (C.c_int, [_VP]),

@@ -116,9 +116,28 @@ static size_t update_smem_bytes(int d, int src) {
     if (nst > 4) nst = 4;
     return (size_t)nst * bytes + 1024;
 }
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel, device) and calling thread instead of before every
+// launch: a small-cloud cycle is a chain of 5-10 us kernels and the host has to stay ahead of it.
+static cudaError_t set_max_smem(const void* f, size_t smem) {
+    struct Ent { const void* f; size_t smem; int dev; };
+    static thread_local Ent cache[96];
+    static thread_local int n_cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = -1; }
+    for (int i = 0; i < n_cached; ++i)
+        if (cache[i].f == f && cache[i].dev == dev) {
+            if (cache[i].smem == smem) return cudaSuccess;
+            const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) cache[i].smem = smem;
+            return e;
+        }
+    const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && dev >= 0 && n_cached < 96) cache[n_cached++] = Ent{f, smem, dev};
+    return e;
+}
 static int launch_update_kernel(const void* f, int d, int src, const ObeUpdateArgs& a, int grid, cudaStream_t st) {
     const size_t smem = update_smem_bytes(d, src);
-    cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = set_max_smem(f, smem);
     if (e != cudaSuccess) return obe_fail("cudaFuncSetAttribute(max dynamic smem): %s%s", cudaGetErrorString(e));
     void* params[1] = {const_cast<ObeUpdateArgs*>(&a)};
     e = cudaLaunchKernel(f, dim3(grid), dim3(OBE_UPDATE_THREADS), params, smem, st);
@@ -354,7 +373,15 @@ __device__ __forceinline__ unsigned long long* obe_peer_flags(double* buf, int k
     return reinterpret_cast<unsigned long long*>(buf + OBE_PEER_FLAGS) + (kind * 2 + parity) * OBE_PEER_MAX;
 }
 
+// Device-side resample decision (obe_cycle, resample == 2): the update writes stats[OBE_ST_FIRED]; the kernels of the
+// resample half run only when it is set (gate), the plain K-draw kernel only when it is not (gate_off).  Armed per
+// calling thread by obe_cycle around the entry points it chains, like the deferred emission below.
+static thread_local const double* g_gate_on = nullptr;
+static thread_local const double* g_gate_off = nullptr;
+static thread_local double g_update_gate_thr = 0.0, g_update_gate_n = 0.0;
+
 struct ObeDrawArgs {
+    const double* gate_off;     // optional: skip the whole launch when *gate_off != 0 (a resample fired instead)
     const double* w; const double* prefix; long long n; long long n_tiles;
     const double* particles; long long ld; int d;
     double* draws; long long* idx; int k;
@@ -376,6 +403,8 @@ __global__ void __launch_bounds__(OBE_THREADS) k_draw(const ObeDrawArgs a) {
     __shared__ int cnt[OBE_THREADS / 32];
     const int q = blockIdx.x;
     obe_grid_dep_launch();
+    obe_grid_dep_wait();                           // (a no-op unless launched with programmatic serialization)
+    if (a.gate_off && *a.gate_off != 0.0) return;
     double uq = a.u[q];
     const long long n = a.n_dev ? *a.n_dev : a.n;
     const long long n_tiles = a.n_dev ? (n + OBE_TILE - 1) / OBE_TILE : a.n_tiles;
@@ -624,6 +653,7 @@ struct ObeResampleArgs {
     unsigned int* unit_counter;    // one-kernel path: next unit to hand out (zeroed by the plan kernel); null: static stride
     unsigned int* anc;             // two-kernel path: ancestor (input index) of every output slot of this shard
     double* out_tile_sums; double* out_prefix; double* out_stats;   // CDF bookkeeping of the offspring cloud
+    const double* gate;            // optional: the one-kernel resample and the pick run only when *gate != 0
     double factor[OBE_MAX_DIMS * OBE_MAX_DIMS];
     double mean[OBE_MAX_DIMS];
 };
@@ -749,12 +779,14 @@ __global__ void __launch_bounds__(OBE_SCAN_THREADS) k_sys_plan(const double* __r
                                                                const long long* __restrict__ n_dev = nullptr,
                                                                const double* __restrict__ plan = nullptr,
                                                                int chunk = OBE_OUT_CHUNK,
-                                                               unsigned int* __restrict__ unit_counter = nullptr) {
+                                                               unsigned int* __restrict__ unit_counter = nullptr,
+                                                               const double* __restrict__ gate = nullptr) {
     __shared__ long long sml[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     __shared__ int smi[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     const int t = threadIdx.x;
     obe_grid_dep_launch();
     obe_grid_dep_wait();
+    if (gate && *gate == 0.0) return;                      // device-side resample test: it did not fire
     if (t == 0 && unit_counter) *unit_counter = 0u;        // the streaming kernel hands its units out dynamically
     if (n_dev) n_tiles = (*n_dev + OBE_TILE - 1) / OBE_TILE;
     if (plan) {
@@ -867,12 +899,13 @@ k_sys_plan_cluster(const double* __restrict__ prefix, long long n_tiles, long lo
                    double cdf_offset, double cdf_total, long long slot_begin, long long slot_end,
                    long long* __restrict__ H, int* __restrict__ unit_start, int* __restrict__ unit_tile,
                    const long long* __restrict__ n_dev, const double* __restrict__ plan, int chunk,
-                   unsigned int* __restrict__ unit_counter) {
+                   unsigned int* __restrict__ unit_counter, const double* __restrict__ gate) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int r = (int)cluster.block_rank();
     obe_grid_dep_launch();
     obe_grid_dep_wait();
+    if (gate && *gate == 0.0) return;                      // (every CTA of the cluster reads the same flag)
     if (r == 0 && threadIdx.x == 0 && unit_counter) *unit_counter = 0u;
     __shared__ long long sml[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
     __shared__ int smi[OBE_SCANW * (OBE_SCAN_THREADS / 32 + 1)];
@@ -1507,6 +1540,7 @@ __global__ void __launch_bounds__(OBE_THREADS, OBE_WR_BLOCKS(D)) k_sys_resample_
     for (int q = threadIdx.x; q < NWARP * OBE_WR_MARKS / 2; q += OBE_THREADS)
         reinterpret_cast<unsigned int*>(wr_marks)[q] = 0u;
     obe_grid_dep_wait();                                 // (programmatic dependent launch: the plan kernel is done)
+    if (a.gate && *a.gate == 0.0) return;                // device-side resample test: it did not fire
     if (threadIdx.x == 0) {
         long long n_tiles_in;
         cs = sys_ctx_of(a, n_tiles_in);
@@ -1819,12 +1853,14 @@ __global__ void __launch_bounds__(OBE_PICK_WARPS * 32) k_sys_pick(const ObeResam
     __shared__ double sMean[D];
     __shared__ SysCtx cs;
     __shared__ long long s_tiles_in;
+    obe_grid_dep_launch();                               // the utility kernel may be scheduled; it waits for this grid
+    obe_grid_dep_wait();                                 // (programmatic dependent launch: the plan kernel is done)
+    if (a.gate && *a.gate == 0.0) return;                // device-side resample test: it did not fire
     if (threadIdx.x == 0) {
         long long n_tiles_in;
         cs = sys_ctx_of(a, n_tiles_in);
         s_tiles_in = n_tiles_in;
     }
-    obe_grid_dep_launch();                               // the utility kernel may be scheduled; it waits for this grid
     setup_factor<D>(a, sF, sMean);                       // ends with a block barrier
     const SysCtx& c = cs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -2215,7 +2251,7 @@ __global__ void __launch_bounds__(OBE_STATS_LEN) k_shard_plan_peer(const ObePeer
 #define OBE_DIM_CASE(dd, KERNEL, grid, st, args)                                                          \
     case dd: {                                                                                            \
         const size_t smem_ = (dd <= OBE_STAGE_MAX_D) ? (size_t)dd * OBE_TILE * sizeof(double) : 0;        \
-        cudaFuncSetAttribute(KERNEL<dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);         \
+        set_max_smem((const void*)KERNEL<dd>, smem_);                                                      \
         KERNEL<dd><<<grid, OBE_THREADS, smem_, st>>>(args);                                                \
     } break;
 #define OBE_DIM_SWITCH(d, KERNEL, grid, st, args)                                     \
@@ -2247,7 +2283,7 @@ __global__ void __launch_bounds__(OBE_STATS_LEN) k_shard_plan_peer(const ObePeer
 
 #define OBE_DIM_CASE_WR(dd, grid, st, args)                                                               \
     case dd:                                                                                              \
-        cudaFuncSetAttribute(k_sys_resample_warp<dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBE_WR_SMEM); \
+        set_max_smem((const void*)k_sys_resample_warp<dd>, OBE_WR_SMEM);                                  \
         launch_pdl(k_sys_resample_warp<dd>, dim3(grid), dim3(OBE_THREADS), OBE_WR_SMEM, st, args);           \
         break;
 #define OBE_DIM_SWITCH_WR(d, grid, st, args)                                          \
@@ -2662,6 +2698,7 @@ static void base_update_args(const obe_cloud_t* c, ObeUpdateArgs& a, const doubl
     a.tile_prefix = c->tile_prefix_dev; a.renormalise = 1;
     for (int j = 0; j < OBE_MAX_CH; ++j) a.noise_idx[j] = -1;
     if (pivot) for (int j = 0; j < c->d; ++j) a.pivot[j] = pivot[j];
+    a.gate_thr = g_update_gate_thr; a.gate_n = g_update_gate_n;
 }
 static int finish_update(const obe_cloud_t*, int, cudaStream_t) {
     return 0;   // the update kernel's last block scans the tile sums itself (ObeUpdateArgs::tile_prefix)
@@ -2852,8 +2889,9 @@ static int draw_impl(const double* w, const double* prefix, int64_t n, const dou
         a.idx = idx_dev ? (long long*)idx_dev + off : nullptr;
         a.k = ld_draws > 0 ? ld_draws : k;
         a.n_dev = n_dev; a.plan = plan; a.post = post; a.stats = stats;
+        a.gate_off = g_gate_off;
         for (int i = 0; i < kk; ++i) a.u[i] = u_host[off + i];
-        k_draw<<<kk, OBE_THREADS, 0, st>>>(a);
+        launch_pdl(k_draw, dim3(kk), dim3(OBE_THREADS), 0, st, a);
         OBE_LAUNCH_CHECK("k_draw");
     }
     return 0;
@@ -2896,6 +2934,7 @@ static int fill_resample_args(const obe_cloud_t* in, const obe_cloud_t* out, con
     a.pout = out->particles_dev; a.ld_out = out->ld; a.w_out = out->weights_dev;
     a.stats = in->stats_dev;
     a.a_param = a_param; a.scale = scale; a.seed = seed; a.epoch = epoch; a.jitter = 1;
+    a.gate = g_gate_on;
     if (factor) {
         if (scale && !mean) return obe_fail("resample: mean required with a host factor when scale is on%s%s");
         for (int q = 0; q < in->d * in->d; ++q) a.factor[q] = factor[q];
@@ -3036,12 +3075,12 @@ static int resample_systematic_impl(const obe_cloud_t* in, const obe_cloud_t* ou
                    (const double*)in->tile_prefix_dev, (long long)a.n_tiles, (long long)n_total, u0,
                    sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0, (long long)slot_begin, (long long)slot_end,
                    s.plan_h, s.unit_start, (int*)a.unit_tile, (const long long*)nullptr, (const double*)nullptr, a.chunk,
-                   s.counter + 18);
+                   s.counter + 18, g_gate_on);
     else
         launch_pdl(k_sys_plan, dim3(1), dim3(OBE_SCAN_THREADS), 0, st, (const double*)in->tile_prefix_dev,
                    (long long)a.n_tiles, (long long)n_total, u0, sharded ? cdf_offset : 0.0, sharded ? cdf_total : 0.0,
                    (long long)slot_begin, (long long)slot_end, s.plan_h, s.unit_start, (int*)a.unit_tile,
-                   (const long long*)nullptr, (const double*)nullptr, a.chunk, s.counter + 18);
+                   (const long long*)nullptr, (const double*)nullptr, a.chunk, s.counter + 18, g_gate_on);
     OBE_LAUNCH_CHECK("k_sys_plan");
     return launch_sys_resample(in, out, a, out->n, st);
 }
@@ -3174,11 +3213,12 @@ int obe_resample_systematic_planned(const obe_cloud_t* in, const obe_cloud_t* ou
         launch_pdl(k_sys_plan_cluster, dim3(OBE_PLAN_CLUSTER), dim3(OBE_SCAN_THREADS), 0, st,
                    (const double*)in->tile_prefix_dev, (long long)a.n_tiles, (long long)n_total, 0.0, 0.0, 1.0, 0ll, 0ll,
                    s.plan_h, s.unit_start, (int*)a.unit_tile, (const long long*)in->n_dev, plan_dev, a.chunk,
-                   s.counter + 18);
+                   s.counter + 18, (const double*)nullptr);
     else
         launch_pdl(k_sys_plan, dim3(1), dim3(OBE_SCAN_THREADS), 0, st, (const double*)in->tile_prefix_dev,
                    (long long)a.n_tiles, (long long)n_total, 0.0, 0.0, 1.0, 0ll, 0ll, s.plan_h, s.unit_start,
-                   (int*)a.unit_tile, (const long long*)in->n_dev, plan_dev, a.chunk, s.counter + 18);
+                   (int*)a.unit_tile, (const long long*)in->n_dev, plan_dev, a.chunk, s.counter + 18,
+                   (const double*)nullptr);
     OBE_LAUNCH_CHECK("k_sys_plan");
     return launch_sys_resample(in, out, a, out->ld, st);
 }
@@ -3189,7 +3229,8 @@ int obe_resample_defer(int on) {
     return 0;
 }
 
-#define OBE_DIM_CASE_PICK(dd) case dd: k_sys_pick<dd><<<grid, OBE_PICK_WARPS * 32, 0, st>>>(g_parked.a, pk); break;
+#define OBE_DIM_CASE_PICK(dd) \
+    case dd: launch_pdl(k_sys_pick<dd>, dim3(grid), dim3(OBE_PICK_WARPS * 32), 0, st, g_parked.a, pk); break;
 
 int obe_resample_pick(const double* u_host, int k, double* draws_dev, void* const* peer_bufs, int rank, int world,
                       uint64_t epoch, void* stream) {
@@ -3250,8 +3291,73 @@ static int stream_edge(int which, void* from, void* to) {
 int obe_stream_fork(void* main_stream, void* side_stream) { return stream_edge(0, main_stream, side_stream); }
 int obe_stream_join(void* main_stream, void* side_stream) { return stream_edge(1, side_stream, main_stream); }
 
+int obe_stream_sync(void* stream) {
+    OBE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+// the results a closed loop waits for, copied into the caller's pinned host blocks behind the cycle's kernels
+static int cycle_copy_out(const obe_cycle_t* c, const obe_cloud_t* updated) {
+    cudaStream_t st = (cudaStream_t)c->stream;
+    if (c->best_host && c->select)
+        OBE_CUDA(cudaMemcpyAsync(c->best_host, c->best_dev, 16, cudaMemcpyDeviceToHost, st));
+    if (c->stats_host)
+        OBE_CUDA(cudaMemcpyAsync(c->stats_host, c->stats_src_dev ? c->stats_src_dev : updated->stats_dev,
+                                 OBE_STATS_LEN * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+// resample == 2: the resample test runs on the device.  The update's finishing block writes stats[FIRED]; plan, pick
+// and the streaming resample are launched gated on it, the plain K-draw kernel gated on its complement, and the
+// utility pass reads whichever draws were produced -- one stream, no host decision, the caller learns the outcome
+// from stats_host[OBE_ST_FIRED] when it synchronises for the argmax (and swaps cloud / alt if it fired).
+static int cycle_auto(const obe_cycle_t* c) {
+    void* st = c->stream;
+    const obe_cloud_t* live = c->cloud;
+    if (c->plan_dev) return obe_fail("obe_cycle: the device-side resample test is for a whole (unsharded) cloud%s%s");
+    if (!c->alt) return obe_fail("obe_cycle: resample needs the second buffer%s%s");
+    if (!c->select || (c->mask_le | c->mask_lt) != 0u || c->noise_from_stats || c->method == 3 || c->k < 1 ||
+        c->k > OBE_MAX_DRAWS || !g_resample_fused)
+        return obe_fail("obe_cycle: resample == 2 needs select, no constraint masks, var_noise by value, a variance/entropy "
+                        "utility, 1..128 draws and the one-kernel resample%s%s");
+    if (!(c->resample_threshold >= 0.0)) return obe_fail("obe_cycle: bad resample_threshold%s%s");
+    g_update_gate_thr = c->resample_threshold; g_update_gate_n = (double)live->n;
+    const int rc_u = obe_update(c->model, live, c->setting, c->constants, c->y_meas, c->has_sigma ? c->sigma : nullptr,
+                                c->has_noise_index ? c->noise_index : nullptr, c->n_lik_channels, c->use_choke, c->choke,
+                                c->pivot, st);
+    g_update_gate_thr = 0.0; g_update_gate_n = 0.0;
+    if (rc_u) return -1;
+    const double* fired = live->stats_dev + OBE_ST_FIRED;
+    g_gate_on = fired;
+    obe_resample_defer(1);
+    int rc = obe_resample_systematic(live, c->alt, c->u0, nullptr, nullptr, c->seed, c->epoch, c->a_param, c->scale, nullptr,
+                                     nullptr, st);
+    if (!rc) rc = obe_resample_pick(c->u, c->k, c->draws_dev, nullptr, 0, 1, 0, st);
+    g_gate_on = nullptr;
+    if (rc) { obe_resample_defer(0); return -1; }
+    g_gate_off = fired;
+    rc = obe_draw(live, c->u, c->k, c->draws_dev, nullptr, st);
+    g_gate_off = nullptr;
+    if (rc) { obe_resample_defer(0); return -1; }
+    if (obe_utility(c->model, c->draws_dev, c->k, c->settings_dev, c->lds, c->n_settings, c->constants, c->var_noise, nullptr,
+                    c->cost_dev, c->method, c->log_form, c->kld_noise_dev, c->utility_dev, c->best_dev,
+                    c->select_scratch_dev, st)) {
+        obe_resample_defer(0);
+        return -1;
+    }
+    if (obe_resample_emit(st)) return -1;
+    return cycle_copy_out(c, live);
+}
+
+static int cycle_body(const obe_cycle_t* c);
 int obe_cycle(const obe_cycle_t* c) {
     if (!c || !c->cloud || !c->model) return obe_fail("obe_cycle: null argument%s%s");
+    if (c->resample == 2) return cycle_auto(c);
+    if (cycle_body(c)) return -1;
+    return cycle_copy_out(c, c->cloud);
+}
+
+static int cycle_body(const obe_cycle_t* c) {
     void* st = c->stream;
     const obe_cloud_t* live = c->cloud;
     const int sharded = c->plan_dev != nullptr;
@@ -3380,7 +3486,7 @@ int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* set
         const size_t with_cache = smem + (size_t)k * m->nch * OBE_THREADS * sizeof(double);
         if (with_cache <= 100 * 1024) {
             if (with_cache > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(m->f_utility, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_cache);
+                cudaError_t e = set_max_smem(m->f_utility, with_cache);
                 if (e != cudaSuccess) { (void)cudaGetLastError(); } else { a.cache = 1; smem = with_cache; }
             } else { a.cache = 1; smem = with_cache; }
         }
@@ -3539,7 +3645,7 @@ static void fill_batch_args(const obe_batch_t* b, ObeBatchArgs& a) {
 }
 static int launch_batch_update(const void* f, int d, const ObeBatchArgs& a, int64_t n_inst, cudaStream_t st) {
     const size_t smem = update_smem_bytes(d, OBE_SRC_MODEL);
-    cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = set_max_smem(f, smem);
     if (e != cudaSuccess) return obe_fail("cudaFuncSetAttribute(max dynamic smem): %s%s", cudaGetErrorString(e));
     int64_t g = obe_sms();
     if (g > n_inst) g = n_inst;

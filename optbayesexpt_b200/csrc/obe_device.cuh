@@ -47,6 +47,8 @@
 #define OBE_ST_UNIFORM 62 /* > 0: the weights are IMPLICIT, every live particle weighs this much (set by a
                             systematic resample, which then never writes the weight row; cleared by the
                             next update, which never reads it) */
+#define OBE_ST_FIRED 63  /* 1.0: the resample test of the update that wrote this block fires (device predicate of
+                            obe_cycle's resample == 2; 0 when the update was not asked to decide) */
 #define OBE_STATS_LEN 64
 #define OBE_NACC_MAX (2 + OBE_MAX_DIMS + 36 + OBE_MAX_CH + 1)
 
@@ -108,6 +110,10 @@ struct ObeUpdateArgs {
     int noise_idx[OBE_MAX_CH];    // >=0: sigma_c is that particle row
     int n_noise;                  // number of noise-parameter channels (0: known sigma)
     double pivot[OBE_MAX_DIMS];
+    // device-side resample test (particlepdf.py:236-258), decided by the block that finishes the stats:
+    // gate_n > 0: stats[FIRED] = (N_eff < 0.1 gate_n) || (N_eff / gate_n < gate_thr), N_eff = 1 / (sumsq * invs^2)
+    double gate_thr;
+    double gate_n;
 };
 
 struct ObeUtilityArgs {
@@ -599,7 +605,8 @@ template <int NW>
 __device__ __forceinline__ void obe_tile_scan_block(const double* __restrict__ tile_sums, long long n_tiles,
                                                     double* __restrict__ prefix, double* __restrict__ stats,
                                                     int renormalise, long long uniform, long long n, int implicit,
-                                                    double* sm, int bar_id) {
+                                                    double* sm, int bar_id, double gate_thr = 0.0,
+                                                    double gate_n = 0.0) {
     constexpr int T_ = NW * 32;
     const int t = threadIdx.x % T_;
     double carry = 0.0;
@@ -633,10 +640,19 @@ __device__ __forceinline__ void obe_tile_scan_block(const double* __restrict__ t
                 stats[OBE_ST_SUMT] = (double)n * wv;
                 stats[OBE_ST_NEFF] = (double)uniform;
                 stats[OBE_ST_UNIFORM] = implicit ? wv : 0.0;
+                stats[OBE_ST_FIRED] = 0.0;
             } else {
-                stats[OBE_ST_INVS] = renormalise ? 1.0 / total : 1.0;
+                const double invs = renormalise ? 1.0 / total : 1.0;
+                stats[OBE_ST_INVS] = invs;
                 const double ssq = stats[OBE_ST_SUMSQ];
                 stats[OBE_ST_NEFF] = (total * total) / ssq;
+                double fired = 0.0;
+                if (gate_n > 0.0) {
+                    // the host's arithmetic (ParticlePDF._n_eff_from / resample_test), operation for operation
+                    const double n_eff = 1.0 / obe_mul(ssq, obe_mul(invs, invs));
+                    fired = (n_eff < obe_mul(0.1, gate_n) || n_eff / gate_n < gate_thr) ? 1.0 : 0.0;
+                }
+                stats[OBE_ST_FIRED] = fired;
             }
         }
     }
@@ -885,7 +901,7 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
     obe_named_bar(1, OBE_CONSUMER_THREADS);
     __threadfence();
     obe_tile_scan_block<OBE_CONSUMER_WARPS>(a.tile_sums, n_tiles, a.tile_prefix, a.stats, a.renormalise, 0, n, 0,
-                                            &accsm[0][0], 1);
+                                            &accsm[0][0], 1, a.gate_thr, a.gate_n);
 }
 
 // ---------------------------------------------------------------------------------------------

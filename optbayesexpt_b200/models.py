@@ -225,4 +225,10 @@ class ParticleBuffers:
                                       self.stats.data_ptr(), self.scratch.data_ptr(),
                                       self.n, self.ld, self.d, 0,
                                       None if n_dev is None else n_dev.data_ptr())
+            self._ptr = C.pointer(self._struct)
         return self._struct
+
+    def ptr(self):
+        """ctypes pointer to struct() (cached with it: the cycle entry takes one per buffer and call)."""
+        self.struct()
+        return self._ptr

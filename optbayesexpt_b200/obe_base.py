@@ -9,6 +9,7 @@ measurement record goes to the GPU each cycle, and only the stats block (64 doub
 chosen index come back.
 """
 import ctypes as C
+import math
 
 import numpy as np
 
@@ -149,8 +150,20 @@ class OptBayesExpt(ParticlePDF):
         #: (auto_resample off, or resample_threshold > 1): one C call, no synchronisation; the pivot of the moment
         #: accumulators and the impoverishment warning then lag one update behind
         self.async_update = False
+        #: with ``eager_select`` and ``async_update`` both on, a pdf_update whose resample decision DOES depend on
+        #: N_eff (the normal case) leaves the test to the device: one C call, the outcome arrives with the argmax at
+        #: the one synchronisation of the cycle (opt_setting / good_setting / just_resampled / any look at the cloud)
+        self.device_resample_test = True
         self._select_ready = False
         self._side = None                 # (torch stream object, raw handle) of the selection stream
+        # pinned landing block of the cycle entry: [0:64] the update's stats block, [64:66] (argmax index, value)
+        self._cy_pin = torch.zeros(_lib.STATS_LEN + 2, dtype=torch.float64).pin_memory()
+        self._cy_pin_np = self._cy_pin.numpy()
+        self._cy_stats_np = self._cy_pin_np[:_lib.STATS_LEN]
+        self._cy_best_np = self._cy_pin_np[_lib.STATS_LEN:].view(np.int64)
+        self._cy_copy_out = False         # the next cycle call also copies stats + argmax into the pinned block
+        self._best_copied = False         # the argmax of the prepared selection is on its way to _cy_best_np
+        self._async_pending = False
 
     # -- the reference rebinds `parameters` to `particles` in pdf_update (obe_base.py:185,395);
     #    here it is a live alias, which removes the stale-alias quirk after resample()/set_pdf()
@@ -172,6 +185,8 @@ class OptBayesExpt(ParticlePDF):
         return self.N_DRAWS
 
     def set_pdf(self, samples, weights=None):
+        if self._pending_cycle:
+            self._settle()
         self._select_ready = False
         noise_index = self._noise_index
         ParticlePDF.set_pdf(self, samples, weights)
@@ -182,6 +197,8 @@ class OptBayesExpt(ParticlePDF):
     # model evaluation in both orientations (obe_base.py:298-338)
     # ------------------------------------------------------------------------------------------
     def eval_over_all_parameters(self, onesettingset):
+        if self._pending_cycle:
+            self._settle()
         y = self._eval_parameters_dev(onesettingset)
         return y[:, :self.n_particles].cpu().numpy()
 
@@ -196,6 +213,8 @@ class OptBayesExpt(ParticlePDF):
         model evaluation can be done while waiting for measurement results").  Enqueued on a side stream, so it
         overlaps whatever else the device is doing; the next ``pdf_update`` for the same setting picks the result up
         (unless the cloud was resampled or replaced in between) instead of evaluating the model in its own pass."""
+        if self._pending_cycle:
+            self._settle()
         torch = self._torch
         side = getattr(self, '_prefetch_stream', None)
         if side is None:
@@ -242,6 +261,8 @@ class OptBayesExpt(ParticlePDF):
         """(y_meas[C], sigma[C] | None, noise_index | None, n_lik) -- the zip() of
         obe_base.py:453-455 truncates to the shortest of (channels, y_meas, sigma)."""
         onesetting, y_meas, sigma = measurement_record[0], measurement_record[1], measurement_record[2]
+        if type(y_meas) is float and type(sigma) is float:       # the common single-channel record, without numpy
+            return (y_meas,), (sigma,), None, 1
         y_meas = np.atleast_1d(np.asarray(y_meas, dtype=np.float64))
         sigma = np.atleast_1d(np.asarray(sigma, dtype=np.float64))
         n_lik = min(self.n_channels, len(y_meas), len(sigma))
@@ -253,10 +274,14 @@ class OptBayesExpt(ParticlePDF):
         Returns ``(particles, particle_weights)`` as lazy, numpy-convertible handles: nothing is
         copied off the GPU unless the caller looks at them.
         """
+        if self._pending_cycle:
+            self._settle()
         if self.async_update and y_model_data is None and getattr(self, '_prefetched', None) is None:
             decision = self._resample_decision_known()
             if decision is not None and self._cycle_c_ok(decision, bool(self.eager_select)):
                 return self._pdf_update_async(measurement_record, decision)
+            if decision is None and self._device_test_ok():
+                return self._pdf_update_device_test(measurement_record)
         onesetting = measurement_record[0]
         y_meas, sigma, noise_index, n_lik = self._likelihood_spec(measurement_record)
         use_choke = 0 if self.choke is None else 1
@@ -312,10 +337,17 @@ class OptBayesExpt(ParticlePDF):
         impoverishment warning of particlepdf.py:245-250 is therefore issued one update late)."""
         self._adopt_async_stats()
         select = bool(self.eager_select)
-        self.run_cycle_async(measurement_record, resample=resample, select=select)
+        self._cy_copy_out = True
+        try:
+            self.run_cycle_async(measurement_record, resample=resample, select=select)
+        finally:
+            copied, self._cy_copy_out = not self._cy_copy_out, False     # (the C entry consumed the request)
         self._select_ready = select
         self.just_resampled = bool(resample)
-        self._post_async_stats(resample)
+        if copied:
+            self._async_pending, self._best_copied = 'cycle', select
+        else:
+            self._post_async_stats(resample)
         if resample and self._constraint_masks() == (0, 0):
             self.enforce_parameter_constraints()          # (mask constraints were applied inside the cycle)
         return (LazyDeviceArray(lambda: self.particles), LazyDeviceArray(lambda: self.particle_weights))
@@ -336,13 +368,21 @@ class OptBayesExpt(ParticlePDF):
         self._async_pending = True
 
     def _adopt_async_stats(self):
-        if not getattr(self, '_async_pending', False):
+        pending, self._async_pending = self._async_pending, False
+        if not pending:
             return
-        self._async_pending = False
-        self._async_ev.synchronize()            # (already complete in a closed loop: opt_setting synchronised since)
-        st = self._async_pin_np.copy()
+        if pending == 'cycle':                  # copied by obe_cycle itself behind its kernels
+            self._check(self._lib.obe_stream_sync(self._stream()))   # (a no-op wait in a closed loop)
+            st = self._cy_stats_np.copy()
+        else:
+            self._async_ev.synchronize()        # (already complete in a closed loop: opt_setting synchronised since)
+            st = self._async_pin_np.copy()
+        self._adopt_stats(st)
+
+    def _adopt_stats(self, st):
+        """Pivot of the next update's moment accumulators and the impoverishment warning, from a stats block."""
         mean = self._mean_from(st)
-        if np.all(np.isfinite(mean)):
+        if math.isfinite(mean.sum()):
             self._pivot = mean
         n_eff = self._n_eff_from(st)
         if n_eff < 0.1 * self._n_total_for_test():
@@ -353,6 +393,59 @@ class OptBayesExpt(ParticlePDF):
 
     def _n_total_for_test(self):
         return self.n_particles
+
+    def _async_stats_ptr(self, resample):
+        """Device address of the stats block the cycle entry copies out (None: the updated cloud's own block)."""
+        return None
+
+    # ---- pdf_update with the resample test on the device ------------------------------------------
+    def _device_test_ok(self):
+        tp = self.tuning_parameters
+        return (self.device_resample_test and self.eager_select and self.resampling == 'systematic'
+                and 0.0 <= tp['resample_threshold'] <= 1.0 and self._constraint_masks() == (0, 0)
+                and not self._noise_from_stats() and self._early_select_ok() and self._cycle_c_ok(True, True))
+
+    def _pdf_update_device_test(self, measurement_record):
+        """pdf_update + the selection of the next opt_setting() as ONE C call whose resample test
+        (particlepdf.py:236-258) runs on the device: obe_cycle(resample=2).  The host learns whether the cloud was
+        resampled when it synchronises for the argmax; until then the cycle is pending and any look at the cloud
+        (``_buf``), ``just_resampled`` or the selection settles it first.  ``self.rng`` is consumed as in the
+        synchronous path when a resample fires (u0, then the K uniforms); when it does not, the u0 drawn for it
+        is simply unused."""
+        self._settle()
+        self._adopt_async_stats()
+        cy = self._cycle_struct()
+        self._cy_copy_out = True
+        self._fill_cycle(cy, measurement_record, True, True)
+        cy.resample = 2
+        cy.resample_threshold = float(self.tuning_parameters['resample_threshold'])
+        cy.side_stream = None
+        cy.u0 = float(self.rng.random())
+        self._cy_u[:cy.k] = self.rng.random(cy.k)
+        self._check(self._lib.obe_cycle(C.byref(cy)))
+        self._invalidate(particles=True)
+        self._stats = None
+        self._last_ancestors = None
+        self._pending_cycle = True
+        self._select_ready = True
+        self._best_copied = True
+        return (LazyDeviceArray(lambda: self.particles), LazyDeviceArray(lambda: self.particle_weights))
+
+    def _settle(self):
+        """Wait for a pending device-decided cycle and do the host bookkeeping of its outcome."""
+        if not self._pending_cycle:
+            return
+        self._pending_cycle = False
+        self._check(self._lib.obe_stream_sync(self._stream()))
+        st = self._cy_stats_np.copy()
+        fired = bool(st[_lib.ST_FIRED] != 0.0)
+        ready, copied = self._select_ready, self._best_copied
+        self._after_cycle_c(fired)
+        self._select_ready, self._best_copied = ready, copied     # (the prepared selection belongs to this outcome)
+        self._just_resampled = fired
+        if not fired:
+            self._stats = st                    # the live cloud's stats block, already on the host
+        self._adopt_stats(st)
 
     def _noise_iarr(self, noise_index):
         """ctypes int array of the noise-parameter rows (cached: it never changes for an engine)."""
@@ -369,6 +462,8 @@ class OptBayesExpt(ParticlePDF):
         on the current stream with NO host synchronisation: the resample decision is the
         caller's, the chosen index stays in ``best_index_dev``.  For pipelined / benchmark use;
         ``pdf_update`` + ``opt_setting`` is the synchronous, reference-shaped API."""
+        if self._pending_cycle:
+            self._settle()
         if self._cycle_c_ok(resample, select):
             return self._run_cycle_c(measurement_record, resample, select)
         onesetting = measurement_record[0]
@@ -413,65 +508,76 @@ class OptBayesExpt(ParticlePDF):
             cy.utility_dev = self._utility_dev.data_ptr()
             cy.best_dev = self._best_dev.data_ptr()
             cy.select_scratch_dev = self._select_scratch.data_ptr()
-            self._cy_u = np.frombuffer(cy, dtype=np.float64, count=128, offset=_lib.Cycle.u.offset)
+
+            def view(field, count):         # the by-value arrays of the struct as numpy views: one slice store each
+                return np.frombuffer(cy, dtype=np.float64, count=count, offset=getattr(_lib.Cycle, field).offset)
+            self._cy_u = view('u', 128)
+            self._cy_setting, self._cy_y = view('setting', _lib.MAX_SETTINGS), view('y_meas', _lib.MAX_CHANNELS)
+            self._cy_sigma, self._cy_pivot = view('sigma', _lib.MAX_CHANNELS), view('pivot', _lib.MAX_PARAMS)
+            self._cy_vn = view('var_noise', _lib.MAX_CHANNELS)
+            self._cy_ni = np.frombuffer(cy, dtype=np.int32, count=_lib.MAX_CHANNELS,
+                                        offset=_lib.Cycle.noise_index.offset)
         return cy
 
     def _fill_cycle(self, cy, measurement_record, resample, select):
         """The per-cycle fields of the obe_cycle_t; consumes self.rng in the order resample() / opt_setting() do."""
-        onesetting = measurement_record[0]
         y_meas, sigma, noise_index, n_lik = self._likelihood_spec(measurement_record)
         cy.model = self._model
-        st = np.atleast_1d(onesetting)
-        for i in range(min(len(st), _lib.MAX_SETTINGS)):
-            cy.setting[i] = st[i]
-        for i in range(len(y_meas)):
-            cy.y_meas[i] = y_meas[i]
+        st = np.atleast_1d(measurement_record[0])
+        self._cy_setting[:min(len(st), _lib.MAX_SETTINGS)] = st[:_lib.MAX_SETTINGS]
+        self._cy_y[:len(y_meas)] = y_meas
         cy.has_sigma = 0 if sigma is None else 1
         if sigma is not None:
-            for i in range(len(sigma)):
-                cy.sigma[i] = sigma[i]
+            self._cy_sigma[:len(sigma)] = sigma
         cy.has_noise_index = 0 if noise_index is None else 1
         ni = self._noise_index
         if noise_index is not None:
-            for i in range(len(noise_index)):
-                cy.noise_index[i] = noise_index[i]
+            self._cy_ni[:len(noise_index)] = noise_index
         elif ni is not None:
-            for i in range(len(ni)):
-                cy.noise_index[i] = ni[i]
+            self._cy_ni[:len(ni)] = ni
         cy.n_noise = 0 if ni is None else len(ni)
         cy.n_lik_channels = n_lik
-        cy.use_choke = 0 if self.choke is None else 1
-        cy.choke = 0.0 if self.choke is None else float(self.choke)
-        piv = self._pivot
-        for i in range(self.n_dims):
-            cy.pivot[i] = piv[i]
-        cy.cloud = C.pointer(self._buf.struct())
+        choke = self.choke
+        cy.use_choke = 0 if choke is None else 1
+        cy.choke = 0.0 if choke is None else float(choke)
+        self._cy_pivot[:self.n_dims] = self._pivot
+        buf = self._buf
+        cy.cloud = buf.ptr()
         cy.resample = 1 if resample else 0
         if resample:
-            if self._alt is None:
-                self._alt = self._buf.empty_like()
-            cy.alt = C.pointer(self._alt.struct())
-            cy.scale = 1 if self.tuning_parameters['scale'] else 0
-            cy.a_param = float(self.tuning_parameters['a_param'])
+            alt = self._alt
+            if alt is None:
+                alt = self._alt = buf.empty_like()
+            cy.alt = alt.ptr()
+            tp = self.tuning_parameters
+            cy.scale = 1 if tp['scale'] else 0
+            cy.a_param = float(tp['a_param'])
             cy.seed = self._philox_seed
             cy.epoch = self._epoch + 1
             cy.mask_le, cy.mask_lt = self._constraint_masks()
         cy.select = 1 if select else 0
         cy.noise_from_stats = 1 if self._noise_from_stats() else 0
         if select:
-            k = int(self.N_DRAWS)
-            cy.k = k
+            cy.k = int(self.N_DRAWS)
             cy.draws_dev = self._draws_buffer().data_ptr()
             cy.method = self._utility_code
             cy.log_form = 1 if self.utility_log_form else 0
             if not cy.noise_from_stats:
                 vn = np.asarray(self.yvar_noise_model(), dtype=np.float64).reshape(-1)
-                for i in range(min(len(vn), _lib.MAX_CHANNELS)):
-                    cy.var_noise[i] = vn[i]
+                self._cy_vn[:min(len(vn), _lib.MAX_CHANNELS)] = vn[:_lib.MAX_CHANNELS]
         cy.stream = self._stream().value
         cy.side_stream = self._side_stream()[1].value if (self.early_select and resample and select) else None
+        if self._cy_copy_out:
+            self._cy_copy_out = False
+            base = self._cy_pin.data_ptr()
+            cy.stats_host, cy.best_host = base, base + 8 * _lib.STATS_LEN
+            cy.stats_src_dev = self._async_stats_ptr(resample)
+        else:
+            cy.stats_host = cy.best_host = cy.stats_src_dev = None
 
     def _run_cycle_c(self, measurement_record, resample, select):
+        if self._pending_cycle:
+            self._settle()
         cy = self._cycle_struct()
         self._fill_cycle(cy, measurement_record, resample, select)
         if resample:
@@ -506,6 +612,8 @@ class OptBayesExpt(ParticlePDF):
         """The part of run_cycle_async after the update: (forced) resample and selection, enqueued without a host
         synchronisation.  With both on and early select available the K draws come from the resample plan and the
         utility pass overlaps the resample on the selection stream."""
+        if self._pending_cycle:
+            self._settle()
         if resample:
             if self.resampling == 'multinomial':
                 raise ValueError('run_cycle_async needs a device-side resampler (systematic or multinomial_device)')
@@ -584,6 +692,8 @@ class OptBayesExpt(ParticlePDF):
     def enforce_parameter_constraints(self):
         """Stub, as in the reference (obe_base.py:401-416).  Device-side constraints are data:
         see ``_apply_constraint_masks``."""
+        if self._pending_cycle:
+            self._settle()
         pass
 
     def _apply_constraint_masks(self, mask_le=0, mask_lt=0, sync=True):
@@ -638,6 +748,8 @@ class OptBayesExpt(ParticlePDF):
 
     def yvar_noise_model(self):
         """Constant noise variance per channel, (C,1) (obe_base.py:542-564)."""
+        if self._pending_cycle:
+            self._settle()
         return self.default_noise_std ** 2
 
     def cost_estimate(self):
@@ -657,6 +769,8 @@ class OptBayesExpt(ParticlePDF):
     def _utility_dev_run(self, draws=None, side=None):
         """draws -> utility over the grid -> argmax, all on the device; returns nothing.  ``draws``: already on the
         device (early select); ``side``: the torch stream the kernels go to when it is not the current one."""
+        if self._pending_cycle:
+            self._settle()
         torch = self._torch
         if draws is None:
             draws = self._randdraw_dev(self.N_DRAWS, out=self._draws_buffer())
@@ -708,6 +822,8 @@ class OptBayesExpt(ParticlePDF):
 
     def utility(self):
         """Utility over all settings as a numpy array (obe_base.py:579-655)."""
+        if self._pending_cycle:
+            self._settle()
         self._utility_dev_run()
         return self._utility_dev.cpu().numpy()
 
@@ -740,13 +856,20 @@ class OptBayesExpt(ParticlePDF):
 
     def opt_setting(self):
         """Setting with the maximum utility (obe_base.py:733-756)."""
+        self._settle()
         if self._select_ready:
             self._select_ready = False          # started by the resample (eager_select): only the argmax is fetched
         else:
             self._utility_dev_run()
-        self._best_host.copy_(self._best_dev, non_blocking=True)
-        self._torch.cuda.current_stream().synchronize()
-        bestindex = int(self._best_host_np[0])
+            self._best_copied = False
+        if self._best_copied:                   # the cycle entry already copied it into the pinned block
+            self._best_copied = False
+            self._check(self._lib.obe_stream_sync(self._stream()))
+            bestindex = int(self._cy_best_np[0])
+        else:
+            self._best_host.copy_(self._best_dev, non_blocking=True)
+            self._check(self._lib.obe_stream_sync(self._stream()))
+            bestindex = int(self._best_host_np[0])
         self.last_setting_index = bestindex
         return tuple(self.allsettings[:, bestindex])
 
@@ -754,10 +877,12 @@ class OptBayesExpt(ParticlePDF):
         """Setting drawn with probability ~ utility**pickiness (obe_base.py:758-789)."""
         if pickiness is None:
             pickiness = self.pickiness
+        self._settle()
         if self._select_ready:
             self._select_ready = False
         else:
             self._utility_dev_run()
+        self._best_copied = False
         u = float(self.rng.random())
         self._check(self._lib.obe_pick(C.c_void_p(self._utility_dev.data_ptr()), len(self.setting_indices),
                                        float(pickiness), u, C.c_void_p(self._pick_dev.data_ptr()),

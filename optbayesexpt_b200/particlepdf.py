@@ -53,6 +53,47 @@ class ParticlePDF:
     # ------------------------------------------------------------------------------------------
     # plumbing
     # ------------------------------------------------------------------------------------------
+    # A cycle whose resample test runs on the device (OptBayesExpt._pdf_update_device_test) leaves the outcome --
+    # which of the two buffers holds the cloud -- unknown to the host until the stream has been synchronised.  Every
+    # path to the cloud goes through ``_buf`` / ``_alt`` / ``just_resampled``: looking at any of them settles the
+    # pending cycle first.
+    _pending_cycle = False
+
+    def _settle(self):
+        """Nothing is pending on a plain ParticlePDF (OptBayesExpt overrides this)."""
+        self._pending_cycle = False
+
+    @property
+    def _buf(self):
+        if self._pending_cycle:
+            self._settle()
+        return self._buf_live
+
+    @_buf.setter
+    def _buf(self, value):
+        self._buf_live = value
+
+    @property
+    def _alt(self):
+        if self._pending_cycle:
+            self._settle()
+        return self._buf_alt
+
+    @_alt.setter
+    def _alt(self, value):
+        self._buf_alt = value
+
+    @property
+    def just_resampled(self):
+        """True if the last update resampled (particlepdf.py:120-126)."""
+        if self._pending_cycle:
+            self._settle()
+        return self._just_resampled
+
+    @just_resampled.setter
+    def just_resampled(self, value):
+        self._just_resampled = value
+
     def _install(self, samples):
         self._buf = ParticleBuffers(samples, self._device, capacity=getattr(self, '_capacity', None))
         self._dev_index = self._buf.device.index
@@ -102,6 +143,8 @@ class ParticlePDF:
 
     def _refresh(self, mask_le=0, mask_lt=0, renormalise=0):
         """Tile sums + CDF prefix + moments from the current device weights."""
+        if self._pending_cycle:
+            self._settle()
         ni = self._noise_index
         self._check(self._lib.obe_refresh(self._cs(), mask_le, mask_lt, _lib.iarr(ni),
                                           0 if ni is None else len(ni), _lib.darr(self._pivot, _lib.MAX_PARAMS),
@@ -122,6 +165,8 @@ class ParticlePDF:
         return st
 
     def _ensure_moments(self):
+        if self._pending_cycle:
+            self._settle()
         if not self._moments_valid or self._stats is None:
             self._refresh(renormalise=1 if self._weights_lazy else 0)
         return self._stats
@@ -157,6 +202,8 @@ class ParticlePDF:
     @property
     def particles(self):
         """(n_dims, n_particles) float64, read-only host mirror (particlepdf.py:101-105)."""
+        if self._pending_cycle:
+            self._settle()
         if self._host_particles is None:
             arr = self._buf.particles[:, :self.n_particles].cpu().numpy()
             arr.setflags(write=False)
@@ -165,6 +212,8 @@ class ParticlePDF:
 
     @particles.setter
     def particles(self, value):
+        if self._pending_cycle:
+            self._settle()
         value = np.atleast_2d(np.asarray(value, dtype=np.float64))
         if value.shape != (self.n_dims, self.n_particles):
             raise ValueError('particles has the wrong shape; use set_pdf() to change the geometry')
@@ -176,6 +225,8 @@ class ParticlePDF:
     @property
     def particle_weights(self):
         """(n_particles,) normalised weights, read-only host mirror (particlepdf.py:119-121)."""
+        if self._pending_cycle:
+            self._settle()
         if self._host_weights is None:
             out = self._torch.empty(self.n_particles, dtype=self._torch.float64, device=self._buf.device)
             self._check(self._lib.obe_normalized_weights(self._cs(), C.c_void_p(out.data_ptr()), self._stream()))
@@ -186,6 +237,8 @@ class ParticlePDF:
 
     @particle_weights.setter
     def particle_weights(self, value):
+        if self._pending_cycle:
+            self._settle()
         # stored as given, like the reference (tests/test_particlepdf.py:128,142,149 assign directly)
         value = np.asarray(value, dtype=np.float64).reshape(-1)
         if value.shape[0] != self.n_particles:
@@ -201,21 +254,29 @@ class ParticlePDF:
     @property
     def particles_dev(self):
         """torch view (n_dims, n_particles) of the device cloud, zero-copy."""
+        if self._pending_cycle:
+            self._settle()
         return self._buf.particles[:, :self.n_particles]
 
     @property
     def weights_dev(self):
         """torch view of the UN-normalised device weights; multiply by ``weight_scale``.  (After a
         systematic resample the weights are implicit on the device; this materialises them.)"""
+        if self._pending_cycle:
+            self._settle()
         self._check(self._lib.obe_materialize_weights(self._cs(), self._stream()))
         return self._buf.weights[:self.n_particles]
 
     @property
     def weight_scale(self):
+        if self._pending_cycle:
+            self._settle()
         return float(self._buf.stats[_lib.ST_INVS].item())
 
     def set_pdf(self, samples, weights=None):
         """Re-initialise the distribution (particlepdf.py:147-171)."""
+        if self._pending_cycle:
+            self._settle()
         self._install(samples)
         self._cloud_version = getattr(self, '_cloud_version', 0) + 1
         if weights is None:
@@ -232,10 +293,14 @@ class ParticlePDF:
     # ------------------------------------------------------------------------------------------
     def mean(self):
         """Weighted mean, size n_dims (particlepdf.py:182-183)."""
+        if self._pending_cycle:
+            self._settle()
         return self._mean_from(self._ensure_moments()).copy()
 
     def covariance(self):
         """np.cov(particles, aweights=w): (n_dims, n_dims) (particlepdf.py:194-198)."""
+        if self._pending_cycle:
+            self._settle()
         st = self._ensure_moments()
         d = self.n_dims
         s = st[_lib.ST_SUMT]
@@ -246,9 +311,13 @@ class ParticlePDF:
     def std(self):
         """sqrt(sum w x^2 - (sum w x)^2) per parameter (particlepdf.py:209-214); evaluated from the
         pivot-shifted accumulators, so without the reference's cancellation error."""
+        if self._pending_cycle:
+            self._settle()
         return np.sqrt(np.maximum(self._var_from(self._ensure_moments()), 0.0))
 
     def n_eff(self):
+        if self._pending_cycle:
+            self._settle()
         return float(self._n_eff_from(self._ensure_moments()))
 
     # ------------------------------------------------------------------------------------------
@@ -256,6 +325,8 @@ class ParticlePDF:
     # ------------------------------------------------------------------------------------------
     def bayesian_update(self, likelihood):
         """weights <- normalised(weights * likelihood), then the resample test."""
+        if self._pending_cycle:
+            self._settle()
         lik = np.asarray(likelihood, dtype=np.float64).reshape(-1)
         if lik.shape[0] != self.n_particles:
             raise ValueError('likelihood length does not match the number of particles')
@@ -277,6 +348,8 @@ class ParticlePDF:
 
     def resample_test(self):
         """Resample if N_eff/N is below the threshold; sets just_resampled (particlepdf.py:236-258)."""
+        if self._pending_cycle:
+            self._settle()
         n_eff = self._n_eff_from(self._ensure_moments())
         if n_eff < 0.1 * self.n_particles:
             warnings.warn("\nParticle filter rejected > 90 % of particles. "
@@ -299,6 +372,8 @@ class ParticlePDF:
     # ------------------------------------------------------------------------------------------
     def resample(self):
         """Weighted re-draw of the cloud + Liu-West jitter (particlepdf.py:260-310)."""
+        if self._pending_cycle:
+            self._settle()
         torch = self._torch
         if self._alt is None:
             self._alt = self._buf.empty_like()
@@ -368,9 +443,13 @@ class ParticlePDF:
 
     def randdraw(self, n_draws=1):
         """(n_dims, n_draws) weighted random draws (particlepdf.py:312-345)."""
+        if self._pending_cycle:
+            self._settle()
         return self._randdraw_dev(n_draws).cpu().numpy()
 
     def _randdraw_dev(self, n_draws, out=None):
+        if self._pending_cycle:
+            self._settle()
         u = self.rng.random(n_draws)
         draws = out if out is not None else self._torch.empty((self.n_dims, n_draws), dtype=self._torch.float64,
                                                                device=self._buf.device)

@@ -596,10 +596,19 @@ class ShardedOptBayesExpt(OptBayesExpt):
             self._select_ready = False
         else:
             self._utility_dev_run()
+            self._best_copied = False
         if self._replicate_grid:
-            best = int(self._best_dev.cpu()[0])
+            if self._best_copied:               # the cycle entry copied the argmax into the pinned block already
+                self._best_copied = False
+                self._check(self._lib.obe_stream_sync(self._stream()))
+                best = int(self._cy_best_np[0])
+            else:
+                self._best_host.copy_(self._best_dev, non_blocking=True)
+                self._check(self._lib.obe_stream_sync(self._stream()))
+                best = int(self._best_host_np[0])
             self.last_setting_index = best
             return tuple(self.allsettings[:, best])
+        self._best_copied = False
         pairs = self._comm.allgather(self._best_dev).cpu()
         vals = pairs[:, 1].contiguous().view(torch.float64).numpy()
         idxs = pairs[:, 0].numpy()
@@ -675,6 +684,12 @@ class ShardedOptBayesExpt(OptBayesExpt):
 
     def _async_stats_source(self, resample):
         return self._plan[_lib.PLAN_GSTATS:_lib.PLAN_GSTATS + _lib.STATS_LEN]      # the combined (global) block
+
+    def _async_stats_ptr(self, resample):
+        return self._plan.data_ptr() + 8 * _lib.PLAN_GSTATS
+
+    def _device_test_ok(self):
+        return False            # the resample test of a sharded cloud needs the combined stats of all ranks
 
     def _n_total_for_test(self):
         return self.n_total

@@ -1,5 +1,6 @@
 """Where does a small-cloud cycle spend its host time?  cProfile of the closed loop pdf_update -> opt_setting on the
-c1 shape (1e4 particles x 200 settings).  python tools/profile_small.py [n_cycles]"""
+c1 shape (1e4 particles x 200 settings).  python tools/profile_small.py [n_cycles] [c1|c2|c3] [sync|fast] [threshold]
+(fast: eager_select + async_update, i.e. one C call per cycle with the resample test on the device)"""
 import cProfile
 import os
 import pstats
@@ -24,6 +25,10 @@ def main():
     else:
         eng = obe.OptBayesExpt(wl['device_model'], wl['settings'](), prior, wl['cons'],
                                default_noise_std=wl['default_noise_std'], **kw)
+    if len(sys.argv) > 3 and sys.argv[3] == 'fast':
+        eng.eager_select = eng.async_update = True
+    if len(sys.argv) > 4:
+        eng.tuning_parameters['resample_threshold'] = float(sys.argv[4])
     meas = np.random.default_rng(1002)
     cycles = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
     import warnings
