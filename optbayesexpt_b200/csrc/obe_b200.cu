@@ -890,6 +890,7 @@ static int64_t g_resample_fused = 1;              /* obe_set_option("resample_fu
 static int64_t g_resample_units_per_sm = 16;      /* obe_set_option("resample_units_per_sm"): work units per SM the chunk size aims at */
 static int64_t g_resample_reserve = 0;            /* obe_set_option("resample_reserve_ctas"): CTA slots an early-select resample leaves to the selection kernels */
 static int64_t g_resample_dynamic = 1;            /* obe_set_option("resample_dynamic"): units handed out by an atomic counter */
+static int64_t g_copy_out_side = 1;               /* obe_set_option("copy_out_side"): early-select cycles copy stats + argmax out on the selection stream */
 static int64_t g_resample_blocks = 0;             /* obe_set_option("resample_blocks"): CTAs per SM of the fused kernel (0: default) */
 #ifndef OBE_PLAN_CLUSTER_MIN_TILES
 #define OBE_PLAN_CLUSTER_MIN_TILES 8192     /* below: one CTA does every pass in a single round anyway */
@@ -2561,6 +2562,7 @@ int obe_set_option(const char* name, int64_t value) {
     if (s == "resample_blocks") { g_resample_blocks = value < 0 ? 0 : value; return 0; }
     if (s == "resample_reserve_ctas") { g_resample_reserve = value < 0 ? 0 : value; return 0; }
     if (s == "pdl") { g_pdl = value ? 1 : 0; return 0; }
+    if (s == "copy_out_side") { g_copy_out_side = value ? 1 : 0; return 0; }
     if (s == "resample_dynamic") { g_resample_dynamic = value ? 1 : 0; return 0; }
     if (s == "resample_units_per_sm") { g_resample_units_per_sm = value < 1 ? 1 : value; return 0; }
     return obe_fail("unknown option '%s'%s", name);
@@ -3297,8 +3299,8 @@ int obe_stream_sync(void* stream) {
 }
 
 // the results a closed loop waits for, copied into the caller's pinned host blocks behind the cycle's kernels
-static int cycle_copy_out(const obe_cycle_t* c, const obe_cloud_t* updated) {
-    cudaStream_t st = (cudaStream_t)c->stream;
+static int cycle_copy_out(const obe_cycle_t* c, const obe_cloud_t* updated, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
     if (c->best_host && c->select)
         OBE_CUDA(cudaMemcpyAsync(c->best_host, c->best_dev, 16, cudaMemcpyDeviceToHost, st));
     if (c->stats_host)
@@ -3346,18 +3348,19 @@ static int cycle_auto(const obe_cycle_t* c) {
         return -1;
     }
     if (obe_resample_emit(st)) return -1;
-    return cycle_copy_out(c, live);
+    return cycle_copy_out(c, live, st);
 }
 
-static int cycle_body(const obe_cycle_t* c);
+static int cycle_body(const obe_cycle_t* c, bool& copied);
 int obe_cycle(const obe_cycle_t* c) {
     if (!c || !c->cloud || !c->model) return obe_fail("obe_cycle: null argument%s%s");
     if (c->resample == 2) return cycle_auto(c);
-    if (cycle_body(c)) return -1;
-    return cycle_copy_out(c, c->cloud);
+    bool copied = false;
+    if (cycle_body(c, copied)) return -1;
+    return copied ? 0 : cycle_copy_out(c, c->cloud, c->stream);
 }
 
-static int cycle_body(const obe_cycle_t* c) {
+static int cycle_body(const obe_cycle_t* c, bool& copied) {
     void* st = c->stream;
     const obe_cloud_t* live = c->cloud;
     const int sharded = c->plan_dev != nullptr;
@@ -3391,6 +3394,12 @@ static int cycle_body(const obe_cycle_t* c) {
                             c->var_noise, nullptr, c->cost_dev, c->method, c->log_form, c->kld_noise_dev, c->utility_dev,
                             c->best_dev, c->select_scratch_dev, side))
                 return -1;
+            // the copies a closed loop waits for ride the selection stream: they are done long before the streaming
+            // kernel, so nothing trails it but the join (the stats block is final since the update / shard plan)
+            if (g_copy_out_side) {
+                if (cycle_copy_out(c, c->cloud, side)) return -1;
+                copied = true;
+            }
             if (obe_resample_emit(st)) return -1;
             return obe_stream_join(st, side);
         }
