@@ -678,6 +678,31 @@ def main():
         tt = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
+    # the same closed loop at the NATURAL resample rate (threshold 0.5): the resample test runs on the device, most cycles
+    # are update + selection only (single GPU; a sharded cloud decides on the host from the combined stats)
+    e2e_natural = None
+    if world == 1:
+        eng.tuning_parameters['resample_threshold'] = 0.5
+        for _ in range(5):
+            eng.pdf_update(record_for(x[0]))
+            x = eng.opt_setting()
+        settle()
+        for _ in range(3):
+            eng.pdf_update(record_for(x[0]))
+            x = eng.opt_setting()
+        torch.cuda.synchronize()
+        n_res, t0 = 0, time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.pdf_update(record_for(x[0]))
+            x = eng.opt_setting()
+            n_res += 1 if eng.just_resampled else 0
+        torch.cuda.synchronize()
+        e2e_natural = {'value': e2e_steps / (time.perf_counter() - t0), 'unit': 'cycles/s', 'steps': e2e_steps,
+                       'resamples_per_cycle': n_res / e2e_steps, 'resample_threshold': 0.5,
+                       'device_resample_test': bool(eng._pending_cycle is not None and eng._device_test_ok())}
+        eng.tuning_parameters['resample_threshold'] = 2.0
+        eng.pdf_update(record_for(x[0]))            # back to a freshly resampled cloud for the diagnostics below
+        x = eng.opt_setting()
     eng.eager_select = eng.async_update = False
     # the same cycle once more with an event between the update and the rest (per-phase split of the overlapped cycle)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
@@ -856,6 +881,8 @@ def main():
                               'its own warm-up cycles)' % SETTLE_S},
         'clocks': clocks,
     }
+    if e2e_natural is not None:
+        line['e2e_natural'] = e2e_natural
     if multinomial is not None:
         line['multinomial_device'] = multinomial
     if invariance is not None:
