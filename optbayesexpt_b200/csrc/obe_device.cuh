@@ -359,16 +359,21 @@ struct ObeUpdateEval {
 // polynomial, ...) are independent, and written this way ptxas interleaves them, which is what hides the
 // ~8-cycle FP64 latency at 4 warps per SM sub-partition.  (Element-at-a-time code compiled to one serial
 // DFMA chain per particle: ncu showed the FP64 pipe 41 % busy and "wait" the top stall.)
+// The underflow cut (x < -708 -> 0, NaN -> 0: nan_to_num zeroes that weight anyway) is applied to the SCALE, on a
+// clamped argument: written as `x < -708 ? 0 : p * scale`, ptxas sank each element's polynomial into its own
+// branch region and the four 14-deep DFMA chains ran one after the other ("wait" was 30 % of the update kernel's
+// stall samples); p * scale with a selected scale has to be evaluated unconditionally, so the chains interleave.
 template <int NE>
 __device__ __forceinline__ void obe_exp_nonpos_vec(const double (&x)[NE], double (&out)[NE]) {
     double r[NE], p[NE];
     int k[NE];
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-        const double t = fma(x[e], 1.4426950408889634, 6755399441055744.0);
+        const double xc = fmax(x[e], -708.0);                   // (NaN -> -708: finite polynomial, zero scale below)
+        const double t = fma(xc, 1.4426950408889634, 6755399441055744.0);
         k[e] = __double2loint(t);
         const double kf = t - 6755399441055744.0;
-        r[e] = fma(kf, -6.93147180369123816490e-01, x[e]);
+        r[e] = fma(kf, -6.93147180369123816490e-01, xc);
         r[e] = fma(kf, -1.90821492927058770002e-10, r[e]);
         p[e] = obe_exp_c[0];
     }
@@ -381,8 +386,8 @@ __device__ __forceinline__ void obe_exp_nonpos_vec(const double (&x)[NE], double
     for (int e = 0; e < NE; ++e) {
         p[e] = fma(p[e], r[e], 1.0);
         p[e] = fma(p[e], r[e], 1.0);
-        const double scale = __hiloint2double((max(k[e], -1022) + 1023) << 20, 0);
-        out[e] = (x[e] < -708.0) ? 0.0 : p[e] * scale;
+        const int hi = (x[e] >= -708.0) ? ((max(k[e], -1022) + 1023) << 20) : 0;
+        out[e] = p[e] * __hiloint2double(hi, 0);
     }
 }
 
@@ -407,7 +412,8 @@ __device__ __forceinline__ void obe_pick_rows(const double (&p)[NE][D], int ni, 
     for (int e = 0; e < NE; ++e) out[e] = dflt;
 }
 
-template <class Model, int D, int SRC, int NE, bool BATCHED>
+// ALLV: every element of the stage is a live particle (all stages but the ragged last one): the valid[] selects vanish.
+template <class Model, int D, int SRC, int NE, bool BATCHED, bool ALLV = false>
 __device__ __forceinline__ void obe_update_vec(const ObeUpdateArgs& a, const double (&p)[NE][D],
                                                const double (&w_in)[NE], const double (&yg)[NE][OBE_MAX_CH],
                                                const double (&lik_given)[NE], const bool (&valid)[NE], double invS,
@@ -507,21 +513,23 @@ __device__ __forceinline__ void obe_update_vec(const ObeUpdateArgs& a, const dou
                 if (((a.mask_le >> j) & 1u) && p[e][j] <= 0.0) bad = true;
                 if (((a.mask_lt >> j) & 1u) && p[e][j] < 0.0) bad = true;
             }
-            if (bad && valid[e]) {
+            if (bad && (ALLV || valid[e])) {
                 if (t[e] != 0.0) acc.nzero += 1.0;
                 t[e] = 0.0;
             }
         }
     }
+    if (!ALLV) {
 #pragma unroll
-    for (int e = 0; e < NE; ++e) t[e] = valid[e] ? t[e] : 0.0;
+        for (int e = 0; e < NE; ++e) t[e] = valid[e] ? t[e] : 0.0;
+    }
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
         acc.sumsq += t[e] * t[e];
         acc.sumt += t[e];
         double dx[D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) dx[j] = valid[e] ? p[e][j] - r_piv[j] : 0.0;
+        for (int j = 0; j < D; ++j) dx[j] = (ALLV || valid[e]) ? p[e][j] - r_piv[j] : 0.0;
         int q = 0;
 #pragma unroll
         for (int j = 0; j < D; ++j) {
@@ -539,7 +547,7 @@ __device__ __forceinline__ void obe_update_vec(const ObeUpdateArgs& a, const dou
                 double sig[NE];
                 obe_pick_rows<D, NE>(p, ni, sig, 0.0);
 #pragma unroll
-                for (int e = 0; e < NE; ++e) acc.noise[c] += valid[e] ? t[e] * (sig[e] * sig[e]) : 0.0;
+                for (int e = 0; e < NE; ++e) acc.noise[c] += (ALLV || valid[e]) ? t[e] * (sig[e] * sig[e]) : 0.0;
             }
         }
     }
@@ -839,7 +847,9 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
                 }
             }
         }
-        // tile sum: warp partials -> one named barrier among the consumers -> fixed-order sum
+        // tile sum: warp partials -> one named barrier among the consumers -> fixed-order sum.  (A barrier-free
+        // variant -- ring of partial slots, the last warp to arrive sums -- and a select-free path for full stages
+        // were measured on top of the interleaved exp and changed nothing: 0.586 vs 0.590 ms at 1e8.)
         tsum = obe_warp_sum(tsum);
         if (lane == 0) red[tile_par][cwarp] = tsum;
         obe_named_bar(1, OBE_CONSUMER_THREADS);
