@@ -402,7 +402,8 @@ def bench_c5(args, rank, world):
             'kernels_ms': {'select (draws + utility + argmax)': split[0], 'simulate measurement': split[1],
                            'update + resample of the flagged instances': split[2]},
             'gpu_launches': 6 * args.steps, 'clocks': clocks,
-            'fp64_note': 'update and select are FP64-throughput-bound (lock-in model, 2 channels): see DESIGN 6b',
+            'bound_note': 'update and select are barrier- and latency-bound (per-instance block barriers; FP64 pipe 35 % / '
+                          '47 % busy): profiles/r2_ncu_summary.md, c5 section',
             'e2e': {'value': 1.0 / e2e_s, 'unit': 'batched cycles/s', 'h2d_bytes_per_step': B * 12 * 8,
                     'd2h_bytes_per_step': B * 8},
             'roofline': {'bound': 'hbm', 'achieved': b_cycle / world / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
