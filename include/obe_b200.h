@@ -294,7 +294,8 @@ typedef struct obe_cycle {
     /* optional PINNED host blocks, filled by asynchronous copies behind the cycle's kernels on `stream`:
      * stats_host (64 doubles) <- the stats block the update wrote (stats_src_dev, default cloud->stats_dev);
      * best_host (16 bytes) <- (int64 index, double value) of the argmax, when select != 0.  Valid after
-     * obe_stream_sync(stream). */
+     * obe_stream_sync(stream).  When the blocks are device-visible (cudaHostAlloc / cudaHostRegister memory under
+     * UVA) the update and utility kernels store into them directly and no copy is enqueued at all. */
     void* stats_host;
     const double* stats_src_dev;
     void* best_host;

@@ -379,6 +379,10 @@ __device__ __forceinline__ unsigned long long* obe_peer_flags(double* buf, int k
 static thread_local const double* g_gate_on = nullptr;
 static thread_local const double* g_gate_off = nullptr;
 static thread_local double g_update_gate_thr = 0.0, g_update_gate_n = 0.0;
+// Zero-copy results of a closed-loop cycle (obe_cycle with stats_host / best_host): the update kernel's finishing block
+// and the utility kernel's last block store straight into the caller's pinned host block (device-visible under UVA).
+static thread_local double* g_update_stats_out = nullptr;
+static thread_local long long* g_utility_best_out = nullptr;
 
 struct ObeDrawArgs {
     const double* gate_off;     // optional: skip the whole launch when *gate_off != 0 (a resample fired instead)
@@ -890,6 +894,7 @@ static int64_t g_resample_fused = 1;              /* obe_set_option("resample_fu
 static int64_t g_resample_units_per_sm = 16;      /* obe_set_option("resample_units_per_sm"): work units per SM the chunk size aims at */
 static int64_t g_resample_reserve = 0;            /* obe_set_option("resample_reserve_ctas"): CTA slots an early-select resample leaves to the selection kernels */
 static int64_t g_resample_dynamic = 1;            /* obe_set_option("resample_dynamic"): units handed out by an atomic counter */
+static int64_t g_zero_copy_out = 1;               /* obe_set_option("zero_copy_out"): kernels store stats / argmax into the pinned host block themselves */
 static int64_t g_copy_out_side = 1;               /* obe_set_option("copy_out_side"): early-select cycles copy stats + argmax out on the selection stream */
 static int64_t g_resample_blocks = 0;             /* obe_set_option("resample_blocks"): CTAs per SM of the fused kernel (0: default) */
 #ifndef OBE_PLAN_CLUSTER_MIN_TILES
@@ -2563,6 +2568,7 @@ int obe_set_option(const char* name, int64_t value) {
     if (s == "resample_reserve_ctas") { g_resample_reserve = value < 0 ? 0 : value; return 0; }
     if (s == "pdl") { g_pdl = value ? 1 : 0; return 0; }
     if (s == "copy_out_side") { g_copy_out_side = value ? 1 : 0; return 0; }
+    if (s == "zero_copy_out") { g_zero_copy_out = value ? 1 : 0; return 0; }
     if (s == "resample_dynamic") { g_resample_dynamic = value ? 1 : 0; return 0; }
     if (s == "resample_units_per_sm") { g_resample_units_per_sm = value < 1 ? 1 : value; return 0; }
     return obe_fail("unknown option '%s'%s", name);
@@ -2701,6 +2707,7 @@ static void base_update_args(const obe_cloud_t* c, ObeUpdateArgs& a, const doubl
     for (int j = 0; j < OBE_MAX_CH; ++j) a.noise_idx[j] = -1;
     if (pivot) for (int j = 0; j < c->d; ++j) a.pivot[j] = pivot[j];
     a.gate_thr = g_update_gate_thr; a.gate_n = g_update_gate_n;
+    a.stats_out2 = g_update_stats_out;
 }
 static int finish_update(const obe_cloud_t*, int, cudaStream_t) {
     return 0;   // the update kernel's last block scans the tile sums itself (ObeUpdateArgs::tile_prefix)
@@ -3299,11 +3306,33 @@ int obe_stream_sync(void* stream) {
 }
 
 // the results a closed loop waits for, copied into the caller's pinned host blocks behind the cycle's kernels
-static int cycle_copy_out(const obe_cycle_t* c, const obe_cloud_t* updated, void* stream) {
+// device-side address of a pinned host block (identical under UVA; cached per block), NULL if it is not device-visible
+static void* device_view(void* host) {
+    static thread_local void* seen_host[4] = {nullptr, nullptr, nullptr, nullptr};
+    static thread_local void* seen_dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    static thread_local int next = 0;
+    if (!host || !g_zero_copy_out) return nullptr;
+    for (int i = 0; i < 4; ++i)
+        if (seen_host[i] == host) return seen_dev[i];
+    void* dev = nullptr;
+    if (cudaHostGetDevicePointer(&dev, host, 0) != cudaSuccess) { (void)cudaGetLastError(); dev = nullptr; }
+    seen_host[next] = host; seen_dev[next] = dev;
+    next = (next + 1) & 3;
+    return dev;
+}
+struct CycleZeroCopy { double* stats; long long* best; };
+static CycleZeroCopy cycle_zero_copy(const obe_cycle_t* c) {
+    CycleZeroCopy z = {nullptr, nullptr};
+    // the update's own stats block only: a sharded cycle wants the COMBINED block of the plan (stats_src_dev)
+    if (c->stats_host && !c->stats_src_dev) z.stats = (double*)device_view(c->stats_host);
+    if (c->best_host && c->select) z.best = (long long*)device_view(c->best_host);
+    return z;
+}
+static int cycle_copy_out(const obe_cycle_t* c, const obe_cloud_t* updated, void* stream, const CycleZeroCopy& z) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (c->best_host && c->select)
+    if (c->best_host && c->select && !z.best)
         OBE_CUDA(cudaMemcpyAsync(c->best_host, c->best_dev, 16, cudaMemcpyDeviceToHost, st));
-    if (c->stats_host)
+    if (c->stats_host && !z.stats)
         OBE_CUDA(cudaMemcpyAsync(c->stats_host, c->stats_src_dev ? c->stats_src_dev : updated->stats_dev,
                                  OBE_STATS_LEN * sizeof(double), cudaMemcpyDeviceToHost, st));
     return 0;
@@ -3323,11 +3352,14 @@ static int cycle_auto(const obe_cycle_t* c) {
         return obe_fail("obe_cycle: resample == 2 needs select, no constraint masks, var_noise by value, a variance/entropy "
                         "utility, 1..128 draws and the one-kernel resample%s%s");
     if (!(c->resample_threshold >= 0.0)) return obe_fail("obe_cycle: bad resample_threshold%s%s");
+    const CycleZeroCopy z = cycle_zero_copy(c);
     g_update_gate_thr = c->resample_threshold; g_update_gate_n = (double)live->n;
+    g_update_stats_out = z.stats;
     const int rc_u = obe_update(c->model, live, c->setting, c->constants, c->y_meas, c->has_sigma ? c->sigma : nullptr,
                                 c->has_noise_index ? c->noise_index : nullptr, c->n_lik_channels, c->use_choke, c->choke,
                                 c->pivot, st);
     g_update_gate_thr = 0.0; g_update_gate_n = 0.0;
+    g_update_stats_out = nullptr;
     if (rc_u) return -1;
     const double* fired = live->stats_dev + OBE_ST_FIRED;
     g_gate_on = fired;
@@ -3341,33 +3373,44 @@ static int cycle_auto(const obe_cycle_t* c) {
     rc = obe_draw(live, c->u, c->k, c->draws_dev, nullptr, st);
     g_gate_off = nullptr;
     if (rc) { obe_resample_defer(0); return -1; }
-    if (obe_utility(c->model, c->draws_dev, c->k, c->settings_dev, c->lds, c->n_settings, c->constants, c->var_noise, nullptr,
-                    c->cost_dev, c->method, c->log_form, c->kld_noise_dev, c->utility_dev, c->best_dev,
-                    c->select_scratch_dev, st)) {
+    g_utility_best_out = z.best;
+    const int rc_s = obe_utility(c->model, c->draws_dev, c->k, c->settings_dev, c->lds, c->n_settings, c->constants,
+                                 c->var_noise, nullptr, c->cost_dev, c->method, c->log_form, c->kld_noise_dev, c->utility_dev,
+                                 c->best_dev, c->select_scratch_dev, st);
+    g_utility_best_out = nullptr;
+    if (rc_s) {
         obe_resample_defer(0);
         return -1;
     }
     if (obe_resample_emit(st)) return -1;
-    return cycle_copy_out(c, live, st);
+    return cycle_copy_out(c, live, st, z);
 }
 
-static int cycle_body(const obe_cycle_t* c, bool& copied);
+static int cycle_body(const obe_cycle_t* c, bool& copied, const CycleZeroCopy& z);
 int obe_cycle(const obe_cycle_t* c) {
     if (!c || !c->cloud || !c->model) return obe_fail("obe_cycle: null argument%s%s");
     if (c->resample == 2) return cycle_auto(c);
+    const CycleZeroCopy z = cycle_zero_copy(c);
     bool copied = false;
-    if (cycle_body(c, copied)) return -1;
-    return copied ? 0 : cycle_copy_out(c, c->cloud, c->stream);
+    g_utility_best_out = z.best;                 // (every path through cycle_body runs obe_utility at most once)
+    const int rc = cycle_body(c, copied, z);
+    g_utility_best_out = nullptr;
+    g_update_stats_out = nullptr;
+    if (rc) return -1;
+    return copied ? 0 : cycle_copy_out(c, c->cloud, c->stream, z);
 }
 
-static int cycle_body(const obe_cycle_t* c, bool& copied) {
+static int cycle_body(const obe_cycle_t* c, bool& copied, const CycleZeroCopy& z) {
     void* st = c->stream;
     const obe_cloud_t* live = c->cloud;
     const int sharded = c->plan_dev != nullptr;
     if (sharded && !c->peer_bufs) return obe_fail("obe_cycle: a sharded cycle needs the peer exchange%s%s");
-    if (obe_update(c->model, live, c->setting, c->constants, c->y_meas, c->has_sigma ? c->sigma : nullptr,
-                   c->has_noise_index ? c->noise_index : nullptr, c->n_lik_channels, c->use_choke, c->choke, c->pivot, st))
-        return -1;
+    g_update_stats_out = z.stats;
+    const int rc_u = obe_update(c->model, live, c->setting, c->constants, c->y_meas, c->has_sigma ? c->sigma : nullptr,
+                                c->has_noise_index ? c->noise_index : nullptr, c->n_lik_channels, c->use_choke, c->choke,
+                                c->pivot, st);
+    g_update_stats_out = nullptr;              // (a constraint refresh further down must not overwrite the block)
+    if (rc_u) return -1;
     if (sharded &&
         obe_shard_plan_peer(c->peer_bufs, c->rank, c->world, c->epoch_stats, live->d, c->u0, c->n_total, c->a_param, 1,
                             live, c->alt, c->plan_dev, st))
@@ -3397,7 +3440,7 @@ static int cycle_body(const obe_cycle_t* c, bool& copied) {
             // the copies a closed loop waits for ride the selection stream: they are done long before the streaming
             // kernel, so nothing trails it but the join (the stats block is final since the update / shard plan)
             if (g_copy_out_side) {
-                if (cycle_copy_out(c, c->cloud, side)) return -1;
+                if (cycle_copy_out(c, c->cloud, side, z)) return -1;
                 copied = true;
             }
             if (obe_resample_emit(st)) return -1;
@@ -3473,6 +3516,7 @@ int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* set
     a.best_idx = (long long*)best_dev; a.best_val = (double*)((char*)best_dev + 8);
     a.noise_from_stats = var_noise ? 0 : 1;
     a.log_form = log_form; a.method = method; a.kld_noise = kld_noise_dev;
+    a.best_out2 = g_utility_best_out;
     if (var_noise) for (int c = 0; c < m->nch; ++c) a.var_noise[c] = var_noise[c];
     for (int j = 0; j < m->ncons; ++j) a.cons[j] = constants[j];
     size_t smem = (size_t)k * (m->np_model > 0 ? m->np_model : 1) * sizeof(double);

@@ -114,6 +114,7 @@ struct ObeUpdateArgs {
     // gate_n > 0: stats[FIRED] = (N_eff < 0.1 gate_n) || (N_eff / gate_n < gate_thr), N_eff = 1 / (sumsq * invs^2)
     double gate_thr;
     double gate_n;
+    double* stats_out2;      // optional copy of the finished stats block into device-visible PINNED HOST memory
 };
 
 struct ObeUtilityArgs {
@@ -139,6 +140,8 @@ struct ObeUtilityArgs {
     const double* kld_noise; // method 3: (K, C) noise values added to the model outputs
     double var_noise[OBE_MAX_CH];
     double cons[OBE_MAX_CONS];
+    long long* best_out2;    // optional second destination of the (index, value) pair: device-visible PINNED HOST
+                             // memory, so a closed loop needs no copy after the kernel (obe_cycle, best_host)
 };
 
 struct ObeEvalArgs {
@@ -614,7 +617,7 @@ __device__ __forceinline__ void obe_tile_scan_block(const double* __restrict__ t
                                                     double* __restrict__ prefix, double* __restrict__ stats,
                                                     int renormalise, long long uniform, long long n, int implicit,
                                                     double* sm, int bar_id, double gate_thr = 0.0,
-                                                    double gate_n = 0.0) {
+                                                    double gate_n = 0.0, double* stats_out2 = nullptr) {
     constexpr int T_ = NW * 32;
     const int t = threadIdx.x % T_;
     double carry = 0.0;
@@ -663,6 +666,12 @@ __device__ __forceinline__ void obe_tile_scan_block(const double* __restrict__ t
                 stats[OBE_ST_FIRED] = fired;
             }
         }
+    }
+    if (stats_out2 && stats) {
+        // the block is complete (every slot was written by thread 0 of this CTA, before the caller's barriers or just
+        // now): 64 threads copy it into the caller's pinned host block -- no D2H copy behind the kernel
+        obe_named_bar(bar_id, NW * 32);
+        if (t < OBE_STATS_LEN) stats_out2[t] = __ldcg(stats + t);
     }
 }
 
@@ -911,7 +920,7 @@ __device__ void obe_update_body(const ObeUpdateArgs& a) {
     obe_named_bar(1, OBE_CONSUMER_THREADS);
     __threadfence();
     obe_tile_scan_block<OBE_CONSUMER_WARPS>(a.tile_sums, n_tiles, a.tile_prefix, a.stats, a.renormalise, 0, n, 0,
-                                            &accsm[0][0], 1, a.gate_thr, a.gate_n);
+                                            &accsm[0][0], 1, a.gate_thr, a.gate_n, a.stats_out2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1566,6 +1575,7 @@ __device__ void obe_utility_body(const ObeUtilityArgs& a) {
     if (tid == 0) {
         *a.best_idx = besti;
         *a.best_val = best;
+        if (a.best_out2) { a.best_out2[0] = besti; reinterpret_cast<double*>(a.best_out2)[1] = best; }
         *a.counter = 0u;
     }
     (void)lane; (void)warp;

@@ -50,6 +50,19 @@ def main():
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print(f'{cycles / dt:.0f} cycles/s, {dt / cycles * 1e6:.1f} us per cycle (no profiler)')
+    if len(sys.argv) > 5:                     # A/B of a library option inside one process (boxes differ in host speed)
+        from optbayesexpt_b200 import _lib
+        lib = _lib.load()
+        for rep in range(3):
+            for val in (1, 0):
+                lib.obe_set_option(sys.argv[5].encode(), val)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                loop()
+                torch.cuda.synchronize()
+                print(f'  {sys.argv[5]}={val}: {(time.perf_counter() - t0) / cycles * 1e6:.1f} us per cycle')
+        lib.obe_set_option(sys.argv[5].encode(), 1)
+        return
     pr = cProfile.Profile()
     pr.enable()
     loop()
