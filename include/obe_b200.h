@@ -299,6 +299,10 @@ typedef struct obe_cycle {
     void* stats_host;
     const double* stats_src_dev;
     void* best_host;
+    /* 0: the whole cycle.  1: the update only; 2: everything after it (same struct, completed in between): a
+     * small-cloud closed loop gets its first kernel on the device before the host has drawn the uniforms and filled
+     * in the selection half. */
+    int32_t phase, pad1;
 } obe_cycle_t;
 int obe_cycle(const obe_cycle_t* c);
 /* cudaStreamSynchronize(stream): what a closed loop waits on before it reads best_host / stats_host

@@ -3346,21 +3346,26 @@ static int cycle_auto(const obe_cycle_t* c) {
     void* st = c->stream;
     const obe_cloud_t* live = c->cloud;
     if (c->plan_dev) return obe_fail("obe_cycle: the device-side resample test is for a whole (unsharded) cloud%s%s");
-    if (!c->alt) return obe_fail("obe_cycle: resample needs the second buffer%s%s");
-    if (!c->select || (c->mask_le | c->mask_lt) != 0u || c->noise_from_stats || c->method == 3 || c->k < 1 ||
-        c->k > OBE_MAX_DRAWS || !g_resample_fused)
-        return obe_fail("obe_cycle: resample == 2 needs select, no constraint masks, var_noise by value, a variance/entropy "
-                        "utility, 1..128 draws and the one-kernel resample%s%s");
+    if (c->phase != 1) {            // (phase 1 launches the update alone: the rest of the struct is filled in afterwards)
+        if (!c->alt) return obe_fail("obe_cycle: resample needs the second buffer%s%s");
+        if (!c->select || (c->mask_le | c->mask_lt) != 0u || c->noise_from_stats || c->method == 3 || c->k < 1 ||
+            c->k > OBE_MAX_DRAWS || !g_resample_fused)
+            return obe_fail("obe_cycle: resample == 2 needs select, no constraint masks, var_noise by value, a "
+                            "variance/entropy utility, 1..128 draws and the one-kernel resample%s%s");
+    }
     if (!(c->resample_threshold >= 0.0)) return obe_fail("obe_cycle: bad resample_threshold%s%s");
     const CycleZeroCopy z = cycle_zero_copy(c);
-    g_update_gate_thr = c->resample_threshold; g_update_gate_n = (double)live->n;
-    g_update_stats_out = z.stats;
-    const int rc_u = obe_update(c->model, live, c->setting, c->constants, c->y_meas, c->has_sigma ? c->sigma : nullptr,
-                                c->has_noise_index ? c->noise_index : nullptr, c->n_lik_channels, c->use_choke, c->choke,
-                                c->pivot, st);
-    g_update_gate_thr = 0.0; g_update_gate_n = 0.0;
-    g_update_stats_out = nullptr;
-    if (rc_u) return -1;
+    if (c->phase != 2) {
+        g_update_gate_thr = c->resample_threshold; g_update_gate_n = (double)live->n;
+        g_update_stats_out = z.stats;
+        const int rc_u = obe_update(c->model, live, c->setting, c->constants, c->y_meas, c->has_sigma ? c->sigma : nullptr,
+                                    c->has_noise_index ? c->noise_index : nullptr, c->n_lik_channels, c->use_choke,
+                                    c->choke, c->pivot, st);
+        g_update_gate_thr = 0.0; g_update_gate_n = 0.0;
+        g_update_stats_out = nullptr;
+        if (rc_u) return -1;
+        if (c->phase == 1) return 0;
+    }
     const double* fired = live->stats_dev + OBE_ST_FIRED;
     g_gate_on = fired;
     obe_resample_defer(1);
@@ -3405,12 +3410,15 @@ static int cycle_body(const obe_cycle_t* c, bool& copied, const CycleZeroCopy& z
     const obe_cloud_t* live = c->cloud;
     const int sharded = c->plan_dev != nullptr;
     if (sharded && !c->peer_bufs) return obe_fail("obe_cycle: a sharded cycle needs the peer exchange%s%s");
-    g_update_stats_out = z.stats;
-    const int rc_u = obe_update(c->model, live, c->setting, c->constants, c->y_meas, c->has_sigma ? c->sigma : nullptr,
-                                c->has_noise_index ? c->noise_index : nullptr, c->n_lik_channels, c->use_choke, c->choke,
-                                c->pivot, st);
-    g_update_stats_out = nullptr;              // (a constraint refresh further down must not overwrite the block)
-    if (rc_u) return -1;
+    if (c->phase != 2) {
+        g_update_stats_out = z.stats;
+        const int rc_u = obe_update(c->model, live, c->setting, c->constants, c->y_meas, c->has_sigma ? c->sigma : nullptr,
+                                    c->has_noise_index ? c->noise_index : nullptr, c->n_lik_channels, c->use_choke,
+                                    c->choke, c->pivot, st);
+        g_update_stats_out = nullptr;          // (a constraint refresh further down must not overwrite the block)
+        if (rc_u) return -1;
+        if (c->phase == 1) { copied = true; return 0; }     // (nothing to copy out yet)
+    }
     if (sharded &&
         obe_shard_plan_peer(c->peer_bufs, c->rank, c->world, c->epoch_stats, live->d, c->u0, c->n_total, c->a_param, 1,
                             live, c->alt, c->plan_dev, st))

@@ -154,6 +154,9 @@ class OptBayesExpt(ParticlePDF):
         #: N_eff (the normal case) leaves the test to the device: one C call, the outcome arrives with the argmax at
         #: the one synchronisation of the cycle (opt_setting / good_setting / just_resampled / any look at the cloud)
         self.device_resample_test = True
+        #: ... and that call is split in two: the update kernel is enqueued first, the resample / selection half of
+        #: the argument struct is filled in (and the uniforms drawn) while it runs
+        self.split_cycle = True
         self._select_ready = False
         self._side = None                 # (torch stream object, raw handle) of the selection stream
         # pinned landing block of the cycle entry: [0:64] the update's stats block, [64:66] (argmax index, value)
@@ -164,6 +167,7 @@ class OptBayesExpt(ParticlePDF):
         self._cy_copy_out = False         # the next cycle call also copies stats + argmax into the pinned block
         self._best_copied = False         # the argmax of the prepared selection is on its way to _cy_best_np
         self._async_pending = False
+        self._dt_cache = None
 
     # -- the reference rebinds `parameters` to `particles` in pdf_update (obe_base.py:185,395);
     #    here it is a live alias, which removes the stale-alias quirk after resample()/set_pdf()
@@ -381,10 +385,17 @@ class OptBayesExpt(ParticlePDF):
 
     def _adopt_stats(self, st):
         """Pivot of the next update's moment accumulators and the impoverishment warning, from a stats block."""
-        mean = self._mean_from(st)
-        if math.isfinite(mean.sum()):
-            self._pivot = mean
-        n_eff = self._n_eff_from(st)
+        # (plain floats: the same IEEE operations as _mean_from / _n_eff_from without the numpy call overhead -- this
+        # runs between the synchronisation of a cycle and the launch of the next one)
+        v = st.tolist()
+        sumt, d = v[_lib.ST_SUMT], self.n_dims
+        if sumt != 0.0:
+            mean = [v[_lib.ST_PIVOT + j] + v[_lib.ST_M1 + j] / sumt for j in range(d)]
+            if math.isfinite(sum(mean)):
+                self._pivot = np.array(mean)
+        invs, ssq = v[_lib.ST_INVS], v[_lib.ST_SUMSQ]
+        den = ssq * (invs * invs)
+        n_eff = 1.0 / den if den != 0.0 else math.inf
         if n_eff < 0.1 * self._n_total_for_test():
             import warnings
             warnings.warn("\nParticle filter rejected > 90 % of particles. "
@@ -401,9 +412,19 @@ class OptBayesExpt(ParticlePDF):
     # ---- pdf_update with the resample test on the device ------------------------------------------
     def _device_test_ok(self):
         tp = self.tuning_parameters
-        return (self.device_resample_test and self.eager_select and self.resampling == 'systematic'
-                and 0.0 <= tp['resample_threshold'] <= 1.0 and self._constraint_masks() == (0, 0)
-                and not self._noise_from_stats() and self._early_select_ok() and self._cycle_c_ok(True, True))
+        # the answer only changes with these switches: one tuple compare per update instead of seven method calls
+        key = (self.device_resample_test, self.eager_select, self.resampling, tp['resample_threshold'], self.early_select,
+               self.use_cycle_entry, self.N_DRAWS, self._utility_code, self._stream_override)
+        cached = self._dt_cache
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        ok = bool(self.device_resample_test and self.eager_select and self.resampling == 'systematic'
+                  and 0.0 <= tp['resample_threshold'] <= 1.0 and self._constraint_masks() == (0, 0)
+                  and not self._noise_from_stats() and self._early_select_ok() and self._cycle_c_ok(True, True))
+        # (a subclass with its own cost model can change its mind between calls: do not cache for it)
+        if type(self).cost_estimate is OptBayesExpt.cost_estimate:
+            self._dt_cache = (key, ok)
+        return ok
 
     def _pdf_update_device_test(self, measurement_record):
         """pdf_update + the selection of the next opt_setting() as ONE C call whose resample test
@@ -416,13 +437,22 @@ class OptBayesExpt(ParticlePDF):
         self._adopt_async_stats()
         cy = self._cycle_struct()
         self._cy_copy_out = True
-        self._fill_cycle(cy, measurement_record, True, True)
+        lib, ref = self._lib, C.byref(cy)
+        # phase 1: the update kernel goes to the device before the host has filled in the other half of the struct
+        self._fill_cycle_update(cy, measurement_record, True)
         cy.resample = 2
         cy.resample_threshold = float(self.tuning_parameters['resample_threshold'])
+        split = self.split_cycle
+        if split:
+            cy.phase = 1
+            self._check(lib.obe_cycle(ref))
+        # phase 2: gated resample half + selection, enqueued while the update runs
+        self._fill_cycle_rest(cy, True, True)
         cy.side_stream = None
         cy.u0 = float(self.rng.random())
         self._cy_u[:cy.k] = self.rng.random(cy.k)
-        self._check(self._lib.obe_cycle(C.byref(cy)))
+        cy.phase = 2 if split else 0
+        self._check(lib.obe_cycle(ref))
         self._invalidate(particles=True)
         self._stats = None
         self._last_ancestors = None
@@ -434,7 +464,7 @@ class OptBayesExpt(ParticlePDF):
     def _settle(self):
         """Wait for a pending device-decided cycle and do the host bookkeeping of its outcome."""
         if not self._pending_cycle:
-            return
+            return False
         self._pending_cycle = False
         self._check(self._lib.obe_stream_sync(self._stream()))
         st = self._cy_stats_np.copy()
@@ -446,6 +476,7 @@ class OptBayesExpt(ParticlePDF):
         if not fired:
             self._stats = st                    # the live cloud's stats block, already on the host
         self._adopt_stats(st)
+        return True
 
     def _noise_iarr(self, noise_index):
         """ctypes int array of the noise-parameter rows (cached: it never changes for an engine)."""
@@ -521,6 +552,11 @@ class OptBayesExpt(ParticlePDF):
 
     def _fill_cycle(self, cy, measurement_record, resample, select):
         """The per-cycle fields of the obe_cycle_t; consumes self.rng in the order resample() / opt_setting() do."""
+        self._fill_cycle_update(cy, measurement_record, resample)
+        self._fill_cycle_rest(cy, resample, select)
+
+    def _fill_cycle_update(self, cy, measurement_record, resample):
+        """What the update kernel needs: the record, the pivot, the live cloud, the stream, the copy-out block."""
         y_meas, sigma, noise_index, n_lik = self._likelihood_spec(measurement_record)
         cy.model = self._model
         st = np.atleast_1d(measurement_record[0])
@@ -541,9 +577,21 @@ class OptBayesExpt(ParticlePDF):
         cy.use_choke = 0 if choke is None else 1
         cy.choke = 0.0 if choke is None else float(choke)
         self._cy_pivot[:self.n_dims] = self._pivot
-        buf = self._buf
-        cy.cloud = buf.ptr()
+        cy.cloud = self._buf.ptr()
         cy.resample = 1 if resample else 0
+        cy.stream = self._stream().value
+        if self._cy_copy_out:
+            self._cy_copy_out = False
+            base = self._cy_pin.data_ptr()
+            cy.stats_host, cy.best_host = base, base + 8 * _lib.STATS_LEN
+            cy.stats_src_dev = self._async_stats_ptr(resample)
+        else:
+            cy.stats_host = cy.best_host = cy.stats_src_dev = None
+        cy.phase = 0
+
+    def _fill_cycle_rest(self, cy, resample, select):
+        """The resample and selection halves of the struct."""
+        buf = self._buf
         if resample:
             alt = self._alt
             if alt is None:
@@ -565,25 +613,23 @@ class OptBayesExpt(ParticlePDF):
             if not cy.noise_from_stats:
                 vn = np.asarray(self.yvar_noise_model(), dtype=np.float64).reshape(-1)
                 self._cy_vn[:min(len(vn), _lib.MAX_CHANNELS)] = vn[:_lib.MAX_CHANNELS]
-        cy.stream = self._stream().value
         cy.side_stream = self._side_stream()[1].value if (self.early_select and resample and select) else None
-        if self._cy_copy_out:
-            self._cy_copy_out = False
-            base = self._cy_pin.data_ptr()
-            cy.stats_host, cy.best_host = base, base + 8 * _lib.STATS_LEN
-            cy.stats_src_dev = self._async_stats_ptr(resample)
-        else:
-            cy.stats_host = cy.best_host = cy.stats_src_dev = None
 
     def _run_cycle_c(self, measurement_record, resample, select):
         if self._pending_cycle:
             self._settle()
         cy = self._cycle_struct()
-        self._fill_cycle(cy, measurement_record, resample, select)
+        split = self.split_cycle and (resample or select)
+        self._fill_cycle_update(cy, measurement_record, resample)
+        if split:                               # the update kernel first, the rest of the struct while it runs
+            cy.phase = 1
+            self._check(self._lib.obe_cycle(C.byref(cy)))
+        self._fill_cycle_rest(cy, resample, select)
         if resample:
             cy.u0 = float(self.rng.random())
         if select:
             self._cy_u[:cy.k] = self.rng.random(cy.k)
+        cy.phase = 2 if split else 0
         self._check(self._lib.obe_cycle(C.byref(cy)))
         self._after_cycle_c(resample)
 
@@ -856,15 +902,16 @@ class OptBayesExpt(ParticlePDF):
 
     def opt_setting(self):
         """Setting with the maximum utility (obe_base.py:733-756)."""
-        self._settle()
+        synced = self._settle()
         if self._select_ready:
             self._select_ready = False          # started by the resample (eager_select): only the argmax is fetched
         else:
             self._utility_dev_run()
             self._best_copied = False
-        if self._best_copied:                   # the cycle entry already copied it into the pinned block
+        if self._best_copied:                   # the cycle entry already put it into the pinned block
             self._best_copied = False
-            self._check(self._lib.obe_stream_sync(self._stream()))
+            if not synced:
+                self._check(self._lib.obe_stream_sync(self._stream()))
             bestindex = int(self._cy_best_np[0])
         else:
             self._best_host.copy_(self._best_dev, non_blocking=True)

@@ -710,7 +710,12 @@ class ShardedOptBayesExpt(OptBayesExpt):
         if not resample:
             return OptBayesExpt._run_cycle_c(self, measurement_record, resample, select)
         cy = self._cycle_struct()
-        self._fill_cycle(cy, measurement_record, resample, select)
+        self._fill_cycle_update(cy, measurement_record, resample)
+        if self.split_cycle:                                # the update kernel first, the rest of the struct while it runs
+            cy.phase = 1
+            self._check(self._lib.obe_cycle(C.byref(cy)))
+            cy.phase = 2
+        self._fill_cycle_rest(cy, resample, select)
         self._u0 = float(self.rng.random())                 # identical on every rank
         cy.u0 = self._u0
         cy.plan_dev = self._plan.data_ptr()

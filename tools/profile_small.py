@@ -55,13 +55,15 @@ def main():
         lib = _lib.load()
         for rep in range(3):
             for val in (1, 0):
-                lib.obe_set_option(sys.argv[5].encode(), val)
+                if sys.argv[5] == 'split_cycle':
+                    eng.split_cycle = bool(val)
+                else:
+                    lib.obe_set_option(sys.argv[5].encode(), val)
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 loop()
                 torch.cuda.synchronize()
                 print(f'  {sys.argv[5]}={val}: {(time.perf_counter() - t0) / cycles * 1e6:.1f} us per cycle')
-        lib.obe_set_option(sys.argv[5].encode(), 1)
         return
     pr = cProfile.Profile()
     pr.enable()
