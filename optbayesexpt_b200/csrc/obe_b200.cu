@@ -3436,8 +3436,11 @@ static int cycle_body(const obe_cycle_t* c, bool& copied, const CycleZeroCopy& z
                                                          c->a_param, c->scale, nullptr, nullptr, st);
         if (rc) { obe_resample_defer(0); return -1; }
         if (early) {
+            // side_stream == stream: the early order (plan, pick, utility, then the streaming kernel) on ONE stream --
+            // for small clouds the fork / join events cost more than the overlap hides
             void* side = c->side_stream;
-            if (obe_stream_fork(st, side)) return -1;
+            const bool two_streams = side != st;
+            if (two_streams && obe_stream_fork(st, side)) return -1;
             if (obe_resample_pick(c->u, c->k, c->draws_dev, sharded ? c->peer_bufs : nullptr, c->rank, c->world,
                                   c->epoch_draws, side))
                 return -1;
@@ -3452,7 +3455,7 @@ static int cycle_body(const obe_cycle_t* c, bool& copied, const CycleZeroCopy& z
                 copied = true;
             }
             if (obe_resample_emit(st)) return -1;
-            return obe_stream_join(st, side);
+            return two_streams ? obe_stream_join(st, side) : 0;
         }
         live = c->alt;
         if (masks) {

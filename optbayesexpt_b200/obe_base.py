@@ -157,6 +157,10 @@ class OptBayesExpt(ParticlePDF):
         #: ... and that call is split in two: the update kernel is enqueued first, the resample / selection half of
         #: the argument struct is filled in (and the uniforms drawn) while it runs
         self.split_cycle = True
+        #: early select runs the selection on a second stream beside the streaming resample from this many particles on;
+        #: below, the same early order goes to the main stream.  Measured: two streams win even at 1e4 particles (65 vs
+        #: 72 us per forced c1 cycle, 115 vs 124 us at c3), so the default is 0
+        self.two_stream_min_particles = 0
         self._select_ready = False
         self._side = None                 # (torch stream object, raw handle) of the selection stream
         # pinned landing block of the cycle entry: [0:64] the update's stats block, [64:66] (argmax index, value)
@@ -613,7 +617,12 @@ class OptBayesExpt(ParticlePDF):
             if not cy.noise_from_stats:
                 vn = np.asarray(self.yvar_noise_model(), dtype=np.float64).reshape(-1)
                 self._cy_vn[:min(len(vn), _lib.MAX_CHANNELS)] = vn[:_lib.MAX_CHANNELS]
-        cy.side_stream = self._side_stream()[1].value if (self.early_select and resample and select) else None
+        if self.early_select and resample and select:
+            # (small clouds: same early order on the main stream -- the fork / join cost more than the overlap hides)
+            cy.side_stream = (self._side_stream()[1].value if self._n_total_for_test() >= self.two_stream_min_particles
+                              else cy.stream)
+        else:
+            cy.side_stream = None
 
     def _run_cycle_c(self, measurement_record, resample, select):
         if self._pending_cycle:

@@ -55,8 +55,10 @@ def main():
         lib = _lib.load()
         for rep in range(3):
             for val in (1, 0):
-                if sys.argv[5] == 'split_cycle':
-                    eng.split_cycle = bool(val)
+                if sys.argv[5] in ('split_cycle', 'early_select'):
+                    setattr(eng, sys.argv[5], bool(val))
+                elif sys.argv[5] == 'one_stream':
+                    eng.two_stream_min_particles = 10 ** 12 if val else 0
                 else:
                     lib.obe_set_option(sys.argv[5].encode(), val)
                 torch.cuda.synchronize()
