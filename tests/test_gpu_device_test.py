@@ -152,3 +152,43 @@ def test_closed_loop_converges_with_the_device_test(obe):
     assert abs(m[0] - 3.14) < 5 * s[0] + 1e-3 and s[0] < 0.02
     assert abs(m[1] + 1200.0) < 5 * s[1] and abs(m[2] - 50400.0) < 5 * s[2]
     assert abs(e.particle_weights.sum() - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize('variant', ['copy_engine', 'single_call', 'one_stream'])
+@pytest.mark.parametrize('thr', [0.5, 2.0], ids=['natural', 'forced'])
+def test_result_delivery_variants_agree(obe, variant, thr):
+    """The kernels store stats + argmax into the pinned host block themselves and the cycle call is split in two phases
+    (defaults); asynchronous D2H copies, one whole call and the early order on one stream must give the same trajectory."""
+    from optbayesexpt_b200 import _lib
+    lib = _lib.load()
+    n, cycles = 30_000, 25
+    a, b = _engine(obe, n, thr=thr), _engine(obe, n, thr=thr)
+    for e in (a, b):
+        e.eager_select = e.async_update = True
+        e.rng = ScriptedRng(5, cycles, 30)
+    if variant == 'single_call':
+        b.split_cycle = False
+    elif variant == 'one_stream':
+        b.two_stream_min_particles = 10 ** 12
+    meas = np.random.default_rng(9)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', RuntimeWarning)
+            xa, xb = a.opt_setting(), b.opt_setting()
+            for t in range(cycles):
+                a.rng.t = b.rng.t = t + 1
+                assert xa == xb, f'cycle {t}'
+                y = _measure(xa, meas)
+                a.pdf_update((xa, y, 500.0))
+                if variant == 'copy_engine':
+                    lib.obe_set_option(b'zero_copy_out', 0)
+                b.pdf_update((xb, y, 500.0))
+                lib.obe_set_option(b'zero_copy_out', 1)
+                xa, xb = a.opt_setting(), b.opt_setting()
+                assert a.just_resampled == b.just_resampled
+                assert a.last_setting_index == b.last_setting_index
+    finally:
+        lib.obe_set_option(b'zero_copy_out', 1)
+    np.testing.assert_array_equal(a.particles, b.particles)
+    np.testing.assert_array_equal(a.particle_weights, b.particle_weights)
+    np.testing.assert_array_equal(a.mean(), b.mean())
