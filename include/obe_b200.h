@@ -303,6 +303,13 @@ typedef struct obe_cycle {
      * small-cloud closed loop gets its first kernel on the device before the host has drawn the uniforms and filled
      * in the selection half. */
     int32_t phase, pad1;
+    /* optional completion word (8 bytes of the same kind of pinned host memory as best_host; needs select != 0 and
+     * device-visible blocks): the utility kernel stores `seq` there after the argmax pair has landed, so a closed loop
+     * can POLL it instead of synchronising the stream -- the selection of an early-select cycle is on the host while
+     * the streaming resample is still running, and the next measurement / pdf_update overlap it.  stats_host is
+     * complete when the word appears (the update kernel wrote it, or its copy was enqueued ahead of the selection). */
+    uint64_t seq;
+    void* seq_host;
 } obe_cycle_t;
 int obe_cycle(const obe_cycle_t* c);
 /* cudaStreamSynchronize(stream): what a closed loop waits on before it reads best_host / stats_host

@@ -71,7 +71,8 @@ class Cycle(C.Structure):
                 ('best_dev', C.c_void_p), ('select_scratch_dev', C.c_void_p),
                 ('stream', C.c_void_p), ('side_stream', C.c_void_p),
                 ('resample_threshold', C.c_double), ('stats_host', C.c_void_p), ('stats_src_dev', C.c_void_p),
-                ('best_host', C.c_void_p), ('phase', C.c_int32), ('pad1', C.c_int32)]
+                ('best_host', C.c_void_p), ('phase', C.c_int32), ('pad1', C.c_int32),
+                ('seq', C.c_uint64), ('seq_host', C.c_void_p)]
 
 
 _PD = C.POINTER(C.c_double)

@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -118,10 +119,15 @@ static size_t update_smem_bytes(int d, int src) {
 }
 // cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel, device) and calling thread instead of before every
 // launch: a small-cloud cycle is a chain of 5-10 us kernels and the host has to stay ahead of it.
+// (Unloading a user model may hand its kernel addresses to the next one: g_smem_epoch drops every thread's cache.)
+static std::atomic<int> g_smem_epoch{0};
 static cudaError_t set_max_smem(const void* f, size_t smem) {
     struct Ent { const void* f; size_t smem; int dev; };
     static thread_local Ent cache[96];
     static thread_local int n_cached = 0;
+    static thread_local int seen_epoch = 0;
+    const int epoch = g_smem_epoch.load(std::memory_order_relaxed);
+    if (seen_epoch != epoch) { seen_epoch = epoch; n_cached = 0; }
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = -1; }
     for (int i = 0; i < n_cached; ++i)
@@ -383,6 +389,8 @@ static thread_local double g_update_gate_thr = 0.0, g_update_gate_n = 0.0;
 // and the utility kernel's last block store straight into the caller's pinned host block (device-visible under UVA).
 static thread_local double* g_update_stats_out = nullptr;
 static thread_local long long* g_utility_best_out = nullptr;
+static thread_local unsigned long long* g_utility_seq_out = nullptr;
+static thread_local unsigned long long g_utility_seq_val = 0;
 
 struct ObeDrawArgs {
     const double* gate_off;     // optional: skip the whole launch when *gate_off != 0 (a resample fired instead)
@@ -2674,7 +2682,10 @@ int obe_model_info(obe_model_t m, int* ns, int* npm, int* nc, int* nch, int* np)
 }
 void obe_model_free(obe_model_t m) {
     if (!m) return;
-    if (m->user && m->lib) cudaLibraryUnload(m->lib);
+    if (m->user && m->lib) {
+        cudaLibraryUnload(m->lib);
+        g_smem_epoch.fetch_add(1, std::memory_order_relaxed);
+    }
     delete m;
 }
 
@@ -3320,19 +3331,21 @@ static void* device_view(void* host) {
     next = (next + 1) & 3;
     return dev;
 }
-struct CycleZeroCopy { double* stats; long long* best; };
+struct CycleZeroCopy { double* stats; long long* best; unsigned long long* seq; };
 static CycleZeroCopy cycle_zero_copy(const obe_cycle_t* c) {
-    CycleZeroCopy z = {nullptr, nullptr};
+    CycleZeroCopy z = {nullptr, nullptr, nullptr};
     // the update's own stats block only: a sharded cycle wants the COMBINED block of the plan (stats_src_dev)
     if (c->stats_host && !c->stats_src_dev) z.stats = (double*)device_view(c->stats_host);
     if (c->best_host && c->select) z.best = (long long*)device_view(c->best_host);
+    if (z.best && c->seq_host) z.seq = (unsigned long long*)device_view(c->seq_host);
     return z;
 }
-static int cycle_copy_out(const obe_cycle_t* c, const obe_cloud_t* updated, void* stream, const CycleZeroCopy& z) {
+static int cycle_copy_out(const obe_cycle_t* c, const obe_cloud_t* updated, void* stream, const CycleZeroCopy& z,
+                          int what = 3) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (c->best_host && c->select && !z.best)
+    if ((what & 1) && c->best_host && c->select && !z.best)
         OBE_CUDA(cudaMemcpyAsync(c->best_host, c->best_dev, 16, cudaMemcpyDeviceToHost, st));
-    if (c->stats_host && !z.stats)
+    if ((what & 2) && c->stats_host && !z.stats)
         OBE_CUDA(cudaMemcpyAsync(c->stats_host, c->stats_src_dev ? c->stats_src_dev : updated->stats_dev,
                                  OBE_STATS_LEN * sizeof(double), cudaMemcpyDeviceToHost, st));
     return 0;
@@ -3378,11 +3391,11 @@ static int cycle_auto(const obe_cycle_t* c) {
     rc = obe_draw(live, c->u, c->k, c->draws_dev, nullptr, st);
     g_gate_off = nullptr;
     if (rc) { obe_resample_defer(0); return -1; }
-    g_utility_best_out = z.best;
+    g_utility_best_out = z.best; g_utility_seq_out = z.seq; g_utility_seq_val = c->seq;
     const int rc_s = obe_utility(c->model, c->draws_dev, c->k, c->settings_dev, c->lds, c->n_settings, c->constants,
                                  c->var_noise, nullptr, c->cost_dev, c->method, c->log_form, c->kld_noise_dev, c->utility_dev,
                                  c->best_dev, c->select_scratch_dev, st);
-    g_utility_best_out = nullptr;
+    g_utility_best_out = nullptr; g_utility_seq_out = nullptr;
     if (rc_s) {
         obe_resample_defer(0);
         return -1;
@@ -3398,8 +3411,9 @@ int obe_cycle(const obe_cycle_t* c) {
     const CycleZeroCopy z = cycle_zero_copy(c);
     bool copied = false;
     g_utility_best_out = z.best;                 // (every path through cycle_body runs obe_utility at most once)
+    g_utility_seq_out = z.seq; g_utility_seq_val = c->seq;
     const int rc = cycle_body(c, copied, z);
-    g_utility_best_out = nullptr;
+    g_utility_best_out = nullptr; g_utility_seq_out = nullptr;
     g_update_stats_out = nullptr;
     if (rc) return -1;
     return copied ? 0 : cycle_copy_out(c, c->cloud, c->stream, z);
@@ -3441,6 +3455,9 @@ static int cycle_body(const obe_cycle_t* c, bool& copied, const CycleZeroCopy& z
             void* side = c->side_stream;
             const bool two_streams = side != st;
             if (two_streams && obe_stream_fork(st, side)) return -1;
+            // a stats block that has to be COPIED (sharded: the combined block of the plan) goes first on the selection
+            // stream, so that it has landed when the utility kernel raises the completion word
+            if (g_copy_out_side && cycle_copy_out(c, c->cloud, side, z, 2)) return -1;
             if (obe_resample_pick(c->u, c->k, c->draws_dev, sharded ? c->peer_bufs : nullptr, c->rank, c->world,
                                   c->epoch_draws, side))
                 return -1;
@@ -3451,7 +3468,7 @@ static int cycle_body(const obe_cycle_t* c, bool& copied, const CycleZeroCopy& z
             // the copies a closed loop waits for ride the selection stream: they are done long before the streaming
             // kernel, so nothing trails it but the join (the stats block is final since the update / shard plan)
             if (g_copy_out_side) {
-                if (cycle_copy_out(c, c->cloud, side, z)) return -1;
+                if (cycle_copy_out(c, c->cloud, side, z, 1)) return -1;
                 copied = true;
             }
             if (obe_resample_emit(st)) return -1;
@@ -3528,6 +3545,7 @@ int obe_utility(obe_model_t m, const double* draws_dev, int k, const double* set
     a.noise_from_stats = var_noise ? 0 : 1;
     a.log_form = log_form; a.method = method; a.kld_noise = kld_noise_dev;
     a.best_out2 = g_utility_best_out;
+    a.seq_out2 = g_utility_best_out ? g_utility_seq_out : nullptr; a.seq_val = g_utility_seq_val;
     if (var_noise) for (int c = 0; c < m->nch; ++c) a.var_noise[c] = var_noise[c];
     for (int j = 0; j < m->ncons; ++j) a.cons[j] = constants[j];
     size_t smem = (size_t)k * (m->np_model > 0 ? m->np_model : 1) * sizeof(double);

@@ -142,6 +142,8 @@ struct ObeUtilityArgs {
     double cons[OBE_MAX_CONS];
     long long* best_out2;    // optional second destination of the (index, value) pair: device-visible PINNED HOST
                              // memory, so a closed loop needs no copy after the kernel (obe_cycle, best_host)
+    unsigned long long* seq_out2;   // optional: after best_out2 is written (system-scope fence), seq_val is stored here --
+    unsigned long long seq_val;     // the host polls this word instead of synchronising the stream (obe_cycle, seq_host)
 };
 
 struct ObeEvalArgs {
@@ -1575,7 +1577,14 @@ __device__ void obe_utility_body(const ObeUtilityArgs& a) {
     if (tid == 0) {
         *a.best_idx = besti;
         *a.best_val = best;
-        if (a.best_out2) { a.best_out2[0] = besti; reinterpret_cast<double*>(a.best_out2)[1] = best; }
+        if (a.best_out2) {
+            a.best_out2[0] = besti;
+            reinterpret_cast<double*>(a.best_out2)[1] = best;
+            if (a.seq_out2) {
+                __threadfence_system();                    // the pair (and the stats block of the update kernel before
+                *reinterpret_cast<volatile unsigned long long*>(a.seq_out2) = a.seq_val;   // it) land before the flag
+            }
+        }
         *a.counter = 0u;
     }
     (void)lane; (void)warp;

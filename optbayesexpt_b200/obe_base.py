@@ -164,10 +164,20 @@ class OptBayesExpt(ParticlePDF):
         self._select_ready = False
         self._side = None                 # (torch stream object, raw handle) of the selection stream
         # pinned landing block of the cycle entry: [0:64] the update's stats block, [64:66] (argmax index, value)
-        self._cy_pin = torch.zeros(_lib.STATS_LEN + 2, dtype=torch.float64).pin_memory()
+        # and [66] the completion word the utility kernel raises once the pair has landed
+        self._cy_pin = torch.zeros(_lib.STATS_LEN + 4, dtype=torch.float64).pin_memory()
         self._cy_pin_np = self._cy_pin.numpy()
         self._cy_stats_np = self._cy_pin_np[:_lib.STATS_LEN]
-        self._cy_best_np = self._cy_pin_np[_lib.STATS_LEN:].view(np.int64)
+        self._cy_best_np = self._cy_pin_np[_lib.STATS_LEN:_lib.STATS_LEN + 2].view(np.int64)
+        self._cy_seq_np = self._cy_pin_np[_lib.STATS_LEN + 2:_lib.STATS_LEN + 3].view(np.uint64)
+        self._cy_seq = 0                  # number of the last cycle that was asked to deliver its results
+        self._cy_seq_seen = 0             # ... and of the last one whose results were seen on the host
+        #: wait for a cycle's results by polling the completion word instead of synchronising the stream: the
+        #: selection of an early-select cycle reaches the host while the streaming resample is still running, so the
+        #: next measurement and pdf_update overlap it (falls back to a stream synchronisation after `poll_spins` looks)
+        self.poll_results = True
+        self.poll_spins = 40000
+        self._cy_polls = False            # the last delivering cycle ran a selection (which raises the word)
         self._cy_copy_out = False         # the next cycle call also copies stats + argmax into the pinned block
         self._best_copied = False         # the argmax of the prepared selection is on its way to _cy_best_np
         self._async_pending = False
@@ -379,13 +389,30 @@ class OptBayesExpt(ParticlePDF):
         pending, self._async_pending = self._async_pending, False
         if not pending:
             return
-        if pending == 'cycle':                  # copied by obe_cycle itself behind its kernels
-            self._check(self._lib.obe_stream_sync(self._stream()))   # (a no-op wait in a closed loop)
+        if pending == 'cycle':                  # delivered by obe_cycle itself
+            self._wait_cycle()                  # (already seen in a closed loop: opt_setting waited for this cycle)
             st = self._cy_stats_np.copy()
         else:
             self._async_ev.synchronize()        # (already complete in a closed loop: opt_setting synchronised since)
             st = self._async_pin_np.copy()
         self._adopt_stats(st)
+
+    def _wait_cycle(self):
+        """Block until the results of the last delivering cycle (stats block, argmax pair) are on the host: poll the
+        completion word the utility kernel raises, or synchronise the stream."""
+        seq = self._cy_seq
+        if self._cy_seq_seen == seq:
+            return
+        # (no completion word without a selection; kernels on an override stream are not ordered with torch's copies,
+        # so the host must not run ahead of them)
+        if self.poll_results and self._cy_polls and self._stream_override is None:
+            flag = self._cy_seq_np
+            for _ in range(self.poll_spins):
+                if flag[0] == seq:
+                    self._cy_seq_seen = seq
+                    return
+        self._check(self._lib.obe_stream_sync(self._stream()))
+        self._cy_seq_seen = seq
 
     def _adopt_stats(self, st):
         """Pivot of the next update's moment accumulators and the impoverishment warning, from a stats block."""
@@ -470,7 +497,7 @@ class OptBayesExpt(ParticlePDF):
         if not self._pending_cycle:
             return False
         self._pending_cycle = False
-        self._check(self._lib.obe_stream_sync(self._stream()))
+        self._wait_cycle()
         st = self._cy_stats_np.copy()
         fired = bool(st[_lib.ST_FIRED] != 0.0)
         ready, copied = self._select_ready, self._best_copied
@@ -589,8 +616,11 @@ class OptBayesExpt(ParticlePDF):
             base = self._cy_pin.data_ptr()
             cy.stats_host, cy.best_host = base, base + 8 * _lib.STATS_LEN
             cy.stats_src_dev = self._async_stats_ptr(resample)
+            self._cy_seq += 1
+            self._cy_polls = False        # (set by _fill_cycle_rest when the cycle selects)
+            cy.seq, cy.seq_host = self._cy_seq, base + 8 * (_lib.STATS_LEN + 2)
         else:
-            cy.stats_host = cy.best_host = cy.stats_src_dev = None
+            cy.stats_host = cy.best_host = cy.stats_src_dev = cy.seq_host = None
         cy.phase = 0
 
     def _fill_cycle_rest(self, cy, resample, select):
@@ -608,6 +638,8 @@ class OptBayesExpt(ParticlePDF):
             cy.epoch = self._epoch + 1
             cy.mask_le, cy.mask_lt = self._constraint_masks()
         cy.select = 1 if select else 0
+        if select and cy.seq_host:
+            self._cy_polls = True
         cy.noise_from_stats = 1 if self._noise_from_stats() else 0
         if select:
             cy.k = int(self.N_DRAWS)
@@ -920,7 +952,7 @@ class OptBayesExpt(ParticlePDF):
         if self._best_copied:                   # the cycle entry already put it into the pinned block
             self._best_copied = False
             if not synced:
-                self._check(self._lib.obe_stream_sync(self._stream()))
+                self._wait_cycle()
             bestindex = int(self._cy_best_np[0])
         else:
             self._best_host.copy_(self._best_dev, non_blocking=True)

@@ -598,9 +598,9 @@ class ShardedOptBayesExpt(OptBayesExpt):
             self._utility_dev_run()
             self._best_copied = False
         if self._replicate_grid:
-            if self._best_copied:               # the cycle entry copied the argmax into the pinned block already
+            if self._best_copied:               # the cycle entry delivers the argmax into the pinned block
                 self._best_copied = False
-                self._check(self._lib.obe_stream_sync(self._stream()))
+                self._wait_cycle()
                 best = int(self._cy_best_np[0])
             else:
                 self._best_host.copy_(self._best_dev, non_blocking=True)

@@ -154,7 +154,7 @@ def test_closed_loop_converges_with_the_device_test(obe):
     assert abs(e.particle_weights.sum() - 1.0) < 1e-12
 
 
-@pytest.mark.parametrize('variant', ['copy_engine', 'single_call', 'one_stream'])
+@pytest.mark.parametrize('variant', ['copy_engine', 'single_call', 'one_stream', 'stream_sync'])
 @pytest.mark.parametrize('thr', [0.5, 2.0], ids=['natural', 'forced'])
 def test_result_delivery_variants_agree(obe, variant, thr):
     """The kernels store stats + argmax into the pinned host block themselves and the cycle call is split in two phases
@@ -166,10 +166,14 @@ def test_result_delivery_variants_agree(obe, variant, thr):
     for e in (a, b):
         e.eager_select = e.async_update = True
         e.rng = ScriptedRng(5, cycles, 30)
-    if variant == 'single_call':
+    if variant == 'copy_engine':
+        b.poll_results = False                  # (no completion word without the kernels' own stores)
+    elif variant == 'single_call':
         b.split_cycle = False
     elif variant == 'one_stream':
         b.two_stream_min_particles = 10 ** 12
+    elif variant == 'stream_sync':
+        b.poll_results = False
     meas = np.random.default_rng(9)
     try:
         with warnings.catch_warnings():
