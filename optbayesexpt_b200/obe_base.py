@@ -172,9 +172,10 @@ class OptBayesExpt(ParticlePDF):
         self._cy_seq_np = self._cy_pin_np[_lib.STATS_LEN + 2:_lib.STATS_LEN + 3].view(np.uint64)
         self._cy_seq = 0                  # number of the last cycle that was asked to deliver its results
         self._cy_seq_seen = 0             # ... and of the last one whose results were seen on the host
-        #: wait for a cycle's results by polling the completion word instead of synchronising the stream: the
-        #: selection of an early-select cycle reaches the host while the streaming resample is still running, so the
-        #: next measurement and pdf_update overlap it (falls back to a stream synchronisation after `poll_spins` looks)
+        #: wait for a cycle's results by polling the completion word instead of synchronising the stream: trailing
+        #: gated-off launches and the stream-synchronisation wake-up leave the critical path (3 us per small-cloud
+        #: cycle); falls back to a stream synchronisation after `poll_spins` looks (~4 ms).  Kernels still in flight
+        #: behind the word (the streaming resample of a resampling cycle) are ordered before everything enqueued later
         self.poll_results = True
         self.poll_spins = 40000
         self._cy_polls = False            # the last delivering cycle ran a selection (which raises the word)
