@@ -305,9 +305,9 @@ typedef struct obe_cycle {
     int32_t phase, pad1;
     /* optional completion word (8 bytes of the same kind of pinned host memory as best_host; needs select != 0 and
      * device-visible blocks): the utility kernel stores `seq` there after the argmax pair has landed, so a closed loop
-     * can POLL it instead of synchronising the stream -- the selection of an early-select cycle is on the host while
-     * the streaming resample is still running, and the next measurement / pdf_update overlap it.  stats_host is
-     * complete when the word appears (the update kernel wrote it, or its copy was enqueued ahead of the selection). */
+     * can POLL it instead of synchronising the stream (kernels enqueued behind the utility pass -- gated-off launches,
+     * the streaming kernel of a resampling cycle -- no longer delay the host).  stats_host is complete when the word
+     * appears (the update kernel wrote it, or its copy was enqueued ahead of the selection). */
     uint64_t seq;
     void* seq_host;
 } obe_cycle_t;
