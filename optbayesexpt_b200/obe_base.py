@@ -639,8 +639,6 @@ class OptBayesExpt(ParticlePDF):
             cy.epoch = self._epoch + 1
             cy.mask_le, cy.mask_lt = self._constraint_masks()
         cy.select = 1 if select else 0
-        if select and cy.seq_host:
-            self._cy_polls = True
         cy.noise_from_stats = 1 if self._noise_from_stats() else 0
         if select:
             cy.k = int(self.N_DRAWS)
@@ -656,6 +654,11 @@ class OptBayesExpt(ParticlePDF):
                               else cy.stream)
         else:
             cy.side_stream = None
+        # The completion word is raised by the utility kernel.  A stats block the kernels store themselves is on the
+        # host before it; one that is COPIED (stats_src_dev: the combined block of a sharded cloud) is only ahead of
+        # the word in the early order, where the copy is enqueued before the selection -- otherwise wait on the stream.
+        if select and cy.seq_host:
+            self._cy_polls = bool(cy.stats_src_dev is None or cy.side_stream)
 
     def _run_cycle_c(self, measurement_record, resample, select):
         if self._pending_cycle:
