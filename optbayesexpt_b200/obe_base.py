@@ -484,7 +484,14 @@ class OptBayesExpt(ParticlePDF):
         cy.u0 = float(self.rng.random())
         self._cy_u[:cy.k] = self.rng.random(cy.k)
         cy.phase = 2 if split else 0
-        self._check(lib.obe_cycle(ref))
+        try:
+            self._check(lib.obe_cycle(ref))
+        except Exception:
+            if split:                           # the update of phase 1 is already on the device: account for it
+                self._invalidate(particles=True)
+                self._stats = None
+                self._moments_valid, self._weights_lazy = True, True
+            raise
         self._invalidate(particles=True)
         self._stats = None
         self._last_ancestors = None
